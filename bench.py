@@ -1,0 +1,379 @@
+#!/usr/bin/env python
+"""bench.py -- learner transitions/sec of the B200-native DQN learner hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload per256|...]
+
+Contract (see DESIGN.md "Measurement"): one JSON line on stdout (rank 0).
+  metric   learner transitions/sec = B x learner-steps/s; a learner step = sample + TD target +
+           forward/backward + Adam + the per-step Polyak target sync (BASELINE.json).
+  workload (N = 1) BASELINE.json configs[1]: PER + double + dueling, B = 256, 1M-transition replay
+           resident in HBM (128 MB ring + 16 MB float64 sum tree).  N > 1: one independent agent per
+           GPU (ensemble members, no collective) -> weak scaling.
+  value    device-timed (CUDA events), inputs resident in HBM.
+  e2e      the same through the drop-in Agent API with HOST buffers: every step pushes one new
+           transition from host memory (pinned staging -> H2D), runs learn()+update_target_network()
+           and reads the loss back (D2H), all inside the timed region.
+  roofline dominant kernel k_learner_step: algorithmic HBM bytes per launch / mean launch duration.
+  cpu_baseline / --impl reference: the oracle port of the reference's CPU learner (torch CPU + numpy
+           + python loops, oracle/dqn_oracle.py) on this box's host cores, bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+D, A, H1, H2 = 14, 8, 256, 128
+CAP = 1_000_000
+P_COUNT = D * H1 + H1 + H1 * H2 + H2 + H2 * (A + 1) + (A + 1)
+W_FWD = D * H1 + H1 * H2 + H2 * (A + 1)
+W_DGRAD = H1 * H2 + H2 * (A + 1)
+FLOP_PER_TRANSITION = 2 * (4 * W_FWD + W_DGRAD)            # 367,872
+TREE_LEVELS = 21
+BYTES_PER_TRANSITION_PER = 4 * (2 * D + 3) + 8 * TREE_LEVELS + 16 * TREE_LEVELS   # 628
+BYTES_PER_TRANSITION_UNI = 4 * (2 * D + 3)                                          # 124
+METRIC = "learner transitions/sec (sample+TD+fwd/bwd+Adam) at 1/2/4/8 B200 vs host CPU"
+
+WORKLOADS = {
+    "per256": dict(algo="PerDuelingDoubleDQNAgent", B=256, cap=CAP, size=CAP,
+                   name="PER+double+dueling DQN learner, batch 256, 1M-transition GPU-resident replay (BASELINE configs[1])"),
+    "default32": dict(algo="DuelingDoubleDQNAgent", B=32, cap=CAP, size=100_000,
+                      name="DuelingDouble DQN learner, repo defaults: batch 32, uniform replay cap 1M filled to 100k (configs[0])"),
+}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            d = json.load(fh)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.1)
+
+    def summary(self):
+        self.stop_flag.set()
+        self.join(timeout=6)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(s) > 2 + k and s[2 + k].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.samples[0][1]) if self.samples[0][1].replace(".", "").isdigit() else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def synthetic(n, seed):
+    from oracle.dqn_oracle import synthetic_transitions
+    return synthetic_transitions(n, D, seed)
+
+
+def seeded_priorities(n, seed):
+    rng = np.random.default_rng(seed)
+    return np.power(np.minimum(np.abs(rng.normal(size=n)).astype(np.float32) + np.float32(1e-4), np.float32(1.0)),
+                    np.float32(0.6)).astype(np.float32)
+
+
+# ------------------------------------------------------------------------------------ CPU arm
+def build_cpu_learner(wl, threads):
+    """Oracle port of the reference learner with its replay filled to the workload's size.  The fill
+    writes the oracle's own data structures directly (vectorised) -- only the learner step is timed."""
+    import torch
+    from oracle.dqn_oracle import OracleLearner
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    lrn = OracleLearner(wl["algo"], D, A, wl["B"], wl["cap"])
+    n = wl["size"]
+    obs, act, rew, done, nxt = synthetic(n, 20251018)
+    rows = list(zip(list(obs), act.tolist(), rew.tolist(), (done != 0).tolist(), list(nxt)))
+    if lrn.per:
+        t = lrn.replay.tree
+        cap = t.capacity
+        t.data[:n] = np.array(rows + [None], dtype=object)[:n]
+        t.size, t.data_pointer = n, n % cap
+        pri = seeded_priorities(n, 7)
+        t.tree[cap - 1:cap - 1 + n] = pri
+        for node in range(cap - 2, -1, -1) if cap < 4096 else ():
+            t.tree[node] = t.tree[2 * node + 1] + t.tree[2 * node + 2]
+        if cap >= 4096:   # vectorised bottom-up rebuild, level by level (exact sums)
+            level = int(np.floor(np.log2(cap - 1))) if cap > 1 else 0
+            for L in range(level, -1, -1):
+                first, last = (1 << L) - 1, min((1 << (L + 1)) - 2, cap - 2)
+                if first <= last:
+                    idx = np.arange(first, last + 1)
+                    t.tree[idx] = t.tree[2 * idx + 1] + t.tree[2 * idx + 2]
+        leaves = t.tree[cap - 1:cap - 1 + n]
+        t.arg_max, t.arg_min = int(np.argmax(leaves)) + cap - 1, int(np.argmin(leaves)) + cap - 1
+    else:
+        lrn.replay.buf.extend(rows)
+    return lrn
+
+
+def time_cpu_learner(lrn, steps, warmup, budget_s=25.0):
+    np.random.seed(1000)
+    import random
+    random.seed(1000)
+    for s in range(warmup):
+        lrn.step = s
+        lrn.learn()
+        lrn.sync_target()
+    t0 = time.perf_counter()
+    done = 0
+    for s in range(steps):
+        lrn.step = warmup + s
+        lrn.learn()
+        lrn.sync_target()
+        done += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return done, dt
+
+
+def cpu_baseline(wl, steps, warmup, threads):
+    lrn = build_cpu_learner(wl, threads)
+    done, dt = time_cpu_learner(lrn, steps, warmup)
+    return {"value": wl["B"] * done / dt, "unit": "transitions/s", "cores": threads, "kind": "port",
+            "ms_per_step": 1e3 * dt / done,
+            "sample": "%d learner steps (after %d warm-up) of the oracle port of the reference learner (torch-CPU %d threads + numpy "
+                      "+ python sum tree), same workload: B=%d, replay size %d" % (done, warmup, threads, wl["B"], wl["size"])}
+
+
+def run_reference_arm(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    cb = cpu_baseline(wl, max(args.steps, 1), max(args.warmup, 1), threads)
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "transitions/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["name"], "batch": wl["B"], "replay_capacity": wl["cap"], "replay_size": wl["size"], "obs_dim": D},
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": cb["value"], "unit": "transitions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------ GPU arm
+def build_gpu_agent(wl, device_index, seed):
+    import tempfile
+    import torch
+    from multimodal_drl_rmc_b200 import _lib, macro_config
+    tmp = tempfile.mkdtemp(prefix="rmc_bench_")
+    torch.manual_seed(seed)
+    agent = macro_config.make_agent(wl["algo"], D, wl["B"], wl["cap"], save_dir=tmp + "/", log_dir=tmp + "/", gpu=str(device_index))
+    n = wl["size"]
+    obs, act, rew, done, nxt = synthetic(n, 20251018 + seed)
+    ring = agent.replay_memory_buffer._ring
+    ring.push_host(obs, act, rew, done, nxt)           # bulk path: pinned staging -> H2D -> ring (+ tree rebuild)
+    if agent._PER:
+        pri = torch.as_tensor(seeded_priorities(n, 7 + seed), device=agent.device)
+        _lib.check(_lib.lib().rmc_replay_set_priorities(ring.handle, pri.data_ptr(), n, _lib.stream_ptr()))
+    agent.sampling_seed = 1000 + seed
+    torch.cuda.synchronize()
+    return agent, (obs, act, rew, done, nxt)
+
+
+def run_ours(args, wl):
+    import torch
+    import torch.distributed as dist
+    from multimodal_drl_rmc_b200 import _lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl ours) needs a CUDA device: there is no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    B, K, W = wl["B"], args.steps, max(args.warmup, 3)
+    agent, data = build_gpu_agent(wl, local, seed=rank)
+    obs, act, rew, done, nxt = data
+    lib = _lib.lib()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_step():
+        agent.step += 1
+        agent.learn(fuse_target_update=True)
+        agent.update_target_network()        # no-op: already fused into the launch above
+
+    # ---- device-timed: inputs resident in HBM ----------------------------------------------
+    for _ in range(W):
+        one_step()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    l0 = lib.rmc_launch_count()
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_start.record()
+    for k in range(K):
+        ev[k][0].record()
+        one_step()
+        ev[k][1].record()
+    t_end.record()
+    barrier()
+    launches = int(lib.rmc_launch_count() - l0)
+    ms_total = t_start.elapsed_time(t_end)
+    kern_ms = sum(a.elapsed_time(b) for a, b in ev) / K
+
+    # ---- end to end through the public API with host buffers --------------------------------
+    n_new = min(len(obs), 4096)
+    for k in range(W):
+        j = k % n_new
+        agent.store_transitions(obs[j:j + 1], [int(act[j])], [float(rew[j])], [bool(done[j])], nxt[j:j + 1], None)
+        one_step()
+        agent.last_loss()
+    barrier()
+    e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e_start.record()
+    wall0 = time.perf_counter()
+    loss = 0.0
+    for k in range(K):
+        j = (W + k) % n_new
+        agent.store_transitions(obs[j:j + 1], [int(act[j])], [float(rew[j])], [bool(done[j])], nxt[j:j + 1], None)
+        one_step()
+        loss = agent.last_loss()              # D2H read of the step's loss (synchronises)
+    e_end.record()
+    barrier()
+    e2e_ms = max(e_start.elapsed_time(e_end), 1e3 * (time.perf_counter() - wall0))
+    clocks = sampler.summary() if sampler else None
+
+    # ---- max over ranks -----------------------------------------------------------------------
+    t = torch.tensor([ms_total, e2e_ms, kern_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms, kern_ms = (float(x) for x in t.tolist())
+
+    extra = {}
+    if rank == 0 and world == 1 and not args.no_extra:
+        extra = extra_workloads(agent)
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        per = agent._PER
+        bytes_per_launch = (BYTES_PER_TRANSITION_PER if per else BYTES_PER_TRANSITION_UNI) * B
+        achieved = bytes_per_launch / (kern_ms * 1e-3) / 1e9
+        flops_per_launch = FLOP_PER_TRANSITION * B + 16 * P_COUNT
+        cb = None
+        if world == 1 and not args.no_cpu:
+            threads = os.cpu_count() or 1
+            cb = cpu_baseline(wl, 200, 5, threads)
+        line = {
+            "metric": METRIC, "value": world * B * K / (ms_total * 1e-3), "unit": "transitions/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": wl["name"], "batch": B, "replay_capacity": wl["cap"], "replay_size": wl["size"], "obs_dim": D,
+                       "net": "MLP %d-256-128-(1+8) dueling" % D if agent._DUELING else "MLP %d-256-128-8" % D,
+                       "parallelism": "1 independent agent per GPU (ensemble members), no collective" if world > 1 else "single agent",
+                       "l2": "inputs larger than L2: 128 MB ring + 16 MB tree sampled at random each step (126 MB L2); the 0.3 MB of weights "
+                             "and the per-step scratch are L2-resident by design",
+                       "sampling": "on-device Philox uniforms", "target_sync": "Polyak fused into the step launch"},
+            "e2e": {"value": world * B * K / (e2e_ms * 1e-3), "unit": "transitions/s", "ms_per_step": e2e_ms / K,
+                    "h2d_bytes_per_step": int(agent.replay_memory_buffer._ring.row_floats * 4), "d2h_bytes_per_step": 4,
+                    "what": "store_transitions(1 host row) + learn() + update_target_network() + loss read-back per step", "last_loss": loss},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "kernel": "k_learner_step", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_launch,
+                         "kernel_ms": kern_ms, "fp32_tflops": flops_per_launch / (kern_ms * 1e-3) / 1e12,
+                         "note": "latency-bound step (SURVEY 8d): report us/step next to the fraction"},
+            "clocks": clocks,
+        }
+        if cb is not None:
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        if extra:
+            line["extra"] = extra
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def extra_workloads(agent):
+    """Secondary configs of BASELINE.json, measured after the headline (not part of its timed region)."""
+    import torch
+    out = {}
+    try:
+        states = np.random.default_rng(0).random((65536, D), dtype=np.float32)
+        dev_states = torch.as_tensor(states, device=agent.device)
+        net = agent.online_network
+        for _ in range(3):
+            net.actions(dev_states[:1024])
+        from multimodal_drl_rmc_b200 import _lib
+        acts = torch.empty(65536, dtype=torch.int64, device=agent.device)
+        lh = agent._lh
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(3):
+            _lib.check(_lib.lib().rmc_learner_act(lh.handle, dev_states.data_ptr(), 65536, acts.data_ptr(), _lib.stream_ptr()))
+        s.record()
+        for _ in range(10):
+            _lib.check(_lib.lib().rmc_learner_act(lh.handle, dev_states.data_ptr(), 65536, acts.data_ptr(), _lib.stream_ptr()))
+        e.record()
+        torch.cuda.synchronize()
+        ms = s.elapsed_time(e) / 10
+        t0 = time.perf_counter()
+        for _ in range(5):
+            net.actions(states)
+        host_ms = 1e3 * (time.perf_counter() - t0) / 5
+        out["act_65536"] = {"device_ms": ms, "states_per_s": 65536 / (ms * 1e-3), "fp32_tflops": 65536 * 2 * (D * H1 + H1 * H2 + H2 * A) / (ms * 1e-3) / 1e12,
+                            "host_api_ms": host_ms, "host_api_states_per_s": 65536 / (host_ms * 1e-3)}
+    except Exception as exc:  # pragma: no cover
+        out["act_65536"] = {"error": repr(exc)}
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="per256", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary workloads")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference_arm(args, wl)
+    else:
+        run_ours(args, wl)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,273 @@
+"""Drop-in agents: same constructor, attributes and methods as ``dqn/agent.py`` (Agent :18-158 and
+the four concrete agents :275-320); ``learn()`` / ``update_target_network()`` / ``choose_actions()``
+run as fused CUDA launches of librmc_b200 on a GPU-resident replay.
+
+Randomness of the minibatch draw (``Agent.sampling``):
+  "device" (default)  counter-based Philox / keyed permutation on the GPU, no host work per step
+  "host"              consume the host RNG streams exactly like the reference does
+                      (``np.random.random_sample(B)`` for PER, ``random.sample(range(n), B)`` for
+                      uniform replay) and upload them: with equal seeds the sampled transitions
+                      are bit-identical to the reference's.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+import random
+import time
+from collections import deque
+from datetime import timedelta
+
+import numpy as np
+import torch as T
+
+from . import _lib
+from ._lib import check, lib, ptr, stream_ptr
+from .network import DeepQNetwork, DuelingDeepQNetwork, LearnerHandle
+from .replay_memory import ReplayMemoryNaive, ReplayMemoryPrioritized
+
+
+class Agent:
+    # flavour switches, fixed by the concrete classes below (dqn/agent.py:275-320)
+    _PER = False
+    _DUELING = False
+    _DOUBLE = False
+
+    def __init__(self, n_env, lr, gamma, epsilon_start, epsilon_min, epsilon_decay, epsilon_exp_decay, nn_conf_func,
+                 input_dim, output_dim, batch_size, min_buffer_size, buffer_size, update_target_frequency,
+                 target_soft_update, target_soft_update_tau, save_frequency, log_frequency, save_dir, log_dir, load,
+                 algo, gpu):
+        self.n_env = n_env
+        self.lr = lr
+        self.gamma = gamma
+        self.epsilon_start = epsilon_start
+        self.epsilon_min = epsilon_min
+        self.epsilon_decay = epsilon_decay
+        self.epsilon_exp_decay = epsilon_exp_decay
+        self.nn_conf_func = nn_conf_func
+        self.input_dim = input_dim
+        self.output_dim = output_dim
+        self.batch_size = batch_size
+        self.min_buffer_size = min_buffer_size
+        self.buffer_size = buffer_size
+        self.update_target_frequency = update_target_frequency
+        self.target_soft_update = target_soft_update
+        self.target_soft_update_tau = target_soft_update_tau
+        self.save_frequency = save_frequency
+        self.log_frequency = log_frequency
+        self.load = load
+
+        self.step = 0
+        self.resume_step = 0
+        self.episode_count = 0
+        self.ep_info_buffer = deque([], maxlen=50)
+
+        path = algo + '_lr' + str(lr)
+        self.save_path = save_dir + path + '_' + 'model.pack'
+        self.summary_writer = self._make_writer(log_dir + path + '/')
+
+        if not T.cuda.is_available():
+            raise RuntimeError("multimodal_drl_rmc_b200 agents need a CUDA (sm_100a) device: there is no CPU fallback")
+        self.device = T.device("cuda:" + str(gpu))
+        print("DEVICE", "=", self.device, T.cuda.get_device_name(self.device))
+        self.start_time = time.time()
+
+        # ---- wiring of dqn/agent.py:275-320 -------------------------------------------------
+        if self._PER:
+            self.replay_memory_buffer = ReplayMemoryPrioritized(self.buffer_size, self.batch_size, self.epsilon_decay)
+        else:
+            self.replay_memory_buffer = ReplayMemoryNaive(self.buffer_size, self.batch_size)
+        self.replay_memory_buffer._ring.device_index = self.device.index
+        net_cls = DuelingDeepQNetwork if self._DUELING else DeepQNetwork
+        reduction = 'none' if self._PER else 'mean'
+        self.online_network = net_cls(self.device, self.lr, self.nn_conf_func, self.input_dim, self.output_dim, reduction=reduction)
+        self.target_network = net_cls(self.device, self.lr, self.nn_conf_func, self.input_dim, self.output_dim, reduction=reduction)
+
+        hyper = _lib.Hyper(float(lr), 0.9, 0.999, 1e-8, float(gamma), float(target_soft_update_tau) * n_env,
+                           1e-4, 0.6, 1.0)
+        self._lh = LearnerHandle(self.online_network._obs_dim, output_dim, self._DUELING, self._DOUBLE, self._PER,
+                                 max(int(batch_size), 1), self.device.index, hyper)
+        self.online_network._bind(self._lh, _lib.ONLINE)
+        self.target_network._bind(self._lh, _lib.TARGET)
+        self.update_target_network(force=True)
+
+        self.sampling = "device"
+        self.sampling_seed = 0x5EED
+        self._learn_calls = 0
+        self._adam_t = 0
+
+    @staticmethod
+    def _make_writer(path):
+        from torch.utils.tensorboard import SummaryWriter
+        return SummaryWriter(path)
+
+    # ------------------------------------------------------------------ replay ---------------
+    def store_transitions(self, obses, actions, rews, dones, new_obses, infos):
+        for i in self.replay_memory_buffer.store_transitions(obses, actions, rews, dones, new_obses):
+            if infos:
+                self.ep_info_buffer.append({'r': infos[i]['r'], 'l': infos[i]['l']})
+                self.episode_count += 1
+
+    # ------------------------------------------------------------------ acting ---------------
+    def epsilon(self):
+        if self.epsilon_exp_decay:
+            return np.exp(np.interp(self.step * self.n_env, [0, self.epsilon_decay],
+                                    [np.log(self.epsilon_start), np.log(self.epsilon_min)]))
+        return np.interp(self.step * self.n_env, [0, self.epsilon_decay], [self.epsilon_start, self.epsilon_min])
+
+    def choose_actions(self, obses):
+        actions = self.online_network.actions(obses)
+        for i in range(len(actions)):
+            if random.random() <= self.epsilon():
+                actions[i] = random.randint(0, self.output_dim - 1)
+        return actions
+
+    # ------------------------------------------------------------------ learning -------------
+    def _step_args(self, phases, u=None, indices=None):
+        B = int(self.batch_size)
+        a = _lib.StepArgs()
+        a.batch, a.phases = B, int(phases)
+        a.seed, a.counter = int(self.sampling_seed), int(self._learn_calls)
+        a.adam_t = int(self._adam_t)
+        keep = None
+        if phases & _lib.PH_SAMPLE:
+            if self._PER:
+                a.per_beta = self.replay_memory_buffer.beta(self.step * self.n_env)
+                if u is None and self.sampling == "host":
+                    u = np.random.random_sample(B)
+                if u is not None:
+                    keep = T.as_tensor(np.asarray(u, np.float64), device=self.device)
+                    a.u_dev = ptr(keep)
+            else:
+                if indices is None and self.sampling == "host":
+                    indices = random.sample(range(len(self.replay_memory_buffer.replay_buffer)), B)
+                if indices is not None:
+                    keep = T.as_tensor(np.asarray(indices, np.int64), device=self.device)
+                    a.idx_dev = ptr(keep)
+        return a, keep
+
+    def learn(self, u=None, indices=None, fuse_target_update=False):
+        """dqn/agent.py:166-185 / 204-226 / 245-272 as one launch.  ``u`` / ``indices`` inject the
+        sampling randomness (tests).  ``fuse_target_update=True`` also performs this step's
+        ``update_target_network()`` inside the same launch (call order of train.py:99-101); the
+        following ``update_target_network()`` call is then skipped once."""
+        ring = self.replay_memory_buffer._ring
+        self._learn_calls += 1
+        self._adam_t += 1
+        phases = _lib.PH_LEARN
+        if not self._PER:
+            phases &= ~_lib.PH_PRIORITY
+        if fuse_target_update:
+            phases |= self._target_phase()
+            self._target_fused_for = self._learn_calls
+        a, keep = self._step_args(phases, u, indices)
+        check(lib().rmc_learner_step(self._lh.handle, ring.require(), C.byref(a), stream_ptr()))
+        self._lh.version[_lib.ONLINE] += 1
+        if fuse_target_update:
+            self._lh.version[_lib.TARGET] += 1
+        self._keepalive = keep
+
+    def _target_phase(self, force=False):
+        if (not self.target_soft_update and self.step % (self.update_target_frequency // self.n_env) == 0) or force:
+            return _lib.PH_HARDSYNC
+        if self.target_soft_update:
+            return _lib.PH_POLYAK
+        return 0
+
+    def update_target_network(self, force=False):
+        """dqn/agent.py:101-110."""
+        if not force and getattr(self, "_target_fused_for", None) == self._learn_calls:
+            self._target_fused_for = None
+            return
+        phase = self._target_phase(force)
+        if not phase:
+            return
+        self.online_network._push()
+        self.target_network._push()
+        a = _lib.StepArgs()
+        a.batch, a.phases, a.adam_t = 1, int(phase), 1
+        ring = self.replay_memory_buffer._ring
+        rh = ring.handle if ring.handle is not None else self._dummy_ring().handle
+        check(lib().rmc_learner_step(self._lh.handle, rh, C.byref(a), stream_ptr()))
+        self._lh.version[_lib.TARGET] += 1
+
+    def _dummy_ring(self):
+        # target sync before the first transition arrives (constructor): a 1-slot ring of the right kind
+        if getattr(self, "_dummy", None) is None:
+            from .replay_memory import DeviceRing
+            self._dummy = DeviceRing(1, prioritized=self._PER, device_index=self.device.index).ensure(self.online_network._obs_dim)
+        return self._dummy
+
+    def last_loss(self):
+        """Loss of the last learn() (device -> host read; synchronises)."""
+        out = C.c_float()
+        check(lib().rmc_learner_loss_sync(self._lh.handle, C.byref(out), stream_ptr()))
+        return out.value
+
+    # ------------------------------------------------------------------ checkpoints / logs ---
+    def load_model(self):
+        if self.load and os.path.exists(self.save_path):
+            print()
+            print("Resume training from " + self.save_path + "...")
+            self.resume_step, self.episode_count, rew_mean, len_mean = self.online_network.load(self.save_path)
+            [self.ep_info_buffer.append({'r': rew_mean, 'l': len_mean}) for _ in range(np.min([self.episode_count, self.ep_info_buffer.maxlen]))]
+            print("Step: ", self.resume_step * self.n_env, ", Episodes: ", self.episode_count, ", Avg Rew: ", rew_mean, ", Avg Ep Len: ", len_mean)
+            self.update_target_network(force=True)
+            self.step = self.resume_step
+
+    def save_model(self):
+        if self.step % self.save_frequency == 0 and self.step > self.resume_step:
+            print()
+            print("Saving model...")
+            self.online_network.save(self.save_path, self.step, self.episode_count, self.info_mean('r'), self.info_mean('l'))
+            print("OK!")
+
+    def log(self):
+        if self.step % self.log_frequency == 0 and self.step > self.resume_step:
+            rew_mean, len_mean = self.info_mean('r'), self.info_mean('l')
+            print()
+            print('Step: ', self.step * self.n_env, ' (' + str(self.step) + 'x' + str(self.n_env) + ')')
+            print('Avg Rew: ', rew_mean)
+            print('Avg Ep Len: ', len_mean)
+            print('Episodes: ', self.episode_count)
+            print('---', str(timedelta(seconds=round((time.time() - self.start_time), 0))), '---')
+            self.summary_writer.add_scalar('AvgRew', rew_mean, global_step=(self.step * self.n_env))
+            self.summary_writer.add_scalar('AvgEpLen', len_mean, global_step=(self.step * self.n_env))
+            self.summary_writer.add_scalar('Episodes', self.episode_count, global_step=(self.step * self.n_env))
+
+    def info_mean(self, i):
+        i_mean = np.mean([e[i] for e in self.ep_info_buffer]) if len(self.ep_info_buffer) else float('nan')
+        return i_mean if not math.isnan(i_mean) else 0.
+
+
+class SimpleAgent(Agent):
+    """dqn/agent.py:148-185: y = r + (1-d) gamma max_a Q_target(s')."""
+    _DOUBLE = False
+
+
+class DoubleAgent(Agent):
+    """dqn/agent.py:188-226: a* = argmax_a Q_online(s'), y uses Q_target(s')[a*]."""
+    _DOUBLE = True
+
+
+class PerDoubleAgent(Agent):
+    """dqn/agent.py:229-272: DoubleAgent + IS weights + |td| write-back before backward."""
+    _DOUBLE = True
+    _PER = True
+
+
+class DQNAgent(SimpleAgent):
+    pass
+
+
+class DoubleDQNAgent(DoubleAgent):
+    pass
+
+
+class DuelingDoubleDQNAgent(DoubleAgent):
+    _DUELING = True
+
+
+class PerDuelingDoubleDQNAgent(PerDoubleAgent):
+    _DUELING = True

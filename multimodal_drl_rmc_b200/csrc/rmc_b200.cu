@@ -1,0 +1,787 @@
+// rmc_b200.cu -- host side of librmc_b200.so: the C ABI declared in include/rmc_b200.h.
+// Plain CUDA runtime, no torch.  One translation unit with the kernels (rmc_tree.cuh, rmc_mlp.cuh).
+#include "../../include/rmc_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "rmc_device.cuh"
+#include "rmc_mlp.cuh"
+#include "rmc_tree.cuh"
+
+using namespace rmc;
+
+// ------------------------------------------------------------------------------ errors
+static thread_local std::string g_err;
+static std::atomic<long long> g_launches{0};
+
+static int32_t fail(int32_t code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define RMC_CUDA(expr)                                                                                   \
+  do {                                                                                                   \
+    cudaError_t _e = (expr);                                                                             \
+    if (_e != cudaSuccess)                                                                               \
+      return fail(RMC_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));                    \
+  } while (0)
+#define RMC_KERNEL_OK()                                                                                  \
+  do {                                                                                                   \
+    g_launches.fetch_add(1, std::memory_order_relaxed);                                                  \
+    cudaError_t _e = cudaGetLastError();                                                                 \
+    if (_e != cudaSuccess) return fail(RMC_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(_e)); \
+  } while (0)
+
+static inline cudaStream_t as_stream(rmc_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline unsigned blocks_for(long long n, int threads) { return static_cast<unsigned>((n + threads - 1) / threads); }
+static inline int round4(int x) { return (x + 3) & ~3; }
+
+// ------------------------------------------------------------------------------ handles
+static constexpr int kStageSlots = 4;
+
+struct rmc_replay {
+  int device = 0;
+  long long cap = 0, size = 0, dp = 0;   // host mirrors of the device state
+  int D = 0, rf = 0, prioritized = 0;
+  long long n_nodes = 0;
+  ReplayDev dev{};
+  long long* scratch_nodes = nullptr;
+  float* scratch_pri = nullptr;
+  // staging ring for host pushes
+  long long stage_rows = 0;
+  float* pin[kStageSlots] = {nullptr, nullptr, nullptr, nullptr};
+  float* dstage[kStageSlots] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev[kStageSlots] = {nullptr, nullptr, nullptr, nullptr};
+  bool ev_used[kStageSlots] = {false, false, false, false};
+  int slot = 0;
+};
+
+struct rmc_learner {
+  int device = 0;
+  rmc_net_spec_t spec{};
+  rmc_hyper_t hyper{};
+  NetLayout L{};
+  long long P = 0;           // torch parameter count
+  long long max_batch = 0, last_batch = 0;
+  int rf = 0;
+  int num_sms = 0;
+  int smem_bytes = 0;
+  float* blobs[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // online,target,m,v,grads
+  int* map = nullptr;        // torch index -> device-layout index
+  float* io = nullptr;       // [P] device staging for set/get
+  AgentCtx ctx{};            // replay part filled per step
+  unsigned barrier_count = 0;
+  // act staging
+  float* act_pin_obs = nullptr; long long* act_pin_out = nullptr; float* act_dev_obs = nullptr; long long* act_dev_out = nullptr;
+  long long act_cap = 0;
+  std::vector<void*> owned;
+};
+
+struct rmc_group {
+  int n = 0;
+  std::vector<rmc_learner*> learners;
+  std::vector<rmc_replay*> replays;
+  AgentCtx* ctx_dev = nullptr;
+  unsigned* barriers = nullptr;
+  unsigned barrier_count = 0;
+};
+
+// ------------------------------------------------------------------------------ library
+extern "C" int32_t rmc_abi_version(void) { return RMC_ABI_VERSION; }
+extern "C" const char* rmc_last_error(void) { return g_err.c_str(); }
+extern "C" int64_t rmc_launch_count(void) { return g_launches.load(); }
+
+static int32_t use_device(int device) {
+  RMC_CUDA(cudaSetDevice(device));
+  return RMC_OK;
+}
+
+template <typename T>
+static int32_t dev_alloc(T** p, size_t count, bool zero = true) {
+  RMC_CUDA(cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(T)));
+  if (zero) RMC_CUDA(cudaMemset(*p, 0, count * sizeof(T)));
+  return RMC_OK;
+}
+
+__global__ void k_fill_f32(float* p, long long n, float v) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+__global__ void k_init_state(ReplayState* st) {
+  st->size = 0; st->dp = 0; st->max_p = 0.f; st->min_p = __int_as_float(0x7f800000); st->push_p = 1.f; st->pad = 0;
+}
+
+// ------------------------------------------------------------------------------ replay
+extern "C" int32_t rmc_replay_create(rmc_replay_t** out, int64_t capacity, int32_t obs_dim, int32_t prioritized,
+                                     int32_t device) {
+  if (!out || capacity < 1 || obs_dim < 1 || obs_dim > kMaxD) return fail(RMC_ERR_ARG, "rmc_replay_create: bad capacity/obs_dim");
+  if (capacity > (1ll << 30)) return fail(RMC_ERR_ARG, "rmc_replay_create: capacity too large");
+  if (int32_t e = use_device(device)) return e;
+  auto* r = new rmc_replay();
+  r->device = device;
+  r->cap = capacity;
+  r->D = obs_dim;
+  r->rf = round4(2 * obs_dim + 3);
+  r->prioritized = prioritized ? 1 : 0;
+  r->n_nodes = 2 * capacity - 1;
+  ReplayDev& d = r->dev;
+  d.cap = capacity; d.row_floats = r->rf; d.obs_dim = obs_dim; d.prioritized = r->prioritized;
+  d.n0 = (capacity + kBlk - 1) / kBlk;
+  d.n1 = (d.n0 + kBlk - 1) / kBlk;
+  int32_t e = RMC_OK;
+  if ((e = dev_alloc(&d.ring, static_cast<size_t>(capacity) * r->rf))) return e;
+  if ((e = dev_alloc(&d.st, 1))) return e;
+  k_init_state<<<1, 1>>>(d.st);
+  RMC_KERNEL_OK();
+  if (r->prioritized) {
+    if ((e = dev_alloc(&d.tree, static_cast<size_t>(r->n_nodes)))) return e;
+    if ((e = dev_alloc(&d.stamps, static_cast<size_t>(capacity)))) return e;
+    if ((e = dev_alloc(&d.b0min, static_cast<size_t>(d.n0), false))) return e;
+    if ((e = dev_alloc(&d.b0max, static_cast<size_t>(d.n0)))) return e;
+    if ((e = dev_alloc(&d.b1min, static_cast<size_t>(d.n1), false))) return e;
+    if ((e = dev_alloc(&d.b1max, static_cast<size_t>(d.n1)))) return e;
+    const float inf = INFINITY;
+    k_fill_f32<<<blocks_for(d.n0, 256), 256>>>(d.b0min, d.n0, inf);
+    RMC_KERNEL_OK();
+    k_fill_f32<<<blocks_for(d.n1, 256), 256>>>(d.b1min, d.n1, inf);
+    RMC_KERNEL_OK();
+  }
+  if ((e = dev_alloc(&r->scratch_nodes, kTreeCtaMax))) return e;
+  if ((e = dev_alloc(&r->scratch_pri, kTreeCtaMax))) return e;
+  r->stage_rows = 16384;
+  for (int s = 0; s < kStageSlots; ++s) {
+    RMC_CUDA(cudaMallocHost(reinterpret_cast<void**>(&r->pin[s]), static_cast<size_t>(r->stage_rows) * r->rf * sizeof(float)));
+    if ((e = dev_alloc(&r->dstage[s], static_cast<size_t>(r->stage_rows) * r->rf, false))) return e;
+    RMC_CUDA(cudaEventCreateWithFlags(&r->ev[s], cudaEventDisableTiming));
+  }
+  RMC_CUDA(cudaDeviceSynchronize());
+  *out = r;
+  return RMC_OK;
+}
+
+extern "C" int32_t rmc_replay_destroy(rmc_replay_t* r) {
+  if (!r) return RMC_OK;
+  cudaSetDevice(r->device);
+  cudaDeviceSynchronize();
+  ReplayDev& d = r->dev;
+  cudaFree(d.ring); cudaFree(d.tree); cudaFree(d.stamps); cudaFree(d.b0min); cudaFree(d.b0max);
+  cudaFree(d.b1min); cudaFree(d.b1max); cudaFree(d.st); cudaFree(r->scratch_nodes); cudaFree(r->scratch_pri);
+  for (int s = 0; s < kStageSlots; ++s) {
+    if (r->pin[s]) cudaFreeHost(r->pin[s]);
+    cudaFree(r->dstage[s]);
+    if (r->ev[s]) cudaEventDestroy(r->ev[s]);
+  }
+  delete r;
+  return RMC_OK;
+}
+
+extern "C" int32_t rmc_replay_row_floats(const rmc_replay_t* r) { return r ? r->rf : 0; }
+
+static int32_t tree_rebuild(rmc_replay* r, cudaStream_t st) {
+  // internal nodes are 0 .. cap-2; rebuild level by level from the deepest
+  const long long last_internal = r->cap - 2;
+  for (int L = 40; L >= 0; --L) {
+    const long long first = (1ll << L) - 1;
+    if (first > last_internal) continue;
+    const long long last = std::min((1ll << (L + 1)) - 2, last_internal);
+    const long long count = last - first + 1;
+    k_tree_rebuild_level<<<blocks_for(count, 256), 256, 0, st>>>(r->dev.tree, first, count);
+    RMC_KERNEL_OK();
+  }
+  return RMC_OK;
+}
+static int32_t minmax_rebuild(rmc_replay* r, cudaStream_t st) {
+  k_minmax_l0_all<<<blocks_for(r->dev.n0, 256), 256, 0, st>>>(r->dev);
+  RMC_KERNEL_OK();
+  k_minmax_l1_all<<<blocks_for(r->dev.n1, 256), 256, 0, st>>>(r->dev);
+  RMC_KERNEL_OK();
+  k_minmax_global<<<1, 32, 0, st>>>(r->dev);
+  RMC_KERNEL_OK();
+  return RMC_OK;
+}
+
+// rows already packed in a device staging buffer
+static int32_t push_packed_small(rmc_replay* r, const float* rows_dev, long long n, cudaStream_t st) {
+  k_push_small<<<1, kThreads, 0, st>>>(r->dev, rows_dev, n, r->scratch_nodes, r->scratch_pri, 1.0f);
+  RMC_KERNEL_OK();
+  r->dp = (r->dp + n) % r->cap;
+  r->size = std::min(r->size + n, r->cap);
+  return RMC_OK;
+}
+
+static void pack_rows_host(float* dst, const float* obs, const int64_t* act, const float* rew, const float* done,
+                           const float* nxt, long long n, int D, int rf) {
+  for (long long i = 0; i < n; ++i) {
+    float* row = dst + i * rf;
+    std::memcpy(row, obs + i * D, sizeof(float) * D);
+    std::memcpy(row + D, nxt + i * D, sizeof(float) * D);
+    const int32_t a = static_cast<int32_t>(act[i]);
+    std::memcpy(row + 2 * D, &a, sizeof(float));
+    row[2 * D + 1] = rew[i];
+    row[2 * D + 2] = done[i];
+    for (int c = 2 * D + 3; c < rf; ++c) row[c] = 0.f;
+  }
+}
+
+static int32_t push_impl(rmc_replay* r, const float* obs, const int64_t* act, const float* rew, const float* done,
+                         const float* nxt, int64_t n, bool host, cudaStream_t st) {
+  if (!r || n < 0) return fail(RMC_ERR_ARG, "rmc_replay_push: bad args");
+  if (n == 0) return RMC_OK;
+  if (int32_t e = use_device(r->device)) return e;
+  const long long small_max = std::min<long long>(kTreeCtaMax, r->cap);
+  const bool bulk = n > small_max;
+  const long long chunk_max = bulk ? std::min<long long>(r->stage_rows, r->cap) : small_max;
+  if (bulk) {
+    k_push_begin<<<1, 1, 0, st>>>(r->dev, 1.0f);
+    RMC_KERNEL_OK();
+  }
+  for (long long off = 0; off < n; off += chunk_max) {
+    const long long m = std::min<long long>(chunk_max, n - off);
+    const int s = r->slot;
+    r->slot = (r->slot + 1) % kStageSlots;
+    if (host) {
+      if (r->ev_used[s]) RMC_CUDA(cudaEventSynchronize(r->ev[s]));
+      pack_rows_host(r->pin[s], obs + off * r->D, act + off, rew + off, done + off, nxt + off * r->D, m, r->D, r->rf);
+      RMC_CUDA(cudaMemcpyAsync(r->dstage[s], r->pin[s], static_cast<size_t>(m) * r->rf * sizeof(float), cudaMemcpyHostToDevice, st));
+      RMC_CUDA(cudaEventRecord(r->ev[s], st));
+      r->ev_used[s] = true;
+    } else {
+      k_pack_rows<<<blocks_for(m * r->rf, 256), 256, 0, st>>>(r->dstage[s], obs + off * r->D, reinterpret_cast<const long long*>(act + off), rew + off, done + off,
+                                                             nxt + off * r->D, m, r->D, r->rf);
+      RMC_KERNEL_OK();
+    }
+    if (!bulk) {
+      if (int32_t e = push_packed_small(r, r->dstage[s], m, st)) return e;
+    } else {
+      k_push_rows_bulk<<<blocks_for(m * r->rf, 256), 256, 0, st>>>(r->dev, r->dstage[s], m, r->dp);
+      RMC_KERNEL_OK();
+      r->dp = (r->dp + m) % r->cap;
+      r->size = std::min(r->size + m, r->cap);
+    }
+  }
+  if (bulk) {
+    k_push_end<<<1, 1, 0, st>>>(r->dev, r->dp, r->size);
+    RMC_KERNEL_OK();
+    if (r->prioritized) {
+      if (int32_t e = tree_rebuild(r, st)) return e;
+      if (int32_t e = minmax_rebuild(r, st)) return e;
+    }
+  }
+  return RMC_OK;
+}
+
+extern "C" int32_t rmc_replay_push(rmc_replay_t* r, const float* obs_dev, const int64_t* act_dev, const float* rew_dev,
+                                   const float* done_dev, const float* next_obs_dev, int64_t n, rmc_stream_t s) {
+  return push_impl(r, obs_dev, act_dev, rew_dev, done_dev, next_obs_dev, n, false, as_stream(s));
+}
+extern "C" int32_t rmc_replay_push_host(rmc_replay_t* r, const float* obs_host, const int64_t* act_host, const float* rew_host,
+                                        const float* done_host, const float* next_obs_host, int64_t n, rmc_stream_t s) {
+  return push_impl(r, obs_host, act_host, rew_host, done_host, next_obs_host, n, true, as_stream(s));
+}
+
+extern "C" int32_t rmc_replay_set_priorities(rmc_replay_t* r, const float* pri_dev, int64_t n, rmc_stream_t s) {
+  if (!r || !r->prioritized || n < 0 || n > r->size) return fail(RMC_ERR_ARG, "rmc_replay_set_priorities: bad args");
+  if (int32_t e = use_device(r->device)) return e;
+  cudaStream_t st = as_stream(s);
+  if (n > 0) {
+    k_set_leaves<<<blocks_for(n, 256), 256, 0, st>>>(r->dev, pri_dev, n);
+    RMC_KERNEL_OK();
+  }
+  if (int32_t e = tree_rebuild(r, st)) return e;
+  return minmax_rebuild(r, st);
+}
+
+extern "C" int32_t rmc_replay_stats_sync(rmc_replay_t* r, rmc_replay_stats_t* out, rmc_stream_t s) {
+  if (!r || !out) return fail(RMC_ERR_ARG, "rmc_replay_stats_sync: null");
+  if (int32_t e = use_device(r->device)) return e;
+  cudaStream_t st = as_stream(s);
+  ReplayState hs{};
+  double total = 0.0;
+  RMC_CUDA(cudaMemcpyAsync(&hs, r->dev.st, sizeof(hs), cudaMemcpyDeviceToHost, st));
+  if (r->prioritized) RMC_CUDA(cudaMemcpyAsync(&total, r->dev.tree, sizeof(double), cudaMemcpyDeviceToHost, st));
+  RMC_CUDA(cudaStreamSynchronize(st));
+  out->capacity = r->cap;
+  out->size = hs.size;
+  out->data_pointer = hs.dp;
+  out->total_priority = total;
+  out->max_priority = (hs.size > 0 && r->prioritized) ? static_cast<double>(hs.max_p) : 0.0;
+  out->min_priority = (hs.size > 0 && r->prioritized) ? static_cast<double>(hs.min_p) : 0.0;
+  return RMC_OK;
+}
+
+extern "C" int32_t rmc_replay_read_tree_sync(rmc_replay_t* r, double* out_host, int64_t first, int64_t n, rmc_stream_t s) {
+  if (!r || !r->prioritized || first < 0 || n < 0 || first + n > r->n_nodes) return fail(RMC_ERR_ARG, "rmc_replay_read_tree_sync: range");
+  if (int32_t e = use_device(r->device)) return e;
+  RMC_CUDA(cudaMemcpyAsync(out_host, r->dev.tree + first, static_cast<size_t>(n) * sizeof(double), cudaMemcpyDeviceToHost, as_stream(s)));
+  RMC_CUDA(cudaStreamSynchronize(as_stream(s)));
+  return RMC_OK;
+}
+extern "C" int32_t rmc_replay_read_rows_sync(rmc_replay_t* r, float* out_host, int64_t first_slot, int64_t n, rmc_stream_t s) {
+  if (!r || first_slot < 0 || n < 0 || first_slot + n > r->cap) return fail(RMC_ERR_ARG, "rmc_replay_read_rows_sync: range");
+  if (int32_t e = use_device(r->device)) return e;
+  RMC_CUDA(cudaMemcpyAsync(out_host, r->dev.ring + first_slot * r->rf, static_cast<size_t>(n) * r->rf * sizeof(float),
+                           cudaMemcpyDeviceToHost, as_stream(s)));
+  RMC_CUDA(cudaStreamSynchronize(as_stream(s)));
+  return RMC_OK;
+}
+
+extern "C" int32_t rmc_per_sample(rmc_replay_t* r, int64_t batch, double beta, const double* u_dev, uint64_t seed, uint64_t counter,
+                                  int64_t* out_nodes_dev, float* out_is_w_dev, float* out_rows_dev, rmc_stream_t s) {
+  if (!r || !r->prioritized || batch < 1 || !out_nodes_dev) return fail(RMC_ERR_ARG, "rmc_per_sample: bad args");
+  if (r->size < 1) return fail(RMC_ERR_STATE, "rmc_per_sample: empty replay");
+  if (int32_t e = use_device(r->device)) return e;
+  k_per_sample<<<blocks_for(batch, kWarps), kThreads, 0, as_stream(s)>>>(r->dev, batch, batch, 0, beta, u_dev, seed, counter, 0u,
+                                                                        reinterpret_cast<long long*>(out_nodes_dev), out_is_w_dev,
+                                                                        out_rows_dev);
+  RMC_KERNEL_OK();
+  return RMC_OK;
+}
+
+extern "C" int32_t rmc_tree_get_leaf(rmc_replay_t* r, const double* v_dev, int64_t n, int64_t* out_nodes_dev, double* out_pri_dev,
+                                     rmc_stream_t s) {
+  if (!r || !r->prioritized || n < 1 || !v_dev || !out_nodes_dev) return fail(RMC_ERR_ARG, "rmc_tree_get_leaf: bad args");
+  if (int32_t e = use_device(r->device)) return e;
+  k_tree_get_leaf<<<blocks_for(n, kWarps), kThreads, 0, as_stream(s)>>>(r->dev, v_dev, n, reinterpret_cast<long long*>(out_nodes_dev), out_pri_dev);
+  RMC_KERNEL_OK();
+  return RMC_OK;
+}
+
+extern "C" int32_t rmc_uniform_sample(rmc_replay_t* r, int64_t batch, const int64_t* idx_dev, uint64_t seed, uint64_t counter,
+                                      int64_t* out_slots_dev, float* out_rows_dev, rmc_stream_t s) {
+  if (!r || batch < 1 || !out_slots_dev) return fail(RMC_ERR_ARG, "rmc_uniform_sample: bad args");
+  if (r->size < batch) return fail(RMC_ERR_STATE, "rmc_uniform_sample: sample larger than population");
+  if (int32_t e = use_device(r->device)) return e;
+  k_uniform_sample<<<blocks_for(batch, kWarps), kThreads, 0, as_stream(s)>>>(r->dev, batch, reinterpret_cast<const long long*>(idx_dev),
+                                                                            seed, counter, 0u,
+                                                                            reinterpret_cast<long long*>(out_slots_dev), out_rows_dev);
+  RMC_KERNEL_OK();
+  return RMC_OK;
+}
+
+static int32_t tree_update_large(rmc_replay* r, const long long* nodes, const float* pri, long long n, bool stamps_done, cudaStream_t st) {
+  if (!stamps_done) {
+    k_tree_stamp<<<blocks_for(n, 256), 256, 0, st>>>(r->dev, nodes, n);
+    RMC_KERNEL_OK();
+  }
+  k_tree_apply<<<blocks_for(n, 256), 256, 0, st>>>(r->dev, nodes, pri, n);
+  RMC_KERNEL_OK();
+  return minmax_rebuild(r, st);
+}
+
+extern "C" int32_t rmc_per_update_from_td(rmc_replay_t* r, const int64_t* nodes_dev, const float* abs_td_dev, int64_t batch, float eps,
+                                          float alpha, float pmax, float* out_pri_dev, rmc_stream_t s) {
+  if (!r || !r->prioritized || batch < 1 || !nodes_dev || !abs_td_dev) return fail(RMC_ERR_ARG, "rmc_per_update_from_td: bad args");
+  if (int32_t e = use_device(r->device)) return e;
+  cudaStream_t st = as_stream(s);
+  const long long* nodes = reinterpret_cast<const long long*>(nodes_dev);
+  if (batch <= kTreeCtaMax) {
+    float* pri = out_pri_dev ? out_pri_dev : r->scratch_pri;
+    k_tree_update_small<<<1, kThreads, 0, st>>>(r->dev, nodes, nullptr, abs_td_dev, pri, batch, eps, alpha, pmax);
+    RMC_KERNEL_OK();
+    return RMC_OK;
+  }
+  if (!out_pri_dev) return fail(RMC_ERR_ARG, "rmc_per_update_from_td: out_pri_dev required for batch > 4096");
+  k_td_to_pri<<<blocks_for(batch, 256), 256, 0, st>>>(abs_td_dev, out_pri_dev, batch, eps, alpha, pmax);
+  RMC_KERNEL_OK();
+  return tree_update_large(r, nodes, out_pri_dev, batch, false, st);
+}
+
+extern "C" int32_t rmc_per_update(rmc_replay_t* r, const int64_t* nodes_dev, const float* pri_dev, int64_t batch, rmc_stream_t s) {
+  if (!r || !r->prioritized || batch < 1 || !nodes_dev || !pri_dev) return fail(RMC_ERR_ARG, "rmc_per_update: bad args");
+  if (int32_t e = use_device(r->device)) return e;
+  cudaStream_t st = as_stream(s);
+  const long long* nodes = reinterpret_cast<const long long*>(nodes_dev);
+  if (batch <= kTreeCtaMax) {
+    k_tree_update_small<<<1, kThreads, 0, st>>>(r->dev, nodes, pri_dev, nullptr, nullptr, batch, 0.f, 0.f, 0.f);
+    RMC_KERNEL_OK();
+    return RMC_OK;
+  }
+  return tree_update_large(r, nodes, pri_dev, batch, false, st);
+}
+
+// ------------------------------------------------------------------------------ learner
+static NetLayout make_layout(const rmc_net_spec_t& sp) {
+  NetLayout L{};
+  L.D = sp.obs_dim; L.A = sp.n_actions; L.dueling = sp.dueling ? 1 : 0;
+  L.NH = L.dueling ? L.A + 1 : L.A;
+  int o = 0;
+  L.off_w0t = o; o += L.D * kH1;
+  L.off_b0 = o; o += kH1;
+  L.off_w2t = o; o += kH1 * kW2LD;
+  L.off_b2 = o; o += kH2;
+  L.off_wh = o; o += L.NH * kH2;
+  L.off_bh = o; o += round4(L.NH);
+  L.total = o;
+  return L;
+}
+
+static std::vector<int> make_param_map(const NetLayout& L) {
+  std::vector<int> m;
+  for (int i = 0; i < kH1; ++i) for (int d = 0; d < L.D; ++d) m.push_back(L.off_w0t + d * kH1 + i);   // net.0.weight [H1][D]
+  for (int i = 0; i < kH1; ++i) m.push_back(L.off_b0 + i);                                              // net.0.bias
+  for (int j = 0; j < kH2; ++j) for (int k = 0; k < kH1; ++k) m.push_back(L.off_w2t + k * kW2LD + j);  // net.2.weight [H2][H1]
+  for (int j = 0; j < kH2; ++j) m.push_back(L.off_b2 + j);                                              // net.2.bias
+  if (L.dueling) {
+    for (int j = 0; j < kH2; ++j) m.push_back(L.off_wh + j);                                            // fc_val.weight [1][H2]
+    m.push_back(L.off_bh);                                                                              // fc_val.bias
+    for (int a = 0; a < L.A; ++a) for (int j = 0; j < kH2; ++j) m.push_back(L.off_wh + (1 + a) * kH2 + j);   // fc_adv.weight
+    for (int a = 0; a < L.A; ++a) m.push_back(L.off_bh + 1 + a);                                        // fc_adv.bias
+  } else {
+    for (int a = 0; a < L.A; ++a) for (int j = 0; j < kH2; ++j) m.push_back(L.off_wh + a * kH2 + j);   // fc_out.weight
+    for (int a = 0; a < L.A; ++a) m.push_back(L.off_bh + a);                                            // fc_out.bias
+  }
+  return m;
+}
+
+template <typename T>
+static int32_t owned_alloc(rmc_learner* l, T** p, size_t count) {
+  if (int32_t e = dev_alloc(p, count)) return e;
+  l->owned.push_back(*p);
+  return RMC_OK;
+}
+
+extern "C" int32_t rmc_learner_create(rmc_learner_t** out, const rmc_net_spec_t* spec, const rmc_hyper_t* hyper, int64_t max_batch,
+                                      int32_t device) {
+  if (!out || !spec || !hyper || max_batch < 1) return fail(RMC_ERR_ARG, "rmc_learner_create: null/bad args");
+  if (spec->hidden1 != kH1 || spec->hidden2 != kH2)
+    return fail(RMC_ERR_UNSUPPORTED, "rmc_learner_create: only the macro MLP body 256-128 is built (no fallback path)");
+  if (spec->activation != RMC_ACT_RELU) return fail(RMC_ERR_UNSUPPORTED, "rmc_learner_create: only ReLU bodies are built");
+  if (spec->obs_dim < 1 || spec->obs_dim > kMaxD || spec->n_actions < 1 || spec->n_actions > 15)
+    return fail(RMC_ERR_UNSUPPORTED, "rmc_learner_create: obs_dim must be 1..32 and n_actions 1..15");
+  if (int32_t e = use_device(device)) return e;
+  auto* l = new rmc_learner();
+  l->device = device;
+  l->spec = *spec;
+  l->hyper = *hyper;
+  l->L = make_layout(*spec);
+  l->max_batch = max_batch;
+  l->rf = round4(2 * spec->obs_dim + 3);
+  RMC_CUDA(cudaDeviceGetAttribute(&l->num_sms, cudaDevAttrMultiProcessorCount, device));
+  const SmemPlan plan = make_smem_plan(l->L.total);
+  l->smem_bytes = std::max(plan.total_floats, kGemmSmemFloats) * 4;
+  int max_optin = 0;
+  RMC_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+  if (l->smem_bytes > max_optin) return fail(RMC_ERR_UNSUPPORTED, "rmc_learner_create: parameter blob does not fit shared memory");
+  RMC_CUDA(cudaFuncSetAttribute(k_learner_step, cudaFuncAttributeMaxDynamicSharedMemorySize, l->smem_bytes));
+  RMC_CUDA(cudaFuncSetAttribute(k_mlp_infer, cudaFuncAttributeMaxDynamicSharedMemorySize, l->smem_bytes));
+  const std::vector<int> map = make_param_map(l->L);
+  l->P = static_cast<long long>(map.size());
+  int32_t e = RMC_OK;
+  for (int k = 0; k < 5; ++k)
+    if ((e = owned_alloc(l, &l->blobs[k], static_cast<size_t>(l->L.total)))) return e;
+  if ((e = owned_alloc(l, &l->map, map.size()))) return e;
+  RMC_CUDA(cudaMemcpy(l->map, map.data(), map.size() * sizeof(int), cudaMemcpyHostToDevice));
+  if ((e = owned_alloc(l, &l->io, map.size()))) return e;
+  AgentCtx& c = l->ctx;
+  c.L = l->L;
+  c.online = l->blobs[0]; c.target = l->blobs[1]; c.adam_m = l->blobs[2]; c.adam_v = l->blobs[3]; c.grads = l->blobs[4];
+  const size_t B = static_cast<size_t>(max_batch);
+  if ((e = owned_alloc(l, &c.nodes, B))) return e;
+  float** per_sample[] = {&c.is_w, &c.q_sa, &c.y, &c.abs_td, &c.hub, &c.pri, &c.gcoef};
+  for (float** p : per_sample)
+    if ((e = owned_alloc(l, p, B))) return e;
+  if ((e = owned_alloc(l, &c.QT, B * kQLD))) return e;
+  if ((e = owned_alloc(l, &c.QN, B * kQLD))) return e;
+  if ((e = owned_alloc(l, &c.Q, B * kQLD))) return e;
+  if ((e = owned_alloc(l, &c.X, B * l->rf))) return e;
+  if ((e = owned_alloc(l, &c.H1, B * kH1))) return e;
+  if ((e = owned_alloc(l, &c.DZ1, B * kH1))) return e;
+  if ((e = owned_alloc(l, &c.H2, B * kH2))) return e;
+  if ((e = owned_alloc(l, &c.DZ2, B * kH2))) return e;
+  if ((e = owned_alloc(l, &c.DH, B * kQLD))) return e;
+  if ((e = owned_alloc(l, &c.loss_part, 1024))) return e;
+  if ((e = owned_alloc(l, &c.loss, 1))) return e;
+  if ((e = owned_alloc(l, &c.barrier, 1))) return e;
+  RMC_CUDA(cudaDeviceSynchronize());
+  *out = l;
+  return RMC_OK;
+}
+
+extern "C" int32_t rmc_learner_destroy(rmc_learner_t* l) {
+  if (!l) return RMC_OK;
+  cudaSetDevice(l->device);
+  cudaDeviceSynchronize();
+  for (void* p : l->owned) cudaFree(p);
+  if (l->act_pin_obs) cudaFreeHost(l->act_pin_obs);
+  if (l->act_pin_out) cudaFreeHost(l->act_pin_out);
+  cudaFree(l->act_dev_obs);
+  cudaFree(l->act_dev_out);
+  delete l;
+  return RMC_OK;
+}
+
+extern "C" int64_t rmc_learner_param_count(const rmc_learner_t* l) { return l ? l->P : 0; }
+
+extern "C" int32_t rmc_learner_set_hyper(rmc_learner_t* l, const rmc_hyper_t* hyper) {
+  if (!l || !hyper) return fail(RMC_ERR_ARG, "rmc_learner_set_hyper: null");
+  l->hyper = *hyper;
+  return RMC_OK;
+}
+
+extern "C" int32_t rmc_learner_set_params(rmc_learner_t* l, int32_t kind, const float* src, int64_t n, int32_t src_is_host, rmc_stream_t s) {
+  if (!l || kind < 0 || kind > 4 || !src || n != l->P) return fail(RMC_ERR_ARG, "rmc_learner_set_params: bad kind/size");
+  if (int32_t e = use_device(l->device)) return e;
+  cudaStream_t st = as_stream(s);
+  const float* dsrc = src;
+  if (src_is_host) {
+    RMC_CUDA(cudaMemcpyAsync(l->io, src, static_cast<size_t>(n) * sizeof(float), cudaMemcpyHostToDevice, st));
+    dsrc = l->io;
+  }
+  k_params_scatter<<<blocks_for(n, 256), 256, 0, st>>>(l->blobs[kind], dsrc, l->map, n);
+  RMC_KERNEL_OK();
+  if (src_is_host) RMC_CUDA(cudaStreamSynchronize(st));
+  return RMC_OK;
+}
+
+extern "C" int32_t rmc_learner_get_params(rmc_learner_t* l, int32_t kind, float* dst, int64_t n, int32_t dst_is_host, rmc_stream_t s) {
+  if (!l || kind < 0 || kind > 4 || !dst || n != l->P) return fail(RMC_ERR_ARG, "rmc_learner_get_params: bad kind/size");
+  if (int32_t e = use_device(l->device)) return e;
+  cudaStream_t st = as_stream(s);
+  float* ddst = dst_is_host ? l->io : dst;
+  k_params_gather<<<blocks_for(n, 256), 256, 0, st>>>(ddst, l->blobs[kind], l->map, n);
+  RMC_KERNEL_OK();
+  if (dst_is_host) {
+    RMC_CUDA(cudaMemcpyAsync(dst, l->io, static_cast<size_t>(n) * sizeof(float), cudaMemcpyDeviceToHost, st));
+    RMC_CUDA(cudaStreamSynchronize(st));
+  }
+  return RMC_OK;
+}
+
+static int32_t fill_scalars(const rmc_learner* l, const rmc_step_args_t* a, StepScalars* S) {
+  const rmc_hyper_t& h = l->hyper;
+  std::memset(S, 0, sizeof(*S));
+  S->B = a->batch;
+  S->Bglobal = a->global_batch > 0 ? a->global_batch : a->batch;
+  S->shard_off = a->shard_offset;
+  S->phases = a->phases;
+  S->double_dqn = l->spec.double_dqn;
+  S->prioritized = l->spec.prioritized;
+  S->beta = a->per_beta;
+  S->u = a->u_dev;
+  S->idx = reinterpret_cast<const long long*>(a->idx_dev);
+  S->seed = a->seed;
+  S->counter = a->counter;
+  S->grads_in = a->grads_in_dev;
+  S->gamma = static_cast<float>(h.gamma);
+  if (a->phases & RMC_PH_ADAM) {
+    if (a->adam_t < 1) return fail(RMC_ERR_ARG, "rmc_learner_step: adam_t must be >= 1");
+    // torch/optim/adam.py (_single_tensor_adam): python-float bias corrections
+    const double t = static_cast<double>(a->adam_t);
+    const double bc1 = 1.0 - std::pow(h.adam_beta1, t);
+    const double bc2 = 1.0 - std::pow(h.adam_beta2, t);
+    const double step_size = h.lr / bc1;
+    const double bc2_sqrt = std::pow(bc2, 0.5);
+    S->adam_w1 = static_cast<float>(1.0 - h.adam_beta1);
+    S->adam_b2 = static_cast<float>(h.adam_beta2);
+    S->adam_w2 = static_cast<float>(1.0 - h.adam_beta2);
+    S->adam_neg_step = static_cast<float>(-step_size);
+    S->adam_bc2_sqrt = static_cast<float>(bc2_sqrt);
+    S->adam_eps = static_cast<float>(h.adam_eps);
+  }
+  S->polyak_k = static_cast<float>(h.polyak_k);
+  S->polyak_1mk = static_cast<float>(1.0 - h.polyak_k);
+  S->per_eps = static_cast<float>(h.per_eps);
+  S->per_alpha = static_cast<float>(h.per_alpha);
+  S->per_pmax = static_cast<float>(h.per_pmax);
+  return RMC_OK;
+}
+
+static int32_t check_step(const rmc_learner* l, const rmc_replay* r, const rmc_step_args_t* a) {
+  if (!l || !r || !a) return fail(RMC_ERR_ARG, "rmc_learner_step: null");
+  if (a->batch < 1 || a->batch > l->max_batch) return fail(RMC_ERR_ARG, "rmc_learner_step: batch outside [1, max_batch]");
+  if (r->D != l->spec.obs_dim) return fail(RMC_ERR_ARG, "rmc_learner_step: replay obs_dim differs from the learner's");
+  if ((l->spec.prioritized != 0) != (r->prioritized != 0))
+    return fail(RMC_ERR_ARG, "rmc_learner_step: prioritized learner needs a prioritized replay (and vice versa)");
+  if (r->device != l->device) return fail(RMC_ERR_ARG, "rmc_learner_step: replay and learner on different devices");
+  if (a->phases & RMC_PH_SAMPLE) {
+    if (r->size < 1) return fail(RMC_ERR_STATE, "rmc_learner_step: empty replay");
+    if (!r->prioritized && a->batch > r->size && a->idx_dev == nullptr)
+      return fail(RMC_ERR_STATE, "rmc_learner_step: sample larger than population");
+  }
+  return RMC_OK;
+}
+
+static int grid_for(const rmc_learner* l, long long B, int max_ctas) {
+  const long long n_tiles = (B + kTM - 1) / kTM;
+  const int want = static_cast<int>(std::min<long long>(max_ctas, std::max<long long>(n_tiles, 46)));
+  return std::max(1, std::min(want, max_ctas));
+}
+
+extern "C" int32_t rmc_learner_step(rmc_learner_t* l, rmc_replay_t* r, const rmc_step_args_t* a, rmc_stream_t s) {
+  if (int32_t e = check_step(l, r, a)) return e;
+  if (int32_t e = use_device(l->device)) return e;
+  cudaStream_t st = as_stream(s);
+  StepScalars S;
+  if (int32_t e = fill_scalars(l, a, &S)) return e;
+  l->ctx.rp = r->dev;
+  l->last_batch = a->batch;
+  const int G = grid_for(l, a->batch, l->num_sms);
+  const long long n_tiles = (a->batch + kTM - 1) / kTM;
+  S.n_row_ctas = static_cast<int>(std::min<long long>(G, n_tiles));
+  const bool rows = (a->phases & (RMC_PH_SAMPLE | RMC_PH_FORWARD)) != 0;
+  const bool phase_b = (a->phases & (RMC_PH_PRIORITY | RMC_PH_BACKWARD | RMC_PH_ADAM | RMC_PH_POLYAK | RMC_PH_HARDSYNC)) != 0;
+  if (rows && phase_b) S.barrier_target = l->barrier_count + static_cast<unsigned>(G);
+  AgentCtx single = l->ctx;
+  const AgentCtx* many = nullptr;
+  void* args[] = {&single, &many, &S};
+  RMC_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_learner_step), dim3(G, 1, 1), dim3(kThreads, 1, 1), args,
+                                       static_cast<size_t>(l->smem_bytes), st));
+  if (rows && phase_b) l->barrier_count = S.barrier_target;
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if ((a->phases & RMC_PH_PRIORITY) && l->spec.prioritized && a->batch > kTreeCtaMax) {
+    if (int32_t e = tree_update_large(r, l->ctx.nodes, l->ctx.pri, a->batch, true, st)) return e;
+  }
+  return RMC_OK;
+}
+
+extern "C" int32_t rmc_learner_output(rmc_learner_t* l, const char* name, void** dev_ptr, int64_t* n_elems) {
+  if (!l || !name || !dev_ptr || !n_elems) return fail(RMC_ERR_ARG, "rmc_learner_output: null");
+  const AgentCtx& c = l->ctx;
+  const long long B = l->last_batch;
+  struct Ent { const char* n; void* p; long long cnt; };
+  const Ent table[] = {{"nodes", c.nodes, B}, {"is_w", c.is_w, B}, {"q_sa", c.q_sa, B}, {"y", c.y, B}, {"abs_td", c.abs_td, B},
+                       {"huber", c.hub, B}, {"pri", c.pri, B}, {"gcoef", c.gcoef, B}, {"loss", c.loss, 1},
+                       {"q_next_tgt", c.QT, B * kQLD}, {"q_next_on", c.QN, B * kQLD}, {"q", c.Q, B * kQLD},
+                       {"rows", c.X, B * l->rf}, {"h1", c.H1, B * kH1}, {"h2", c.H2, B * kH2}, {"dz1", c.DZ1, B * kH1},
+                       {"dz2", c.DZ2, B * kH2}, {"dh", c.DH, B * kQLD}};
+  for (const Ent& e : table)
+    if (std::strcmp(e.n, name) == 0) {
+      *dev_ptr = e.p;
+      *n_elems = e.cnt;
+      return RMC_OK;
+    }
+  return fail(RMC_ERR_ARG, std::string("rmc_learner_output: unknown output ") + name);
+}
+
+extern "C" int32_t rmc_learner_loss_sync(rmc_learner_t* l, float* out_host, rmc_stream_t s) {
+  if (!l || !out_host) return fail(RMC_ERR_ARG, "rmc_learner_loss_sync: null");
+  if (int32_t e = use_device(l->device)) return e;
+  RMC_CUDA(cudaMemcpyAsync(out_host, l->ctx.loss, sizeof(float), cudaMemcpyDeviceToHost, as_stream(s)));
+  RMC_CUDA(cudaStreamSynchronize(as_stream(s)));
+  return RMC_OK;
+}
+
+static int32_t infer_launch(rmc_learner* l, const float* params, const float* obs_dev, long long n, long long* actions, float* q, int mode,
+                            cudaStream_t st) {
+  const long long n_tiles = (n + kR - 1) / kR;
+  const unsigned grid = static_cast<unsigned>(std::min<long long>(n_tiles, l->num_sms));
+  k_mlp_infer<<<grid, kThreads, static_cast<size_t>(l->smem_bytes), st>>>(l->L, params, obs_dev, n, actions, q, mode);
+  RMC_KERNEL_OK();
+  return RMC_OK;
+}
+
+extern "C" int32_t rmc_learner_q_values(rmc_learner_t* l, int32_t which, const float* obs_dev, int64_t n, float* q_out_dev, rmc_stream_t s) {
+  if (!l || !obs_dev || !q_out_dev || n < 1 || (which != RMC_ONLINE && which != RMC_TARGET)) return fail(RMC_ERR_ARG, "rmc_learner_q_values: bad args");
+  if (int32_t e = use_device(l->device)) return e;
+  return infer_launch(l, l->blobs[which], obs_dev, n, nullptr, q_out_dev, 1, as_stream(s));
+}
+
+extern "C" int32_t rmc_learner_act(rmc_learner_t* l, const float* obs_dev, int64_t n, int64_t* actions_dev, rmc_stream_t s) {
+  if (!l || !obs_dev || !actions_dev || n < 1) return fail(RMC_ERR_ARG, "rmc_learner_act: bad args");
+  if (int32_t e = use_device(l->device)) return e;
+  return infer_launch(l, l->blobs[RMC_ONLINE], obs_dev, n, reinterpret_cast<long long*>(actions_dev), nullptr, 0, as_stream(s));
+}
+
+extern "C" int32_t rmc_learner_act_host_sync(rmc_learner_t* l, const float* obs_host, int64_t n, int64_t* actions_host, rmc_stream_t s) {
+  if (!l || !obs_host || !actions_host || n < 1) return fail(RMC_ERR_ARG, "rmc_learner_act_host_sync: bad args");
+  if (int32_t e = use_device(l->device)) return e;
+  cudaStream_t st = as_stream(s);
+  if (n > l->act_cap) {
+    RMC_CUDA(cudaStreamSynchronize(st));
+    if (l->act_pin_obs) cudaFreeHost(l->act_pin_obs);
+    if (l->act_pin_out) cudaFreeHost(l->act_pin_out);
+    cudaFree(l->act_dev_obs);
+    cudaFree(l->act_dev_out);
+    const long long cap = std::max<long long>(n, 1024);
+    RMC_CUDA(cudaMallocHost(reinterpret_cast<void**>(&l->act_pin_obs), static_cast<size_t>(cap) * l->L.D * sizeof(float)));
+    RMC_CUDA(cudaMallocHost(reinterpret_cast<void**>(&l->act_pin_out), static_cast<size_t>(cap) * sizeof(long long)));
+    RMC_CUDA(cudaMalloc(reinterpret_cast<void**>(&l->act_dev_obs), static_cast<size_t>(cap) * l->L.D * sizeof(float)));
+    RMC_CUDA(cudaMalloc(reinterpret_cast<void**>(&l->act_dev_out), static_cast<size_t>(cap) * sizeof(long long)));
+    l->act_cap = cap;
+  }
+  std::memcpy(l->act_pin_obs, obs_host, static_cast<size_t>(n) * l->L.D * sizeof(float));
+  RMC_CUDA(cudaMemcpyAsync(l->act_dev_obs, l->act_pin_obs, static_cast<size_t>(n) * l->L.D * sizeof(float), cudaMemcpyHostToDevice, st));
+  if (int32_t e = infer_launch(l, l->blobs[RMC_ONLINE], l->act_dev_obs, n, l->act_dev_out, nullptr, 0, st)) return e;
+  RMC_CUDA(cudaMemcpyAsync(l->act_pin_out, l->act_dev_out, static_cast<size_t>(n) * sizeof(long long), cudaMemcpyDeviceToHost, st));
+  RMC_CUDA(cudaStreamSynchronize(st));
+  std::memcpy(actions_host, l->act_pin_out, static_cast<size_t>(n) * sizeof(long long));
+  return RMC_OK;
+}
+
+// ------------------------------------------------------------------------------ groups (ensembles)
+extern "C" int32_t rmc_group_create(rmc_group_t** out, rmc_learner_t* const* learners, rmc_replay_t* const* replays, int32_t n_agents) {
+  if (!out || !learners || !replays || n_agents < 1) return fail(RMC_ERR_ARG, "rmc_group_create: bad args");
+  rmc_learner* l0 = learners[0];
+  if (n_agents > l0->num_sms) return fail(RMC_ERR_ARG, "rmc_group_create: more agents than SMs");
+  for (int i = 0; i < n_agents; ++i) {
+    rmc_learner* l = learners[i];
+    rmc_replay* r = replays[i];
+    if (!l || !r) return fail(RMC_ERR_ARG, "rmc_group_create: null member");
+    if (std::memcmp(&l->spec, &l0->spec, sizeof(rmc_net_spec_t)) != 0 || l->max_batch != l0->max_batch || l->device != l0->device)
+      return fail(RMC_ERR_ARG, "rmc_group_create: members must share spec, max_batch and device");
+    if (r->D != l->spec.obs_dim || (r->prioritized != 0) != (l->spec.prioritized != 0) || r->device != l->device)
+      return fail(RMC_ERR_ARG, "rmc_group_create: replay/learner mismatch");
+  }
+  if (int32_t e = use_device(l0->device)) return e;
+  auto* g = new rmc_group();
+  g->n = n_agents;
+  g->learners.assign(learners, learners + n_agents);
+  g->replays.assign(replays, replays + n_agents);
+  int32_t e = RMC_OK;
+  if ((e = dev_alloc(&g->ctx_dev, static_cast<size_t>(n_agents), false))) return e;
+  if ((e = dev_alloc(&g->barriers, static_cast<size_t>(n_agents)))) return e;
+  std::vector<AgentCtx> h(n_agents);
+  for (int i = 0; i < n_agents; ++i) {
+    h[i] = learners[i]->ctx;
+    h[i].rp = replays[i]->dev;
+    h[i].barrier = g->barriers + i;
+  }
+  RMC_CUDA(cudaMemcpy(g->ctx_dev, h.data(), sizeof(AgentCtx) * n_agents, cudaMemcpyHostToDevice));
+  *out = g;
+  return RMC_OK;
+}
+
+extern "C" int32_t rmc_group_destroy(rmc_group_t* g) {
+  if (!g) return RMC_OK;
+  cudaSetDevice(g->learners[0]->device);
+  cudaDeviceSynchronize();
+  cudaFree(g->ctx_dev);
+  cudaFree(g->barriers);
+  delete g;
+  return RMC_OK;
+}
+
+extern "C" int32_t rmc_group_step(rmc_group_t* g, const rmc_step_args_t* a, rmc_stream_t s) {
+  if (!g || !a) return fail(RMC_ERR_ARG, "rmc_group_step: null");
+  rmc_learner* l0 = g->learners[0];
+  for (int i = 0; i < g->n; ++i)
+    if (int32_t e = check_step(g->learners[i], g->replays[i], a)) return e;
+  if (a->batch > kTreeCtaMax && l0->spec.prioritized && (a->phases & RMC_PH_PRIORITY))
+    return fail(RMC_ERR_UNSUPPORTED, "rmc_group_step: PER batches above 4096 are stepped per agent");
+  if (int32_t e = use_device(l0->device)) return e;
+  cudaStream_t st = as_stream(s);
+  StepScalars S;
+  if (int32_t e = fill_scalars(l0, a, &S)) return e;
+  const int per_agent_max = std::max(1, l0->num_sms / g->n);
+  const int G = grid_for(l0, a->batch, per_agent_max);
+  const long long n_tiles = (a->batch + kTM - 1) / kTM;
+  S.n_row_ctas = static_cast<int>(std::min<long long>(G, n_tiles));
+  const bool rows = (a->phases & (RMC_PH_SAMPLE | RMC_PH_FORWARD)) != 0;
+  const bool phase_b = (a->phases & (RMC_PH_PRIORITY | RMC_PH_BACKWARD | RMC_PH_ADAM | RMC_PH_POLYAK | RMC_PH_HARDSYNC)) != 0;
+  if (rows && phase_b) S.barrier_target = g->barrier_count + static_cast<unsigned>(G);
+  for (int i = 0; i < g->n; ++i) g->learners[i]->last_batch = a->batch;
+  AgentCtx single = l0->ctx;
+  const AgentCtx* many = g->ctx_dev;
+  void* args[] = {&single, &many, &S};
+  RMC_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_learner_step), dim3(G, g->n, 1), dim3(kThreads, 1, 1), args,
+                                       static_cast<size_t>(l0->smem_bytes), st));
+  if (rows && phase_b) g->barrier_count = S.barrier_target;
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return RMC_OK;
+}

@@ -1,0 +1,203 @@
+// rmc_device.cuh -- device-side building blocks shared by the kernels of librmc_b200.
+// sm_100a only.  Compiled with -fmad=false: every FMA in this library is an explicit fmaf()
+// so that the parity-critical scalar arithmetic (sampling values, TD target, Adam, Polyak)
+// rounds exactly like the reference's un-fused numpy / ATen-CPU expressions.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace rmc {
+
+constexpr int kH1 = 256;        // hidden1 (macro network_config)
+constexpr int kH2 = 128;        // hidden2
+constexpr int kW2LD = 132;      // padded leading dim of W2^T rows: conflict-free for both fwd and dgrad
+constexpr int kTM = 4;          // batch rows per row-tile (online pass runs 2*kTM rows: s' and s)
+constexpr int kR = 2 * kTM;     // rows held per tile in shared memory
+constexpr int kThreads = 256;
+constexpr int kWarps = 8;
+constexpr int kMaxD = 32;
+constexpr int kMaxRowFloats = 68;   // round4(2*32+3)
+constexpr int kQLD = 16;        // leading dim of per-sample Q rows (A <= 15, heads <= 16)
+constexpr int kBlk = 64;        // fan-in of the two min/max summary levels over the leaves
+constexpr int kTreeCtaMax = 4096;  // batches up to this size get their tree write-back from one CTA
+
+// ----------------------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+// TMA bulk copy global -> shared (1-D, no tensor map), completion signalled on an mbarrier.
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_u32(const unsigned* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Barrier across the CTAs of one agent inside ONE cooperative launch (all CTAs co-resident).
+// `ctr` only ever grows; `target` = value it must reach (wrap-safe signed comparison).
+__device__ __forceinline__ void agent_barrier(unsigned* ctr, unsigned target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(ctr, 1u);
+    while (static_cast<int>(ld_acquire_u32(ctr) - target) < 0) {
+      __nanosleep(32);
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// ----------------------------------------------------------------------------- Philox4x32-10
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
+    uint32_t hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += W0;
+    k.y += W1;
+  }
+  return c;
+}
+// uniform double in [0,1) with 53 random bits
+__device__ __forceinline__ double philox_uniform(uint64_t seed, uint64_t counter, uint32_t agent, uint32_t i) {
+  uint4 c = make_uint4(i, agent, static_cast<uint32_t>(counter), static_cast<uint32_t>(counter >> 32));
+  uint2 k = make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+  uint4 r = philox4x32_10(c, k);
+  uint64_t bits = ((static_cast<uint64_t>(r.x) << 32) | r.y) >> 11;
+  return static_cast<double>(bits) * (1.0 / 9007199254740992.0);
+}
+// Keyed bijection on [0, n): balanced Feistel over the next even power of two + cycle walking.
+// Gives `batch` DISTINCT positions for i = 0..batch-1 (sampling without replacement).
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+  return x;
+}
+__device__ __forceinline__ uint64_t feistel_perm(uint64_t i, uint64_t n, uint64_t seed, uint64_t counter, uint32_t agent) {
+  int bits = 2;
+  while ((1ull << bits) < n) bits += 2;   // even number of bits
+  const int half = bits / 2;
+  const uint32_t mask = (1u << half) - 1u;
+  const uint32_t k0 = mix32(static_cast<uint32_t>(seed) ^ 0x9E3779B9u) ^ mix32(static_cast<uint32_t>(counter) + agent * 0x85ebca6bu);
+  const uint32_t k1 = mix32(static_cast<uint32_t>(seed >> 32) + 0x632BE5ABu) ^ mix32(static_cast<uint32_t>(counter >> 32) ^ 0xc2b2ae35u);
+  uint64_t x = i;
+  do {
+    uint32_t l = static_cast<uint32_t>(x >> half) & mask, r = static_cast<uint32_t>(x) & mask;
+#pragma unroll
+    for (int rd = 0; rd < 4; ++rd) {
+      uint32_t f = mix32(r ^ (rd & 1 ? k1 : k0) ^ (0x27d4eb2fu * (rd + 1))) & mask;
+      uint32_t nl = r;
+      r = l ^ f;
+      l = nl;
+    }
+    x = (static_cast<uint64_t>(l) << half) | r;
+  } while (x >= n);
+  return x;
+}
+
+// ----------------------------------------------------------------------------- data structs
+struct ReplayState {   // lives in HBM, updated by the kernels themselves
+  long long size;
+  long long dp;
+  float max_p;       // max(leaves[:size])  (0 when empty)
+  float min_p;       // min(leaves[:size])  (+inf when empty)
+  float push_p;      // priority given to the rows of the current (chunked) push call
+  int pad;
+};
+
+struct ReplayDev {
+  float* ring;       // [cap][row_floats]
+  double* tree;      // [2*cap-1]  reference heap layout (dqn/utils/sum_tree.py:6-13)
+  int* stamps;       // [cap]   last-writer election for duplicate leaves in a batch
+  float* b0min;      // [n0] min / max over blocks of kBlk leaves (only leaves < size)
+  float* b0max;
+  float* b1min;      // [n1] min / max over blocks of kBlk level-0 entries
+  float* b1max;
+  ReplayState* st;
+  long long cap;
+  long long n0, n1;
+  int row_floats;
+  int obs_dim;
+  int prioritized;
+  int pad;
+};
+
+struct NetLayout {     // float offsets inside one parameter blob (device layout)
+  int D, A, NH, dueling;
+  int off_w0t, off_b0, off_w2t, off_b2, off_wh, off_bh, total;   // total is a multiple of 4
+};
+
+struct AgentCtx {
+  ReplayDev rp;
+  NetLayout L;
+  float *online, *target, *adam_m, *adam_v, *grads;
+  // per-sample products of the last step
+  long long* nodes;     // [B] tree node (PER) or ring slot (uniform)
+  float *is_w, *q_sa, *y, *abs_td, *hub, *pri, *gcoef;
+  float *QT, *QN, *Q;   // [B][kQLD]  Q_target(s'), Q_online(s'), Q_online(s)
+  float *X;             // [B][row_floats] gathered rows
+  float *H1, *H2, *DZ1, *DZ2, *DH;   // saved activations / deltas of the s rows
+  float* loss_part;     // [n_tiles]
+  float* loss;          // [1]
+  unsigned* barrier;
+};
+
+struct StepScalars {
+  long long B;            // local batch
+  long long Bglobal;      // batch of the whole job (loss / gradient scale, stratified segments)
+  long long shard_off;    // global index of local sample 0
+  int phases;
+  int double_dqn;
+  int prioritized;        // learner flavour uses IS weights + write-back
+  int n_row_ctas;         // CTAs that own row tiles
+  unsigned barrier_target;  // counter value after the (single) A->B barrier
+  double beta;
+  const double* u;        // injected uniforms (agent-major) or nullptr
+  const long long* idx;   // injected positions or nullptr
+  unsigned long long seed, counter;
+  const float* grads_in;
+  float gamma;
+  float adam_w1;          // (float)(1 - beta1)
+  float adam_b2;          // (float)beta2
+  float adam_w2;          // (float)(1 - beta2)
+  float adam_neg_step;    // (float)(-(lr / (1 - beta1^t)))
+  float adam_bc2_sqrt;    // (float)sqrt(1 - beta2^t)
+  float adam_eps;
+  float polyak_k, polyak_1mk;
+  float per_eps, per_alpha, per_pmax;
+};
+
+}  // namespace rmc

@@ -1,0 +1,642 @@
+// rmc_mlp.cuh -- the fused learner-step kernel (one cooperative launch per step) and the
+// batched act / Q-value kernel for the macro-state MLP  D -> 256 -> ReLU -> 128 -> ReLU -> heads.
+//
+// Phase A (row parallel, CTAs own tiles of kTM batch rows):
+//     TMA bulk copy of the whole target / online parameter blob into shared memory,
+//     sample (PER prefix search or uniform) + coalesced row gather,
+//     Q_target(s'), then [Q_online(s'); Q_online(s)] in one 2*kTM-row pass,
+//     double-DQN target, |td|, Huber, priorities + last-writer stamps, and the dgrad chain
+//     (dQ -> dheads -> dh2 -> dz2 -> dz1); activations/deltas of the s rows go to L2-resident scratch.
+// ---- one agent-wide barrier ----
+// Phase B (parameter parallel): output-stationary weight-gradient tiles with a fixed summation
+//     order (deterministic), fused Adam (+ Polyak) on the owning CTA; the last CTA of a PER agent
+//     meanwhile applies the priority write-back to the sum tree.
+//
+// Arithmetic follows SURVEY.md Appendix A / dqn/agent.py:245-272, dqn/network.py:83,90-96 and
+// torch.optim.Adam (single-tensor path); fp32 FFMA accumulation only (no tensor cores here: the
+// 1e-5 parity bar needs fp32 accumulation and at B<=1024 the step is latency bound).
+#pragma once
+#include "rmc_device.cuh"
+#include "rmc_tree.cuh"
+
+namespace rmc {
+
+// ------------------------------------------------------------------ shared memory carve-up (floats)
+struct SmemPlan {
+  int w;        // parameter blob (L.total floats)
+  int xt;       // [kMaxD][kR]      x transposed
+  int h1t;      // [kH1][kR]        h1 transposed
+  int h2;       // [kR][kH2]
+  int part;     // [kWarps][kR][kH2] K-split partials of layer 2
+  int q;        // [kR][kQLD]
+  int dz2;      // [kTM][kH2]
+  int dh;       // [kTM][kQLD]
+  int meta;     // [kTM][4]  action(bits), reward, done, is_w
+  int red;      // [kWarps] loss partials
+  int bar;      // mbarrier (8 bytes, 8-byte aligned)
+  int total_floats;
+};
+__host__ __device__ inline SmemPlan make_smem_plan(int param_floats) {
+  SmemPlan s;
+  int o = 0;
+  s.w = o; o += param_floats;             // multiple of 4
+  s.xt = o; o += kMaxD * kR;
+  s.h1t = o; o += kH1 * kR;
+  s.h2 = o; o += kR * kH2;
+  s.part = o; o += kWarps * kR * kH2;
+  s.q = o; o += kR * kQLD;
+  s.dz2 = o; o += kTM * kH2;
+  s.dh = o; o += kTM * kQLD;
+  s.meta = o; o += kTM * 4;
+  s.red = o; o += kWarps;
+  o = (o + 3) & ~3;
+  s.bar = o; o += 4;
+  s.total_floats = o;
+  return s;
+}
+// phase-B staging (reuses the same dynamic shared memory)
+constexpr int kGChunk = 256;                         // batch rows staged per chunk
+constexpr int kGTile = 32;                           // 32 x 32 outputs per unit
+constexpr int kGemmSmemFloats = 2 * kGChunk * kGTile + kWarps * kGTile * kGTile + kWarps * kGTile;
+
+// ------------------------------------------------------------------ forward of R rows (R = 4 or 8)
+// sXT[d][kR], rows [0,R) are computed.  Results: sH1T[k][r], sH2[r][j], sQ[r][a] (Q values, or raw
+// head outputs when raw_heads: [0]=val, [1..A]=adv for dueling).
+template <int R>
+__device__ __forceinline__ void mlp_forward(const float* __restrict__ sW, const NetLayout& L, const float* __restrict__ sXT,
+                                            float* __restrict__ sH1T, float* __restrict__ sH2, float* __restrict__ sPart,
+                                            float* __restrict__ sQ, float* __restrict__ sRaw) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // ---- layer 1: thread i owns hidden unit i for all R rows
+  {
+    float acc[R];
+    const float b = sW[L.off_b0 + tid];
+#pragma unroll
+    for (int r = 0; r < R; ++r) acc[r] = b;
+    const float* w0t = sW + L.off_w0t + tid;
+    for (int d = 0; d < L.D; ++d) {
+      const float w = w0t[d * kH1];
+      const float4* xp = reinterpret_cast<const float4*>(sXT + d * kR);
+      const float4 x0 = xp[0];
+      acc[0] = fmaf(x0.x, w, acc[0]); acc[1] = fmaf(x0.y, w, acc[1]);
+      acc[2] = fmaf(x0.z, w, acc[2]); acc[3] = fmaf(x0.w, w, acc[3]);
+      if (R == 8) {
+        const float4 x1 = xp[1];
+        acc[4 % R] = fmaf(x1.x, w, acc[4 % R]); acc[5 % R] = fmaf(x1.y, w, acc[5 % R]);
+        acc[6 % R] = fmaf(x1.z, w, acc[6 % R]); acc[7 % R] = fmaf(x1.w, w, acc[7 % R]);
+      }
+    }
+    float4* hp = reinterpret_cast<float4*>(sH1T + tid * kR);
+    hp[0] = make_float4(fmaxf(acc[0], 0.f), fmaxf(acc[1], 0.f), fmaxf(acc[2], 0.f), fmaxf(acc[3], 0.f));
+    if (R == 8) hp[1] = make_float4(fmaxf(acc[4 % R], 0.f), fmaxf(acc[5 % R], 0.f), fmaxf(acc[6 % R], 0.f), fmaxf(acc[7 % R], 0.f));
+  }
+  __syncthreads();
+  // ---- layer 2, K split over the 8 warps (32 k each); lane owns 4 columns for all R rows
+  {
+    float acc[R][4];
+#pragma unroll
+    for (int r = 0; r < R; ++r) { acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.f; }
+    const float* w2 = sW + L.off_w2t + (warp * 32) * kW2LD + lane * 4;
+    const float* h1 = sH1T + (warp * 32) * kR;
+#pragma unroll 4
+    for (int k = 0; k < 32; ++k) {
+      const float4 w = *reinterpret_cast<const float4*>(w2 + k * kW2LD);
+      const float4 a0 = *reinterpret_cast<const float4*>(h1 + k * kR);
+      float a[R];
+      a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w;
+      if (R == 8) {
+        const float4 a1 = *reinterpret_cast<const float4*>(h1 + k * kR + 4);
+        a[4 % R] = a1.x; a[5 % R] = a1.y; a[6 % R] = a1.z; a[7 % R] = a1.w;
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        acc[r][0] = fmaf(a[r], w.x, acc[r][0]);
+        acc[r][1] = fmaf(a[r], w.y, acc[r][1]);
+        acc[r][2] = fmaf(a[r], w.z, acc[r][2]);
+        acc[r][3] = fmaf(a[r], w.w, acc[r][3]);
+      }
+    }
+    float* pp = sPart + (warp * kR) * kH2 + lane * 4;
+#pragma unroll
+    for (int r = 0; r < R; ++r) *reinterpret_cast<float4*>(pp + r * kH2) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+  }
+  __syncthreads();
+  // ---- reduce the 8 partials in fixed order, bias, ReLU -> sH2[r][j]
+  {
+    const int r = tid >> 5;            // 0..7
+    if (r < R) {
+      const int c = lane * 4;
+      float4 s = *reinterpret_cast<const float4*>(sW + L.off_b2 + c);
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) {
+        const float4 p = *reinterpret_cast<const float4*>(sPart + (w * kR + r) * kH2 + c);
+        s.x += p.x; s.y += p.y; s.z += p.z; s.w += p.w;
+      }
+      *reinterpret_cast<float4*>(sH2 + r * kH2 + c) = make_float4(fmaxf(s.x, 0.f), fmaxf(s.y, 0.f), fmaxf(s.z, 0.f), fmaxf(s.w, 0.f));
+    }
+  }
+  __syncthreads();
+  // ---- heads: warp r <-> row r, lanes over j, butterfly reduce
+  if (warp < R) {
+    const float* h = sH2 + warp * kH2;
+    const float h0 = h[lane], h1v = h[lane + 32], h2v = h[lane + 64], h3v = h[lane + 96];
+    float out = 0.f;   // lane a keeps head a
+    for (int a = 0; a < L.NH; ++a) {
+      const float* wh = sW + L.off_wh + a * kH2;
+      float s = h0 * wh[lane];
+      s = fmaf(h1v, wh[lane + 32], s);
+      s = fmaf(h2v, wh[lane + 64], s);
+      s = fmaf(h3v, wh[lane + 96], s);
+#pragma unroll
+      for (int sh = 16; sh > 0; sh >>= 1) s += __shfl_xor_sync(0xffffffffu, s, sh);
+      if (lane == a) out = s + sW[L.off_bh + a];
+    }
+    if (sRaw != nullptr && lane < kQLD) sRaw[warp * kQLD + lane] = (lane < L.NH) ? out : 0.f;
+    if (L.dueling) {   // Q = val + (adv - mean(adv))   (dqn/network.py:83)
+      const float val = __shfl_sync(0xffffffffu, out, 0);
+      float sum = 0.f;
+      for (int a = 1; a <= L.A; ++a) sum += __shfl_sync(0xffffffffu, out, a);
+      const float mean = sum / static_cast<float>(L.A);
+      const float adv = __shfl_sync(0xffffffffu, out, (lane + 1) & 31);   // lane a gets adv[a]
+      if (lane < kQLD) sQ[warp * kQLD + lane] = (lane < L.A) ? (val + (adv - mean)) : 0.f;
+    } else {
+      if (lane < kQLD) sQ[warp * kQLD + lane] = (lane < L.A) ? out : 0.f;
+    }
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ int argmax_first(const float* q, int A) {
+  int best = 0;
+  float bv = q[0];
+  for (int a = 1; a < A; ++a) {
+    const float v = q[a];
+    if (v > bv) { bv = v; best = a; }   // strict '>' keeps the first maximum (torch.argmax)
+  }
+  return best;
+}
+
+// stage one parameter blob into shared memory with a single TMA bulk copy
+__device__ __forceinline__ void stage_params(float* sW, const float* gW, int floats, uint64_t* bar, uint32_t& parity) {
+  // all generic-proxy accesses to sW by this CTA are complete (caller synchronised); order them
+  // before the async-proxy write
+  if (threadIdx.x == 0) {
+    fence_proxy_async();
+    const uint32_t bytes = static_cast<uint32_t>(floats) * 4u;
+    mbar_expect_tx(bar, bytes);
+    bulk_g2s(sW, gW, bytes, bar);
+  }
+}
+__device__ __forceinline__ void wait_params(uint64_t* bar, uint32_t& parity) {
+  mbar_wait(bar, parity);
+  parity ^= 1u;
+}
+
+// ------------------------------------------------------------------ Adam / Polyak on one element
+__device__ __forceinline__ void adam_polyak_element(const AgentCtx& C, const StepScalars& S, int pi, float g) {
+  float p = C.online[pi];
+  if (S.phases & 16 /*ADAM*/) {
+    float m = C.adam_m[pi], v = C.adam_v[pi];
+    m = m + S.adam_w1 * (g - m);                       // exp_avg.lerp_(grad, 1-beta1)
+    v = v * S.adam_b2 + (S.adam_w2 * g) * g;           // mul_(beta2).addcmul_(grad, grad, value=1-beta2)
+    const float denom = __fsqrt_rn(v) / S.adam_bc2_sqrt + S.adam_eps;
+    p = p + S.adam_neg_step * (m / denom);             // addcdiv_(exp_avg, denom, value=-step_size)
+    C.online[pi] = p;
+    C.adam_m[pi] = m;
+    C.adam_v[pi] = v;
+  }
+  if (S.phases & 32 /*POLYAK: dqn/agent.py:105-110, post-Adam weights*/) {
+    C.target[pi] = S.polyak_k * p + S.polyak_1mk * C.target[pi];
+  } else if (S.phases & 64 /*HARDSYNC: dqn/agent.py:102-103*/) {
+    C.target[pi] = p;
+  }
+}
+
+// ------------------------------------------------------------------ phase B: one 32x32 gradient tile
+// out[m][n] = sum_b A[b][m0+m] * Bm[b][n0+n]   (+ column sums of Bm as the bias gradient)
+struct GemmUnit {
+  const float* A; int lda; int m0; int m_valid;
+  const float* Bm; int ldb; int n0; int n_valid;
+  int out_base; int out_sm; int out_sn;    // param index = out_base + m*out_sm + n*out_sn
+  int bias_base;                           // param index of bias[n] or -1
+};
+
+__device__ void wgrad_unit(const AgentCtx& C, const StepScalars& S, const GemmUnit& U, float* smem) {
+  float* As = smem;                               // [kGChunk][32]
+  float* Bs = smem + kGChunk * kGTile;            // [kGChunk][32]
+  float* Ps = Bs + kGChunk * kGTile;              // [kWarps][32*32]
+  float* Pb = Ps + kWarps * kGTile * kGTile;      // [kWarps][32]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int mg = lane >> 2, ng = lane & 3;        // lane tile: 4 m x 8 n
+  float acc[4][8];
+  float bsum[8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) bsum[j] = 0.f;
+
+  for (long long b0 = 0; b0 < S.B; b0 += kGChunk) {
+    const int rows = static_cast<int>(min(static_cast<long long>(kGChunk), S.B - b0));
+    __syncthreads();
+    for (int t = tid; t < kGChunk * kGTile; t += kThreads) {
+      const int r = t >> 5, c = t & 31;
+      float a = 0.f, b = 0.f;
+      if (r < rows) {
+        if (c < U.m_valid) a = __ldcg(U.A + (b0 + r) * U.lda + U.m0 + c);
+        if (c < U.n_valid) b = __ldcg(U.Bm + (b0 + r) * U.ldb + U.n0 + c);
+      }
+      As[t] = a;
+      Bs[t] = b;
+    }
+    __syncthreads();
+    // warp w takes rows w, w+8, ... (fixed order -> deterministic sums)
+    for (int r = warp; r < rows; r += kWarps) {
+      const float4 a4 = *reinterpret_cast<const float4*>(As + r * kGTile + mg * 4);
+      const float4 b0v = *reinterpret_cast<const float4*>(Bs + r * kGTile + ng * 8);
+      const float4 b1v = *reinterpret_cast<const float4*>(Bs + r * kGTile + ng * 8 + 4);
+      const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+      const float b[8] = {b0v.x, b0v.y, b0v.z, b0v.w, b1v.x, b1v.y, b1v.z, b1v.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) bsum[j] += b[j];
+    }
+  }
+  // cross-warp reduction in fixed order
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float* pp = Ps + warp * (kGTile * kGTile) + (mg * 4 + i) * kGTile + ng * 8;
+    *reinterpret_cast<float4*>(pp) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    *reinterpret_cast<float4*>(pp + 4) = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
+  }
+  if (mg == 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) Pb[warp * kGTile + ng * 8 + j] = bsum[j];
+  }
+  __syncthreads();
+  for (int o = tid; o < kGTile * kGTile; o += kThreads) {
+    const int m = o >> 5, n = o & 31;
+    if (m < U.m_valid && n < U.n_valid) {
+      float g = 0.f;
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) g += Ps[w * (kGTile * kGTile) + o];
+      const int pi = U.out_base + m * U.out_sm + n * U.out_sn;
+      C.grads[pi] = g;
+      adam_polyak_element(C, S, pi, g);
+    }
+  }
+  if (U.bias_base >= 0 && tid < kGTile && tid < U.n_valid) {
+    float g = 0.f;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) g += Pb[w * kGTile + tid];
+    const int pi = U.bias_base + tid;
+    C.grads[pi] = g;
+    adam_polyak_element(C, S, pi, g);
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ int wgrad_unit_count(const NetLayout& L) { return kH1 / 32 + (kH1 / 32) * (kH2 / 32) + kH2 / 32; }
+
+__device__ __forceinline__ GemmUnit make_unit(const AgentCtx& C, int u) {
+  const NetLayout& L = C.L;
+  GemmUnit U;
+  const int n_w0 = kH1 / 32, n_w2 = (kH1 / 32) * (kH2 / 32);
+  if (u < n_w0) {                       // dW0^T[d][i] = sum_b X[b][d] * DZ1[b][i] ; db0 = colsum(DZ1)
+    U.A = C.X; U.lda = C.rp.row_floats; U.m0 = 0; U.m_valid = L.D;
+    U.Bm = C.DZ1; U.ldb = kH1; U.n0 = u * 32; U.n_valid = 32;
+    U.out_base = L.off_w0t + U.n0; U.out_sm = kH1; U.out_sn = 1;
+    U.bias_base = L.off_b0 + U.n0;
+  } else if (u < n_w0 + n_w2) {         // dW2^T[k][j] = sum_b H1[b][k] * DZ2[b][j] ; db2 = colsum(DZ2)
+    const int v = u - n_w0, kt = v / (kH2 / 32), jt = v % (kH2 / 32);
+    U.A = C.H1; U.lda = kH1; U.m0 = kt * 32; U.m_valid = 32;
+    U.Bm = C.DZ2; U.ldb = kH2; U.n0 = jt * 32; U.n_valid = 32;
+    U.out_base = L.off_w2t + U.m0 * kW2LD + U.n0; U.out_sm = kW2LD; U.out_sn = 1;
+    U.bias_base = (kt == 0) ? L.off_b2 + U.n0 : -1;
+  } else {                              // dWh[a][j] = sum_b H2[b][j] * DH[b][a] ; dbh = colsum(DH)
+    const int jt = u - n_w0 - n_w2;
+    U.A = C.H2; U.lda = kH2; U.m0 = jt * 32; U.m_valid = 32;
+    U.Bm = C.DH; U.ldb = kQLD; U.n0 = 0; U.n_valid = L.NH;
+    U.out_base = L.off_wh + U.m0; U.out_sm = 1; U.out_sn = kH2;
+    U.bias_base = (jt == 0) ? L.off_bh : -1;
+  }
+  return U;
+}
+
+// ------------------------------------------------------------------ the fused learner step
+__global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, const AgentCtx* __restrict__ many, StepScalars S) {
+  extern __shared__ __align__(16) float smem[];
+  const AgentCtx& C = (many != nullptr) ? many[blockIdx.y] : single;
+  const unsigned agent = blockIdx.y;
+  const NetLayout L = C.L;
+  const SmemPlan P = make_smem_plan(L.total);
+  float* sW = smem + P.w;
+  float* sXT = smem + P.xt;
+  float* sH1T = smem + P.h1t;
+  float* sH2 = smem + P.h2;
+  float* sPart = smem + P.part;
+  float* sQ = smem + P.q;
+  float* sDZ2 = smem + P.dz2;
+  float* sDH = smem + P.dh;
+  float* sMeta = smem + P.meta;
+  float* sRed = smem + P.red;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + P.bar);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int cta = blockIdx.x, G = gridDim.x;
+  const long long B = S.B;
+  const long long n_tiles = (B + kTM - 1) / kTM;
+  const int rf = C.rp.row_floats;
+  const int D = L.D;
+  const bool do_rows = (S.phases & (1 | 2)) != 0;
+  const bool per = S.prioritized != 0;
+  const long long first_leaf = C.rp.cap - 1;
+  uint32_t parity = 0;
+
+  if (do_rows && cta < S.n_row_ctas && cta < n_tiles) {
+    if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+    __syncthreads();
+    const bool do_fwd = (S.phases & 2) != 0;
+    if (do_fwd) stage_params(sW, C.target, L.total, bar, parity);
+
+    // -------- pass 1 over this CTA's tiles: sample + gather, then Q_target(s')
+    const long long size = C.rp.st->size, dp = C.rp.st->dp;
+    const double total = per ? __ldcg(C.rp.tree) : 0.0;
+    const double min_p = per ? static_cast<double>(C.rp.st->min_p) : 0.0;
+    if (S.phases & 1) {
+      for (long long tile = cta; tile < n_tiles; tile += S.n_row_ctas) {
+        if (warp < kTM) {
+          const long long i = tile * kTM + warp;
+          if (i < B) {
+            long long slot, node;
+            float w = 1.f;
+            if (C.rp.prioritized) {
+              const long long gi = S.shard_off + i;
+              const double ui = (S.u != nullptr) ? S.u[agent * B + i] : philox_uniform(S.seed, S.counter, agent, static_cast<uint32_t>(gi));
+              const double v = stratum_value(total, S.Bglobal, gi, ui);
+              double p;
+              node = per_descend_warp(C.rp.tree, 2 * C.rp.cap - 1, v, &p);
+              slot = node - first_leaf;
+              w = static_cast<float>(is_weight(static_cast<double>(size), p, total, min_p, S.beta));
+            } else {
+              const long long pos = (S.idx != nullptr) ? S.idx[agent * B + i]
+                                                       : static_cast<long long>(feistel_perm(S.shard_off + i, size, S.seed, S.counter, agent));
+              slot = deque_pos_to_slot(pos, size, dp, C.rp.cap);
+              node = slot;
+            }
+            if (lane == 0) { C.nodes[i] = node; C.is_w[i] = w; }
+            gather_row_warp(C.rp, slot, C.X + i * rf);
+          }
+        }
+      }
+    }
+    __syncthreads();   // X rows written by this CTA are visible to it
+    if (do_fwd) {
+      wait_params(bar, parity);
+      for (long long tile = cta; tile < n_tiles; tile += S.n_row_ctas) {
+        // x^T of the s' rows -> sXT[d][0..3]
+        for (int t = tid; t < kTM * D; t += kThreads) {
+          const int r = t / D, d = t % D;
+          const long long i = tile * kTM + r;
+          sXT[d * kR + r] = (i < B) ? __ldcg(C.X + i * rf + D + d) : 0.f;
+        }
+        __syncthreads();
+        mlp_forward<kTM>(sW, L, sXT, sH1T, sH2, sPart, sQ, nullptr);
+        if (tid < kTM * kQLD) {
+          const int r = tid / kQLD;
+          const long long i = tile * kTM + r;
+          if (i < B) C.QT[i * kQLD + (tid % kQLD)] = sQ[tid];
+        }
+        __syncthreads();
+      }
+      // -------- pass 2: online weights; [s'; s] rows
+      stage_params(sW, C.online, L.total, bar, parity);
+      wait_params(bar, parity);
+      float loss_local = 0.f;   // thread 0 accumulates this CTA's tiles in order
+      for (long long tile = cta; tile < n_tiles; tile += S.n_row_ctas) {
+        for (int t = tid; t < kR * D; t += kThreads) {
+          const int r = t / D, d = t % D;
+          const long long i = tile * kTM + (r % kTM);
+          const int col = (r < kTM) ? (D + d) : d;   // rows 0..3: s', rows 4..7: s
+          sXT[d * kR + r] = (i < B) ? __ldcg(C.X + i * rf + col) : 0.f;
+        }
+        if (tid < kTM) {
+          const long long i = tile * kTM + tid;
+          const bool ok = i < B;
+          sMeta[tid * 4 + 0] = ok ? __ldcg(C.X + i * rf + 2 * D) : 0.f;
+          sMeta[tid * 4 + 1] = ok ? __ldcg(C.X + i * rf + 2 * D + 1) : 0.f;
+          sMeta[tid * 4 + 2] = ok ? __ldcg(C.X + i * rf + 2 * D + 2) : 0.f;
+          sMeta[tid * 4 + 3] = ok ? C.is_w[i] : 0.f;
+        }
+        __syncthreads();
+        mlp_forward<kR>(sW, L, sXT, sH1T, sH2, sPart, sQ, nullptr);
+        // ---- TD target, |td|, Huber, dQ coefficient (threads 0..kTM-1)
+        if (tid < kTM) {
+          const int r = tid;
+          const long long i = tile * kTM + r;
+          float g = 0.f, lterm = 0.f;
+          int act = 0;
+          if (i < B) {
+            const float* qt = C.QT + i * kQLD;
+            float qsel;
+            if (S.double_dqn) {                                   // dqn/agent.py:252-256
+              const int astar = argmax_first(sQ + r * kQLD, L.A);
+              qsel = __ldcg(qt + astar);
+            } else {                                              // dqn/agent.py:172-173
+              qsel = __ldcg(qt);
+              for (int a = 1; a < L.A; ++a) qsel = fmaxf(qsel, __ldcg(qt + a));
+            }
+            act = __float_as_int(sMeta[r * 4 + 0]);
+            const float rew = sMeta[r * 4 + 1], done = sMeta[r * 4 + 2], w = sMeta[r * 4 + 3];
+            const float y = rew + ((1.f - done) * S.gamma) * qsel;   // dqn/agent.py:258
+            const float q_sa = sQ[(kTM + r) * kQLD + act];
+            const float delta = q_sa - y;
+            const float atd = fabsf(y - q_sa);                     // dqn/agent.py:264
+            const float z = fabsf(delta);
+            const float hub = (z < 1.f) ? (0.5f * z) * z : z - 0.5f;   // SmoothL1, beta = 1
+            const float go = per ? (1.f / static_cast<float>(S.Bglobal)) * w : 1.f / static_cast<float>(S.Bglobal);
+            g = fminf(fmaxf(delta, -1.f), 1.f) * go;
+            lterm = per ? w * hub : hub;
+            C.y[i] = y; C.q_sa[i] = q_sa; C.abs_td[i] = atd; C.hub[i] = hub; C.gcoef[i] = g;
+            if (per) {
+              C.pri[i] = td_to_priority(atd, S.per_eps, S.per_alpha, S.per_pmax);
+              if (S.phases & 4) atomicMax(C.rp.stamps + (C.nodes[i] - first_leaf), static_cast<int>(i + 1));
+            }
+          }
+          // dheads
+          float* dh = sDH + r * kQLD;
+          for (int a = 0; a < kQLD; ++a) dh[a] = 0.f;
+          if (L.dueling) {
+            const float mean = g / static_cast<float>(L.A);
+            dh[0] = g;                                             // dval = sum_a dQ
+            for (int a = 0; a < L.A; ++a) dh[1 + a] = ((a == act) ? g : 0.f) - mean;
+          } else {
+            dh[act] = g;
+          }
+          sRed[r] = lterm;
+        }
+        // debug / parity outputs of the Q rows
+        if (tid < kR * kQLD) {
+          const int r = tid / kQLD;
+          const long long i = tile * kTM + (r % kTM);
+          if (i < B) ((r < kTM) ? C.QN : C.Q)[i * kQLD + (tid % kQLD)] = sQ[tid];
+        }
+        __syncthreads();
+        if (tid == 0) {
+          for (int r = 0; r < kTM; ++r) loss_local += sRed[r];
+        }
+        // ---- dh2 -> dz2 (thread: column j, rows r and r+2)
+        {
+          const int j = tid & (kH2 - 1), r0 = tid >> 7;   // r0 in {0,1}
+#pragma unroll
+          for (int rr = 0; rr < 2; ++rr) {
+            const int r = r0 + 2 * rr;
+            const float* dh = sDH + r * kQLD;
+            float s = 0.f;
+            for (int a = 0; a < L.NH; ++a) s = fmaf(dh[a], sW[L.off_wh + a * kH2 + j], s);
+            const float h2v = sH2[(kTM + r) * kH2 + j];
+            const float dz = (h2v > 0.f) ? s : 0.f;
+            sDZ2[r * kH2 + j] = dz;
+            const long long i = tile * kTM + r;
+            if (i < B) { C.DZ2[i * kH2 + j] = dz; C.H2[i * kH2 + j] = h2v; }
+          }
+          if (tid < kTM * kQLD) {
+            const long long i = tile * kTM + tid / kQLD;
+            if (i < B) C.DH[i * kQLD + (tid % kQLD)] = sDH[tid];
+          }
+        }
+        __syncthreads();
+        // ---- dz1[r][k] = (sum_j dz2[r][j] W2^T[k][j]) * [h1 > 0]   (thread k)
+        {
+          float acc[kTM] = {0.f, 0.f, 0.f, 0.f};
+          const float* wrow = sW + L.off_w2t + tid * kW2LD;
+#pragma unroll 4
+          for (int j = 0; j < kH2; j += 4) {
+            const float4 w = *reinterpret_cast<const float4*>(wrow + j);
+#pragma unroll
+            for (int r = 0; r < kTM; ++r) {
+              const float4 dz = *reinterpret_cast<const float4*>(sDZ2 + r * kH2 + j);
+              acc[r] = fmaf(dz.x, w.x, acc[r]);
+              acc[r] = fmaf(dz.y, w.y, acc[r]);
+              acc[r] = fmaf(dz.z, w.z, acc[r]);
+              acc[r] = fmaf(dz.w, w.w, acc[r]);
+            }
+          }
+#pragma unroll
+          for (int r = 0; r < kTM; ++r) {
+            const long long i = tile * kTM + r;
+            const float h1v = sH1T[tid * kR + kTM + r];
+            if (i < B) {
+              C.DZ1[i * kH1 + tid] = (h1v > 0.f) ? acc[r] : 0.f;
+              C.H1[i * kH1 + tid] = h1v;
+            }
+          }
+        }
+        __syncthreads();
+      }
+      if (tid == 0) C.loss_part[cta] = loss_local;
+    }
+  } else if (do_rows && (S.phases & 2) && tid == 0 && cta < S.n_row_ctas) {
+    C.loss_part[cta] = 0.f;
+  }
+
+  const int phaseB = S.phases & (4 | 8 | 16 | 32 | 64);
+  if (!phaseB) return;
+  if (do_rows) agent_barrier(C.barrier, S.barrier_target);
+
+  // ---------------------------------------------------------------- phase B
+  const bool tree_here = per && (S.phases & 4) && C.rp.prioritized && B <= kTreeCtaMax;
+  int n_workers = G, wid = cta;
+  if (tree_here && G > 1) {
+    n_workers = G - 1;
+    if (cta == G - 1) {
+      tree_update_cta(C.rp, C.nodes, C.pri, B, C.rp.st->size, true);
+      return;
+    }
+  }
+  if (cta == 0 && (S.phases & 2) && tid == 0) {   // loss = (1/B) sum of the per-CTA partials, fixed order
+    float s = 0.f;
+    const int np = static_cast<int>(min(static_cast<long long>(S.n_row_ctas), n_tiles));
+    for (int c = 0; c < np; ++c) s += __ldcg(C.loss_part + c);
+    C.loss[0] = s / static_cast<float>(S.Bglobal);
+  }
+  if (S.phases & 8) {                             // BACKWARD (+ fused Adam/Polyak)
+    const int n_units = wgrad_unit_count(L);
+    for (int u = wid; u < n_units; u += n_workers) {
+      const GemmUnit U = make_unit(C, u);
+      wgrad_unit(C, S, U, smem);
+    }
+  } else if (S.phases & (16 | 32 | 64)) {         // element-wise Adam from given grads / target sync only
+    const float* gsrc = (S.grads_in != nullptr) ? S.grads_in + static_cast<size_t>(agent) * L.total : C.grads;
+    for (int pi = wid * kThreads + tid; pi < L.total; pi += n_workers * kThreads)
+      adam_polyak_element(C, S, pi, (S.phases & 16) ? __ldcg(gsrc + pi) : 0.f);
+  }
+  if (tree_here && G == 1) {
+    __syncthreads();
+    tree_update_cta(C.rp, C.nodes, C.pri, B, C.rp.st->size, true);
+  }
+}
+
+// ------------------------------------------------------------------ batched act / Q values
+// mode 0: greedy actions (dueling -> argmax raw adv, plain -> argmax Q; dqn/network.py:67-74,110-117)
+// mode 1: Q values [n][A]
+__global__ void __launch_bounds__(kThreads, 1) k_mlp_infer(NetLayout L, const float* __restrict__ params, const float* __restrict__ obs,
+                                                           long long n, long long* __restrict__ actions, float* __restrict__ q_out, int mode) {
+  extern __shared__ __align__(16) float smem[];
+  const SmemPlan P = make_smem_plan(L.total);
+  float* sW = smem + P.w;
+  float* sXT = smem + P.xt;
+  float* sH1T = smem + P.h1t;
+  float* sH2 = smem + P.h2;
+  float* sPart = smem + P.part;
+  float* sQ = smem + P.q;
+  float* sRaw = smem + P.dz2;   // [kR][kQLD] fits in the dz2 area
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + P.bar);
+  const int tid = threadIdx.x;
+  const long long n_tiles = (n + kR - 1) / kR;
+  if (blockIdx.x >= n_tiles) return;
+  uint32_t parity = 0;
+  if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+  __syncthreads();
+  stage_params(sW, params, L.total, bar, parity);
+  wait_params(bar, parity);
+  const int D = L.D;
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (int t = tid; t < kR * D; t += kThreads) {
+      const int r = t / D, d = t % D;
+      const long long i = tile * kR + r;
+      sXT[d * kR + r] = (i < n) ? __ldg(obs + i * D + d) : 0.f;
+    }
+    __syncthreads();
+    mlp_forward<kR>(sW, L, sXT, sH1T, sH2, sPart, sQ, sRaw);
+    if (mode == 0) {
+      if (tid < kR) {
+        const long long i = tile * kR + tid;
+        if (i < n) actions[i] = L.dueling ? argmax_first(sRaw + tid * kQLD + 1, L.A) : argmax_first(sQ + tid * kQLD, L.A);
+      }
+    } else {
+      for (int t = tid; t < kR * L.A; t += kThreads) {
+        const int r = t / L.A, a = t % L.A;
+        const long long i = tile * kR + r;
+        if (i < n) q_out[i * L.A + a] = sQ[r * kQLD + a];
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// parameter (de)interleave between torch state_dict order and the device layout
+__global__ void k_params_scatter(float* dev_blob, const float* src_torch, const int* map, long long n) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i < n) dev_blob[map[i]] = src_torch[i];
+}
+__global__ void k_params_gather(float* dst_torch, const float* dev_blob, const int* map, long long n) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i < n) dst_torch[i] = dev_blob[map[i]];
+}
+
+}  // namespace rmc

@@ -1,0 +1,127 @@
+"""GPU parity harness: drives the CUDA drop-in and the CPU oracle on identical seeded inputs and
+identical injected sampling randomness, step by step, and returns error metrics.
+Used by the -m gpu tests and by __graft_entry__.smoke()."""
+from __future__ import annotations
+
+import ctypes as C
+import tempfile
+
+import numpy as np
+import torch
+
+from oracle.dqn_oracle import OracleLearner, synthetic_transitions
+from tests.recipes import max_rel, perturb_target
+
+
+def tensor_sizes(net):
+    return [(k, int(v.numel())) for k, v in net.state_dict().items()]
+
+
+def per_tensor_max_rel(flat_a, flat_b, sizes):
+    out, off = {}, 0
+    for k, n in sizes:
+        out[k] = max_rel(flat_a[off:off + n], flat_b[off:off + n])
+        off += n
+    return out
+
+
+def flat_sd(net):
+    return np.concatenate([v.detach().cpu().numpy().ravel() for v in net.state_dict().values()])
+
+
+def make_pair(algo, D, B, cap, fill, seed, soft=True, target_freq=30000, tmpdir=None):
+    """(oracle learner, CUDA agent) with identical weights and identical replay contents."""
+    from multimodal_drl_rmc_b200 import macro_config
+    torch.set_num_threads(1)
+    torch.manual_seed(seed)
+    orc = OracleLearner(algo, D, 8, B, cap, soft=soft, target_freq=target_freq)
+    perturb_target(orc.target, seed + 100)
+    tmp = tmpdir or tempfile.mkdtemp(prefix="rmc_parity_")
+    agent = macro_config.make_agent(algo, D, B, cap, save_dir=tmp + "/", log_dir=tmp + "/",
+                                    target_soft_update=soft, target_update_freq=target_freq)
+    agent.online_network.load_state_dict({k: v.clone() for k, v in orc.online.state_dict().items()})
+    agent.target_network.load_state_dict({k: v.clone() for k, v in orc.target.state_dict().items()})
+    obs, act, rew, done, nxt = synthetic_transitions(fill, D, 20251018 + seed)
+    for i in range(fill):
+        orc.store([obs[i]], [int(act[i])], [float(rew[i])], [bool(done[i])], [nxt[i]])
+    # the drop-in receives the same stream, in uneven chunks (exercises ring wrap + multi-row pushes)
+    i = 0
+    chunk = 1
+    while i < fill:
+        j = min(fill, i + chunk)
+        agent.store_transitions(obs[i:j], act[i:j].tolist(), rew[i:j].tolist(), done[i:j].astype(bool).tolist(), nxt[i:j], None)
+        i, chunk = j, (chunk * 3) % 97 + 1
+    return orc, agent
+
+
+def gpu_out(agent, name, dtype=torch.float32):
+    return agent._lh.output(name, dtype).cpu().numpy()
+
+
+def run_parity_case(algo, D, B, cap, fill, steps, seed, soft=True, target_freq=30000, resync_tree=True):
+    from multimodal_drl_rmc_b200 import _lib
+    orc, agent = make_pair(algo, D, B, cap, fill, seed, soft, target_freq)
+    per = orc.per
+    sizes = tensor_sizes(orc.online)
+    rng = np.random.default_rng(seed + 1)
+    res = dict(nodes_equal=True, tree_equal=True, max_rel_q=0.0, max_rel_loss=0.0, max_rel_isw=0.0,
+               max_rel_grads=0.0, max_rel_weights=0.0, max_rel_target=0.0, max_pri_ulp=0.0, worst_grad="", worst_w="")
+    if per:
+        res["tree_equal"] = bool(np.array_equal(agent.replay_memory_buffer.replay_buffer.tree, orc.replay.tree.tree))
+    for s in range(steps):
+        step_no = 1000 * s + 17
+        orc.step = agent.step = step_no
+        tr = {}
+        if per:
+            u = rng.random(B)
+            orc.learn(u=u, trace=tr)
+            agent.learn(u=u)
+        else:
+            idx = rng.permutation(len(orc.replay.buf))[:B].astype(np.int64)
+            orc.learn(indices=[int(i) for i in idx], trace=tr)
+            agent.learn(indices=idx)
+        # ---- per-sample products
+        if per:
+            nodes = gpu_out(agent, "nodes", torch.int64)
+            res["nodes_equal"] &= bool(np.array_equal(nodes, tr["nodes"]))
+            res["max_rel_isw"] = max(res["max_rel_isw"], max_rel(gpu_out(agent, "is_w"), tr["is_w"].astype(np.float32)))
+        res["max_rel_q"] = max(res["max_rel_q"], max_rel(gpu_out(agent, "q_sa"), tr["q_sa"].reshape(-1)),
+                               max_rel(gpu_out(agent, "y"), tr["y"].reshape(-1)))
+        A = 8
+        qn = gpu_out(agent, "q").reshape(B, -1)[:, :A]
+        res["max_rel_q"] = max(res["max_rel_q"], max_rel(qn, tr["q"]))
+        res["max_rel_loss"] = max(res["max_rel_loss"], abs(agent.last_loss() - tr["loss"]) / max(abs(tr["loss"]), 1e-30))
+        # ---- gradients (torch state_dict order)
+        g_gpu = agent._lh.get_params(_lib.GRADS).cpu().numpy()
+        g_ref = np.concatenate([tr["grads"][k].ravel() for k, _ in orc.online.named_parameters()])
+        pt = per_tensor_max_rel(g_gpu, g_ref, sizes)
+        worst = max(pt, key=pt.get)
+        if pt[worst] > res["max_rel_grads"]:
+            res["max_rel_grads"], res["worst_grad"] = pt[worst], worst
+        # ---- priorities / tree
+        if per:
+            p_ref = np.power(np.minimum(tr["abs_td"].reshape(-1) + np.float32(1e-4), np.float32(1.0)), np.float32(0.6)).astype(np.float32)
+            p_gpu = gpu_out(agent, "pri")
+            ulp = np.abs(p_gpu.astype(np.float64) - p_ref.astype(np.float64)) / np.spacing(p_ref).astype(np.float64)
+            res["max_pri_ulp"] = max(res["max_pri_ulp"], float(ulp.max()))
+            if resync_tree:   # make the trees bit-identical again (1-ulp pow / |td| differences), then compare
+                dev = agent.device
+                n_t = torch.as_tensor(tr["nodes"], device=dev)
+                p_t = torch.as_tensor(p_ref, device=dev)
+                _lib.check(_lib.lib().rmc_per_update(agent.replay_memory_buffer._ring.handle, n_t.data_ptr(), p_t.data_ptr(),
+                                                     B, _lib.stream_ptr()))
+                t_gpu = agent.replay_memory_buffer.replay_buffer.tree
+                res["tree_equal"] &= bool(np.array_equal(t_gpu, orc.replay.tree.tree))
+                st = agent.replay_memory_buffer._ring.stats()
+                res["tree_equal"] &= (st.total_priority == orc.replay.tree.total and st.max_priority == orc.replay.tree.max_leaf
+                                      and st.min_priority == orc.replay.tree.min_leaf)
+        # ---- target sync, then weights
+        orc.sync_target()
+        agent.update_target_network()
+        w_pt = per_tensor_max_rel(flat_sd(agent.online_network), flat_sd(orc.online), sizes)
+        worst = max(w_pt, key=w_pt.get)
+        if w_pt[worst] > res["max_rel_weights"]:
+            res["max_rel_weights"], res["worst_w"] = w_pt[worst], worst
+        t_pt = per_tensor_max_rel(flat_sd(agent.target_network), flat_sd(orc.target), sizes)
+        res["max_rel_target"] = max(res["max_rel_target"], max(t_pt.values()))
+    return res

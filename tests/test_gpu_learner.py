@@ -1,0 +1,136 @@
+"""-m gpu: the fused CUDA learner step vs the oracle, through the drop-in Agent API / C ABI.
+Tolerances (north star): sampled indices and tree bit-exact; Q, loss, gradients, post-Adam
+weights within 1e-5 relative (per-tensor max-norm, fp32 FFMA accumulation)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from tests import parity_utils as PU
+from tests import recipes as R
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+CASES = [
+    # algo, D, B, cap, fill, steps, soft, target_freq
+    ("PerDuelingDoubleDQNAgent", 14, 64, 1000, 1300, 4, True, 30000),
+    ("PerDuelingDoubleDQNAgent", 14, 256, 5000, 5000, 3, True, 30000),
+    ("PerDuelingDoubleDQNAgent", 8, 32, 37, 37, 3, True, 30000),
+    ("PerDuelingDoubleDQNAgent", 14, 30, 333, 200, 2, True, 30000),     # ragged batch (not a multiple of the row tile), partial fill
+    ("DuelingDoubleDQNAgent", 14, 32, 512, 700, 3, True, 30000),
+    ("DoubleDQNAgent", 8, 32, 256, 200, 4, False, 2),                   # hard target copy every 2 steps
+    ("DQNAgent", 14, 16, 128, 128, 2, True, 30000),
+    ("DuelingDoubleDQNAgent", 14, 1024, 4096, 4096, 2, True, 30000),    # several row tiles per CTA
+]
+
+
+@pytest.mark.parametrize("algo,D,B,cap,fill,steps,soft,tf", CASES)
+def test_learner_step_parity(algo, D, B, cap, fill, steps, soft, tf):
+    res = PU.run_parity_case(algo, D, B, cap, fill, steps, seed=11, soft=soft, target_freq=tf)
+    print(res)
+    assert res["nodes_equal"], "sampled tree indices must be bit-exact"
+    assert res["tree_equal"], "sum tree must be bit-exact given equal float32 priorities"
+    assert res["max_pri_ulp"] <= 1.0, "|td| -> priority must be within 1 ulp(f32)"
+    assert res["max_rel_isw"] < 1e-6
+    assert res["max_rel_q"] < TOL
+    assert res["max_rel_loss"] < TOL
+    assert res["max_rel_grads"] < TOL, res["worst_grad"]
+    assert res["max_rel_weights"] < TOL, res["worst_w"]
+    assert res["max_rel_target"] < TOL
+
+
+def test_adam_on_identical_inputs_is_ulp_exact():
+    """Adam in isolation: identical (p, g, m, v, t) on both sides -> <= 2 ulp."""
+    from multimodal_drl_rmc_b200 import _lib
+    orc, agent = PU.make_pair("PerDuelingDoubleDQNAgent", 14, 64, 500, 500, seed=5)
+    rng = np.random.default_rng(0)
+    for t in range(1, 4):
+        tr = {}
+        orc.step = agent.step = t
+        u = rng.random(64)
+        p_before = PU.flat_sd(orc.online)
+        orc.learn(u=u, trace=tr)
+        g_ref = np.concatenate([tr["grads"][k].ravel() for k, _ in orc.online.named_parameters()])
+        # device: load the oracle's pre-step weights + grads, run Adam only
+        agent._lh.set_params(_lib.ONLINE, torch.as_tensor(p_before))
+        agent._lh.set_params(_lib.GRADS, torch.as_tensor(g_ref))
+        if t == 1:
+            z = torch.zeros(agent._lh.n_params)
+            agent._lh.set_params(_lib.ADAM_M, z)
+            agent._lh.set_params(_lib.ADAM_V, z)
+        a = _lib.StepArgs()
+        a.batch, a.phases, a.adam_t = 64, _lib.PH_ADAM, t
+        _lib.check(_lib.lib().rmc_learner_step(agent._lh.handle, agent.replay_memory_buffer._ring.handle, C.byref(a), _lib.stream_ptr()))
+        p_gpu = agent._lh.get_params(_lib.ONLINE).cpu().numpy()
+        p_ref = PU.flat_sd(orc.online)
+        ulps = np.abs(p_gpu.astype(np.float64) - p_ref) / np.maximum(np.spacing(np.abs(p_ref).astype(np.float32)), 1e-45)
+        assert ulps.max() <= 2.0, (t, ulps.max())
+        m_ref = np.concatenate([orc.opt.state[p]["exp_avg"].numpy().ravel() for p in orc.online.parameters()])
+        v_ref = np.concatenate([orc.opt.state[p]["exp_avg_sq"].numpy().ravel() for p in orc.online.parameters()])
+        assert R.max_rel(agent._lh.get_params(_lib.ADAM_M).cpu().numpy(), m_ref) < 1e-6
+        assert R.max_rel(agent._lh.get_params(_lib.ADAM_V).cpu().numpy(), v_ref) < 1e-6
+
+
+def test_fused_target_update_equals_separate_call():
+    _, a1 = PU.make_pair("PerDuelingDoubleDQNAgent", 14, 64, 500, 500, seed=9)
+    _, a2 = PU.make_pair("PerDuelingDoubleDQNAgent", 14, 64, 500, 500, seed=9)
+    u = np.random.default_rng(1).random(64)
+    a1.step = a2.step = 5
+    a1.learn(u=u)
+    a1.update_target_network()
+    a2.learn(u=u, fuse_target_update=True)
+    a2.update_target_network()          # must be skipped (already done inside the launch)
+    np.testing.assert_array_equal(PU.flat_sd(a1.online_network), PU.flat_sd(a2.online_network))
+    np.testing.assert_array_equal(PU.flat_sd(a1.target_network), PU.flat_sd(a2.target_network))
+
+
+def test_device_rng_sampling_is_valid_and_reproducible():
+    """Without injected randomness: PER indices fall in their strata, uniform indices are distinct."""
+    _, a = PU.make_pair("PerDuelingDoubleDQNAgent", 14, 128, 2000, 2000, seed=2)
+    a.learn()
+    nodes = PU.gpu_out(a, "nodes", torch.int64)
+    assert nodes.min() >= 1999 and nodes.max() <= 2 * 2000 - 2
+    _, b = PU.make_pair("DuelingDoubleDQNAgent", 14, 128, 300, 300, seed=2)
+    b.learn()
+    slots = PU.gpu_out(b, "nodes", torch.int64)
+    assert len(set(slots.tolist())) == 128 and slots.min() >= 0 and slots.max() < 300
+    _, b2 = PU.make_pair("DuelingDoubleDQNAgent", 14, 128, 300, 300, seed=2)
+    b2.learn()
+    np.testing.assert_array_equal(slots, PU.gpu_out(b2, "nodes", torch.int64))
+
+
+def test_host_sampling_mode_matches_oracle_streams():
+    """Agent.sampling='host' consumes numpy's / python's global RNG exactly like the reference."""
+    import random
+    orc, a = PU.make_pair("PerDuelingDoubleDQNAgent", 14, 64, 800, 800, seed=4)
+    a.sampling = "host"
+    np.random.seed(123)
+    tr = {}
+    orc.step = a.step = 40
+    orc.learn(trace=tr)
+    np.random.seed(123)
+    a.learn()
+    np.testing.assert_array_equal(PU.gpu_out(a, "nodes", torch.int64), tr["nodes"])
+    orc2, b = PU.make_pair("DuelingDoubleDQNAgent", 14, 32, 400, 400, seed=4)
+    b.sampling = "host"
+    random.seed(77)
+    tr2 = {}
+    orc2.learn(trace=tr2)
+    random.seed(77)
+    b.learn()
+    assert R.max_rel(PU.gpu_out(b, "q_sa"), tr2["q_sa"].reshape(-1)) < TOL
+
+
+def test_unsupported_configs_raise():
+    import torch.nn as nn
+    import torch.optim as optim
+    from multimodal_drl_rmc_b200 import Networks
+    from multimodal_drl_rmc_b200.macro_config import ObsSpace
+
+    def elu_conf(space):
+        return nn.Sequential(nn.Linear(space.shape[0], 256), nn.ELU(), nn.Linear(256, 128), nn.ELU()), 128, optim.Adam, nn.SmoothL1Loss
+
+    with pytest.raises(NotImplementedError):
+        Networks.DuelingDeepQNetwork(torch.device("cuda:0"), 1e-4, elu_conf, ObsSpace(14), 8)
