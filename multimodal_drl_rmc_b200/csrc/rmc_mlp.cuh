@@ -197,10 +197,12 @@ __device__ __forceinline__ void adam_polyak_element(const AgentCtx& C, const Ste
   float p = C.online[pi];
   if (S.phases & 16 /*ADAM*/) {
     float m = C.adam_m[pi], v = C.adam_v[pi];
-    m = m + S.adam_w1 * (g - m);                       // exp_avg.lerp_(grad, 1-beta1)
-    v = v * S.adam_b2 + (S.adam_w2 * g) * g;           // mul_(beta2).addcmul_(grad, grad, value=1-beta2)
+    // Rounding sequence of torch 2.11's CPU kernels, found by bit-matching torch.optim.Adam
+    // (tests/test_oracle_golden.py::test_numpy_adam_bit_matches_torch): lerp and addcmul are FMAs.
+    m = fmaf(S.adam_w1, g - m, m);                     // exp_avg.lerp_(grad, 1-beta1)
+    v = fmaf(S.adam_w2 * g, g, v * S.adam_b2);         // mul_(beta2).addcmul_(grad, grad, value=1-beta2)
     const float denom = __fsqrt_rn(v) / S.adam_bc2_sqrt + S.adam_eps;
-    p = p + S.adam_neg_step * (m / denom);             // addcdiv_(exp_avg, denom, value=-step_size)
+    p = p + (S.adam_neg_step * m) / denom;             // addcdiv_(exp_avg, denom, value=-step_size)
     C.online[pi] = p;
     C.adam_m[pi] = m;
     C.adam_v[pi] = v;

@@ -411,18 +411,24 @@ def numpy_td_and_grads(online: dict, target: dict, obs, act, rew, done, nxt, is_
                 grads={k: v.astype(f) for k, v in grads.items()})
 
 
+def _fma32(a, b, c):
+    """float32 fused multiply-add emulated through float64 (exact product, one rounding)."""
+    return (np.asarray(a, np.float64) * np.asarray(b, np.float64) + np.asarray(c, np.float64)).astype(np.float32)
+
+
 def numpy_adam(p, g, m, v, t, lr=1e-4, b1=0.9, b2=0.999, eps=1e-8):
-    """torch.optim.Adam single-tensor step as executed by torch 2.11 (Appendix A step 11):
-    m <- m + (1-b1)(g-m) [lerp]; v <- b2 v + (1-b2) g^2; bias corrections in python float64;
-    p <- p - (lr/bc1) * m / (sqrt(v)/sqrt(bc2) + eps).  float32 tensors, in-place semantics."""
+    """torch.optim.Adam single-tensor step with the rounding sequence torch 2.11's CPU kernels
+    execute (Appendix A step 11; found by bit-matching, see test_numpy_adam_bit_matches_torch):
+    m <- fma(1-b1, g-m, m) [lerp_]; v <- fma((1-b2) g, g, b2 v) [mul_ + addcmul_]; python-float64
+    bias corrections; denom = sqrt(v)/sqrt(bc2) + eps; p <- p + (-(lr/bc1) m) / denom [addcdiv_]."""
     f = np.float32
-    m = (m + f(1 - b1) * (g - m)).astype(f)
-    v = (v * f(b2) + f(1 - b2) * g * g).astype(f)
+    m = _fma32(f(1 - b1), (g - m).astype(f), m)
+    v = _fma32((f(1 - b2) * g).astype(f), g, (v * f(b2)).astype(f))
     bc1 = 1 - b1 ** t
     bc2 = 1 - b2 ** t
     step_size = lr / bc1
-    denom = (np.sqrt(v) / f(bc2 ** 0.5) + f(eps)).astype(f)
-    p = (p - f(step_size) * (m / denom)).astype(f)
+    denom = ((np.sqrt(v).astype(f) / f(bc2 ** 0.5)).astype(f) + f(eps)).astype(f)
+    p = (p + ((f(-step_size) * m).astype(f) / denom).astype(f)).astype(f)
     return p, m, v
 
 
