@@ -221,6 +221,13 @@ int32_t rmc_learner_act(rmc_learner_t* l, const float* obs_dev, int64_t n, int64
 int32_t rmc_learner_act_host_sync(rmc_learner_t* l, const float* obs_host, int64_t n, int64_t* actions_host,
                                   rmc_stream_t s);
 
+/* Diagnostics (not a reference interface): per-CTA phase timestamps (%globaltimer, ns) of the last
+ * rmc_learner_step: out_host[cta*16 + k], k = 0 start, 1 sampled, 2 target weights landed,
+ * 3 target pass done, 4 online weights landed, 5 row phase done, 6 past the barrier, 7 done. */
+int32_t rmc_learner_debug_timing(rmc_learner_t* l, int32_t enable);
+int32_t rmc_learner_debug_read_sync(rmc_learner_t* l, uint64_t* out_host, int32_t max_ctas, int32_t* n_ctas,
+                                    rmc_stream_t s);
+
 /* ---------------------------------------------------------------- ensembles (C4) ------- */
 /* N independent agents (own replay, weights, Adam state, RNG stream) stepped by one launch
  * (grid.y = agent); no communication.  All members must share spec/hyper/batch. */

@@ -77,6 +77,8 @@ struct rmc_learner {
   float* io = nullptr;       // [P] device staging for set/get
   AgentCtx ctx{};            // replay part filled per step
   unsigned barrier_count = 0;
+  unsigned long long* dbg_buf = nullptr;
+  int last_grid = 0;
   // act staging
   float* act_pin_obs = nullptr; long long* act_pin_out = nullptr; float* act_dev_obs = nullptr; long long* act_dev_out = nullptr;
   long long act_cap = 0;
@@ -498,6 +500,7 @@ extern "C" int32_t rmc_learner_create(rmc_learner_t** out, const rmc_net_spec_t*
   if ((e = owned_alloc(l, &c.loss_part, 1024))) return e;
   if ((e = owned_alloc(l, &c.loss, 1))) return e;
   if ((e = owned_alloc(l, &c.barrier, 1))) return e;
+  if ((e = owned_alloc(l, &l->dbg_buf, 1024 * 16))) return e;
   RMC_CUDA(cudaDeviceSynchronize());
   *out = l;
   return RMC_OK;
@@ -628,6 +631,7 @@ extern "C" int32_t rmc_learner_step(rmc_learner_t* l, rmc_replay_t* r, const rmc
   const bool phase_b = (a->phases & (RMC_PH_PRIORITY | RMC_PH_BACKWARD | RMC_PH_ADAM | RMC_PH_POLYAK | RMC_PH_HARDSYNC)) != 0;
   if (rows && phase_b) S.barrier_target = l->barrier_count + static_cast<unsigned>(G);
   AgentCtx single = l->ctx;
+  l->last_grid = G;
   const AgentCtx* many = nullptr;
   void* args[] = {&single, &many, &S};
   RMC_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_learner_step), dim3(G, 1, 1), dim3(kThreads, 1, 1), args,
@@ -783,5 +787,21 @@ extern "C" int32_t rmc_group_step(rmc_group_t* g, const rmc_step_args_t* a, rmc_
                                        static_cast<size_t>(l0->smem_bytes), st));
   if (rows && phase_b) g->barrier_count = S.barrier_target;
   g_launches.fetch_add(1, std::memory_order_relaxed);
+  return RMC_OK;
+}
+
+// ------------------------------------------------------------------------------ debug timing
+extern "C" int32_t rmc_learner_debug_timing(rmc_learner_t* l, int32_t enable) {
+  if (!l) return fail(RMC_ERR_ARG, "rmc_learner_debug_timing: null");
+  l->ctx.dbg = enable ? l->dbg_buf : nullptr;
+  return RMC_OK;
+}
+extern "C" int32_t rmc_learner_debug_read_sync(rmc_learner_t* l, uint64_t* out_host, int32_t max_ctas, int32_t* n_ctas, rmc_stream_t s) {
+  if (!l || !out_host || !n_ctas) return fail(RMC_ERR_ARG, "rmc_learner_debug_read_sync: null");
+  if (int32_t e = use_device(l->device)) return e;
+  const int n = std::min(max_ctas, l->last_grid);
+  RMC_CUDA(cudaMemcpyAsync(out_host, l->dbg_buf, static_cast<size_t>(n) * 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost, as_stream(s)));
+  RMC_CUDA(cudaStreamSynchronize(as_stream(s)));
+  *n_ctas = n;
   return RMC_OK;
 }

@@ -79,6 +79,17 @@ __device__ __forceinline__ void agent_barrier(unsigned* ctr, unsigned target) {
   __syncthreads();
 }
 
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define RMC_STAMP(C, slot)                                                                 \
+  do {                                                                                     \
+    if ((C).dbg != nullptr && threadIdx.x == 0)                                            \
+      (C).dbg[(blockIdx.y * gridDim.x + blockIdx.x) * 16 + (slot)] = global_timer_ns();    \
+  } while (0)
+
 // ----------------------------------------------------------------------------- Philox4x32-10
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
   const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
@@ -173,6 +184,7 @@ struct AgentCtx {
   float* loss_part;     // [n_tiles]
   float* loss;          // [1]
   unsigned* barrier;
+  unsigned long long* dbg;   // optional per-CTA phase timestamps [G][16] (nullptr = off)
 };
 
 struct StepScalars {

@@ -358,6 +358,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, c
   const bool per = S.prioritized != 0;
   const long long first_leaf = C.rp.cap - 1;
   uint32_t parity = 0;
+  RMC_STAMP(C, 0);
 
   if (do_rows && cta < S.n_row_ctas && cta < n_tiles) {
     if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
@@ -397,8 +398,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, c
       }
     }
     __syncthreads();   // X rows written by this CTA are visible to it
+    RMC_STAMP(C, 1);
     if (do_fwd) {
       wait_params(bar, parity);
+      RMC_STAMP(C, 2);
       for (long long tile = cta; tile < n_tiles; tile += S.n_row_ctas) {
         // x^T of the s' rows -> sXT[d][0..3]
         for (int t = tid; t < kTM * D; t += kThreads) {
@@ -416,8 +419,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, c
         __syncthreads();
       }
       // -------- pass 2: online weights; [s'; s] rows
+      RMC_STAMP(C, 3);
       stage_params(sW, C.online, L.total, bar, parity);
       wait_params(bar, parity);
+      RMC_STAMP(C, 4);
       float loss_local = 0.f;   // thread 0 accumulates this CTA's tiles in order
       for (long long tile = cta; tile < n_tiles; tile += S.n_row_ctas) {
         for (int t = tid; t < kR * D; t += kThreads) {
@@ -541,6 +546,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, c
         __syncthreads();
       }
       if (tid == 0) C.loss_part[cta] = loss_local;
+      RMC_STAMP(C, 5);
     }
   } else if (do_rows && (S.phases & 2) && tid == 0 && cta < S.n_row_ctas) {
     C.loss_part[cta] = 0.f;
@@ -549,6 +555,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, c
   const int phaseB = S.phases & (4 | 8 | 16 | 32 | 64);
   if (!phaseB) return;
   if (do_rows) agent_barrier(C.barrier, S.barrier_target);
+  RMC_STAMP(C, 6);
 
   // ---------------------------------------------------------------- phase B
   const bool tree_here = per && (S.phases & 4) && C.rp.prioritized && B <= kTreeCtaMax;
@@ -557,6 +564,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, c
     n_workers = G - 1;
     if (cta == G - 1) {
       tree_update_cta(C.rp, C.nodes, C.pri, B, C.rp.st->size, true);
+      RMC_STAMP(C, 7);
       return;
     }
   }
@@ -581,6 +589,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, c
     __syncthreads();
     tree_update_cta(C.rp, C.nodes, C.pri, B, C.rp.st->size, true);
   }
+  RMC_STAMP(C, 7);
 }
 
 // ------------------------------------------------------------------ batched act / Q values
