@@ -116,7 +116,8 @@ __global__ void k_fill_f32(float* p, long long n, float v) {
   if (i < n) p[i] = v;
 }
 __global__ void k_init_state(ReplayState* st) {
-  st->size = 0; st->dp = 0; st->max_p = 0.f; st->min_p = __int_as_float(0x7f800000); st->push_p = 1.f; st->pad = 0;
+  st->size = 0; st->dp = 0; st->max_p = 0.f; st->min_p = __int_as_float(0x7f800000); st->cnt_max = 0; st->cnt_min = 0;
+  st->push_p = 1.f; st->pad = 0;
 }
 
 // ------------------------------------------------------------------------------ replay
@@ -134,8 +135,6 @@ extern "C" int32_t rmc_replay_create(rmc_replay_t** out, int64_t capacity, int32
   r->n_nodes = 2 * capacity - 1;
   ReplayDev& d = r->dev;
   d.cap = capacity; d.row_floats = r->rf; d.obs_dim = obs_dim; d.prioritized = r->prioritized;
-  d.n0 = (capacity + kBlk - 1) / kBlk;
-  d.n1 = (d.n0 + kBlk - 1) / kBlk;
   int32_t e = RMC_OK;
   if ((e = dev_alloc(&d.ring, static_cast<size_t>(capacity) * r->rf))) return e;
   if ((e = dev_alloc(&d.st, 1))) return e;
@@ -144,15 +143,7 @@ extern "C" int32_t rmc_replay_create(rmc_replay_t** out, int64_t capacity, int32
   if (r->prioritized) {
     if ((e = dev_alloc(&d.tree, static_cast<size_t>(r->n_nodes)))) return e;
     if ((e = dev_alloc(&d.stamps, static_cast<size_t>(capacity)))) return e;
-    if ((e = dev_alloc(&d.b0min, static_cast<size_t>(d.n0), false))) return e;
-    if ((e = dev_alloc(&d.b0max, static_cast<size_t>(d.n0)))) return e;
-    if ((e = dev_alloc(&d.b1min, static_cast<size_t>(d.n1), false))) return e;
-    if ((e = dev_alloc(&d.b1max, static_cast<size_t>(d.n1)))) return e;
-    const float inf = INFINITY;
-    k_fill_f32<<<blocks_for(d.n0, 256), 256>>>(d.b0min, d.n0, inf);
-    RMC_KERNEL_OK();
-    k_fill_f32<<<blocks_for(d.n1, 256), 256>>>(d.b1min, d.n1, inf);
-    RMC_KERNEL_OK();
+    if ((e = dev_alloc(&d.scratch_old, kTreeCtaMax))) return e;
   }
   if ((e = dev_alloc(&r->scratch_nodes, kTreeCtaMax))) return e;
   if ((e = dev_alloc(&r->scratch_pri, kTreeCtaMax))) return e;
@@ -172,8 +163,7 @@ extern "C" int32_t rmc_replay_destroy(rmc_replay_t* r) {
   cudaSetDevice(r->device);
   cudaDeviceSynchronize();
   ReplayDev& d = r->dev;
-  cudaFree(d.ring); cudaFree(d.tree); cudaFree(d.stamps); cudaFree(d.b0min); cudaFree(d.b0max);
-  cudaFree(d.b1min); cudaFree(d.b1max); cudaFree(d.st); cudaFree(r->scratch_nodes); cudaFree(r->scratch_pri);
+  cudaFree(d.ring); cudaFree(d.tree); cudaFree(d.stamps); cudaFree(d.scratch_old); cudaFree(d.st); cudaFree(r->scratch_nodes); cudaFree(r->scratch_pri);
   for (int s = 0; s < kStageSlots; ++s) {
     if (r->pin[s]) cudaFreeHost(r->pin[s]);
     cudaFree(r->dstage[s]);
@@ -199,11 +189,12 @@ static int32_t tree_rebuild(rmc_replay* r, cudaStream_t st) {
   return RMC_OK;
 }
 static int32_t minmax_rebuild(rmc_replay* r, cudaStream_t st) {
-  k_minmax_l0_all<<<blocks_for(r->dev.n0, 256), 256, 0, st>>>(r->dev);
+  k_extremes_reset<<<1, 1, 0, st>>>(r->dev);
   RMC_KERNEL_OK();
-  k_minmax_l1_all<<<blocks_for(r->dev.n1, 256), 256, 0, st>>>(r->dev);
+  const unsigned grid = std::max(1u, std::min(1184u, blocks_for(r->cap, 256)));
+  k_extremes_pass1<<<grid, 256, 0, st>>>(r->dev);
   RMC_KERNEL_OK();
-  k_minmax_global<<<1, 32, 0, st>>>(r->dev);
+  k_extremes_pass2<<<grid, 256, 0, st>>>(r->dev);
   RMC_KERNEL_OK();
   return RMC_OK;
 }

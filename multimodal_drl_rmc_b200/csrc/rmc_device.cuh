@@ -18,7 +18,7 @@ constexpr int kWarps = 8;
 constexpr int kMaxD = 32;
 constexpr int kMaxRowFloats = 68;   // round4(2*32+3)
 constexpr int kQLD = 16;        // leading dim of per-sample Q rows (A <= 15, heads <= 16)
-constexpr int kBlk = 64;        // fan-in of the two min/max summary levels over the leaves
+constexpr int kTopNodes = 1023;  // tree[0..1023) = the top 10 levels, cached in shared memory by the sampler
 constexpr int kTreeCtaMax = 4096;  // batches up to this size get their tree write-back from one CTA
 
 // ----------------------------------------------------------------------------- PTX helpers
@@ -145,6 +145,8 @@ struct ReplayState {   // lives in HBM, updated by the kernels themselves
   long long dp;
   float max_p;       // max(leaves[:size])  (0 when empty)
   float min_p;       // min(leaves[:size])  (+inf when empty)
+  long long cnt_max; // number of leaves equal to max_p
+  long long cnt_min; // number of leaves equal to min_p
   float push_p;      // priority given to the rows of the current (chunked) push call
   int pad;
 };
@@ -153,13 +155,9 @@ struct ReplayDev {
   float* ring;       // [cap][row_floats]
   double* tree;      // [2*cap-1]  reference heap layout (dqn/utils/sum_tree.py:6-13)
   int* stamps;       // [cap]   last-writer election for duplicate leaves in a batch
-  float* b0min;      // [n0] min / max over blocks of kBlk leaves (only leaves < size)
-  float* b0max;
-  float* b1min;      // [n1] min / max over blocks of kBlk level-0 entries
-  float* b1max;
+  float* scratch_old;// [kTreeCtaMax] overwritten leaf values of the batch being applied
   ReplayState* st;
   long long cap;
-  long long n0, n1;
   int row_floats;
   int obs_dim;
   int prioritized;

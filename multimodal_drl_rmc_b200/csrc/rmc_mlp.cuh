@@ -33,6 +33,10 @@ struct SmemPlan {
   int dh;       // [kTM][kQLD]
   int meta;     // [kTM][4]  action(bits), reward, done, is_w
   int red;      // [kWarps] loss partials
+  int rows;     // [kTM][kMaxRowFloats] gathered rows of the CTA's tile (single-tile fast path)
+  int qt;       // [kTM][kQLD] Q_target(s') of the tile
+  int isw;      // [kTM] importance weights of the tile
+  int top;      // [kTopNodes] float64: top levels of the sum tree (8-byte aligned)
   int bar;      // mbarrier (8 bytes, 8-byte aligned)
   int total_floats;
 };
@@ -49,6 +53,11 @@ __host__ __device__ inline SmemPlan make_smem_plan(int param_floats) {
   s.dh = o; o += kTM * kQLD;
   s.meta = o; o += kTM * 4;
   s.red = o; o += kWarps;
+  s.rows = o; o += kTM * kMaxRowFloats;
+  s.qt = o; o += kTM * kQLD;
+  s.isw = o; o += kTM;
+  o = (o + 3) & ~3;
+  s.top = o; o += 2 * kTopNodes + 2;
   o = (o + 3) & ~3;
   s.bar = o; o += 4;
   s.total_floats = o;
@@ -193,10 +202,19 @@ __device__ __forceinline__ void wait_params(uint64_t* bar, uint32_t& parity) {
 }
 
 // ------------------------------------------------------------------ Adam / Polyak on one element
-__device__ __forceinline__ void adam_polyak_element(const AgentCtx& C, const StepScalars& S, int pi, float g) {
-  float p = C.online[pi];
+struct ParamVals { float p, m, v, t; };
+__device__ __forceinline__ ParamVals param_load(const AgentCtx& C, const StepScalars& S, int pi) {
+  ParamVals x;
+  x.p = __ldcg(C.online + pi);
+  x.m = (S.phases & 16) ? __ldcg(C.adam_m + pi) : 0.f;
+  x.v = (S.phases & 16) ? __ldcg(C.adam_v + pi) : 0.f;
+  x.t = (S.phases & 32) ? __ldcg(C.target + pi) : 0.f;
+  return x;
+}
+__device__ __forceinline__ void param_apply(const AgentCtx& C, const StepScalars& S, int pi, float g, ParamVals x) {
+  float p = x.p;
   if (S.phases & 16 /*ADAM*/) {
-    float m = C.adam_m[pi], v = C.adam_v[pi];
+    float m = x.m, v = x.v;
     // Rounding sequence of torch 2.11's CPU kernels, found by bit-matching torch.optim.Adam
     // (tests/test_oracle_golden.py::test_numpy_adam_bit_matches_torch): lerp and addcmul are FMAs.
     m = fmaf(S.adam_w1, g - m, m);                     // exp_avg.lerp_(grad, 1-beta1)
@@ -208,10 +226,20 @@ __device__ __forceinline__ void adam_polyak_element(const AgentCtx& C, const Ste
     C.adam_v[pi] = v;
   }
   if (S.phases & 32 /*POLYAK: dqn/agent.py:105-110, post-Adam weights*/) {
-    C.target[pi] = S.polyak_k * p + S.polyak_1mk * C.target[pi];
+    C.target[pi] = S.polyak_k * p + S.polyak_1mk * x.t;
   } else if (S.phases & 64 /*HARDSYNC: dqn/agent.py:102-103*/) {
     C.target[pi] = p;
   }
+}
+__device__ __forceinline__ void adam_polyak_element(const AgentCtx& C, const StepScalars& S, int pi, float g) {
+  param_apply(C, S, pi, g, param_load(C, S, pi));
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
 
 // ------------------------------------------------------------------ phase B: one 32x32 gradient tile
@@ -239,19 +267,22 @@ __device__ void wgrad_unit(const AgentCtx& C, const StepScalars& S, const GemmUn
 #pragma unroll
   for (int j = 0; j < 8; ++j) bsum[j] = 0.f;
 
+  // 16-byte chunks per staged row; columns past the valid ones are zeroed once and never written
+  const int ca = min(8, (U.m_valid + 3) >> 2), cb = min(8, (U.n_valid + 3) >> 2), cab = ca + cb;
+  __syncthreads();
+  if (cab < 16) {
+    for (int t = tid; t < 2 * kGChunk * kGTile; t += kThreads) As[t] = 0.f;
+    __syncthreads();
+  }
   for (long long b0 = 0; b0 < S.B; b0 += kGChunk) {
     const int rows = static_cast<int>(min(static_cast<long long>(kGChunk), S.B - b0));
-    __syncthreads();
-    for (int t = tid; t < kGChunk * kGTile; t += kThreads) {
-      const int r = t >> 5, c = t & 31;
-      float a = 0.f, b = 0.f;
-      if (r < rows) {
-        if (c < U.m_valid) a = __ldcg(U.A + (b0 + r) * U.lda + U.m0 + c);
-        if (c < U.n_valid) b = __ldcg(U.Bm + (b0 + r) * U.ldb + U.n0 + c);
-      }
-      As[t] = a;
-      Bs[t] = b;
+    if (b0 > 0) __syncthreads();
+    for (int t = tid; t < rows * cab; t += kThreads) {      // LDGSTS: all copies of the chunk in flight at once
+      const int r = t / cab, c = t - r * cab;
+      if (c < ca) cp_async16(As + r * kGTile + 4 * c, U.A + (b0 + r) * U.lda + U.m0 + 4 * c);
+      else cp_async16(Bs + r * kGTile + 4 * (c - ca), U.Bm + (b0 + r) * U.ldb + U.n0 + 4 * (c - ca));
     }
+    cp_async_wait_all();
     __syncthreads();
     // warp w takes rows w, w+8, ... (fixed order -> deterministic sums)
     for (int r = warp; r < rows; r += kWarps) {
@@ -280,15 +311,28 @@ __device__ void wgrad_unit(const AgentCtx& C, const StepScalars& S, const GemmUn
     for (int j = 0; j < 8; ++j) Pb[warp * kGTile + ng * 8 + j] = bsum[j];
   }
   __syncthreads();
-  for (int o = tid; o < kGTile * kGTile; o += kThreads) {
-    const int m = o >> 5, n = o & 31;
-    if (m < U.m_valid && n < U.n_valid) {
-      float g = 0.f;
+  {
+    // four outputs per thread: all parameter loads first (independent, one L2 round trip), then the updates
+    float g[4];
+    int pi[4];
+    ParamVals pv[4];
 #pragma unroll
-      for (int w = 0; w < kWarps; ++w) g += Ps[w * (kGTile * kGTile) + o];
-      const int pi = U.out_base + m * U.out_sm + n * U.out_sn;
-      C.grads[pi] = g;
-      adam_polyak_element(C, S, pi, g);
+    for (int q = 0; q < 4; ++q) {
+      const int o = tid + q * kThreads;
+      const int m = o >> 5, n = o & 31;
+      pi[q] = (m < U.m_valid && n < U.n_valid) ? U.out_base + m * U.out_sm + n * U.out_sn : -1;
+      float acc_g = 0.f;
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) acc_g += Ps[w * (kGTile * kGTile) + o];
+      g[q] = acc_g;
+      if (pi[q] >= 0) pv[q] = param_load(C, S, pi[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (pi[q] >= 0) {
+        C.grads[pi[q]] = g[q];
+        param_apply(C, S, pi[q], g[q], pv[q]);
+      }
     }
   }
   if (U.bias_base >= 0 && tid < kGTile && tid < U.n_valid) {
@@ -346,6 +390,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, c
   float* sDH = smem + P.dh;
   float* sMeta = smem + P.meta;
   float* sRed = smem + P.red;
+  float* sRows = smem + P.rows;
+  float* sQT = smem + P.qt;
+  float* sIsw = smem + P.isw;
+  double* sTop = reinterpret_cast<double*>(smem + P.top);
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + P.bar);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -361,7 +409,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, c
   RMC_STAMP(C, 0);
 
   if (do_rows && cta < S.n_row_ctas && cta < n_tiles) {
+    const bool single = n_tiles <= S.n_row_ctas;   // every CTA owns at most one tile: rows / Q_target stay in smem
+    const long long n_nodes = 2 * C.rp.cap - 1;
+    const int n_top = static_cast<int>(min(static_cast<long long>(kTopNodes), n_nodes));
     if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+    if ((S.phases & 1) && C.rp.prioritized)        // top levels of the tree: one coalesced read, then smem descents
+      for (int t = tid; t < n_top; t += kThreads) sTop[t] = __ldcg(C.rp.tree + t);
     __syncthreads();
     const bool do_fwd = (S.phases & 2) != 0;
     if (do_fwd) stage_params(sW, C.target, L.total, bar, parity);
@@ -382,7 +435,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, c
               const double ui = (S.u != nullptr) ? S.u[agent * B + i] : philox_uniform(S.seed, S.counter, agent, static_cast<uint32_t>(gi));
               const double v = stratum_value(total, S.Bglobal, gi, ui);
               double p;
-              node = per_descend_warp(C.rp.tree, 2 * C.rp.cap - 1, v, &p);
+              node = per_descend_cached(sTop, n_top, C.rp.tree, n_nodes, v, &p);
               slot = node - first_leaf;
               w = static_cast<float>(is_weight(static_cast<double>(size), p, total, min_p, S.beta));
             } else {
@@ -391,8 +444,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, c
               slot = deque_pos_to_slot(pos, size, dp, C.rp.cap);
               node = slot;
             }
-            if (lane == 0) { C.nodes[i] = node; C.is_w[i] = w; }
-            gather_row_warp(C.rp, slot, C.X + i * rf);
+            if (lane == 0) { C.nodes[i] = node; C.is_w[i] = w; sIsw[warp] = w; }
+            gather_row_warp2(C.rp, slot, C.X + i * rf, sRows + warp * kMaxRowFloats);
           }
         }
       }
@@ -407,13 +460,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, c
         for (int t = tid; t < kTM * D; t += kThreads) {
           const int r = t / D, d = t % D;
           const long long i = tile * kTM + r;
-          sXT[d * kR + r] = (i < B) ? __ldcg(C.X + i * rf + D + d) : 0.f;
+          sXT[d * kR + r] = (i < B) ? (single ? sRows[r * kMaxRowFloats + D + d] : __ldcg(C.X + i * rf + D + d)) : 0.f;
         }
         __syncthreads();
         mlp_forward<kTM>(sW, L, sXT, sH1T, sH2, sPart, sQ, nullptr);
         if (tid < kTM * kQLD) {
           const int r = tid / kQLD;
           const long long i = tile * kTM + r;
+          sQT[tid] = sQ[tid];
           if (i < B) C.QT[i * kQLD + (tid % kQLD)] = sQ[tid];
         }
         __syncthreads();
@@ -429,15 +483,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, c
           const int r = t / D, d = t % D;
           const long long i = tile * kTM + (r % kTM);
           const int col = (r < kTM) ? (D + d) : d;   // rows 0..3: s', rows 4..7: s
-          sXT[d * kR + r] = (i < B) ? __ldcg(C.X + i * rf + col) : 0.f;
+          sXT[d * kR + r] = (i < B) ? (single ? sRows[(r % kTM) * kMaxRowFloats + col] : __ldcg(C.X + i * rf + col)) : 0.f;
         }
         if (tid < kTM) {
           const long long i = tile * kTM + tid;
           const bool ok = i < B;
-          sMeta[tid * 4 + 0] = ok ? __ldcg(C.X + i * rf + 2 * D) : 0.f;
-          sMeta[tid * 4 + 1] = ok ? __ldcg(C.X + i * rf + 2 * D + 1) : 0.f;
-          sMeta[tid * 4 + 2] = ok ? __ldcg(C.X + i * rf + 2 * D + 2) : 0.f;
-          sMeta[tid * 4 + 3] = ok ? C.is_w[i] : 0.f;
+          const float* row = sRows + tid * kMaxRowFloats;
+          sMeta[tid * 4 + 0] = ok ? (single ? row[2 * D] : __ldcg(C.X + i * rf + 2 * D)) : 0.f;
+          sMeta[tid * 4 + 1] = ok ? (single ? row[2 * D + 1] : __ldcg(C.X + i * rf + 2 * D + 1)) : 0.f;
+          sMeta[tid * 4 + 2] = ok ? (single ? row[2 * D + 2] : __ldcg(C.X + i * rf + 2 * D + 2)) : 0.f;
+          sMeta[tid * 4 + 3] = ok ? (single ? sIsw[tid] : __ldcg(C.is_w + i)) : 0.f;
         }
         __syncthreads();
         mlp_forward<kR>(sW, L, sXT, sH1T, sH2, sPart, sQ, nullptr);
@@ -448,14 +503,19 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, c
           float g = 0.f, lterm = 0.f;
           int act = 0;
           if (i < B) {
-            const float* qt = C.QT + i * kQLD;
+            float qtv[kQLD];
+#pragma unroll
+            for (int a = 0; a < kQLD; ++a) qtv[a] = single ? sQT[r * kQLD + a] : __ldcg(C.QT + i * kQLD + a);
             float qsel;
             if (S.double_dqn) {                                   // dqn/agent.py:252-256
               const int astar = argmax_first(sQ + r * kQLD, L.A);
-              qsel = __ldcg(qt + astar);
+              qsel = qtv[0];
+#pragma unroll
+              for (int a = 1; a < kQLD; ++a) qsel = (a == astar) ? qtv[a] : qsel;
             } else {                                              // dqn/agent.py:172-173
-              qsel = __ldcg(qt);
-              for (int a = 1; a < L.A; ++a) qsel = fmaxf(qsel, __ldcg(qt + a));
+              qsel = qtv[0];
+#pragma unroll
+              for (int a = 1; a < kQLD; ++a) qsel = (a < L.A) ? fmaxf(qsel, qtv[a]) : qsel;
             }
             act = __float_as_int(sMeta[r * 4 + 0]);
             const float rew = sMeta[r * 4 + 1], done = sMeta[r * 4 + 2], w = sMeta[r * 4 + 3];
@@ -563,7 +623,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, c
   if (tree_here && G > 1) {
     n_workers = G - 1;
     if (cta == G - 1) {
-      tree_update_cta(C.rp, C.nodes, C.pri, B, C.rp.st->size, true);
+      const long long tsize = C.rp.st->size;
+      tree_update_cta(C.rp, C.nodes, C.pri, B, tsize, tsize, true);
       RMC_STAMP(C, 7);
       return;
     }
@@ -587,7 +648,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, c
   }
   if (tree_here && G == 1) {
     __syncthreads();
-    tree_update_cta(C.rp, C.nodes, C.pri, B, C.rp.st->size, true);
+    const long long tsize = C.rp.st->size;
+    tree_update_cta(C.rp, C.nodes, C.pri, B, tsize, tsize, true);
   }
   RMC_STAMP(C, 7);
 }

@@ -7,8 +7,8 @@
 //                                           finding 6, so atomics are bit-identical to the
 //                                           reference's sequential propagation)
 //   dqn/utils/sum_tree.py:42-61  get_leaf-> per_descend_warp (same `v <= left` / `v -= left`)
-//   dqn/utils/sum_tree.py:67-73  max/min -> values of max/min(leaves[:size]) kept by two summary
-//                                           levels (fan-in kBlk) instead of index tracking + rescans
+//   dqn/utils/sum_tree.py:67-73  max/min -> values of max/min(leaves[:size]) tracked as (value,
+//                                           multiplicity) instead of index tracking + O(N) rescans
 #pragma once
 #include "rmc_device.cuh"
 
@@ -18,7 +18,7 @@ __device__ __forceinline__ float finf() { return __int_as_float(0x7f800000); }
 
 // ---- stratified prefix search: one warp per sample, 4 tree levels per L2 round trip -------------
 // All 32 lanes call with identical (v); returns the leaf's tree index on every lane.
-__device__ __forceinline__ long long per_descend_warp(const double* __restrict__ tree, long long n_nodes,
+__device__ __forceinline__ long long per_descend_from(const double* __restrict__ tree, long long n_nodes, long long p,
                                                       double v, double* leaf_val) {
   const int lane = threadIdx.x & 31;
   int d = 0, o = 0;
@@ -26,7 +26,6 @@ __device__ __forceinline__ long long per_descend_warp(const double* __restrict__
     d = 31 - __clz(lane + 2);
     o = lane + 2 - (1 << d);
   }
-  long long p = 0;
   while (2 * p + 1 < n_nodes) {
     double val = 0.0;
     if (lane < 30) {
@@ -50,6 +49,22 @@ __device__ __forceinline__ long long per_descend_warp(const double* __restrict__
   *leaf_val = __ldcg(tree + p);
   return p;
 }
+__device__ __forceinline__ long long per_descend_warp(const double* __restrict__ tree, long long n_nodes, double v,
+                                                      double* leaf_val) {
+  return per_descend_from(tree, n_nodes, 0, v, leaf_val);
+}
+// same walk, the first levels served from a shared-memory copy of tree[0 .. n_top)
+__device__ __forceinline__ long long per_descend_cached(const double* __restrict__ s_top, int n_top,
+                                                        const double* __restrict__ tree, long long n_nodes, double v,
+                                                        double* leaf_val) {
+  long long p = 0;
+  while (2 * p + 2 < n_top) {          // both children cached
+    const double lv = s_top[2 * p + 1];
+    if (v <= lv) p = 2 * p + 1;
+    else { v = v - lv; p = 2 * p + 2; }
+  }
+  return per_descend_from(tree, n_nodes, p, v, leaf_val);
+}
 
 // value drawn in stratum i (dqn/replay_memory.py:72,80; np.random.uniform(lo,hi) == lo+(hi-lo)*u)
 __device__ __forceinline__ double stratum_value(double total, long long Bglobal, long long i, double u) {
@@ -72,58 +87,32 @@ __device__ __forceinline__ float td_to_priority(float abs_td, float eps, float a
   return static_cast<float>(pow(static_cast<double>(x), static_cast<double>(alpha)));
 }
 
-// ---- min/max summaries ----------------------------------------------------------------------
-__device__ __forceinline__ void minmax_l0(const ReplayDev& R, long long size, long long b) {
-  const double* leaves = R.tree + (R.cap - 1);
-  const long long lo = b * kBlk;
-  float mn = finf(), mx = 0.f;
-#pragma unroll 8
-  for (int j = 0; j < kBlk; ++j) {
-    const long long k = lo + j;
-    if (k < size) {
-      const float p = static_cast<float>(__ldcg(leaves + k));
-      mn = fminf(mn, p);
-      mx = fmaxf(mx, p);
-    }
-  }
-  R.b0min[b] = mn;
-  R.b0max[b] = mx;
-}
-__device__ __forceinline__ void minmax_l1(const ReplayDev& R, long long c) {
-  const long long lo = c * kBlk;
-  float mn = finf(), mx = 0.f;
-#pragma unroll 8
-  for (int j = 0; j < kBlk; ++j) {
-    const long long k = lo + j;
-    if (k < R.n0) {
-      mn = fminf(mn, __ldcg(R.b0min + k));
-      mx = fmaxf(mx, __ldcg(R.b0max + k));
-    }
-  }
-  R.b1min[c] = mn;
-  R.b1max[c] = mx;
-}
-// one warp
-__device__ __forceinline__ void minmax_global_warp(const ReplayDev& R) {
-  const int lane = threadIdx.x & 31;
-  float mn = finf(), mx = 0.f;
-  for (long long k = lane; k < R.n1; k += 32) {
-    mn = fminf(mn, __ldcg(R.b1min + k));
-    mx = fmaxf(mx, __ldcg(R.b1max + k));
-  }
+// ---- extreme tracking -------------------------------------------------------------------------
+// The reference keeps arg-max / arg-min leaf indices and rescans all leaves when the extreme leaf is
+// overwritten (dqn/utils/sum_tree.py:16-28); only the VALUES max/min(leaves[:size]) are observable
+// (replay_memory.py:57,76).  Here the state keeps (value, number of leaves holding it) for both
+// extremes: a batch update adjusts the counts exactly, and only when a count drops to zero (the last
+// leaf holding the extreme was overwritten by a non-extreme value -- probability ~ B*p_min/total per
+// step) are the leaves rescanned.
+
+__device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
-  for (int s = 16; s > 0; s >>= 1) {
-    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, s));
-    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, s));
-  }
-  if (lane == 0) {
-    R.st->min_p = mn;
-    R.st->max_p = mx;
-  }
+  for (int s = 16; s > 0; s >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, s));
+  return v;
+}
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, s));
+  return v;
+}
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+  return v;
 }
 
-// leaf store + exact ancestor fix-up for the elected writer of a leaf
-__device__ __forceinline__ void tree_set_leaf(const ReplayDev& R, long long leaf, float p) {
+// leaf store + exact ancestor fix-up for the elected writer of a leaf; returns the old leaf value
+__device__ __forceinline__ double tree_set_leaf(const ReplayDev& R, long long leaf, float p) {
   const double np = static_cast<double>(p);
   const double old = __ldcg(R.tree + leaf);
   R.tree[leaf] = np;
@@ -135,32 +124,116 @@ __device__ __forceinline__ void tree_set_leaf(const ReplayDev& R, long long leaf
       atomicAdd(R.tree + n, delta);
     }
   }
+  return old;
+}
+
+// full rescan of leaves[:size] by one CTA (rare path): exact extremes and their multiplicities
+__device__ void extremes_rescan_cta(const ReplayDev& R, long long size, float* s_f, int* s_i) {
+  const int tid = threadIdx.x, nt = blockDim.x, warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
+  const double* leaves = R.tree + (R.cap - 1);
+  float mx = 0.f, mn = finf();
+  for (long long k = tid; k < size; k += nt) {
+    const float p = static_cast<float>(__ldcg(leaves + k));
+    mx = fmaxf(mx, p);
+    mn = fminf(mn, p);
+  }
+  mx = warp_max(mx);
+  mn = warp_min(mn);
+  __syncthreads();
+  if (lane == 0) { s_f[warp] = mx; s_f[32 + warp] = mn; }
+  __syncthreads();
+  mx = 0.f; mn = finf();
+  for (int w = 0; w < nw; ++w) { mx = fmaxf(mx, s_f[w]); mn = fminf(mn, s_f[32 + w]); }
+  int cx = 0, cn = 0;
+  for (long long k = tid; k < size; k += nt) {
+    const float p = static_cast<float>(__ldcg(leaves + k));
+    cx += (p == mx);
+    cn += (p == mn);
+  }
+  cx = warp_sum(cx);
+  cn = warp_sum(cn);
+  __syncthreads();
+  if (lane == 0) { s_i[warp] = cx; s_i[32 + warp] = cn; }
+  __syncthreads();
+  if (tid == 0) {
+    long long tx = 0, tn = 0;
+    for (int w = 0; w < nw; ++w) { tx += s_i[w]; tn += s_i[32 + w]; }
+    R.st->max_p = mx; R.st->min_p = mn; R.st->cnt_max = tx; R.st->cnt_min = tn;
+  }
 }
 
 // Whole write-back by ONE CTA (n <= kTreeCtaMax): duplicates -> last in batch order wins
-// (dqn/replay_memory.py:97-98 applies updates sequentially).
+// (dqn/replay_memory.py:97-98 applies updates sequentially).  old_size/new_size: number of valid
+// leaves before / after (they differ for pushes).
 __device__ void tree_update_cta(const ReplayDev& R, const long long* __restrict__ nodes,
-                                const float* __restrict__ pri, long long n, long long size, bool stamps_done) {
-  const int tid = threadIdx.x, nt = blockDim.x;
+                                const float* __restrict__ pri, long long n, long long old_size, long long new_size,
+                                bool stamps_done) {
+  __shared__ float s_f[64];
+  __shared__ int s_i[64];
+  __shared__ float s_ext[4];   // M0, m0, M1, m1
+  const int tid = threadIdx.x, nt = blockDim.x, warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
   const long long first_leaf = R.cap - 1;
   if (!stamps_done) {
     for (long long i = tid; i < n; i += nt) atomicMax(R.stamps + (nodes[i] - first_leaf), static_cast<int>(i + 1));
     __syncthreads();
   }
+  // pass 1: elected writers apply; remember the overwritten value (-1: leaf was outside the old domain,
+  // -2: not the elected writer); batch extremes of the NEW values
+  float bmax = 0.f, bmin = finf();
   for (long long i = tid; i < n; i += nt) {
     const long long leaf = nodes[i];
-    int* st = R.stamps + (leaf - first_leaf);
+    const long long di = leaf - first_leaf;
+    int* st = R.stamps + di;
+    float oldv = -2.f;
     if (__ldcg(st) == static_cast<int>(i + 1)) {
       *st = 0;
-      tree_set_leaf(R, leaf, pri[i]);
+      const float p = pri[i];
+      const double old = tree_set_leaf(R, leaf, p);
+      oldv = (di < old_size) ? static_cast<float>(old) : -1.f;
+      bmax = fmaxf(bmax, p);
+      bmin = fminf(bmin, p);
     }
+    R.scratch_old[i] = oldv;
+  }
+  bmax = warp_max(bmax);
+  bmin = warp_min(bmin);
+  if (lane == 0) { s_f[warp] = bmax; s_f[32 + warp] = bmin; }
+  __syncthreads();
+  if (tid == 0) {
+    float M = 0.f, m = finf();
+    for (int w = 0; w < nw; ++w) { M = fmaxf(M, s_f[w]); m = fminf(m, s_f[32 + w]); }
+    const float M0 = (old_size > 0) ? R.st->max_p : 0.f;
+    const float m0 = (old_size > 0) ? R.st->min_p : finf();
+    s_ext[0] = M0; s_ext[1] = m0; s_ext[2] = fmaxf(M0, M); s_ext[3] = fminf(m0, m);
   }
   __syncthreads();
-  for (long long i = tid; i < n; i += nt) minmax_l0(R, size, (nodes[i] - first_leaf) / kBlk);
+  const float M0 = s_ext[0], m0 = s_ext[1], M1 = s_ext[2], m1 = s_ext[3];
+  // pass 2: multiplicities
+  int a = 0, b = 0, c = 0, d = 0;   // new==M1, old==M0, new==m1, old==m0
+  for (long long i = tid; i < n; i += nt) {
+    const float oldv = R.scratch_old[i];
+    if (oldv != -2.f) {
+      const float p = pri[i];
+      a += (p == M1);
+      c += (p == m1);
+      if (oldv >= 0.f) { b += (oldv == M0); d += (oldv == m0); }
+    }
+  }
+  a = warp_sum(a); b = warp_sum(b); c = warp_sum(c); d = warp_sum(d);
   __syncthreads();
-  for (long long i = tid; i < n; i += nt) minmax_l1(R, ((nodes[i] - first_leaf) / kBlk) / kBlk);
+  if (lane == 0) { s_i[warp] = a; s_i[8 + warp] = b; s_i[16 + warp] = c; s_i[24 + warp] = d; }
   __syncthreads();
-  if (tid < 32) minmax_global_warp(R);
+  if (tid == 0) {
+    long long ta = 0, tb = 0, tc = 0, td = 0;
+    for (int w = 0; w < nw; ++w) { ta += s_i[w]; tb += s_i[8 + w]; tc += s_i[16 + w]; td += s_i[24 + w]; }
+    const long long c0M = (old_size > 0) ? R.st->cnt_max : 0, c0m = (old_size > 0) ? R.st->cnt_min : 0;
+    const long long cM = (M1 > M0) ? ta : c0M - tb + ta;
+    const long long cm = (m1 < m0) ? tc : c0m - td + tc;
+    R.st->max_p = M1; R.st->min_p = m1; R.st->cnt_max = cM; R.st->cnt_min = cm;
+    s_i[63] = (new_size > 0 && (cM <= 0 || cm <= 0)) ? 1 : 0;
+  }
+  __syncthreads();
+  if (s_i[63]) extremes_rescan_cta(R, new_size, s_f, s_i);
 }
 
 // ---- standalone kernels -------------------------------------------------------------------
@@ -174,7 +247,8 @@ __global__ void __launch_bounds__(kThreads) k_tree_update_small(ReplayDev R, con
     __syncthreads();
     pri = pri_out;
   }
-  tree_update_cta(R, nodes, pri, n, R.st->size, false);
+  const long long size = R.st->size;
+  tree_update_cta(R, nodes, pri, n, size, size, false);
 }
 
 // grid-wide variants for large batches
@@ -197,15 +271,43 @@ __global__ void k_tree_apply(ReplayDev R, const long long* nodes, const float* p
     }
   }
 }
-__global__ void k_minmax_l0_all(ReplayDev R) {
-  const long long b = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  if (b < R.n0) minmax_l0(R, R.st->size, b);
+// grid-wide rescan of the extremes (bulk paths): reset, pass 1 (values), pass 2 (multiplicities)
+__global__ void k_extremes_reset(ReplayDev R) {
+  R.st->max_p = 0.f; R.st->min_p = finf(); R.st->cnt_max = 0; R.st->cnt_min = 0;
 }
-__global__ void k_minmax_l1_all(ReplayDev R) {
-  const long long c = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  if (c < R.n1) minmax_l1(R, c);
+__global__ void __launch_bounds__(256) k_extremes_pass1(ReplayDev R) {
+  const long long size = R.st->size;
+  const double* leaves = R.tree + (R.cap - 1);
+  float mx = 0.f, mn = finf();
+  for (long long k = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; k < size; k += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float p = static_cast<float>(__ldcg(leaves + k));
+    mx = fmaxf(mx, p);
+    mn = fminf(mn, p);
+  }
+  mx = warp_max(mx);
+  mn = warp_min(mn);
+  if ((threadIdx.x & 31) == 0) {   // positive floats order like their bit patterns
+    atomicMax(reinterpret_cast<int*>(&R.st->max_p), __float_as_int(mx));
+    atomicMin(reinterpret_cast<int*>(&R.st->min_p), __float_as_int(mn));
+  }
 }
-__global__ void k_minmax_global(ReplayDev R) { minmax_global_warp(R); }
+__global__ void __launch_bounds__(256) k_extremes_pass2(ReplayDev R) {
+  const long long size = R.st->size;
+  const double* leaves = R.tree + (R.cap - 1);
+  const float mx = R.st->max_p, mn = R.st->min_p;
+  int cx = 0, cn = 0;
+  for (long long k = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; k < size; k += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float p = static_cast<float>(__ldcg(leaves + k));
+    cx += (p == mx);
+    cn += (p == mn);
+  }
+  cx = warp_sum(cx);
+  cn = warp_sum(cn);
+  if ((threadIdx.x & 31) == 0) {
+    if (cx) atomicAdd(reinterpret_cast<unsigned long long*>(&R.st->cnt_max), static_cast<unsigned long long>(cx));
+    if (cn) atomicAdd(reinterpret_cast<unsigned long long*>(&R.st->cnt_min), static_cast<unsigned long long>(cn));
+  }
+}
 
 // bottom-up rebuild of one heap level: nodes [first, first+count)
 __global__ void k_tree_rebuild_level(double* tree, long long first, long long count) {
@@ -266,7 +368,7 @@ __global__ void __launch_bounds__(kThreads) k_push_small(ReplayDev R, const floa
       scratch_pri[j] = p;
     }
     __syncthreads();
-    tree_update_cta(R, scratch_nodes, scratch_pri, n, new_size, false);
+    tree_update_cta(R, scratch_nodes, scratch_pri, n, s_size, new_size, false);
   }
   __syncthreads();
   if (tid == 0) {
@@ -296,6 +398,15 @@ __global__ void k_push_end(ReplayDev R, long long dp, long long size) {
 }
 
 // ---- standalone samplers (ReplayMemory*.sample_transitions) ---------------------------------
+__device__ __forceinline__ void gather_row_warp2(const ReplayDev& R, long long slot, float* __restrict__ dst, float* __restrict__ sdst) {
+  const int lane = threadIdx.x & 31;
+  const float* src = R.ring + slot * R.row_floats;
+  for (int c = lane; c < R.row_floats; c += 32) {
+    const float v = __ldcg(src + c);
+    dst[c] = v;
+    sdst[c] = v;
+  }
+}
 __device__ __forceinline__ void gather_row_warp(const ReplayDev& R, long long slot, float* __restrict__ dst) {
   const int lane = threadIdx.x & 31;
   const float* src = R.ring + slot * R.row_floats;
