@@ -476,6 +476,7 @@ extern "C" int32_t rmc_learner_create(rmc_learner_t** out, const rmc_net_spec_t*
   c.online = l->blobs[0]; c.target = l->blobs[1]; c.adam_m = l->blobs[2]; c.adam_v = l->blobs[3]; c.grads = l->blobs[4];
   const size_t B = static_cast<size_t>(max_batch);
   if ((e = owned_alloc(l, &c.nodes, B))) return e;
+  if ((e = owned_alloc(l, &c.leaf_p, B))) return e;
   float** per_sample[] = {&c.is_w, &c.q_sa, &c.y, &c.abs_td, &c.hub, &c.pri, &c.gcoef};
   for (float** p : per_sample)
     if ((e = owned_alloc(l, p, B))) return e;
@@ -603,7 +604,7 @@ static int32_t check_step(const rmc_learner* l, const rmc_replay* r, const rmc_s
 
 static int grid_for(const rmc_learner* l, long long B, int max_ctas) {
   const long long n_tiles = (B + kTM - 1) / kTM;
-  const int want = static_cast<int>(std::min<long long>(max_ctas, std::max<long long>(n_tiles, 46)));
+  const int want = static_cast<int>(std::min<long long>(max_ctas, std::max<long long>(n_tiles, 154)));
   return std::max(1, std::min(want, max_ctas));
 }
 
@@ -630,7 +631,9 @@ extern "C" int32_t rmc_learner_step(rmc_learner_t* l, rmc_replay_t* r, const rmc
   if (rows && phase_b) l->barrier_count = S.barrier_target;
   g_launches.fetch_add(1, std::memory_order_relaxed);
   if ((a->phases & RMC_PH_PRIORITY) && l->spec.prioritized && a->batch > kTreeCtaMax) {
-    if (int32_t e = tree_update_large(r, l->ctx.nodes, l->ctx.pri, a->batch, true, st)) return e;
+    k_td_to_pri<<<blocks_for(a->batch, 256), 256, 0, st>>>(l->ctx.abs_td, l->ctx.pri, a->batch, S.per_eps, S.per_alpha, S.per_pmax);
+    RMC_KERNEL_OK();
+    if (int32_t e = tree_update_large(r, l->ctx.nodes, l->ctx.pri, a->batch, false, st)) return e;
   }
   return RMC_OK;
 }

@@ -175,6 +175,7 @@ struct AgentCtx {
   float *online, *target, *adam_m, *adam_v, *grads;
   // per-sample products of the last step
   long long* nodes;     // [B] tree node (PER) or ring slot (uniform)
+  double* leaf_p;       // [B] priority of the sampled leaf (its tree value at sampling time)
   float *is_w, *q_sa, *y, *abs_td, *hub, *pri, *gcoef;
   float *QT, *QN, *Q;   // [B][kQLD]  Q_target(s'), Q_online(s'), Q_online(s)
   float *X;             // [B][row_floats] gathered rows

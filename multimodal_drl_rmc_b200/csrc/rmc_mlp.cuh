@@ -65,7 +65,7 @@ __host__ __device__ inline SmemPlan make_smem_plan(int param_floats) {
 }
 // phase-B staging (reuses the same dynamic shared memory)
 constexpr int kGChunk = 256;                         // batch rows staged per chunk
-constexpr int kGTile = 32;                           // 32 x 32 outputs per unit
+constexpr int kGTile = 16;                           // 16 x 16 outputs per unit (one per thread)
 constexpr int kGemmSmemFloats = 2 * kGChunk * kGTile + kWarps * kGTile * kGTile + kWarps * kGTile;
 
 // ------------------------------------------------------------------ forward of R rows (R = 4 or 8)
@@ -252,25 +252,26 @@ struct GemmUnit {
 };
 
 __device__ void wgrad_unit(const AgentCtx& C, const StepScalars& S, const GemmUnit& U, float* smem) {
-  float* As = smem;                               // [kGChunk][32]
-  float* Bs = smem + kGChunk * kGTile;            // [kGChunk][32]
-  float* Ps = Bs + kGChunk * kGTile;              // [kWarps][32*32]
-  float* Pb = Ps + kWarps * kGTile * kGTile;      // [kWarps][32]
+  float* As = smem;                               // [kGChunk][16]
+  float* Bs = smem + kGChunk * kGTile;            // [kGChunk][16]
+  float* Ps = Bs + kGChunk * kGTile;              // [kWarps][16*16]
+  float* Pb = Ps + kWarps * kGTile * kGTile;      // [kWarps][16]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int mg = lane >> 2, ng = lane & 3;        // lane tile: 4 m x 8 n
-  float acc[4][8];
-  float bsum[8];
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) bsum[j] = 0.f;
+  const int mg = lane >> 2, ng = lane & 3;        // lane tile: 2 m x 4 n
+  // this thread's output element and (prefetched) parameter state: independent of the gradient
+  const int om = tid >> 4, on = tid & 15;
+  const int pi = (om < U.m_valid && on < U.n_valid) ? U.out_base + om * U.out_sm + on * U.out_sn : -1;
+  const int pb = (U.bias_base >= 0 && tid < U.n_valid && tid < kGTile) ? U.bias_base + tid : -1;
+  ParamVals pv{}, pvb{};
+  if (pi >= 0) pv = param_load(C, S, pi);
+  if (pb >= 0) pvb = param_load(C, S, pb);
+  float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+  float bsum[4] = {0.f, 0.f, 0.f, 0.f};
 
   // 16-byte chunks per staged row; columns past the valid ones are zeroed once and never written
-  const int ca = min(8, (U.m_valid + 3) >> 2), cb = min(8, (U.n_valid + 3) >> 2), cab = ca + cb;
+  const int ca = min(4, (U.m_valid + 3) >> 2), cb = min(4, (U.n_valid + 3) >> 2), cab = ca + cb;
   __syncthreads();
-  if (cab < 16) {
+  if (cab < 8) {
     for (int t = tid; t < 2 * kGChunk * kGTile; t += kThreads) As[t] = 0.f;
     __syncthreads();
   }
@@ -285,87 +286,67 @@ __device__ void wgrad_unit(const AgentCtx& C, const StepScalars& S, const GemmUn
     cp_async_wait_all();
     __syncthreads();
     // warp w takes rows w, w+8, ... (fixed order -> deterministic sums)
+#pragma unroll 4
     for (int r = warp; r < rows; r += kWarps) {
-      const float4 a4 = *reinterpret_cast<const float4*>(As + r * kGTile + mg * 4);
-      const float4 b0v = *reinterpret_cast<const float4*>(Bs + r * kGTile + ng * 8);
-      const float4 b1v = *reinterpret_cast<const float4*>(Bs + r * kGTile + ng * 8 + 4);
-      const float a[4] = {a4.x, a4.y, a4.z, a4.w};
-      const float b[8] = {b0v.x, b0v.y, b0v.z, b0v.w, b1v.x, b1v.y, b1v.z, b1v.w};
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) bsum[j] += b[j];
+      const float2 a2 = *reinterpret_cast<const float2*>(As + r * kGTile + mg * 2);
+      const float4 b4 = *reinterpret_cast<const float4*>(Bs + r * kGTile + ng * 4);
+      acc[0][0] = fmaf(a2.x, b4.x, acc[0][0]); acc[0][1] = fmaf(a2.x, b4.y, acc[0][1]);
+      acc[0][2] = fmaf(a2.x, b4.z, acc[0][2]); acc[0][3] = fmaf(a2.x, b4.w, acc[0][3]);
+      acc[1][0] = fmaf(a2.y, b4.x, acc[1][0]); acc[1][1] = fmaf(a2.y, b4.y, acc[1][1]);
+      acc[1][2] = fmaf(a2.y, b4.z, acc[1][2]); acc[1][3] = fmaf(a2.y, b4.w, acc[1][3]);
+      bsum[0] += b4.x; bsum[1] += b4.y; bsum[2] += b4.z; bsum[3] += b4.w;
     }
   }
   // cross-warp reduction in fixed order
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    float* pp = Ps + warp * (kGTile * kGTile) + (mg * 4 + i) * kGTile + ng * 8;
-    *reinterpret_cast<float4*>(pp) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-    *reinterpret_cast<float4*>(pp + 4) = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
-  }
-  if (mg == 0) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) Pb[warp * kGTile + ng * 8 + j] = bsum[j];
-  }
+  for (int i = 0; i < 2; ++i)
+    *reinterpret_cast<float4*>(Ps + warp * (kGTile * kGTile) + (mg * 2 + i) * kGTile + ng * 4) =
+        make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+  if (mg == 0) *reinterpret_cast<float4*>(Pb + warp * kGTile + ng * 4) = make_float4(bsum[0], bsum[1], bsum[2], bsum[3]);
   __syncthreads();
-  {
-    // four outputs per thread: all parameter loads first (independent, one L2 round trip), then the updates
-    float g[4];
-    int pi[4];
-    ParamVals pv[4];
+  if (pi >= 0) {
+    float g = 0.f;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int o = tid + q * kThreads;
-      const int m = o >> 5, n = o & 31;
-      pi[q] = (m < U.m_valid && n < U.n_valid) ? U.out_base + m * U.out_sm + n * U.out_sn : -1;
-      float acc_g = 0.f;
-#pragma unroll
-      for (int w = 0; w < kWarps; ++w) acc_g += Ps[w * (kGTile * kGTile) + o];
-      g[q] = acc_g;
-      if (pi[q] >= 0) pv[q] = param_load(C, S, pi[q]);
-    }
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      if (pi[q] >= 0) {
-        C.grads[pi[q]] = g[q];
-        param_apply(C, S, pi[q], g[q], pv[q]);
-      }
-    }
+    for (int w = 0; w < kWarps; ++w) g += Ps[w * (kGTile * kGTile) + tid];
+    C.grads[pi] = g;
+    param_apply(C, S, pi, g, pv);
   }
-  if (U.bias_base >= 0 && tid < kGTile && tid < U.n_valid) {
+  if (pb >= 0) {
     float g = 0.f;
 #pragma unroll
     for (int w = 0; w < kWarps; ++w) g += Pb[w * kGTile + tid];
-    const int pi = U.bias_base + tid;
-    C.grads[pi] = g;
-    adam_polyak_element(C, S, pi, g);
+    C.grads[pb] = g;
+    param_apply(C, S, pb, g, pvb);
   }
   __syncthreads();
 }
 
-__device__ __forceinline__ int wgrad_unit_count(const NetLayout& L) { return kH1 / 32 + (kH1 / 32) * (kH2 / 32) + kH2 / 32; }
+__device__ __forceinline__ int wgrad_unit_count(const NetLayout& L) {
+  const int mt0 = (L.D + kGTile - 1) / kGTile;
+  return mt0 * (kH1 / kGTile) + (kH1 / kGTile) * (kH2 / kGTile) + kH2 / kGTile;
+}
 
 __device__ __forceinline__ GemmUnit make_unit(const AgentCtx& C, int u) {
   const NetLayout& L = C.L;
   GemmUnit U;
-  const int n_w0 = kH1 / 32, n_w2 = (kH1 / 32) * (kH2 / 32);
+  const int T = kGTile;
+  const int mt0 = (L.D + T - 1) / T;
+  const int n_w0 = mt0 * (kH1 / T), n_w2 = (kH1 / T) * (kH2 / T);
   if (u < n_w0) {                       // dW0^T[d][i] = sum_b X[b][d] * DZ1[b][i] ; db0 = colsum(DZ1)
-    U.A = C.X; U.lda = C.rp.row_floats; U.m0 = 0; U.m_valid = L.D;
-    U.Bm = C.DZ1; U.ldb = kH1; U.n0 = u * 32; U.n_valid = 32;
-    U.out_base = L.off_w0t + U.n0; U.out_sm = kH1; U.out_sn = 1;
-    U.bias_base = L.off_b0 + U.n0;
+    const int mt = u / (kH1 / T), nt = u % (kH1 / T);
+    U.A = C.X; U.lda = C.rp.row_floats; U.m0 = mt * T; U.m_valid = min(T, L.D - mt * T);
+    U.Bm = C.DZ1; U.ldb = kH1; U.n0 = nt * T; U.n_valid = T;
+    U.out_base = L.off_w0t + U.m0 * kH1 + U.n0; U.out_sm = kH1; U.out_sn = 1;
+    U.bias_base = (mt == 0) ? L.off_b0 + U.n0 : -1;
   } else if (u < n_w0 + n_w2) {         // dW2^T[k][j] = sum_b H1[b][k] * DZ2[b][j] ; db2 = colsum(DZ2)
-    const int v = u - n_w0, kt = v / (kH2 / 32), jt = v % (kH2 / 32);
-    U.A = C.H1; U.lda = kH1; U.m0 = kt * 32; U.m_valid = 32;
-    U.Bm = C.DZ2; U.ldb = kH2; U.n0 = jt * 32; U.n_valid = 32;
+    const int v = u - n_w0, kt = v / (kH2 / T), jt = v % (kH2 / T);
+    U.A = C.H1; U.lda = kH1; U.m0 = kt * T; U.m_valid = T;
+    U.Bm = C.DZ2; U.ldb = kH2; U.n0 = jt * T; U.n_valid = T;
     U.out_base = L.off_w2t + U.m0 * kW2LD + U.n0; U.out_sm = kW2LD; U.out_sn = 1;
     U.bias_base = (kt == 0) ? L.off_b2 + U.n0 : -1;
   } else {                              // dWh[a][j] = sum_b H2[b][j] * DH[b][a] ; dbh = colsum(DH)
     const int jt = u - n_w0 - n_w2;
-    U.A = C.H2; U.lda = kH2; U.m0 = jt * 32; U.m_valid = 32;
+    U.A = C.H2; U.lda = kH2; U.m0 = jt * T; U.m_valid = T;
     U.Bm = C.DH; U.ldb = kQLD; U.n0 = 0; U.n_valid = L.NH;
     U.out_base = L.off_wh + U.m0; U.out_sm = 1; U.out_sn = kH2;
     U.bias_base = (jt == 0) ? L.off_bh : -1;
@@ -416,38 +397,58 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, c
     if ((S.phases & 1) && C.rp.prioritized)        // top levels of the tree: one coalesced read, then smem descents
       for (int t = tid; t < n_top; t += kThreads) sTop[t] = __ldcg(C.rp.tree + t);
     __syncthreads();
+    RMC_STAMP(C, 8);
     const bool do_fwd = (S.phases & 2) != 0;
     if (do_fwd) stage_params(sW, C.target, L.total, bar, parity);
 
     // -------- pass 1 over this CTA's tiles: sample + gather, then Q_target(s')
+    // warps 0..kTM-1: one sample each; warp kTM meanwhile computes the max IS weight (replay_memory.py:76-77),
+    // which the samplers pick up at a 5-warp named barrier after their own descent.
     const long long size = C.rp.st->size, dp = C.rp.st->dp;
     const double total = per ? __ldcg(C.rp.tree) : 0.0;
-    const double min_p = per ? static_cast<double>(C.rp.st->min_p) : 0.0;
+    const bool tree_sampling = C.rp.prioritized != 0;
     if (S.phases & 1) {
+      bool first_iter = true;
       for (long long tile = cta; tile < n_tiles; tile += S.n_row_ctas) {
         if (warp < kTM) {
           const long long i = tile * kTM + warp;
-          if (i < B) {
-            long long slot, node;
-            float w = 1.f;
-            if (C.rp.prioritized) {
+          const bool ok = i < B;
+          long long slot = 0, node = 0;
+          double p = 0.0, numer = 1.0;
+          RowRegs rr{};
+          if (ok) {
+            if (tree_sampling) {
               const long long gi = S.shard_off + i;
               const double ui = (S.u != nullptr) ? S.u[agent * B + i] : philox_uniform(S.seed, S.counter, agent, static_cast<uint32_t>(gi));
               const double v = stratum_value(total, S.Bglobal, gi, ui);
-              double p;
+              RMC_STAMP(C, 9);
               node = per_descend_cached(sTop, n_top, C.rp.tree, n_nodes, v, &p);
               slot = node - first_leaf;
-              w = static_cast<float>(is_weight(static_cast<double>(size), p, total, min_p, S.beta));
+              RMC_STAMP(C, 10);
             } else {
               const long long pos = (S.idx != nullptr) ? S.idx[agent * B + i]
                                                        : static_cast<long long>(feistel_perm(S.shard_off + i, size, S.seed, S.counter, agent));
               slot = deque_pos_to_slot(pos, size, dp, C.rp.cap);
               node = slot;
             }
-            if (lane == 0) { C.nodes[i] = node; C.is_w[i] = w; sIsw[warp] = w; }
-            gather_row_warp2(C.rp, slot, C.X + i * rf, sRows + warp * kMaxRowFloats);
+            rr = gather_row_load(C.rp, slot);                      // row loads in flight during the pow
+            if (tree_sampling) numer = pow(static_cast<double>(size) * (p / total), -S.beta);
+            RMC_STAMP(C, 11);
           }
+          if (tree_sampling) asm volatile("bar.sync 1, %0;" ::"n"((kTM + 1) * 32) : "memory");
+          if (ok) {
+            const float w = tree_sampling ? static_cast<float>(numer / sTop[kTopNodes]) : 1.f;
+            gather_row_store(C.rp, rr, C.X + i * rf, sRows + warp * kMaxRowFloats);
+            if (lane == 0) { C.nodes[i] = node; C.is_w[i] = w; sIsw[warp] = w; C.leaf_p[i] = p; }
+            RMC_STAMP(C, 12);
+          }
+        } else if (warp == kTM && tree_sampling) {
+          if (first_iter && lane == 0)
+            sTop[kTopNodes] = is_weight_max(static_cast<double>(size), total, static_cast<double>(C.rp.st->min_p), S.beta);
+          __syncwarp();
+          asm volatile("bar.sync 1, %0;" ::"n"((kTM + 1) * 32) : "memory");
         }
+        first_iter = false;
       }
     }
     __syncthreads();   // X rows written by this CTA are visible to it
@@ -529,10 +530,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, c
             g = fminf(fmaxf(delta, -1.f), 1.f) * go;
             lterm = per ? w * hub : hub;
             C.y[i] = y; C.q_sa[i] = q_sa; C.abs_td[i] = atd; C.hub[i] = hub; C.gcoef[i] = g;
-            if (per) {
-              C.pri[i] = td_to_priority(atd, S.per_eps, S.per_alpha, S.per_pmax);
-              if (S.phases & 4) atomicMax(C.rp.stamps + (C.nodes[i] - first_leaf), static_cast<int>(i + 1));
-            }
+            // (|td| -> priority and the last-writer stamps are produced by the write-back itself, phase B)
           }
           // dheads
           float* dh = sDH + r * kQLD;
@@ -624,7 +622,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, c
     n_workers = G - 1;
     if (cta == G - 1) {
       const long long tsize = C.rp.st->size;
-      tree_update_cta(C.rp, C.nodes, C.pri, B, tsize, tsize, true);
+      // |td| -> priority for the whole batch here (off the row CTAs' critical path), then the write-back
+      for (long long i = tid; i < B; i += kThreads) C.pri[i] = td_to_priority(__ldcg(C.abs_td + i), S.per_eps, S.per_alpha, S.per_pmax);
+      __syncthreads();
+      RMC_STAMP(C, 8);
+      tree_update_cta(C.rp, C.nodes, C.pri, B, tsize, tsize, false, (S.phases & 1) ? C.leaf_p : nullptr,
+                      reinterpret_cast<double*>(smem), C.dbg ? C.dbg + (blockIdx.y * gridDim.x + blockIdx.x) * 16 : nullptr);
       RMC_STAMP(C, 7);
       return;
     }
@@ -649,7 +652,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, c
   if (tree_here && G == 1) {
     __syncthreads();
     const long long tsize = C.rp.st->size;
-    tree_update_cta(C.rp, C.nodes, C.pri, B, tsize, tsize, true);
+    for (long long i = tid; i < B; i += kThreads) C.pri[i] = td_to_priority(__ldcg(C.abs_td + i), S.per_eps, S.per_alpha, S.per_pmax);
+    __syncthreads();
+    tree_update_cta(C.rp, C.nodes, C.pri, B, tsize, tsize, false, (S.phases & 1) ? C.leaf_p : nullptr,
+                    reinterpret_cast<double*>(smem), nullptr);
   }
   RMC_STAMP(C, 7);
 }

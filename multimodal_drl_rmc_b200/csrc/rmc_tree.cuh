@@ -18,52 +18,62 @@ __device__ __forceinline__ float finf() { return __int_as_float(0x7f800000); }
 
 // ---- stratified prefix search: one warp per sample, 4 tree levels per L2 round trip -------------
 // All 32 lanes call with identical (v); returns the leaf's tree index on every lane.
+// `p`/`pv`: start node and its value.  Lane l holds the look-ahead nodes at linear positions l, l+32, l+64,
+// l+96 of the 2+4+...+64 = 126 descendants of p at relative depth 1..6 (depth d starts at position 2^d-2).
+__device__ __forceinline__ double lookahead_pick(const double (&val)[4], int pos) {
+  const int reg = pos >> 5;   // warp-uniform
+  const double x = (reg == 0) ? val[0] : (reg == 1) ? val[1] : (reg == 2) ? val[2] : val[3];
+  return __shfl_sync(0xffffffffu, x, pos & 31);
+}
 __device__ __forceinline__ long long per_descend_from(const double* __restrict__ tree, long long n_nodes, long long p,
-                                                      double v, double* leaf_val) {
+                                                      double pv, double v, double* leaf_val) {
   const int lane = threadIdx.x & 31;
-  int d = 0, o = 0;
-  if (lane < 30) {  // lanes 0..29 <-> the 2+4+8+16 descendants at relative depth 1..4
-    d = 31 - __clz(lane + 2);
-    o = lane + 2 - (1 << d);
-  }
   while (2 * p + 1 < n_nodes) {
-    double val = 0.0;
-    if (lane < 30) {
-      const long long idx = ((p + 1) << d) - 1 + o;
-      if (idx < n_nodes) val = __ldcg(tree + idx);
+    double val[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int pos = lane + 32 * q;
+      val[q] = 0.0;
+      if (pos < 126) {
+        const int d = 31 - __clz(pos + 2);
+        const long long idx = ((p + 1) << d) - 1 + (pos + 2 - (1 << d));
+        if (idx < n_nodes) val[q] = __ldcg(tree + idx);
+      }
     }
     long long cur = p;
     int oc = 0;
     bool leaf = false;
 #pragma unroll
-    for (int dd = 1; dd <= 4; ++dd) {
+    for (int dd = 1; dd <= 6; ++dd) {
       const long long left = 2 * cur + 1;
       if (left >= n_nodes) { leaf = true; break; }
-      const double lv = __shfl_sync(0xffffffffu, val, (1 << dd) - 2 + 2 * oc);
-      if (v <= lv) { cur = left; oc = 2 * oc; }
-      else { v = v - lv; cur = left + 1; oc = 2 * oc + 1; }
+      const int lpos = (1 << dd) - 2 + 2 * oc;
+      const double lv = lookahead_pick(val, lpos);
+      if (v <= lv) { cur = left; oc = 2 * oc; pv = lv; }
+      else { v = v - lv; cur = left + 1; oc = 2 * oc + 1; pv = lookahead_pick(val, lpos + 1); }
     }
     p = cur;
     if (leaf) break;
   }
-  *leaf_val = __ldcg(tree + p);
+  *leaf_val = pv;
   return p;
 }
 __device__ __forceinline__ long long per_descend_warp(const double* __restrict__ tree, long long n_nodes, double v,
                                                       double* leaf_val) {
-  return per_descend_from(tree, n_nodes, 0, v, leaf_val);
+  return per_descend_from(tree, n_nodes, 0, __ldcg(tree), v, leaf_val);
 }
 // same walk, the first levels served from a shared-memory copy of tree[0 .. n_top)
 __device__ __forceinline__ long long per_descend_cached(const double* __restrict__ s_top, int n_top,
                                                         const double* __restrict__ tree, long long n_nodes, double v,
                                                         double* leaf_val) {
   long long p = 0;
+  double pv = s_top[0];
   while (2 * p + 2 < n_top) {          // both children cached
     const double lv = s_top[2 * p + 1];
-    if (v <= lv) p = 2 * p + 1;
-    else { v = v - lv; p = 2 * p + 2; }
+    if (v <= lv) { p = 2 * p + 1; pv = lv; }
+    else { v = v - lv; p = 2 * p + 2; pv = s_top[p]; }
   }
-  return per_descend_from(tree, n_nodes, p, v, leaf_val);
+  return per_descend_from(tree, n_nodes, p, pv, v, leaf_val);
 }
 
 // value drawn in stratum i (dqn/replay_memory.py:72,80; np.random.uniform(lo,hi) == lo+(hi-lo)*u)
@@ -75,9 +85,11 @@ __device__ __forceinline__ double stratum_value(double total, long long Bglobal,
 }
 
 // importance weight (dqn/replay_memory.py:76-77,84-86), float64 then cast by the caller
+__device__ __forceinline__ double is_weight_max(double size, double total, double min_p, double beta) {
+  return pow(size * (min_p / total), -beta);
+}
 __device__ __forceinline__ double is_weight(double size, double p, double total, double min_p, double beta) {
-  const double max_w = pow(size * (min_p / total), -beta);
-  return pow(size * (p / total), -beta) / max_w;
+  return pow(size * (p / total), -beta) / is_weight_max(size, total, min_p, beta);
 }
 
 // |td| -> priority (dqn/replay_memory.py:95): float32 min/add, pow evaluated in float64 and rounded
@@ -111,20 +123,40 @@ __device__ __forceinline__ int warp_sum(int v) {
   return v;
 }
 
-// leaf store + exact ancestor fix-up for the elected writer of a leaf; returns the old leaf value
-__device__ __forceinline__ double tree_set_leaf(const ReplayDev& R, long long leaf, float p) {
+// leaf store + exact ancestor fix-up for the elected writer of a leaf; returns the old leaf value.
+// Nodes below `first_fixed` are NOT touched here: the caller rebuilds those (heavily shared) top levels
+// from their children afterwards (sums are exact, SURVEY finding 6, so a rebuild equals propagation).
+constexpr int kTopRebuild = 511;   // nodes 0..510 = top 9 levels, children of the last of them: 511..1022
+__device__ __forceinline__ double tree_set_leaf(const ReplayDev& R, long long leaf, float p, const double* old_known,
+                                                long long first_fixed) {
   const double np = static_cast<double>(p);
-  const double old = __ldcg(R.tree + leaf);
+  const double old = (old_known != nullptr) ? *old_known : __ldcg(R.tree + leaf);
   R.tree[leaf] = np;
   const double delta = np - old;
   if (delta != 0.0) {
     long long n = leaf;
     while (n != 0) {
       n = (n - 1) >> 1;
+      if (n < first_fixed) break;
       atomicAdd(R.tree + n, delta);
     }
   }
   return old;
+}
+
+// Rebuild tree[0 .. kTopRebuild) bottom-up in shared memory from tree[kTopRebuild .. 2*kTopRebuild+1)
+// (requires 2*kTopRebuild+1 <= n_nodes).  s_buf: 2*kTopRebuild+1 doubles.  All threads of the CTA call.
+__device__ void tree_rebuild_top_cta(const ReplayDev& R, double* s_buf) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int k = kTopRebuild + tid; k < 2 * kTopRebuild + 1; k += nt) s_buf[k] = __ldcg(R.tree + k);
+  __syncthreads();
+  for (int first = (kTopRebuild - 1) / 2; ; first = (first - 1) / 2) {   // levels 255..510, 127..254, ..., 0
+    const int count = first + 1;
+    for (int k = first + tid; k < first + count; k += nt) s_buf[k] = s_buf[2 * k + 1] + s_buf[2 * k + 2];
+    __syncthreads();
+    if (first == 0) break;
+  }
+  for (int k = tid; k < kTopRebuild; k += nt) R.tree[k] = s_buf[k];
 }
 
 // full rescan of leaves[:size] by one CTA (rare path): exact extremes and their multiplicities
@@ -167,16 +199,21 @@ __device__ void extremes_rescan_cta(const ReplayDev& R, long long size, float* s
 // leaves before / after (they differ for pushes).
 __device__ void tree_update_cta(const ReplayDev& R, const long long* __restrict__ nodes,
                                 const float* __restrict__ pri, long long n, long long old_size, long long new_size,
-                                bool stamps_done) {
+                                bool stamps_done, const double* __restrict__ old_vals, double* s_top_buf,
+                                unsigned long long* dbg = nullptr) {
+#define RMC_TSTAMP(k) do { if (dbg != nullptr && threadIdx.x == 0) dbg[k] = global_timer_ns(); } while (0)
   __shared__ float s_f[64];
   __shared__ int s_i[64];
   __shared__ float s_ext[4];   // M0, m0, M1, m1
   const int tid = threadIdx.x, nt = blockDim.x, warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
   const long long first_leaf = R.cap - 1;
-  if (!stamps_done) {
+  // big trees: per-leaf atomics only below the top 9 levels, which are rebuilt afterwards
+  const bool rebuild_top = (s_top_buf != nullptr) && (2 * R.cap - 1 >= 2 * kTopRebuild + 1);
+  const long long first_fixed = rebuild_top ? kTopRebuild : 0;
+  if (!stamps_done)
     for (long long i = tid; i < n; i += nt) atomicMax(R.stamps + (nodes[i] - first_leaf), static_cast<int>(i + 1));
-    __syncthreads();
-  }
+  __syncthreads();
+  RMC_TSTAMP(9);
   // pass 1: elected writers apply; remember the overwritten value (-1: leaf was outside the old domain,
   // -2: not the elected writer); batch extremes of the NEW values
   float bmax = 0.f, bmin = finf();
@@ -188,7 +225,7 @@ __device__ void tree_update_cta(const ReplayDev& R, const long long* __restrict_
     if (__ldcg(st) == static_cast<int>(i + 1)) {
       *st = 0;
       const float p = pri[i];
-      const double old = tree_set_leaf(R, leaf, p);
+      const double old = tree_set_leaf(R, leaf, p, old_vals ? old_vals + i : nullptr, first_fixed);
       oldv = (di < old_size) ? static_cast<float>(old) : -1.f;
       bmax = fmaxf(bmax, p);
       bmin = fminf(bmin, p);
@@ -199,6 +236,7 @@ __device__ void tree_update_cta(const ReplayDev& R, const long long* __restrict_
   bmin = warp_min(bmin);
   if (lane == 0) { s_f[warp] = bmax; s_f[32 + warp] = bmin; }
   __syncthreads();
+  RMC_TSTAMP(10);
   if (tid == 0) {
     float M = 0.f, m = finf();
     for (int w = 0; w < nw; ++w) { M = fmaxf(M, s_f[w]); m = fminf(m, s_f[32 + w]); }
@@ -234,6 +272,14 @@ __device__ void tree_update_cta(const ReplayDev& R, const long long* __restrict_
   }
   __syncthreads();
   if (s_i[63]) extremes_rescan_cta(R, new_size, s_f, s_i);
+  RMC_TSTAMP(11);
+  if (rebuild_top) {
+    __threadfence();     // this thread's reductions on the lower levels have been performed
+    __syncthreads();
+    RMC_TSTAMP(12);
+    tree_rebuild_top_cta(R, s_top_buf);
+  }
+#undef RMC_TSTAMP
 }
 
 // ---- standalone kernels -------------------------------------------------------------------
@@ -247,8 +293,9 @@ __global__ void __launch_bounds__(kThreads) k_tree_update_small(ReplayDev R, con
     __syncthreads();
     pri = pri_out;
   }
+  __shared__ double s_top_buf[2 * kTopRebuild + 1];
   const long long size = R.st->size;
-  tree_update_cta(R, nodes, pri, n, size, size, false);
+  tree_update_cta(R, nodes, pri, n, size, size, false, nullptr, s_top_buf);
 }
 
 // grid-wide variants for large batches
@@ -267,7 +314,7 @@ __global__ void k_tree_apply(ReplayDev R, const long long* nodes, const float* p
     int* st = R.stamps + (leaf - (R.cap - 1));
     if (__ldcg(st) == static_cast<int>(i + 1)) {
       *st = 0;
-      tree_set_leaf(R, leaf, pri[i]);
+      tree_set_leaf(R, leaf, pri[i], nullptr, 0);
     }
   }
 }
@@ -345,6 +392,7 @@ __global__ void __launch_bounds__(kThreads) k_push_small(ReplayDev R, const floa
                                                          long long* scratch_nodes, float* scratch_pri, float pmax) {
   __shared__ long long s_dp, s_size;
   __shared__ float s_p;
+  __shared__ double s_top_buf[2 * kTopRebuild + 1];
   const int tid = threadIdx.x, nt = blockDim.x;
   if (tid == 0) {
     s_dp = R.st->dp;
@@ -368,7 +416,7 @@ __global__ void __launch_bounds__(kThreads) k_push_small(ReplayDev R, const floa
       scratch_pri[j] = p;
     }
     __syncthreads();
-    tree_update_cta(R, scratch_nodes, scratch_pri, n, s_size, new_size, false);
+    tree_update_cta(R, scratch_nodes, scratch_pri, n, s_size, new_size, false, nullptr, s_top_buf);
   }
   __syncthreads();
   if (tid == 0) {
@@ -398,14 +446,21 @@ __global__ void k_push_end(ReplayDev R, long long dp, long long size) {
 }
 
 // ---- standalone samplers (ReplayMemory*.sample_transitions) ---------------------------------
-__device__ __forceinline__ void gather_row_warp2(const ReplayDev& R, long long slot, float* __restrict__ dst, float* __restrict__ sdst) {
+// split gather: issue the loads (<= 3 floats per lane, rows are <= 68 floats), do other work, then store
+struct RowRegs { float v[3]; };
+__device__ __forceinline__ RowRegs gather_row_load(const ReplayDev& R, long long slot) {
   const int lane = threadIdx.x & 31;
   const float* src = R.ring + slot * R.row_floats;
-  for (int c = lane; c < R.row_floats; c += 32) {
-    const float v = __ldcg(src + c);
-    dst[c] = v;
-    sdst[c] = v;
-  }
+  RowRegs r;
+#pragma unroll
+  for (int q = 0; q < 3; ++q) r.v[q] = (lane + 32 * q < R.row_floats) ? __ldcg(src + lane + 32 * q) : 0.f;
+  return r;
+}
+__device__ __forceinline__ void gather_row_store(const ReplayDev& R, const RowRegs& r, float* __restrict__ dst, float* __restrict__ sdst) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int q = 0; q < 3; ++q)
+    if (lane + 32 * q < R.row_floats) { dst[lane + 32 * q] = r.v[q]; sdst[lane + 32 * q] = r.v[q]; }
 }
 __device__ __forceinline__ void gather_row_warp(const ReplayDev& R, long long slot, float* __restrict__ dst) {
   const int lane = threadIdx.x & 31;

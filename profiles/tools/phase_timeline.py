@@ -19,7 +19,8 @@ for _ in range(20):
     agent.step += 1
     agent.learn(fuse_target_update=True)
 lib.rmc_learner_debug_timing(agent._lh.handle, 1)
-names = ["start", "sampled", "tgt_w_landed", "tgt_pass", "onl_w_landed", "rows_done", "past_barrier", "done"]
+names = ["start", "sampled", "tgt_w_landed", "tgt_pass", "onl_w_landed", "rows_done", "past_barrier", "done",
+         "s8:top_synced|pri_done", "s9:descent_start|stamped", "s10:descent_end|applied", "s11:pow_done|extremes", "s12:row_stored|fenced"]
 acc = []
 for it in range(10):
     agent.step += 1
@@ -27,17 +28,17 @@ for it in range(10):
     buf = np.zeros(1024 * 16, np.uint64)
     n = C.c_int32()
     _lib.check(lib.rmc_learner_debug_read_sync(agent._lh.handle, buf.ctypes.data, 1024, C.byref(n), _lib.stream_ptr()))
-    t = buf[: n.value * 16].reshape(n.value, 16)[:, :8].astype(np.int64)
+    t = buf[: n.value * 16].reshape(n.value, 16)[:, :13].astype(np.int64)
     t0 = t[:, 0][t[:, 0] > 0].min()
     acc.append(np.where(t > 0, t - t0, -1))
 a = np.stack(acc[2:])
 print("grid", a.shape[1], "CTAs; ns since the first CTA started (median over", a.shape[0], "launches)")
 med = np.median(a, axis=0)
-print("%-14s %10s %10s %10s" % ("stamp", "min", "median", "max"))
+print("%-28s %10s %10s %10s" % ("stamp", "min", "median", "max"))
 for k, nm in enumerate(names):
     col = med[:, k][med[:, k] >= 0]
     if len(col):
-        print("%-14s %10.0f %10.0f %10.0f" % (nm, col.min(), np.median(col), col.max()))
+        print("%-28s %10.0f %10.0f %10.0f" % (nm, col.min(), np.median(col), col.max()))
 print("per-CTA rows (first 8, last 2):")
 for c in list(range(min(8, med.shape[0]))) + list(range(max(8, med.shape[0] - 2), med.shape[0])):
     print(c, " ".join("%7.0f" % x for x in med[c]))
