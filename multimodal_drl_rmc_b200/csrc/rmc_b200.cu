@@ -144,6 +144,8 @@ extern "C" int32_t rmc_replay_create(rmc_replay_t** out, int64_t capacity, int32
     if ((e = dev_alloc(&d.tree, static_cast<size_t>(r->n_nodes)))) return e;
     if ((e = dev_alloc(&d.stamps, static_cast<size_t>(capacity)))) return e;
     if ((e = dev_alloc(&d.scratch_old, kTreeCtaMax))) return e;
+    if ((e = dev_alloc(&d.team_part, kTreeTeam))) return e;
+    if ((e = dev_alloc(&d.team_ctr, 1))) return e;
   }
   if ((e = dev_alloc(&r->scratch_nodes, kTreeCtaMax))) return e;
   if ((e = dev_alloc(&r->scratch_pri, kTreeCtaMax))) return e;
@@ -163,7 +165,7 @@ extern "C" int32_t rmc_replay_destroy(rmc_replay_t* r) {
   cudaSetDevice(r->device);
   cudaDeviceSynchronize();
   ReplayDev& d = r->dev;
-  cudaFree(d.ring); cudaFree(d.tree); cudaFree(d.stamps); cudaFree(d.scratch_old); cudaFree(d.st); cudaFree(r->scratch_nodes); cudaFree(r->scratch_pri);
+  cudaFree(d.ring); cudaFree(d.tree); cudaFree(d.stamps); cudaFree(d.scratch_old); cudaFree(d.team_part); cudaFree(d.team_ctr); cudaFree(d.st); cudaFree(r->scratch_nodes); cudaFree(r->scratch_pri);
   for (int s = 0; s < kStageSlots; ++s) {
     if (r->pin[s]) cudaFreeHost(r->pin[s]);
     cudaFree(r->dstage[s]);

@@ -151,11 +151,21 @@ struct ReplayState {   // lives in HBM, updated by the kernels themselves
   int pad;
 };
 
+constexpr int kTreeTeam = 8;     // CTAs that share the priority write-back of one learner step
+struct TeamPart {                // one tree-team member's contribution to the extremes
+  float bmax, bmin;              // extremes of the NEW values it applied
+  int cnt_bmax, cnt_bmin;        // how many of its new values equal its own bmax / bmin
+  int old_eq_max, old_eq_min;    // how many overwritten (in-domain) values equalled the previous global max / min
+  int pad[2];
+};
+
 struct ReplayDev {
   float* ring;       // [cap][row_floats]
   double* tree;      // [2*cap-1]  reference heap layout (dqn/utils/sum_tree.py:6-13)
   int* stamps;       // [cap]   last-writer election for duplicate leaves in a batch
   float* scratch_old;// [kTreeCtaMax] overwritten leaf values of the batch being applied
+  TeamPart* team_part;   // [kTreeTeam]
+  unsigned* team_ctr;    // arrival counter of the tree team (returns to 0 after every step)
   ReplayState* st;
   long long cap;
   int row_floats;

@@ -65,8 +65,8 @@ __host__ __device__ inline SmemPlan make_smem_plan(int param_floats) {
 }
 // phase-B staging (reuses the same dynamic shared memory)
 constexpr int kGChunk = 256;                         // batch rows staged per chunk
-constexpr int kGTile = 16;                           // 16 x 16 outputs per unit (one per thread)
-constexpr int kGemmSmemFloats = 2 * kGChunk * kGTile + kWarps * kGTile * kGTile + kWarps * kGTile;
+// phase-B unit shapes: 16x16 (W2), 16x32 (W0: D<=16 rows x 32 hidden units), 32x16 (heads: 32 h2 columns x NH)
+constexpr int kGemmSmemFloats = kGChunk * (32 + 32) + kWarps * 32 * 16 + kWarps * 32;
 
 // ------------------------------------------------------------------ forward of R rows (R = 4 or 8)
 // sXT[d][kR], rows [0,R) are computed.  Results: sH1T[k][r], sH2[r][j], sQ[r][a] (Q values, or raw
@@ -251,28 +251,42 @@ struct GemmUnit {
   int bias_base;                           // param index of bias[n] or -1
 };
 
+template <int TMO, int TNO>
 __device__ void wgrad_unit(const AgentCtx& C, const StepScalars& S, const GemmUnit& U, float* smem) {
-  float* As = smem;                               // [kGChunk][16]
-  float* Bs = smem + kGChunk * kGTile;            // [kGChunk][16]
-  float* Ps = Bs + kGChunk * kGTile;              // [kWarps][16*16]
-  float* Pb = Ps + kWarps * kGTile * kGTile;      // [kWarps][16]
+  constexpr int LM = TMO / 8, LN = TNO / 4;       // lane tile (8 x 4 lanes cover the unit)
+  constexpr int NOUT = TMO * TNO / kThreads;      // outputs per thread (1 or 2)
+  float* As = smem;                               // [kGChunk][TMO]
+  float* Bs = smem + kGChunk * TMO;               // [kGChunk][TNO]
+  float* Ps = Bs + kGChunk * TNO;                 // [kWarps][TMO*TNO]
+  float* Pb = Ps + kWarps * TMO * TNO;            // [kWarps][TNO]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int mg = lane >> 2, ng = lane & 3;        // lane tile: 2 m x 4 n
-  // this thread's output element and (prefetched) parameter state: independent of the gradient
-  const int om = tid >> 4, on = tid & 15;
-  const int pi = (om < U.m_valid && on < U.n_valid) ? U.out_base + om * U.out_sm + on * U.out_sn : -1;
-  const int pb = (U.bias_base >= 0 && tid < U.n_valid && tid < kGTile) ? U.bias_base + tid : -1;
-  ParamVals pv{}, pvb{};
-  if (pi >= 0) pv = param_load(C, S, pi);
+  const int mg = lane >> 2, ng = lane & 3;
+  // this thread's output elements and their (prefetched) parameter state: independent of the gradient
+  int pi[NOUT];
+  ParamVals pv[NOUT];
+#pragma unroll
+  for (int q = 0; q < NOUT; ++q) {
+    const int o = tid + q * kThreads, om = o / TNO, on = o % TNO;
+    pi[q] = (om < U.m_valid && on < U.n_valid) ? U.out_base + om * U.out_sm + on * U.out_sn : -1;
+    if (pi[q] >= 0) pv[q] = param_load(C, S, pi[q]);
+  }
+  const int pb = (U.bias_base >= 0 && tid < U.n_valid && tid < TNO) ? U.bias_base + tid : -1;
+  ParamVals pvb{};
   if (pb >= 0) pvb = param_load(C, S, pb);
-  float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-  float bsum[4] = {0.f, 0.f, 0.f, 0.f};
+  float acc[LM][LN];
+  float bsum[LN];
+#pragma unroll
+  for (int i = 0; i < LM; ++i)
+#pragma unroll
+    for (int j = 0; j < LN; ++j) acc[i][j] = 0.f;
+#pragma unroll
+  for (int j = 0; j < LN; ++j) bsum[j] = 0.f;
 
   // 16-byte chunks per staged row; columns past the valid ones are zeroed once and never written
-  const int ca = min(4, (U.m_valid + 3) >> 2), cb = min(4, (U.n_valid + 3) >> 2), cab = ca + cb;
+  const int ca = min(TMO / 4, (U.m_valid + 3) >> 2), cb = min(TNO / 4, (U.n_valid + 3) >> 2), cab = ca + cb;
   __syncthreads();
-  if (cab < 8) {
-    for (int t = tid; t < 2 * kGChunk * kGTile; t += kThreads) As[t] = 0.f;
+  if (cab < (TMO + TNO) / 4) {
+    for (int t = tid; t < kGChunk * (TMO + TNO); t += kThreads) As[t] = 0.f;
     __syncthreads();
   }
   for (long long b0 = 0; b0 < S.B; b0 += kGChunk) {
@@ -280,78 +294,89 @@ __device__ void wgrad_unit(const AgentCtx& C, const StepScalars& S, const GemmUn
     if (b0 > 0) __syncthreads();
     for (int t = tid; t < rows * cab; t += kThreads) {      // LDGSTS: all copies of the chunk in flight at once
       const int r = t / cab, c = t - r * cab;
-      if (c < ca) cp_async16(As + r * kGTile + 4 * c, U.A + (b0 + r) * U.lda + U.m0 + 4 * c);
-      else cp_async16(Bs + r * kGTile + 4 * (c - ca), U.Bm + (b0 + r) * U.ldb + U.n0 + 4 * (c - ca));
+      if (c < ca) cp_async16(As + r * TMO + 4 * c, U.A + (b0 + r) * U.lda + U.m0 + 4 * c);
+      else cp_async16(Bs + r * TNO + 4 * (c - ca), U.Bm + (b0 + r) * U.ldb + U.n0 + 4 * (c - ca));
     }
     cp_async_wait_all();
     __syncthreads();
     // warp w takes rows w, w+8, ... (fixed order -> deterministic sums)
 #pragma unroll 4
     for (int r = warp; r < rows; r += kWarps) {
-      const float2 a2 = *reinterpret_cast<const float2*>(As + r * kGTile + mg * 2);
-      const float4 b4 = *reinterpret_cast<const float4*>(Bs + r * kGTile + ng * 4);
-      acc[0][0] = fmaf(a2.x, b4.x, acc[0][0]); acc[0][1] = fmaf(a2.x, b4.y, acc[0][1]);
-      acc[0][2] = fmaf(a2.x, b4.z, acc[0][2]); acc[0][3] = fmaf(a2.x, b4.w, acc[0][3]);
-      acc[1][0] = fmaf(a2.y, b4.x, acc[1][0]); acc[1][1] = fmaf(a2.y, b4.y, acc[1][1]);
-      acc[1][2] = fmaf(a2.y, b4.z, acc[1][2]); acc[1][3] = fmaf(a2.y, b4.w, acc[1][3]);
-      bsum[0] += b4.x; bsum[1] += b4.y; bsum[2] += b4.z; bsum[3] += b4.w;
+      float a[LM], b[LN];
+#pragma unroll
+      for (int i = 0; i < LM; ++i) a[i] = As[r * TMO + mg * LM + i];
+#pragma unroll
+      for (int j = 0; j < LN; ++j) b[j] = Bs[r * TNO + ng * LN + j];
+#pragma unroll
+      for (int i = 0; i < LM; ++i)
+#pragma unroll
+        for (int j = 0; j < LN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+#pragma unroll
+      for (int j = 0; j < LN; ++j) bsum[j] += b[j];
     }
   }
   // cross-warp reduction in fixed order
 #pragma unroll
-  for (int i = 0; i < 2; ++i)
-    *reinterpret_cast<float4*>(Ps + warp * (kGTile * kGTile) + (mg * 2 + i) * kGTile + ng * 4) =
-        make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-  if (mg == 0) *reinterpret_cast<float4*>(Pb + warp * kGTile + ng * 4) = make_float4(bsum[0], bsum[1], bsum[2], bsum[3]);
-  __syncthreads();
-  if (pi >= 0) {
-    float g = 0.f;
+  for (int i = 0; i < LM; ++i)
 #pragma unroll
-    for (int w = 0; w < kWarps; ++w) g += Ps[w * (kGTile * kGTile) + tid];
-    C.grads[pi] = g;
-    param_apply(C, S, pi, g, pv);
+    for (int j = 0; j < LN; ++j) Ps[warp * (TMO * TNO) + (mg * LM + i) * TNO + ng * LN + j] = acc[i][j];
+  if (mg == 0) {
+#pragma unroll
+    for (int j = 0; j < LN; ++j) Pb[warp * TNO + ng * LN + j] = bsum[j];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < NOUT; ++q) {
+    if (pi[q] >= 0) {
+      float g = 0.f;
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) g += Ps[w * (TMO * TNO) + tid + q * kThreads];
+      C.grads[pi[q]] = g;
+      param_apply(C, S, pi[q], g, pv[q]);
+    }
   }
   if (pb >= 0) {
     float g = 0.f;
 #pragma unroll
-    for (int w = 0; w < kWarps; ++w) g += Pb[w * kGTile + tid];
+    for (int w = 0; w < kWarps; ++w) g += Pb[w * TNO + tid];
     C.grads[pb] = g;
     param_apply(C, S, pb, g, pvb);
   }
   __syncthreads();
 }
 
+// units: [W0: mt0 x 8 of 16x32] [W2: 16 x 8 of 16x16] [heads: 4 of 32x16]  = 140 for D <= 16
 __device__ __forceinline__ int wgrad_unit_count(const NetLayout& L) {
-  const int mt0 = (L.D + kGTile - 1) / kGTile;
-  return mt0 * (kH1 / kGTile) + (kH1 / kGTile) * (kH2 / kGTile) + kH2 / kGTile;
+  return ((L.D + 15) / 16) * (kH1 / 32) + (kH1 / 16) * (kH2 / 16) + kH2 / 32;
 }
 
-__device__ __forceinline__ GemmUnit make_unit(const AgentCtx& C, int u) {
+__device__ void wgrad_run_unit(const AgentCtx& C, const StepScalars& S, int u, float* smem) {
   const NetLayout& L = C.L;
   GemmUnit U;
-  const int T = kGTile;
-  const int mt0 = (L.D + T - 1) / T;
-  const int n_w0 = mt0 * (kH1 / T), n_w2 = (kH1 / T) * (kH2 / T);
+  const int mt0 = (L.D + 15) / 16;
+  const int n_w0 = mt0 * (kH1 / 32), n_w2 = (kH1 / 16) * (kH2 / 16);
   if (u < n_w0) {                       // dW0^T[d][i] = sum_b X[b][d] * DZ1[b][i] ; db0 = colsum(DZ1)
-    const int mt = u / (kH1 / T), nt = u % (kH1 / T);
-    U.A = C.X; U.lda = C.rp.row_floats; U.m0 = mt * T; U.m_valid = min(T, L.D - mt * T);
-    U.Bm = C.DZ1; U.ldb = kH1; U.n0 = nt * T; U.n_valid = T;
+    const int mt = u / (kH1 / 32), nt = u % (kH1 / 32);
+    U.A = C.X; U.lda = C.rp.row_floats; U.m0 = mt * 16; U.m_valid = min(16, L.D - mt * 16);
+    U.Bm = C.DZ1; U.ldb = kH1; U.n0 = nt * 32; U.n_valid = 32;
     U.out_base = L.off_w0t + U.m0 * kH1 + U.n0; U.out_sm = kH1; U.out_sn = 1;
     U.bias_base = (mt == 0) ? L.off_b0 + U.n0 : -1;
+    wgrad_unit<16, 32>(C, S, U, smem);
   } else if (u < n_w0 + n_w2) {         // dW2^T[k][j] = sum_b H1[b][k] * DZ2[b][j] ; db2 = colsum(DZ2)
-    const int v = u - n_w0, kt = v / (kH2 / T), jt = v % (kH2 / T);
-    U.A = C.H1; U.lda = kH1; U.m0 = kt * T; U.m_valid = T;
-    U.Bm = C.DZ2; U.ldb = kH2; U.n0 = jt * T; U.n_valid = T;
+    const int v = u - n_w0, kt = v / (kH2 / 16), jt = v % (kH2 / 16);
+    U.A = C.H1; U.lda = kH1; U.m0 = kt * 16; U.m_valid = 16;
+    U.Bm = C.DZ2; U.ldb = kH2; U.n0 = jt * 16; U.n_valid = 16;
     U.out_base = L.off_w2t + U.m0 * kW2LD + U.n0; U.out_sm = kW2LD; U.out_sn = 1;
     U.bias_base = (kt == 0) ? L.off_b2 + U.n0 : -1;
+    wgrad_unit<16, 16>(C, S, U, smem);
   } else {                              // dWh[a][j] = sum_b H2[b][j] * DH[b][a] ; dbh = colsum(DH)
     const int jt = u - n_w0 - n_w2;
-    U.A = C.H2; U.lda = kH2; U.m0 = jt * T; U.m_valid = T;
+    U.A = C.H2; U.lda = kH2; U.m0 = jt * 32; U.m_valid = 32;
     U.Bm = C.DH; U.ldb = kQLD; U.n0 = 0; U.n_valid = L.NH;
     U.out_base = L.off_wh + U.m0; U.out_sm = 1; U.out_sn = kH2;
     U.bias_base = (jt == 0) ? L.off_bh : -1;
+    wgrad_unit<32, 16>(C, S, U, smem);
   }
-  return U;
 }
 
 // ------------------------------------------------------------------ the fused learner step
@@ -617,17 +642,26 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, c
 
   // ---------------------------------------------------------------- phase B
   const bool tree_here = per && (S.phases & 4) && C.rp.prioritized && B <= kTreeCtaMax;
+  // big tree + enough CTAs: a team of kTreeTeam CTAs shares the write-back; otherwise one CTA does it
+  const bool team = tree_here && (2 * C.rp.cap - 1 >= 2 * kTopRebuild + 1) && (G >= wgrad_unit_count(L) + kTreeTeam);
+  const int n_tree = !tree_here ? 0 : (team ? kTreeTeam : 1);
   int n_workers = G, wid = cta;
   if (tree_here && G > 1) {
-    n_workers = G - 1;
-    if (cta == G - 1) {
+    n_workers = G - n_tree;
+    if (cta >= n_workers) {
       const long long tsize = C.rp.st->size;
-      // |td| -> priority for the whole batch here (off the row CTAs' critical path), then the write-back
-      for (long long i = tid; i < B; i += kThreads) C.pri[i] = td_to_priority(__ldcg(C.abs_td + i), S.per_eps, S.per_alpha, S.per_pmax);
-      __syncthreads();
-      RMC_STAMP(C, 8);
-      tree_update_cta(C.rp, C.nodes, C.pri, B, tsize, tsize, false, (S.phases & 1) ? C.leaf_p : nullptr,
-                      reinterpret_cast<double*>(smem), C.dbg ? C.dbg + (blockIdx.y * gridDim.x + blockIdx.x) * 16 : nullptr);
+      unsigned long long* tdbg = C.dbg ? C.dbg + (blockIdx.y * gridDim.x + blockIdx.x) * 16 : nullptr;
+      if (team) {
+        tree_update_team(C.rp, C.nodes, C.abs_td, C.pri, B, tsize, (S.phases & 1) ? C.leaf_p : nullptr, S.per_eps, S.per_alpha,
+                         S.per_pmax, cta - n_workers, reinterpret_cast<double*>(smem), tdbg);
+      } else {
+        // |td| -> priority for the whole batch here (off the row CTAs' critical path), then the write-back
+        for (long long i = tid; i < B; i += kThreads) C.pri[i] = td_to_priority(__ldcg(C.abs_td + i), S.per_eps, S.per_alpha, S.per_pmax);
+        __syncthreads();
+        RMC_STAMP(C, 8);
+        tree_update_cta(C.rp, C.nodes, C.pri, B, tsize, tsize, false, (S.phases & 1) ? C.leaf_p : nullptr,
+                        reinterpret_cast<double*>(smem), tdbg);
+      }
       RMC_STAMP(C, 7);
       return;
     }
@@ -640,10 +674,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, c
   }
   if (S.phases & 8) {                             // BACKWARD (+ fused Adam/Polyak)
     const int n_units = wgrad_unit_count(L);
-    for (int u = wid; u < n_units; u += n_workers) {
-      const GemmUnit U = make_unit(C, u);
-      wgrad_unit(C, S, U, smem);
-    }
+    for (int u = wid; u < n_units; u += n_workers) wgrad_run_unit(C, S, u, smem);
   } else if (S.phases & (16 | 32 | 64)) {         // element-wise Adam from given grads / target sync only
     const float* gsrc = (S.grads_in != nullptr) ? S.grads_in + static_cast<size_t>(agent) * L.total : C.grads;
     for (int pi = wid * kThreads + tid; pi < L.total; pi += n_workers * kThreads)

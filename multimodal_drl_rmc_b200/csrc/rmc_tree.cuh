@@ -282,6 +282,125 @@ __device__ void tree_update_cta(const ReplayDev& R, const long long* __restrict_
 #undef RMC_TSTAMP
 }
 
+// ---- write-back by a TEAM of kTreeTeam CTAs (learner step, big trees) ---------------------------------
+// Spatial partition: member t owns the leaves below the t-th node of depth 3 (heap indices 7..14), so
+// elections (stamps) and all fix-up atomics below depth 3 are private to one member; the top 9 levels
+// are rebuilt, and the extremes combined, by whichever member arrives last (no spinning).
+__device__ __forceinline__ int depth3_owner(long long node) {
+  const unsigned long long n1 = static_cast<unsigned long long>(node) + 1ull;
+  const int depth = 63 - __clzll(n1);            // root = depth 0
+  return static_cast<int>((n1 >> (depth - 3)) - 8ull);   // valid for depth >= 3
+}
+
+__device__ void tree_update_team(const ReplayDev& R, const long long* __restrict__ nodes, const float* __restrict__ abs_td,
+                                 float* __restrict__ pri_out, long long n, long long size, const double* __restrict__ old_vals,
+                                 float eps, float alpha, float pmax, int member, double* s_top_buf, unsigned long long* dbg) {
+  __shared__ float s_f[64];
+  __shared__ int s_i[64];
+  __shared__ float s_loc[2];
+  __shared__ int s_last;
+#define RMC_TSTAMP(k) do { if (dbg != nullptr && threadIdx.x == 0) dbg[k] = global_timer_ns(); } while (0)
+  const int tid = threadIdx.x, nt = blockDim.x, warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
+  const long long first_leaf = R.cap - 1;
+  const float M0 = R.st->max_p, m0 = R.st->min_p;      // extremes before this batch (size > 0 here)
+  // pass 0: my samples -> priority, election stamp
+  for (long long i = tid; i < n; i += nt) {
+    const long long leaf = __ldcg(nodes + i);
+    if (depth3_owner(leaf) == member) {
+      pri_out[i] = td_to_priority(__ldcg(abs_td + i), eps, alpha, pmax);
+      atomicMax(R.stamps + (leaf - first_leaf), static_cast<int>(i + 1));
+    }
+  }
+  __syncthreads();
+  RMC_TSTAMP(9);
+  // pass 1: elected writers apply (atomics only below the top 9 levels); local extremes of the new values
+  float bmax = 0.f, bmin = finf();
+  for (long long i = tid; i < n; i += nt) {
+    const long long leaf = nodes[i];
+    float oldv = -2.f;
+    if (depth3_owner(leaf) == member) {
+      int* st = R.stamps + (leaf - first_leaf);
+      if (__ldcg(st) == static_cast<int>(i + 1)) {
+        *st = 0;
+        const float p = pri_out[i];
+        oldv = static_cast<float>(tree_set_leaf(R, leaf, p, old_vals ? old_vals + i : nullptr, kTopRebuild));
+        bmax = fmaxf(bmax, p);
+        bmin = fminf(bmin, p);
+      }
+      R.scratch_old[i] = oldv;
+    }
+  }
+  bmax = warp_max(bmax);
+  bmin = warp_min(bmin);
+  if (lane == 0) { s_f[warp] = bmax; s_f[32 + warp] = bmin; }
+  __syncthreads();
+  if (tid == 0) {
+    float M = 0.f, m = finf();
+    for (int w = 0; w < nw; ++w) { M = fmaxf(M, s_f[w]); m = fminf(m, s_f[32 + w]); }
+    s_loc[0] = M; s_loc[1] = m;
+  }
+  __syncthreads();
+  RMC_TSTAMP(10);
+  const float Mt = s_loc[0], mt = s_loc[1];
+  int a = 0, b = 0, c = 0, d = 0;   // new==Mt, old==M0, new==mt, old==m0
+  for (long long i = tid; i < n; i += nt) {
+    if (depth3_owner(nodes[i]) == member) {
+      const float oldv = R.scratch_old[i];
+      if (oldv != -2.f) {
+        const float p = pri_out[i];
+        a += (p == Mt); c += (p == mt);
+        b += (oldv == M0); d += (oldv == m0);
+      }
+    }
+  }
+  a = warp_sum(a); b = warp_sum(b); c = warp_sum(c); d = warp_sum(d);
+  if (lane == 0) { s_i[warp] = a; s_i[8 + warp] = b; s_i[16 + warp] = c; s_i[24 + warp] = d; }
+  __threadfence();          // this thread's leaf stores / reductions are performed before the team hand-off
+  __syncthreads();
+  if (tid == 0) {
+    int ta = 0, tb = 0, tc = 0, td = 0;
+    for (int w = 0; w < nw; ++w) { ta += s_i[w]; tb += s_i[8 + w]; tc += s_i[16 + w]; td += s_i[24 + w]; }
+    TeamPart tp;
+    tp.bmax = Mt; tp.bmin = mt; tp.cnt_bmax = ta; tp.cnt_bmin = tc; tp.old_eq_max = tb; tp.old_eq_min = td; tp.pad[0] = tp.pad[1] = 0;
+    R.team_part[member] = tp;
+    __threadfence();
+    const unsigned prev = atomicAdd(R.team_ctr, 1u);
+    s_last = (prev == kTreeTeam - 1) ? 1 : 0;
+    if (s_last) { *R.team_ctr = 0u; __threadfence(); }
+  }
+  __syncthreads();
+  RMC_TSTAMP(11);
+  if (!s_last) return;
+  // ---- last member: combine the extremes, rebuild the top of the tree
+  if (tid == 0) {
+    float Mb = 0.f, mb = finf();
+    TeamPart tp[kTreeTeam];
+    for (int t = 0; t < kTreeTeam; ++t) {
+      const int4 lo = __ldcg(reinterpret_cast<const int4*>(R.team_part + t));
+      const int4 hi = __ldcg(reinterpret_cast<const int4*>(R.team_part + t) + 1);
+      tp[t].bmax = __int_as_float(lo.x); tp[t].bmin = __int_as_float(lo.y); tp[t].cnt_bmax = lo.z; tp[t].cnt_bmin = lo.w;
+      tp[t].old_eq_max = hi.x; tp[t].old_eq_min = hi.y;
+      Mb = fmaxf(Mb, tp[t].bmax); mb = fminf(mb, tp[t].bmin);
+    }
+    long long ta = 0, tb = 0, tc = 0, td = 0;
+    for (int t = 0; t < kTreeTeam; ++t) {
+      if (tp[t].bmax == Mb) ta += tp[t].cnt_bmax;
+      if (tp[t].bmin == mb) tc += tp[t].cnt_bmin;
+      tb += tp[t].old_eq_max; td += tp[t].old_eq_min;
+    }
+    const float M1 = fmaxf(M0, Mb), m1 = fminf(m0, mb);
+    const long long cM = (Mb > M0) ? ta : R.st->cnt_max - tb + ((Mb == M0) ? ta : 0);
+    const long long cm = (mb < m0) ? tc : R.st->cnt_min - td + ((mb == m0) ? tc : 0);
+    R.st->max_p = M1; R.st->min_p = m1; R.st->cnt_max = cM; R.st->cnt_min = cm;
+    s_i[63] = (cM <= 0 || cm <= 0) ? 1 : 0;
+  }
+  __syncthreads();
+  if (s_i[63]) extremes_rescan_cta(R, size, s_f, s_i);
+  tree_rebuild_top_cta(R, s_top_buf);
+  RMC_TSTAMP(12);
+#undef RMC_TSTAMP
+}
+
 // ---- standalone kernels -------------------------------------------------------------------
 // one CTA: rmc_per_update for n <= kTreeCtaMax; optional |td| -> priority conversion first
 __global__ void __launch_bounds__(kThreads) k_tree_update_small(ReplayDev R, const long long* nodes, const float* pri_in,
