@@ -167,6 +167,15 @@ def ptr(t) -> int:
     return 0 if t is None else t.data_ptr()
 
 
-def stream_ptr() -> int:
+_raw_stream = None
+
+
+def stream_ptr(device_index=None) -> int:
+    """cudaStream_t of torch's current stream on the current (or given) device."""
+    global _raw_stream
     import torch
+    if _raw_stream is None:
+        _raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", False)
+    if _raw_stream:
+        return _raw_stream(torch.cuda.current_device() if device_index is None else device_index)
     return torch.cuda.current_stream().cuda_stream

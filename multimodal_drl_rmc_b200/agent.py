@@ -93,9 +93,24 @@ class Agent:
         self.update_target_network(force=True)
 
         self.sampling = "device"
-        self.sampling_seed = 0x5EED
         self._learn_calls = 0
         self._adam_t = 0
+        self._B = int(batch_size)
+        self._dev_index = self.device.index
+        self._args = _lib.StepArgs()
+        self._args.batch = self._B
+        self._args_ref = C.byref(self._args)
+        self._step_fn = lib().rmc_learner_step
+        self._learn_phases = _lib.PH_LEARN if self._PER else (_lib.PH_LEARN & ~_lib.PH_PRIORITY)
+        self.sampling_seed = 0x5EED
+
+    @property
+    def sampling_seed(self):
+        return self._args.seed
+
+    @sampling_seed.setter
+    def sampling_seed(self, v):
+        self._args.seed = int(v)
 
     @staticmethod
     def _make_writer(path):
@@ -125,47 +140,63 @@ class Agent:
 
     # ------------------------------------------------------------------ learning -------------
     def _step_args(self, phases, u=None, indices=None):
-        B = int(self.batch_size)
-        a = _lib.StepArgs()
-        a.batch, a.phases = B, int(phases)
-        a.seed, a.counter = int(self.sampling_seed), int(self._learn_calls)
-        a.adam_t = int(self._adam_t)
+        a = self._args                      # one StepArgs per agent, refreshed in place (no per-step allocation)
+        a.phases = int(phases)
+        a.counter = self._learn_calls
+        a.adam_t = self._adam_t
+        a.u_dev = None
+        a.idx_dev = None
         keep = None
         if phases & _lib.PH_SAMPLE:
             if self._PER:
-                a.per_beta = self.replay_memory_buffer.beta(self.step * self.n_env)
+                a.per_beta = self._beta(self.step * self.n_env)
                 if u is None and self.sampling == "host":
-                    u = np.random.random_sample(B)
+                    u = np.random.random_sample(self._B)
                 if u is not None:
                     keep = T.as_tensor(np.asarray(u, np.float64), device=self.device)
-                    a.u_dev = ptr(keep)
+                    a.u_dev = keep.data_ptr()
             else:
                 if indices is None and self.sampling == "host":
-                    indices = random.sample(range(len(self.replay_memory_buffer.replay_buffer)), B)
+                    indices = random.sample(range(len(self.replay_memory_buffer.replay_buffer)), self._B)
                 if indices is not None:
                     keep = T.as_tensor(np.asarray(indices, np.int64), device=self.device)
-                    a.idx_dev = ptr(keep)
+                    a.idx_dev = keep.data_ptr()
         return a, keep
+
+    def _beta(self, x):
+        """np.interp(x, [0, beta_inc], [0.4, 1.0]) (dqn/replay_memory.py:74) in plain python floats: same
+        IEEE operations as numpy's compiled interp (slope * (x - x0) + y0), without the array round trip."""
+        mem = self.replay_memory_buffer
+        x = float(x)
+        x1 = float(mem.beta_inc)
+        if x <= 0.0:
+            return mem.beta_start
+        if x >= x1:
+            return mem.beta_end
+        return ((mem.beta_end - mem.beta_start) / (x1 - 0.0)) * (x - 0.0) + mem.beta_start
 
     def learn(self, u=None, indices=None, fuse_target_update=False):
         """dqn/agent.py:166-185 / 204-226 / 245-272 as one launch.  ``u`` / ``indices`` inject the
         sampling randomness (tests).  ``fuse_target_update=True`` also performs this step's
         ``update_target_network()`` inside the same launch (call order of train.py:99-101); the
         following ``update_target_network()`` call is then skipped once."""
-        ring = self.replay_memory_buffer._ring
+        rh = self.replay_memory_buffer._ring.handle
+        if rh is None:
+            raise RuntimeError("replay memory is empty (no transition stored yet)")
         self._learn_calls += 1
         self._adam_t += 1
-        phases = _lib.PH_LEARN
-        if not self._PER:
-            phases &= ~_lib.PH_PRIORITY
+        phases = self._learn_phases
         if fuse_target_update:
             phases |= self._target_phase()
             self._target_fused_for = self._learn_calls
         a, keep = self._step_args(phases, u, indices)
-        check(lib().rmc_learner_step(self._lh.handle, ring.require(), C.byref(a), stream_ptr()))
-        self._lh.version[_lib.ONLINE] += 1
+        rc = self._step_fn(self._lh.handle, rh, self._args_ref, stream_ptr(self._dev_index))
+        if rc:
+            check(rc)
+        ver = self._lh.version
+        ver[0] += 1
         if fuse_target_update:
-            self._lh.version[_lib.TARGET] += 1
+            ver[1] += 1
         self._keepalive = keep
 
     def _target_phase(self, force=False):
@@ -189,7 +220,7 @@ class Agent:
         a.batch, a.phases, a.adam_t = 1, int(phase), 1
         ring = self.replay_memory_buffer._ring
         rh = ring.handle if ring.handle is not None else self._dummy_ring().handle
-        check(lib().rmc_learner_step(self._lh.handle, rh, C.byref(a), stream_ptr()))
+        check(lib().rmc_learner_step(self._lh.handle, rh, C.byref(a), stream_ptr(self.device.index)))
         self._lh.version[_lib.TARGET] += 1
 
     def _dummy_ring(self):

@@ -7,6 +7,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -203,7 +204,11 @@ static int32_t minmax_rebuild(rmc_replay* r, cudaStream_t st) {
 
 // rows already packed in a device staging buffer
 static int32_t push_packed_small(rmc_replay* r, const float* rows_dev, long long n, cudaStream_t st) {
-  k_push_small<<<1, kThreads, 0, st>>>(r->dev, rows_dev, n, r->scratch_nodes, r->scratch_pri, 1.0f);
+  if (n <= 32 && n <= r->cap) {
+    k_push_tiny<<<1, 32, 0, st>>>(r->dev, rows_dev, static_cast<int>(n), 1.0f);
+  } else {
+    k_push_small<<<1, kThreads, 0, st>>>(r->dev, rows_dev, n, r->scratch_nodes, r->scratch_pri, 1.0f);
+  }
   RMC_KERNEL_OK();
   r->dp = (r->dp + n) % r->cap;
   r->size = std::min(r->size + n, r->cap);
@@ -604,6 +609,34 @@ static int32_t check_step(const rmc_learner* l, const rmc_replay* r, const rmc_s
   return RMC_OK;
 }
 
+// One launch of the fused step.  Default: cooperative launch (co-residency of the agent barrier's CTAs is
+// guaranteed by the driver).  RMC_LAUNCH=plain / pdl are diagnostics that measure the launch-gap cost of
+// that guarantee (a plain launch of <= #SM single-CTA/SM blocks is co-resident on an otherwise idle GPU).
+static int launch_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = std::getenv("RMC_LAUNCH");
+    mode = (e && std::strcmp(e, "plain") == 0) ? 1 : (e && std::strcmp(e, "pdl") == 0) ? 2 : 0;
+  }
+  return mode;
+}
+static int32_t launch_step(dim3 grid, void** args, size_t smem, cudaStream_t st) {
+  const int mode = launch_mode();
+  if (mode == 0) {
+    RMC_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_learner_step), grid, dim3(kThreads, 1, 1), args, smem, st));
+  } else {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = dim3(kThreads, 1, 1); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = (mode == 2) ? 1 : 0;
+    RMC_CUDA(cudaLaunchKernelExC(&cfg, reinterpret_cast<void*>(k_learner_step), args));
+  }
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return RMC_OK;
+}
+
 static int grid_for(const rmc_learner* l, long long B, int max_ctas) {
   const long long n_tiles = (B + kTM - 1) / kTM;
   const int want = static_cast<int>(std::min<long long>(max_ctas, std::max<long long>(n_tiles, 154)));
@@ -628,10 +661,8 @@ extern "C" int32_t rmc_learner_step(rmc_learner_t* l, rmc_replay_t* r, const rmc
   l->last_grid = G;
   const AgentCtx* many = nullptr;
   void* args[] = {&single, &many, &S};
-  RMC_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_learner_step), dim3(G, 1, 1), dim3(kThreads, 1, 1), args,
-                                       static_cast<size_t>(l->smem_bytes), st));
+  if (int32_t e = launch_step(dim3(G, 1, 1), args, static_cast<size_t>(l->smem_bytes), st)) return e;
   if (rows && phase_b) l->barrier_count = S.barrier_target;
-  g_launches.fetch_add(1, std::memory_order_relaxed);
   if ((a->phases & RMC_PH_PRIORITY) && l->spec.prioritized && a->batch > kTreeCtaMax) {
     k_td_to_pri<<<blocks_for(a->batch, 256), 256, 0, st>>>(l->ctx.abs_td, l->ctx.pri, a->batch, S.per_eps, S.per_alpha, S.per_pmax);
     RMC_KERNEL_OK();
@@ -779,10 +810,8 @@ extern "C" int32_t rmc_group_step(rmc_group_t* g, const rmc_step_args_t* a, rmc_
   AgentCtx single = l0->ctx;
   const AgentCtx* many = g->ctx_dev;
   void* args[] = {&single, &many, &S};
-  RMC_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_learner_step), dim3(G, g->n, 1), dim3(kThreads, 1, 1), args,
-                                       static_cast<size_t>(l0->smem_bytes), st));
+  if (int32_t e = launch_step(dim3(G, g->n, 1), args, static_cast<size_t>(l0->smem_bytes), st)) return e;
   if (rows && phase_b) g->barrier_count = S.barrier_target;
-  g_launches.fetch_add(1, std::memory_order_relaxed);
   return RMC_OK;
 }
 

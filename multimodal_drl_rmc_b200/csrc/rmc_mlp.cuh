@@ -412,6 +412,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, c
   const bool per = S.prioritized != 0;
   const long long first_leaf = C.rp.cap - 1;
   uint32_t parity = 0;
+  // programmatic dependent launch (no-ops for ordinary / cooperative launches): let the next launch be
+  // scheduled early, and order everything below after the previous grid's memory operations
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   RMC_STAMP(C, 0);
 
   if (do_rows && cta < S.n_row_ctas && cta < n_tiles) {

@@ -544,6 +544,45 @@ __global__ void __launch_bounds__(kThreads) k_push_small(ReplayDev R, const floa
   }
 }
 
+// n <= 32 rows (the per-env-step push of the trainer), ONE warp: ring write, leaf <- max_priority with direct
+// ancestor atomics on every level, exact extremes bookkeeping.
+__global__ void __launch_bounds__(32) k_push_tiny(ReplayDev R, const float* __restrict__ rows, int n, float pmax) {
+  __shared__ float s_f[64];
+  __shared__ int s_i[64];
+  const int lane = threadIdx.x;
+  const long long dp = R.st->dp, size = R.st->size;
+  const long long new_size = min(size + static_cast<long long>(n), R.cap);
+  const float M0 = (size > 0) ? R.st->max_p : 0.f, m0 = (size > 0) ? R.st->min_p : finf();
+  const float p = (M0 == 0.f) ? pmax : M0;
+  const int rf = R.row_floats;
+  for (int t = lane; t < n * rf; t += 32) R.ring[((dp + t / rf) % R.cap) * rf + (t % rf)] = rows[t];
+  if (R.prioritized) {
+    int b = 0, d = 0;
+    if (lane < n) {
+      const long long slot = (dp + lane) % R.cap;
+      const double old = tree_set_leaf(R, slot + R.cap - 1, p, nullptr, 0);
+      if (slot < size) { b = (static_cast<float>(old) == M0); d = (static_cast<float>(old) == m0); }
+    }
+    b = warp_sum(b);
+    d = warp_sum(d);
+    if (lane == 0) {
+      const float M1 = fmaxf(M0, p), m1 = fminf(m0, p);
+      const long long c0M = (size > 0) ? R.st->cnt_max : 0, c0m = (size > 0) ? R.st->cnt_min : 0;
+      const long long cM = (p > M0) ? n : c0M - b + ((p == M0) ? n : 0);
+      const long long cm = (p < m0) ? n : c0m - d + ((p == m0) ? n : 0);
+      R.st->max_p = M1; R.st->min_p = m1; R.st->cnt_max = cM; R.st->cnt_min = cm;
+      s_i[63] = (cM <= 0 || cm <= 0) ? 1 : 0;
+    }
+    __syncwarp();
+    if (s_i[63]) { __threadfence(); extremes_rescan_cta(R, new_size, s_f, s_i); }
+  }
+  __syncwarp();
+  if (lane == 0) {
+    R.st->dp = (dp + n) % R.cap;
+    R.st->size = new_size;
+  }
+}
+
 // bulk path pieces
 __global__ void k_push_begin(ReplayDev R, float pmax) {
   const float mp = R.st->max_p;
