@@ -680,7 +680,8 @@ extern "C" int32_t rmc_learner_output(rmc_learner_t* l, const char* name, void**
                        {"huber", c.hub, B}, {"pri", c.pri, B}, {"gcoef", c.gcoef, B}, {"loss", c.loss, 1},
                        {"q_next_tgt", c.QT, B * kQLD}, {"q_next_on", c.QN, B * kQLD}, {"q", c.Q, B * kQLD},
                        {"rows", c.X, B * l->rf}, {"h1", c.H1, B * kH1}, {"h2", c.H2, B * kH2}, {"dz1", c.DZ1, B * kH1},
-                       {"dz2", c.DZ2, B * kH2}, {"dh", c.DH, B * kQLD}};
+                       {"dz2", c.DZ2, B * kH2}, {"dh", c.DH, B * kQLD}, {"leaf_p", c.leaf_p, B},
+                       {"grads_blob", c.grads, l->L.total}, {"loss_part", c.loss_part, 1024}};
   for (const Ent& e : table)
     if (std::strcmp(e.n, name) == 0) {
       *dev_ptr = e.p;

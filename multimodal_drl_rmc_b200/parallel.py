@@ -1,0 +1,152 @@
+"""Multi-GPU forms of the learner path.  One process per GPU, torch.distributed for the
+plumbing (NCCL on GPUs, gloo in the CPU tests of the host logic).
+
+* ``AgentEnsemble``  -- N independent agents of ONE GPU stepped by a single launch (``rmc_group_*``); across
+  GPUs ensembles need no communication at all (config C4).
+* ``ShardedLearner`` -- large-batch learner (config C5): the minibatch is split across ranks, every rank keeps
+  a full replica of replay, tree, weights and Adam state; per step one gradient all-reduce (+ an all-gather of
+  (leaf, |td|) for PER so that every replica applies the identical write-back).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch as T
+
+from . import _lib
+from ._lib import check, lib, stream_ptr
+
+
+def shard_range(batch: int, rank: int, world: int):
+    """Contiguous slice [lo, hi) of the global stratified sample indices owned by ``rank``; slices tile [0, batch)."""
+    base, rem = divmod(int(batch), int(world))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+class AgentEnsemble:
+    """Agents sharing spec / hyper-parameters / batch size on one GPU, stepped together.  Each member keeps its own
+    replay ring, tree, weights, Adam state and RNG stream (Philox counter = (step, agent index))."""
+
+    def __init__(self, agents):
+        self.agents = list(agents)
+        n = len(self.agents)
+        lh = (C.c_void_p * n)(*[a._lh.handle for a in self.agents])
+        rh = (C.c_void_p * n)(*[a.replay_memory_buffer._ring.require() for a in self.agents])
+        g = C.c_void_p()
+        check(lib().rmc_group_create(C.byref(g), lh, rh, n))
+        self.handle = g
+        self._args = _lib.StepArgs()
+        self._args.batch = int(self.agents[0].batch_size)
+        self._dev = self.agents[0].device.index
+
+    def __del__(self):
+        try:
+            if self.handle is not None:
+                lib().rmc_group_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    def learn(self, fuse_target_update=True, u=None, indices=None):
+        """One learner step of every member (dqn/agent.py learn() + update_target_network()).
+        ``u`` / ``indices``: optional injected sampling randomness, shape [n_agents, batch]."""
+        a0 = self.agents[0]
+        for a in self.agents:
+            a._learn_calls += 1
+            a._adam_t += 1
+        args = self._args
+        args.phases = a0._learn_phases | (a0._target_phase() if fuse_target_update else 0)
+        args.counter = a0._learn_calls
+        args.adam_t = a0._adam_t
+        args.seed = a0.sampling_seed
+        if a0._PER:
+            args.per_beta = a0._beta(a0.step * a0.n_env)
+        args.u_dev = args.idx_dev = None
+        keep = None
+        if u is not None:
+            keep = T.as_tensor(np.ascontiguousarray(np.asarray(u, np.float64)), device=a0.device)
+            args.u_dev = keep.data_ptr()
+        if indices is not None:
+            keep = T.as_tensor(np.ascontiguousarray(np.asarray(indices, np.int64)), device=a0.device)
+            args.idx_dev = keep.data_ptr()
+        self._keep = keep
+        check(lib().rmc_group_step(self.handle, C.byref(args), stream_ptr(self._dev)))
+        for a in self.agents:
+            a._lh.version[_lib.ONLINE] += 1
+            if fuse_target_update:
+                a._lh.version[_lib.TARGET] += 1
+                a._target_fused_for = a._learn_calls
+
+
+class ShardedLearner:
+    """Data-parallel learner step for one logical agent replicated on every rank.
+
+    Per step and rank r of W (global batch B, slice [lo, hi) = shard_range(B, r, W)):
+      1. sample the slice's strata with the GLOBAL segment length total/B and the global uniforms u[lo:hi]
+         (the union over ranks is exactly the single-GPU batch), forward, TD, dgrad, weight gradients scaled
+         by 1/B -> local gradient blob;
+      2. all-reduce(sum) of the gradient blob (P floats) and of the loss partial;
+      3. PER: all-gather (leaf index, |td|) and apply the full write-back on every replica in global batch order;
+      4. Adam (+ Polyak) from the reduced gradients, identical on every rank.
+    """
+
+    def __init__(self, agent, group=None):
+        import torch.distributed as dist
+        self.agent, self.dist, self.group = agent, dist, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.B = int(agent.batch_size)
+        self.lo, self.hi = shard_range(self.B, self.rank, self.world)
+        self._args = _lib.StepArgs()
+
+    def learn(self, u=None, fuse_target_update=True):
+        ag, dist = self.agent, self.dist
+        lh = ag._lh
+        rh = ag.replay_memory_buffer._ring.require()
+        ag._learn_calls += 1
+        ag._adam_t += 1
+        a = self._args
+        n_local = self.hi - self.lo
+        a.batch, a.global_batch, a.shard_offset = n_local, self.B, self.lo
+        a.phases = _lib.PH_SAMPLE | _lib.PH_FORWARD | _lib.PH_BACKWARD
+        a.seed, a.counter, a.adam_t = ag.sampling_seed, ag._learn_calls, ag._adam_t
+        a.grads_in_dev = None
+        keep = None
+        if ag._PER:
+            a.per_beta = ag._beta(ag.step * ag.n_env)
+            if u is not None:
+                keep = T.as_tensor(np.asarray(u, np.float64)[self.lo:self.hi].copy(), device=ag.device)
+                a.u_dev = keep.data_ptr()
+            else:
+                a.u_dev = None
+        s = stream_ptr(ag.device.index)
+        check(lib().rmc_learner_step(lh.handle, rh, C.byref(a), s))
+        grads = lh.output("grads_blob")
+        loss = lh.output("loss")
+        dist.all_reduce(grads, group=self.group)
+        dist.all_reduce(loss, group=self.group)
+        if ag._PER:
+            nodes = lh.output("nodes", T.int64)[:n_local]
+            td = lh.output("abs_td")[:n_local]
+            sizes = [shard_range(self.B, r, self.world) for r in range(self.world)]
+            all_nodes = [T.empty(h - l, dtype=T.int64, device=ag.device) for l, h in sizes]
+            all_td = [T.empty(h - l, dtype=T.float32, device=ag.device) for l, h in sizes]
+            dist.all_gather(all_nodes, nodes.contiguous(), group=self.group)
+            dist.all_gather(all_td, td.contiguous(), group=self.group)
+            gn, gt = T.cat(all_nodes), T.cat(all_td)
+            pri = T.empty_like(gt)
+            mem = ag.replay_memory_buffer
+            check(lib().rmc_per_update_from_td(rh, gn.data_ptr(), gt.data_ptr(), gn.numel(), mem.epsilon, mem.alpha,
+                                               mem.max_priority_high, pri.data_ptr(), s))
+        b = _lib.StepArgs()
+        b.batch, b.adam_t = n_local, ag._adam_t
+        b.phases = _lib.PH_ADAM | (ag._target_phase() if fuse_target_update else 0)
+        b.grads_in_dev = grads.data_ptr()
+        check(lib().rmc_learner_step(lh.handle, rh, C.byref(b), s))
+        lh.version[_lib.ONLINE] += 1
+        if fuse_target_update:
+            lh.version[_lib.TARGET] += 1
+            ag._target_fused_for = ag._learn_calls
+        self._keep = (keep, grads, loss)
+        return loss
