@@ -333,28 +333,32 @@ def run_ours(args, wl):
         dist.destroy_process_group()
 
 
+def _time_steps(fn, steps, warmup=10):
+    import torch
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(steps):
+        fn()
+    e.record()
+    torch.cuda.synchronize()
+    return s.elapsed_time(e) / steps
+
+
 def extra_workloads(agent):
     """Secondary configs of BASELINE.json, measured after the headline (not part of its timed region)."""
     import torch
+    from multimodal_drl_rmc_b200 import _lib
     out = {}
-    try:
+    try:   # C3: batched greedy act over 65,536 macro-state vectors
         states = np.random.default_rng(0).random((65536, D), dtype=np.float32)
         dev_states = torch.as_tensor(states, device=agent.device)
         net = agent.online_network
-        for _ in range(3):
-            net.actions(dev_states[:1024])
-        from multimodal_drl_rmc_b200 import _lib
         acts = torch.empty(65536, dtype=torch.int64, device=agent.device)
         lh = agent._lh
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        for _ in range(3):
-            _lib.check(_lib.lib().rmc_learner_act(lh.handle, dev_states.data_ptr(), 65536, acts.data_ptr(), _lib.stream_ptr()))
-        s.record()
-        for _ in range(10):
-            _lib.check(_lib.lib().rmc_learner_act(lh.handle, dev_states.data_ptr(), 65536, acts.data_ptr(), _lib.stream_ptr()))
-        e.record()
-        torch.cuda.synchronize()
-        ms = s.elapsed_time(e) / 10
+        ms = _time_steps(lambda: _lib.check(_lib.lib().rmc_learner_act(lh.handle, dev_states.data_ptr(), 65536, acts.data_ptr(), _lib.stream_ptr())), 20, 3)
         t0 = time.perf_counter()
         for _ in range(5):
             net.actions(states)
@@ -363,6 +367,48 @@ def extra_workloads(agent):
                             "host_api_ms": host_ms, "host_api_states_per_s": 65536 / (host_ms * 1e-3)}
     except Exception as exc:  # pragma: no cover
         out["act_65536"] = {"error": repr(exc)}
+    try:   # C1: repo defaults (B = 32, uniform replay)
+        wl = WORKLOADS["default32"]
+        a1, _ = build_gpu_agent(wl, agent.device.index, seed=11)
+
+        def step1():
+            a1.step += 1
+            a1.learn(fuse_target_update=True)
+        ms = _time_steps(step1, 1000)
+        out["default32"] = {"us_per_step": 1e3 * ms, "transitions_per_s": wl["B"] / (ms * 1e-3)}
+        del a1
+    except Exception as exc:  # pragma: no cover
+        out["default32"] = {"error": repr(exc)}
+    try:   # C4: 8 independent agents on this GPU, one launch per step for all of them
+        from multimodal_drl_rmc_b200.parallel import AgentEnsemble
+        for name, wl in (("ensemble8_default32", dict(WORKLOADS["default32"], size=100_000, cap=200_000)),
+                         ("ensemble8_per256", dict(WORKLOADS["per256"], size=200_000, cap=200_000))):
+            members = [build_gpu_agent(wl, agent.device.index, seed=50 + k)[0] for k in range(8)]
+            ens = AgentEnsemble(members)
+
+            def stepe():
+                for m in members:
+                    m.step += 1
+                ens.learn()
+            ms = _time_steps(stepe, 300)
+            out[name] = {"us_per_step": 1e3 * ms, "transitions_per_s": 8 * wl["B"] / (ms * 1e-3), "agents": 8,
+                         "replay": "cap = size = %d per agent" % wl["cap"]}
+            del ens, members
+    except Exception as exc:  # pragma: no cover
+        out["ensemble8"] = {"error": repr(exc)}
+    try:   # C5 at N = 1: one learner step on a 65,536-transition minibatch
+        wl = dict(WORKLOADS["per256"], B=65536)
+        a5, _ = build_gpu_agent(wl, agent.device.index, seed=12)
+
+        def step5():
+            a5.step += 1
+            a5.learn(fuse_target_update=True)
+        ms = _time_steps(step5, 10, 2)
+        out["large_batch_65536"] = {"ms_per_step": ms, "transitions_per_s": 65536 / (ms * 1e-3),
+                                    "fp32_tflops": 65536 * FLOP_PER_TRANSITION / (ms * 1e-3) / 1e12}
+        del a5
+    except Exception as exc:  # pragma: no cover
+        out["large_batch_65536"] = {"error": repr(exc)}
     return out
 
 
