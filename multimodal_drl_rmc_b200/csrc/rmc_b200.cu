@@ -78,6 +78,7 @@ struct rmc_learner {
   float* io = nullptr;       // [P] device staging for set/get
   AgentCtx ctx{};            // replay part filled per step
   unsigned barrier_count = 0;
+  unsigned epoch = 0;
   unsigned long long* dbg_buf = nullptr;
   int last_grid = 0;
   // act staging
@@ -92,7 +93,9 @@ struct rmc_group {
   std::vector<rmc_replay*> replays;
   AgentCtx* ctx_dev = nullptr;
   unsigned* barriers = nullptr;
+  unsigned* qt_flags = nullptr;
   unsigned barrier_count = 0;
+  unsigned epoch = 0;
 };
 
 // ------------------------------------------------------------------------------ library
@@ -499,6 +502,7 @@ extern "C" int32_t rmc_learner_create(rmc_learner_t** out, const rmc_net_spec_t*
   if ((e = owned_alloc(l, &c.loss_part, 1024))) return e;
   if ((e = owned_alloc(l, &c.loss, 1))) return e;
   if ((e = owned_alloc(l, &c.barrier, 1))) return e;
+  if ((e = owned_alloc(l, &c.qt_flag, 1024))) return e;
   if ((e = owned_alloc(l, &l->dbg_buf, 1024 * 16))) return e;
   RMC_CUDA(cudaDeviceSynchronize());
   *out = l;
@@ -657,6 +661,8 @@ extern "C" int32_t rmc_learner_step(rmc_learner_t* l, rmc_replay_t* r, const rmc
   const bool rows = (a->phases & (RMC_PH_SAMPLE | RMC_PH_FORWARD)) != 0;
   const bool phase_b = (a->phases & (RMC_PH_PRIORITY | RMC_PH_BACKWARD | RMC_PH_ADAM | RMC_PH_POLYAK | RMC_PH_HARDSYNC)) != 0;
   if (rows && phase_b) S.barrier_target = l->barrier_count + static_cast<unsigned>(G);
+  l->epoch = (l->epoch == 0xffffffffu) ? 1u : l->epoch + 1u;
+  S.epoch = l->epoch;
   AgentCtx single = l->ctx;
   l->last_grid = G;
   const AgentCtx* many = nullptr;
@@ -768,11 +774,13 @@ extern "C" int32_t rmc_group_create(rmc_group_t** out, rmc_learner_t* const* lea
   int32_t e = RMC_OK;
   if ((e = dev_alloc(&g->ctx_dev, static_cast<size_t>(n_agents), false))) return e;
   if ((e = dev_alloc(&g->barriers, static_cast<size_t>(n_agents)))) return e;
+  if ((e = dev_alloc(&g->qt_flags, static_cast<size_t>(n_agents) * 1024))) return e;
   std::vector<AgentCtx> h(n_agents);
   for (int i = 0; i < n_agents; ++i) {
     h[i] = learners[i]->ctx;
     h[i].rp = replays[i]->dev;
     h[i].barrier = g->barriers + i;
+    h[i].qt_flag = g->qt_flags + static_cast<size_t>(i) * 1024;
   }
   RMC_CUDA(cudaMemcpy(g->ctx_dev, h.data(), sizeof(AgentCtx) * n_agents, cudaMemcpyHostToDevice));
   *out = g;
@@ -785,6 +793,7 @@ extern "C" int32_t rmc_group_destroy(rmc_group_t* g) {
   cudaDeviceSynchronize();
   cudaFree(g->ctx_dev);
   cudaFree(g->barriers);
+  cudaFree(g->qt_flags);
   delete g;
   return RMC_OK;
 }
@@ -807,6 +816,8 @@ extern "C" int32_t rmc_group_step(rmc_group_t* g, const rmc_step_args_t* a, rmc_
   const bool rows = (a->phases & (RMC_PH_SAMPLE | RMC_PH_FORWARD)) != 0;
   const bool phase_b = (a->phases & (RMC_PH_PRIORITY | RMC_PH_BACKWARD | RMC_PH_ADAM | RMC_PH_POLYAK | RMC_PH_HARDSYNC)) != 0;
   if (rows && phase_b) S.barrier_target = g->barrier_count + static_cast<unsigned>(G);
+  g->epoch = (g->epoch == 0xffffffffu) ? 1u : g->epoch + 1u;
+  S.epoch = g->epoch;
   for (int i = 0; i < g->n; ++i) g->learners[i]->last_batch = a->batch;
   AgentCtx single = l0->ctx;
   const AgentCtx* many = g->ctx_dev;

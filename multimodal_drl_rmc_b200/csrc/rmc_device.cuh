@@ -58,6 +58,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ uint32_t ld_acquire_u32(const unsigned* p) {
   uint32_t v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -193,6 +196,7 @@ struct AgentCtx {
   float* loss_part;     // [n_tiles]
   float* loss;          // [1]
   unsigned* barrier;
+  unsigned* qt_flag;    // [tiles] epoch of the launch whose Q_target(s') for that tile is in QT (role split)
   unsigned long long* dbg;   // optional per-CTA phase timestamps [G][16] (nullptr = off)
 };
 
@@ -205,6 +209,7 @@ struct StepScalars {
   int prioritized;        // learner flavour uses IS weights + write-back
   int n_row_ctas;         // CTAs that own row tiles
   unsigned barrier_target;  // counter value after the (single) A->B barrier
+  unsigned epoch;           // unique per launch of this agent / group (never 0)
   double beta;
   const double* u;        // injected uniforms (agent-major) or nullptr
   const long long* idx;   // injected positions or nullptr

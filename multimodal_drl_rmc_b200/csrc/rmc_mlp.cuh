@@ -382,7 +382,10 @@ __device__ void wgrad_run_unit(const AgentCtx& C, const StepScalars& S, int u, f
 // ------------------------------------------------------------------ the fused learner step
 __global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, const AgentCtx* __restrict__ many, StepScalars S) {
   extern __shared__ __align__(16) float smem[];
-  const AgentCtx& C = (many != nullptr) ? many[blockIdx.y] : single;
+  // private copy of the context: field reads become register / local-memory accesses that the compiler can hoist
+  // (through a reference into parameter-or-global memory every C.x is a generic load that no store may cross)
+  const AgentCtx Cv = (many != nullptr) ? many[blockIdx.y] : single;
+  const AgentCtx& C = Cv;
   const unsigned agent = blockIdx.y;
   const NetLayout L = C.L;
   const SmemPlan P = make_smem_plan(L.total);
@@ -418,8 +421,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, c
   asm volatile("griddepcontrol.wait;" ::: "memory");
   RMC_STAMP(C, 0);
 
-  if (do_rows && cta < S.n_row_ctas && cta < n_tiles) {
-    const bool single = n_tiles <= S.n_row_ctas;   // every CTA owns at most one tile: rows / Q_target stay in smem
+  // Role split: when every row CTA owns one tile and enough CTAs are idle in phase A, CTA n_tiles+t computes
+  // Q_target(s') of tile t concurrently (it repeats tile t's sampling -- same uniforms, same leaves -- and stages
+  // only the target blob), while row CTA t stages only the online blob and picks Q_target up through a flag.
+  const bool one_tile = n_tiles <= S.n_row_ctas;   // every row CTA owns at most one tile: rows / Q_target stay in smem
+  const bool split = one_tile && ((S.phases & 3) == 3) && (static_cast<long long>(G) >= 2 * n_tiles);
+  const bool is_row = do_rows && cta < S.n_row_ctas && cta < n_tiles;
+  const bool is_tgt = do_rows && split && cta >= n_tiles && cta < 2 * n_tiles;
+  const int tile0 = is_tgt ? cta - static_cast<int>(n_tiles) : cta;
+  if (is_row || is_tgt) {
     const long long n_nodes = 2 * C.rp.cap - 1;
     const int n_top = static_cast<int>(min(static_cast<long long>(kTopNodes), n_nodes));
     if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
@@ -428,7 +438,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, c
     __syncthreads();
     RMC_STAMP(C, 8);
     const bool do_fwd = (S.phases & 2) != 0;
-    if (do_fwd) stage_params(sW, C.target, L.total, bar, parity);
+    if (do_fwd) stage_params(sW, (split && !is_tgt) ? C.online : C.target, L.total, bar, parity);
 
     // -------- pass 1 over this CTA's tiles: sample + gather, then Q_target(s')
     // warps 0..kTM-1: one sample each; warp kTM meanwhile computes the max IS weight (replay_memory.py:76-77),
@@ -438,7 +448,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, c
     const bool tree_sampling = C.rp.prioritized != 0;
     if (S.phases & 1) {
       bool first_iter = true;
-      for (long long tile = cta; tile < n_tiles; tile += S.n_row_ctas) {
+      for (long long tile = tile0; tile < n_tiles; tile += S.n_row_ctas) {
         if (warp < kTM) {
           const long long i = tile * kTM + warp;
           const bool ok = i < B;
@@ -461,17 +471,21 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, c
               node = slot;
             }
             rr = gather_row_load(C.rp, slot);                      // row loads in flight during the pow
-            if (tree_sampling) numer = pow(static_cast<double>(size) * (p / total), -S.beta);
+            if (tree_sampling && !is_tgt) numer = pow(static_cast<double>(size) * (p / total), -S.beta);
             RMC_STAMP(C, 11);
           }
-          if (tree_sampling) asm volatile("bar.sync 1, %0;" ::"n"((kTM + 1) * 32) : "memory");
+          if (tree_sampling && !is_tgt) asm volatile("bar.sync 1, %0;" ::"n"((kTM + 1) * 32) : "memory");
           if (ok) {
-            const float w = tree_sampling ? static_cast<float>(numer / sTop[kTopNodes]) : 1.f;
-            gather_row_store(C.rp, rr, C.X + i * rf, sRows + warp * kMaxRowFloats);
-            if (lane == 0) { C.nodes[i] = node; C.is_w[i] = w; sIsw[warp] = w; C.leaf_p[i] = p; }
+            if (is_tgt) {                                          // target role: rows stay in shared memory only
+              gather_row_store_smem(C.rp, rr, sRows + warp * kMaxRowFloats);
+            } else {
+              const float w = tree_sampling ? static_cast<float>(numer / sTop[kTopNodes]) : 1.f;
+              gather_row_store(C.rp, rr, C.X + i * rf, sRows + warp * kMaxRowFloats);
+              if (lane == 0) { C.nodes[i] = node; C.is_w[i] = w; sIsw[warp] = w; C.leaf_p[i] = p; }
+            }
             RMC_STAMP(C, 12);
           }
-        } else if (warp == kTM && tree_sampling) {
+        } else if (warp == kTM && tree_sampling && !is_tgt) {
           if (first_iter && lane == 0)
             sTop[kTopNodes] = is_weight_max(static_cast<double>(size), total, static_cast<double>(C.rp.st->min_p), S.beta);
           __syncwarp();
@@ -485,12 +499,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, c
     if (do_fwd) {
       wait_params(bar, parity);
       RMC_STAMP(C, 2);
-      for (long long tile = cta; tile < n_tiles; tile += S.n_row_ctas) {
+      if (!split || is_tgt)
+      for (long long tile = tile0; tile < n_tiles; tile += S.n_row_ctas) {
         // x^T of the s' rows -> sXT[d][0..3]
         for (int t = tid; t < kTM * D; t += kThreads) {
           const int r = t / D, d = t % D;
           const long long i = tile * kTM + r;
-          sXT[d * kR + r] = (i < B) ? (single ? sRows[r * kMaxRowFloats + D + d] : __ldcg(C.X + i * rf + D + d)) : 0.f;
+          sXT[d * kR + r] = (i < B) ? (one_tile ? sRows[r * kMaxRowFloats + D + d] : __ldcg(C.X + i * rf + D + d)) : 0.f;
         }
         __syncthreads();
         mlp_forward<kTM>(sW, L, sXT, sH1T, sH2, sPart, sQ, nullptr);
@@ -502,30 +517,45 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, c
         }
         __syncthreads();
       }
+      if (is_tgt) {      // publish Q_target(s') of the tile: data, fence, flag (release) -- then on to phase B
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) st_release_u32(C.qt_flag + tile0, S.epoch);
+      }
       // -------- pass 2: online weights; [s'; s] rows
       RMC_STAMP(C, 3);
-      stage_params(sW, C.online, L.total, bar, parity);
-      wait_params(bar, parity);
+      if (!split) {
+        stage_params(sW, C.online, L.total, bar, parity);
+        wait_params(bar, parity);
+      }
       RMC_STAMP(C, 4);
       float loss_local = 0.f;   // thread 0 accumulates this CTA's tiles in order
+      if (!is_tgt)
       for (long long tile = cta; tile < n_tiles; tile += S.n_row_ctas) {
         for (int t = tid; t < kR * D; t += kThreads) {
           const int r = t / D, d = t % D;
           const long long i = tile * kTM + (r % kTM);
           const int col = (r < kTM) ? (D + d) : d;   // rows 0..3: s', rows 4..7: s
-          sXT[d * kR + r] = (i < B) ? (single ? sRows[(r % kTM) * kMaxRowFloats + col] : __ldcg(C.X + i * rf + col)) : 0.f;
+          sXT[d * kR + r] = (i < B) ? (one_tile ? sRows[(r % kTM) * kMaxRowFloats + col] : __ldcg(C.X + i * rf + col)) : 0.f;
         }
         if (tid < kTM) {
           const long long i = tile * kTM + tid;
           const bool ok = i < B;
           const float* row = sRows + tid * kMaxRowFloats;
-          sMeta[tid * 4 + 0] = ok ? (single ? row[2 * D] : __ldcg(C.X + i * rf + 2 * D)) : 0.f;
-          sMeta[tid * 4 + 1] = ok ? (single ? row[2 * D + 1] : __ldcg(C.X + i * rf + 2 * D + 1)) : 0.f;
-          sMeta[tid * 4 + 2] = ok ? (single ? row[2 * D + 2] : __ldcg(C.X + i * rf + 2 * D + 2)) : 0.f;
-          sMeta[tid * 4 + 3] = ok ? (single ? sIsw[tid] : __ldcg(C.is_w + i)) : 0.f;
+          sMeta[tid * 4 + 0] = ok ? (one_tile ? row[2 * D] : __ldcg(C.X + i * rf + 2 * D)) : 0.f;
+          sMeta[tid * 4 + 1] = ok ? (one_tile ? row[2 * D + 1] : __ldcg(C.X + i * rf + 2 * D + 1)) : 0.f;
+          sMeta[tid * 4 + 2] = ok ? (one_tile ? row[2 * D + 2] : __ldcg(C.X + i * rf + 2 * D + 2)) : 0.f;
+          sMeta[tid * 4 + 3] = ok ? (one_tile ? sIsw[tid] : __ldcg(C.is_w + i)) : 0.f;
         }
         __syncthreads();
         mlp_forward<kR>(sW, L, sXT, sH1T, sH2, sPart, sQ, nullptr);
+        RMC_STAMP(C, 13);
+        if (split) {     // Q_target(s') of this tile comes from its partner CTA
+          if (tid == 0) while (ld_acquire_u32(C.qt_flag + tile) != S.epoch) __nanosleep(20);
+          __syncthreads();
+          if (tid < kTM * kQLD) sQT[tid] = __ldcg(C.QT + tile * kTM * kQLD + tid);
+          __syncthreads();
+        }
         // ---- TD target, |td|, Huber, dQ coefficient (threads 0..kTM-1)
         if (tid < kTM) {
           const int r = tid;
@@ -535,7 +565,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, c
           if (i < B) {
             float qtv[kQLD];
 #pragma unroll
-            for (int a = 0; a < kQLD; ++a) qtv[a] = single ? sQT[r * kQLD + a] : __ldcg(C.QT + i * kQLD + a);
+            for (int a = 0; a < kQLD; ++a) qtv[a] = one_tile ? sQT[r * kQLD + a] : __ldcg(C.QT + i * kQLD + a);
             float qsel;
             if (S.double_dqn) {                                   // dqn/agent.py:252-256
               const int astar = argmax_first(sQ + r * kQLD, L.A);
@@ -632,7 +662,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, c
         }
         __syncthreads();
       }
-      if (tid == 0) C.loss_part[cta] = loss_local;
+      if (tid == 0 && !is_tgt) C.loss_part[cta] = loss_local;
       RMC_STAMP(C, 5);
     }
   } else if (do_rows && (S.phases & 2) && tid == 0 && cta < S.n_row_ctas) {

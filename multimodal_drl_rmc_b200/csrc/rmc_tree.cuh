@@ -15,6 +15,10 @@
 namespace rmc {
 
 __device__ __forceinline__ float finf() { return __int_as_float(0x7f800000); }
+// fire-and-forget float64 reduction on a GLOBAL address (the generic atomicAdd carries address-space dispatch)
+__device__ __forceinline__ void red_add_f64(double* gptr, double v) {
+  asm volatile("red.global.add.f64 [%0], %1;" ::"l"(gptr), "d"(v) : "memory");
+}
 
 // ---- stratified prefix search: one warp per sample, 4 tree levels per L2 round trip -------------
 // All 32 lanes call with identical (v); returns the leaf's tree index on every lane.
@@ -131,14 +135,15 @@ __device__ __forceinline__ double tree_set_leaf(const ReplayDev& R, long long le
                                                 long long first_fixed) {
   const double np = static_cast<double>(p);
   const double old = (old_known != nullptr) ? *old_known : __ldcg(R.tree + leaf);
-  R.tree[leaf] = np;
+  double* const tree = R.tree;
+  tree[leaf] = np;
   const double delta = np - old;
   if (delta != 0.0) {
     long long n = leaf;
     while (n != 0) {
       n = (n - 1) >> 1;
       if (n < first_fixed) break;
-      atomicAdd(R.tree + n, delta);
+      red_add_f64(tree + n, delta);
     }
   }
   return old;
@@ -613,6 +618,12 @@ __device__ __forceinline__ RowRegs gather_row_load(const ReplayDev& R, long long
 #pragma unroll
   for (int q = 0; q < 3; ++q) r.v[q] = (lane + 32 * q < R.row_floats) ? __ldcg(src + lane + 32 * q) : 0.f;
   return r;
+}
+__device__ __forceinline__ void gather_row_store_smem(const ReplayDev& R, const RowRegs& r, float* __restrict__ sdst) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int q = 0; q < 3; ++q)
+    if (lane + 32 * q < R.row_floats) sdst[lane + 32 * q] = r.v[q];
 }
 __device__ __forceinline__ void gather_row_store(const ReplayDev& R, const RowRegs& r, float* __restrict__ dst, float* __restrict__ sdst) {
   const int lane = threadIdx.x & 31;

@@ -20,7 +20,7 @@ for _ in range(20):
     agent.learn(fuse_target_update=True)
 lib.rmc_learner_debug_timing(agent._lh.handle, 1)
 names = ["start", "sampled", "tgt_w_landed", "tgt_pass", "onl_w_landed", "rows_done", "past_barrier", "done",
-         "s8:top_synced|pri_done", "s9:descent_start|stamped", "s10:descent_end|applied", "s11:pow_done|extremes", "s12:row_stored|fenced"]
+         "s8:top_synced|pri_done", "s9:descent_start|stamped", "s10:descent_end|applied", "s11:pow_done|extremes", "s12:row_stored|fenced", "s13:online_fwd_done"]
 acc = []
 for it in range(10):
     agent.step += 1
@@ -28,7 +28,7 @@ for it in range(10):
     buf = np.zeros(1024 * 16, np.uint64)
     n = C.c_int32()
     _lib.check(lib.rmc_learner_debug_read_sync(agent._lh.handle, buf.ctypes.data, 1024, C.byref(n), _lib.stream_ptr()))
-    t = buf[: n.value * 16].reshape(n.value, 16)[:, :13].astype(np.int64)
+    t = buf[: n.value * 16].reshape(n.value, 16)[:, :14].astype(np.int64)
     t0 = t[:, 0][t[:, 0] > 0].min()
     acc.append(np.where(t > 0, t - t0, -1))
 a = np.stack(acc[2:])
