@@ -79,6 +79,8 @@ struct rmc_learner {
   AgentCtx ctx{};            // replay part filled per step
   unsigned barrier_count = 0;
   unsigned epoch = 0;
+  unsigned loss_epoch = 0;          // epoch of the last launch that produced a loss
+  volatile float* host_loss = nullptr;   // mapped pinned host memory (host view)
   unsigned long long* dbg_buf = nullptr;
   int last_grid = 0;
   // act staging
@@ -208,7 +210,7 @@ static int32_t minmax_rebuild(rmc_replay* r, cudaStream_t st) {
 // rows already packed in a device staging buffer
 static int32_t push_packed_small(rmc_replay* r, const float* rows_dev, long long n, cudaStream_t st) {
   if (n <= 32 && n <= r->cap) {
-    k_push_tiny<<<1, 32, 0, st>>>(r->dev, rows_dev, static_cast<int>(n), 1.0f);
+    k_push_tiny<false><<<1, 32, 0, st>>>(r->dev, rows_dev, TinyRows{}, static_cast<int>(n), 1.0f);
   } else {
     k_push_small<<<1, kThreads, 0, st>>>(r->dev, rows_dev, n, r->scratch_nodes, r->scratch_pri, 1.0f);
   }
@@ -237,6 +239,17 @@ static int32_t push_impl(rmc_replay* r, const float* obs, const int64_t* act, co
   if (!r || n < 0) return fail(RMC_ERR_ARG, "rmc_replay_push: bad args");
   if (n == 0) return RMC_OK;
   if (int32_t e = use_device(r->device)) return e;
+  if (host && n <= 8 && n <= r->cap) {
+    // the trainer's per-env-step push: the packed rows ride in the kernel-argument buffer of the launch (no
+    // staging copy, no event) -- that launch IS the host->device transfer of these n*row_floats*4 bytes
+    TinyRows tr;
+    pack_rows_host(tr.v, obs, act, rew, done, nxt, n, r->D, r->rf);
+    k_push_tiny<true><<<1, 32, 0, st>>>(r->dev, nullptr, tr, static_cast<int>(n), 1.0f);
+    RMC_KERNEL_OK();
+    r->dp = (r->dp + n) % r->cap;
+    r->size = std::min<long long>(r->size + n, r->cap);
+    return RMC_OK;
+  }
   const long long small_max = std::min<long long>(kTreeCtaMax, r->cap);
   const bool bulk = n > small_max;
   const long long chunk_max = bulk ? std::min<long long>(r->stage_rows, r->cap) : small_max;
@@ -503,6 +516,19 @@ extern "C" int32_t rmc_learner_create(rmc_learner_t** out, const rmc_net_spec_t*
   if ((e = owned_alloc(l, &c.loss, 1))) return e;
   if ((e = owned_alloc(l, &c.barrier, 1))) return e;
   if ((e = owned_alloc(l, &c.qt_flag, 1024))) return e;
+  {
+    float* hp = nullptr;
+    float* dp = nullptr;
+    if (cudaHostAlloc(reinterpret_cast<void**>(&hp), 64, cudaHostAllocMapped) == cudaSuccess &&
+        cudaHostGetDevicePointer(reinterpret_cast<void**>(&dp), hp, 0) == cudaSuccess) {
+      hp[0] = 0.f; hp[1] = 0.f;
+      l->host_loss = hp;
+      c.host_loss = dp;
+    } else {
+      cudaGetLastError();
+      c.host_loss = nullptr;
+    }
+  }
   if ((e = owned_alloc(l, &l->dbg_buf, 1024 * 16))) return e;
   RMC_CUDA(cudaDeviceSynchronize());
   *out = l;
@@ -516,6 +542,7 @@ extern "C" int32_t rmc_learner_destroy(rmc_learner_t* l) {
   for (void* p : l->owned) cudaFree(p);
   if (l->act_pin_obs) cudaFreeHost(l->act_pin_obs);
   if (l->act_pin_out) cudaFreeHost(l->act_pin_out);
+  if (l->host_loss) cudaFreeHost(const_cast<float*>(l->host_loss));
   cudaFree(l->act_dev_obs);
   cudaFree(l->act_dev_out);
   delete l;
@@ -669,6 +696,7 @@ extern "C" int32_t rmc_learner_step(rmc_learner_t* l, rmc_replay_t* r, const rmc
   void* args[] = {&single, &many, &S};
   if (int32_t e = launch_step(dim3(G, 1, 1), args, static_cast<size_t>(l->smem_bytes), st)) return e;
   if (rows && phase_b) l->barrier_count = S.barrier_target;
+  if ((a->phases & RMC_PH_FORWARD) && phase_b) l->loss_epoch = S.epoch;
   if ((a->phases & RMC_PH_PRIORITY) && l->spec.prioritized && a->batch > kTreeCtaMax) {
     k_td_to_pri<<<blocks_for(a->batch, 256), 256, 0, st>>>(l->ctx.abs_td, l->ctx.pri, a->batch, S.per_eps, S.per_alpha, S.per_pmax);
     RMC_KERNEL_OK();
@@ -700,6 +728,24 @@ extern "C" int32_t rmc_learner_output(rmc_learner_t* l, const char* name, void**
 extern "C" int32_t rmc_learner_loss_sync(rmc_learner_t* l, float* out_host, rmc_stream_t s) {
   if (!l || !out_host) return fail(RMC_ERR_ARG, "rmc_learner_loss_sync: null");
   if (int32_t e = use_device(l->device)) return e;
+  if (l->host_loss != nullptr && l->loss_epoch != 0) {
+    // the step kernel stores (loss, epoch) straight into mapped host memory: wait for this launch's epoch
+    unsigned want = l->loss_epoch, got = 0;
+    for (long long spin = 0; spin < 200000000ll; ++spin) {
+      const float bits = l->host_loss[1];
+      std::memcpy(&got, &bits, sizeof(got));
+      if (got == want) {
+        std::atomic_thread_fence(std::memory_order_acquire);
+        *out_host = l->host_loss[0];
+        return RMC_OK;
+      }
+      if ((spin & 0xfff) == 0xfff && cudaStreamQuery(as_stream(s)) != cudaErrorNotReady) break;   // finished or faulted
+    }
+    RMC_CUDA(cudaStreamSynchronize(as_stream(s)));
+    const float bits = l->host_loss[1];
+    std::memcpy(&got, &bits, sizeof(got));
+    if (got == want) { *out_host = l->host_loss[0]; return RMC_OK; }
+  }
   RMC_CUDA(cudaMemcpyAsync(out_host, l->ctx.loss, sizeof(float), cudaMemcpyDeviceToHost, as_stream(s)));
   RMC_CUDA(cudaStreamSynchronize(as_stream(s)));
   return RMC_OK;

@@ -162,6 +162,8 @@ struct TeamPart {                // one tree-team member's contribution to the e
   int pad[2];
 };
 
+struct TinyRows { float v[8 * kMaxRowFloats]; };   // up to 8 packed rows carried in the kernel-argument buffer
+
 struct ReplayDev {
   float* ring;       // [cap][row_floats]
   double* tree;      // [2*cap-1]  reference heap layout (dqn/utils/sum_tree.py:6-13)
@@ -197,6 +199,7 @@ struct AgentCtx {
   float* loss;          // [1]
   unsigned* barrier;
   unsigned* qt_flag;    // [tiles] epoch of the launch whose Q_target(s') for that tile is in QT (role split)
+  volatile float* host_loss;      // mapped pinned host memory: [0] loss of the last step, [1] its epoch (as bits)
   unsigned long long* dbg;   // optional per-CTA phase timestamps [G][16] (nullptr = off)
 };
 

@@ -704,7 +704,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, c
     float s = 0.f;
     const int np = static_cast<int>(min(static_cast<long long>(S.n_row_ctas), n_tiles));
     for (int c = 0; c < np; ++c) s += __ldcg(C.loss_part + c);
-    C.loss[0] = s / static_cast<float>(S.Bglobal);
+    const float loss = s / static_cast<float>(S.Bglobal);
+    C.loss[0] = loss;
+    if (C.host_loss != nullptr) {     // zero-copy publication: value, system fence, then the launch's epoch
+      C.host_loss[0] = loss;
+      __threadfence_system();
+      C.host_loss[1] = __uint_as_float(S.epoch);
+    }
   }
   if (S.phases & 8) {                             // BACKWARD (+ fused Adam/Polyak)
     const int n_units = wgrad_unit_count(L);

@@ -551,7 +551,9 @@ __global__ void __launch_bounds__(kThreads) k_push_small(ReplayDev R, const floa
 
 // n <= 32 rows (the per-env-step push of the trainer), ONE warp: ring write, leaf <- max_priority with direct
 // ancestor atomics on every level, exact extremes bookkeeping.
-__global__ void __launch_bounds__(32) k_push_tiny(ReplayDev R, const float* __restrict__ rows, int n, float pmax) {
+template <bool kArgs>
+__global__ void __launch_bounds__(32) k_push_tiny(ReplayDev R, const float* __restrict__ rows_ptr, TinyRows rows_arg, int n, float pmax) {
+  const float* rows = kArgs ? rows_arg.v : rows_ptr;   // kArgs: the rows travelled inside the launch itself
   __shared__ float s_f[64];
   __shared__ int s_i[64];
   const int lane = threadIdx.x;

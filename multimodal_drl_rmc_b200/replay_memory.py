@@ -40,6 +40,11 @@ class DeviceRing:
                                       int(self.device_index)))
         self.handle, self.obs_dim = h, int(obs_dim)
         self.row_floats = lib().rmc_replay_row_floats(h)
+        d = self.obs_dim
+        self._small = (np.zeros((8, d), np.float32), np.zeros(8, np.int64), np.zeros(8, np.float32),
+                       np.zeros(8, np.float32), np.zeros((8, d), np.float32))
+        self._small_ptrs = tuple(a.ctypes.data for a in self._small)
+        self._push_fn = lib().rmc_replay_push_host
         return self
 
     def require(self):
@@ -57,6 +62,19 @@ class DeviceRing:
 
     # -- host-buffer push (what store_transitions uses) ---------------------------------
     def push_host(self, obses, actions, rews, dones, new_obses):
+        n = len(actions)
+        if n <= 8 and self.handle is not None:
+            # per-env-step push: copy into preallocated scratch arrays whose addresses are cached
+            b = self._small
+            b[0][:n] = obses
+            b[1][:n] = actions
+            b[2][:n] = rews
+            b[3][:n] = dones
+            b[4][:n] = new_obses
+            rc = self._push_fn(self.handle, *self._small_ptrs, n, stream_ptr(self.device_index))
+            if rc:
+                check(rc)
+            return
         obs = np.ascontiguousarray(np.asarray(obses, dtype=np.float32))
         if obs.ndim == 1:
             obs = obs.reshape(1, -1)
@@ -68,7 +86,7 @@ class DeviceRing:
         done = np.ascontiguousarray(np.asarray(dones, dtype=np.float32)).reshape(n)
         self.ensure(obs.shape[1])
         check(lib().rmc_replay_push_host(self.handle, obs.ctypes.data, act.ctypes.data, rew.ctypes.data,
-                                         done.ctypes.data, nxt.ctypes.data, n, stream_ptr()))
+                                         done.ctypes.data, nxt.ctypes.data, n, stream_ptr(self.device_index)))
 
     def push_device(self, obs, act, rew, done, nxt):
         """torch CUDA tensors: obs/nxt float32 [n,D], act int64 [n], rew/done float32 [n]."""
