@@ -44,7 +44,11 @@ BYTES_PER_TRANSITION_PER = 4 * (2 * D + 3) + 8 * TREE_LEVELS + 16 * TREE_LEVELS 
 BYTES_PER_TRANSITION_UNI = 4 * (2 * D + 3)                                          # 124
 METRIC = "learner transitions/sec (sample+TD+fwd/bwd+Adam) at 1/2/4/8 B200 vs host CPU"
 
+# --workload large65536: config C5 (strong scaling): ONE logical agent, B = 65,536, minibatch sharded over the
+# ranks with an NCCL gradient all-reduce (+ (leaf,|td|) all-gather for the replicated PER write-back).
 WORKLOADS = {
+    "large65536": dict(algo="PerDuelingDoubleDQNAgent", B=65536, cap=CAP, size=CAP, sharded=True,
+                       name="large-batch learner (batch 65,536) minibatch-sharded across GPUs with NCCL gradient allreduce (BASELINE configs[4])"),
     "per256": dict(algo="PerDuelingDoubleDQNAgent", B=256, cap=CAP, size=CAP,
                    name="PER+double+dueling DQN learner, batch 256, 1M-transition GPU-resident replay (BASELINE configs[1])"),
     "default32": dict(algo="DuelingDoubleDQNAgent", B=32, cap=CAP, size=100_000,
@@ -218,9 +222,12 @@ def run_ours(args, wl):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     B, K, W = wl["B"], args.steps, max(args.warmup, 3)
-    agent, data = build_gpu_agent(wl, local, seed=rank)
+    sharded = bool(wl.get("sharded"))
+    agent, data = build_gpu_agent(wl, local, seed=0 if sharded else rank)   # sharded: identical replicas on every rank
     obs, act, rew, done, nxt = data
     lib = _lib.lib()
+    if sharded:
+        return run_sharded(args, wl, agent, rank, world, local)
 
     def barrier():
         if world > 1:
@@ -331,6 +338,59 @@ def run_ours(args, wl):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_sharded(args, wl, agent, rank, world, local):
+    """C5: strong scaling of one B = 65,536 learner step over the ranks (ShardedLearner; NCCL over NVLink)."""
+    import torch
+    import torch.distributed as dist
+    from multimodal_drl_rmc_b200 import _lib
+    from multimodal_drl_rmc_b200.parallel import ShardedLearner
+    if world == 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29533")
+        dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", local))
+    sl = ShardedLearner(agent)
+    B, K, W = wl["B"], args.steps, max(args.warmup, 3)
+
+    def one_step():
+        agent.step += 1
+        return sl.learn()
+    for _ in range(W):
+        one_step()
+    dist.barrier()
+    torch.cuda.synchronize()
+    l0 = _lib.lib().rmc_launch_count()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(K):
+        loss = one_step()
+    e.record()
+    dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([s.elapsed_time(e)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    # replicas must stay identical: compare a weight checksum across ranks
+    chk = agent._lh.get_params(_lib.ONLINE).double().sum().reshape(1)
+    lo, hi = chk.clone(), chk.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        line = {"metric": METRIC, "value": B * K / (ms * 1e-3), "unit": "transitions/s", "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": wl["name"], "batch": B, "replay_capacity": wl["cap"], "replay_size": wl["size"], "obs_dim": D,
+                           "parallelism": "dp%d: minibatch sharded, replicated replay/tree/weights, NCCL all-reduce of %d gradient floats per step"
+                                          % (world, int(agent._lh.output("grads_blob").numel())),
+                           "l2": "inputs larger than L2 (144 MB replay + 200 MB step scratch)"},
+                "gpu_launches": int(_lib.lib().rmc_launch_count() - l0),
+                "replicas_identical": bool(float(lo) == float(hi)), "last_loss": float(loss.item()),
+                "roofline": {"bound": "tensor", "kernel": "k_learner_step (fp32 FFMA exact-parity mode)", "achieved": B * FLOP_PER_TRANSITION * K / (ms * 1e-3) / 1e12,
+                             "peak": 1682.8, "unit": "TFLOP/s", "frac": B * FLOP_PER_TRANSITION * K / (ms * 1e-3) / 1e12 / 1682.8, "traffic": None,
+                             "peak_source": "measured bf16 (MEASURED_PEAKS.json); this mode runs on the FP32 pipe by design"}}
+        print(json.dumps(line), flush=True)
+    dist.destroy_process_group()
 
 
 def _time_steps(fn, steps, warmup=10):
