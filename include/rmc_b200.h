@@ -214,9 +214,18 @@ int32_t rmc_learner_loss_sync(rmc_learner_t* l, float* out_host, rmc_stream_t s)
 /* Network.forward (network.py:59-63,90-96): Q values of `which` net (RMC_ONLINE/RMC_TARGET). */
 int32_t rmc_learner_q_values(rmc_learner_t* l, int32_t which, const float* obs_dev, int64_t n, float* q_out_dev,
                              rmc_stream_t s);
+/* DuelingDeepQNetwork.value / .advantages (network.py:98-108): raw head outputs [n][NH]; dueling: column 0 is
+ * the value stream, columns 1..A the advantages; plain head: NH = A (same as Q). */
+int32_t rmc_learner_heads(rmc_learner_t* l, int32_t which, const float* obs_dev, int64_t n, float* heads_out_dev,
+                          rmc_stream_t s);
 /* Network.actions (network.py:67-74, 110-117): greedy actions, dueling -> argmax of RAW
  * advantages, plain -> argmax Q; first maximum wins. */
 int32_t rmc_learner_act(rmc_learner_t* l, const float* obs_dev, int64_t n, int64_t* actions_dev, rmc_stream_t s);
+/* Tensor-core mode of the two calls above for the dense batched-act config (tcgen05.mma, bf16 operands, fp32
+ * accumulation in tensor memory).  NOT the parity path: Q within 1e-2 max-norm-relative of the fp32 kernel,
+ * greedy actions equal except near-ties (stated looser bound of the north star).  obs_dim <= 16. */
+int32_t rmc_learner_act_tc(rmc_learner_t* l, const float* obs_dev, int64_t n, int64_t* actions_dev, rmc_stream_t s);
+int32_t rmc_learner_heads_tc(rmc_learner_t* l, const float* obs_dev, int64_t n, float* heads_out_dev, rmc_stream_t s);
 /* same with host buffers (H2D + kernel + D2H, synchronises): what Agent.choose_actions calls. */
 int32_t rmc_learner_act_host_sync(rmc_learner_t* l, const float* obs_host, int64_t n, int64_t* actions_host,
                                   rmc_stream_t s);

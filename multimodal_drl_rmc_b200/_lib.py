@@ -115,7 +115,10 @@ _SIGS = {
     "rmc_learner_output": (_i32, [_vp, _cp, C.POINTER(_vp), C.POINTER(_i64)]),
     "rmc_learner_loss_sync": (_i32, [_vp, C.POINTER(_f32), _vp]),
     "rmc_learner_q_values": (_i32, [_vp, _i32, _vp, _i64, _vp, _vp]),
+    "rmc_learner_heads": (_i32, [_vp, _i32, _vp, _i64, _vp, _vp]),
     "rmc_learner_act": (_i32, [_vp, _vp, _i64, _vp, _vp]),
+    "rmc_learner_act_tc": (_i32, [_vp, _vp, _i64, _vp, _vp]),
+    "rmc_learner_heads_tc": (_i32, [_vp, _vp, _i64, _vp, _vp]),
     "rmc_learner_act_host_sync": (_i32, [_vp, _vp, _i64, _vp, _vp]),
     "rmc_learner_debug_timing": (_i32, [_vp, _i32]),
     "rmc_learner_debug_read_sync": (_i32, [_vp, _vp, _i32, C.POINTER(_i32), _vp]),

@@ -14,6 +14,7 @@
 
 #include "rmc_device.cuh"
 #include "rmc_mlp.cuh"
+#include "rmc_tc.cuh"
 #include "rmc_tree.cuh"
 
 using namespace rmc;
@@ -82,6 +83,7 @@ struct rmc_learner {
   unsigned loss_epoch = 0;          // epoch of the last launch that produced a loss
   volatile float* host_loss = nullptr;   // mapped pinned host memory (host view)
   unsigned long long* dbg_buf = nullptr;
+  unsigned char* tc_packed = nullptr;   // bf16 operands of the tensor-core act mode (lazily allocated)
   int last_grid = 0;
   // act staging
   float* act_pin_obs = nullptr; long long* act_pin_out = nullptr; float* act_dev_obs = nullptr; long long* act_dev_out = nullptr;
@@ -766,10 +768,42 @@ extern "C" int32_t rmc_learner_q_values(rmc_learner_t* l, int32_t which, const f
   return infer_launch(l, l->blobs[which], obs_dev, n, nullptr, q_out_dev, 1, as_stream(s));
 }
 
+extern "C" int32_t rmc_learner_heads(rmc_learner_t* l, int32_t which, const float* obs_dev, int64_t n, float* heads_out_dev, rmc_stream_t s) {
+  if (!l || !obs_dev || !heads_out_dev || n < 1 || (which != RMC_ONLINE && which != RMC_TARGET)) return fail(RMC_ERR_ARG, "rmc_learner_heads: bad args");
+  if (int32_t e = use_device(l->device)) return e;
+  return infer_launch(l, l->blobs[which], obs_dev, n, nullptr, heads_out_dev, 2, as_stream(s));
+}
+
 extern "C" int32_t rmc_learner_act(rmc_learner_t* l, const float* obs_dev, int64_t n, int64_t* actions_dev, rmc_stream_t s) {
   if (!l || !obs_dev || !actions_dev || n < 1) return fail(RMC_ERR_ARG, "rmc_learner_act: bad args");
   if (int32_t e = use_device(l->device)) return e;
   return infer_launch(l, l->blobs[RMC_ONLINE], obs_dev, n, reinterpret_cast<long long*>(actions_dev), nullptr, 0, as_stream(s));
+}
+
+// tensor-core (tcgen05, bf16 operands / fp32 accumulate) mode of act / heads: looser, stated bound (see rmc_tc.cuh)
+static int32_t infer_tc(rmc_learner* l, const float* obs_dev, long long n, long long* actions, float* heads, int mode, cudaStream_t st) {
+  if (l->L.D > kTcK1) return fail(RMC_ERR_UNSUPPORTED, "tensor-core act mode: obs_dim must be <= 16");
+  if (l->tc_packed == nullptr) {
+    if (int32_t e = owned_alloc(l, &l->tc_packed, static_cast<size_t>(kTcBlobBytes))) return e;
+    RMC_CUDA(cudaFuncSetAttribute(k_mlp_infer_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
+  }
+  k_tc_pack<<<blocks_for(kH2 * kH1, 256), 256, 0, st>>>(l->blobs[RMC_ONLINE], l->L, l->tc_packed);
+  RMC_KERNEL_OK();
+  const long long n_tiles = (n + kTcRows - 1) / kTcRows;
+  const unsigned grid = static_cast<unsigned>(std::min<long long>(n_tiles, l->num_sms));
+  k_mlp_infer_tc<<<grid, kThreads, kTcSmemBytes, st>>>(l->tc_packed, l->L.D, l->L.A, l->L.NH, l->L.dueling, obs_dev, n, actions, heads, mode);
+  RMC_KERNEL_OK();
+  return RMC_OK;
+}
+extern "C" int32_t rmc_learner_act_tc(rmc_learner_t* l, const float* obs_dev, int64_t n, int64_t* actions_dev, rmc_stream_t s) {
+  if (!l || !obs_dev || !actions_dev || n < 1) return fail(RMC_ERR_ARG, "rmc_learner_act_tc: bad args");
+  if (int32_t e = use_device(l->device)) return e;
+  return infer_tc(l, obs_dev, n, reinterpret_cast<long long*>(actions_dev), nullptr, 0, as_stream(s));
+}
+extern "C" int32_t rmc_learner_heads_tc(rmc_learner_t* l, const float* obs_dev, int64_t n, float* heads_out_dev, rmc_stream_t s) {
+  if (!l || !obs_dev || !heads_out_dev || n < 1) return fail(RMC_ERR_ARG, "rmc_learner_heads_tc: bad args");
+  if (int32_t e = use_device(l->device)) return e;
+  return infer_tc(l, obs_dev, n, nullptr, heads_out_dev, 2, as_stream(s));
 }
 
 extern "C" int32_t rmc_learner_act_host_sync(rmc_learner_t* l, const float* obs_host, int64_t n, int64_t* actions_host, rmc_stream_t s) {

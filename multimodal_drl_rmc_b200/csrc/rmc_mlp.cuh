@@ -734,6 +734,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, c
 // ------------------------------------------------------------------ batched act / Q values
 // mode 0: greedy actions (dueling -> argmax raw adv, plain -> argmax Q; dqn/network.py:67-74,110-117)
 // mode 1: Q values [n][A]
+// mode 2: raw head outputs [n][NH]
 __global__ void __launch_bounds__(kThreads, 1) k_mlp_infer(NetLayout L, const float* __restrict__ params, const float* __restrict__ obs,
                                                            long long n, long long* __restrict__ actions, float* __restrict__ q_out, int mode) {
   extern __shared__ __align__(16) float smem[];
@@ -768,11 +769,17 @@ __global__ void __launch_bounds__(kThreads, 1) k_mlp_infer(NetLayout L, const fl
         const long long i = tile * kR + tid;
         if (i < n) actions[i] = L.dueling ? argmax_first(sRaw + tid * kQLD + 1, L.A) : argmax_first(sQ + tid * kQLD, L.A);
       }
-    } else {
+    } else if (mode == 1) {
       for (int t = tid; t < kR * L.A; t += kThreads) {
         const int r = t / L.A, a = t % L.A;
         const long long i = tile * kR + r;
         if (i < n) q_out[i * L.A + a] = sQ[r * kQLD + a];
+      }
+    } else {   // mode 2: raw head outputs [n][NH] (dueling: value then advantages; network.py:98-108)
+      for (int t = tid; t < kR * L.NH; t += kThreads) {
+        const int r = t / L.NH, a = t % L.NH;
+        const long long i = tile * kR + r;
+        if (i < n) q_out[i * L.NH + a] = sRaw[r * kQLD + a];
       }
     }
     __syncthreads();

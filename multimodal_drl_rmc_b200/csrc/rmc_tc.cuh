@@ -1,0 +1,266 @@
+// rmc_tc.cuh -- tensor-core (tcgen05 / TMEM) mode of the batched act kernel for the DENSE config
+// (BASELINE configs[2]: 65,536 macro-state vectors).  bf16 operands, fp32 accumulation in tensor memory.
+//
+// This is the "stated looser bound" mode of the north star: Q values within 1e-2 max-norm-relative of the fp32
+// path (bf16 operand rounding, SURVEY 7.2 estimated 2.5e-3), greedy actions equal except near-ties.  The exact
+// fp32 FFMA kernel (k_mlp_infer) stays the default and the parity reference.
+//
+// One CTA (256 threads) owns a 128-row tile; the three layers are chained through tensor memory:
+//   X[128x16]  . W0^T -> D1 (TMEM, 256 cols) -> +b0, ReLU, bf16 -> H1 (smem, UMMA canonical K-major layout)
+//   H1[128x256]. W2^T -> D2 (TMEM, 128 cols) -> +b2, ReLU, bf16 -> H2 (smem)
+//   H2[128x128]. Wh^T -> D3 (TMEM,  16 cols) -> +bh, argmax    -> actions
+// tcgen05.mma is issued by one thread; accumulators are read back with tcgen05.ld (32 lanes x 32 columns per
+// warp and instruction).  Operands use the no-swizzle canonical layout: 8x8-element core matrices of 128
+// contiguous bytes, K-adjacent cores LBO = 128 B apart, 8-row groups SBO = (K/8)*128 B apart.
+#pragma once
+#include <cuda_bf16.h>
+
+#include "rmc_device.cuh"
+
+namespace rmc {
+
+constexpr int kTcRows = 128;         // rows per tile = UMMA M
+constexpr int kTcK1 = 16;            // layer-1 K (obs_dim padded to one UMMA_K step)
+constexpr int kTcNH = 16;            // heads padded to the minimum N for M = 128
+// packed bf16 blob (element offsets, bf16 units)
+constexpr int kTcOffW0 = 0;                            // [256 rows][K = 16]
+constexpr int kTcOffW2 = kTcOffW0 + kH1 * kTcK1;       // [128 rows][K = 256]
+constexpr int kTcOffWh = kTcOffW2 + kH2 * kH1;         // [ 16 rows][K = 128]
+constexpr int kTcBf16Elems = kTcOffWh + kTcNH * kH2;   // 38,912 bf16 = 77,824 B
+constexpr int kTcBiasFloats = kH1 + kH2 + kTcNH;       // 400 floats
+constexpr int kTcBlobBytes = kTcBf16Elems * 2 + kTcBiasFloats * 4;   // 79,424 B (multiple of 16)
+
+// element offset of (row r, k) inside a canonical K-major no-swizzle operand with K columns
+__host__ __device__ __forceinline__ int tc_off(int r, int k, int K) {
+  return ((r >> 3) * (K >> 3) + (k >> 3)) * 64 + (r & 7) * 8 + (k & 7);
+}
+
+// fp32 device-layout parameter blob -> packed bf16 operands + fp32 biases
+__global__ void k_tc_pack(const float* __restrict__ blob, NetLayout L, unsigned char* __restrict__ out) {
+  __nv_bfloat16* w = reinterpret_cast<__nv_bfloat16*>(out);
+  float* bias = reinterpret_cast<float*>(out + kTcBf16Elems * 2);
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < kH1 * kTcK1) {                                  // W0[i][d]
+    const int i = t / kTcK1, d = t % kTcK1;
+    w[kTcOffW0 + tc_off(i, d, kTcK1)] = __float2bfloat16_rn(d < L.D ? blob[L.off_w0t + d * kH1 + i] : 0.f);
+  }
+  if (t < kH2 * kH1) {                                    // W2[j][k]
+    const int j = t / kH1, k = t % kH1;
+    w[kTcOffW2 + tc_off(j, k, kH1)] = __float2bfloat16_rn(blob[L.off_w2t + k * kW2LD + j]);
+  }
+  if (t < kTcNH * kH2) {                                  // Wh[a][j]
+    const int a = t / kH2, j = t % kH2;
+    w[kTcOffWh + tc_off(a, j, kH2)] = __float2bfloat16_rn(a < L.NH ? blob[L.off_wh + a * kH2 + j] : 0.f);
+  }
+  if (t < kH1) bias[t] = blob[L.off_b0 + t];
+  if (t < kH2) bias[kH1 + t] = blob[L.off_b2 + t];
+  if (t < kTcNH) bias[kH1 + kH2 + t] = (t < L.NH) ? blob[L.off_bh + t] : 0.f;
+}
+
+// ---- tcgen05 wrappers -----------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t tc_smem_desc(const void* smem_ptr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  const uint32_t addr = smem_u32(smem_ptr);
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((addr >> 4) & 0x3fff);                // start address        bits [0,14)
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3fff) << 16;     // leading byte offset  bits [16,30)
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3fff) << 32;     // stride byte offset   bits [32,46)
+  d |= 1ull << 46;                                                  // descriptor version 1 (sm_100)
+  return d;                                                         // layout_type = 0: no swizzle
+}
+__device__ __forceinline__ uint32_t tc_idesc_bf16(int M, int N) {
+  return (1u << 4)                                  // accumulator format f32
+         | (1u << 7) | (1u << 10)                   // A, B formats bf16
+         | (static_cast<uint32_t>(N >> 3) << 17)    // N / 8
+         | (static_cast<uint32_t>(M >> 4) << 24);   // M / 16 ; A and B K-major, no negate, dense
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);   // .x = lo (low 16 bits)
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+
+// epilogue of one hidden layer: TMEM columns [c0, c0+32*n32) of this warp's 32 lanes -> +bias, ReLU, bf16 ->
+// canonical K-major operand `dst` (K = Kdst) for the next layer.  row = TMEM lane.
+__device__ __forceinline__ void tc_hidden_epilogue(uint32_t tmem_acc, int lane_base, int row, int c0, int n32,
+                                                   const float* __restrict__ bias, __nv_bfloat16* __restrict__ dst, int Kdst) {
+  for (int b = 0; b < n32; ++b) {
+    const int col = c0 + 32 * b;
+    uint32_t v[32];
+    tc_ld32(tmem_acc + (static_cast<uint32_t>(lane_base) << 16) + col, v);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {              // 4 cores of 8 columns
+      float f[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] = fmaxf(__uint_as_float(v[8 * c + e]) + bias[col + 8 * c + e], 0.f);
+      uint4 q;
+      q.x = pack_bf16x2(f[0], f[1]); q.y = pack_bf16x2(f[2], f[3]); q.z = pack_bf16x2(f[4], f[5]); q.w = pack_bf16x2(f[6], f[7]);
+      *reinterpret_cast<uint4*>(dst + tc_off(row, col + 8 * c, Kdst)) = q;
+    }
+  }
+}
+
+// mode 0: actions (dueling: argmax of raw advantages = head columns 1..A; plain: argmax of columns 0..A-1)
+// mode 2: raw head outputs [n][NH] float (diagnostics / error measurement)
+__global__ void __launch_bounds__(kThreads, 1) k_mlp_infer_tc(const unsigned char* __restrict__ packed, int D, int A, int NH, int dueling,
+                                                              const float* __restrict__ obs, long long n,
+                                                              long long* __restrict__ actions, float* __restrict__ heads_out, int mode) {
+  extern __shared__ __align__(128) unsigned char tsm[];
+  __nv_bfloat16* sWts = reinterpret_cast<__nv_bfloat16*>(tsm);                 // packed W0 | W2 | Wh
+  float* sBias = reinterpret_cast<float*>(tsm + kTcBf16Elems * 2);             // b0 | b2 | bh
+  __nv_bfloat16* sX = reinterpret_cast<__nv_bfloat16*>(tsm + kTcBlobBytes);     // [128][16]
+  __nv_bfloat16* sH1 = sX + kTcRows * kTcK1;                                    // [128][256]
+  __nv_bfloat16* sH2 = sH1 + kTcRows * kH1;                                     // [128][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sH2 + kTcRows * kH2);            // [0] weights, [1..3] MMA stages
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long n_tiles = (n + kTcRows - 1) / kTcRows;
+  if (blockIdx.x >= n_tiles) return;
+
+  if (tid == 0) {
+    for (int b = 0; b < 4; ++b) mbar_init(bars + b, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) {   // tensor-memory allocation: 512 columns (D1 256 | D2 128 | D3 16), one warp, then release the permit
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tD1 = tmem, tD2 = tmem + 256, tD3 = tmem + 384;
+  if (tid == 0) {    // weights + biases: one TMA bulk copy
+    mbar_expect_tx(bars + 0, kTcBlobBytes);
+    bulk_g2s(tsm, packed, kTcBlobBytes, bars + 0);
+  }
+  mbar_wait(bars + 0, 0);
+
+  const uint32_t id1 = tc_idesc_bf16(kTcRows, kH1), id2 = tc_idesc_bf16(kTcRows, kH2), id3 = tc_idesc_bf16(kTcRows, kTcNH);
+  const int q = warp & 3, half = warp >> 2;       // TMEM lane quarter of this warp, column half it handles
+  const int row = 32 * q + lane;                  // tile row = TMEM lane
+  uint32_t phase = 0;
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    // ---- X tile: fp32 obs -> bf16 canonical [128][16]; thread = (row, 8-column core)
+    {
+      const int r = tid >> 1, c = tid & 1;
+      const long long i = tile * kTcRows + r;
+      float f[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int d = 8 * c + e;
+        f[e] = (i < n && d < D) ? __ldg(obs + i * D + d) : 0.f;
+      }
+      uint4 v;
+      v.x = pack_bf16x2(f[0], f[1]); v.y = pack_bf16x2(f[2], f[3]); v.z = pack_bf16x2(f[4], f[5]); v.w = pack_bf16x2(f[6], f[7]);
+      *reinterpret_cast<uint4*>(sX + tc_off(r, 8 * c, kTcK1)) = v;
+    }
+    fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core's async proxy
+    tc_fence_before();
+    __syncthreads();
+    // ---- layer 1: D1[128x256] = X . W0^T  (one UMMA, K = 16)
+    if (tid == 0) {
+      tc_fence_after();
+      tc_mma_bf16(tD1, tc_smem_desc(sX, 128, (kTcK1 / 8) * 128), tc_smem_desc(sWts + kTcOffW0, 128, (kTcK1 / 8) * 128), id1, 0u);
+      tc_commit(bars + 1);
+    }
+    mbar_wait(bars + 1, phase);
+    tc_fence_after();
+    tc_hidden_epilogue(tD1, 32 * q, row, 128 * half, 4, sBias, sH1, kH1);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    // ---- layer 2: D2[128x128] = H1 . W2^T  (K = 256: 16 UMMAs, descriptors advance by 2 cores = 256 B)
+    if (tid == 0) {
+      tc_fence_after();
+      const uint64_t a0 = tc_smem_desc(sH1, 128, (kH1 / 8) * 128), b0 = tc_smem_desc(sWts + kTcOffW2, 128, (kH1 / 8) * 128);
+#pragma unroll
+      for (int k = 0; k < kH1 / 16; ++k) tc_mma_bf16(tD2, a0 + static_cast<uint64_t>(k * 16), b0 + static_cast<uint64_t>(k * 16), id2, k > 0 ? 1u : 0u);
+      tc_commit(bars + 2);
+    }
+    mbar_wait(bars + 2, phase);
+    tc_fence_after();
+    tc_hidden_epilogue(tD2, 32 * q, row, 64 * half, 2, sBias + kH1, sH2, kH2);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    // ---- heads: D3[128x16] = H2 . Wh^T  (K = 128: 8 UMMAs)
+    if (tid == 0) {
+      tc_fence_after();
+      const uint64_t a0 = tc_smem_desc(sH2, 128, (kH2 / 8) * 128), b0 = tc_smem_desc(sWts + kTcOffWh, 128, (kH2 / 8) * 128);
+#pragma unroll
+      for (int k = 0; k < kH2 / 16; ++k) tc_mma_bf16(tD3, a0 + static_cast<uint64_t>(k * 16), b0 + static_cast<uint64_t>(k * 16), id3, k > 0 ? 1u : 0u);
+      tc_commit(bars + 3);
+    }
+    mbar_wait(bars + 3, phase);
+    tc_fence_after();
+    if (half == 0) {
+      uint32_t v[16];
+      tc_ld16(tD3 + (static_cast<uint32_t>(32 * q) << 16), v);
+      const long long i = tile * kTcRows + row;
+      if (i < n) {
+        const float* bh = sBias + kH1 + kH2;
+        if (mode == 0) {
+          const int first = dueling ? 1 : 0;
+          int best = 0;
+          float bv = __uint_as_float(v[first]) + bh[first];
+#pragma unroll
+          for (int a = 1; a < 15; ++a) {
+            if (a < A) {
+              const float x = __uint_as_float(v[first + a]) + bh[first + a];
+              if (x > bv) { bv = x; best = a; }
+            }
+          }
+          actions[i] = best;
+        } else {
+#pragma unroll
+          for (int a = 0; a < kTcNH; ++a)
+            if (a < NH) heads_out[i * NH + a] = __uint_as_float(v[a]) + bh[a];
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();      // TMEM accumulators and operand buffers are free for the next tile
+    phase ^= 1u;
+  }
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+
+constexpr int kTcSmemBytes = kTcBlobBytes + (kTcRows * kTcK1 + kTcRows * kH1 + kTcRows * kH2) * 2 + 4 * 8 + 16;
+
+}  // namespace rmc

@@ -185,12 +185,21 @@ class Network(nn.Module):
         check(lib().rmc_learner_q_values(lh.handle, self._kind, ptr(x), x.shape[0], ptr(q), stream_ptr()))
         return q[0] if squeeze else q
 
-    def actions(self, obses):
-        """Greedy actions as a python list (network.py:67-74 / 110-117); host buffers in and out."""
+    def actions(self, obses, precision="fp32"):
+        """Greedy actions as a python list (network.py:67-74 / 110-117); host buffers in and out.
+        ``precision="bf16"`` selects the tcgen05 tensor-core kernel (dense batches; looser stated bound)."""
         lh = self._standalone_handle()
         self._push()
         if self._kind != _lib.ONLINE:
             raise RuntimeError("actions() is served from the online blob")
+        if precision == "bf16":
+            dev = T.device("cuda", lh.device_index)
+            x = T.as_tensor(obses, dtype=T.float32, device=dev).contiguous().reshape(-1, self._obs_dim)
+            out = T.empty(x.shape[0], dtype=T.int64, device=dev)
+            check(lib().rmc_learner_act_tc(lh.handle, ptr(x), x.shape[0], ptr(out), stream_ptr()))
+            return out.tolist()
+        if precision != "fp32":
+            raise ValueError("precision must be 'fp32' or 'bf16'")
         if T.is_tensor(obses) and obses.is_cuda:
             x = obses.to(T.float32).contiguous().reshape(-1, self._obs_dim)
             out = T.empty(x.shape[0], dtype=T.int64, device=x.device)
@@ -246,8 +255,19 @@ class DuelingDeepQNetwork(Network):
         self.loss = self.loss_func(reduction=reduction)
         self.to(self.device)
 
+    def _heads(self, s):
+        lh = self._standalone_handle()
+        self._push()
+        dev = T.device("cuda", lh.device_index)
+        x = T.as_tensor(s, dtype=T.float32, device=dev).contiguous().reshape(-1, self._obs_dim)
+        out = T.empty(x.shape[0], self._n_actions + 1, dtype=T.float32, device=dev)
+        check(lib().rmc_learner_heads(lh.handle, self._kind, ptr(x), x.shape[0], ptr(out), stream_ptr()))
+        return out
+
     def value(self, s):
-        raise NotImplementedError("value(): only forward()/advantages-argmax (actions) are served by the fused path")
+        """network.py:98-102."""
+        return self._heads(s)[:, :1]
 
     def advantages(self, s):
-        raise NotImplementedError("advantages(): only forward()/actions() are served by the fused path")
+        """network.py:104-108."""
+        return self._heads(s)[:, 1:]
