@@ -424,7 +424,12 @@ def extra_workloads(agent):
             net.actions(states)
         host_ms = 1e3 * (time.perf_counter() - t0) / 5
         out["act_65536"] = {"device_ms": ms, "states_per_s": 65536 / (ms * 1e-3), "fp32_tflops": 65536 * 2 * (D * H1 + H1 * H2 + H2 * A) / (ms * 1e-3) / 1e12,
-                            "host_api_ms": host_ms, "host_api_states_per_s": 65536 / (host_ms * 1e-3)}
+                            "host_api_ms": host_ms, "host_api_states_per_s": 65536 / (host_ms * 1e-3), "mode": "fp32 FFMA (exact parity)"}
+        ms_tc = _time_steps(lambda: _lib.check(_lib.lib().rmc_learner_act_tc(lh.handle, dev_states.data_ptr(), 65536, acts.data_ptr(), _lib.stream_ptr())), 50, 5)
+        flops_tc = 65536 * 2 * (16 * H1 + H1 * H2 + H2 * 16)      # padded shapes the tensor core actually runs
+        out["act_65536_tc"] = {"device_ms": ms_tc, "states_per_s": 65536 / (ms_tc * 1e-3), "tensor_tflops": flops_tc / (ms_tc * 1e-3) / 1e12,
+                               "frac_of_measured_bf16_peak": flops_tc / (ms_tc * 1e-3) / 1e12 / 1682.8,
+                               "mode": "tcgen05 bf16 operands / fp32 TMEM accumulate (Q within 1e-2 of fp32; includes the per-call weight pack kernel)"}
     except Exception as exc:  # pragma: no cover
         out["act_65536"] = {"error": repr(exc)}
     try:   # C1: repo defaults (B = 32, uniform replay)

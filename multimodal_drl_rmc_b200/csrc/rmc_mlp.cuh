@@ -66,7 +66,7 @@ __host__ __device__ inline SmemPlan make_smem_plan(int param_floats) {
 // phase-B staging (reuses the same dynamic shared memory)
 constexpr int kGChunk = 256;                         // batch rows staged per chunk
 // phase-B unit shapes: 16x16 (W2), 16x32 (W0: D<=16 rows x 32 hidden units), 32x16 (heads: 32 h2 columns x NH)
-constexpr int kGemmSmemFloats = kGChunk * (32 + 32) + kWarps * 32 * 16 + kWarps * 32;
+constexpr int kGemmSmemFloats = kGChunk * (32 + 32) + kWarps * 32 * 32 + kWarps * 32;
 
 // ------------------------------------------------------------------ forward of R rows (R = 4 or 8)
 // sXT[d][kR], rows [0,R) are computed.  Results: sH1T[k][r], sH2[r][j], sQ[r][a] (Q values, or raw
@@ -345,16 +345,19 @@ __device__ void wgrad_unit(const AgentCtx& C, const StepScalars& S, const GemmUn
   __syncthreads();
 }
 
-// units: [W0: mt0 x 8 of 16x32] [W2: 16 x 8 of 16x16] [heads: 4 of 32x16]  = 140 for D <= 16
-__device__ __forceinline__ int wgrad_unit_count(const NetLayout& L) {
-  return ((L.D + 15) / 16) * (kH1 / 32) + (kH1 / 16) * (kH2 / 16) + kH2 / 32;
+// Unit decomposition.  fine (many workers): [W0: mt0 x 8 of 16x32] [W2: 16 x 8 of 16x16] [heads: 4 of 32x16] = 140
+// for D <= 16; coarse (few workers per agent, e.g. 8-agent ensembles): [W0: mt0 x 8 of 16x32] [W2: 8 x 4 of 32x32]
+// [heads: 4 of 32x16] = 44.
+__device__ __forceinline__ int wgrad_unit_count(const NetLayout& L, bool coarse) {
+  const int w2 = coarse ? (kH1 / 32) * (kH2 / 32) : (kH1 / 16) * (kH2 / 16);
+  return ((L.D + 15) / 16) * (kH1 / 32) + w2 + kH2 / 32;
 }
 
-__device__ void wgrad_run_unit(const AgentCtx& C, const StepScalars& S, int u, float* smem) {
+__device__ void wgrad_run_unit(const AgentCtx& C, const StepScalars& S, int u, bool coarse, float* smem) {
   const NetLayout& L = C.L;
   GemmUnit U;
   const int mt0 = (L.D + 15) / 16;
-  const int n_w0 = mt0 * (kH1 / 32), n_w2 = (kH1 / 16) * (kH2 / 16);
+  const int n_w0 = mt0 * (kH1 / 32), n_w2 = coarse ? (kH1 / 32) * (kH2 / 32) : (kH1 / 16) * (kH2 / 16);
   if (u < n_w0) {                       // dW0^T[d][i] = sum_b X[b][d] * DZ1[b][i] ; db0 = colsum(DZ1)
     const int mt = u / (kH1 / 32), nt = u % (kH1 / 32);
     U.A = C.X; U.lda = C.rp.row_floats; U.m0 = mt * 16; U.m_valid = min(16, L.D - mt * 16);
@@ -363,12 +366,14 @@ __device__ void wgrad_run_unit(const AgentCtx& C, const StepScalars& S, int u, f
     U.bias_base = (mt == 0) ? L.off_b0 + U.n0 : -1;
     wgrad_unit<16, 32>(C, S, U, smem);
   } else if (u < n_w0 + n_w2) {         // dW2^T[k][j] = sum_b H1[b][k] * DZ2[b][j] ; db2 = colsum(DZ2)
-    const int v = u - n_w0, kt = v / (kH2 / 16), jt = v % (kH2 / 16);
-    U.A = C.H1; U.lda = kH1; U.m0 = kt * 16; U.m_valid = 16;
-    U.Bm = C.DZ2; U.ldb = kH2; U.n0 = jt * 16; U.n_valid = 16;
+    const int T = coarse ? 32 : 16;
+    const int v = u - n_w0, kt = v / (kH2 / T), jt = v % (kH2 / T);
+    U.A = C.H1; U.lda = kH1; U.m0 = kt * T; U.m_valid = T;
+    U.Bm = C.DZ2; U.ldb = kH2; U.n0 = jt * T; U.n_valid = T;
     U.out_base = L.off_w2t + U.m0 * kW2LD + U.n0; U.out_sm = kW2LD; U.out_sn = 1;
     U.bias_base = (kt == 0) ? L.off_b2 + U.n0 : -1;
-    wgrad_unit<16, 16>(C, S, U, smem);
+    if (coarse) wgrad_unit<32, 32>(C, S, U, smem);
+    else wgrad_unit<16, 16>(C, S, U, smem);
   } else {                              // dWh[a][j] = sum_b H2[b][j] * DH[b][a] ; dbh = colsum(DH)
     const int jt = u - n_w0 - n_w2;
     U.A = C.H2; U.lda = kH2; U.m0 = jt * 32; U.m_valid = 32;
@@ -677,7 +682,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, c
   // ---------------------------------------------------------------- phase B
   const bool tree_here = per && (S.phases & 4) && C.rp.prioritized && B <= kTreeCtaMax;
   // big tree + enough CTAs: a team of kTreeTeam CTAs shares the write-back; otherwise one CTA does it
-  const bool team = tree_here && (2 * C.rp.cap - 1 >= 2 * kTopRebuild + 1) && (G >= wgrad_unit_count(L) + kTreeTeam);
+  const bool coarse = G < 100;   // few CTAs per agent (ensembles): 32x32 gradient tiles instead of 16x16
+  const bool team = tree_here && (2 * C.rp.cap - 1 >= 2 * kTopRebuild + 1) && (G >= wgrad_unit_count(L, false) + kTreeTeam);
   const int n_tree = !tree_here ? 0 : (team ? kTreeTeam : 1);
   int n_workers = G, wid = cta;
   if (tree_here && G > 1) {
@@ -713,8 +719,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, c
     }
   }
   if (S.phases & 8) {                             // BACKWARD (+ fused Adam/Polyak)
-    const int n_units = wgrad_unit_count(L);
-    for (int u = wid; u < n_units; u += n_workers) wgrad_run_unit(C, S, u, smem);
+    const int n_units = wgrad_unit_count(L, coarse);
+    for (int u = wid; u < n_units; u += n_workers) wgrad_run_unit(C, S, u, coarse, smem);
   } else if (S.phases & (16 | 32 | 64)) {         // element-wise Adam from given grads / target sync only
     const float* gsrc = (S.grads_in != nullptr) ? S.grads_in + static_cast<size_t>(agent) * L.total : C.grads;
     for (int pi = wid * kThreads + tid; pi < L.total; pi += n_workers * kThreads)
