@@ -84,6 +84,7 @@ struct rmc_learner {
   volatile float* host_loss = nullptr;   // mapped pinned host memory (host view)
   unsigned long long* dbg_buf = nullptr;
   unsigned char* tc_packed = nullptr;   // bf16 operands of the tensor-core act mode (lazily allocated)
+  unsigned long long online_version = 1, tc_packed_version = 0;   // repack only when the online weights changed
   int last_grid = 0;
   // act staging
   float* act_pin_obs = nullptr; long long* act_pin_out = nullptr; float* act_dev_obs = nullptr; long long* act_dev_out = nullptr;
@@ -570,6 +571,7 @@ extern "C" int32_t rmc_learner_set_params(rmc_learner_t* l, int32_t kind, const 
   }
   k_params_scatter<<<blocks_for(n, 256), 256, 0, st>>>(l->blobs[kind], dsrc, l->map, n);
   RMC_KERNEL_OK();
+  if (kind == RMC_ONLINE) ++l->online_version;
   if (src_is_host) RMC_CUDA(cudaStreamSynchronize(st));
   return RMC_OK;
 }
@@ -699,6 +701,7 @@ extern "C" int32_t rmc_learner_step(rmc_learner_t* l, rmc_replay_t* r, const rmc
   if (int32_t e = launch_step(dim3(G, 1, 1), args, static_cast<size_t>(l->smem_bytes), st)) return e;
   if (rows && phase_b) l->barrier_count = S.barrier_target;
   if ((a->phases & RMC_PH_FORWARD) && phase_b) l->loss_epoch = S.epoch;
+  if (a->phases & RMC_PH_ADAM) ++l->online_version;
   if ((a->phases & RMC_PH_PRIORITY) && l->spec.prioritized && a->batch > kTreeCtaMax) {
     k_td_to_pri<<<blocks_for(a->batch, 256), 256, 0, st>>>(l->ctx.abs_td, l->ctx.pri, a->batch, S.per_eps, S.per_alpha, S.per_pmax);
     RMC_KERNEL_OK();
@@ -787,8 +790,11 @@ static int32_t infer_tc(rmc_learner* l, const float* obs_dev, long long n, long 
     if (int32_t e = owned_alloc(l, &l->tc_packed, static_cast<size_t>(kTcBlobBytes))) return e;
     RMC_CUDA(cudaFuncSetAttribute(k_mlp_infer_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
   }
-  k_tc_pack<<<blocks_for(kH2 * kH1, 256), 256, 0, st>>>(l->blobs[RMC_ONLINE], l->L, l->tc_packed);
-  RMC_KERNEL_OK();
+  if (l->tc_packed_version != l->online_version) {
+    k_tc_pack<<<blocks_for(kH2 * kH1, 256), 256, 0, st>>>(l->blobs[RMC_ONLINE], l->L, l->tc_packed);
+    RMC_KERNEL_OK();
+    l->tc_packed_version = l->online_version;
+  }
   const long long n_tiles = (n + kTcRows - 1) / kTcRows;
   const unsigned grid = static_cast<unsigned>(std::min<long long>(n_tiles, l->num_sms));
   k_mlp_infer_tc<<<grid, kThreads, kTcSmemBytes, st>>>(l->tc_packed, l->L.D, l->L.A, l->L.NH, l->L.dueling, obs_dev, n, actions, heads, mode);
@@ -898,7 +904,10 @@ extern "C" int32_t rmc_group_step(rmc_group_t* g, const rmc_step_args_t* a, rmc_
   if (rows && phase_b) S.barrier_target = g->barrier_count + static_cast<unsigned>(G);
   g->epoch = (g->epoch == 0xffffffffu) ? 1u : g->epoch + 1u;
   S.epoch = g->epoch;
-  for (int i = 0; i < g->n; ++i) g->learners[i]->last_batch = a->batch;
+  for (int i = 0; i < g->n; ++i) {
+    g->learners[i]->last_batch = a->batch;
+    if (a->phases & RMC_PH_ADAM) ++g->learners[i]->online_version;
+  }
   AgentCtx single = l0->ctx;
   const AgentCtx* many = g->ctx_dev;
   void* args[] = {&single, &many, &S};

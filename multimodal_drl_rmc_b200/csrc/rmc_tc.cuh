@@ -9,6 +9,8 @@
 //   X[128x16]  . W0^T -> D1 (TMEM, 256 cols) -> +b0, ReLU, bf16 -> H1 (smem, UMMA canonical K-major layout)
 //   H1[128x256]. W2^T -> D2 (TMEM, 128 cols) -> +b2, ReLU, bf16 -> H2 (smem)
 //   H2[128x128]. Wh^T -> D3 (TMEM,  16 cols) -> +bh, argmax    -> actions
+// and runs TWO such tile pipelines side by side (warps 0-3 / 4-7) so that one group's epilogue overlaps the other
+// group's MMAs.
 // tcgen05.mma is issued by one thread; accumulators are read back with tcgen05.ld (32 lanes x 32 columns per
 // warp and instruction).  Operands use the no-swizzle canonical layout: 8x8-element core matrices of 128
 // contiguous bytes, K-adjacent cores LBO = 128 B apart, 8-row groups SBO = (K/8)*128 B apart.
@@ -114,12 +116,12 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return *reinterpret_cast<const uint32_t*>(&v);
 }
 
-// epilogue of one hidden layer: TMEM columns [c0, c0+32*n32) of this warp's 32 lanes -> +bias, ReLU, bf16 ->
+// epilogue of one hidden layer: TMEM columns [0, 32*n32) of this warp's 32 lanes -> +bias, ReLU, bf16 ->
 // canonical K-major operand `dst` (K = Kdst) for the next layer.  row = TMEM lane.
-__device__ __forceinline__ void tc_hidden_epilogue(uint32_t tmem_acc, int lane_base, int row, int c0, int n32,
+__device__ __forceinline__ void tc_hidden_epilogue(uint32_t tmem_acc, int lane_base, int row, int n32,
                                                    const float* __restrict__ bias, __nv_bfloat16* __restrict__ dst, int Kdst) {
   for (int b = 0; b < n32; ++b) {
-    const int col = c0 + 32 * b;
+    const int col = 32 * b;
     uint32_t v[32];
     tc_ld32(tmem_acc + (static_cast<uint32_t>(lane_base) << 16) + col, v);
 #pragma unroll
@@ -133,7 +135,14 @@ __device__ __forceinline__ void tc_hidden_epilogue(uint32_t tmem_acc, int lane_b
     }
   }
 }
+__device__ __forceinline__ void tc_group_sync(int g) {   // the 128 threads of one tile pipeline
+  asm volatile("bar.sync %0, 128;" ::"r"(g + 1) : "memory");
+}
 
+// Two independent tile pipelines per CTA (warps 0-3 and 4-7): while one group runs its epilogue on the CUDA
+// cores, the other group's UMMAs occupy the tensor core.  Per group: 256 TMEM columns (D2 aliases D1[0:128),
+// D3 aliases D1[128:144) -- each is written only after its predecessor has been drained) and one 64 KB operand
+// buffer (H2 overwrites H1 once layer 2 has consumed it).
 // mode 0: actions (dueling: argmax of raw advantages = head columns 1..A; plain: argmax of columns 0..A-1)
 // mode 2: raw head outputs [n][NH] float (diagnostics / error measurement)
 __global__ void __launch_bounds__(kThreads, 1) k_mlp_infer_tc(const unsigned char* __restrict__ packed, int D, int A, int NH, int dueling,
@@ -142,21 +151,20 @@ __global__ void __launch_bounds__(kThreads, 1) k_mlp_infer_tc(const unsigned cha
   extern __shared__ __align__(128) unsigned char tsm[];
   __nv_bfloat16* sWts = reinterpret_cast<__nv_bfloat16*>(tsm);                 // packed W0 | W2 | Wh
   float* sBias = reinterpret_cast<float*>(tsm + kTcBf16Elems * 2);             // b0 | b2 | bh
-  __nv_bfloat16* sX = reinterpret_cast<__nv_bfloat16*>(tsm + kTcBlobBytes);     // [128][16]
-  __nv_bfloat16* sH1 = sX + kTcRows * kTcK1;                                    // [128][256]
-  __nv_bfloat16* sH2 = sH1 + kTcRows * kH1;                                     // [128][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sH2 + kTcRows * kH2);            // [0] weights, [1..3] MMA stages
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  __nv_bfloat16* sXall = reinterpret_cast<__nv_bfloat16*>(tsm + kTcBlobBytes);  // [2][128][16]
+  __nv_bfloat16* sHall = sXall + 2 * kTcRows * kTcK1;                           // [2][128][256]  (H1, then H2)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sHall + 2 * kTcRows * kH1);      // [0] weights, [1+3g ..] MMA stages of group g
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long n_tiles = (n + kTcRows - 1) / kTcRows;
   if (blockIdx.x >= n_tiles) return;
 
   if (tid == 0) {
-    for (int b = 0; b < 4; ++b) mbar_init(bars + b, 1);
+    for (int b = 0; b < 7; ++b) mbar_init(bars + b, 1);
     fence_mbar_init();
   }
-  if (warp == 0) {   // tensor-memory allocation: 512 columns (D1 256 | D2 128 | D3 16), one warp, then release the permit
+  if (warp == 0) {   // tensor-memory allocation: all 512 columns, one warp, then release the permit
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -164,72 +172,77 @@ __global__ void __launch_bounds__(kThreads, 1) k_mlp_infer_tc(const unsigned cha
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t tD1 = tmem, tD2 = tmem + 256, tD3 = tmem + 384;
   if (tid == 0) {    // weights + biases: one TMA bulk copy
     mbar_expect_tx(bars + 0, kTcBlobBytes);
     bulk_g2s(tsm, packed, kTcBlobBytes, bars + 0);
   }
   mbar_wait(bars + 0, 0);
 
-  const uint32_t id1 = tc_idesc_bf16(kTcRows, kH1), id2 = tc_idesc_bf16(kTcRows, kH2), id3 = tc_idesc_bf16(kTcRows, kTcNH);
-  const int q = warp & 3, half = warp >> 2;       // TMEM lane quarter of this warp, column half it handles
+  const int g = warp >> 2, q = warp & 3, gtid = tid & 127;
   const int row = 32 * q + lane;                  // tile row = TMEM lane
+  __nv_bfloat16* sX = sXall + g * kTcRows * kTcK1;
+  __nv_bfloat16* sH = sHall + g * kTcRows * kH1;
+  uint64_t* gb = bars + 1 + 3 * g;
+  const uint32_t tD1 = tmem + 256 * g, tD2 = tD1, tD3 = tD1 + 128;
+  const uint32_t id1 = tc_idesc_bf16(kTcRows, kH1), id2 = tc_idesc_bf16(kTcRows, kH2), id3 = tc_idesc_bf16(kTcRows, kTcNH);
   uint32_t phase = 0;
-  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    // ---- X tile: fp32 obs -> bf16 canonical [128][16]; thread = (row, 8-column core)
+  for (long long tile = blockIdx.x + static_cast<long long>(g) * gridDim.x; tile < n_tiles; tile += 2ll * gridDim.x) {
+    // ---- X tile: fp32 obs -> bf16 canonical [128][16]; thread = row
     {
-      const int r = tid >> 1, c = tid & 1;
-      const long long i = tile * kTcRows + r;
-      float f[8];
+      const long long i = tile * kTcRows + gtid;
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const int d = 8 * c + e;
-        f[e] = (i < n && d < D) ? __ldg(obs + i * D + d) : 0.f;
+      for (int c = 0; c < 2; ++c) {
+        float f[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int d = 8 * c + e;
+          f[e] = (i < n && d < D) ? __ldg(obs + i * D + d) : 0.f;
+        }
+        uint4 v;
+        v.x = pack_bf16x2(f[0], f[1]); v.y = pack_bf16x2(f[2], f[3]); v.z = pack_bf16x2(f[4], f[5]); v.w = pack_bf16x2(f[6], f[7]);
+        *reinterpret_cast<uint4*>(sX + tc_off(gtid, 8 * c, kTcK1)) = v;
       }
-      uint4 v;
-      v.x = pack_bf16x2(f[0], f[1]); v.y = pack_bf16x2(f[2], f[3]); v.z = pack_bf16x2(f[4], f[5]); v.w = pack_bf16x2(f[6], f[7]);
-      *reinterpret_cast<uint4*>(sX + tc_off(r, 8 * c, kTcK1)) = v;
     }
     fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core's async proxy
     tc_fence_before();
-    __syncthreads();
+    tc_group_sync(g);
     // ---- layer 1: D1[128x256] = X . W0^T  (one UMMA, K = 16)
-    if (tid == 0) {
+    if (gtid == 0) {
       tc_fence_after();
       tc_mma_bf16(tD1, tc_smem_desc(sX, 128, (kTcK1 / 8) * 128), tc_smem_desc(sWts + kTcOffW0, 128, (kTcK1 / 8) * 128), id1, 0u);
-      tc_commit(bars + 1);
+      tc_commit(gb + 0);
     }
-    mbar_wait(bars + 1, phase);
+    mbar_wait(gb + 0, phase);
     tc_fence_after();
-    tc_hidden_epilogue(tD1, 32 * q, row, 128 * half, 4, sBias, sH1, kH1);
+    tc_hidden_epilogue(tD1, 32 * q, row, 8, sBias, sH, kH1);
     fence_proxy_async();
     tc_fence_before();
-    __syncthreads();
+    tc_group_sync(g);
     // ---- layer 2: D2[128x128] = H1 . W2^T  (K = 256: 16 UMMAs, descriptors advance by 2 cores = 256 B)
-    if (tid == 0) {
+    if (gtid == 0) {
       tc_fence_after();
-      const uint64_t a0 = tc_smem_desc(sH1, 128, (kH1 / 8) * 128), b0 = tc_smem_desc(sWts + kTcOffW2, 128, (kH1 / 8) * 128);
+      const uint64_t a0 = tc_smem_desc(sH, 128, (kH1 / 8) * 128), b0 = tc_smem_desc(sWts + kTcOffW2, 128, (kH1 / 8) * 128);
 #pragma unroll
       for (int k = 0; k < kH1 / 16; ++k) tc_mma_bf16(tD2, a0 + static_cast<uint64_t>(k * 16), b0 + static_cast<uint64_t>(k * 16), id2, k > 0 ? 1u : 0u);
-      tc_commit(bars + 2);
+      tc_commit(gb + 1);
     }
-    mbar_wait(bars + 2, phase);
+    mbar_wait(gb + 1, phase);
     tc_fence_after();
-    tc_hidden_epilogue(tD2, 32 * q, row, 64 * half, 2, sBias + kH1, sH2, kH2);
+    tc_hidden_epilogue(tD2, 32 * q, row, 4, sBias + kH1, sH, kH2);     // H2 overwrites H1 (layer 2 has consumed it)
     fence_proxy_async();
     tc_fence_before();
-    __syncthreads();
+    tc_group_sync(g);
     // ---- heads: D3[128x16] = H2 . Wh^T  (K = 128: 8 UMMAs)
-    if (tid == 0) {
+    if (gtid == 0) {
       tc_fence_after();
-      const uint64_t a0 = tc_smem_desc(sH2, 128, (kH2 / 8) * 128), b0 = tc_smem_desc(sWts + kTcOffWh, 128, (kH2 / 8) * 128);
+      const uint64_t a0 = tc_smem_desc(sH, 128, (kH2 / 8) * 128), b0 = tc_smem_desc(sWts + kTcOffWh, 128, (kH2 / 8) * 128);
 #pragma unroll
       for (int k = 0; k < kH2 / 16; ++k) tc_mma_bf16(tD3, a0 + static_cast<uint64_t>(k * 16), b0 + static_cast<uint64_t>(k * 16), id3, k > 0 ? 1u : 0u);
-      tc_commit(bars + 3);
+      tc_commit(gb + 2);
     }
-    mbar_wait(bars + 3, phase);
+    mbar_wait(gb + 2, phase);
     tc_fence_after();
-    if (half == 0) {
+    {
       uint32_t v[16];
       tc_ld16(tD3 + (static_cast<uint32_t>(32 * q) << 16), v);
       const long long i = tile * kTcRows + row;
@@ -255,12 +268,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_mlp_infer_tc(const unsigned cha
       }
     }
     tc_fence_before();
-    __syncthreads();      // TMEM accumulators and operand buffers are free for the next tile
+    tc_group_sync(g);     // this group's TMEM slot and operand buffers are free for its next tile
     phase ^= 1u;
   }
+  tc_fence_before();
+  __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
 }
 
-constexpr int kTcSmemBytes = kTcBlobBytes + (kTcRows * kTcK1 + kTcRows * kH1 + kTcRows * kH2) * 2 + 4 * 8 + 16;
+constexpr int kTcSmemBytes = kTcBlobBytes + 2 * (kTcRows * kTcK1 + kTcRows * kH1) * 2 + 8 * 8 + 16;
 
 }  // namespace rmc
