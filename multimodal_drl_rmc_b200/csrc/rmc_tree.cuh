@@ -643,22 +643,29 @@ __global__ void __launch_bounds__(kThreads) k_per_sample(ReplayDev R, long long 
                                                          double beta, const double* u, unsigned long long seed,
                                                          unsigned long long counter, unsigned agent, long long* out_nodes,
                                                          float* out_w, float* out_rows) {
+  __shared__ double s_max_w;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long i = blockIdx.x * static_cast<long long>(kWarps) + warp;
-  if (i >= B) return;
   const long long n_nodes = 2 * R.cap - 1;
   const double total = __ldcg(R.tree);
   const long long size = R.st->size;
-  const double ui = (u != nullptr) ? u[i] : philox_uniform(seed, counter, agent, static_cast<uint32_t>(shard_off + i));
-  const double v = stratum_value(total, Bglobal, shard_off + i, ui);
-  double p;
-  const long long leaf = per_descend_warp(R.tree, n_nodes, v, &p);
-  if (lane == 0) {
-    out_nodes[i] = leaf;
-    if (out_w != nullptr)
-      out_w[i] = static_cast<float>(is_weight(static_cast<double>(size), p, total, static_cast<double>(R.st->min_p), beta));
+  // the max IS weight is common to the batch: once per CTA (last thread), concurrently with the descents
+  if (out_w != nullptr && threadIdx.x == kThreads - 1)
+    s_max_w = is_weight_max(static_cast<double>(size), total, static_cast<double>(R.st->min_p), beta);
+  long long leaf = 0;
+  double p = 0.0, numer = 1.0;
+  if (i < B) {
+    const double ui = (u != nullptr) ? u[i] : philox_uniform(seed, counter, agent, static_cast<uint32_t>(shard_off + i));
+    const double v = stratum_value(total, Bglobal, shard_off + i, ui);
+    leaf = per_descend_warp(R.tree, n_nodes, v, &p);
+    if (out_rows != nullptr) gather_row_warp(R, leaf - (R.cap - 1), out_rows + i * R.row_floats);
+    if (out_w != nullptr && lane == 0) numer = pow(static_cast<double>(size) * (p / total), -beta);
   }
-  if (out_rows != nullptr) gather_row_warp(R, leaf - (R.cap - 1), out_rows + i * R.row_floats);
+  __syncthreads();
+  if (i < B && lane == 0) {
+    out_nodes[i] = leaf;
+    if (out_w != nullptr) out_w[i] = static_cast<float>(numer / s_max_w);
+  }
 }
 
 // SumTree.get_leaf for explicit prefix values
