@@ -267,6 +267,28 @@ class Agent:
             self.summary_writer.add_scalar('AvgEpLen', len_mean, global_step=(self.step * self.n_env))
             self.summary_writer.add_scalar('Episodes', self.episode_count, global_step=(self.step * self.n_env))
 
+    # ------------------------------------------------------------------ exact-resume side-car ---
+    def save_learner_state(self, path):
+        """Side-car next to the (unchanged) ``.pack`` checkpoint: target net, Adam moments and step, learner
+        counters, and -- for small replays or on request -- nothing of the replay (the reference refills it).
+        The reference's resume drops all of this (dqn/agent.py:112-121); with it a resumed run continues
+        bit-identically."""
+        lh = self._lh
+        np.savez(path, online=lh.get_params(_lib.ONLINE).cpu().numpy(), target=lh.get_params(_lib.TARGET).cpu().numpy(),
+                 adam_m=lh.get_params(_lib.ADAM_M).cpu().numpy(), adam_v=lh.get_params(_lib.ADAM_V).cpu().numpy(),
+                 adam_t=self._adam_t, learn_calls=self._learn_calls, step=self.step, seed=self.sampling_seed)
+
+    def load_learner_state(self, path):
+        z = np.load(path)
+        lh = self._lh
+        for kind, key in ((_lib.ONLINE, "online"), (_lib.TARGET, "target"), (_lib.ADAM_M, "adam_m"), (_lib.ADAM_V, "adam_v")):
+            lh.set_params(kind, T.as_tensor(z[key]))
+        lh.version[_lib.ONLINE] += 1
+        lh.version[_lib.TARGET] += 1
+        self.online_network._module_dirty = self.target_network._module_dirty = False
+        self._adam_t, self._learn_calls, self.step = int(z["adam_t"]), int(z["learn_calls"]), int(z["step"])
+        self.sampling_seed = int(z["seed"])
+
     def info_mean(self, i):
         i_mean = np.mean([e[i] for e in self.ep_info_buffer]) if len(self.ep_info_buffer) else float('nan')
         return i_mean if not math.isnan(i_mean) else 0.

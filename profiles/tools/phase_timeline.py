@@ -12,7 +12,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspa
 import bench  # noqa: E402
 from multimodal_drl_rmc_b200 import _lib  # noqa: E402
 
-wl = bench.WORKLOADS[sys.argv[1] if len(sys.argv) > 1 else "per256"]
+wl = dict(bench.WORKLOADS[sys.argv[1] if len(sys.argv) > 1 else "per256"])
+if len(sys.argv) > 2:
+    wl["B"] = int(sys.argv[2])
 agent, _ = bench.build_gpu_agent(wl, 0, 0)
 lib = _lib.lib()
 for _ in range(20):
