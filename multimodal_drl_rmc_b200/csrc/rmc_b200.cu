@@ -357,7 +357,7 @@ extern "C" int32_t rmc_per_sample(rmc_replay_t* r, int64_t batch, double beta, c
   if (int32_t e = use_device(r->device)) return e;
   k_per_sample<<<blocks_for(batch, kWarps), kThreads, 0, as_stream(s)>>>(r->dev, batch, batch, 0, beta, u_dev, seed, counter, 0u,
                                                                         reinterpret_cast<long long*>(out_nodes_dev), out_is_w_dev,
-                                                                        out_rows_dev);
+                                                                        out_rows_dev, nullptr);
   RMC_KERNEL_OK();
   return RMC_OK;
 }
@@ -376,7 +376,7 @@ extern "C" int32_t rmc_uniform_sample(rmc_replay_t* r, int64_t batch, const int6
   if (!r || batch < 1 || !out_slots_dev) return fail(RMC_ERR_ARG, "rmc_uniform_sample: bad args");
   if (r->size < batch) return fail(RMC_ERR_STATE, "rmc_uniform_sample: sample larger than population");
   if (int32_t e = use_device(r->device)) return e;
-  k_uniform_sample<<<blocks_for(batch, kWarps), kThreads, 0, as_stream(s)>>>(r->dev, batch, reinterpret_cast<const long long*>(idx_dev),
+  k_uniform_sample<<<blocks_for(batch, kWarps), kThreads, 0, as_stream(s)>>>(r->dev, batch, 0, reinterpret_cast<const long long*>(idx_dev),
                                                                             seed, counter, 0u,
                                                                             reinterpret_cast<long long*>(out_slots_dev), out_rows_dev);
   RMC_KERNEL_OK();
@@ -691,6 +691,17 @@ extern "C" int32_t rmc_learner_step(rmc_learner_t* l, rmc_replay_t* r, const rmc
   S.n_row_ctas = static_cast<int>(std::min<long long>(G, n_tiles));
   const bool rows = (a->phases & (RMC_PH_SAMPLE | RMC_PH_FORWARD)) != 0;
   const bool phase_b = (a->phases & (RMC_PH_PRIORITY | RMC_PH_BACKWARD | RMC_PH_ADAM | RMC_PH_POLYAK | RMC_PH_HARDSYNC)) != 0;
+  // Batches with several row tiles per CTA: draw the minibatch with the full-occupancy grid-wide samplers first
+  // (the fused kernel runs 8 warps per SM, far too few to hide the prefix search's dependent round trips).
+  if ((a->phases & RMC_PH_SAMPLE) && n_tiles > G) {
+    if (r->prioritized)
+      k_per_sample<<<blocks_for(a->batch, kWarps), kThreads, 0, st>>>(r->dev, a->batch, S.Bglobal, S.shard_off, S.beta, S.u, S.seed, S.counter, 0u,
+                                                                     l->ctx.nodes, l->ctx.is_w, l->ctx.X, l->ctx.leaf_p);
+    else
+      k_uniform_sample<<<blocks_for(a->batch, kWarps), kThreads, 0, st>>>(r->dev, a->batch, S.shard_off, S.idx, S.seed, S.counter, 0u, l->ctx.nodes, l->ctx.X);
+    RMC_KERNEL_OK();
+    S.phases &= ~RMC_PH_SAMPLE;
+  }
   if (rows && phase_b) S.barrier_target = l->barrier_count + static_cast<unsigned>(G);
   l->epoch = (l->epoch == 0xffffffffu) ? 1u : l->epoch + 1u;
   S.epoch = l->epoch;

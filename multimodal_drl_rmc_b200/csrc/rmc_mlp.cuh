@@ -66,7 +66,7 @@ __host__ __device__ inline SmemPlan make_smem_plan(int param_floats) {
 // phase-B staging (reuses the same dynamic shared memory)
 constexpr int kGChunk = 256;                         // batch rows staged per chunk
 // phase-B unit shapes: 16x16 (W2), 16x32 (W0: D<=16 rows x 32 hidden units), 32x16 (heads: 32 h2 columns x NH)
-constexpr int kGemmSmemFloats = kGChunk * (32 + 32) + kWarps * 32 * 32 + kWarps * 32;
+constexpr int kGemmSmemFloats = 2 * kGChunk * (32 + 32) + kWarps * 32 * 32 + kWarps * 32;
 
 // ------------------------------------------------------------------ forward of R rows (R = 4 or 8)
 // sXT[d][kR], rows [0,R) are computed.  Results: sH1T[k][r], sH2[r][j], sQ[r][a] (Q values, or raw
@@ -255,9 +255,8 @@ template <int TMO, int TNO>
 __device__ void wgrad_unit(const AgentCtx& C, const StepScalars& S, const GemmUnit& U, float* smem) {
   constexpr int LM = TMO / 8, LN = TNO / 4;       // lane tile (8 x 4 lanes cover the unit)
   constexpr int NOUT = TMO * TNO / kThreads;      // outputs per thread (1 or 2)
-  float* As = smem;                               // [kGChunk][TMO]
-  float* Bs = smem + kGChunk * TMO;               // [kGChunk][TNO]
-  float* Ps = Bs + kGChunk * TNO;                 // [kWarps][TMO*TNO]
+  float* stage = smem;                            // 2 x { A [kGChunk][TMO], B [kGChunk][TNO] }
+  float* Ps = smem + 2 * kGChunk * (TMO + TNO);   // [kWarps][TMO*TNO]
   float* Pb = Ps + kWarps * TMO * TNO;            // [kWarps][TNO]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int mg = lane >> 2, ng = lane & 3;
@@ -282,23 +281,37 @@ __device__ void wgrad_unit(const AgentCtx& C, const StepScalars& S, const GemmUn
 #pragma unroll
   for (int j = 0; j < LN; ++j) bsum[j] = 0.f;
 
-  // 16-byte chunks per staged row; columns past the valid ones are zeroed once and never written
+  // 16-byte chunks per staged row; columns past the valid ones are zeroed once and never written.
+  // Two staging buffers: the cp.async copies of chunk c+1 are in flight while chunk c is multiplied.
   const int ca = min(TMO / 4, (U.m_valid + 3) >> 2), cb = min(TNO / 4, (U.n_valid + 3) >> 2), cab = ca + cb;
+  constexpr int kBuf = kGChunk * (TMO + TNO);
   __syncthreads();
   if (cab < (TMO + TNO) / 4) {
-    for (int t = tid; t < kGChunk * (TMO + TNO); t += kThreads) As[t] = 0.f;
+    for (int t = tid; t < 2 * kBuf; t += kThreads) stage[t] = 0.f;
     __syncthreads();
   }
-  for (long long b0 = 0; b0 < S.B; b0 += kGChunk) {
+  auto issue = [&](long long b0, float* buf) {
     const int rows = static_cast<int>(min(static_cast<long long>(kGChunk), S.B - b0));
-    if (b0 > 0) __syncthreads();
+    float* As = buf;
+    float* Bs = buf + kGChunk * TMO;
     for (int t = tid; t < rows * cab; t += kThreads) {      // LDGSTS: all copies of the chunk in flight at once
       const int r = t / cab, c = t - r * cab;
       if (c < ca) cp_async16(As + r * TMO + 4 * c, U.A + (b0 + r) * U.lda + U.m0 + 4 * c);
       else cp_async16(Bs + r * TNO + 4 * (c - ca), U.Bm + (b0 + r) * U.ldb + U.n0 + 4 * (c - ca));
     }
-    cp_async_wait_all();
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  issue(0, stage);
+  int cur = 0;
+  for (long long b0 = 0; b0 < S.B; b0 += kGChunk, cur ^= 1) {
+    const int rows = static_cast<int>(min(static_cast<long long>(kGChunk), S.B - b0));
+    const bool more = b0 + kGChunk < S.B;
+    if (more) issue(b0 + kGChunk, stage + (cur ^ 1) * kBuf);
+    if (more) asm volatile("cp.async.wait_group 1;" ::: "memory");
+    else asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
+    const float* As = stage + cur * kBuf;
+    const float* Bs = As + kGChunk * TMO;
     // warp w takes rows w, w+8, ... (fixed order -> deterministic sums)
 #pragma unroll 4
     for (int r = warp; r < rows; r += kWarps) {
@@ -314,6 +327,7 @@ __device__ void wgrad_unit(const AgentCtx& C, const StepScalars& S, const GemmUn
 #pragma unroll
       for (int j = 0; j < LN; ++j) bsum[j] += b[j];
     }
+    __syncthreads();     // buffer `cur` may be refilled by the next iteration's prefetch
   }
   // cross-warp reduction in fixed order
 #pragma unroll

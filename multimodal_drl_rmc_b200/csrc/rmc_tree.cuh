@@ -642,7 +642,7 @@ __device__ __forceinline__ void gather_row_warp(const ReplayDev& R, long long sl
 __global__ void __launch_bounds__(kThreads) k_per_sample(ReplayDev R, long long B, long long Bglobal, long long shard_off,
                                                          double beta, const double* u, unsigned long long seed,
                                                          unsigned long long counter, unsigned agent, long long* out_nodes,
-                                                         float* out_w, float* out_rows) {
+                                                         float* out_w, float* out_rows, double* out_leaf_p) {
   __shared__ double s_max_w;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long i = blockIdx.x * static_cast<long long>(kWarps) + warp;
@@ -665,6 +665,7 @@ __global__ void __launch_bounds__(kThreads) k_per_sample(ReplayDev R, long long 
   if (i < B && lane == 0) {
     out_nodes[i] = leaf;
     if (out_w != nullptr) out_w[i] = static_cast<float>(numer / s_max_w);
+    if (out_leaf_p != nullptr) out_leaf_p[i] = p;
   }
 }
 
@@ -686,14 +687,14 @@ __device__ __forceinline__ long long deque_pos_to_slot(long long pos, long long 
   return (size == cap) ? (dp + pos) % cap : pos;
 }
 
-__global__ void __launch_bounds__(kThreads) k_uniform_sample(ReplayDev R, long long B, const long long* idx,
+__global__ void __launch_bounds__(kThreads) k_uniform_sample(ReplayDev R, long long B, long long shard_off, const long long* idx,
                                                              unsigned long long seed, unsigned long long counter,
                                                              unsigned agent, long long* out_slots, float* out_rows) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long i = blockIdx.x * static_cast<long long>(kWarps) + warp;
   if (i >= B) return;
   const long long size = R.st->size, dp = R.st->dp;
-  const long long pos = (idx != nullptr) ? idx[i] : static_cast<long long>(feistel_perm(i, size, seed, counter, agent));
+  const long long pos = (idx != nullptr) ? idx[i] : static_cast<long long>(feistel_perm(shard_off + i, size, seed, counter, agent));
   const long long slot = deque_pos_to_slot(pos, size, dp, R.cap);
   if (lane == 0) out_slots[i] = slot;
   if (out_rows != nullptr) gather_row_warp(R, slot, out_rows + i * R.row_floats);
