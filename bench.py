@@ -49,6 +49,8 @@ METRIC = "learner transitions/sec (sample+TD+fwd/bwd+Adam) at 1/2/4/8 B200 vs ho
 WORKLOADS = {
     "large65536": dict(algo="PerDuelingDoubleDQNAgent", B=65536, cap=CAP, size=CAP, sharded=True,
                        name="large-batch learner (batch 65,536) minibatch-sharded across GPUs with NCCL gradient allreduce (BASELINE configs[4])"),
+    "ensemble8_per256": dict(algo="PerDuelingDoubleDQNAgent", B=256, cap=200_000, size=200_000, ensemble=8,
+                             name="ensemble of independent PER+double+dueling agents, 8 per GPU, one launch per step for all 8, no communication (BASELINE configs[3])"),
     "per256": dict(algo="PerDuelingDoubleDQNAgent", B=256, cap=CAP, size=CAP,
                    name="PER+double+dueling DQN learner, batch 256, 1M-transition GPU-resident replay (BASELINE configs[1])"),
     "default32": dict(algo="DuelingDoubleDQNAgent", B=32, cap=CAP, size=100_000,
@@ -228,6 +230,12 @@ def run_ours(args, wl):
     lib = _lib.lib()
     if sharded:
         return run_sharded(args, wl, agent, rank, world, local)
+    ens = None
+    n_agents = int(wl.get("ensemble", 1))
+    if n_agents > 1:
+        from multimodal_drl_rmc_b200.parallel import AgentEnsemble
+        members = [agent] + [build_gpu_agent(wl, local, seed=1000 * rank + k)[0] for k in range(1, n_agents)]
+        ens = AgentEnsemble(members)
 
     def barrier():
         if world > 1:
@@ -235,6 +243,11 @@ def run_ours(args, wl):
         torch.cuda.synchronize()
 
     def one_step():
+        if ens is not None:
+            for m in ens.agents:
+                m.step += 1
+            ens.learn()
+            return
         agent.step += 1
         agent.learn(fuse_target_update=True)
         agent.update_target_network()        # no-op: already fused into the launch above
@@ -271,21 +284,23 @@ def run_ours(args, wl):
 
     # ---- end to end through the public API with host buffers --------------------------------
     n_new = min(len(obs), 4096)
-    for k in range(W):
-        j = k % n_new
-        agent.store_transitions(obs[j:j + 1], [int(act[j])], [float(rew[j])], [bool(done[j])], nxt[j:j + 1], None)
+    group = ens.agents if ens is not None else [agent]
+
+    def e2e_step(j):
+        for m in group:       # every agent receives its env's new transition from host memory ...
+            m.store_transitions(obs[j:j + 1], [int(act[j])], [float(rew[j])], [bool(done[j])], nxt[j:j + 1], None)
         one_step()
-        agent.last_loss()
+        return [m.last_loss() for m in group][-1]      # ... and every agent's loss is read back
+
+    for k in range(W):
+        e2e_step(k % n_new)
     barrier()
     e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e_start.record()
     wall0 = time.perf_counter()
     loss = 0.0
     for k in range(K):
-        j = (W + k) % n_new
-        agent.store_transitions(obs[j:j + 1], [int(act[j])], [float(rew[j])], [bool(done[j])], nxt[j:j + 1], None)
-        one_step()
-        loss = agent.last_loss()              # D2H read of the step's loss (synchronises)
+        loss = e2e_step((W + k) % n_new)      # host rows in, learner step, loss read-back (waits for the step)
     e_end.record()
     barrier()
     e2e_ms = max(e_start.elapsed_time(e_end), 1e3 * (time.perf_counter() - wall0))
@@ -304,25 +319,26 @@ def run_ours(args, wl):
     if rank == 0:
         peak, peak_src = measured_peaks()
         per = agent._PER
-        bytes_per_launch = (BYTES_PER_TRANSITION_PER if per else BYTES_PER_TRANSITION_UNI) * B
+        bytes_per_launch = (BYTES_PER_TRANSITION_PER if per else BYTES_PER_TRANSITION_UNI) * B * n_agents
         achieved = bytes_per_launch / (kern_ms * 1e-3) / 1e9
-        flops_per_launch = FLOP_PER_TRANSITION * B + 16 * P_COUNT
+        flops_per_launch = (FLOP_PER_TRANSITION * B + 16 * P_COUNT) * n_agents
         cb = None
         if world == 1 and not args.no_cpu:
             threads = os.cpu_count() or 1
             cb = cpu_baseline(wl, 200, 5, threads)
         line = {
-            "metric": METRIC, "value": world * B * K / (ms_total * 1e-3), "unit": "transitions/s", "n_gpus": world, "steps": K, "warmup": W,
+            "metric": METRIC, "value": world * n_agents * B * K / (ms_total * 1e-3), "unit": "transitions/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": wl["name"], "batch": B, "replay_capacity": wl["cap"], "replay_size": wl["size"], "obs_dim": D,
                        "net": "MLP %d-256-128-(1+8) dueling" % D if agent._DUELING else "MLP %d-256-128-8" % D,
-                       "parallelism": "1 independent agent per GPU (ensemble members), no collective" if world > 1 else "single agent",
+                       "parallelism": ("%d independent agents per GPU, no collective" % n_agents) if n_agents > 1 else
+                                      ("1 independent agent per GPU (ensemble members), no collective" if world > 1 else "single agent"),
                        "l2": "inputs larger than L2: 128 MB ring + 16 MB tree sampled at random each step (126 MB L2); the 0.3 MB of weights "
                              "and the per-step scratch are L2-resident by design",
                        "sampling": "on-device Philox uniforms", "target_sync": "Polyak fused into the step launch"},
-            "e2e": {"value": world * B * K / (e2e_ms * 1e-3), "unit": "transitions/s", "ms_per_step": e2e_ms / K,
-                    "h2d_bytes_per_step": int(agent.replay_memory_buffer._ring.row_floats * 4), "d2h_bytes_per_step": 4,
+            "e2e": {"value": world * n_agents * B * K / (e2e_ms * 1e-3), "unit": "transitions/s", "ms_per_step": e2e_ms / K,
+                    "h2d_bytes_per_step": int(agent.replay_memory_buffer._ring.row_floats * 4) * n_agents, "d2h_bytes_per_step": 4 * n_agents,
                     "what": "store_transitions(1 host row) + learn() + update_target_network() + loss read-back per step", "last_loss": loss},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": "k_learner_step", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -703,7 +703,7 @@ extern "C" int32_t rmc_learner_step(rmc_learner_t* l, rmc_replay_t* r, const rmc
     S.phases &= ~RMC_PH_SAMPLE;
   }
   if (rows && phase_b) S.barrier_target = l->barrier_count + static_cast<unsigned>(G);
-  l->epoch = (l->epoch == 0xffffffffu) ? 1u : l->epoch + 1u;
+  l->epoch = (l->epoch >= 0x7fffffffu) ? 1u : l->epoch + 1u;
   S.epoch = l->epoch;
   AgentCtx single = l->ctx;
   l->last_grid = G;
@@ -913,11 +913,12 @@ extern "C" int32_t rmc_group_step(rmc_group_t* g, const rmc_step_args_t* a, rmc_
   const bool rows = (a->phases & (RMC_PH_SAMPLE | RMC_PH_FORWARD)) != 0;
   const bool phase_b = (a->phases & (RMC_PH_PRIORITY | RMC_PH_BACKWARD | RMC_PH_ADAM | RMC_PH_POLYAK | RMC_PH_HARDSYNC)) != 0;
   if (rows && phase_b) S.barrier_target = g->barrier_count + static_cast<unsigned>(G);
-  g->epoch = (g->epoch == 0xffffffffu) ? 1u : g->epoch + 1u;
-  S.epoch = g->epoch;
+  g->epoch = (g->epoch >= 0x7fffffffu) ? 1u : g->epoch + 1u;
+  S.epoch = 0x80000000u | g->epoch;      // group launches and single-agent launches never share an epoch value
   for (int i = 0; i < g->n; ++i) {
     g->learners[i]->last_batch = a->batch;
     if (a->phases & RMC_PH_ADAM) ++g->learners[i]->online_version;
+    if ((a->phases & RMC_PH_FORWARD) && phase_b) g->learners[i]->loss_epoch = S.epoch;
   }
   AgentCtx single = l0->ctx;
   const AgentCtx* many = g->ctx_dev;
