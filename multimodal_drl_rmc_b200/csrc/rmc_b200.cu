@@ -62,6 +62,7 @@ struct rmc_replay {
   cudaEvent_t ev[kStageSlots] = {nullptr, nullptr, nullptr, nullptr};
   bool ev_used[kStageSlots] = {false, false, false, false};
   int slot = 0;
+  bool l2_window_set = false;
 };
 
 struct rmc_learner {
@@ -678,10 +679,33 @@ static int grid_for(const rmc_learner* l, long long B, int max_ctas) {
   return std::max(1, std::min(want, max_ctas));
 }
 
+// RMC_L2_PERSIST=1 (diagnostic): pin the sum tree in the persisting part of L2 for the launching stream.
+static void maybe_persist_tree(rmc_replay* r, cudaStream_t st) {
+  static int enabled = -1;
+  if (enabled < 0) { const char* e = std::getenv("RMC_L2_PERSIST"); enabled = (e && e[0] == '1') ? 1 : 0; }
+  if (!enabled || !r->prioritized || r->l2_window_set) return;
+  r->l2_window_set = true;
+  int max_persist = 0, max_window = 0;
+  cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, r->device);
+  cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, r->device);
+  const size_t bytes = static_cast<size_t>(r->n_nodes) * sizeof(double);
+  const size_t want = std::min<size_t>(bytes, static_cast<size_t>(std::min(max_persist, max_window)));
+  if (want == 0) return;
+  cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+  cudaStreamAttrValue v{};
+  v.accessPolicyWindow.base_ptr = r->dev.tree;
+  v.accessPolicyWindow.num_bytes = want;
+  v.accessPolicyWindow.hitRatio = 1.0f;
+  v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+  v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+  if (cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &v) != cudaSuccess) cudaGetLastError();
+}
+
 extern "C" int32_t rmc_learner_step(rmc_learner_t* l, rmc_replay_t* r, const rmc_step_args_t* a, rmc_stream_t s) {
   if (int32_t e = check_step(l, r, a)) return e;
   if (int32_t e = use_device(l->device)) return e;
   cudaStream_t st = as_stream(s);
+  maybe_persist_tree(r, st);
   StepScalars S;
   if (int32_t e = fill_scalars(l, a, &S)) return e;
   l->ctx.rp = r->dev;

@@ -452,6 +452,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, c
     const long long n_nodes = 2 * C.rp.cap - 1;
     const int n_top = static_cast<int>(min(static_cast<long long>(kTopNodes), n_nodes));
     if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+    // replay state and tree total: issued now so that their latency overlaps the top-of-tree load below
+    const long long size = __ldcg(&C.rp.st->size), dp = __ldcg(&C.rp.st->dp);
+    const double total = per ? __ldcg(C.rp.tree) : 0.0;
+    const float min_p_f = per ? __ldcg(&C.rp.st->min_p) : 0.f;
     if ((S.phases & 1) && C.rp.prioritized)        // top levels of the tree: one coalesced read, then smem descents
       for (int t = tid; t < n_top; t += kThreads) sTop[t] = __ldcg(C.rp.tree + t);
     __syncthreads();
@@ -462,8 +466,6 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, c
     // -------- pass 1 over this CTA's tiles: sample + gather, then Q_target(s')
     // warps 0..kTM-1: one sample each; warp kTM meanwhile computes the max IS weight (replay_memory.py:76-77),
     // which the samplers pick up at a 5-warp named barrier after their own descent.
-    const long long size = C.rp.st->size, dp = C.rp.st->dp;
-    const double total = per ? __ldcg(C.rp.tree) : 0.0;
     const bool tree_sampling = C.rp.prioritized != 0;
     if (S.phases & 1) {
       bool first_iter = true;
@@ -506,7 +508,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, c
           }
         } else if (warp == kTM && tree_sampling && !is_tgt) {
           if (first_iter && lane == 0)
-            sTop[kTopNodes] = is_weight_max(static_cast<double>(size), total, static_cast<double>(C.rp.st->min_p), S.beta);
+            sTop[kTopNodes] = is_weight_max(static_cast<double>(size), total, static_cast<double>(min_p_f), S.beta);
           __syncwarp();
           asm volatile("bar.sync 1, %0;" ::"n"((kTM + 1) * 32) : "memory");
         }
