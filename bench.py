@@ -68,35 +68,56 @@ def measured_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons DURING the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons DURING the timed region, sampled every 5 ms through NVML (the library behind
+    nvidia-smi; same fields as the recipe's clocks line)."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.samples, self.stop_flag = index, [], threading.Event()
+        self.index, self.samples, self.stop_flag, self.err, self.h = index, [], threading.Event(), None, None
+        try:       # NVML set-up on the caller's thread, before the timed region
+            import pynvml as nv
+            self.nv = nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+            self.h = nv.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
+            self.reasons_fn = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        except Exception as exc:  # pragma: no cover
+            self.err = repr(exc)
 
     def run(self):
-        while not self.stop_flag.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
-            except Exception:
-                pass
-            self.stop_flag.wait(0.1)
+        if self.h is None:
+            return
+        try:
+            while not self.stop_flag.is_set():
+                self.samples.append((float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)), int(self.reasons_fn(self.h))))
+                self.stop_flag.wait(0.002)
+        except Exception as exc:  # pragma: no cover
+            self.err = repr(exc)
 
     def summary(self):
         self.stop_flag.set()
-        self.join(timeout=6)
+        self.join(timeout=5)
         if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for k, n in enumerate(names) if any(len(s) > 2 + k and s[2 + k].lower().startswith("active") for s in self.samples)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.samples[0][1]) if self.samples[0][1].replace(".", "").isdigit() else None,
-                "reasons": reasons, "samples": len(self.samples)}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: %s" % self.err]}
+        sm = sorted(s[0] for s in self.samples)
+        bits = 0
+        for _, r in self.samples:
+            bits |= r
+        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_mhz, "reasons": [n for b, n in names.items() if bits & b],
+                "samples": len(self.samples)}
+
+
+def measured_traffic(kernel):
+    """DRAM bytes per launch from the committed ncu capture (profiles/r1/ncu_traffic.json), or None."""
+    path = os.path.join(ROOT, "profiles", "r1", "ncu_traffic.json")
+    try:
+        with open(path) as fh:
+            return json.load(fh)[kernel]["dram_bytes_per_launch"]
+    except Exception:
+        return None
 
 
 def synthetic(n, seed):
@@ -342,7 +363,8 @@ def run_ours(args, wl):
                     "what": "store_transitions(1 host row) + learn() + update_target_network() + loss read-back per step", "last_loss": loss},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": "k_learner_step", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_launch,
+                         "traffic": measured_traffic("k_learner_step") if n_agents == 1 else None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": bytes_per_launch,
                          "kernel_ms": kern_ms, "fp32_tflops": flops_per_launch / (kern_ms * 1e-3) / 1e12,
                          "note": "latency-bound step (SURVEY 8d): report us/step next to the fraction"},
             "clocks": clocks,
