@@ -267,6 +267,27 @@ class Agent:
             self.summary_writer.add_scalar('AvgEpLen', len_mean, global_step=(self.step * self.n_env))
             self.summary_writer.add_scalar('Episodes', self.episode_count, global_step=(self.step * self.n_env))
 
+    # ------------------------------------------------------------------ learner diagnostics ------
+    def diagnostics(self):
+        """Scalars of the last learn() step, reduced on the device and read back in one go (call it at log
+        frequency, it synchronises): loss, mean / max |td|, mean Q(s,a), mean target, PER beta and tree extremes.
+        The reference logs none of these (dqn/agent.py:130-143)."""
+        lh = self._lh
+        B = self._B
+        td, q, y = lh.output("abs_td")[:B], lh.output("q_sa")[:B], lh.output("y")[:B]
+        vals = T.stack([lh.output("loss")[0], td.mean(), td.max(), q.mean(), y.mean()]).tolist()
+        out = {"loss": vals[0], "abs_td_mean": vals[1], "abs_td_max": vals[2], "q_mean": vals[3], "target_mean": vals[4]}
+        if self._PER:
+            st = self.replay_memory_buffer._ring.stats()
+            out.update(beta=self._beta(self.step * self.n_env), total_priority=st.total_priority,
+                       max_priority=st.max_priority, min_priority=st.min_priority, replay_size=int(st.size))
+        return out
+
+    def log_diagnostics(self):
+        """Write diagnostics() to the agent's SummaryWriter under Learner/* (same global_step as Agent.log)."""
+        for k, v in self.diagnostics().items():
+            self.summary_writer.add_scalar("Learner/" + k, v, global_step=(self.step * self.n_env))
+
     # ------------------------------------------------------------------ exact-resume side-car (SURVEY 8f-3) ---
     def save_learner_state(self, path):
         """Side-car next to the (unchanged) ``.pack`` checkpoint: target net, Adam moments and step, learner

@@ -119,3 +119,19 @@ def test_sidecar_state_gives_bit_identical_resume(tmp_path):
             ag.learn(u=us[s], fuse_target_update=True)
     np.testing.assert_array_equal(PU.flat_sd(a.online_network), PU.flat_sd(b.online_network))
     np.testing.assert_array_equal(PU.flat_sd(a.target_network), PU.flat_sd(b.target_network))
+
+
+def test_diagnostics_match_oracle_trace():
+    orc, a = PU.make_pair("PerDuelingDoubleDQNAgent", 14, 64, 800, 800, seed=15)
+    u = np.random.default_rng(0).random(64)
+    orc.step = a.step = 123
+    tr = {}
+    orc.learn(u=u, trace=tr)
+    a.learn(u=u)
+    d = a.diagnostics()
+    assert abs(d["loss"] - tr["loss"]) <= 1e-5 * abs(tr["loss"])
+    assert abs(d["abs_td_mean"] - float(tr["abs_td"].mean())) <= 1e-5
+    assert abs(d["abs_td_max"] - float(tr["abs_td"].max())) <= 1e-5 * float(tr["abs_td"].max())
+    assert abs(d["q_mean"] - float(tr["q_sa"].mean())) <= 1e-5
+    assert d["replay_size"] == 800 and d["beta"] == float(orc.replay.beta(123))
+    a.log_diagnostics()
