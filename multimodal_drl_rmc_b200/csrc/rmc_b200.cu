@@ -652,7 +652,7 @@ static int launch_mode() {
   static int mode = -1;
   if (mode < 0) {
     const char* e = std::getenv("RMC_LAUNCH");
-    mode = (e && std::strcmp(e, "plain") == 0) ? 1 : (e && std::strcmp(e, "pdl") == 0) ? 2 : 0;
+    mode = (e && std::strcmp(e, "plain") == 0) ? 1 : (e && std::strcmp(e, "pdl") == 0) ? 2 : (e && std::strcmp(e, "pdlcoop") == 0) ? 3 : 0;
   }
   return mode;
 }
@@ -663,10 +663,12 @@ static int32_t launch_step(dim3 grid, void** args, size_t smem, cudaStream_t st)
   } else {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid; cfg.blockDim = dim3(kThreads, 1, 1); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at; cfg.numAttrs = (mode == 2) ? 1 : 0;
+    at[1].id = cudaLaunchAttributeCooperative;
+    at[1].val.cooperative = 1;
+    cfg.attrs = at; cfg.numAttrs = (mode == 2) ? 1 : (mode == 3) ? 2 : 0;
     RMC_CUDA(cudaLaunchKernelExC(&cfg, reinterpret_cast<void*>(k_learner_step), args));
   }
   g_launches.fetch_add(1, std::memory_order_relaxed);

@@ -362,6 +362,27 @@ __device__ void tree_update_team(const ReplayDev& R, const long long* __restrict
   if (lane == 0) { s_i[warp] = a; s_i[8 + warp] = b; s_i[16 + warp] = c; s_i[24 + warp] = d; }
   __threadfence();          // this thread's leaf stores / reductions are performed before the team hand-off
   __syncthreads();
+  // Local part of the top rebuild: levels 8..3 under this member's depth-3 node depend only on its own level-9
+  // nodes (64 of them), which no other member touches -- done here, off the last arriver's tail.
+  if (warp == 0) {
+    const long long d3 = 7 + member;                              // heap index of the member's depth-3 node
+    const long long first9 = ((d3 + 1) << 6) - 1;                 // its 64 descendants at depth 9
+    double v0 = __ldcg(R.tree + first9 + 2 * lane), v1 = __ldcg(R.tree + first9 + 2 * lane + 1);
+    double sum = v0 + v1;                                         // depth 8: 32 nodes, lane l <-> node l
+    long long first = ((d3 + 1) << 5) - 1;
+    R.tree[first + lane] = sum;
+#pragma unroll
+    for (int lvl = 7, width = 16; lvl >= 3; --lvl, width >>= 1) {  // depth 7 (16 nodes) ... depth 3 (1 node)
+      const double other = __shfl_down_sync(0xffffffffu, sum, 1);   // partner = next lane's value at the level below
+      const double pair = sum + other;                            // valid on even lanes of the previous level
+      // compact: node j of this level = lanes 2j,2j+1 of the level below -> gather into lane j
+      sum = __shfl_sync(0xffffffffu, pair, 2 * lane);
+      first = ((d3 + 1) << (lvl - 3)) - 1;
+      if (lane < width) R.tree[first + lane] = sum;
+    }
+    __threadfence();
+  }
+  __syncthreads();
   if (tid == 0) {
     int ta = 0, tb = 0, tc = 0, td = 0;
     for (int w = 0; w < nw; ++w) { ta += s_i[w]; tb += s_i[8 + w]; tc += s_i[16 + w]; td += s_i[24 + w]; }
@@ -401,7 +422,16 @@ __device__ void tree_update_team(const ReplayDev& R, const long long* __restrict
   }
   __syncthreads();
   if (s_i[63]) extremes_rescan_cta(R, size, s_f, s_i);
-  tree_rebuild_top_cta(R, s_top_buf);
+  if (tid == 0) {      // levels 2..0 from the eight depth-3 nodes the members have just rebuilt
+    double v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = __ldcg(R.tree + 7 + k);
+    const double l2[4] = {v[0] + v[1], v[2] + v[3], v[4] + v[5], v[6] + v[7]};
+    const double l1[2] = {l2[0] + l2[1], l2[2] + l2[3]};
+    R.tree[3] = l2[0]; R.tree[4] = l2[1]; R.tree[5] = l2[2]; R.tree[6] = l2[3];
+    R.tree[1] = l1[0]; R.tree[2] = l1[1];
+    R.tree[0] = l1[0] + l1[1];
+  }
   RMC_TSTAMP(12);
 #undef RMC_TSTAMP
 }
