@@ -29,6 +29,12 @@ import time
 
 import numpy as np
 
+# Launch mode of the fused step kernel for the benchmark: programmatic dependent launch (the next step's launch
+# latency overlaps this step's tail; measured 4.9 -> 2.2 us idle gap between steps, profiles/r1/launch_gaps.txt).
+# The library default stays the cooperative launch (driver-guaranteed co-residency for the in-kernel barrier); the
+# plain+PDL launch is equally co-resident whenever one stream of one process drives the GPU, which is the case here.
+os.environ.setdefault("RMC_LAUNCH", "pdl")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
@@ -357,7 +363,8 @@ def run_ours(args, wl):
                                       ("1 independent agent per GPU (ensemble members), no collective" if world > 1 else "single agent"),
                        "l2": "inputs larger than L2: 128 MB ring + 16 MB tree sampled at random each step (126 MB L2); the 0.3 MB of weights "
                              "and the per-step scratch are L2-resident by design",
-                       "sampling": "on-device Philox uniforms", "target_sync": "Polyak fused into the step launch"},
+                       "sampling": "on-device Philox uniforms", "target_sync": "Polyak fused into the step launch",
+                       "launch": os.environ.get("RMC_LAUNCH", "coop")},
             "e2e": {"value": world * n_agents * B * K / (e2e_ms * 1e-3), "unit": "transitions/s", "ms_per_step": e2e_ms / K,
                     "h2d_bytes_per_step": int(agent.replay_memory_buffer._ring.row_floats * 4) * n_agents, "d2h_bytes_per_step": 4 * n_agents,
                     "what": "store_transitions(1 host row) + learn() + update_target_network() + loss read-back per step", "last_loss": loss},

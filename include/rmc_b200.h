@@ -234,6 +234,8 @@ int32_t rmc_learner_act_host_sync(rmc_learner_t* l, const float* obs_host, int64
  * rmc_learner_step: out_host[cta*16 + k], k = 0 start, 1 sampled, 2 target weights landed,
  * 3 target pass done, 4 online weights landed, 5 row phase done, 6 past the barrier, 7 done. */
 int32_t rmc_learner_debug_timing(rmc_learner_t* l, int32_t enable);
+/* [min CTA start, max CTA end] (%globaltimer ns) of the last 64 launches, slot = epoch % 64 (launch-gap diagnostic) */
+int32_t rmc_learner_debug_gaps_sync(rmc_learner_t* l, uint64_t* out128_host, rmc_stream_t s);
 int32_t rmc_learner_debug_read_sync(rmc_learner_t* l, uint64_t* out_host, int32_t max_ctas, int32_t* n_ctas,
                                     rmc_stream_t s);
 

@@ -533,7 +533,7 @@ extern "C" int32_t rmc_learner_create(rmc_learner_t** out, const rmc_net_spec_t*
       c.host_loss = nullptr;
     }
   }
-  if ((e = owned_alloc(l, &l->dbg_buf, 1024 * 16))) return e;
+  if ((e = owned_alloc(l, &l->dbg_buf, 1024 * 16 + 128))) return e;
   RMC_CUDA(cudaDeviceSynchronize());
   *out = l;
   return RMC_OK;
@@ -958,6 +958,18 @@ extern "C" int32_t rmc_group_step(rmc_group_t* g, const rmc_step_args_t* a, rmc_
 extern "C" int32_t rmc_learner_debug_timing(rmc_learner_t* l, int32_t enable) {
   if (!l) return fail(RMC_ERR_ARG, "rmc_learner_debug_timing: null");
   l->ctx.dbg = enable ? l->dbg_buf : nullptr;
+  if (enable) {   // [min start, max end] slots of the launch-gap diagnostic
+    std::vector<unsigned long long> init(128);
+    for (int k = 0; k < 64; ++k) { init[2 * k] = ~0ull; init[2 * k + 1] = 0ull; }
+    RMC_CUDA(cudaMemcpy(l->dbg_buf + 1024 * 16, init.data(), 128 * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+  }
+  return RMC_OK;
+}
+extern "C" int32_t rmc_learner_debug_gaps_sync(rmc_learner_t* l, uint64_t* out128_host, rmc_stream_t s) {
+  if (!l || !out128_host) return fail(RMC_ERR_ARG, "rmc_learner_debug_gaps_sync: null");
+  if (int32_t e = use_device(l->device)) return e;
+  RMC_CUDA(cudaMemcpyAsync(out128_host, l->dbg_buf + 1024 * 16, 128 * sizeof(uint64_t), cudaMemcpyDeviceToHost, as_stream(s)));
+  RMC_CUDA(cudaStreamSynchronize(as_stream(s)));
   return RMC_OK;
 }
 extern "C" int32_t rmc_learner_debug_read_sync(rmc_learner_t* l, uint64_t* out_host, int32_t max_ctas, int32_t* n_ctas, rmc_stream_t s) {

@@ -439,6 +439,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, c
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
   RMC_STAMP(C, 0);
+  // launch-gap diagnostic: per-launch [min start, max end] in dbg[1024*16 + 2*(epoch % 64) ..] (enabled with the stamps)
+  unsigned long long* gap = (C.dbg != nullptr) ? C.dbg + 1024 * 16 + 2 * (S.epoch & 63u) : nullptr;
+  if (gap != nullptr && threadIdx.x == 0) atomicMin(gap, global_timer_ns());
 
   // Role split: when every row CTA owns one tile and enough CTAs are idle in phase A, CTA n_tiles+t computes
   // Q_target(s') of tile t concurrently (it repeats tile t's sampling -- same uniforms, same leaves -- and stages
@@ -718,7 +721,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, c
         tree_update_cta(C.rp, C.nodes, C.pri, B, tsize, tsize, false, (S.phases & 1) ? C.leaf_p : nullptr,
                         reinterpret_cast<double*>(smem), tdbg);
       }
-      RMC_STAMP(C, 7);
+      RMC_STAMP(C, 7); if (gap != nullptr && threadIdx.x == 0) atomicMax(gap + 1, global_timer_ns());
       return;
     }
   }
@@ -750,7 +753,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, c
     tree_update_cta(C.rp, C.nodes, C.pri, B, tsize, tsize, false, (S.phases & 1) ? C.leaf_p : nullptr,
                     reinterpret_cast<double*>(smem), nullptr);
   }
-  RMC_STAMP(C, 7);
+  RMC_STAMP(C, 7); if (gap != nullptr && threadIdx.x == 0) atomicMax(gap + 1, global_timer_ns());
 }
 
 // ------------------------------------------------------------------ batched act / Q values
