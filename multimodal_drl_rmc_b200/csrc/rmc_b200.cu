@@ -834,7 +834,9 @@ static int32_t infer_tc(rmc_learner* l, const float* obs_dev, long long n, long 
   }
   const long long n_tiles = (n + kTcRows - 1) / kTcRows;
   const unsigned grid = static_cast<unsigned>(std::min<long long>(n_tiles, l->num_sms));
-  k_mlp_infer_tc<<<grid, kThreads, kTcSmemBytes, st>>>(l->tc_packed, l->L.D, l->L.A, l->L.NH, l->L.dueling, obs_dev, n, actions, heads, mode);
+  TcFwdExtra ex{};
+  ex.row_stride = l->L.D;
+  k_mlp_infer_tc<<<grid, kThreads, kTcSmemBytes, st>>>(l->tc_packed, l->L.D, l->L.A, l->L.NH, l->L.dueling, obs_dev, n, actions, heads, mode, ex);
   RMC_KERNEL_OK();
   return RMC_OK;
 }

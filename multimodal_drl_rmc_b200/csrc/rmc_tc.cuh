@@ -118,8 +118,10 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 
 // epilogue of one hidden layer: TMEM columns [0, 32*n32) of this warp's 32 lanes -> +bias, ReLU, bf16 ->
 // canonical K-major operand `dst` (K = Kdst) for the next layer.  row = TMEM lane.
+// `gdst` (optional): the same bf16 activations, row-major [rows][Kdst], for the backward kernels.
 __device__ __forceinline__ void tc_hidden_epilogue(uint32_t tmem_acc, int lane_base, int row, int n32,
-                                                   const float* __restrict__ bias, __nv_bfloat16* __restrict__ dst, int Kdst) {
+                                                   const float* __restrict__ bias, __nv_bfloat16* __restrict__ dst, int Kdst,
+                                                   __nv_bfloat16* __restrict__ gdst = nullptr) {
   for (int b = 0; b < n32; ++b) {
     const int col = 32 * b;
     uint32_t v[32];
@@ -132,6 +134,7 @@ __device__ __forceinline__ void tc_hidden_epilogue(uint32_t tmem_acc, int lane_b
       uint4 q;
       q.x = pack_bf16x2(f[0], f[1]); q.y = pack_bf16x2(f[2], f[3]); q.z = pack_bf16x2(f[4], f[5]); q.w = pack_bf16x2(f[6], f[7]);
       *reinterpret_cast<uint4*>(dst + tc_off(row, col + 8 * c, Kdst)) = q;
+      if (gdst != nullptr) *reinterpret_cast<uint4*>(gdst + col + 8 * c) = q;
     }
   }
 }
@@ -145,9 +148,20 @@ __device__ __forceinline__ void tc_group_sync(int g) {   // the 128 threads of o
 // buffer (H2 overwrites H1 once layer 2 has consumed it).
 // mode 0: actions (dueling: argmax of raw advantages = head columns 1..A; plain: argmax of columns 0..A-1)
 // mode 2: raw head outputs [n][NH] float (diagnostics / error measurement)
+// mode 3: all 16 head columns [n][16] float (training: raw heads), plus the optional row-major bf16 copies of the
+//         input tile / hidden activations (Xb [n][16], H1b [n][256], H2b [n][128]) that the backward kernels consume.
+// Input rows are read at obs + i*row_stride + col_off (act: row_stride = D, col_off = 0; training: the gathered rows).
+struct TcFwdExtra {
+  long long row_stride;
+  int col_off;
+  __nv_bfloat16* Xb;
+  __nv_bfloat16* H1b;
+  __nv_bfloat16* H2b;
+};
 __global__ void __launch_bounds__(kThreads, 1) k_mlp_infer_tc(const unsigned char* __restrict__ packed, int D, int A, int NH, int dueling,
                                                               const float* __restrict__ obs, long long n,
-                                                              long long* __restrict__ actions, float* __restrict__ heads_out, int mode) {
+                                                              long long* __restrict__ actions, float* __restrict__ heads_out, int mode,
+                                                              TcFwdExtra X) {
   extern __shared__ __align__(128) unsigned char tsm[];
   __nv_bfloat16* sWts = reinterpret_cast<__nv_bfloat16*>(tsm);                 // packed W0 | W2 | Wh
   float* sBias = reinterpret_cast<float*>(tsm + kTcBf16Elems * 2);             // b0 | b2 | bh
@@ -196,11 +210,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_mlp_infer_tc(const unsigned cha
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           const int d = 8 * c + e;
-          f[e] = (i < n && d < D) ? __ldg(obs + i * D + d) : 0.f;
+          f[e] = (i < n && d < D) ? __ldg(obs + i * X.row_stride + X.col_off + d) : 0.f;
         }
         uint4 v;
         v.x = pack_bf16x2(f[0], f[1]); v.y = pack_bf16x2(f[2], f[3]); v.z = pack_bf16x2(f[4], f[5]); v.w = pack_bf16x2(f[6], f[7]);
         *reinterpret_cast<uint4*>(sX + tc_off(gtid, 8 * c, kTcK1)) = v;
+        if (X.Xb != nullptr && i < n) *reinterpret_cast<uint4*>(X.Xb + i * kTcK1 + 8 * c) = v;
       }
     }
     fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core's async proxy
@@ -214,7 +229,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_mlp_infer_tc(const unsigned cha
     }
     mbar_wait(gb + 0, phase);
     tc_fence_after();
-    tc_hidden_epilogue(tD1, 32 * q, row, 8, sBias, sH, kH1);
+    const long long grow = tile * kTcRows + row;
+    tc_hidden_epilogue(tD1, 32 * q, row, 8, sBias, sH, kH1, (X.H1b != nullptr && grow < n) ? X.H1b + grow * kH1 : nullptr);
     fence_proxy_async();
     tc_fence_before();
     tc_group_sync(g);
@@ -228,7 +244,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_mlp_infer_tc(const unsigned cha
     }
     mbar_wait(gb + 1, phase);
     tc_fence_after();
-    tc_hidden_epilogue(tD2, 32 * q, row, 4, sBias + kH1, sH, kH2);     // H2 overwrites H1 (layer 2 has consumed it)
+    tc_hidden_epilogue(tD2, 32 * q, row, 4, sBias + kH1, sH, kH2,     // H2 overwrites H1 (layer 2 has consumed it)
+                       (X.H2b != nullptr && grow < n) ? X.H2b + grow * kH2 : nullptr);
     fence_proxy_async();
     tc_fence_before();
     tc_group_sync(g);
@@ -260,6 +277,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_mlp_infer_tc(const unsigned cha
             }
           }
           actions[i] = best;
+        } else if (mode == 3) {
+#pragma unroll
+          for (int a = 0; a < kTcNH; a += 4)
+            *reinterpret_cast<float4*>(heads_out + i * kTcNH + a) =
+                make_float4(__uint_as_float(v[a]) + bh[a], __uint_as_float(v[a + 1]) + bh[a + 1],
+                            __uint_as_float(v[a + 2]) + bh[a + 2], __uint_as_float(v[a + 3]) + bh[a + 3]);
         } else {
 #pragma unroll
           for (int a = 0; a < kTcNH; ++a)
