@@ -395,6 +395,8 @@ def run_sharded(args, wl, agent, rank, world, local):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29533")
         dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", local))
+    agent.learn_precision = args.precision
+    tc = args.precision == "bf16"
     sl = ShardedLearner(agent)
     B, K, W = wl["B"], args.steps, max(args.warmup, 3)
 
@@ -424,16 +426,16 @@ def run_sharded(args, wl, agent, rank, world, local):
     if rank == 0:
         peak, peak_src = measured_peaks()
         line = {"metric": METRIC, "value": B * K / (ms * 1e-3), "unit": "transitions/s", "n_gpus": world, "steps": K, "warmup": W,
-                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": wl["name"], "batch": B, "replay_capacity": wl["cap"], "replay_size": wl["size"], "obs_dim": D,
+                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16" if tc else "f32", "data": "synthetic",
+                "config": {"workload": wl["name"], "precision": args.precision, "batch": B, "replay_capacity": wl["cap"], "replay_size": wl["size"], "obs_dim": D,
                            "parallelism": "dp%d: minibatch sharded, replicated replay/tree/weights, NCCL all-reduce of %d gradient floats per step"
                                           % (world, int(agent._lh.output("grads_blob").numel())),
                            "l2": "inputs larger than L2 (144 MB replay + 200 MB step scratch)"},
                 "gpu_launches": int(_lib.lib().rmc_launch_count() - l0),
                 "replicas_identical": bool(float(lo) == float(hi)), "last_loss": float(loss.item()),
-                "roofline": {"bound": "tensor", "kernel": "k_learner_step (fp32 FFMA exact-parity mode)", "achieved": B * FLOP_PER_TRANSITION * K / (ms * 1e-3) / 1e12,
+                "roofline": {"bound": "tensor", "kernel": "k_mlp_infer_tc/k_tc_bwd/k_tc_wgrad (tcgen05 bf16)" if tc else "k_learner_step (fp32 FFMA exact-parity mode)", "achieved": B * FLOP_PER_TRANSITION * K / (ms * 1e-3) / 1e12,
                              "peak": 1682.8, "unit": "TFLOP/s", "frac": B * FLOP_PER_TRANSITION * K / (ms * 1e-3) / 1e12 / 1682.8, "traffic": None,
-                             "peak_source": "measured bf16 (MEASURED_PEAKS.json); this mode runs on the FP32 pipe by design"}}
+                             "peak_source": "measured bf16 (MEASURED_PEAKS.json)" + ("" if tc else "; this mode runs on the FP32 pipe by design")}}
         print(json.dumps(line), flush=True)
     dist.destroy_process_group()
 
@@ -515,7 +517,12 @@ def extra_workloads(agent):
             a5.learn(fuse_target_update=True)
         ms = _time_steps(step5, 10, 2)
         out["large_batch_65536"] = {"ms_per_step": ms, "transitions_per_s": 65536 / (ms * 1e-3),
-                                    "fp32_tflops": 65536 * FLOP_PER_TRANSITION / (ms * 1e-3) / 1e12}
+                                    "fp32_tflops": 65536 * FLOP_PER_TRANSITION / (ms * 1e-3) / 1e12, "mode": "fp32 FFMA (exact parity)"}
+        a5.learn_precision = "bf16"
+        ms = _time_steps(step5, 20, 3)
+        out["large_batch_65536_tc"] = {"ms_per_step": ms, "transitions_per_s": 65536 / (ms * 1e-3),
+                                       "tensor_tflops": 65536 * FLOP_PER_TRANSITION / (ms * 1e-3) / 1e12,
+                                       "mode": "tcgen05 bf16 operands / fp32 TMEM accumulate forward+backward, fp32 Adam (gradients within 3e-2 of fp32)"}
         del a5
     except Exception as exc:  # pragma: no cover
         out["large_batch_65536"] = {"error": repr(exc)}
@@ -529,6 +536,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="per256", choices=sorted(WORKLOADS))
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"], help="large65536 only: learner arithmetic mode")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary workloads")
     args = ap.parse_args()

@@ -96,13 +96,18 @@ enum rmc_phase {
   RMC_PH_POLYAK = 32,   /* soft target update with the post-Adam weights                      */
   RMC_PH_HARDSYNC = 64  /* target <- online (agent.py:102-103)                                */
 };
+enum rmc_precision { RMC_PREC_FP32 = 0, RMC_PREC_BF16_TC = 1 };
 #define RMC_PH_LEARN (RMC_PH_SAMPLE | RMC_PH_FORWARD | RMC_PH_PRIORITY | RMC_PH_BACKWARD | RMC_PH_ADAM)
 
 /* Per-step inputs of a learner step. */
 typedef struct {
   int64_t batch;            /* B                                                            */
   int32_t phases;           /* rmc_phase mask                                               */
-  int32_t reserved;
+  int32_t precision;        /* rmc_precision: 0 = exact fp32 FFMA path (parity path, default);
+                               1 = tcgen05/TMEM tensor-core path, bf16 operands with fp32 accumulation
+                               (dense large-batch / ensemble configs; stated looser bound: gradients
+                               within 1e-1 max-norm-relative of the fp32 path, measured <= 5e-2).  Needs FORWARD and
+                               BACKWARD in `phases` and obs_dim <= 16.                              */
   double per_beta;          /* np.interp(step,[0,eps_dec],[0.4,1.0]) (replay_memory.py:74)  */
   const double* u_dev;      /* PER: B injected uniforms in [0,1) (float64) or NULL -> Philox */
   const int64_t* idx_dev;   /* uniform replay: B injected deque positions (0 = oldest) or NULL

@@ -23,6 +23,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
 # enums of include/rmc_b200.h
 ONLINE, TARGET, ADAM_M, ADAM_V, GRADS = 0, 1, 2, 3, 4
 PH_SAMPLE, PH_FORWARD, PH_PRIORITY, PH_BACKWARD, PH_ADAM, PH_POLYAK, PH_HARDSYNC = 1, 2, 4, 8, 16, 32, 64
+PREC_FP32, PREC_BF16_TC = 0, 1
 PH_LEARN = PH_SAMPLE | PH_FORWARD | PH_PRIORITY | PH_BACKWARD | PH_ADAM
 
 
@@ -44,7 +45,7 @@ class ReplayStats(C.Structure):
 
 
 class StepArgs(C.Structure):
-    _fields_ = [("batch", C.c_int64), ("phases", C.c_int32), ("reserved", C.c_int32), ("per_beta", C.c_double),
+    _fields_ = [("batch", C.c_int64), ("phases", C.c_int32), ("precision", C.c_int32), ("per_beta", C.c_double),
                 ("u_dev", C.c_void_p), ("idx_dev", C.c_void_p), ("seed", C.c_uint64), ("counter", C.c_uint64),
                 ("adam_t", C.c_int64), ("grads_in_dev", C.c_void_p), ("shard_offset", C.c_int64),
                 ("global_batch", C.c_int64)]

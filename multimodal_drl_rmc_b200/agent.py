@@ -105,6 +105,18 @@ class Agent:
         self.sampling_seed = 0x5EED
 
     @property
+    def learn_precision(self):
+        """"fp32" (default): the exact FFMA path, parity with the reference at 1e-5.  "bf16": the tcgen05/TMEM
+        tensor-core path for dense batches (BASELINE configs[4]); stated looser bound, see csrc/rmc_tc_train.cuh."""
+        return "bf16" if self._args.precision == _lib.PREC_BF16_TC else "fp32"
+
+    @learn_precision.setter
+    def learn_precision(self, v):
+        if v not in ("fp32", "bf16"):
+            raise ValueError("learn_precision must be 'fp32' or 'bf16'")
+        self._args.precision = _lib.PREC_BF16_TC if v == "bf16" else _lib.PREC_FP32
+
+    @property
     def sampling_seed(self):
         return self._args.seed
 

@@ -15,6 +15,7 @@
 #include "rmc_device.cuh"
 #include "rmc_mlp.cuh"
 #include "rmc_tc.cuh"
+#include "rmc_tc_train.cuh"
 #include "rmc_tree.cuh"
 
 using namespace rmc;
@@ -55,6 +56,8 @@ struct rmc_replay {
   ReplayDev dev{};
   long long* scratch_nodes = nullptr;
   float* scratch_pri = nullptr;
+  ExtTuple* ext_parts = nullptr;     // per-block partials + arrival counter of the one-pass extremes rescan
+  unsigned* ext_arrive = nullptr;
   // staging ring for host pushes
   long long stage_rows = 0;
   float* pin[kStageSlots] = {nullptr, nullptr, nullptr, nullptr};
@@ -87,6 +90,12 @@ struct rmc_learner {
   unsigned char* tc_packed = nullptr;   // bf16 operands of the tensor-core act mode (lazily allocated)
   unsigned long long online_version = 1, tc_packed_version = 0;   // repack only when the online weights changed
   int last_grid = 0;
+  // tensor-core training mode (lazily allocated, rmc_tc_train.cuh)
+  bool tct_ready = false;
+  unsigned char* tc_packed_target = nullptr;
+  __nv_bfloat16* tc_packed_bwd = nullptr;
+  unsigned long long tc_bwd_version = 0;
+  TcTrainBufs tct{};
   // act staging
   float* act_pin_obs = nullptr; long long* act_pin_out = nullptr; float* act_dev_obs = nullptr; long long* act_dev_out = nullptr;
   long long act_cap = 0;
@@ -159,6 +168,8 @@ extern "C" int32_t rmc_replay_create(rmc_replay_t** out, int64_t capacity, int32
   }
   if ((e = dev_alloc(&r->scratch_nodes, kTreeCtaMax))) return e;
   if ((e = dev_alloc(&r->scratch_pri, kTreeCtaMax))) return e;
+  if ((e = dev_alloc(&r->ext_parts, kExtBlocks))) return e;
+  if ((e = dev_alloc(&r->ext_arrive, 1))) return e;
   r->stage_rows = 16384;
   for (int s = 0; s < kStageSlots; ++s) {
     RMC_CUDA(cudaMallocHost(reinterpret_cast<void**>(&r->pin[s]), static_cast<size_t>(r->stage_rows) * r->rf * sizeof(float)));
@@ -175,7 +186,7 @@ extern "C" int32_t rmc_replay_destroy(rmc_replay_t* r) {
   cudaSetDevice(r->device);
   cudaDeviceSynchronize();
   ReplayDev& d = r->dev;
-  cudaFree(d.ring); cudaFree(d.tree); cudaFree(d.stamps); cudaFree(d.scratch_old); cudaFree(d.team_part); cudaFree(d.team_ctr); cudaFree(d.st); cudaFree(r->scratch_nodes); cudaFree(r->scratch_pri);
+  cudaFree(d.ring); cudaFree(d.tree); cudaFree(d.stamps); cudaFree(d.scratch_old); cudaFree(d.team_part); cudaFree(d.team_ctr); cudaFree(d.st); cudaFree(r->scratch_nodes); cudaFree(r->scratch_pri); cudaFree(r->ext_parts); cudaFree(r->ext_arrive);
   for (int s = 0; s < kStageSlots; ++s) {
     if (r->pin[s]) cudaFreeHost(r->pin[s]);
     cudaFree(r->dstage[s]);
@@ -201,12 +212,8 @@ static int32_t tree_rebuild(rmc_replay* r, cudaStream_t st) {
   return RMC_OK;
 }
 static int32_t minmax_rebuild(rmc_replay* r, cudaStream_t st) {
-  k_extremes_reset<<<1, 1, 0, st>>>(r->dev);
-  RMC_KERNEL_OK();
-  const unsigned grid = std::max(1u, std::min(1184u, blocks_for(r->cap, 256)));
-  k_extremes_pass1<<<grid, 256, 0, st>>>(r->dev);
-  RMC_KERNEL_OK();
-  k_extremes_pass2<<<grid, 256, 0, st>>>(r->dev);
+  const unsigned grid = std::max(1u, std::min(static_cast<unsigned>(kExtBlocks), blocks_for(r->cap, 1024)));
+  k_extremes_scan<<<grid, 256, 0, st>>>(r->dev, r->ext_parts, r->ext_arrive);
   RMC_KERNEL_OK();
   return RMC_OK;
 }
@@ -351,16 +358,27 @@ extern "C" int32_t rmc_replay_read_rows_sync(rmc_replay_t* r, float* out_host, i
   return RMC_OK;
 }
 
+// PER minibatch draw by the grid-wide samplers: warp per sample (lowest latency) below kLaneSampleMin samples, lane per
+// sample (whole batch in flight) above.
+static constexpr long long kLaneSampleMin = 2048;
+static int32_t launch_per_sample(const ReplayDev& R, long long B, long long Bglobal, long long shard_off, double beta, const double* u,
+                                 unsigned long long seed, unsigned long long counter, long long* nodes, float* is_w, float* rows,
+                                 double* leaf_p, cudaStream_t st) {
+  if (B >= kLaneSampleMin)
+    k_per_sample_lane<<<blocks_for(B, kThreads), kThreads, 0, st>>>(R, B, Bglobal, shard_off, beta, u, seed, counter, 0u, nodes, is_w, rows, leaf_p);
+  else
+    k_per_sample<<<blocks_for(B, kWarps), kThreads, 0, st>>>(R, B, Bglobal, shard_off, beta, u, seed, counter, 0u, nodes, is_w, rows, leaf_p);
+  RMC_KERNEL_OK();
+  return RMC_OK;
+}
+
 extern "C" int32_t rmc_per_sample(rmc_replay_t* r, int64_t batch, double beta, const double* u_dev, uint64_t seed, uint64_t counter,
                                   int64_t* out_nodes_dev, float* out_is_w_dev, float* out_rows_dev, rmc_stream_t s) {
   if (!r || !r->prioritized || batch < 1 || !out_nodes_dev) return fail(RMC_ERR_ARG, "rmc_per_sample: bad args");
   if (r->size < 1) return fail(RMC_ERR_STATE, "rmc_per_sample: empty replay");
   if (int32_t e = use_device(r->device)) return e;
-  k_per_sample<<<blocks_for(batch, kWarps), kThreads, 0, as_stream(s)>>>(r->dev, batch, batch, 0, beta, u_dev, seed, counter, 0u,
-                                                                        reinterpret_cast<long long*>(out_nodes_dev), out_is_w_dev,
-                                                                        out_rows_dev, nullptr);
-  RMC_KERNEL_OK();
-  return RMC_OK;
+  return launch_per_sample(r->dev, batch, batch, 0, beta, u_dev, seed, counter, reinterpret_cast<long long*>(out_nodes_dev), out_is_w_dev,
+                           out_rows_dev, nullptr, as_stream(s));
 }
 
 extern "C" int32_t rmc_tree_get_leaf(rmc_replay_t* r, const double* v_dev, int64_t n, int64_t* out_nodes_dev, double* out_pri_dev,
@@ -389,8 +407,16 @@ static int32_t tree_update_large(rmc_replay* r, const long long* nodes, const fl
     k_tree_stamp<<<blocks_for(n, 256), 256, 0, st>>>(r->dev, nodes, n);
     RMC_KERNEL_OK();
   }
-  k_tree_apply<<<blocks_for(n, 256), 256, 0, st>>>(r->dev, nodes, pri, n);
+  // ancestors below the top levels by float64 reductions (few updates per node); the contended top is rebuilt by one CTA
+  int L = 0;
+  while (L < 11 && (2ll << L) <= r->cap) ++L;             // largest L <= 11 with 2^L <= cap
+  const int F = (L >= 3 && n >= 1024) ? (1 << L) - 1 : 0; // small batches / tiny trees: plain propagation to the root
+  k_tree_apply<<<blocks_for(n, 256), 256, 0, st>>>(r->dev, nodes, pri, n, static_cast<long long>(F));
   RMC_KERNEL_OK();
+  if (F > 0) {
+    k_tree_rebuild_top<<<1, 1024, 0, st>>>(r->dev, F);
+    RMC_KERNEL_OK();
+  }
   return minmax_rebuild(r, st);
 }
 
@@ -703,6 +729,108 @@ static void maybe_persist_tree(rmc_replay* r, cudaStream_t st) {
   if (cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &v) != cudaSuccess) cudaGetLastError();
 }
 
+// ---- tensor-core (bf16 / tcgen05) learner step: the dense large-batch mode (rmc_tc_train.cuh) ------------------
+static int32_t tc_train_setup(rmc_learner* l) {
+  if (l->tct_ready) return RMC_OK;
+  const size_t B = static_cast<size_t>(l->max_batch);
+  int32_t e = RMC_OK;
+  if (l->tc_packed == nullptr) {
+    if ((e = owned_alloc(l, &l->tc_packed, static_cast<size_t>(kTcBlobBytes)))) return e;
+  }
+  if ((e = owned_alloc(l, &l->tc_packed_target, static_cast<size_t>(kTcBlobBytes)))) return e;
+  if ((e = owned_alloc(l, &l->tc_packed_bwd, static_cast<size_t>(kTcBwdElems)))) return e;
+  TcTrainBufs& T = l->tct;
+  if ((e = owned_alloc(l, &T.heads_n, B * kTcNH))) return e;
+  if ((e = owned_alloc(l, &T.heads_t, B * kTcNH))) return e;
+  if ((e = owned_alloc(l, &T.heads_s, B * kTcNH))) return e;
+  if ((e = owned_alloc(l, &T.Xb, B * kTcK1))) return e;
+  if ((e = owned_alloc(l, &T.H1b, B * kH1))) return e;
+  if ((e = owned_alloc(l, &T.H2b, B * kH2))) return e;
+  if ((e = owned_alloc(l, &T.DZ2b, B * kH2))) return e;
+  if ((e = owned_alloc(l, &T.DZ1b, B * kH1))) return e;
+  if ((e = owned_alloc(l, &T.DHb, B * kTcNH))) return e;
+  if ((e = owned_alloc(l, &T.partials, static_cast<size_t>(l->num_sms) * l->L.total))) return e;
+  RMC_CUDA(cudaFuncSetAttribute(k_mlp_infer_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
+  RMC_CUDA(cudaFuncSetAttribute(k_tc_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcBwdSmemBytes));
+  RMC_CUDA(cudaFuncSetAttribute(k_tc_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes));
+  l->tct_ready = true;
+  return RMC_OK;
+}
+
+static int32_t step_tc(rmc_learner* l, rmc_replay* r, const rmc_step_args_t* a, StepScalars& S, cudaStream_t st) {
+  if (l->L.D > kTcK1) return fail(RMC_ERR_UNSUPPORTED, "tensor-core learner mode: obs_dim must be <= 16");
+  if ((a->phases & (RMC_PH_FORWARD | RMC_PH_BACKWARD)) != (RMC_PH_FORWARD | RMC_PH_BACKWARD))
+    return fail(RMC_ERR_UNSUPPORTED, "tensor-core learner mode needs RMC_PH_FORWARD and RMC_PH_BACKWARD in one step");
+  if (a->grads_in_dev != nullptr) return fail(RMC_ERR_ARG, "tensor-core learner mode: grads_in_dev belongs to an Adam-only step");
+  if (int32_t e = tc_train_setup(l)) return e;
+  const long long B = a->batch;
+  AgentCtx& C = l->ctx;
+  TcTrainBufs T = l->tct;
+  if (a->phases & RMC_PH_SAMPLE) {
+    if (r->prioritized) {
+      if (int32_t e = launch_per_sample(r->dev, B, S.Bglobal, S.shard_off, S.beta, S.u, S.seed, S.counter, C.nodes, C.is_w, C.X, C.leaf_p, st)) return e;
+    } else {
+      k_uniform_sample<<<blocks_for(B, kWarps), kThreads, 0, st>>>(r->dev, B, S.shard_off, S.idx, S.seed, S.counter, 0u, C.nodes, C.X);
+      RMC_KERNEL_OK();
+    }
+  }
+  // bf16 operand images of the online net (forward + backward forms) and of the target net
+  if (l->tc_packed_version != l->online_version) {
+    k_tc_pack<<<blocks_for(kH2 * kH1, 256), 256, 0, st>>>(l->blobs[RMC_ONLINE], l->L, l->tc_packed);
+    RMC_KERNEL_OK();
+    l->tc_packed_version = l->online_version;
+  }
+  if (l->tc_bwd_version != l->online_version) {
+    k_tc_pack_bwd<<<blocks_for(kH1 * kH2, 256), 256, 0, st>>>(l->blobs[RMC_ONLINE], l->L, l->tc_packed_bwd);
+    RMC_KERNEL_OK();
+    l->tc_bwd_version = l->online_version;
+  }
+  k_tc_pack<<<blocks_for(kH2 * kH1, 256), 256, 0, st>>>(l->blobs[RMC_TARGET], l->L, l->tc_packed_target);
+  RMC_KERNEL_OK();
+  const long long n_tiles = (B + kTcRows - 1) / kTcRows;
+  const unsigned grid = static_cast<unsigned>(std::min<long long>(n_tiles, l->num_sms));
+  TcFwdExtra nx{};                 // s' rows: next_obs sits D floats into the gathered row
+  nx.row_stride = l->rf; nx.col_off = l->L.D;
+  k_mlp_infer_tc<<<grid, kThreads, kTcSmemBytes, st>>>(l->tc_packed, l->L.D, l->L.A, l->L.NH, l->L.dueling, C.X, B, nullptr, T.heads_n, 3, nx);
+  RMC_KERNEL_OK();
+  k_mlp_infer_tc<<<grid, kThreads, kTcSmemBytes, st>>>(l->tc_packed_target, l->L.D, l->L.A, l->L.NH, l->L.dueling, C.X, B, nullptr, T.heads_t, 3, nx);
+  RMC_KERNEL_OK();
+  TcFwdExtra sx{};                 // s rows, keeping the bf16 activations for the backward kernels
+  sx.row_stride = l->rf; sx.col_off = 0; sx.Xb = T.Xb; sx.H1b = T.H1b; sx.H2b = T.H2b;
+  k_mlp_infer_tc<<<grid, kThreads, kTcSmemBytes, st>>>(l->tc_packed, l->L.D, l->L.A, l->L.NH, l->L.dueling, C.X, B, nullptr, T.heads_s, 3, sx);
+  RMC_KERNEL_OK();
+  l->ctx.rp = r->dev;
+  const unsigned td_blocks = blocks_for(B, 256);
+  if (td_blocks > 1024) return fail(RMC_ERR_UNSUPPORTED, "tensor-core learner mode: batch above 262,144");
+  k_tc_td<<<td_blocks, 256, 0, st>>>(l->ctx, S, T);
+  RMC_KERNEL_OK();
+  k_tc_bwd<<<grid, kThreads, kTcBwdSmemBytes, st>>>(reinterpret_cast<const unsigned char*>(l->tc_packed_bwd), B, T);
+  RMC_KERNEL_OK();
+  const long long chunks = (B + kWgChunk - 1) / kWgChunk;
+  const int n_part = static_cast<int>(std::min<long long>(chunks, l->num_sms));
+  const long long rows_per_cta = ((chunks + n_part - 1) / n_part) * kWgChunk;
+  T.n_part = n_part;
+  k_tc_wgrad<<<n_part, kThreads, kWgSmemBytes, st>>>(l->ctx, B, rows_per_cta, T);
+  RMC_KERNEL_OK();
+  l->epoch = (l->epoch >= 0x7fffffffu) ? 1u : l->epoch + 1u;
+  S.epoch = l->epoch;
+  k_tc_reduce_adam<<<blocks_for(l->L.total, 256), 256, 0, st>>>(l->ctx, S, T, static_cast<int>(td_blocks));
+  RMC_KERNEL_OK();
+  l->loss_epoch = S.epoch;
+  if (a->phases & RMC_PH_ADAM) ++l->online_version;
+  if ((a->phases & RMC_PH_PRIORITY) && l->spec.prioritized) {
+    if (B <= kTreeCtaMax) {
+      k_tree_update_small<<<1, kThreads, 0, st>>>(r->dev, C.nodes, nullptr, C.abs_td, C.pri, B, S.per_eps, S.per_alpha, S.per_pmax);
+      RMC_KERNEL_OK();
+    } else {
+      k_td_to_pri<<<blocks_for(B, 256), 256, 0, st>>>(C.abs_td, C.pri, B, S.per_eps, S.per_alpha, S.per_pmax);
+      RMC_KERNEL_OK();
+      if (int32_t e = tree_update_large(r, C.nodes, C.pri, B, false, st)) return e;
+    }
+  }
+  return RMC_OK;
+}
+
 extern "C" int32_t rmc_learner_step(rmc_learner_t* l, rmc_replay_t* r, const rmc_step_args_t* a, rmc_stream_t s) {
   if (int32_t e = check_step(l, r, a)) return e;
   if (int32_t e = use_device(l->device)) return e;
@@ -712,6 +840,8 @@ extern "C" int32_t rmc_learner_step(rmc_learner_t* l, rmc_replay_t* r, const rmc
   if (int32_t e = fill_scalars(l, a, &S)) return e;
   l->ctx.rp = r->dev;
   l->last_batch = a->batch;
+  if (a->precision == RMC_PREC_BF16_TC) return step_tc(l, r, a, S, st);
+  if (a->precision != RMC_PREC_FP32) return fail(RMC_ERR_ARG, "rmc_learner_step: unknown precision");
   const int G = grid_for(l, a->batch, l->num_sms);
   const long long n_tiles = (a->batch + kTM - 1) / kTM;
   S.n_row_ctas = static_cast<int>(std::min<long long>(G, n_tiles));
@@ -720,12 +850,13 @@ extern "C" int32_t rmc_learner_step(rmc_learner_t* l, rmc_replay_t* r, const rmc
   // Batches with several row tiles per CTA: draw the minibatch with the full-occupancy grid-wide samplers first
   // (the fused kernel runs 8 warps per SM, far too few to hide the prefix search's dependent round trips).
   if ((a->phases & RMC_PH_SAMPLE) && n_tiles > G) {
-    if (r->prioritized)
-      k_per_sample<<<blocks_for(a->batch, kWarps), kThreads, 0, st>>>(r->dev, a->batch, S.Bglobal, S.shard_off, S.beta, S.u, S.seed, S.counter, 0u,
-                                                                     l->ctx.nodes, l->ctx.is_w, l->ctx.X, l->ctx.leaf_p);
-    else
+    if (r->prioritized) {
+      if (int32_t e = launch_per_sample(r->dev, a->batch, S.Bglobal, S.shard_off, S.beta, S.u, S.seed, S.counter, l->ctx.nodes, l->ctx.is_w, l->ctx.X,
+                                        l->ctx.leaf_p, st)) return e;
+    } else {
       k_uniform_sample<<<blocks_for(a->batch, kWarps), kThreads, 0, st>>>(r->dev, a->batch, S.shard_off, S.idx, S.seed, S.counter, 0u, l->ctx.nodes, l->ctx.X);
-    RMC_KERNEL_OK();
+      RMC_KERNEL_OK();
+    }
     S.phases &= ~RMC_PH_SAMPLE;
   }
   if (rows && phase_b) S.barrier_target = l->barrier_count + static_cast<unsigned>(G);

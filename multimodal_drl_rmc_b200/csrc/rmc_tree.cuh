@@ -461,52 +461,85 @@ __global__ void k_tree_stamp(ReplayDev R, const long long* nodes, long long n) {
   const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (i < n) atomicMax(R.stamps + (nodes[i] - (R.cap - 1)), static_cast<int>(i + 1));
 }
-__global__ void k_tree_apply(ReplayDev R, const long long* nodes, const float* pri, long long n) {
+// Leaf stores + float64 reductions on the ancestors at heap index >= first_fixed only (the contended top of the
+// tree is rebuilt afterwards by k_tree_rebuild_top; sums of f32-exact values are exact in any order, SURVEY finding 6).
+__global__ void k_tree_apply(ReplayDev R, const long long* nodes, const float* pri, long long n, long long first_fixed) {
   const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (i < n) {
     const long long leaf = nodes[i];
     int* st = R.stamps + (leaf - (R.cap - 1));
     if (__ldcg(st) == static_cast<int>(i + 1)) {
       *st = 0;
-      tree_set_leaf(R, leaf, pri[i], nullptr, 0);
+      tree_set_leaf(R, leaf, pri[i], nullptr, first_fixed);
     }
   }
 }
-// grid-wide rescan of the extremes (bulk paths): reset, pass 1 (values), pass 2 (multiplicities)
-__global__ void k_extremes_reset(ReplayDev R) {
-  R.st->max_p = 0.f; R.st->min_p = finf(); R.st->cnt_max = 0; R.st->cnt_min = 0;
+// ONE CTA: nodes [0, F) rebuilt bottom-up in shared memory from nodes [F, 2F+1)  (F = 2^L - 1 <= kTopLargeMax)
+constexpr int kTopLargeMax = 2047;
+__global__ void __launch_bounds__(1024) k_tree_rebuild_top(ReplayDev R, int F) {
+  __shared__ double s_buf[2 * kTopLargeMax + 1];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int k = F + tid; k < 2 * F + 1; k += nt) s_buf[k] = __ldcg(R.tree + k);
+  __syncthreads();
+  for (int first = (F - 1) / 2;; first = (first - 1) / 2) {
+    for (int k = first + tid; k < 2 * first + 1; k += nt) s_buf[k] = s_buf[2 * k + 1] + s_buf[2 * k + 2];
+    __syncthreads();
+    if (first == 0) break;
+  }
+  for (int k = tid; k < F; k += nt) R.tree[k] = s_buf[k];
 }
-__global__ void __launch_bounds__(256) k_extremes_pass1(ReplayDev R) {
+// grid-wide rescan of the extremes (bulk paths) in ONE pass: every thread keeps (max, #max, min, #min) of its leaves,
+// blocks publish their merged tuple, the last block to arrive merges the block tuples into the replay state.
+struct __align__(16) ExtTuple { float mx, mn; int cx, cn; };
+__device__ __forceinline__ void ext_merge(ExtTuple& a, float mx, int cx, float mn, int cn) {
+  if (mx > a.mx) { a.mx = mx; a.cx = cx; } else if (mx == a.mx) a.cx += cx;
+  if (mn < a.mn) { a.mn = mn; a.cn = cn; } else if (mn == a.mn) a.cn += cn;
+}
+__device__ __forceinline__ void ext_warp_merge(ExtTuple& a) {
+#pragma unroll
+  for (int sh = 16; sh > 0; sh >>= 1) {
+    const float mx = __shfl_down_sync(0xffffffffu, a.mx, sh), mn = __shfl_down_sync(0xffffffffu, a.mn, sh);
+    const int cx = __shfl_down_sync(0xffffffffu, a.cx, sh), cn = __shfl_down_sync(0xffffffffu, a.cn, sh);
+    ext_merge(a, mx, cx, mn, cn);
+  }
+}
+constexpr int kExtBlocks = 592;
+__global__ void __launch_bounds__(256) k_extremes_scan(ReplayDev R, ExtTuple* parts, unsigned* arrive) {
+  __shared__ ExtTuple s_w[8];
+  __shared__ bool s_last;
   const long long size = R.st->size;
   const double* leaves = R.tree + (R.cap - 1);
-  float mx = 0.f, mn = finf();
+  ExtTuple a{0.f, finf(), 0, 0};
   for (long long k = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; k < size; k += static_cast<long long>(gridDim.x) * blockDim.x) {
     const float p = static_cast<float>(__ldcg(leaves + k));
-    mx = fmaxf(mx, p);
-    mn = fminf(mn, p);
+    ext_merge(a, p, 1, p, 1);
   }
-  mx = warp_max(mx);
-  mn = warp_min(mn);
-  if ((threadIdx.x & 31) == 0) {   // positive floats order like their bit patterns
-    atomicMax(reinterpret_cast<int*>(&R.st->max_p), __float_as_int(mx));
-    atomicMin(reinterpret_cast<int*>(&R.st->min_p), __float_as_int(mn));
+  ext_warp_merge(a);
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = a;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    ExtTuple b = s_w[0];
+    for (int w = 1; w < 8; ++w) ext_merge(b, s_w[w].mx, s_w[w].cx, s_w[w].mn, s_w[w].cn);
+    parts[blockIdx.x] = b;
+    __threadfence();
+    s_last = (atomicAdd(arrive, 1u) == gridDim.x - 1);
   }
-}
-__global__ void __launch_bounds__(256) k_extremes_pass2(ReplayDev R) {
-  const long long size = R.st->size;
-  const double* leaves = R.tree + (R.cap - 1);
-  const float mx = R.st->max_p, mn = R.st->min_p;
-  int cx = 0, cn = 0;
-  for (long long k = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; k < size; k += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const float p = static_cast<float>(__ldcg(leaves + k));
-    cx += (p == mx);
-    cn += (p == mn);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  ExtTuple b{0.f, finf(), 0, 0};
+  for (int k = threadIdx.x; k < static_cast<int>(gridDim.x); k += blockDim.x) {
+    const float4 raw = __ldcg(reinterpret_cast<const float4*>(parts + k));
+    ext_merge(b, raw.x, __float_as_int(raw.z), raw.y, __float_as_int(raw.w));
   }
-  cx = warp_sum(cx);
-  cn = warp_sum(cn);
-  if ((threadIdx.x & 31) == 0) {
-    if (cx) atomicAdd(reinterpret_cast<unsigned long long*>(&R.st->cnt_max), static_cast<unsigned long long>(cx));
-    if (cn) atomicAdd(reinterpret_cast<unsigned long long*>(&R.st->cnt_min), static_cast<unsigned long long>(cn));
+  ext_warp_merge(b);
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = b;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    ExtTuple c = s_w[0];
+    for (int w = 1; w < 8; ++w) ext_merge(c, s_w[w].mx, s_w[w].cx, s_w[w].mn, s_w[w].cn);
+    R.st->max_p = c.mx; R.st->min_p = c.mn; R.st->cnt_max = c.cx; R.st->cnt_min = c.cn;
+    *arrive = 0u;
   }
 }
 
@@ -696,6 +729,59 @@ __global__ void __launch_bounds__(kThreads) k_per_sample(ReplayDev R, long long 
     out_nodes[i] = leaf;
     if (out_w != nullptr) out_w[i] = static_cast<float>(numer / s_max_w);
     if (out_leaf_p != nullptr) out_leaf_p[i] = p;
+  }
+}
+
+// Large batches: ONE LANE per sample.  Stratified samples are sorted, so the 32 descents of a warp share their first
+// ~log2(B) - 5 nodes (one broadcast L1 hit each) and the whole batch is in flight at once (2048 descents per SM);
+// the comparison sequence per sample is still exactly sum_tree.py:53-57.  Rows are then gathered cooperatively:
+// 8 lanes fetch one 128-byte row with float4 loads, the warp's 32 output rows are written contiguously.
+__global__ void __launch_bounds__(kThreads) k_per_sample_lane(ReplayDev R, long long B, long long Bglobal, long long shard_off,
+                                                              double beta, const double* __restrict__ u, unsigned long long seed,
+                                                              unsigned long long counter, unsigned agent, long long* __restrict__ out_nodes,
+                                                              float* __restrict__ out_w, float* __restrict__ out_rows,
+                                                              double* __restrict__ out_leaf_p) {
+  __shared__ double s_max_w;
+  const int lane = threadIdx.x & 31;
+  const long long i = blockIdx.x * static_cast<long long>(kThreads) + threadIdx.x;
+  const long long n_nodes = 2 * R.cap - 1;
+  const double* __restrict__ tree = R.tree;
+  const double total = __ldg(tree);
+  const long long size = R.st->size;
+  if (out_w != nullptr && threadIdx.x == kThreads - 1)
+    s_max_w = is_weight_max(static_cast<double>(size), total, static_cast<double>(R.st->min_p), beta);
+  long long leaf = R.cap - 1;
+  double pv = 0.0, numer = 1.0;
+  if (i < B) {
+    const double ui = (u != nullptr) ? u[i] : philox_uniform(seed, counter, agent, static_cast<uint32_t>(shard_off + i));
+    double v = stratum_value(total, Bglobal, shard_off + i, ui);
+    long long p = 0;
+    while (2 * p + 1 < n_nodes) {
+      const long long l = 2 * p + 1;
+      const double lv = __ldg(tree + l);
+      if (v <= lv) { p = l; } else { v = v - lv; p = l + 1; }
+    }
+    leaf = p;
+    pv = __ldg(tree + p);
+    if (out_w != nullptr) numer = pow(static_cast<double>(size) * (pv / total), -beta);
+  }
+  if (out_rows != nullptr) {
+    const int rf4 = R.row_floats >> 2;
+    const long long i0 = i - lane;                       // first sample of this warp
+    const long long slot = leaf - (R.cap - 1);
+    const float4* __restrict__ ring4 = reinterpret_cast<const float4*>(R.ring);
+    float4* __restrict__ dst4 = reinterpret_cast<float4*>(out_rows + i0 * R.row_floats);
+    for (int t = lane; t < 32 * rf4; t += 32) {
+      const int row = t / rf4, c = t - row * rf4;
+      const long long sl = __shfl_sync(0xffffffffu, slot, row);
+      if (i0 + row < B) dst4[t] = __ldcg(ring4 + sl * rf4 + c);
+    }
+  }
+  __syncthreads();
+  if (i < B) {
+    out_nodes[i] = leaf;
+    if (out_w != nullptr) out_w[i] = static_cast<float>(numer / s_max_w);
+    if (out_leaf_p != nullptr) out_leaf_p[i] = pv;
   }
 }
 

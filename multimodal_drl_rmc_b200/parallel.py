@@ -112,6 +112,7 @@ class ShardedLearner:
         a.phases = _lib.PH_SAMPLE | _lib.PH_FORWARD | _lib.PH_BACKWARD
         a.seed, a.counter, a.adam_t = ag.sampling_seed, ag._learn_calls, ag._adam_t
         a.grads_in_dev = None
+        a.precision = ag._args.precision      # "bf16": tensor-core forward/backward, fp32 all-reduce + Adam
         keep = None
         if ag._PER:
             a.per_beta = ag._beta(ag.step * ag.n_env)
