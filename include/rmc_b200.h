@@ -30,12 +30,13 @@
 extern "C" {
 #endif
 
-#define RMC_ABI_VERSION 1
+#define RMC_ABI_VERSION 2
 
 typedef void* rmc_stream_t;
 typedef struct rmc_replay rmc_replay_t;   /* GPU-resident ring buffer (+ sum tree when prioritized) */
 typedef struct rmc_learner rmc_learner_t; /* online/target nets, Adam state, scratch                */
 typedef struct rmc_group rmc_group_t;     /* N (replay, learner) pairs stepped by ONE launch        */
+typedef struct rmc_comm rmc_comm_t;       /* peer-memory exchange buffers of the sharded learner    */
 
 enum rmc_status {
   RMC_OK = 0,
@@ -252,6 +253,35 @@ int32_t rmc_group_create(rmc_group_t** out, rmc_learner_t* const* learners, rmc_
 int32_t rmc_group_destroy(rmc_group_t* g);
 /* u_dev / idx_dev (if given) hold n_agents * batch entries, agent-major. */
 int32_t rmc_group_step(rmc_group_t* g, const rmc_step_args_t* a, rmc_stream_t s);
+
+/* ---------------------------------------------------------------- sharded large batch (C5) --- */
+/* The reference has no multi-device path; this is the data-parallel form of
+ * PerDoubleAgent.learn (dqn/agent.py:245-272) for one logical agent replicated on `world` GPUs of one
+ * node: rank r draws the strata [lo, hi) = shard_range(global_batch, r, world) of the GLOBAL stratified
+ * sample (replay_memory.py:72-80 with seg = total / global_batch), computes its gradient slice scaled by
+ * 1 / global_batch, and the exchange + Adam run as kernels over NVLink peer memory (no library collective):
+ * each rank publishes its gradient blob into its own exchange buffer, flags every peer, and one kernel
+ * sums the ranks' blobs in rank order straight from peer memory and applies Adam (+ Polyak) -- identical
+ * bits on every replica.  PER: (leaf, |td|) slices travel the same way and every replica applies the full
+ * write-back in global batch order.
+ *   rmc_comm_create  : allocate this rank's exchange buffer (2 parity slots + flags)
+ *   rmc_comm_export  : its cudaIpcMemHandle_t (64 bytes) to all-gather across the ranks' processes
+ *                      (and/or the raw device pointer for ranks living in one process)
+ *   rmc_comm_connect : map the peers' buffers (handles64 = world x 64 bytes, rank-major; or same-process
+ *                      device pointers)
+ *   rmc_learner_step_sharded : the whole step; `a` carries batch = hi - lo, shard_offset = lo,
+ *                      global_batch, phases (FORWARD|BACKWARD|ADAM required), precision.  stages = 3: the
+ *                      whole step (one GPU per rank); 1 = local gradients + publish, 2 = reduce + Adam +
+ *                      write-back -- only for ranks EMULATED on one GPU, where a rank's waiting reduce kernel
+ *                      would keep the other rank's cooperative step kernel from becoming resident
+ *   rmc_comm_status_sync : 0, or the epoch of an exchange that timed out (a peer never published) */
+int32_t rmc_comm_create(rmc_comm_t** out, rmc_learner_t* l, int32_t rank, int32_t world, int64_t global_batch_max);
+int32_t rmc_comm_export(rmc_comm_t* c, void* handle64_out, void** local_ptr_out);
+int32_t rmc_comm_connect(rmc_comm_t* c, const void* handles64, void* const* same_process_ptrs);
+int32_t rmc_comm_destroy(rmc_comm_t* c);
+int32_t rmc_comm_status_sync(rmc_comm_t* c, uint32_t* timed_out_epoch, rmc_stream_t s);
+int32_t rmc_learner_step_sharded(rmc_learner_t* l, rmc_replay_t* r, rmc_comm_t* c, const rmc_step_args_t* a,
+                                 int32_t stages, rmc_stream_t s);
 
 #ifdef __cplusplus
 }

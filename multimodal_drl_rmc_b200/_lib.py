@@ -127,7 +127,14 @@ _SIGS = {
     "rmc_group_create": (_i32, [C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), _i32]),
     "rmc_group_destroy": (_i32, [_vp]),
     "rmc_group_step": (_i32, [_vp, C.POINTER(StepArgs), _vp]),
+    "rmc_comm_create": (_i32, [C.POINTER(_vp), _vp, _i32, _i32, _i64]),
+    "rmc_comm_export": (_i32, [_vp, _vp, C.POINTER(_vp)]),
+    "rmc_comm_connect": (_i32, [_vp, _vp, C.POINTER(_vp)]),
+    "rmc_comm_destroy": (_i32, [_vp]),
+    "rmc_comm_status_sync": (_i32, [_vp, C.POINTER(C.c_uint32), _vp]),
+    "rmc_learner_step_sharded": (_i32, [_vp, _vp, _vp, C.POINTER(StepArgs), _i32, _vp]),
 }
+ABI_VERSION = 2
 
 
 def lib() -> C.CDLL:
@@ -145,7 +152,7 @@ def lib() -> C.CDLL:
             for name, (res, args) in _SIGS.items():
                 fn = getattr(handle, name)
                 fn.restype, fn.argtypes = res, args
-            if handle.rmc_abi_version() != 1:
+            if handle.rmc_abi_version() != ABI_VERSION:
                 raise RuntimeError("librmc_b200.so ABI version mismatch; rebuild")
             _lib = handle
     return _lib

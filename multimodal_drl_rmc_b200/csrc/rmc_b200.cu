@@ -16,6 +16,7 @@
 #include "rmc_mlp.cuh"
 #include "rmc_tc.cuh"
 #include "rmc_tc_train.cuh"
+#include "rmc_comm.cuh"
 #include "rmc_tree.cuh"
 
 using namespace rmc;
@@ -100,6 +101,23 @@ struct rmc_learner {
   float* act_pin_obs = nullptr; long long* act_pin_out = nullptr; float* act_dev_obs = nullptr; long long* act_dev_out = nullptr;
   long long act_cap = 0;
   std::vector<void*> owned;
+};
+
+struct rmc_comm {
+  int device = 0, rank = 0, world = 1;
+  long long global_batch_max = 0, local_max = 0;
+  size_t bytes = 0;
+  unsigned char* local = nullptr;               // this rank's exchange buffer (cudaMalloc: IPC-exportable)
+  void* peer[kCommMaxWorld] = {nullptr};        // mapped peer buffers (own rank: == local)
+  bool ipc_opened[kCommMaxWorld] = {false};
+  bool connected = false;
+  CommView view{};
+  unsigned epoch = 0;
+  unsigned* arrive = nullptr;
+  long long* g_nodes = nullptr;                 // gathered (leaf, |td|) of the whole batch + their priorities
+  float* g_td = nullptr;
+  float* g_pri = nullptr;
+  rmc_learner* learner = nullptr;
 };
 
 struct rmc_group {
@@ -874,6 +892,169 @@ extern "C" int32_t rmc_learner_step(rmc_learner_t* l, rmc_replay_t* r, const rmc
     k_td_to_pri<<<blocks_for(a->batch, 256), 256, 0, st>>>(l->ctx.abs_td, l->ctx.pri, a->batch, S.per_eps, S.per_alpha, S.per_pmax);
     RMC_KERNEL_OK();
     if (int32_t e = tree_update_large(r, l->ctx.nodes, l->ctx.pri, a->batch, false, st)) return e;
+  }
+  return RMC_OK;
+}
+
+// ------------------------------------------------------------------------------ sharded learner: peer-memory exchange
+static void shard_range_c(long long batch, int rank, int world, long long* lo, long long* hi) {   // = parallel.shard_range
+  const long long base = batch / world, rem = batch % world;
+  *lo = rank * base + std::min<long long>(rank, rem);
+  *hi = *lo + base + (rank < rem ? 1 : 0);
+}
+
+extern "C" int32_t rmc_comm_create(rmc_comm_t** out, rmc_learner_t* l, int32_t rank, int32_t world, int64_t global_batch_max) {
+  if (!out || !l || world < 1 || world > kCommMaxWorld || rank < 0 || rank >= world || global_batch_max < world)
+    return fail(RMC_ERR_ARG, "rmc_comm_create: bad args (world must be 1..8)");
+  if (int32_t e = use_device(l->device)) return e;
+  auto* c = new rmc_comm();
+  c->device = l->device; c->rank = rank; c->world = world; c->learner = l;
+  c->global_batch_max = global_batch_max;
+  c->local_max = (global_batch_max + world - 1) / world;
+  if (c->local_max > l->max_batch) { delete c; return fail(RMC_ERR_ARG, "rmc_comm_create: local shard exceeds the learner's max_batch"); }
+  auto up = [](long long x) { return (x + 255) & ~255ll; };
+  CommView& V = c->view;
+  V.rank = rank; V.world = world;
+  V.off_loss = up(static_cast<long long>(l->L.total) * 4);
+  V.off_nodes = V.off_loss + 256;
+  V.off_td = V.off_nodes + up(c->local_max * 8);
+  V.slot_bytes = V.off_td + up(c->local_max * 4);
+  c->bytes = static_cast<size_t>(kCommHeaderBytes + 2 * V.slot_bytes);
+  RMC_CUDA(cudaMalloc(reinterpret_cast<void**>(&c->local), c->bytes));
+  RMC_CUDA(cudaMemset(c->local, 0, c->bytes));
+  int32_t e = RMC_OK;
+  if ((e = dev_alloc(&c->arrive, 1))) return e;
+  if ((e = dev_alloc(&c->g_nodes, static_cast<size_t>(global_batch_max)))) return e;
+  if ((e = dev_alloc(&c->g_td, static_cast<size_t>(global_batch_max)))) return e;
+  if ((e = dev_alloc(&c->g_pri, static_cast<size_t>(global_batch_max)))) return e;
+  RMC_CUDA(cudaDeviceSynchronize());
+  *out = c;
+  return RMC_OK;
+}
+
+extern "C" int32_t rmc_comm_export(rmc_comm_t* c, void* handle64_out, void** local_ptr_out) {
+  if (!c) return fail(RMC_ERR_ARG, "rmc_comm_export: null");
+  if (int32_t e = use_device(c->device)) return e;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  if (handle64_out) {
+    cudaIpcMemHandle_t h;
+    RMC_CUDA(cudaIpcGetMemHandle(&h, c->local));
+    std::memcpy(handle64_out, &h, 64);
+  }
+  if (local_ptr_out) *local_ptr_out = c->local;
+  return RMC_OK;
+}
+
+extern "C" int32_t rmc_comm_connect(rmc_comm_t* c, const void* handles64, void* const* same_process_ptrs) {
+  if (!c || (!handles64 && !same_process_ptrs)) return fail(RMC_ERR_ARG, "rmc_comm_connect: null");
+  if (c->connected) return fail(RMC_ERR_STATE, "rmc_comm_connect: already connected");
+  if (int32_t e = use_device(c->device)) return e;
+  for (int r = 0; r < c->world; ++r) {
+    if (r == c->rank) { c->peer[r] = c->local; continue; }
+    if (same_process_ptrs) {                      // ranks emulated inside one process (tests): plain device pointers
+      c->peer[r] = same_process_ptrs[r];
+      cudaPointerAttributes at{};
+      RMC_CUDA(cudaPointerGetAttributes(&at, c->peer[r]));
+      if (at.device != c->device) {
+        int can = 0;
+        RMC_CUDA(cudaDeviceCanAccessPeer(&can, c->device, at.device));
+        if (!can) return fail(RMC_ERR_UNSUPPORTED, "rmc_comm_connect: no peer access between the devices");
+        cudaError_t pe = cudaDeviceEnablePeerAccess(at.device, 0);
+        if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) RMC_CUDA(pe);
+        cudaGetLastError();
+      }
+    } else {
+      cudaIpcMemHandle_t h;
+      std::memcpy(&h, static_cast<const unsigned char*>(handles64) + 64 * r, 64);
+      RMC_CUDA(cudaIpcOpenMemHandle(&c->peer[r], h, cudaIpcMemLazyEnablePeerAccess));
+      c->ipc_opened[r] = true;
+    }
+  }
+  for (int r = 0; r < kCommMaxWorld; ++r) c->view.base[r] = static_cast<unsigned char*>(r < c->world ? c->peer[r] : nullptr);
+  c->connected = true;
+  return RMC_OK;
+}
+
+extern "C" int32_t rmc_comm_destroy(rmc_comm_t* c) {
+  if (!c) return RMC_OK;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  for (int r = 0; r < c->world; ++r)
+    if (c->ipc_opened[r]) cudaIpcCloseMemHandle(c->peer[r]);
+  cudaFree(c->local); cudaFree(c->arrive); cudaFree(c->g_nodes); cudaFree(c->g_td); cudaFree(c->g_pri);
+  delete c;
+  return RMC_OK;
+}
+
+/* 0 = healthy; otherwise the epoch of the step whose exchange timed out (a peer never published). Synchronises. */
+extern "C" int32_t rmc_comm_status_sync(rmc_comm_t* c, uint32_t* timed_out_epoch, rmc_stream_t s) {
+  if (!c || !timed_out_epoch) return fail(RMC_ERR_ARG, "rmc_comm_status_sync: null");
+  if (int32_t e = use_device(c->device)) return e;
+  RMC_CUDA(cudaMemcpyAsync(timed_out_epoch, c->local + 2 * kCommMaxWorld * sizeof(unsigned), sizeof(unsigned), cudaMemcpyDeviceToHost, as_stream(s)));
+  RMC_CUDA(cudaStreamSynchronize(as_stream(s)));
+  return RMC_OK;
+}
+
+extern "C" int32_t rmc_learner_step_sharded(rmc_learner_t* l, rmc_replay_t* r, rmc_comm_t* c, const rmc_step_args_t* a, int32_t stages, rmc_stream_t s) {
+  if (!l || !r || !c || !a) return fail(RMC_ERR_ARG, "rmc_learner_step_sharded: null");
+  if (!c->connected || c->learner != l) return fail(RMC_ERR_STATE, "rmc_learner_step_sharded: comm not connected to this learner");
+  const long long Bg = a->global_batch > 0 ? a->global_batch : a->batch;
+  if (Bg > c->global_batch_max || Bg < c->world) return fail(RMC_ERR_ARG, "rmc_learner_step_sharded: global batch outside the comm's range");
+  long long lo, hi;
+  shard_range_c(Bg, c->rank, c->world, &lo, &hi);
+  if (a->shard_offset != lo || a->batch != hi - lo) return fail(RMC_ERR_ARG, "rmc_learner_step_sharded: batch/shard_offset differ from shard_range(global_batch, rank, world)");
+  const int want = RMC_PH_FORWARD | RMC_PH_BACKWARD | RMC_PH_ADAM;
+  if ((a->phases & want) != want) return fail(RMC_ERR_ARG, "rmc_learner_step_sharded: needs FORWARD, BACKWARD and ADAM");
+  if (stages < 1 || stages > 3) return fail(RMC_ERR_ARG, "rmc_learner_step_sharded: stages must be 1, 2 or 3");
+  cudaStream_t st = as_stream(s);
+  const bool per = l->spec.prioritized != 0 && (a->phases & RMC_PH_PRIORITY);
+  if (stages & 1) c->epoch = (c->epoch >= 0x7fffffffu) ? 1u : c->epoch + 1u;
+  const int parity = static_cast<int>(c->epoch & 1u);
+  CommView V = c->view;
+  for (int q = 0; q <= c->world; ++q) {
+    long long qlo, qhi;
+    shard_range_c(Bg, std::min(q, c->world - 1), c->world, &qlo, &qhi);
+    V.shard_lo[q] = (q < c->world) ? qlo : qhi;
+  }
+  const long long n_local = a->batch;
+  if (stages & 1) {
+  // 1. local shard: sample (global strata), forward, TD, backward -> local gradient blob scaled by 1/B_global
+  rmc_step_args_t a1 = *a;
+  a1.phases = a->phases & (RMC_PH_SAMPLE | RMC_PH_FORWARD | RMC_PH_BACKWARD);
+  a1.grads_in_dev = nullptr;
+  if (int32_t e = rmc_learner_step(l, r, &a1, s)) return e;
+  // 2. publish: gradient blob, loss partial, (leaf, |td|) slice -> own exchange buffer, then one flag per rank
+  const unsigned pub_blocks = std::max(1u, std::min(64u, blocks_for(std::max<long long>(l->L.total, n_local), 1024)));
+  k_comm_publish<<<pub_blocks, 256, 0, st>>>(V, parity, c->epoch, l->ctx.grads, l->L.total, l->ctx.loss, per ? l->ctx.nodes : nullptr, l->ctx.abs_td,
+                                            n_local, c->arrive);
+  RMC_KERNEL_OK();
+  }
+  if (!(stages & 2)) return RMC_OK;
+  // 3. reduce over the ranks (peer loads, rank order) fused with Adam (+ Polyak)
+  rmc_step_args_t a2 = *a;
+  a2.phases = a->phases & (RMC_PH_ADAM | RMC_PH_POLYAK | RMC_PH_HARDSYNC);
+  StepScalars S;
+  if (int32_t e = fill_scalars(l, &a2, &S)) return e;
+  l->epoch = (l->epoch >= 0x7fffffffu) ? 1u : l->epoch + 1u;
+  S.epoch = l->epoch;
+  const int param_blocks = static_cast<int>(blocks_for(l->L.total, 256));
+  const int gather_blocks = per ? static_cast<int>(std::min<long long>(256, (Bg + 255) / 256)) : 0;
+  k_comm_reduce_adam<<<param_blocks + gather_blocks, 256, 0, st>>>(l->ctx, S, V, parity, c->epoch, param_blocks, c->g_nodes, c->g_td, per ? 1 : 0);
+  RMC_KERNEL_OK();
+  l->loss_epoch = S.epoch;
+  ++l->online_version;
+  // 4. PER: the full write-back of the GLOBAL batch on every replica, in global batch order (trees stay identical)
+  if (per) {
+    if (Bg <= kTreeCtaMax) {
+      k_tree_update_small<<<1, kThreads, 0, st>>>(r->dev, c->g_nodes, nullptr, c->g_td, c->g_pri, Bg, static_cast<float>(l->hyper.per_eps),
+                                                 static_cast<float>(l->hyper.per_alpha), static_cast<float>(l->hyper.per_pmax));
+      RMC_KERNEL_OK();
+    } else {
+      k_td_to_pri<<<blocks_for(Bg, 256), 256, 0, st>>>(c->g_td, c->g_pri, Bg, static_cast<float>(l->hyper.per_eps), static_cast<float>(l->hyper.per_alpha),
+                                                      static_cast<float>(l->hyper.per_pmax));
+      RMC_KERNEL_OK();
+      if (int32_t e = tree_update_large(r, c->g_nodes, c->g_pri, Bg, false, st)) return e;
+    }
   }
   return RMC_OK;
 }

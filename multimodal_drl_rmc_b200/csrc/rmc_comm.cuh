@@ -1,0 +1,136 @@
+// rmc_comm.cuh -- the exchange step of the minibatch-sharded large-batch learner (BASELINE configs[4]) as
+// kernels over NVLink peer memory instead of library collectives:
+//
+//   k_comm_publish      local gradient blob, loss partial and (leaf, |td|) slice -> this rank's exchange buffer (one of two
+//                       parity slots), then ONE release-store per peer of this step's epoch into the peer's flag array
+//   k_comm_reduce_adam  waits for every rank's flag (local polling), then each thread sums ITS parameter's gradient over the
+//                       ranks' buffers in rank order (peer loads over NVLink; fixed order -> every replica computes the same
+//                       bits), applies Adam (+ Polyak) to that parameter in the same kernel, and the spare blocks gather the
+//                       ranks' (leaf, |td|) slices into local arrays for the replicated priority write-back.
+//
+// One-shot all-reduce: every rank reads (W-1) x 152 KB; at W = 8 that is ~1 MB per rank per step, far below the
+// 900 GB/s/direction of NVLink 5, so the exchange costs one flag round trip instead of a multi-step ring.
+// Double buffering: rank r rewrites slot (t & 1) at step t+2 only after it has seen every peer's flag of step t+1,
+// which a peer sends after (stream order) its step-t reads completed.
+#pragma once
+#include "rmc_mlp.cuh"
+
+namespace rmc {
+
+constexpr int kCommMaxWorld = 8;
+constexpr int kCommHeaderBytes = 4096;     // flags[2][kCommMaxWorld] + error word, padded
+
+struct CommView {
+  unsigned char* base[kCommMaxWorld];      // exchange buffer of every rank (own rank: local memory)
+  int rank, world;
+  long long slot_bytes;                    // bytes of one parity slot
+  long long off_loss, off_nodes, off_td;   // byte offsets inside a slot (gradients sit at 0)
+  long long shard_lo[kCommMaxWorld + 1];   // global sample range of every rank
+};
+
+__device__ __forceinline__ unsigned char* comm_slot(const CommView& V, int r, int parity) {
+  return V.base[r] + kCommHeaderBytes + static_cast<long long>(parity) * V.slot_bytes;
+}
+__device__ __forceinline__ void st_release_sys_u32(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float ld_sys_f32(const float* p) {
+  float v;
+  asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ long long ld_sys_s64(const long long* p) {
+  long long v;
+  asm volatile("ld.relaxed.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(256) k_comm_publish(CommView V, int parity, unsigned epoch, const float* __restrict__ grads, int total,
+                                                      const float* __restrict__ loss, const long long* __restrict__ nodes,
+                                                      const float* __restrict__ abs_td, long long n_local, unsigned* arrive) {
+  __shared__ bool s_last;
+  unsigned char* slot = comm_slot(V, V.rank, parity);
+  float* g = reinterpret_cast<float*>(slot);
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const long long t0 = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  for (long long k = t0; k < total; k += stride) g[k] = __ldcg(grads + k);
+  if (t0 == 0) *reinterpret_cast<float*>(slot + V.off_loss) = __ldcg(loss);
+  if (nodes != nullptr) {
+    long long* dn = reinterpret_cast<long long*>(slot + V.off_nodes);
+    float* dt = reinterpret_cast<float*>(slot + V.off_td);
+    for (long long k = t0; k < n_local; k += stride) { dn[k] = __ldcg(nodes + k); dt[k] = __ldcg(abs_td + k); }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(arrive, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence_system();
+  if (threadIdx.x < V.world) {     // flag of (this rank, this parity) in every rank's header, own included
+    unsigned* flags = reinterpret_cast<unsigned*>(V.base[threadIdx.x]);
+    st_release_sys_u32(flags + parity * kCommMaxWorld + V.rank, epoch);
+  }
+  if (threadIdx.x == 0) *arrive = 0u;
+}
+
+// blocks [0, param_blocks): parameters; the remaining blocks: (leaf, |td|) gather.
+__global__ void __launch_bounds__(256) k_comm_reduce_adam(AgentCtx C, StepScalars S, CommView V, int parity, unsigned epoch, int param_blocks,
+                                                          long long* __restrict__ g_nodes, float* __restrict__ g_td, int want_gather) {
+  __shared__ int s_ok;
+  unsigned* my_flags = reinterpret_cast<unsigned*>(V.base[V.rank]);
+  if (threadIdx.x == 0) s_ok = 1;
+  __syncthreads();
+  if (threadIdx.x < V.world) {
+    const unsigned* f = my_flags + parity * kCommMaxWorld + threadIdx.x;
+    const unsigned long long t0 = global_timer_ns();
+    while (ld_acquire_sys_u32(f) != epoch) {
+      if (global_timer_ns() - t0 > 4000000000ull) {      // 4 s: a peer died -- flag the error instead of hanging the GPU
+        s_ok = 0;
+        my_flags[2 * kCommMaxWorld] = epoch;
+        break;
+      }
+      __nanosleep(64);
+    }
+  }
+  __syncthreads();
+  if (!s_ok) return;
+  const NetLayout& L = C.L;
+  if (static_cast<int>(blockIdx.x) < param_blocks) {
+    const int pi = blockIdx.x * 256 + threadIdx.x;
+    if (pi < L.total) {
+      float g = 0.f;
+      for (int r = 0; r < V.world; ++r) g += ld_sys_f32(reinterpret_cast<const float*>(comm_slot(V, r, parity)) + pi);
+      C.grads[pi] = g;
+      adam_polyak_element(C, S, pi, g);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      float loss = 0.f;
+      for (int r = 0; r < V.world; ++r) loss += ld_sys_f32(reinterpret_cast<const float*>(comm_slot(V, r, parity) + V.off_loss));
+      C.loss[0] = loss;
+      if (C.host_loss != nullptr) {
+        C.host_loss[0] = loss;
+        __threadfence_system();
+        C.host_loss[1] = __uint_as_float(S.epoch);
+      }
+    }
+  } else if (want_gather) {
+    const long long nb = gridDim.x - param_blocks;
+    const long long stride = nb * 256;
+    for (int r = 0; r < V.world; ++r) {
+      const long long lo = V.shard_lo[r], n = V.shard_lo[r + 1] - lo;
+      const long long* sn = reinterpret_cast<const long long*>(comm_slot(V, r, parity) + V.off_nodes);
+      const float* st = reinterpret_cast<const float*>(comm_slot(V, r, parity) + V.off_td);
+      for (long long k = (blockIdx.x - param_blocks) * 256ll + threadIdx.x; k < n; k += stride) {
+        g_nodes[lo + k] = ld_sys_s64(sn + k);
+        g_td[lo + k] = ld_sys_f32(st + k);
+      }
+    }
+  }
+}
+
+}  // namespace rmc

@@ -92,15 +92,106 @@ class ShardedLearner:
       4. Adam (+ Polyak) from the reduced gradients, identical on every rank.
     """
 
-    def __init__(self, agent, group=None):
-        import torch.distributed as dist
-        self.agent, self.dist, self.group = agent, dist, group
-        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+    def __init__(self, agent, group=None, exchange="nccl", rank=None, world=None):
+        """``exchange="nccl"``: torch.distributed collectives (all-reduce + all-gather) around two library calls.
+        ``exchange="peer"``: the exchange runs inside the library as kernels over NVLink peer memory (gradient blobs
+        read straight from the peers' buffers and reduced in rank order in the same kernel that applies Adam); the
+        whole step is ONE C call with no collective and no host synchronisation.  The peers' buffers are mapped with
+        CUDA IPC handles all-gathered once at construction (``connect_same_process`` for ranks emulated in one
+        process)."""
+        if exchange not in ("nccl", "peer"):
+            raise ValueError("exchange must be 'nccl' or 'peer'")
+        self.agent, self.group, self.exchange = agent, group, exchange
+        if rank is None:
+            import torch.distributed as dist
+            self.dist = dist
+            self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        else:                               # explicit placement (ranks emulated inside one process)
+            self.dist = None
+            self.rank, self.world = int(rank), int(world)
         self.B = int(agent.batch_size)
         self.lo, self.hi = shard_range(self.B, self.rank, self.world)
         self._args = _lib.StepArgs()
+        self._comm = None
+        if exchange == "peer":
+            h = C.c_void_p()
+            check(lib().rmc_comm_create(C.byref(h), agent._lh.handle, self.rank, self.world, self.B))
+            self._comm = h
+            if self.dist is not None:
+                self._connect_ipc()
 
-    def learn(self, u=None, fuse_target_update=True):
+    def __del__(self):
+        try:
+            if self._comm is not None:
+                lib().rmc_comm_destroy(self._comm)
+                self._comm = None
+        except Exception:
+            pass
+
+    def _export(self):
+        buf = (C.c_ubyte * 64)()
+        p = C.c_void_p()
+        check(lib().rmc_comm_export(self._comm, buf, C.byref(p)))
+        return bytes(buf), p.value
+
+    def _connect_ipc(self):
+        handle, _ = self._export()
+        dev = self.agent.device
+        mine = T.tensor(list(handle), dtype=T.uint8, device=dev)
+        parts = [T.empty(64, dtype=T.uint8, device=dev) for _ in range(self.world)]
+        self.dist.all_gather(parts, mine, group=self.group)
+        blob = b"".join(bytes(p.cpu().tolist()) for p in parts)
+        check(lib().rmc_comm_connect(self._comm, blob, None))
+        self.dist.barrier(group=self.group)
+
+    @staticmethod
+    def connect_same_process(members):
+        """Wire the exchange buffers of ``members`` (one ShardedLearner per emulated rank, all in this process)."""
+        ptrs = [m._export()[1] for m in members]
+        arr = (C.c_void_p * len(ptrs))(*ptrs)
+        for m in members:
+            check(lib().rmc_comm_connect(m._comm, None, arr))
+
+    def _learn_peer(self, u, fuse_target_update, stages=3):
+        ag = self.agent
+        if stages == 2:       # second half of a split step (emulated ranks): same arguments as the first half
+            check(lib().rmc_learner_step_sharded(ag._lh.handle, ag.replay_memory_buffer._ring.require(), self._comm,
+                                                 C.byref(self._args), 2, stream_ptr(ag.device.index)))
+            return ag._lh.output("loss")
+        ag._learn_calls += 1
+        ag._adam_t += 1
+        a = self._args
+        a.batch, a.global_batch, a.shard_offset = self.hi - self.lo, self.B, self.lo
+        a.phases = ag._learn_phases | (ag._target_phase() if fuse_target_update else 0)
+        a.seed, a.counter, a.adam_t = ag.sampling_seed, ag._learn_calls, ag._adam_t
+        a.grads_in_dev, a.u_dev, a.idx_dev = None, None, None
+        a.precision = ag._args.precision
+        keep = None
+        if ag._PER:
+            a.per_beta = ag._beta(ag.step * ag.n_env)
+            if u is not None:
+                keep = T.as_tensor(np.asarray(u, np.float64)[self.lo:self.hi].copy(), device=ag.device)
+                a.u_dev = keep.data_ptr()
+        rh = ag.replay_memory_buffer._ring.require()
+        check(lib().rmc_learner_step_sharded(ag._lh.handle, rh, self._comm, C.byref(a), stages, stream_ptr(ag.device.index)))
+        ag._lh.version[_lib.ONLINE] += 1
+        if fuse_target_update:
+            ag._lh.version[_lib.TARGET] += 1
+            ag._target_fused_for = ag._learn_calls
+        self._keep = keep
+        return ag._lh.output("loss")
+
+    def exchange_status(self):
+        """0, or the epoch of an exchange that timed out because a peer never published (synchronises)."""
+        if self._comm is None:
+            return 0
+        v = C.c_uint32(0)
+        check(lib().rmc_comm_status_sync(self._comm, C.byref(v), stream_ptr(self.agent.device.index)))
+        return int(v.value)
+
+    def learn(self, u=None, fuse_target_update=True, stages=3):
+        if self.exchange == "peer":
+            return self._learn_peer(u, fuse_target_update, stages)
         ag, dist = self.agent, self.dist
         lh = ag._lh
         rh = ag.replay_memory_buffer._ring.require()

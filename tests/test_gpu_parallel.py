@@ -92,3 +92,55 @@ def test_large_batch_per_step_uses_grid_wide_tree_path():
     assert res["nodes_equal"] and res["tree_equal"]
     assert res["max_rel_q"] < 1e-5 and res["max_rel_loss"] < 1e-5 and res["max_rel_grads"] < 1e-5
     assert res["max_rel_weights"] < 1e-5 and res["max_pri_ulp"] <= 1.0
+
+
+@pytest.mark.parametrize("B,precision,steps", [(512, "fp32", 3), (8192, "fp32", 2), (8192, "bf16", 2), (515, "fp32", 2)])
+def test_peer_memory_exchange_two_ranks_on_one_gpu(B, precision, steps):
+    """ShardedLearner(exchange="peer"): the gradient exchange + Adam as kernels over peer memory (here: two ranks emulated
+    in one process on two streams of one GPU, buffers wired by plain device pointers instead of CUDA IPC handles).
+    Replicas must end bit-identical (weights, target, tree); against the single-GPU full-batch step the weights agree to
+    1e-5 (the rank-order gradient sum differs from the full-batch summation order) and sampled indices are bit-exact."""
+    from multimodal_drl_rmc_b200 import _lib
+    from multimodal_drl_rmc_b200.parallel import ShardedLearner
+    W, cap = 2, 20000
+    full = PU.make_pair("PerDuelingDoubleDQNAgent", 14, B, cap, cap, seed=41)[1]
+    reps = [PU.make_pair("PerDuelingDoubleDQNAgent", 14, B, cap, cap, seed=41)[1] for _ in range(W)]
+    for ag in reps + [full]:
+        ag.learn_precision = precision
+    members = [ShardedLearner(ag, exchange="peer", rank=r, world=W) for r, ag in enumerate(reps)]
+    ShardedLearner.connect_same_process(members)
+    streams = [torch.cuda.Stream() for _ in range(W)]
+    rng = np.random.default_rng(3)
+    torch.cuda.synchronize()
+    for s in range(steps):
+        u = rng.random(B)
+        for ag in reps + [full]:
+            ag.step = 50 + s
+        full.learn(u=u, fuse_target_update=True)
+        full.update_target_network()
+        nodes_full = PU.gpu_out(full, "nodes", torch.int64)
+        g_full = full._lh.get_params(_lib.GRADS).cpu().numpy()
+        # one GPU hosts both ranks here: local gradients + publish of every rank first, then the waiting reduce kernels
+        for stage in (1, 2):
+            for m, st in zip(members, streams):
+                with torch.cuda.stream(st):
+                    m.learn(u=u, fuse_target_update=True, stages=stage)
+        torch.cuda.synchronize()
+        assert all(m.exchange_status() == 0 for m in members)
+        got = np.concatenate([PU.gpu_out(m.agent, "nodes", torch.int64)[: m.hi - m.lo] for m in members])
+        if s == 0:      # later steps start from weights/trees that differ from the full-batch run in the last bits
+            np.testing.assert_array_equal(got, nodes_full)
+        w = [PU.flat_sd(ag.online_network) for ag in reps]
+        np.testing.assert_array_equal(w[0], w[1])
+        np.testing.assert_array_equal(PU.flat_sd(reps[0].target_network), PU.flat_sd(reps[1].target_network))
+        t = [ag.replay_memory_buffer.replay_buffer.tree for ag in reps]
+        np.testing.assert_array_equal(t[0], t[1])
+        if s == 0:
+            assert abs(reps[0].last_loss() - full.last_loss()) / abs(full.last_loss()) < (1e-5 if precision == "fp32" else 1e-3)
+        if precision == "fp32" and s == 0:
+            w_full = PU.flat_sd(full.online_network)
+            well = np.abs(g_full) >= 1e-6
+            assert R.max_rel(np.where(well, w[0], w_full), w_full) < 1e-5
+            np.testing.assert_array_equal(t[0], full.replay_memory_buffer.replay_buffer.tree)
+            sa, sb = reps[0].replay_memory_buffer._ring.stats(), full.replay_memory_buffer._ring.stats()
+            assert (sa.max_priority, sa.min_priority, sa.total_priority) == (sb.max_priority, sb.min_priority, sb.total_priority)
