@@ -397,7 +397,7 @@ def run_sharded(args, wl, agent, rank, world, local):
         dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", local))
     agent.learn_precision = args.precision
     tc = args.precision == "bf16"
-    sl = ShardedLearner(agent)
+    sl = ShardedLearner(agent, exchange=args.exchange)
     B, K, W = wl["B"], args.steps, max(args.warmup, 3)
 
     def one_step():
@@ -428,8 +428,10 @@ def run_sharded(args, wl, agent, rank, world, local):
         line = {"metric": METRIC, "value": B * K / (ms * 1e-3), "unit": "transitions/s", "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16" if tc else "f32", "data": "synthetic",
                 "config": {"workload": wl["name"], "precision": args.precision, "batch": B, "replay_capacity": wl["cap"], "replay_size": wl["size"], "obs_dim": D,
-                           "parallelism": "dp%d: minibatch sharded, replicated replay/tree/weights, NCCL all-reduce of %d gradient floats per step"
-                                          % (world, int(agent._lh.output("grads_blob").numel())),
+                           "parallelism": "dp%d: minibatch sharded, replicated replay/tree/weights, %s of %d gradient floats per step"
+                                          % (world, "in-kernel rank-order reduce over NVLink peer memory fused with Adam (no library collective)"
+                                             if args.exchange == "peer" else "NCCL all-reduce", int(agent._lh.output("grads_blob").numel())),
+                           "exchange": args.exchange,
                            "l2": "inputs larger than L2 (144 MB replay + 200 MB step scratch)"},
                 "gpu_launches": int(_lib.lib().rmc_launch_count() - l0),
                 "replicas_identical": bool(float(lo) == float(hi)), "last_loss": float(loss.item()),
@@ -537,6 +539,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="per256", choices=sorted(WORKLOADS))
     ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"], help="large65536 only: learner arithmetic mode")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="large65536 only: gradient exchange (peer-memory kernels or NCCL)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary workloads")
     args = ap.parse_args()

@@ -96,6 +96,7 @@ struct rmc_learner {
   unsigned char* tc_packed_target = nullptr;
   __nv_bfloat16* tc_packed_bwd = nullptr;
   unsigned long long tc_bwd_version = 0;
+  unsigned long long target_version = 1, tc_target_version = 0;
   TcTrainBufs tct{};
   // act staging
   float* act_pin_obs = nullptr; long long* act_pin_out = nullptr; float* act_dev_obs = nullptr; long long* act_dev_out = nullptr;
@@ -617,6 +618,7 @@ extern "C" int32_t rmc_learner_set_params(rmc_learner_t* l, int32_t kind, const 
   k_params_scatter<<<blocks_for(n, 256), 256, 0, st>>>(l->blobs[kind], dsrc, l->map, n);
   RMC_KERNEL_OK();
   if (kind == RMC_ONLINE) ++l->online_version;
+  if (kind == RMC_TARGET) ++l->target_version;
   if (src_is_host) RMC_CUDA(cudaStreamSynchronize(st));
   return RMC_OK;
 }
@@ -771,6 +773,7 @@ static int32_t tc_train_setup(rmc_learner* l) {
   RMC_CUDA(cudaFuncSetAttribute(k_mlp_infer_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
   RMC_CUDA(cudaFuncSetAttribute(k_tc_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcBwdSmemBytes));
   RMC_CUDA(cudaFuncSetAttribute(k_tc_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes));
+  RMC_CUDA(cudaFuncSetAttribute(k_tc_bwd_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcBwdFusedSmemBytes));
   l->tct_ready = true;
   return RMC_OK;
 }
@@ -803,8 +806,11 @@ static int32_t step_tc(rmc_learner* l, rmc_replay* r, const rmc_step_args_t* a, 
     RMC_KERNEL_OK();
     l->tc_bwd_version = l->online_version;
   }
-  k_tc_pack<<<blocks_for(kH2 * kH1, 256), 256, 0, st>>>(l->blobs[RMC_TARGET], l->L, l->tc_packed_target);
-  RMC_KERNEL_OK();
+  if (l->tc_target_version != l->target_version) {
+    k_tc_pack<<<blocks_for(kH2 * kH1, 256), 256, 0, st>>>(l->blobs[RMC_TARGET], l->L, l->tc_packed_target);
+    RMC_KERNEL_OK();
+    l->tc_target_version = l->target_version;
+  }
   const long long n_tiles = (B + kTcRows - 1) / kTcRows;
   const unsigned grid = static_cast<unsigned>(std::min<long long>(n_tiles, l->num_sms));
   TcFwdExtra nx{};                 // s' rows: next_obs sits D floats into the gathered row
@@ -822,20 +828,31 @@ static int32_t step_tc(rmc_learner* l, rmc_replay* r, const rmc_step_args_t* a, 
   if (td_blocks > 1024) return fail(RMC_ERR_UNSUPPORTED, "tensor-core learner mode: batch above 262,144");
   k_tc_td<<<td_blocks, 256, 0, st>>>(l->ctx, S, T);
   RMC_KERNEL_OK();
-  k_tc_bwd<<<grid, kThreads, kTcBwdSmemBytes, st>>>(reinterpret_cast<const unsigned char*>(l->tc_packed_bwd), B, T);
-  RMC_KERNEL_OK();
-  const long long chunks = (B + kWgChunk - 1) / kWgChunk;
-  const int n_part = static_cast<int>(std::min<long long>(chunks, l->num_sms));
-  const long long rows_per_cta = ((chunks + n_part - 1) / n_part) * kWgChunk;
-  T.n_part = n_part;
-  k_tc_wgrad<<<n_part, kThreads, kWgSmemBytes, st>>>(l->ctx, B, rows_per_cta, T);
-  RMC_KERNEL_OK();
+  // backward: dgrad chain + weight gradients fused per 128-row tile (RMC_TC_BWD=split keeps the two-kernel form for A/B runs)
+  static const bool split_bwd = [] { const char* e = std::getenv("RMC_TC_BWD"); return e && std::strcmp(e, "split") == 0; }();
+  if (!split_bwd && l->L.D <= 15) {
+    T.n_part = static_cast<int>(grid);
+    k_tc_bwd_fused<<<grid, kThreads, kTcBwdFusedSmemBytes, st>>>(l->ctx, reinterpret_cast<const unsigned char*>(l->tc_packed_bwd), B, T);
+    RMC_KERNEL_OK();
+  } else {
+    k_tc_bwd<<<grid, kThreads, kTcBwdSmemBytes, st>>>(reinterpret_cast<const unsigned char*>(l->tc_packed_bwd), B, T);
+    RMC_KERNEL_OK();
+    const long long chunks = (B + kWgChunk - 1) / kWgChunk;
+    const int n_part = static_cast<int>(std::min<long long>(chunks, l->num_sms));
+    const long long rows_per_cta = ((chunks + n_part - 1) / n_part) * kWgChunk;
+    T.n_part = n_part;
+    k_tc_wgrad<<<n_part, kThreads, kWgSmemBytes, st>>>(l->ctx, B, rows_per_cta, T);
+    RMC_KERNEL_OK();
+  }
   l->epoch = (l->epoch >= 0x7fffffffu) ? 1u : l->epoch + 1u;
   S.epoch = l->epoch;
-  k_tc_reduce_adam<<<blocks_for(l->L.total, 256), 256, 0, st>>>(l->ctx, S, T, static_cast<int>(td_blocks));
+  // the Adam kernel refreshes the bf16 operand images element by element: no pack kernels on the next step
+  const TcPackOut P{l->tc_packed, l->tc_packed_bwd, l->tc_packed_target};
+  k_tc_reduce_adam<<<blocks_for(l->L.total, 128), 256, 0, st>>>(l->ctx, S, T, static_cast<int>(td_blocks), P);
   RMC_KERNEL_OK();
   l->loss_epoch = S.epoch;
-  if (a->phases & RMC_PH_ADAM) ++l->online_version;
+  if (a->phases & RMC_PH_ADAM) l->tc_packed_version = l->tc_bwd_version = ++l->online_version;
+  if (a->phases & (RMC_PH_POLYAK | RMC_PH_HARDSYNC)) l->tc_target_version = ++l->target_version;
   if ((a->phases & RMC_PH_PRIORITY) && l->spec.prioritized) {
     if (B <= kTreeCtaMax) {
       k_tree_update_small<<<1, kThreads, 0, st>>>(r->dev, C.nodes, nullptr, C.abs_td, C.pri, B, S.per_eps, S.per_alpha, S.per_pmax);
@@ -888,6 +905,7 @@ extern "C" int32_t rmc_learner_step(rmc_learner_t* l, rmc_replay_t* r, const rmc
   if (rows && phase_b) l->barrier_count = S.barrier_target;
   if ((a->phases & RMC_PH_FORWARD) && phase_b) l->loss_epoch = S.epoch;
   if (a->phases & RMC_PH_ADAM) ++l->online_version;
+  if (a->phases & (RMC_PH_POLYAK | RMC_PH_HARDSYNC)) ++l->target_version;
   if ((a->phases & RMC_PH_PRIORITY) && l->spec.prioritized && a->batch > kTreeCtaMax) {
     k_td_to_pri<<<blocks_for(a->batch, 256), 256, 0, st>>>(l->ctx.abs_td, l->ctx.pri, a->batch, S.per_eps, S.per_alpha, S.per_pmax);
     RMC_KERNEL_OK();
@@ -1039,10 +1057,18 @@ extern "C" int32_t rmc_learner_step_sharded(rmc_learner_t* l, rmc_replay_t* r, r
   S.epoch = l->epoch;
   const int param_blocks = static_cast<int>(blocks_for(l->L.total, 256));
   const int gather_blocks = per ? static_cast<int>(std::min<long long>(256, (Bg + 255) / 256)) : 0;
-  k_comm_reduce_adam<<<param_blocks + gather_blocks, 256, 0, st>>>(l->ctx, S, V, parity, c->epoch, param_blocks, c->g_nodes, c->g_td, per ? 1 : 0);
+  const bool images = l->tct_ready && l->tc_packed_version == l->online_version && l->tc_bwd_version == l->online_version &&
+                      l->tc_target_version == l->target_version;      // keep the bf16 operand images current (tensor-core mode)
+  const TcPackOut P{images ? l->tc_packed : nullptr, images ? l->tc_packed_bwd : nullptr, images ? l->tc_packed_target : nullptr};
+  k_comm_reduce_adam<<<param_blocks + gather_blocks, 256, 0, st>>>(l->ctx, S, V, parity, c->epoch, param_blocks, c->g_nodes, c->g_td, per ? 1 : 0, P);
   RMC_KERNEL_OK();
   l->loss_epoch = S.epoch;
   ++l->online_version;
+  if (a->phases & (RMC_PH_POLYAK | RMC_PH_HARDSYNC)) ++l->target_version;
+  if (images) {
+    l->tc_packed_version = l->tc_bwd_version = l->online_version;
+    if (a->phases & (RMC_PH_POLYAK | RMC_PH_HARDSYNC)) l->tc_target_version = l->target_version;
+  }
   // 4. PER: the full write-back of the GLOBAL batch on every replica, in global batch order (trees stay identical)
   if (per) {
     if (Bg <= kTreeCtaMax) {
@@ -1258,6 +1284,7 @@ extern "C" int32_t rmc_group_step(rmc_group_t* g, const rmc_step_args_t* a, rmc_
   for (int i = 0; i < g->n; ++i) {
     g->learners[i]->last_batch = a->batch;
     if (a->phases & RMC_PH_ADAM) ++g->learners[i]->online_version;
+    if (a->phases & (RMC_PH_POLYAK | RMC_PH_HARDSYNC)) ++g->learners[i]->target_version;
     if ((a->phases & RMC_PH_FORWARD) && phase_b) g->learners[i]->loss_epoch = S.epoch;
   }
   AgentCtx single = l0->ctx;

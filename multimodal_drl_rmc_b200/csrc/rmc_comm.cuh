@@ -14,6 +14,7 @@
 // which a peer sends after (stream order) its step-t reads completed.
 #pragma once
 #include "rmc_mlp.cuh"
+#include "rmc_tc_train.cuh"
 
 namespace rmc {
 
@@ -80,7 +81,7 @@ __global__ void __launch_bounds__(256) k_comm_publish(CommView V, int parity, un
 
 // blocks [0, param_blocks): parameters; the remaining blocks: (leaf, |td|) gather.
 __global__ void __launch_bounds__(256) k_comm_reduce_adam(AgentCtx C, StepScalars S, CommView V, int parity, unsigned epoch, int param_blocks,
-                                                          long long* __restrict__ g_nodes, float* __restrict__ g_td, int want_gather) {
+                                                          long long* __restrict__ g_nodes, float* __restrict__ g_td, int want_gather, TcPackOut P) {
   __shared__ int s_ok;
   unsigned* my_flags = reinterpret_cast<unsigned*>(V.base[V.rank]);
   if (threadIdx.x == 0) s_ok = 1;
@@ -106,7 +107,8 @@ __global__ void __launch_bounds__(256) k_comm_reduce_adam(AgentCtx C, StepScalar
       float g = 0.f;
       for (int r = 0; r < V.world; ++r) g += ld_sys_f32(reinterpret_cast<const float*>(comm_slot(V, r, parity)) + pi);
       C.grads[pi] = g;
-      adam_polyak_element(C, S, pi, g);
+      const float2 pt = adam_polyak_element(C, S, pi, g);
+      tc_pack_updated(L, S, pi, pt, P);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
       float loss = 0.f;

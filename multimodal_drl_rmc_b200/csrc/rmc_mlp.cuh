@@ -211,8 +211,10 @@ __device__ __forceinline__ ParamVals param_load(const AgentCtx& C, const StepSca
   x.t = (S.phases & 32) ? __ldcg(C.target + pi) : 0.f;
   return x;
 }
-__device__ __forceinline__ void param_apply(const AgentCtx& C, const StepScalars& S, int pi, float g, ParamVals x) {
+// returns (online weight after the step, target weight after the step -- meaningful only with POLYAK / HARDSYNC)
+__device__ __forceinline__ float2 param_apply(const AgentCtx& C, const StepScalars& S, int pi, float g, ParamVals x) {
   float p = x.p;
+  float tnew = x.t;
   if (S.phases & 16 /*ADAM*/) {
     float m = x.m, v = x.v;
     // Rounding sequence of torch 2.11's CPU kernels, found by bit-matching torch.optim.Adam
@@ -226,13 +228,16 @@ __device__ __forceinline__ void param_apply(const AgentCtx& C, const StepScalars
     C.adam_v[pi] = v;
   }
   if (S.phases & 32 /*POLYAK: dqn/agent.py:105-110, post-Adam weights*/) {
-    C.target[pi] = S.polyak_k * p + S.polyak_1mk * x.t;
+    tnew = S.polyak_k * p + S.polyak_1mk * x.t;
+    C.target[pi] = tnew;
   } else if (S.phases & 64 /*HARDSYNC: dqn/agent.py:102-103*/) {
+    tnew = p;
     C.target[pi] = p;
   }
+  return make_float2(p, tnew);
 }
-__device__ __forceinline__ void adam_polyak_element(const AgentCtx& C, const StepScalars& S, int pi, float g) {
-  param_apply(C, S, pi, g, param_load(C, S, pi));
+__device__ __forceinline__ float2 adam_polyak_element(const AgentCtx& C, const StepScalars& S, int pi, float g) {
+  return param_apply(C, S, pi, g, param_load(C, S, pi));
 }
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {

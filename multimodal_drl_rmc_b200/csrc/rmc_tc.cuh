@@ -200,24 +200,29 @@ __global__ void __launch_bounds__(kThreads, 1) k_mlp_infer_tc(const unsigned cha
   const uint32_t tD1 = tmem + 256 * g, tD2 = tD1, tD3 = tD1 + 128;
   const uint32_t id1 = tc_idesc_bf16(kTcRows, kH1), id2 = tc_idesc_bf16(kTcRows, kH2), id3 = tc_idesc_bf16(kTcRows, kTcNH);
   uint32_t phase = 0;
+  // the NEXT tile's input row is fetched into registers while this tile runs (the global-load latency of the tiny X tile
+  // would otherwise sit at the head of every tile's dependent MMA -> epilogue chain)
+  float xr[16];
+  auto load_row = [&](long long t) {
+    const long long i = t * kTcRows + gtid;
+#pragma unroll
+    for (int d = 0; d < 16; ++d) xr[d] = (t < n_tiles && i < n && d < D) ? __ldg(obs + i * X.row_stride + X.col_off + d) : 0.f;
+  };
+  load_row(blockIdx.x + static_cast<long long>(g) * gridDim.x);
   for (long long tile = blockIdx.x + static_cast<long long>(g) * gridDim.x; tile < n_tiles; tile += 2ll * gridDim.x) {
     // ---- X tile: fp32 obs -> bf16 canonical [128][16]; thread = row
     {
       const long long i = tile * kTcRows + gtid;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
-        float f[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int d = 8 * c + e;
-          f[e] = (i < n && d < D) ? __ldg(obs + i * X.row_stride + X.col_off + d) : 0.f;
-        }
         uint4 v;
-        v.x = pack_bf16x2(f[0], f[1]); v.y = pack_bf16x2(f[2], f[3]); v.z = pack_bf16x2(f[4], f[5]); v.w = pack_bf16x2(f[6], f[7]);
+        v.x = pack_bf16x2(xr[8 * c + 0], xr[8 * c + 1]); v.y = pack_bf16x2(xr[8 * c + 2], xr[8 * c + 3]);
+        v.z = pack_bf16x2(xr[8 * c + 4], xr[8 * c + 5]); v.w = pack_bf16x2(xr[8 * c + 6], xr[8 * c + 7]);
         *reinterpret_cast<uint4*>(sX + tc_off(gtid, 8 * c, kTcK1)) = v;
         if (X.Xb != nullptr && i < n) *reinterpret_cast<uint4*>(X.Xb + i * kTcK1 + 8 * c) = v;
       }
     }
+    load_row(tile + 2ll * gridDim.x);
     fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core's async proxy
     tc_fence_before();
     tc_group_sync(g);

@@ -41,6 +41,44 @@ struct TcTrainBufs {
   int n_part;
 };
 
+// The Adam / Polyak kernels of this mode refresh the bf16 operand images themselves, element by element, as they write
+// the fp32 master weights (no separate pack kernels on the step's critical path).  Null pointers = image not kept.
+struct TcPackOut {
+  unsigned char* fwd_online;       // k_tc_pack image of the online net (bf16 operands | fp32 biases)
+  __nv_bfloat16* bwd_online;       // k_tc_pack_bwd image of the online net
+  unsigned char* fwd_target;       // k_tc_pack image of the target net
+};
+__device__ __forceinline__ void tc_pack_param(const NetLayout& L, int pi, float val, unsigned char* fwd, __nv_bfloat16* bwd) {
+  __nv_bfloat16* w = reinterpret_cast<__nv_bfloat16*>(fwd);
+  float* bias = (fwd != nullptr) ? reinterpret_cast<float*>(fwd + kTcBf16Elems * 2) : nullptr;
+  const __nv_bfloat16 hv = __float2bfloat16_rn(val);
+  int r;
+  if ((r = pi - L.off_w0t) >= 0 && r < L.D * kH1) {
+    const int d = r / kH1, i = r - d * kH1;
+    if (w) w[kTcOffW0 + tc_off(i, d, kTcK1)] = hv;
+  } else if ((r = pi - L.off_b0) >= 0 && r < kH1) {
+    if (bias) bias[r] = val;
+  } else if ((r = pi - L.off_w2t) >= 0 && r < kH1 * kW2LD) {
+    const int k = r / kW2LD, j = r - k * kW2LD;
+    if (j < kH2) {
+      if (w) w[kTcOffW2 + tc_off(j, k, kH1)] = hv;
+      if (bwd) bwd[kTcBwdOffW2 + tc_off(k, j, kH2)] = hv;
+    }
+  } else if ((r = pi - L.off_b2) >= 0 && r < kH2) {
+    if (bias) bias[kH1 + r] = val;
+  } else if ((r = pi - L.off_wh) >= 0 && r < L.NH * kH2) {
+    const int a = r / kH2, j = r - a * kH2;
+    if (w) w[kTcOffWh + tc_off(a, j, kH2)] = hv;
+    if (bwd) bwd[kTcBwdOffWhT + tc_off(j, a, kTcNH)] = hv;
+  } else if ((r = pi - L.off_bh) >= 0 && r < L.NH) {
+    if (bias) bias[kH1 + kH2 + r] = val;
+  }
+}
+__device__ __forceinline__ void tc_pack_updated(const NetLayout& L, const StepScalars& S, int pi, float2 pt, const TcPackOut& P) {
+  if (S.phases & 16) tc_pack_param(L, pi, pt.x, P.fwd_online, P.bwd_online);
+  if ((S.phases & (32 | 64)) && P.fwd_target != nullptr) tc_pack_param(L, pi, pt.y, P.fwd_target, nullptr);
+}
+
 // ------------------------------------------------------------------------------------------ TD / head deltas
 __device__ __forceinline__ void heads_to_q(const float* __restrict__ h, int A, int dueling, float* q) {
   if (dueling) {
@@ -382,17 +420,288 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_wgrad(AgentCtx C, long long 
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
 }
 
-// fixed-order reduction of the per-CTA partials -> gradient blob -> Adam (+ Polyak); also the loss
-__global__ void __launch_bounds__(256) k_tc_reduce_adam(AgentCtx C, StepScalars S, TcTrainBufs T, int n_loss_parts) {
-  const int pi = blockIdx.x * 256 + threadIdx.x;
-  const NetLayout& L = C.L;
-  if (pi < L.total) {
-    float g = 0.f;
-    for (int c = 0; c < T.n_part; ++c) g += __ldcg(T.partials + static_cast<size_t>(c) * L.total + pi);
-    C.grads[pi] = g;
-    adam_polyak_element(C, S, pi, g);
+// ------------------------------------------------------------------------------------------ fused backward
+// k_tc_bwd_fused: dgrad chain AND weight gradients of a 128-row tile in one CTA; DZ1 / DZ2 never leave the SM and every
+// activation is read from HBM exactly once (H1 | H2 | X | DH: 52 MB per 65,536-row step instead of ~200 MB for the
+// k_tc_bwd + k_tc_wgrad pair).
+//
+// One shared-memory image serves BOTH operand roles.  A [128 b][C] tile is stored as 8x8 cores with element (b, c) at
+//   uoff(b, c) = ((c/8)*16 + b/8)*64 + (b%8)*8 + c%8 ;
+// read as a K-major operand (rows = b, K = c) its cores are LBO = 2048 B apart along K and SBO = 128 B apart along rows;
+// read as an MN-major operand (MN = c, K = b) they are LBO = 128 B apart along K and SBO = 2048 B apart along MN.  So the
+// DZ2 tile the first epilogue writes is the A operand of dz1 = DZ2.W2 (K-major) and the B operand of dW2 = H1^T.DZ2
+// (MN-major) without a second copy.
+//
+// Bias gradients ride on the tensor core: the staged X tile carries 1.0 in its spare column 15, so column 15 of
+// dW0 = DZ1^T.X is db0 and an extra N = 16 product DZ2^T.X yields db2 (dbh: 16 threads sum the 128x16 DH tile).
+//
+// TMEM columns: [0,128) scratch (dh2, dz1[:, :128], dz1[:, 128:]) | [128,384) dW2^T (two M halves) | [384,416) dW0 (two
+// halves) | [416,432) dWh | [432,448) DZ2^T.X.   Per tile: stage -> dh2 -> mask(H2) -> DZ2 -> dz1a -> mask(H1) -> DZ1a
+// (into the H2 buffer, free once dWh has completed) -> dW0a, dz1b -> DZ1b (into the DZ2 buffer, free once dW2 / dz1b
+// have completed) -> dW0b.
+__host__ __device__ __forceinline__ int uoff(int b, int c) { return (((c >> 3) << 4) + (b >> 3)) * 64 + (b & 7) * 8 + (c & 7); }
+constexpr int kBfOffDH = kTcBwdBytes;                               // byte offsets inside the dynamic shared memory
+constexpr int kBfOffX = kBfOffDH + kTcRows * kTcNH * 2;
+constexpr int kBfOffH2 = kBfOffX + kTcRows * kTcK1 * 2;             // later: DZ1 half a
+constexpr int kBfOffDZ2 = kBfOffH2 + kTcRows * kH2 * 2;             // later: DZ1 half b
+constexpr int kBfOffH1 = kBfOffDZ2 + kTcRows * kH2 * 2;
+constexpr int kBfOffBars = kBfOffH1 + kTcRows * kH1 * 2;
+constexpr int kTcBwdFusedSmemBytes = kBfOffBars + 8 * 8 + 16;       // 208,976 B
+
+// stage a [128][C] bf16 row-major global tile into the universal layout with cp.async; a warp covers 8 rows x 64 B
+// (whole 32-byte sectors from HBM; 4 cores x 128 contiguous bytes in shared memory, conflict-free)
+template <int C>
+__device__ __forceinline__ void bf_stage(__nv_bfloat16* dst, const __nv_bfloat16* __restrict__ src, long long row0, int rows) {
+  constexpr int C8 = C / 8;
+  for (int q = threadIdx.x; q < kTcRows * C8; q += kThreads) {
+    const int b_lo = q & 7, c_lo = (q >> 3) & 3, rem = q >> 5;
+    const int c_hi = rem % (C8 / 4), b_hi = rem / (C8 / 4);
+    const int b = b_hi * 8 + b_lo, c8 = c_hi * 4 + c_lo;
+    __nv_bfloat16* d = dst + uoff(b, 8 * c8);
+    if (b < rows) cp_async16(d, src + (row0 + b) * C + 8 * c8);
+    else *reinterpret_cast<uint4*>(d) = make_uint4(0, 0, 0, 0);
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
+}
+
+// epilogue: scratch columns [col0, col0+64) of this warp's 32 rows -> ReLU mask from `act` (universal tile, column offset
+// act_c0) -> bf16 -> universal tile `dst`
+__device__ __forceinline__ void bf_mask_epilogue(uint32_t tS, int q, int row, int col0, const __nv_bfloat16* __restrict__ act, int act_c0,
+                                                 __nv_bfloat16* __restrict__ dst) {
+#pragma unroll
+  for (int blk = 0; blk < 2; ++blk) {
+    const int col = col0 + 32 * blk;
+    uint32_t v[32];
+    tc_ld32(tS + (static_cast<uint32_t>(32 * q) << 16) + col, v);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const uint4 hq = *reinterpret_cast<const uint4*>(act + uoff(row, act_c0 + col + 8 * c));
+      const uint32_t hw[4] = {hq.x, hq.y, hq.z, hq.w};
+      float f[8];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {     // bf16 > 0  <=>  sign clear and magnitude bits non-zero
+        const uint32_t lo = hw[e] & 0xffffu, hi = hw[e] >> 16;
+        f[2 * e] = (lo != 0u && lo < 0x8000u) ? __uint_as_float(v[8 * c + 2 * e]) : 0.f;
+        f[2 * e + 1] = (hi != 0u && hi < 0x8000u) ? __uint_as_float(v[8 * c + 2 * e + 1]) : 0.f;
+      }
+      uint4 pk;
+      pk.x = pack_bf16x2(f[0], f[1]); pk.y = pack_bf16x2(f[2], f[3]); pk.z = pack_bf16x2(f[4], f[5]); pk.w = pack_bf16x2(f[6], f[7]);
+      *reinterpret_cast<uint4*>(dst + uoff(row, col + 8 * c)) = pk;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) k_tc_bwd_fused(AgentCtx C, const unsigned char* __restrict__ packed_bwd, long long n, TcTrainBufs T) {
+  extern __shared__ __align__(128) unsigned char tsm[];
+  const __nv_bfloat16* sW = reinterpret_cast<const __nv_bfloat16*>(tsm);          // Wh^T | W2 (K-major, packed by k_tc_pack_bwd)
+  __nv_bfloat16* sDH = reinterpret_cast<__nv_bfloat16*>(tsm + kBfOffDH);
+  __nv_bfloat16* sX = reinterpret_cast<__nv_bfloat16*>(tsm + kBfOffX);
+  __nv_bfloat16* sH2 = reinterpret_cast<__nv_bfloat16*>(tsm + kBfOffH2);
+  __nv_bfloat16* sDZ2 = reinterpret_cast<__nv_bfloat16*>(tsm + kBfOffDZ2);
+  __nv_bfloat16* sH1 = reinterpret_cast<__nv_bfloat16*>(tsm + kBfOffH1);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tsm + kBfOffBars);                 // [0] weights, [1..5] MMA stages A..E
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const NetLayout& L = C.L;
+  const long long n_tiles = (n + kTcRows - 1) / kTcRows;
+  float* part = T.partials + static_cast<size_t>(blockIdx.x) * L.total;
+  if (tid == 0) {
+    for (int b = 0; b < 6; ++b) mbar_init(bars + b, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tS = tmem, tW2 = tmem + 128, tW0 = tmem + 384, tWh = tmem + 416, tB2 = tmem + 432;
+  if (tid == 0) {
+    mbar_expect_tx(bars + 0, kTcBwdBytes);
+    bulk_g2s(tsm, packed_bwd, kTcBwdBytes, bars + 0);
+  }
+  const uint32_t idK_128 = tc_idesc_bf16(kTcRows, 128);                         // K-major A and B, N = 128
+  const uint32_t idMN_128 = tc_idesc_bf16_mn(128, 128), idMN_16 = tc_idesc_bf16_mn(128, 16);
+  constexpr uint32_t kUL = 2048, kUS = 128;                                     // universal tile: K-major (LBO, SBO) = (2048, 128); MN-major = (128, 2048)
+  const int q = warp & 3, half = warp >> 2;
+  const int row = 32 * q + lane;
+  float dbh = 0.f;                     // threads 0..15: bias gradient of head column tid
+  uint32_t phase = 0;
+  bool first = true;
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const long long row0 = tile * kTcRows;
+    const int rows = static_cast<int>(min(static_cast<long long>(kTcRows), n - row0));
+    // ---- S0: stage DH, X (register path: X gets 1.0 in column 15), H2, H1
+    bf_stage<kH2>(sH2, T.H2b, row0, rows);
+    bf_stage<kH1>(sH1, T.H1b, row0, rows);
+    {
+      const int b = tid >> 1, c8 = tid & 1;
+      uint4 dh = make_uint4(0, 0, 0, 0), x = make_uint4(0, 0, 0, 0);
+      if (b < rows) {
+        dh = *reinterpret_cast<const uint4*>(T.DHb + (row0 + b) * kTcNH + 8 * c8);
+        x = *reinterpret_cast<const uint4*>(T.Xb + (row0 + b) * kTcK1 + 8 * c8);
+        if (c8 == 1) x.w = (x.w & 0xffffu) | 0x3f800000u;      // element 15 = bf16(1.0): bias gradients as an extra GEMM column
+      }
+      *reinterpret_cast<uint4*>(sDH + uoff(b, 8 * c8)) = dh;
+      *reinterpret_cast<uint4*>(sX + uoff(b, 8 * c8)) = x;
+    }
+    cp_async_wait_all();
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (first) mbar_wait(bars + 0, 0);
+    const uint32_t acc = first ? 0u : 1u;
+    // ---- S1: dh2 = DH . Wh (scratch), dWh += H2^T . DH
+    if (tid == 0) {
+      tc_fence_after();
+      tc_mma_bf16(tS, tc_smem_desc(sDH, kUL, kUS), tc_smem_desc(sW + kTcBwdOffWhT, 128, (kTcNH / 8) * 128), idK_128, 0u);
+      tc_commit(bars + 1);
+      const uint64_t aH2 = tc_smem_desc(sH2, kUS, kUL), bDH = tc_smem_desc(sDH, kUS, kUL);
+#pragma unroll
+      for (int ks = 0; ks < kTcRows / 16; ++ks) tc_mma_bf16(tWh, aH2 + 16u * ks, bDH + 16u * ks, idMN_16, (ks > 0) ? 1u : acc);
+    }
+    if (tid < kTcNH) {                 // dbh: column sums of the staged DH tile
+      float s = 0.f;
+      for (int b = 0; b < rows; ++b) s += __bfloat162float(sDH[uoff(b, tid)]);
+      dbh += s;
+    }
+    mbar_wait(bars + 1, phase);
+    tc_fence_after();
+    // ---- S2: DZ2 = dh2 (.) [H2 > 0]
+    bf_mask_epilogue(tS, q, row, 64 * half, sH2, 0, sDZ2);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    // ---- S3: dz1[:, :128] = DZ2 . W2[:128] (scratch); dW2 += H1^T . DZ2 (two M halves); db2 column via DZ2^T . X
+    if (tid == 0) {
+      tc_fence_after();
+      const uint64_t aDZ2k = tc_smem_desc(sDZ2, kUL, kUS), bW2 = tc_smem_desc(sW + kTcBwdOffW2, 128, (kH2 / 8) * 128);
+#pragma unroll
+      for (int k = 0; k < kH2 / 16; ++k) tc_mma_bf16(tS, aDZ2k + 256u * k, bW2 + 16u * k, idK_128, k > 0 ? 1u : 0u);
+      tc_commit(bars + 2);
+      const uint64_t aH1 = tc_smem_desc(sH1, kUS, kUL), aH1b = tc_smem_desc(sH1 + uoff(0, 128), kUS, kUL);
+      const uint64_t bDZ2 = tc_smem_desc(sDZ2, kUS, kUL), bX = tc_smem_desc(sX, kUS, kUL);
+#pragma unroll
+      for (int ks = 0; ks < kTcRows / 16; ++ks) {
+        const uint32_t a2 = (ks > 0) ? 1u : acc;
+        tc_mma_bf16(tW2, aH1 + 16u * ks, bDZ2 + 16u * ks, idMN_128, a2);
+        tc_mma_bf16(tW2 + 128, aH1b + 16u * ks, bDZ2 + 16u * ks, idMN_128, a2);
+        tc_mma_bf16(tB2, bDZ2 + 16u * ks, bX + 16u * ks, idMN_16, a2);
+      }
+    }
+    mbar_wait(bars + 2, phase);        // dz1a done; the commit also covers dWh -> the H2 buffer is free
+    tc_fence_after();
+    // ---- S4: DZ1[:, :128] = dz1a (.) [H1[:, :128] > 0]  -> H2 buffer
+    bf_mask_epilogue(tS, q, row, 64 * half, sH1, 0, sH2);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    // ---- S5: dW0[:128] += DZ1a^T . X ; dz1[:, 128:] = DZ2 . W2[128:]
+    if (tid == 0) {
+      tc_fence_after();
+      const uint64_t aZ = tc_smem_desc(sH2, kUS, kUL), bX = tc_smem_desc(sX, kUS, kUL);
+#pragma unroll
+      for (int ks = 0; ks < kTcRows / 16; ++ks) tc_mma_bf16(tW0, aZ + 16u * ks, bX + 16u * ks, idMN_16, (ks > 0) ? 1u : acc);
+      const uint64_t aDZ2k = tc_smem_desc(sDZ2, kUL, kUS), bW2 = tc_smem_desc(sW + kTcBwdOffW2 + tc_off(128, 0, kH2), 128, (kH2 / 8) * 128);
+#pragma unroll
+      for (int k = 0; k < kH2 / 16; ++k) tc_mma_bf16(tS, aDZ2k + 256u * k, bW2 + 16u * k, idK_128, k > 0 ? 1u : 0u);
+      tc_commit(bars + 3);
+    }
+    mbar_wait(bars + 3, phase);        // dz1b done; covers dW2 / db2 / dz1a / dW0a -> the DZ2 buffer is free
+    tc_fence_after();
+    // ---- S6: DZ1[:, 128:] -> DZ2 buffer
+    bf_mask_epilogue(tS, q, row, 64 * half, sH1, 128, sDZ2);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    // ---- S7: dW0[128:] += DZ1b^T . X
+    if (tid == 0) {
+      tc_fence_after();
+      const uint64_t aZ = tc_smem_desc(sDZ2, kUS, kUL), bX = tc_smem_desc(sX, kUS, kUL);
+#pragma unroll
+      for (int ks = 0; ks < kTcRows / 16; ++ks) tc_mma_bf16(tW0 + 16, aZ + 16u * ks, bX + 16u * ks, idMN_16, (ks > 0) ? 1u : acc);
+      tc_commit(bars + 4);
+    }
+    mbar_wait(bars + 4, phase);        // every operand buffer may be restaged
+    tc_fence_after();
+    __syncthreads();
+    phase ^= 1u;
+    first = false;
+  }
+  // ---- accumulators -> this CTA's partial gradient blob (device parameter layout)
+  for (int mh = 0; mh < 2; ++mh) {            // dW2^T rows k = 128*mh + row, this warp's 64 columns j
+    const int k = 128 * mh + row;
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      const int j0 = 64 * half + 32 * b;
+      uint32_t v[32];
+      tc_ld32(tW2 + 128 * mh + (static_cast<uint32_t>(32 * q) << 16) + j0, v);
+#pragma unroll
+      for (int e = 0; e < 32; e += 4)
+        *reinterpret_cast<float4*>(part + L.off_w2t + k * kW2LD + j0 + e) =
+            make_float4(__uint_as_float(v[e]), __uint_as_float(v[e + 1]), __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
+    }
+  }
+  {   // dW0^T[d][i] and db0[i] (column 15): half h handles i = 128*h + row
+    uint32_t v[16];
+    tc_ld16(tW0 + 16 * half + (static_cast<uint32_t>(32 * q) << 16), v);
+    const int i = 128 * half + row;
+#pragma unroll
+    for (int d = 0; d < 15; ++d)
+      if (d < L.D) part[L.off_w0t + d * kH1 + i] = __uint_as_float(v[d]);
+    part[L.off_b0 + i] = __uint_as_float(v[15]);
+  }
+  if (half == 0) {   // dWh[a][j], j = row
+    uint32_t v[16];
+    tc_ld16(tWh + (static_cast<uint32_t>(32 * q) << 16), v);
+#pragma unroll
+    for (int a = 0; a < 16; ++a)
+      if (a < L.NH) part[L.off_wh + a * kH2 + row] = __uint_as_float(v[a]);
+  } else {           // db2[j] = column 15 of DZ2^T . X
+    uint32_t v[16];
+    tc_ld16(tB2 + (static_cast<uint32_t>(32 * q) << 16), v);
+    part[L.off_b2 + row] = __uint_as_float(v[15]);
+  }
+  if (tid < L.NH) part[L.off_bh + tid] = dbh;
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+
+// fixed-order reduction of the per-CTA partials -> gradient blob -> Adam (+ Polyak) -> refreshed bf16 images; also the loss.
+// A block owns 128 consecutive parameters: warp w sums partials w, w+8, ... with float4 loads (512 contiguous bytes per
+// warp load), the eight warp sums are combined in warp order through shared memory.
+__global__ void __launch_bounds__(256) k_tc_reduce_adam(AgentCtx C, StepScalars S, TcTrainBufs T, int n_loss_parts, TcPackOut P) {
+  __shared__ float4 s_sum[8][32];
+  const NetLayout& L = C.L;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int p4 = blockIdx.x * 32 + lane;                 // float4 index
+  const int n4 = L.total >> 2;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (p4 < n4) {
+    const float4* src = reinterpret_cast<const float4*>(T.partials) + p4;
+#pragma unroll 4
+    for (int c = warp; c < T.n_part; c += 8) {
+      const float4 v = __ldcg(src + static_cast<size_t>(c) * n4);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+  }
+  s_sum[warp][lane] = acc;
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int l4 = threadIdx.x >> 2, e = threadIdx.x & 3;
+    const int pi = (blockIdx.x * 32 + l4) * 4 + e;
+    if (pi < L.total) {
+      float g = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) g += reinterpret_cast<const float*>(&s_sum[w][l4])[e];
+      C.grads[pi] = g;
+      const float2 pt = adam_polyak_element(C, S, pi, g);
+      tc_pack_updated(L, S, pi, pt, P);
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 255) {
     float s = 0.f;
     for (int c = 0; c < n_loss_parts; ++c) s += __ldcg(C.loss_part + c);
     const float loss = s / static_cast<float>(S.Bglobal);
