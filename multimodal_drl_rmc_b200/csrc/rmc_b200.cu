@@ -773,6 +773,7 @@ static int32_t tc_train_setup(rmc_learner* l) {
   RMC_CUDA(cudaFuncSetAttribute(k_mlp_infer_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
   RMC_CUDA(cudaFuncSetAttribute(k_tc_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcBwdSmemBytes));
   RMC_CUDA(cudaFuncSetAttribute(k_tc_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes));
+  RMC_CUDA(cudaFuncSetAttribute(k_tc_fwd3, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
   RMC_CUDA(cudaFuncSetAttribute(k_tc_bwd_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcBwdFusedSmemBytes));
   l->tct_ready = true;
   return RMC_OK;
@@ -813,20 +814,26 @@ static int32_t step_tc(rmc_learner* l, rmc_replay* r, const rmc_step_args_t* a, 
   }
   const long long n_tiles = (B + kTcRows - 1) / kTcRows;
   const unsigned grid = static_cast<unsigned>(std::min<long long>(n_tiles, l->num_sms));
-  TcFwdExtra nx{};                 // s' rows: next_obs sits D floats into the gathered row
-  nx.row_stride = l->rf; nx.col_off = l->L.D;
-  k_mlp_infer_tc<<<grid, kThreads, kTcSmemBytes, st>>>(l->tc_packed, l->L.D, l->L.A, l->L.NH, l->L.dueling, C.X, B, nullptr, T.heads_n, 3, nx);
-  RMC_KERNEL_OK();
-  k_mlp_infer_tc<<<grid, kThreads, kTcSmemBytes, st>>>(l->tc_packed_target, l->L.D, l->L.A, l->L.NH, l->L.dueling, C.X, B, nullptr, T.heads_t, 3, nx);
-  RMC_KERNEL_OK();
-  TcFwdExtra sx{};                 // s rows, keeping the bf16 activations for the backward kernels
-  sx.row_stride = l->rf; sx.col_off = 0; sx.Xb = T.Xb; sx.H1b = T.H1b; sx.H2b = T.H2b;
-  k_mlp_infer_tc<<<grid, kThreads, kTcSmemBytes, st>>>(l->tc_packed, l->L.D, l->L.A, l->L.NH, l->L.dueling, C.X, B, nullptr, T.heads_s, 3, sx);
+  // the three forwards in ONE launch: online(s'), target(s'), online(s) (+ saved bf16 activations) on disjoint CTA ranges
+  TcFwdJobs J{};
+  J.j[0].packed = l->tc_packed;        J.j[0].heads_out = T.heads_n;
+  J.j[1].packed = l->tc_packed_target; J.j[1].heads_out = T.heads_t;
+  J.j[2].packed = l->tc_packed;        J.j[2].heads_out = T.heads_s;
+  J.j[0].X.row_stride = J.j[1].X.row_stride = J.j[2].X.row_stride = l->rf;
+  J.j[0].X.col_off = J.j[1].X.col_off = l->L.D;      // s' rows: next_obs sits D floats into the gathered row
+  J.j[2].X.col_off = 0; J.j[2].X.Xb = T.Xb; J.j[2].X.H1b = T.H1b; J.j[2].X.H2b = T.H2b;
+  int c0, c2;
+  if (3 * n_tiles <= l->num_sms) { c0 = c2 = static_cast<int>(n_tiles); }
+  else { c0 = std::max(1, (l->num_sms * 2) / 7); c2 = l->num_sms - 2 * c0; }   // the s pass also stores activations: ~1.5x the work
+  J.j[0].cta_begin = 0;      J.j[0].cta_count = c0;
+  J.j[1].cta_begin = c0;     J.j[1].cta_count = c0;
+  J.j[2].cta_begin = 2 * c0; J.j[2].cta_count = c2;
+  k_tc_fwd3<<<2 * c0 + c2, kThreads, kTcSmemBytes, st>>>(J, l->L.D, l->L.A, l->L.NH, l->L.dueling, C.X, B);
   RMC_KERNEL_OK();
   l->ctx.rp = r->dev;
-  const unsigned td_blocks = blocks_for(B, 256);
-  if (td_blocks > 1024) return fail(RMC_ERR_UNSUPPORTED, "tensor-core learner mode: batch above 262,144");
-  k_tc_td<<<td_blocks, 256, 0, st>>>(l->ctx, S, T);
+  const unsigned td_blocks = blocks_for(B, kTdThreads);
+  if (td_blocks > 1024) return fail(RMC_ERR_UNSUPPORTED, "tensor-core learner mode: batch above 131,072");
+  k_tc_td<<<td_blocks, kTdThreads, 0, st>>>(l->ctx, S, T);
   RMC_KERNEL_OK();
   // backward: dgrad chain + weight gradients fused per 128-row tile (RMC_TC_BWD=split keeps the two-kernel form for A/B runs)
   static const bool split_bwd = [] { const char* e = std::getenv("RMC_TC_BWD"); return e && std::strcmp(e, "split") == 0; }();

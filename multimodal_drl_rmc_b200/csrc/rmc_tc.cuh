@@ -158,10 +158,9 @@ struct TcFwdExtra {
   __nv_bfloat16* H1b;
   __nv_bfloat16* H2b;
 };
-__global__ void __launch_bounds__(kThreads, 1) k_mlp_infer_tc(const unsigned char* __restrict__ packed, int D, int A, int NH, int dueling,
-                                                              const float* __restrict__ obs, long long n,
-                                                              long long* __restrict__ actions, float* __restrict__ heads_out, int mode,
-                                                              TcFwdExtra X) {
+__device__ __forceinline__ void tc_fwd_body(const unsigned char* __restrict__ packed, int D, int A, int NH, int dueling,
+                                            const float* __restrict__ obs, long long n, long long* __restrict__ actions,
+                                            float* __restrict__ heads_out, int mode, const TcFwdExtra& X, int bid, int nb) {
   extern __shared__ __align__(128) unsigned char tsm[];
   __nv_bfloat16* sWts = reinterpret_cast<__nv_bfloat16*>(tsm);                 // packed W0 | W2 | Wh
   float* sBias = reinterpret_cast<float*>(tsm + kTcBf16Elems * 2);             // b0 | b2 | bh
@@ -172,8 +171,6 @@ __global__ void __launch_bounds__(kThreads, 1) k_mlp_infer_tc(const unsigned cha
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long n_tiles = (n + kTcRows - 1) / kTcRows;
-  if (blockIdx.x >= n_tiles) return;
-
   if (tid == 0) {
     for (int b = 0; b < 7; ++b) mbar_init(bars + b, 1);
     fence_mbar_init();
@@ -208,8 +205,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_mlp_infer_tc(const unsigned cha
 #pragma unroll
     for (int d = 0; d < 16; ++d) xr[d] = (t < n_tiles && i < n && d < D) ? __ldg(obs + i * X.row_stride + X.col_off + d) : 0.f;
   };
-  load_row(blockIdx.x + static_cast<long long>(g) * gridDim.x);
-  for (long long tile = blockIdx.x + static_cast<long long>(g) * gridDim.x; tile < n_tiles; tile += 2ll * gridDim.x) {
+  load_row(bid + static_cast<long long>(g) * nb);
+  for (long long tile = bid + static_cast<long long>(g) * nb; tile < n_tiles; tile += 2ll * nb) {
     // ---- X tile: fp32 obs -> bf16 canonical [128][16]; thread = row
     {
       const long long i = tile * kTcRows + gtid;
@@ -222,7 +219,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_mlp_infer_tc(const unsigned cha
         if (X.Xb != nullptr && i < n) *reinterpret_cast<uint4*>(X.Xb + i * kTcK1 + 8 * c) = v;
       }
     }
-    load_row(tile + 2ll * gridDim.x);
+    load_row(tile + 2ll * nb);
     fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core's async proxy
     tc_fence_before();
     tc_group_sync(g);
@@ -302,6 +299,29 @@ __global__ void __launch_bounds__(kThreads, 1) k_mlp_infer_tc(const unsigned cha
   tc_fence_before();
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+
+__global__ void __launch_bounds__(kThreads, 1) k_mlp_infer_tc(const unsigned char* __restrict__ packed, int D, int A, int NH, int dueling,
+                                                              const float* __restrict__ obs, long long n,
+                                                              long long* __restrict__ actions, float* __restrict__ heads_out, int mode,
+                                                              TcFwdExtra X) {
+  tc_fwd_body(packed, D, A, NH, dueling, obs, n, actions, heads_out, mode, X, blockIdx.x, gridDim.x);
+}
+
+// The three forward passes of a learner step (online(s'), target(s'), online(s) + saved activations) in ONE launch: each
+// job owns a contiguous range of CTAs, which stage that job's weight image and walk that job's tiles.
+struct TcFwdJob {
+  const unsigned char* packed;
+  float* heads_out;
+  TcFwdExtra X;
+  int cta_begin, cta_count;
+};
+struct TcFwdJobs { TcFwdJob j[3]; };
+__global__ void __launch_bounds__(kThreads, 1) k_tc_fwd3(TcFwdJobs J, int D, int A, int NH, int dueling, const float* __restrict__ rows, long long n) {
+  const int b = blockIdx.x;
+  const int k = (b >= J.j[2].cta_begin) ? 2 : (b >= J.j[1].cta_begin) ? 1 : 0;
+  const TcFwdJob& job = J.j[k];
+  tc_fwd_body(job.packed, D, A, NH, dueling, rows, n, nullptr, job.heads_out, 3, job.X, b - job.cta_begin, job.cta_count);
 }
 
 constexpr int kTcSmemBytes = kTcBlobBytes + 2 * (kTcRows * kTcK1 + kTcRows * kH1) * 2 + 8 * 8 + 16;

@@ -80,20 +80,34 @@ __device__ __forceinline__ void tc_pack_updated(const NetLayout& L, const StepSc
 }
 
 // ------------------------------------------------------------------------------------------ TD / head deltas
-__device__ __forceinline__ void heads_to_q(const float* __restrict__ h, int A, int dueling, float* q) {
+// raw heads [16] -> Q values q[0..A): fully unrolled with predicates so the arrays stay in registers (A <= 15)
+__device__ __forceinline__ void heads_to_q(const float (&h)[16], int A, int dueling, float (&q)[16]) {
   if (dueling) {
     float sum = 0.f;
-    for (int a = 0; a < A; ++a) sum += h[1 + a];
+#pragma unroll
+    for (int a = 0; a < 15; ++a) sum += (a < A) ? h[1 + a] : 0.f;
     const float mean = sum / static_cast<float>(A);
-    for (int a = 0; a < A; ++a) q[a] = h[0] + (h[1 + a] - mean);
+#pragma unroll
+    for (int a = 0; a < 15; ++a) q[a] = h[0] + (h[1 + a] - mean);
+    q[15] = 0.f;
   } else {
-    for (int a = 0; a < A; ++a) q[a] = h[a];
+#pragma unroll
+    for (int a = 0; a < 16; ++a) q[a] = h[a];
   }
 }
+__device__ __forceinline__ int argmax_first16(const float (&q)[16], int A) {
+  int best = 0;
+  float bv = q[0];
+#pragma unroll
+  for (int a = 1; a < 15; ++a)
+    if (a < A && q[a] > bv) { bv = q[a]; best = a; }
+  return best;
+}
 
-__global__ void __launch_bounds__(256) k_tc_td(AgentCtx C, StepScalars S, TcTrainBufs T) {
-  __shared__ float s_part[8];
-  const long long i = blockIdx.x * 256ll + threadIdx.x;
+constexpr int kTdThreads = 128;
+__global__ void __launch_bounds__(kTdThreads) k_tc_td(AgentCtx C, StepScalars S, TcTrainBufs T) {
+  __shared__ float s_part[kTdThreads / 32];
+  const long long i = blockIdx.x * static_cast<long long>(kTdThreads) + threadIdx.x;
   const NetLayout& L = C.L;
   const bool per = S.prioritized != 0;
   float lterm = 0.f;
@@ -109,21 +123,22 @@ __global__ void __launch_bounds__(256) k_tc_td(AgentCtx C, StepScalars S, TcTrai
     heads_to_q(hn, L.A, L.dueling, qn);
     heads_to_q(ht, L.A, L.dueling, qt);
     heads_to_q(hs, L.A, L.dueling, qs);
-    float qsel;
+    float qsel = qt[0];
     if (S.double_dqn) {
-      const int astar = argmax_first(qn, L.A);
-      qsel = qt[0];
-      for (int a = 1; a < L.A; ++a) qsel = (a == astar) ? qt[a] : qsel;
+      const int astar = argmax_first16(qn, L.A);
+#pragma unroll
+      for (int a = 1; a < 15; ++a) qsel = (a == astar) ? qt[a] : qsel;
     } else {
-      qsel = qt[0];
-      for (int a = 1; a < L.A; ++a) qsel = fmaxf(qsel, qt[a]);
+#pragma unroll
+      for (int a = 1; a < 15; ++a) qsel = (a < L.A) ? fmaxf(qsel, qt[a]) : qsel;
     }
     const int act = __float_as_int(__ldcg(C.X + i * rf + 2 * L.D));
     const float rew = __ldcg(C.X + i * rf + 2 * L.D + 1), done = __ldcg(C.X + i * rf + 2 * L.D + 2);
     const float w = per ? C.is_w[i] : 1.f;
     const float y = rew + ((1.f - done) * S.gamma) * qsel;
     float q_sa = qs[0];
-    for (int a = 1; a < L.A; ++a) q_sa = (a == act) ? qs[a] : q_sa;
+#pragma unroll
+    for (int a = 1; a < 15; ++a) q_sa = (a == act) ? qs[a] : q_sa;
     const float delta = q_sa - y;
     const float atd = fabsf(y - q_sa);
     const float z = fabsf(delta);
@@ -138,17 +153,13 @@ __global__ void __launch_bounds__(256) k_tc_td(AgentCtx C, StepScalars S, TcTrai
     if (L.dueling) {
       const float mean = g / static_cast<float>(L.A);
       dh[0] = g;
-      for (int a = 0; a < L.A; ++a) dh[1 + a] = ((a == act) ? g : 0.f) - mean;
-    } else {
-      for (int a = 0; a < L.A; ++a) dh[a] = (a == act) ? g : 0.f;
-    }
 #pragma unroll
-    for (int a = 0; a < 16; a += 4) {
-      *reinterpret_cast<float4*>(C.DH + i * kQLD + a) = make_float4(dh[a], dh[a + 1], dh[a + 2], dh[a + 3]);
-      *reinterpret_cast<float4*>(C.QT + i * kQLD + a) = make_float4(qt[a], qt[a + 1], qt[a + 2], qt[a + 3]);
-      *reinterpret_cast<float4*>(C.QN + i * kQLD + a) = make_float4(qn[a], qn[a + 1], qn[a + 2], qn[a + 3]);
-      *reinterpret_cast<float4*>(C.Q + i * kQLD + a) = make_float4(qs[a], qs[a + 1], qs[a + 2], qs[a + 3]);
+      for (int a = 0; a < 15; ++a) dh[1 + a] = (a < L.A) ? ((a == act) ? g : 0.f) - mean : 0.f;
+    } else {
+#pragma unroll
+      for (int a = 0; a < 15; ++a) dh[a] = (a < L.A && a == act) ? g : 0.f;
     }
+    // (this mode keeps the per-sample scalars only; the fp32 Q / delta rows of the exact path are not materialised)
     uint4 lo, hi;
     lo.x = pack_bf16x2(dh[0], dh[1]); lo.y = pack_bf16x2(dh[2], dh[3]); lo.z = pack_bf16x2(dh[4], dh[5]); lo.w = pack_bf16x2(dh[6], dh[7]);
     hi.x = pack_bf16x2(dh[8], dh[9]); hi.y = pack_bf16x2(dh[10], dh[11]); hi.z = pack_bf16x2(dh[12], dh[13]); hi.w = pack_bf16x2(dh[14], dh[15]);
@@ -162,7 +173,7 @@ __global__ void __launch_bounds__(256) k_tc_td(AgentCtx C, StepScalars S, TcTrai
   __syncthreads();
   if (threadIdx.x == 0) {
     float s = 0.f;
-    for (int w = 0; w < 8; ++w) s += s_part[w];
+    for (int w = 0; w < kTdThreads / 32; ++w) s += s_part[w];
     C.loss_part[blockIdx.x] = s;
   }
 }
