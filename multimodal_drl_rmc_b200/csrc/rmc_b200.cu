@@ -763,16 +763,13 @@ static int32_t tc_train_setup(rmc_learner* l) {
   if ((e = owned_alloc(l, &T.heads_n, B * kTcNH))) return e;
   if ((e = owned_alloc(l, &T.heads_t, B * kTcNH))) return e;
   if ((e = owned_alloc(l, &T.heads_s, B * kTcNH))) return e;
-  if ((e = owned_alloc(l, &T.Xb, B * kTcK1))) return e;
-  if ((e = owned_alloc(l, &T.H1b, B * kH1))) return e;
-  if ((e = owned_alloc(l, &T.H2b, B * kH2))) return e;
-  if ((e = owned_alloc(l, &T.DZ2b, B * kH2))) return e;
-  if ((e = owned_alloc(l, &T.DZ1b, B * kH1))) return e;
-  if ((e = owned_alloc(l, &T.DHb, B * kTcNH))) return e;
+  const size_t Bt = ((B + kTcRows - 1) / kTcRows) * kTcRows;        // whole 128-row tile images
+  if ((e = owned_alloc(l, &T.Xb, Bt * kTcK1))) return e;
+  if ((e = owned_alloc(l, &T.H1b, Bt * kH1))) return e;
+  if ((e = owned_alloc(l, &T.H2b, Bt * kH2))) return e;
+  if ((e = owned_alloc(l, &T.DHb, Bt * kTcNH))) return e;
   if ((e = owned_alloc(l, &T.partials, static_cast<size_t>(l->num_sms) * l->L.total))) return e;
   RMC_CUDA(cudaFuncSetAttribute(k_mlp_infer_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
-  RMC_CUDA(cudaFuncSetAttribute(k_tc_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcBwdSmemBytes));
-  RMC_CUDA(cudaFuncSetAttribute(k_tc_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes));
   RMC_CUDA(cudaFuncSetAttribute(k_tc_fwd3, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
   RMC_CUDA(cudaFuncSetAttribute(k_tc_bwd_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcBwdFusedSmemBytes));
   l->tct_ready = true;
@@ -780,7 +777,7 @@ static int32_t tc_train_setup(rmc_learner* l) {
 }
 
 static int32_t step_tc(rmc_learner* l, rmc_replay* r, const rmc_step_args_t* a, StepScalars& S, cudaStream_t st) {
-  if (l->L.D > kTcK1) return fail(RMC_ERR_UNSUPPORTED, "tensor-core learner mode: obs_dim must be <= 16");
+  if (l->L.D > kTcK1 - 1) return fail(RMC_ERR_UNSUPPORTED, "tensor-core learner mode: obs_dim must be <= 15 (column 15 of the X tile carries the bias-gradient ones)");
   if ((a->phases & (RMC_PH_FORWARD | RMC_PH_BACKWARD)) != (RMC_PH_FORWARD | RMC_PH_BACKWARD))
     return fail(RMC_ERR_UNSUPPORTED, "tensor-core learner mode needs RMC_PH_FORWARD and RMC_PH_BACKWARD in one step");
   if (a->grads_in_dev != nullptr) return fail(RMC_ERR_ARG, "tensor-core learner mode: grads_in_dev belongs to an Adam-only step");
@@ -828,29 +825,17 @@ static int32_t step_tc(rmc_learner* l, rmc_replay* r, const rmc_step_args_t* a, 
   J.j[0].cta_begin = 0;      J.j[0].cta_count = c0;
   J.j[1].cta_begin = c0;     J.j[1].cta_count = c0;
   J.j[2].cta_begin = 2 * c0; J.j[2].cta_count = c2;
-  k_tc_fwd3<<<2 * c0 + c2, kThreads, kTcSmemBytes, st>>>(J, l->L.D, l->L.A, l->L.NH, l->L.dueling, C.X, B);
+  k_tc_fwd3<<<2 * c0 + c2, kTcFwdThreads, kTcSmemBytes, st>>>(J, l->L.D, l->L.A, l->L.NH, l->L.dueling, C.X, B);
   RMC_KERNEL_OK();
   l->ctx.rp = r->dev;
   const unsigned td_blocks = blocks_for(B, kTdThreads);
   if (td_blocks > 1024) return fail(RMC_ERR_UNSUPPORTED, "tensor-core learner mode: batch above 131,072");
   k_tc_td<<<td_blocks, kTdThreads, 0, st>>>(l->ctx, S, T);
   RMC_KERNEL_OK();
-  // backward: dgrad chain + weight gradients fused per 128-row tile (RMC_TC_BWD=split keeps the two-kernel form for A/B runs)
-  static const bool split_bwd = [] { const char* e = std::getenv("RMC_TC_BWD"); return e && std::strcmp(e, "split") == 0; }();
-  if (!split_bwd && l->L.D <= 15) {
-    T.n_part = static_cast<int>(grid);
-    k_tc_bwd_fused<<<grid, kThreads, kTcBwdFusedSmemBytes, st>>>(l->ctx, reinterpret_cast<const unsigned char*>(l->tc_packed_bwd), B, T);
-    RMC_KERNEL_OK();
-  } else {
-    k_tc_bwd<<<grid, kThreads, kTcBwdSmemBytes, st>>>(reinterpret_cast<const unsigned char*>(l->tc_packed_bwd), B, T);
-    RMC_KERNEL_OK();
-    const long long chunks = (B + kWgChunk - 1) / kWgChunk;
-    const int n_part = static_cast<int>(std::min<long long>(chunks, l->num_sms));
-    const long long rows_per_cta = ((chunks + n_part - 1) / n_part) * kWgChunk;
-    T.n_part = n_part;
-    k_tc_wgrad<<<n_part, kThreads, kWgSmemBytes, st>>>(l->ctx, B, rows_per_cta, T);
-    RMC_KERNEL_OK();
-  }
+  // backward: dgrad chain + weight gradients fused per 128-row tile
+  T.n_part = static_cast<int>(grid);
+  k_tc_bwd_fused<<<grid, kThreads, kTcBwdFusedSmemBytes, st>>>(l->ctx, reinterpret_cast<const unsigned char*>(l->tc_packed_bwd), B, T);
+  RMC_KERNEL_OK();
   l->epoch = (l->epoch >= 0x7fffffffu) ? 1u : l->epoch + 1u;
   S.epoch = l->epoch;
   // the Adam kernel refreshes the bf16 operand images element by element: no pack kernels on the next step
@@ -1181,7 +1166,8 @@ static int32_t infer_tc(rmc_learner* l, const float* obs_dev, long long n, long 
   const unsigned grid = static_cast<unsigned>(std::min<long long>(n_tiles, l->num_sms));
   TcFwdExtra ex{};
   ex.row_stride = l->L.D;
-  k_mlp_infer_tc<<<grid, kThreads, kTcSmemBytes, st>>>(l->tc_packed, l->L.D, l->L.A, l->L.NH, l->L.dueling, obs_dev, n, actions, heads, mode, ex);
+  if (std::getenv("RMC_TC_FWD_DBG") != nullptr) ex.dbg = reinterpret_cast<long long*>(l->dbg_buf);   // diagnostics: stage clocks of CTA 0
+  k_mlp_infer_tc<<<grid, kTcFwdThreads, kTcSmemBytes, st>>>(l->tc_packed, l->L.D, l->L.A, l->L.NH, l->L.dueling, obs_dev, n, actions, heads, mode, ex);
   RMC_KERNEL_OK();
   return RMC_OK;
 }

@@ -118,28 +118,70 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 
 // epilogue of one hidden layer: TMEM columns [0, 32*n32) of this warp's 32 lanes -> +bias, ReLU, bf16 ->
 // canonical K-major operand `dst` (K = Kdst) for the next layer.  row = TMEM lane.
-// `gdst` (optional): the same bf16 activations, row-major [rows][Kdst], for the backward kernels.
-__device__ __forceinline__ void tc_hidden_epilogue(uint32_t tmem_acc, int lane_base, int row, int n32,
-                                                   const float* __restrict__ bias, __nv_bfloat16* __restrict__ dst, int Kdst,
-                                                   __nv_bfloat16* __restrict__ gdst = nullptr) {
-  for (int b = 0; b < n32; ++b) {
-    const int col = 32 * b;
-    uint32_t v[32];
-    tc_ld32(tmem_acc + (static_cast<uint32_t>(lane_base) << 16) + col, v);
+__device__ __forceinline__ void tc_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {      // no wait: pair with tc_ld_wait()
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+// wait for the outstanding tensor-memory loads; the registers are in/out operands so that no use of them can be scheduled
+// above the wait
+__device__ __forceinline__ void tc_ld_wait(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]),
+                 "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]),
+                 "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]),
+                 "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
+
+// 32 accumulator columns of this thread's row -> +bias, ReLU, bf16 -> operand tile (+ global copy).
+// The epilogue is instruction-issue bound (profiles/r1/tc_fwd_stages.txt), so it runs on packed operations: one
+// add.f32x2 per two bias adds (sm_100 packed fp32), one cvt per two elements, and ReLU as one max.bf16x2 on the rounded
+// pair -- max(round(x), 0) == round(max(x, 0)) because rounding is monotonic and keeps the sign.
+__device__ __forceinline__ uint32_t tc_bias_relu_pack(uint32_t a0, uint32_t a1, float b0, float b1) {
+  const float2 s = __fadd2_rn(make_float2(__uint_as_float(a0), __uint_as_float(a1)), make_float2(b0, b1));
+  const __nv_bfloat162 r = __hmax2(__floats2bfloat162_rn(s.x, s.y), __floats2bfloat162_rn(0.f, 0.f));
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
+__device__ __forceinline__ void tc_hidden_chunk(const uint32_t (&v)[32], int row, int col, const float* __restrict__ bias,
+                                                __nv_bfloat16* __restrict__ dst, int Kdst) {
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {              // 4 cores of 8 columns
-      float f[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) f[e] = fmaxf(__uint_as_float(v[8 * c + e]) + bias[col + 8 * c + e], 0.f);
-      uint4 q;
-      q.x = pack_bf16x2(f[0], f[1]); q.y = pack_bf16x2(f[2], f[3]); q.z = pack_bf16x2(f[4], f[5]); q.w = pack_bf16x2(f[6], f[7]);
-      *reinterpret_cast<uint4*>(dst + tc_off(row, col + 8 * c, Kdst)) = q;
-      if (gdst != nullptr) *reinterpret_cast<uint4*>(gdst + col + 8 * c) = q;
-    }
+  for (int c = 0; c < 4; ++c) {              // 4 cores of 8 columns
+    const float4 b0 = *reinterpret_cast<const float4*>(bias + col + 8 * c), b1 = *reinterpret_cast<const float4*>(bias + col + 8 * c + 4);
+    uint4 q;
+    q.x = tc_bias_relu_pack(v[8 * c + 0], v[8 * c + 1], b0.x, b0.y);
+    q.y = tc_bias_relu_pack(v[8 * c + 2], v[8 * c + 3], b0.z, b0.w);
+    q.z = tc_bias_relu_pack(v[8 * c + 4], v[8 * c + 5], b1.x, b1.y);
+    q.w = tc_bias_relu_pack(v[8 * c + 6], v[8 * c + 7], b1.z, b1.w);
+    *reinterpret_cast<uint4*>(dst + tc_off(row, col + 8 * c, Kdst)) = q;
   }
 }
-__device__ __forceinline__ void tc_group_sync(int g) {   // the 128 threads of one tile pipeline
-  asm volatile("bar.sync %0, 128;" ::"r"(g + 1) : "memory");
+// chunks [c_first, c_first + n32) of 32 columns each; the tensor-memory load of the next chunk is in flight while the
+// current one is converted (n32 is even)
+__device__ __forceinline__ void tc_hidden_epilogue(uint32_t tmem_acc, int lane_base, int row, int c_first, int n32,
+                                                   const float* __restrict__ bias, __nv_bfloat16* __restrict__ dst, int Kdst) {
+  const uint32_t t0 = tmem_acc + (static_cast<uint32_t>(lane_base) << 16) + 32 * c_first;
+  uint32_t va[32], vb[32];
+  tc_ld32_issue(t0, va);
+  for (int b = 0; b < n32; b += 2) {
+    tc_ld_wait(va);
+    tc_ld32_issue(t0 + 32 * (b + 1), vb);
+    tc_hidden_chunk(va, row, 32 * (c_first + b), bias, dst, Kdst);
+    tc_ld_wait(vb);
+    if (b + 2 < n32) tc_ld32_issue(t0 + 32 * (b + 2), va);
+    tc_hidden_chunk(vb, row, 32 * (c_first + b + 1), bias, dst, Kdst);
+  }
+}
+constexpr int kTcFwdThreads = 512;   // two tile pipelines x 8 warps: each TMEM lane quadrant is drained by two warps (column halves)
+__device__ __forceinline__ void tc_group_sync(int g) {   // the 256 threads of one tile pipeline
+  asm volatile("bar.sync %0, 256;" ::"r"(g + 1) : "memory");
 }
 
 // Two independent tile pipelines per CTA (warps 0-3 and 4-7): while one group runs its epilogue on the CUDA
@@ -149,7 +191,9 @@ __device__ __forceinline__ void tc_group_sync(int g) {   // the 128 threads of o
 // mode 0: actions (dueling: argmax of raw advantages = head columns 1..A; plain: argmax of columns 0..A-1)
 // mode 2: raw head outputs [n][NH] float (diagnostics / error measurement)
 // mode 3: all 16 head columns [n][16] float (training: raw heads), plus the optional row-major bf16 copies of the
-//         input tile / hidden activations (Xb [n][16], H1b [n][256], H2b [n][128]) that the backward kernels consume.
+//         input tile / hidden activations that the backward kernel consumes: per 128-row tile the shared-memory
+//         operand images themselves (UMMA canonical core layout tc_off(r, k, K), K = 16 / 256 / 128), written with
+//         bulk stores -- the backward kernel bulk-loads them and uses them as K-major and MN-major operands as they are.
 // Input rows are read at obs + i*row_stride + col_off (act: row_stride = D, col_off = 0; training: the gathered rows).
 struct TcFwdExtra {
   long long row_stride;
@@ -157,6 +201,7 @@ struct TcFwdExtra {
   __nv_bfloat16* Xb;
   __nv_bfloat16* H1b;
   __nv_bfloat16* H2b;
+  long long* dbg;          // diagnostics: clock64() of CTA 0 / pipeline 0 at the stage boundaries of its first tiles ([tile][8])
 };
 __device__ __forceinline__ void tc_fwd_body(const unsigned char* __restrict__ packed, int D, int A, int NH, int dueling,
                                             const float* __restrict__ obs, long long n, long long* __restrict__ actions,
@@ -189,7 +234,7 @@ __device__ __forceinline__ void tc_fwd_body(const unsigned char* __restrict__ pa
   }
   mbar_wait(bars + 0, 0);
 
-  const int g = warp >> 2, q = warp & 3, gtid = tid & 127;
+  const int g = warp >> 3, q = warp & 3, half = (warp >> 2) & 1, gtid = tid & 255;
   const int row = 32 * q + lane;                  // tile row = TMEM lane
   __nv_bfloat16* sX = sXall + g * kTcRows * kTcK1;
   __nv_bfloat16* sH = sHall + g * kTcRows * kH1;
@@ -197,29 +242,43 @@ __device__ __forceinline__ void tc_fwd_body(const unsigned char* __restrict__ pa
   const uint32_t tD1 = tmem + 256 * g, tD2 = tD1, tD3 = tD1 + 128;
   const uint32_t id1 = tc_idesc_bf16(kTcRows, kH1), id2 = tc_idesc_bf16(kTcRows, kH2), id3 = tc_idesc_bf16(kTcRows, kTcNH);
   uint32_t phase = 0;
+  const bool save = X.H1b != nullptr;       // training pass over the s rows: keep X / H1 / H2 for the backward kernel
   // the NEXT tile's input row is fetched into registers while this tile runs (the global-load latency of the tiny X tile
   // would otherwise sit at the head of every tile's dependent MMA -> epilogue chain)
   float xr[16];
-  auto load_row = [&](long long t) {
-    const long long i = t * kTcRows + gtid;
+  auto load_row = [&](long long t) {        // unconditional loads from a clamped (always valid) row: nothing depends on them until
+    if (half != 0) return;                  // the next iteration packs them (invalid rows / columns are zeroed there)
+    const long long i = min(t * kTcRows + gtid, n - 1);
+    const float* src = obs + i * X.row_stride + X.col_off;
 #pragma unroll
-    for (int d = 0; d < 16; ++d) xr[d] = (t < n_tiles && i < n && d < D) ? __ldg(obs + i * X.row_stride + X.col_off + d) : 0.f;
+    for (int d = 0; d < 16; ++d)
+      if (d < D) xr[d] = __ldg(src + d);
   };
+#pragma unroll
+  for (int d = 0; d < 16; ++d) xr[d] = 0.f;
   load_row(bid + static_cast<long long>(g) * nb);
   for (long long tile = bid + static_cast<long long>(g) * nb; tile < n_tiles; tile += 2ll * nb) {
     // ---- X tile: fp32 obs -> bf16 canonical [128][16]; thread = row
-    {
+    if (half == 0) {
       const long long i = tile * kTcRows + gtid;
+      if (i >= n) {
+#pragma unroll
+        for (int d = 0; d < 16; ++d) xr[d] = 0.f;
+      }
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         uint4 v;
         v.x = pack_bf16x2(xr[8 * c + 0], xr[8 * c + 1]); v.y = pack_bf16x2(xr[8 * c + 2], xr[8 * c + 3]);
         v.z = pack_bf16x2(xr[8 * c + 4], xr[8 * c + 5]); v.w = pack_bf16x2(xr[8 * c + 6], xr[8 * c + 7]);
         *reinterpret_cast<uint4*>(sX + tc_off(gtid, 8 * c, kTcK1)) = v;
-        if (X.Xb != nullptr && i < n) *reinterpret_cast<uint4*>(X.Xb + i * kTcK1 + 8 * c) = v;
       }
     }
     load_row(tile + 2ll * nb);
+    int dslot = 0;
+    const bool dbg_on = X.dbg != nullptr && bid == 0 && gtid == 0 && (tile - bid) / (2ll * nb) < 4;
+    long long* dbg_row = dbg_on ? X.dbg + ((tile - bid) / (2ll * nb)) * 8 : nullptr;
+#define TC_FWD_STAMP() do { if (dbg_on) dbg_row[dslot++] = clock64(); } while (0)
+    TC_FWD_STAMP();               // 0: X packed
     fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core's async proxy
     tc_fence_before();
     tc_group_sync(g);
@@ -231,8 +290,9 @@ __device__ __forceinline__ void tc_fwd_body(const unsigned char* __restrict__ pa
     }
     mbar_wait(gb + 0, phase);
     tc_fence_after();
-    const long long grow = tile * kTcRows + row;
-    tc_hidden_epilogue(tD1, 32 * q, row, 8, sBias, sH, kH1, (X.H1b != nullptr && grow < n) ? X.H1b + grow * kH1 : nullptr);
+    TC_FWD_STAMP();               // 1: layer-1 MMA complete
+    tc_hidden_epilogue(tD1, 32 * q, row, 4 * half, 4, sBias, sH, kH1);
+    TC_FWD_STAMP();               // 2: epilogue 1 done (this thread)
     fence_proxy_async();
     tc_fence_before();
     tc_group_sync(g);
@@ -243,11 +303,21 @@ __device__ __forceinline__ void tc_fwd_body(const unsigned char* __restrict__ pa
 #pragma unroll
       for (int k = 0; k < kH1 / 16; ++k) tc_mma_bf16(tD2, a0 + static_cast<uint64_t>(k * 16), b0 + static_cast<uint64_t>(k * 16), id2, k > 0 ? 1u : 0u);
       tc_commit(gb + 1);
+      if (save) {     // the operand images of X and H1 go to HBM as they are: two bulk stores, read by the TMA engine while layer 2 runs
+        bulk_s2g(X.Xb + tile * (kTcRows * kTcK1), sX, kTcRows * kTcK1 * 2);
+        bulk_s2g(X.H1b + tile * (kTcRows * kH1), sH, kTcRows * kH1 * 2);
+        bulk_commit();
+      }
     }
     mbar_wait(gb + 1, phase);
     tc_fence_after();
-    tc_hidden_epilogue(tD2, 32 * q, row, 4, sBias + kH1, sH, kH2,     // H2 overwrites H1 (layer 2 has consumed it)
-                       (X.H2b != nullptr && grow < n) ? X.H2b + grow * kH2 : nullptr);
+    TC_FWD_STAMP();               // 3: layer-2 MMAs complete
+    if (save) {                   // H2 overwrites H1: the bulk store must have finished READING the buffer
+      if (gtid == 0) bulk_wait_read();
+      tc_group_sync(g);
+    }
+    tc_hidden_epilogue(tD2, 32 * q, row, 2 * half, 2, sBias + kH1, sH, kH2);     // H2 overwrites H1 (layer 2 has consumed it)
+    TC_FWD_STAMP();               // 4: epilogue 2 done
     fence_proxy_async();
     tc_fence_before();
     tc_group_sync(g);
@@ -258,10 +328,15 @@ __device__ __forceinline__ void tc_fwd_body(const unsigned char* __restrict__ pa
 #pragma unroll
       for (int k = 0; k < kH2 / 16; ++k) tc_mma_bf16(tD3, a0 + static_cast<uint64_t>(k * 16), b0 + static_cast<uint64_t>(k * 16), id3, k > 0 ? 1u : 0u);
       tc_commit(gb + 2);
+      if (save) {
+        bulk_s2g(X.H2b + tile * (kTcRows * kH2), sH, kTcRows * kH2 * 2);
+        bulk_commit();
+      }
     }
     mbar_wait(gb + 2, phase);
     tc_fence_after();
-    {
+    TC_FWD_STAMP();               // 5: head MMAs complete
+    if (half == 0) {
       uint32_t v[16];
       tc_ld16(tD3 + (static_cast<uint32_t>(32 * q) << 16), v);
       const long long i = tile * kTcRows + row;
@@ -292,16 +367,20 @@ __device__ __forceinline__ void tc_fwd_body(const unsigned char* __restrict__ pa
         }
       }
     }
+    TC_FWD_STAMP();               // 6: head epilogue done
+    if (save && gtid == 0) bulk_wait_read();      // sX / sH are rewritten by the next tile
     tc_fence_before();
     tc_group_sync(g);     // this group's TMEM slot and operand buffers are free for its next tile
+    TC_FWD_STAMP();               // 7: tile done
     phase ^= 1u;
   }
+  if (save && gtid == 0) bulk_wait_all();
   tc_fence_before();
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
 }
 
-__global__ void __launch_bounds__(kThreads, 1) k_mlp_infer_tc(const unsigned char* __restrict__ packed, int D, int A, int NH, int dueling,
+__global__ void __launch_bounds__(kTcFwdThreads, 1) k_mlp_infer_tc(const unsigned char* __restrict__ packed, int D, int A, int NH, int dueling,
                                                               const float* __restrict__ obs, long long n,
                                                               long long* __restrict__ actions, float* __restrict__ heads_out, int mode,
                                                               TcFwdExtra X) {
@@ -317,7 +396,7 @@ struct TcFwdJob {
   int cta_begin, cta_count;
 };
 struct TcFwdJobs { TcFwdJob j[3]; };
-__global__ void __launch_bounds__(kThreads, 1) k_tc_fwd3(TcFwdJobs J, int D, int A, int NH, int dueling, const float* __restrict__ rows, long long n) {
+__global__ void __launch_bounds__(kTcFwdThreads, 1) k_tc_fwd3(TcFwdJobs J, int D, int A, int NH, int dueling, const float* __restrict__ rows, long long n) {
   const int b = blockIdx.x;
   const int k = (b >= J.j[2].cta_begin) ? 2 : (b >= J.j[1].cta_begin) ? 1 : 0;
   const TcFwdJob& job = J.j[k];

@@ -4,12 +4,13 @@
 // path and the default.
 //
 // Pipeline (all on one stream; the minibatch is drawn by the grid-wide sampler first):
-//   k_mlp_infer_tc x3   Q_online(s'), Q_target(s'), Q_online(s) as raw heads; the s pass also writes X, H1, H2 (bf16)
-//   k_tc_td             TD target, |td|, Huber, loss partials, head deltas DH (fp32 + bf16)          [CUDA cores]
-//   k_tc_bwd            per 128-row tile: dh2 = DH.Wh -> mask -> DZ2 ;  dz1 = DZ2.W2 -> mask -> DZ1   [2 UMMA chains]
-//   k_tc_wgrad          per batch slice: dW2 = H1^T.DZ2, dW0 = DZ1^T.X, dWh = H2^T.DH (MN-major operands, K = batch)
-//                       accumulated in TMEM, bias gradients as column sums, one partial blob per CTA
-//   k_tc_reduce_adam    fixed-order sum of the partials -> gradients -> Adam (+ Polyak), loss
+//   k_tc_fwd3           Q_online(s'), Q_target(s'), Q_online(s) as raw heads in ONE launch (rmc_tc.cuh); the s pass leaves the
+//                       shared-memory operand images of X, H1, H2 in HBM with bulk stores
+//   k_tc_td             TD target, |td|, Huber, loss partials, head deltas DH (bf16)                    [CUDA cores]
+//   k_tc_bwd_fused      per 128-row tile: bulk-load X | H1 | H2, dh2 = DH.Wh -> mask -> DZ2, dz1 = DZ2.W2 -> mask -> DZ1,
+//                       dW2 += H1^T.DZ2, dW0 += DZ1^T.X, dWh += H2^T.DH (accumulators stay in TMEM across the CTA's tiles);
+//                       one partial gradient blob per CTA
+//   k_tc_reduce_adam    fixed-order sum of the partials -> gradients -> Adam (+ Polyak) -> refreshed bf16 operand images, loss
 #pragma once
 #include "rmc_mlp.cuh"
 #include "rmc_tc.cuh"
@@ -36,7 +37,8 @@ __global__ void k_tc_pack_bwd(const float* __restrict__ blob, NetLayout L, __nv_
 
 struct TcTrainBufs {
   float *heads_n, *heads_t, *heads_s;                    // [B][16] raw heads: online(s'), target(s'), online(s)
-  __nv_bfloat16 *Xb, *H1b, *H2b, *DZ2b, *DZ1b, *DHb;     // row-major bf16: [B][16] [B][256] [B][128] [B][128] [B][256] [B][16]
+  __nv_bfloat16 *Xb, *H1b, *H2b;                         // per 128-row tile: the forward kernel's operand images (tc_off layout)
+  __nv_bfloat16* DHb;                                    // head deltas, row-major bf16 [B][16]
   float* partials;                                       // [n_ctas][L.total]
   int n_part;
 };
@@ -178,278 +180,28 @@ __global__ void __launch_bounds__(kTdThreads) k_tc_td(AgentCtx C, StepScalars S,
   }
 }
 
-// ------------------------------------------------------------------------------------------ dgrad chain
-constexpr int kTcBwdSmemBytes = kTcBwdBytes + (kTcRows * kTcNH + kTcRows * kH2) * 2 + 4 * 8 + 16;
-
-__device__ __forceinline__ void load_bf16x32(const __nv_bfloat16* __restrict__ g, float (&f)[32]) {
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    const uint4 q = *reinterpret_cast<const uint4*>(g + 8 * c);
-    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      f[8 * c + 2 * e] = __uint_as_float(w[e] << 16);
-      f[8 * c + 2 * e + 1] = __uint_as_float(w[e] & 0xffff0000u);
-    }
-  }
-}
-
-__global__ void __launch_bounds__(kThreads, 1) k_tc_bwd(const unsigned char* __restrict__ packed_bwd, long long n, TcTrainBufs T) {
-  extern __shared__ __align__(128) unsigned char tsm[];
-  __nv_bfloat16* sW = reinterpret_cast<__nv_bfloat16*>(tsm);                    // Wh^T | W2
-  __nv_bfloat16* sDH = reinterpret_cast<__nv_bfloat16*>(tsm + kTcBwdBytes);     // [128][16]
-  __nv_bfloat16* sDZ2 = sDH + kTcRows * kTcNH;                                  // [128][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sDZ2 + kTcRows * kH2);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const long long n_tiles = (n + kTcRows - 1) / kTcRows;
-  if (blockIdx.x >= n_tiles) return;
-  if (tid == 0) {
-    for (int b = 0; b < 3; ++b) mbar_init(bars + b, 1);
-    fence_mbar_init();
-  }
-  if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-  const uint32_t tD1 = tmem, tD2 = tmem + 128;
-  if (tid == 0) {
-    mbar_expect_tx(bars + 0, kTcBwdBytes);
-    bulk_g2s(tsm, packed_bwd, kTcBwdBytes, bars + 0);
-  }
-  mbar_wait(bars + 0, 0);
-  const uint32_t id1 = tc_idesc_bf16(kTcRows, kH2), id2 = tc_idesc_bf16(kTcRows, kH1);
-  const int q = warp & 3, half = warp >> 2;
-  const int row = 32 * q + lane;
-  uint32_t phase = 0;
-  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    {   // DH tile -> canonical K-major [128][16]
-      const int r = tid >> 1, c = tid & 1;
-      const long long i = tile * kTcRows + r;
-      uint4 v = make_uint4(0, 0, 0, 0);
-      if (i < n) v = *reinterpret_cast<const uint4*>(T.DHb + i * 16 + 8 * c);
-      *reinterpret_cast<uint4*>(sDH + tc_off(r, 8 * c, kTcNH)) = v;
-    }
-    fence_proxy_async();
-    tc_fence_before();
-    __syncthreads();
-    if (tid == 0) {   // dh2[128x128] = DH . Wh   (K = 16: one UMMA)
-      tc_fence_after();
-      tc_mma_bf16(tD1, tc_smem_desc(sDH, 128, (kTcNH / 8) * 128), tc_smem_desc(sW + kTcBwdOffWhT, 128, (kTcNH / 8) * 128), id1, 0u);
-      tc_commit(bars + 1);
-    }
-    mbar_wait(bars + 1, phase);
-    tc_fence_after();
-    const long long i = tile * kTcRows + row;
-    for (int b = 0; b < 2; ++b) {      // this warp: 64 of the 128 dh2 columns of its 32 rows
-      const int col = 64 * half + 32 * b;
-      uint32_t v[32];
-      tc_ld32(tD1 + (static_cast<uint32_t>(32 * q) << 16) + col, v);
-      float h[32];
-      if (i < n) load_bf16x32(T.H2b + i * kH2 + col, h);
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        float f[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) f[e] = (i < n && h[8 * c + e] > 0.f) ? __uint_as_float(v[8 * c + e]) : 0.f;
-        uint4 pk;
-        pk.x = pack_bf16x2(f[0], f[1]); pk.y = pack_bf16x2(f[2], f[3]); pk.z = pack_bf16x2(f[4], f[5]); pk.w = pack_bf16x2(f[6], f[7]);
-        *reinterpret_cast<uint4*>(sDZ2 + tc_off(row, col + 8 * c, kH2)) = pk;
-        if (i < n) *reinterpret_cast<uint4*>(T.DZ2b + i * kH2 + col + 8 * c) = pk;
-      }
-    }
-    fence_proxy_async();
-    tc_fence_before();
-    __syncthreads();
-    if (tid == 0) {   // dz1_pre[128x256] = DZ2 . W2   (K = 128: 8 UMMAs)
-      tc_fence_after();
-      const uint64_t a0 = tc_smem_desc(sDZ2, 128, (kH2 / 8) * 128), b0 = tc_smem_desc(sW + kTcBwdOffW2, 128, (kH2 / 8) * 128);
-#pragma unroll
-      for (int k = 0; k < kH2 / 16; ++k) tc_mma_bf16(tD2, a0 + static_cast<uint64_t>(k * 16), b0 + static_cast<uint64_t>(k * 16), id2, k > 0 ? 1u : 0u);
-      tc_commit(bars + 2);
-    }
-    mbar_wait(bars + 2, phase);
-    tc_fence_after();
-    for (int b = 0; b < 4; ++b) {      // 128 of the 256 dz1 columns
-      const int col = 128 * half + 32 * b;
-      uint32_t v[32];
-      tc_ld32(tD2 + (static_cast<uint32_t>(32 * q) << 16) + col, v);
-      if (i < n) {
-        float h[32];
-        load_bf16x32(T.H1b + i * kH1 + col, h);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          float f[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) f[e] = (h[8 * c + e] > 0.f) ? __uint_as_float(v[8 * c + e]) : 0.f;
-          uint4 pk;
-          pk.x = pack_bf16x2(f[0], f[1]); pk.y = pack_bf16x2(f[2], f[3]); pk.z = pack_bf16x2(f[4], f[5]); pk.w = pack_bf16x2(f[6], f[7]);
-          *reinterpret_cast<uint4*>(T.DZ1b + i * kH1 + col + 8 * c) = pk;
-        }
-      }
-    }
-    tc_fence_before();
-    __syncthreads();
-    phase ^= 1u;
-  }
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
-}
-
-// ------------------------------------------------------------------------------------------ weight gradients
-// MN-major canonical operand for a staged [kWgChunk b-rows][ncols] tile: 8x8 cores of 128 contiguous bytes
-// ((b % 8) * 8 + col % 8), K-groups (b / 8) LBO = 128 B apart, column cores (col / 8) SBO = (kWgChunk/8)*128 B apart.
-constexpr int kWgChunk = 64;
-__host__ __device__ __forceinline__ int mn_off(int col, int b) { return ((col >> 3) * (kWgChunk >> 3) + (b >> 3)) * 64 + (b & 7) * 8 + (col & 7); }
-constexpr int kWgElems = kWgChunk * (kH1 + kH2 + kH1 + kTcK1 + kH2 + kTcNH);      // H1 | DZ2 | DZ1 | X | H2 | DH per chunk
-constexpr int kWgSmemBytes = kWgElems * 2 + 4 * 8 + 16;
-
-__device__ __forceinline__ uint32_t tc_idesc_bf16_mn(int M, int N) { return tc_idesc_bf16(M, N) | (1u << 15) | (1u << 16); }
-
-__device__ __forceinline__ void wg_stage(__nv_bfloat16* dst, const __nv_bfloat16* __restrict__ src, int ncols, long long b0, int rows) {
-  const int cpr = ncols >> 3;                           // 16-byte chunks per row
-  for (int t = threadIdx.x; t < kWgChunk * cpr; t += kThreads) {
-    const int b = t / cpr, mi = t - b * cpr;
-    __nv_bfloat16* d = dst + mn_off(8 * mi, b);
-    if (b < rows) cp_async16(d, src + (b0 + b) * ncols + 8 * mi);
-    else *reinterpret_cast<uint4*>(d) = make_uint4(0, 0, 0, 0);
-  }
-}
-
-__global__ void __launch_bounds__(kThreads, 1) k_tc_wgrad(AgentCtx C, long long n, long long rows_per_cta, TcTrainBufs T) {
-  extern __shared__ __align__(128) unsigned char tsm[];
-  __nv_bfloat16* sH1 = reinterpret_cast<__nv_bfloat16*>(tsm);
-  __nv_bfloat16* sDZ2 = sH1 + kWgChunk * kH1;
-  __nv_bfloat16* sDZ1 = sDZ2 + kWgChunk * kH2;
-  __nv_bfloat16* sX = sDZ1 + kWgChunk * kH1;
-  __nv_bfloat16* sH2 = sX + kWgChunk * kTcK1;
-  __nv_bfloat16* sDH = sH2 + kWgChunk * kH2;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sDH + kWgChunk * kTcNH);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const NetLayout& L = C.L;
-  const long long lo = blockIdx.x * rows_per_cta, hi = min(lo + rows_per_cta, n);
-  float* part = T.partials + static_cast<size_t>(blockIdx.x) * L.total;
-  if (tid == 0) { mbar_init(bars, 1); fence_mbar_init(); }
-  if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-  // TMEM columns: dW2 rows 0..127 [0,128) | dW2 rows 128..255 [128,256) | dW0 i<128 [256,272) | dW0 i>=128 [272,288) | dWh [288,304)
-  const uint32_t idN128 = tc_idesc_bf16_mn(128, kH2), idN16 = tc_idesc_bf16_mn(128, 16);
-  constexpr uint32_t kSbo = (kWgChunk / 8) * 128, kLbo = 128;
-  float db0 = 0.f, db2 = 0.f, dbh = 0.f;      // bias gradients: thread t owns column t of DZ1, t of DZ2 (t<128), t-128 of DH
-  uint32_t phase = 0;
-  bool any = false;
-  for (long long b0 = lo; b0 < hi; b0 += kWgChunk) {
-    const int rows = static_cast<int>(min(static_cast<long long>(kWgChunk), hi - b0));
-    wg_stage(sH1, T.H1b, kH1, b0, rows);
-    wg_stage(sDZ2, T.DZ2b, kH2, b0, rows);
-    wg_stage(sDZ1, T.DZ1b, kH1, b0, rows);
-    wg_stage(sX, T.Xb, kTcK1, b0, rows);
-    wg_stage(sH2, T.H2b, kH2, b0, rows);
-    wg_stage(sDH, T.DHb, kTcNH, b0, rows);
-    cp_async_wait_all();
-    fence_proxy_async();
-    tc_fence_before();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-#pragma unroll
-      for (int ks = 0; ks < kWgChunk / 16; ++ks) {
-        const uint32_t acc = (any || ks > 0) ? 1u : 0u;
-        const uint64_t koff = static_cast<uint64_t>(ks * 2 * kLbo) >> 4;
-        const uint64_t aH1 = tc_smem_desc(sH1, kLbo, kSbo) + koff, aH1b = tc_smem_desc(sH1 + mn_off(128, 0), kLbo, kSbo) + koff;
-        const uint64_t bDZ2 = tc_smem_desc(sDZ2, kLbo, kSbo) + koff;
-        const uint64_t aDZ1 = tc_smem_desc(sDZ1, kLbo, kSbo) + koff, aDZ1b = tc_smem_desc(sDZ1 + mn_off(128, 0), kLbo, kSbo) + koff;
-        const uint64_t bX = tc_smem_desc(sX, kLbo, kSbo) + koff;
-        const uint64_t aH2 = tc_smem_desc(sH2, kLbo, kSbo) + koff, bDH = tc_smem_desc(sDH, kLbo, kSbo) + koff;
-        tc_mma_bf16(tmem + 0, aH1, bDZ2, idN128, acc);
-        tc_mma_bf16(tmem + 128, aH1b, bDZ2, idN128, acc);
-        tc_mma_bf16(tmem + 256, aDZ1, bX, idN16, acc);
-        tc_mma_bf16(tmem + 272, aDZ1b, bX, idN16, acc);
-        tc_mma_bf16(tmem + 288, aH2, bDH, idN16, acc);
-      }
-      tc_commit(bars);
-    }
-    any = true;
-    // bias gradients from the staged tiles (CUDA cores, concurrently with the UMMAs; smem is only read)
-    for (int b = 0; b < rows; ++b) {
-      db0 += __bfloat162float(sDZ1[mn_off(tid, b)]);
-      if (tid < kH2) db2 += __bfloat162float(sDZ2[mn_off(tid, b)]);
-      else if (tid < kH2 + kTcNH) dbh += __bfloat162float(sDH[mn_off(tid - kH2, b)]);
-    }
-    mbar_wait(bars, phase);
-    tc_fence_after();
-    phase ^= 1u;
-    __syncthreads();          // operand buffers may be restaged
-  }
-  // ---- partial gradients of this CTA's batch slice -> part[] (device parameter layout)
-  const int q = warp & 3, half = warp >> 2;
-  const int r = 32 * q + lane;
-  if (any) {
-    for (int mh = 0; mh < 2; ++mh) {          // dW2^T rows k = 128*mh + r, this warp's 64 columns j
-      const int k = 128 * mh + r;
-      for (int b = 0; b < 2; ++b) {
-        const int j0 = 64 * half + 32 * b;
-        uint32_t v[32];
-        tc_ld32(tmem + 128 * mh + (static_cast<uint32_t>(32 * q) << 16) + j0, v);
-#pragma unroll
-        for (int e = 0; e < 32; e += 4)
-          *reinterpret_cast<float4*>(part + L.off_w2t + k * kW2LD + j0 + e) =
-              make_float4(__uint_as_float(v[e]), __uint_as_float(v[e + 1]), __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
-      }
-    }
-    {   // dW0^T[d][i]: half h handles i = 128*h + r
-      uint32_t v[16];
-      tc_ld16(tmem + 256 + 16 * half + (static_cast<uint32_t>(32 * q) << 16), v);
-      const int i = 128 * half + r;
-      for (int d = 0; d < L.D; ++d) part[L.off_w0t + d * kH1 + i] = __uint_as_float(v[d]);
-    }
-    if (half == 0) {   // dWh[a][j], j = r
-      uint32_t v[16];
-      tc_ld16(tmem + 288 + (static_cast<uint32_t>(32 * q) << 16), v);
-      for (int a = 0; a < L.NH; ++a) part[L.off_wh + a * kH2 + r] = __uint_as_float(v[a]);
-    }
-  } else {
-    for (int p = tid; p < L.total; p += kThreads) part[p] = 0.f;
-  }
-  if (any) {
-    part[L.off_b0 + tid] = db0;
-    if (tid < kH2) part[L.off_b2 + tid] = db2;
-    else if (tid < kH2 + L.NH) part[L.off_bh + (tid - kH2)] = dbh;
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
-}
+__device__ __forceinline__ uint32_t tc_idesc_bf16_mn(int M, int N) { return tc_idesc_bf16(M, N) | (1u << 15) | (1u << 16); }   // A and B MN-major
 
 // ------------------------------------------------------------------------------------------ fused backward
 // k_tc_bwd_fused: dgrad chain AND weight gradients of a 128-row tile in one CTA; DZ1 / DZ2 never leave the SM and every
-// activation is read from HBM exactly once (H1 | H2 | X | DH: 52 MB per 65,536-row step instead of ~200 MB for the
-// k_tc_bwd + k_tc_wgrad pair).
+// activation is read from HBM exactly once (X | H1 | H2 | DH: 52 MB per 65,536-row step).
 //
-// One shared-memory image serves BOTH operand roles.  A [128 b][C] tile is stored as 8x8 cores with element (b, c) at
-//   uoff(b, c) = ((c/8)*16 + b/8)*64 + (b%8)*8 + c%8 ;
-// read as a K-major operand (rows = b, K = c) its cores are LBO = 2048 B apart along K and SBO = 128 B apart along rows;
-// read as an MN-major operand (MN = c, K = b) they are LBO = 128 B apart along K and SBO = 2048 B apart along MN.  So the
-// DZ2 tile the first epilogue writes is the A operand of dz1 = DZ2.W2 (K-major) and the B operand of dW2 = H1^T.DZ2
-// (MN-major) without a second copy.
+// One shared-memory image serves BOTH operand roles.  A [128 b][C] tile stored as 8x8 cores (element (b, c) at
+// core * 64 + (b%8)*8 + c%8) is a K-major operand (rows = b, K = c) AND an MN-major operand (MN = c, K = b): only the two
+// descriptor strides swap roles.  X, H1, H2 arrive in the forward kernel's own layout tc_off(b, c, C) -- the forward
+// kernel's shared-memory images, bulk-stored per tile and bulk-loaded here with three TMA copies -- with cores of
+// neighbouring columns 128 B apart and 8-row groups (C/8)*128 B apart: as MN-major operands LBO = (C/8)*128, SBO = 128.
+// The tiles this kernel produces (DH, DZ2, DZ1) use uoff(b, c) (8-row groups 128 B apart, column cores 2048 B apart):
+// K-major (LBO, SBO) = (2048, 128), MN-major (128, 2048).  So the DZ2 tile the first epilogue writes is the A operand of
+// dz1 = DZ2.W2 (K-major) and the B operand of dW2 = H1^T.DZ2 (MN-major) without a second copy.
 //
-// Bias gradients ride on the tensor core: the staged X tile carries 1.0 in its spare column 15, so column 15 of
+// Bias gradients ride on the tensor core: the staged X tile gets 1.0 in its spare column 15, so column 15 of
 // dW0 = DZ1^T.X is db0 and an extra N = 16 product DZ2^T.X yields db2 (dbh: 16 threads sum the 128x16 DH tile).
 //
 // TMEM columns: [0,128) scratch (dh2, dz1[:, :128], dz1[:, 128:]) | [128,384) dW2^T (two M halves) | [384,416) dW0 (two
 // halves) | [416,432) dWh | [432,448) DZ2^T.X.   Per tile: stage -> dh2 -> mask(H2) -> DZ2 -> dz1a -> mask(H1) -> DZ1a
 // (into the H2 buffer, free once dWh has completed) -> dW0a, dz1b -> DZ1b (into the DZ2 buffer, free once dW2 / dz1b
-// have completed) -> dW0b.
+// have completed) -> dW0b.  The next tile's H1 / H2 loads are issued as soon as their buffers are free (before dW0b).
 __host__ __device__ __forceinline__ int uoff(int b, int c) { return (((c >> 3) << 4) + (b >> 3)) * 64 + (b & 7) * 8 + (c & 7); }
 constexpr int kBfOffDH = kTcBwdBytes;                               // byte offsets inside the dynamic shared memory
 constexpr int kBfOffX = kBfOffDH + kTcRows * kTcNH * 2;
@@ -459,25 +211,10 @@ constexpr int kBfOffH1 = kBfOffDZ2 + kTcRows * kH2 * 2;
 constexpr int kBfOffBars = kBfOffH1 + kTcRows * kH1 * 2;
 constexpr int kTcBwdFusedSmemBytes = kBfOffBars + 8 * 8 + 16;       // 208,976 B
 
-// stage a [128][C] bf16 row-major global tile into the universal layout with cp.async; a warp covers 8 rows x 64 B
-// (whole 32-byte sectors from HBM; 4 cores x 128 contiguous bytes in shared memory, conflict-free)
-template <int C>
-__device__ __forceinline__ void bf_stage(__nv_bfloat16* dst, const __nv_bfloat16* __restrict__ src, long long row0, int rows) {
-  constexpr int C8 = C / 8;
-  for (int q = threadIdx.x; q < kTcRows * C8; q += kThreads) {
-    const int b_lo = q & 7, c_lo = (q >> 3) & 3, rem = q >> 5;
-    const int c_hi = rem % (C8 / 4), b_hi = rem / (C8 / 4);
-    const int b = b_hi * 8 + b_lo, c8 = c_hi * 4 + c_lo;
-    __nv_bfloat16* d = dst + uoff(b, 8 * c8);
-    if (b < rows) cp_async16(d, src + (row0 + b) * C + 8 * c8);
-    else *reinterpret_cast<uint4*>(d) = make_uint4(0, 0, 0, 0);
-  }
-}
-
-// epilogue: scratch columns [col0, col0+64) of this warp's 32 rows -> ReLU mask from `act` (universal tile, column offset
-// act_c0) -> bf16 -> universal tile `dst`
+// epilogue: scratch columns [col0, col0+64) of this warp's 32 rows -> ReLU mask from `act` (forward-layout tile with act_K
+// columns, column offset act_c0) -> bf16 -> uoff tile `dst`
 __device__ __forceinline__ void bf_mask_epilogue(uint32_t tS, int q, int row, int col0, const __nv_bfloat16* __restrict__ act, int act_c0,
-                                                 __nv_bfloat16* __restrict__ dst) {
+                                                 int act_K, __nv_bfloat16* __restrict__ dst) {
 #pragma unroll
   for (int blk = 0; blk < 2; ++blk) {
     const int col = col0 + 32 * blk;
@@ -485,7 +222,7 @@ __device__ __forceinline__ void bf_mask_epilogue(uint32_t tS, int q, int row, in
     tc_ld32(tS + (static_cast<uint32_t>(32 * q) << 16) + col, v);
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-      const uint4 hq = *reinterpret_cast<const uint4*>(act + uoff(row, act_c0 + col + 8 * c));
+      const uint4 hq = *reinterpret_cast<const uint4*>(act + tc_off(row, act_c0 + col + 8 * c, act_K));
       const uint32_t hw[4] = {hq.x, hq.y, hq.z, hq.w};
       float f[8];
 #pragma unroll
@@ -540,24 +277,30 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_bwd_fused(AgentCtx C, const 
   float dbh = 0.f;                     // threads 0..15: bias gradient of head column tid
   uint32_t phase = 0;
   bool first = true;
+  uint64_t* barL = bars + 5;           // the tile's TMA loads
+  constexpr uint32_t kLoadBytes = (kTcRows * kH1 + kTcRows * kH2 + kTcRows * kTcK1) * 2;
+  // descriptor strides of the forward-layout tiles used as MN-major operands: (LBO = 8-row-group stride, SBO = 128)
+  constexpr uint32_t kH1L = (kH1 / 8) * 128, kH2L = (kH2 / 8) * 128, kXL = (kTcK1 / 8) * 128;
+  if (tid == 0 && static_cast<long long>(blockIdx.x) < n_tiles) {
+    const long long t = blockIdx.x;
+    mbar_expect_tx(barL, kLoadBytes);
+    bulk_g2s(sH1, T.H1b + t * (kTcRows * kH1), kTcRows * kH1 * 2, barL);
+    bulk_g2s(sH2, T.H2b + t * (kTcRows * kH2), kTcRows * kH2 * 2, barL);
+    bulk_g2s(sX, T.Xb + t * (kTcRows * kTcK1), kTcRows * kTcK1 * 2, barL);
+  }
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const long long row0 = tile * kTcRows;
     const int rows = static_cast<int>(min(static_cast<long long>(kTcRows), n - row0));
-    // ---- S0: stage DH, X (register path: X gets 1.0 in column 15), H2, H1
-    bf_stage<kH2>(sH2, T.H2b, row0, rows);
-    bf_stage<kH1>(sH1, T.H1b, row0, rows);
+    const long long next = tile + gridDim.x;
+    // ---- S0: DH by the register path (uoff layout); X | H1 | H2 arrive by TMA in the forward kernel's layout
     {
       const int b = tid >> 1, c8 = tid & 1;
-      uint4 dh = make_uint4(0, 0, 0, 0), x = make_uint4(0, 0, 0, 0);
-      if (b < rows) {
-        dh = *reinterpret_cast<const uint4*>(T.DHb + (row0 + b) * kTcNH + 8 * c8);
-        x = *reinterpret_cast<const uint4*>(T.Xb + (row0 + b) * kTcK1 + 8 * c8);
-        if (c8 == 1) x.w = (x.w & 0xffffu) | 0x3f800000u;      // element 15 = bf16(1.0): bias gradients as an extra GEMM column
-      }
+      uint4 dh = make_uint4(0, 0, 0, 0);
+      if (b < rows) dh = *reinterpret_cast<const uint4*>(T.DHb + (row0 + b) * kTcNH + 8 * c8);
       *reinterpret_cast<uint4*>(sDH + uoff(b, 8 * c8)) = dh;
-      *reinterpret_cast<uint4*>(sX + uoff(b, 8 * c8)) = x;
     }
-    cp_async_wait_all();
+    mbar_wait(barL, phase);
+    if (tid < rows) sX[tc_off(tid, 15, kTcK1)] = __float2bfloat16_rn(1.f);   // spare column: bias gradients as a GEMM column
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -568,9 +311,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_bwd_fused(AgentCtx C, const 
       tc_fence_after();
       tc_mma_bf16(tS, tc_smem_desc(sDH, kUL, kUS), tc_smem_desc(sW + kTcBwdOffWhT, 128, (kTcNH / 8) * 128), idK_128, 0u);
       tc_commit(bars + 1);
-      const uint64_t aH2 = tc_smem_desc(sH2, kUS, kUL), bDH = tc_smem_desc(sDH, kUS, kUL);
+      const uint64_t aH2 = tc_smem_desc(sH2, kH2L, 128), bDH = tc_smem_desc(sDH, kUS, kUL);
 #pragma unroll
-      for (int ks = 0; ks < kTcRows / 16; ++ks) tc_mma_bf16(tWh, aH2 + 16u * ks, bDH + 16u * ks, idMN_16, (ks > 0) ? 1u : acc);
+      for (int ks = 0; ks < kTcRows / 16; ++ks) tc_mma_bf16(tWh, aH2 + (2u * kH2L / 16u) * ks, bDH + 16u * ks, idMN_16, (ks > 0) ? 1u : acc);
     }
     if (tid < kTcNH) {                 // dbh: column sums of the staged DH tile
       float s = 0.f;
@@ -580,7 +323,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_bwd_fused(AgentCtx C, const 
     mbar_wait(bars + 1, phase);
     tc_fence_after();
     // ---- S2: DZ2 = dh2 (.) [H2 > 0]
-    bf_mask_epilogue(tS, q, row, 64 * half, sH2, 0, sDZ2);
+    bf_mask_epilogue(tS, q, row, 64 * half, sH2, 0, kH2, sDZ2);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -591,51 +334,57 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_bwd_fused(AgentCtx C, const 
 #pragma unroll
       for (int k = 0; k < kH2 / 16; ++k) tc_mma_bf16(tS, aDZ2k + 256u * k, bW2 + 16u * k, idK_128, k > 0 ? 1u : 0u);
       tc_commit(bars + 2);
-      const uint64_t aH1 = tc_smem_desc(sH1, kUS, kUL), aH1b = tc_smem_desc(sH1 + uoff(0, 128), kUS, kUL);
-      const uint64_t bDZ2 = tc_smem_desc(sDZ2, kUS, kUL), bX = tc_smem_desc(sX, kUS, kUL);
+      const uint64_t aH1 = tc_smem_desc(sH1, kH1L, 128), aH1b = tc_smem_desc(sH1 + tc_off(0, 128, kH1), kH1L, 128);
+      const uint64_t bDZ2 = tc_smem_desc(sDZ2, kUS, kUL), bX = tc_smem_desc(sX, kXL, 128);
 #pragma unroll
       for (int ks = 0; ks < kTcRows / 16; ++ks) {
         const uint32_t a2 = (ks > 0) ? 1u : acc;
-        tc_mma_bf16(tW2, aH1 + 16u * ks, bDZ2 + 16u * ks, idMN_128, a2);
-        tc_mma_bf16(tW2 + 128, aH1b + 16u * ks, bDZ2 + 16u * ks, idMN_128, a2);
-        tc_mma_bf16(tB2, bDZ2 + 16u * ks, bX + 16u * ks, idMN_16, a2);
+        tc_mma_bf16(tW2, aH1 + (2u * kH1L / 16u) * ks, bDZ2 + 16u * ks, idMN_128, a2);
+        tc_mma_bf16(tW2 + 128, aH1b + (2u * kH1L / 16u) * ks, bDZ2 + 16u * ks, idMN_128, a2);
+        tc_mma_bf16(tB2, bDZ2 + 16u * ks, bX + (2u * kXL / 16u) * ks, idMN_16, a2);
       }
     }
     mbar_wait(bars + 2, phase);        // dz1a done; the commit also covers dWh -> the H2 buffer is free
     tc_fence_after();
-    // ---- S4: DZ1[:, :128] = dz1a (.) [H1[:, :128] > 0]  -> H2 buffer
-    bf_mask_epilogue(tS, q, row, 64 * half, sH1, 0, sH2);
+    // ---- S4: DZ1[:, :128] = dz1a (.) [H1[:, :128] > 0]  -> H2 buffer (uoff layout)
+    bf_mask_epilogue(tS, q, row, 64 * half, sH1, 0, kH1, sH2);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     // ---- S5: dW0[:128] += DZ1a^T . X ; dz1[:, 128:] = DZ2 . W2[128:]
     if (tid == 0) {
       tc_fence_after();
-      const uint64_t aZ = tc_smem_desc(sH2, kUS, kUL), bX = tc_smem_desc(sX, kUS, kUL);
+      const uint64_t aZ = tc_smem_desc(sH2, kUS, kUL), bX = tc_smem_desc(sX, kXL, 128);
 #pragma unroll
-      for (int ks = 0; ks < kTcRows / 16; ++ks) tc_mma_bf16(tW0, aZ + 16u * ks, bX + 16u * ks, idMN_16, (ks > 0) ? 1u : acc);
+      for (int ks = 0; ks < kTcRows / 16; ++ks) tc_mma_bf16(tW0, aZ + 16u * ks, bX + (2u * kXL / 16u) * ks, idMN_16, (ks > 0) ? 1u : acc);
       const uint64_t aDZ2k = tc_smem_desc(sDZ2, kUL, kUS), bW2 = tc_smem_desc(sW + kTcBwdOffW2 + tc_off(128, 0, kH2), 128, (kH2 / 8) * 128);
 #pragma unroll
       for (int k = 0; k < kH2 / 16; ++k) tc_mma_bf16(tS, aDZ2k + 256u * k, bW2 + 16u * k, idK_128, k > 0 ? 1u : 0u);
       tc_commit(bars + 3);
     }
-    mbar_wait(bars + 3, phase);        // dz1b done; covers dW2 / db2 / dz1a / dW0a -> the DZ2 buffer is free
+    mbar_wait(bars + 3, phase);        // dz1b done; covers dW2 / db2 / dz1a / dW0a -> the DZ2 and H2 buffers are free
     tc_fence_after();
     // ---- S6: DZ1[:, 128:] -> DZ2 buffer
-    bf_mask_epilogue(tS, q, row, 64 * half, sH1, 128, sDZ2);
+    bf_mask_epilogue(tS, q, row, 64 * half, sH1, 128, kH1, sDZ2);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
-    // ---- S7: dW0[128:] += DZ1b^T . X
+    // ---- S7: dW0[128:] += DZ1b^T . X ; the next tile's H1 / H2 start loading (nothing reads those buffers any more)
     if (tid == 0) {
       tc_fence_after();
-      const uint64_t aZ = tc_smem_desc(sDZ2, kUS, kUL), bX = tc_smem_desc(sX, kUS, kUL);
+      const uint64_t aZ = tc_smem_desc(sDZ2, kUS, kUL), bX = tc_smem_desc(sX, kXL, 128);
 #pragma unroll
-      for (int ks = 0; ks < kTcRows / 16; ++ks) tc_mma_bf16(tW0 + 16, aZ + 16u * ks, bX + 16u * ks, idMN_16, (ks > 0) ? 1u : acc);
+      for (int ks = 0; ks < kTcRows / 16; ++ks) tc_mma_bf16(tW0 + 16, aZ + 16u * ks, bX + (2u * kXL / 16u) * ks, idMN_16, (ks > 0) ? 1u : acc);
       tc_commit(bars + 4);
+      if (next < n_tiles) {
+        mbar_expect_tx(barL, kLoadBytes);
+        bulk_g2s(sH1, T.H1b + next * (kTcRows * kH1), kTcRows * kH1 * 2, barL);
+        bulk_g2s(sH2, T.H2b + next * (kTcRows * kH2), kTcRows * kH2 * 2, barL);
+      }
     }
-    mbar_wait(bars + 4, phase);        // every operand buffer may be restaged
+    mbar_wait(bars + 4, phase);        // every operand buffer may be rewritten
     tc_fence_after();
+    if (tid == 0 && next < n_tiles) bulk_g2s(sX, T.Xb + next * (kTcRows * kTcK1), kTcRows * kTcK1 * 2, barL);
     __syncthreads();
     phase ^= 1u;
     first = false;
