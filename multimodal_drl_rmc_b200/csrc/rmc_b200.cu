@@ -821,7 +821,7 @@ static int32_t step_tc(rmc_learner* l, rmc_replay* r, const rmc_step_args_t* a, 
   J.j[2].X.col_off = 0; J.j[2].X.Xb = T.Xb; J.j[2].X.H1b = T.H1b; J.j[2].X.H2b = T.H2b;
   int c0, c2;
   if (3 * n_tiles <= l->num_sms) { c0 = c2 = static_cast<int>(n_tiles); }
-  else { c0 = std::max(1, (l->num_sms * 2) / 7); c2 = l->num_sms - 2 * c0; }   // the s pass also stores activations: ~1.5x the work
+  else { c0 = std::max(1, l->num_sms / 3); c2 = l->num_sms - 2 * c0; }
   J.j[0].cta_begin = 0;      J.j[0].cta_count = c0;
   J.j[1].cta_begin = c0;     J.j[1].cta_count = c0;
   J.j[2].cta_begin = 2 * c0; J.j[2].cta_count = c2;
