@@ -47,7 +47,7 @@ enum rmc_status {
 };
 
 enum rmc_param_kind { RMC_ONLINE = 0, RMC_TARGET = 1, RMC_ADAM_M = 2, RMC_ADAM_V = 3, RMC_GRADS = 4 };
-enum rmc_activation { RMC_ACT_RELU = 0 };
+enum rmc_activation { RMC_ACT_RELU = 0, RMC_ACT_ELU = 1 /* nn.ELU(alpha=1): env/dqn_config.py:175 */ };
 
 /* Network + algorithm shape.  Mirrors what dqn/network.py:12-19 obtains from the user's
  * nn_conf_func and what dqn/agent.py:275-320 wires per agent flavour. */

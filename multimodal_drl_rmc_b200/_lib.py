@@ -24,6 +24,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
 ONLINE, TARGET, ADAM_M, ADAM_V, GRADS = 0, 1, 2, 3, 4
 PH_SAMPLE, PH_FORWARD, PH_PRIORITY, PH_BACKWARD, PH_ADAM, PH_POLYAK, PH_HARDSYNC = 1, 2, 4, 8, 16, 32, 64
 PREC_FP32, PREC_BF16_TC = 0, 1
+ACT_RELU, ACT_ELU = 0, 1
 PH_LEARN = PH_SAMPLE | PH_FORWARD | PH_PRIORITY | PH_BACKWARD | PH_ADAM
 
 

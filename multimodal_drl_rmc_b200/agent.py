@@ -87,7 +87,8 @@ class Agent:
         hyper = _lib.Hyper(float(lr), 0.9, 0.999, 1e-8, float(gamma), float(target_soft_update_tau) * n_env,
                            1e-4, 0.6, 1.0)
         self._lh = LearnerHandle(self.online_network._obs_dim, output_dim, self._DUELING, self._DOUBLE, self._PER,
-                                 max(int(batch_size), 1), self.device.index, hyper)
+                                 max(int(batch_size), 1), self.device.index, hyper,
+                                 activation=self.online_network._activation)
         self.online_network._bind(self._lh, _lib.ONLINE)
         self.target_network._bind(self._lh, _lib.TARGET)
         self.update_target_network(force=True)

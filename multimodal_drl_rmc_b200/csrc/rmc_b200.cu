@@ -475,6 +475,7 @@ static NetLayout make_layout(const rmc_net_spec_t& sp) {
   NetLayout L{};
   L.D = sp.obs_dim; L.A = sp.n_actions; L.dueling = sp.dueling ? 1 : 0;
   L.NH = L.dueling ? L.A + 1 : L.A;
+  L.act = (sp.activation == RMC_ACT_ELU) ? 1 : 0;
   int o = 0;
   L.off_w0t = o; o += L.D * kH1;
   L.off_b0 = o; o += kH1;
@@ -516,7 +517,8 @@ extern "C" int32_t rmc_learner_create(rmc_learner_t** out, const rmc_net_spec_t*
   if (!out || !spec || !hyper || max_batch < 1) return fail(RMC_ERR_ARG, "rmc_learner_create: null/bad args");
   if (spec->hidden1 != kH1 || spec->hidden2 != kH2)
     return fail(RMC_ERR_UNSUPPORTED, "rmc_learner_create: only the macro MLP body 256-128 is built (no fallback path)");
-  if (spec->activation != RMC_ACT_RELU) return fail(RMC_ERR_UNSUPPORTED, "rmc_learner_create: only ReLU bodies are built");
+  if (spec->activation != RMC_ACT_RELU && spec->activation != RMC_ACT_ELU)
+    return fail(RMC_ERR_UNSUPPORTED, "rmc_learner_create: hidden activation must be ReLU or ELU(alpha=1)");
   if (spec->obs_dim < 1 || spec->obs_dim > kMaxD || spec->n_actions < 1 || spec->n_actions > 15)
     return fail(RMC_ERR_UNSUPPORTED, "rmc_learner_create: obs_dim must be 1..32 and n_actions 1..15");
   if (int32_t e = use_device(device)) return e;
@@ -778,6 +780,7 @@ static int32_t tc_train_setup(rmc_learner* l) {
 
 static int32_t step_tc(rmc_learner* l, rmc_replay* r, const rmc_step_args_t* a, StepScalars& S, cudaStream_t st) {
   if (l->L.D > kTcK1 - 1) return fail(RMC_ERR_UNSUPPORTED, "tensor-core learner mode: obs_dim must be <= 15 (column 15 of the X tile carries the bias-gradient ones)");
+  if (l->L.act != 0) return fail(RMC_ERR_UNSUPPORTED, "tensor-core modes are built for ReLU bodies only");
   if ((a->phases & (RMC_PH_FORWARD | RMC_PH_BACKWARD)) != (RMC_PH_FORWARD | RMC_PH_BACKWARD))
     return fail(RMC_ERR_UNSUPPORTED, "tensor-core learner mode needs RMC_PH_FORWARD and RMC_PH_BACKWARD in one step");
   if (a->grads_in_dev != nullptr) return fail(RMC_ERR_ARG, "tensor-core learner mode: grads_in_dev belongs to an Adam-only step");
@@ -1153,6 +1156,7 @@ extern "C" int32_t rmc_learner_act(rmc_learner_t* l, const float* obs_dev, int64
 // tensor-core (tcgen05, bf16 operands / fp32 accumulate) mode of act / heads: looser, stated bound (see rmc_tc.cuh)
 static int32_t infer_tc(rmc_learner* l, const float* obs_dev, long long n, long long* actions, float* heads, int mode, cudaStream_t st) {
   if (l->L.D > kTcK1) return fail(RMC_ERR_UNSUPPORTED, "tensor-core act mode: obs_dim must be <= 16");
+  if (l->L.act != 0) return fail(RMC_ERR_UNSUPPORTED, "tensor-core modes are built for ReLU bodies only");
   if (l->tc_packed == nullptr) {
     if (int32_t e = owned_alloc(l, &l->tc_packed, static_cast<size_t>(kTcBlobBytes))) return e;
     RMC_CUDA(cudaFuncSetAttribute(k_mlp_infer_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));

@@ -189,7 +189,20 @@ struct ReplayDev {
 struct NetLayout {     // float offsets inside one parameter blob (device layout)
   int D, A, NH, dueling;
   int off_w0t, off_b0, off_w2t, off_b2, off_wh, off_bh, total;   // total is a multiple of 4
+  int act;           // hidden activation: 0 = ReLU, 1 = ELU(alpha = 1)
 };
+
+// Hidden activation and its derivative expressed through the OUTPUT h (what the step keeps):
+//   ReLU: h = max(z, 0),               dh/dz = [h > 0]
+//   ELU : h = z > 0 ? z : exp(z) - 1   (torch's CPU kernel: exp then subtract, not expm1),  dh/dz = h > 0 ? 1 : h + 1 (= exp(z))
+__device__ __forceinline__ float act_fwd(float z, int act) {
+  if (act == 0) return fmaxf(z, 0.f);
+  return (z > 0.f) ? z : expf(z) - 1.f;
+}
+__device__ __forceinline__ float act_bwd(float upstream, float h, int act) {
+  if (act == 0) return (h > 0.f) ? upstream : 0.f;
+  return (h > 0.f) ? upstream : upstream * (h + 1.f);
+}
 
 struct AgentCtx {
   ReplayDev rp;

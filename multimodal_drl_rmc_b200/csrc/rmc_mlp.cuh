@@ -1,5 +1,5 @@
 // rmc_mlp.cuh -- the fused learner-step kernel (one cooperative launch per step) and the
-// batched act / Q-value kernel for the macro-state MLP  D -> 256 -> ReLU -> 128 -> ReLU -> heads.
+// batched act / Q-value kernel for the macro-state MLP  D -> 256 -> ReLU|ELU -> 128 -> ReLU|ELU -> heads.
 //
 // Phase A (row parallel, CTAs own tiles of kTM batch rows):
 //     TMA bulk copy of the whole target / online parameter blob into shared memory,
@@ -96,8 +96,8 @@ __device__ __forceinline__ void mlp_forward(const float* __restrict__ sW, const 
       }
     }
     float4* hp = reinterpret_cast<float4*>(sH1T + tid * kR);
-    hp[0] = make_float4(fmaxf(acc[0], 0.f), fmaxf(acc[1], 0.f), fmaxf(acc[2], 0.f), fmaxf(acc[3], 0.f));
-    if (R == 8) hp[1] = make_float4(fmaxf(acc[4 % R], 0.f), fmaxf(acc[5 % R], 0.f), fmaxf(acc[6 % R], 0.f), fmaxf(acc[7 % R], 0.f));
+    hp[0] = make_float4(act_fwd(acc[0], L.act), act_fwd(acc[1], L.act), act_fwd(acc[2], L.act), act_fwd(acc[3], L.act));
+    if (R == 8) hp[1] = make_float4(act_fwd(acc[4 % R], L.act), act_fwd(acc[5 % R], L.act), act_fwd(acc[6 % R], L.act), act_fwd(acc[7 % R], L.act));
   }
   __syncthreads();
   // ---- layer 2, K split over the 8 warps (32 k each); lane owns 4 columns for all R rows
@@ -141,7 +141,7 @@ __device__ __forceinline__ void mlp_forward(const float* __restrict__ sW, const 
         const float4 p = *reinterpret_cast<const float4*>(sPart + (w * kR + r) * kH2 + c);
         s.x += p.x; s.y += p.y; s.z += p.z; s.w += p.w;
       }
-      *reinterpret_cast<float4*>(sH2 + r * kH2 + c) = make_float4(fmaxf(s.x, 0.f), fmaxf(s.y, 0.f), fmaxf(s.z, 0.f), fmaxf(s.w, 0.f));
+      *reinterpret_cast<float4*>(sH2 + r * kH2 + c) = make_float4(act_fwd(s.x, L.act), act_fwd(s.y, L.act), act_fwd(s.z, L.act), act_fwd(s.w, L.act));
     }
   }
   __syncthreads();
@@ -652,7 +652,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, c
             float s = 0.f;
             for (int a = 0; a < L.NH; ++a) s = fmaf(dh[a], sW[L.off_wh + a * kH2 + j], s);
             const float h2v = sH2[(kTM + r) * kH2 + j];
-            const float dz = (h2v > 0.f) ? s : 0.f;
+            const float dz = act_bwd(s, h2v, L.act);
             sDZ2[r * kH2 + j] = dz;
             const long long i = tile * kTM + r;
             if (i < B) { C.DZ2[i * kH2 + j] = dz; C.H2[i * kH2 + j] = h2v; }
@@ -684,7 +684,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, c
             const long long i = tile * kTM + r;
             const float h1v = sH1T[tid * kR + kTM + r];
             if (i < B) {
-              C.DZ1[i * kH1 + tid] = (h1v > 0.f) ? acc[r] : 0.f;
+              C.DZ1[i * kH1 + tid] = act_bwd(acc[r], h1v, L.act);
               C.H1[i * kH1 + tid] = h1v;
             }
           }

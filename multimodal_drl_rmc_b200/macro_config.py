@@ -29,7 +29,15 @@ def network_config(input_dim_space):
     return net, 128, optim.Adam, nn.SmoothL1Loss
 
 
-def make_agent(algo, obs_dim, batch_size, buffer_size, *, save_dir, log_dir, n_actions=8, gpu="0", **overrides):
+def network_config_elu(input_dim_space):
+    """The same body with the activation of the repo-HEAD config (``ACTIVATION = nn.ELU()``, env/dqn_config.py:175)."""
+    d = input_dim_space.shape[0]
+    net = nn.Sequential(nn.Linear(d, 256), nn.ELU(), nn.Linear(256, 128), nn.ELU())
+    return net, 128, optim.Adam, nn.SmoothL1Loss
+
+
+def make_agent(algo, obs_dim, batch_size, buffer_size, *, save_dir, log_dir, n_actions=8, gpu="0", activation="relu",
+               **overrides):
     """Construct an agent the way train.py:24-48 does, with the reference defaults."""
     from . import agent as Agents
     hp = dict(HYPER_PARAMS)
@@ -37,7 +45,8 @@ def make_agent(algo, obs_dim, batch_size, buffer_size, *, save_dir, log_dir, n_a
     cls = getattr(Agents, algo)
     return cls(n_env=hp["n_env"], lr=hp["lr"], gamma=hp["gamma"], epsilon_start=hp["eps_start"],
                epsilon_min=hp["eps_min"], epsilon_decay=hp["eps_dec"], epsilon_exp_decay=hp["eps_dec_exp"],
-               nn_conf_func=network_config, input_dim=ObsSpace(obs_dim), output_dim=n_actions,
+               nn_conf_func=network_config_elu if activation == "elu" else network_config, input_dim=ObsSpace(obs_dim),
+               output_dim=n_actions,
                batch_size=batch_size, min_buffer_size=min(hp["min_mem"], buffer_size), buffer_size=buffer_size,
                update_target_frequency=hp["target_update_freq"], target_soft_update=hp["target_soft_update"],
                target_soft_update_tau=hp["target_soft_update_tau"], save_frequency=hp["save_freq"],

@@ -20,32 +20,44 @@ from ._lib import check, lib, ptr, stream_ptr
 from . import packfmt
 
 
+def _hidden_activation(mod):
+    """0 for nn.ReLU, 1 for nn.ELU(alpha=1) (the activation of env/dqn_config.py:175), else None."""
+    if isinstance(mod, nn.ReLU):
+        return _lib.ACT_RELU
+    if isinstance(mod, nn.ELU) and float(mod.alpha) == 1.0:
+        return _lib.ACT_ELU
+    return None
+
+
 def match_macro_body(net, fc_out_dim, optim_func, loss_func):
     """The fused path is built for the macro-state body of the reference
-    (env/custom_env/macro with lane/dqn_config.py:58-104): Sequential(Linear(D,256), ReLU,
-    Linear(256,128), ReLU) + optim.Adam + nn.SmoothL1Loss.  Anything else raises: there is no
-    eager / CPU fallback by design."""
+    (env/custom_env/macro with lane/dqn_config.py:58-104): Sequential(Linear(D,256), act,
+    Linear(256,128), act) with act = ReLU or ELU(alpha=1) (the same in both places) + optim.Adam +
+    nn.SmoothL1Loss.  Anything else raises: there is no eager / CPU fallback by design.
+    Returns (obs_dim, activation code)."""
     ok = (isinstance(net, nn.Sequential) and len(net) == 4 and isinstance(net[0], nn.Linear)
-          and isinstance(net[1], nn.ReLU) and isinstance(net[2], nn.Linear) and isinstance(net[3], nn.ReLU)
+          and isinstance(net[2], nn.Linear) and _hidden_activation(net[1]) is not None
+          and _hidden_activation(net[1]) == _hidden_activation(net[3])
           and net[0].out_features == 256 and net[2].in_features == 256 and net[2].out_features == 128
           and fc_out_dim == 128 and net[0].bias is not None and net[2].bias is not None)
     if not ok:
-        raise NotImplementedError("librmc_b200 implements the macro-state MLP body Linear(D,256)-ReLU-Linear(256,128)-ReLU "
-                                  "only (got %r); no fallback path exists" % (net,))
+        raise NotImplementedError("librmc_b200 implements the macro-state MLP body Linear(D,256)-act-Linear(256,128)-act with "
+                                  "act = ReLU or ELU(alpha=1) only (got %r); no fallback path exists" % (net,))
     if optim_func is not T.optim.Adam:
         raise NotImplementedError("librmc_b200 fuses torch.optim.Adam only (got %r)" % (optim_func,))
     if loss_func is not nn.SmoothL1Loss:
         raise NotImplementedError("librmc_b200 fuses nn.SmoothL1Loss only (got %r)" % (loss_func,))
-    return net[0].in_features
+    return net[0].in_features, _hidden_activation(net[1])
 
 
 class LearnerHandle:
     """Owner of one ``rmc_learner_t`` (online + target + Adam state + scratch)."""
 
-    def __init__(self, obs_dim, n_actions, dueling, double_dqn, prioritized, max_batch, device_index, hyper: _lib.Hyper):
+    def __init__(self, obs_dim, n_actions, dueling, double_dqn, prioritized, max_batch, device_index, hyper: _lib.Hyper,
+                 activation=0):
         _lib.require_cuda()
         self.spec = _lib.NetSpec(int(obs_dim), 256, 128, int(n_actions), int(dueling), int(double_dqn),
-                                 int(prioritized), 0)
+                                 int(prioritized), int(activation))
         self.hyper = hyper
         self.device_index = int(device_index)
         self.max_batch = int(max_batch)
@@ -100,7 +112,7 @@ class Network(nn.Module):
     def __init__(self, device, nn_conf_func, input_dim):
         super().__init__()
         self.net, self.fc_out_dim, optim_func, loss_func = nn_conf_func(input_dim)
-        self._obs_dim = match_macro_body(self.net, self.fc_out_dim, optim_func, loss_func)
+        self._obs_dim, self._activation = match_macro_body(self.net, self.fc_out_dim, optim_func, loss_func)
         self.optim_func = (lambda params, lr: optim_func(params, lr=lr))
         self.loss_func = (lambda reduction: loss_func(reduction=reduction))
         self.device = device
@@ -123,7 +135,8 @@ class Network(nn.Module):
                 raise RuntimeError("Network compute needs a CUDA device (no CPU fallback); got device=%s" % (self.device,))
             index = dev.index if dev.index is not None else T.cuda.current_device()
             hyper = _lib.Hyper(1e-4, 0.9, 0.999, 1e-8, 0.99, 1e-3, 1e-4, 0.6, 1.0)
-            self._bind(LearnerHandle(self._obs_dim, self._n_actions, self._dueling, True, False, 1, index, hyper), _lib.ONLINE)
+            self._bind(LearnerHandle(self._obs_dim, self._n_actions, self._dueling, True, False, 1, index, hyper,
+                                     activation=self._activation), _lib.ONLINE)
         return self._lh
 
     def _flat_module_params(self):

@@ -192,10 +192,12 @@ class OraclePrioritizedReplay:
 # --------------------------------------------------------------------------------------
 # Networks  (reference: dqn/network.py + the macro network_config)
 # --------------------------------------------------------------------------------------
-def macro_body(obs_dim: int, hidden=(256, 128)):
-    """env/custom_env/macro with lane/dqn_config.py:58-104 (Linear-ReLU-Linear-ReLU)."""
-    return nn.Sequential(nn.Linear(obs_dim, hidden[0]), nn.ReLU(),
-                         nn.Linear(hidden[0], hidden[1]), nn.ReLU())
+def macro_body(obs_dim: int, hidden=(256, 128), activation="relu"):
+    """env/custom_env/macro with lane/dqn_config.py:58-104 (Linear-ReLU-Linear-ReLU); activation="elu" is the same body
+    with the repo-HEAD activation (``ACTIVATION = nn.ELU()``, env/dqn_config.py:175)."""
+    act = nn.ELU if activation == "elu" else nn.ReLU
+    return nn.Sequential(nn.Linear(obs_dim, hidden[0]), act(),
+                         nn.Linear(hidden[0], hidden[1]), act())
 
 
 class OracleQNet(nn.Module):
@@ -205,10 +207,10 @@ class OracleQNet(nn.Module):
     checkpoint keys (``net.0.weight`` ... ``fc_adv.bias``).  Construction order (body, then
     val, then adv / out) matches the reference so that a seeded default init is identical."""
 
-    def __init__(self, obs_dim: int, n_actions: int, dueling: bool, hidden=(256, 128)):
+    def __init__(self, obs_dim: int, n_actions: int, dueling: bool, hidden=(256, 128), activation="relu"):
         super().__init__()
         self.dueling = bool(dueling)
-        self.net = macro_body(obs_dim, hidden)
+        self.net = macro_body(obs_dim, hidden, activation)
         if self.dueling:
             self.fc_val = nn.Linear(hidden[1], 1)
             self.fc_adv = nn.Linear(hidden[1], n_actions)
@@ -252,7 +254,7 @@ class OracleLearner:
 
     def __init__(self, algo: str, obs_dim: int, n_actions: int, batch: int, capacity: int, *,
                  lr=1e-4, gamma=0.99, tau=1e-3, soft=True, target_freq=30000, eps_decay=2e6,
-                 n_env=1):
+                 n_env=1, activation="relu"):
         f = self.ALGOS[algo]
         self.algo, self.per, self.dueling, self.double = algo, f["per"], f["dueling"], f["double"]
         self.obs_dim, self.n_actions, self.batch, self.capacity = obs_dim, n_actions, batch, capacity
@@ -261,8 +263,8 @@ class OracleLearner:
         self.replay = (OraclePrioritizedReplay(capacity, batch, eps_decay) if self.per
                        else OracleUniformReplay(capacity, batch))
         # construction order online -> target, as in agent.py:282-283 etc.
-        self.online = OracleQNet(obs_dim, n_actions, self.dueling)
-        self.target = OracleQNet(obs_dim, n_actions, self.dueling)
+        self.online = OracleQNet(obs_dim, n_actions, self.dueling, activation=activation)
+        self.target = OracleQNet(obs_dim, n_actions, self.dueling, activation=activation)
         self.opt = torch.optim.Adam(self.online.parameters(), lr=lr)   # network.py:17,56
         self.huber = nn.SmoothL1Loss(reduction="none" if self.per else "mean")  # agent.py:317
         self.sync_target(force=True)                                   # agent.py:284

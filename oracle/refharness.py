@@ -102,14 +102,25 @@ def macro_network_config(input_dim_space):
     return body, 128, optim.Adam, nn.SmoothL1Loss
 
 
+def macro_network_config_elu(input_dim_space):
+    """The macro body with the repo-HEAD activation (reference: ``env/dqn_config.py:175`` ``ACTIVATION = nn.ELU()``)."""
+    import torch.nn as nn
+    import torch.optim as optim
+
+    d = input_dim_space.shape[0]
+    body = nn.Sequential(nn.Linear(d, 256), nn.ELU(), nn.Linear(256, 128), nn.ELU())
+    return body, 128, optim.Adam, nn.SmoothL1Loss
+
+
 def make_reference_agent(algo: str, obs_dim: int, batch: int, cap: int, tmpdir: str, *,
                          lr=1e-4, gamma=0.99, tau=1e-3, soft=True, target_freq=30000,
-                         eps_decay=2e6, n_env=1, n_actions=8):
+                         eps_decay=2e6, n_env=1, n_actions=8, activation="relu"):
     """Construct a reference agent exactly as train.py:24-48 would (macro MLP)."""
     dqn = import_reference()
     cls = getattr(dqn.Agents, algo)
     return cls(n_env=n_env, lr=lr, gamma=gamma, epsilon_start=1.0, epsilon_min=0.01,
-               epsilon_decay=eps_decay, epsilon_exp_decay=True, nn_conf_func=macro_network_config,
+               epsilon_decay=eps_decay, epsilon_exp_decay=True,
+               nn_conf_func=macro_network_config_elu if activation == "elu" else macro_network_config,
                input_dim=ObsBox(obs_dim), output_dim=n_actions, batch_size=batch,
                min_buffer_size=batch, buffer_size=cap, update_target_frequency=target_freq,
                target_soft_update=soft, target_soft_update_tau=tau, save_frequency=10000,

@@ -38,6 +38,7 @@ CASES = {
     "double_d8_hard": dict(algo="DoubleDQNAgent", D=8, B=32, cap=256, fill=200, steps=4, soft=False,
                            target_freq=2),
     "dqn_d14": dict(algo="DQNAgent", D=14, B=16, cap=128, fill=128, steps=2, soft=True),
+    "per_d14_elu": dict(algo="PerDuelingDoubleDQNAgent", D=14, B=64, cap=600, fill=600, steps=3, soft=True, activation="elu"),
 }
 WEIGHT_SEED = 0
 DATA_SEED = 20251018
@@ -78,7 +79,8 @@ def run_case(name: str, c: dict, tmp: str) -> dict:
     torch.set_num_threads(1)
     torch.manual_seed(WEIGHT_SEED)
     agent = refharness.make_reference_agent(c["algo"], c["D"], c["B"], c["cap"], tmp,
-                                            soft=c["soft"], target_freq=c.get("target_freq", 30000))
+                                            soft=c["soft"], target_freq=c.get("target_freq", 30000),
+                                            activation=c.get("activation", "relu"))
     perturb_target(agent)
     per = c["algo"].startswith("Per")
     out = {"init_online_sha": sha(flat_params(agent.online_network)),
@@ -180,7 +182,10 @@ def main() -> None:
     meta = {"cpu": cpu_fingerprint(), "weight_seed": WEIGHT_SEED, "data_seed": DATA_SEED,
             "target_noise_seed": TARGET_NOISE_SEED, "sample_stride": SAMPLE_STRIDE, "cases": CASES}
     try:
+        only = [a for a in sys.argv[1:] if a in CASES]       # `make_golden.py per_d14_elu`: add one learner case, keep the rest
         for name, c in CASES.items():
+            if only and name not in only:
+                continue
             res = run_case(name, c, tmp)
             flat = {}
             for k, v in res.items():
@@ -192,6 +197,12 @@ def main() -> None:
                     flat[k] = np.asarray(v)
             np.savez_compressed(os.path.join(HERE, "learner_%s.npz" % name), **flat)
             print("wrote", name, {k: (v.shape if hasattr(v, "shape") else v) for k, v in list(flat.items())[:4]})
+        if only:
+            old = json.load(open(os.path.join(HERE, "golden_meta.json")))
+            old["cases"] = CASES
+            with open(os.path.join(HERE, "golden_meta.json"), "w") as fh:
+                json.dump(old, fh, indent=1, sort_keys=True)
+            return
         for cap, n_ops, seed in [(1, 20, 1), (2, 60, 2), (3, 80, 3), (7, 200, 4), (69, 1500, 5), (64, 800, 6),
                                  (1000, 6000, 7)]:
             r = sumtree_case(cap, n_ops, seed)

@@ -29,16 +29,16 @@ def flat_sd(net):
     return np.concatenate([v.detach().cpu().numpy().ravel() for v in net.state_dict().values()])
 
 
-def make_pair(algo, D, B, cap, fill, seed, soft=True, target_freq=30000, tmpdir=None):
+def make_pair(algo, D, B, cap, fill, seed, soft=True, target_freq=30000, tmpdir=None, activation="relu"):
     """(oracle learner, CUDA agent) with identical weights and identical replay contents."""
     from multimodal_drl_rmc_b200 import macro_config
     torch.set_num_threads(1)
     torch.manual_seed(seed)
-    orc = OracleLearner(algo, D, 8, B, cap, soft=soft, target_freq=target_freq)
+    orc = OracleLearner(algo, D, 8, B, cap, soft=soft, target_freq=target_freq, activation=activation)
     perturb_target(orc.target, seed + 100)
     tmp = tmpdir or tempfile.mkdtemp(prefix="rmc_parity_")
     agent = macro_config.make_agent(algo, D, B, cap, save_dir=tmp + "/", log_dir=tmp + "/",
-                                    target_soft_update=soft, target_update_freq=target_freq)
+                                    target_soft_update=soft, target_update_freq=target_freq, activation=activation)
     agent.online_network.load_state_dict({k: v.clone() for k, v in orc.online.state_dict().items()})
     agent.target_network.load_state_dict({k: v.clone() for k, v in orc.target.state_dict().items()})
     obs, act, rew, done, nxt = synthetic_transitions(fill, D, 20251018 + seed)
@@ -58,9 +58,9 @@ def gpu_out(agent, name, dtype=torch.float32):
     return agent._lh.output(name, dtype).cpu().numpy()
 
 
-def run_parity_case(algo, D, B, cap, fill, steps, seed, soft=True, target_freq=30000, resync_tree=True):
+def run_parity_case(algo, D, B, cap, fill, steps, seed, soft=True, target_freq=30000, resync_tree=True, activation="relu"):
     from multimodal_drl_rmc_b200 import _lib
-    orc, agent = make_pair(algo, D, B, cap, fill, seed, soft, target_freq)
+    orc, agent = make_pair(algo, D, B, cap, fill, seed, soft, target_freq, activation=activation)
     per = orc.per
     sizes = tensor_sizes(orc.online)
     rng = np.random.default_rng(seed + 1)

@@ -26,9 +26,16 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize("algo,D,B,cap,fill,steps,soft,tf", CASES)
-def test_learner_step_parity(algo, D, B, cap, fill, steps, soft, tf):
-    res = PU.run_parity_case(algo, D, B, cap, fill, steps, seed=11, soft=soft, target_freq=tf)
+ELU_CASES = [   # the same body with nn.ELU() (the repo-HEAD activation, env/dqn_config.py:175)
+    ("PerDuelingDoubleDQNAgent", 14, 64, 1000, 1300, 3, True, 30000),
+    ("DuelingDoubleDQNAgent", 8, 32, 512, 700, 2, True, 30000),
+    ("DQNAgent", 14, 1024, 4096, 4096, 2, False, 2),
+]
+
+
+@pytest.mark.parametrize("algo,D,B,cap,fill,steps,soft,tf,act", [c + ("relu",) for c in CASES] + [c + ("elu",) for c in ELU_CASES])
+def test_learner_step_parity(algo, D, B, cap, fill, steps, soft, tf, act):
+    res = PU.run_parity_case(algo, D, B, cap, fill, steps, seed=11, soft=soft, target_freq=tf, activation=act)
     print(res)
     assert res["nodes_equal"], "sampled tree indices must be bit-exact"
     assert res["tree_equal"], "sum tree must be bit-exact given equal float32 priorities"
@@ -132,8 +139,16 @@ def test_unsupported_configs_raise():
     from multimodal_drl_rmc_b200 import Networks
     from multimodal_drl_rmc_b200.macro_config import ObsSpace
 
-    def elu_conf(space):
-        return nn.Sequential(nn.Linear(space.shape[0], 256), nn.ELU(), nn.Linear(256, 128), nn.ELU()), 128, optim.Adam, nn.SmoothL1Loss
+    def conf(act1, act2, width=256, opt=optim.Adam):
+        return lambda space: (nn.Sequential(nn.Linear(space.shape[0], width), act1, nn.Linear(width, 128), act2), 128, opt, nn.SmoothL1Loss)
 
-    with pytest.raises(NotImplementedError):
-        Networks.DuelingDeepQNetwork(torch.device("cuda:0"), 1e-4, elu_conf, ObsSpace(14), 8)
+    for bad in (conf(nn.Tanh(), nn.Tanh()), conf(nn.ELU(alpha=0.5), nn.ELU(alpha=0.5)), conf(nn.ReLU(), nn.ELU()),
+                conf(nn.ReLU(), nn.ReLU(), width=512), conf(nn.ReLU(), nn.ReLU(), opt=optim.SGD)):
+        with pytest.raises(NotImplementedError):
+            Networks.DuelingDeepQNetwork(torch.device("cuda:0"), 1e-4, bad, ObsSpace(14), 8)
+    # ELU(alpha=1) bodies are built; the tensor-core modes are ReLU-only and must say so
+    net = Networks.DuelingDeepQNetwork(torch.device("cuda:0"), 1e-4, conf(nn.ELU(), nn.ELU()), ObsSpace(14), 8)
+    obs = np.random.default_rng(0).random((64, 14), dtype=np.float32)
+    assert len(net.actions(obs)) == 64
+    with pytest.raises(Exception):
+        net.actions(obs, precision="bf16")
