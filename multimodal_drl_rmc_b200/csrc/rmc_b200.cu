@@ -17,6 +17,7 @@
 #include "rmc_tc.cuh"
 #include "rmc_tc_train.cuh"
 #include "rmc_comm.cuh"
+#include "rmc_infer64.cuh"
 #include "rmc_tree.cuh"
 
 using namespace rmc;
@@ -79,6 +80,8 @@ struct rmc_learner {
   int rf = 0;
   int num_sms = 0;
   int smem_bytes = 0;
+  int max_smem_optin = 0;
+  bool big_ready = false;
   float* blobs[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // online,target,m,v,grads
   int* map = nullptr;        // torch index -> device-layout index
   float* io = nullptr;       // [P] device staging for set/get
@@ -384,7 +387,7 @@ static int32_t launch_per_sample(const ReplayDev& R, long long B, long long Bglo
                                  unsigned long long seed, unsigned long long counter, long long* nodes, float* is_w, float* rows,
                                  double* leaf_p, cudaStream_t st) {
   if (B >= kLaneSampleMin)
-    k_per_sample_lane<<<blocks_for(B, kThreads), kThreads, 0, st>>>(R, B, Bglobal, shard_off, beta, u, seed, counter, 0u, nodes, is_w, rows, leaf_p);
+    k_per_sample_lane<<<blocks_for(B, kLaneThreads), kLaneThreads, 0, st>>>(R, B, Bglobal, shard_off, beta, u, seed, counter, 0u, nodes, is_w, rows, leaf_p);
   else
     k_per_sample<<<blocks_for(B, kWarps), kThreads, 0, st>>>(R, B, Bglobal, shard_off, beta, u, seed, counter, 0u, nodes, is_w, rows, leaf_p);
   RMC_KERNEL_OK();
@@ -534,6 +537,7 @@ extern "C" int32_t rmc_learner_create(rmc_learner_t** out, const rmc_net_spec_t*
   l->smem_bytes = std::max(plan.total_floats, kGemmSmemFloats) * 4;
   int max_optin = 0;
   RMC_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+  l->max_smem_optin = max_optin;
   if (l->smem_bytes > max_optin) return fail(RMC_ERR_UNSUPPORTED, "rmc_learner_create: parameter blob does not fit shared memory");
   RMC_CUDA(cudaFuncSetAttribute(k_learner_step, cudaFuncAttributeMaxDynamicSharedMemorySize, l->smem_bytes));
   RMC_CUDA(cudaFuncSetAttribute(k_mlp_infer, cudaFuncAttributeMaxDynamicSharedMemorySize, l->smem_bytes));
@@ -1128,6 +1132,19 @@ extern "C" int32_t rmc_learner_loss_sync(rmc_learner_t* l, float* out_host, rmc_
 
 static int32_t infer_launch(rmc_learner* l, const float* params, const float* obs_dev, long long n, long long* actions, float* q, int mode,
                             cudaStream_t st) {
+  // large batches: 64-row tiles (every weight fetched from shared memory serves 64 rows; rmc_infer64.cuh)
+  const int big_bytes = big_smem_floats(l->L.total) * 4;
+  if (n >= 1024 && l->L.D <= 16 && big_bytes <= l->max_smem_optin) {
+    if (!l->big_ready) {
+      RMC_CUDA(cudaFuncSetAttribute(k_mlp_infer64, cudaFuncAttributeMaxDynamicSharedMemorySize, big_bytes));
+      l->big_ready = true;
+    }
+    const long long big_tiles = (n + kBigRows - 1) / kBigRows;
+    k_mlp_infer64<<<static_cast<unsigned>(std::min<long long>(big_tiles, l->num_sms)), kThreads, static_cast<size_t>(big_bytes), st>>>(
+        l->L, params, obs_dev, n, actions, q, mode);
+    RMC_KERNEL_OK();
+    return RMC_OK;
+  }
   const long long n_tiles = (n + kR - 1) / kR;
   const unsigned grid = static_cast<unsigned>(std::min<long long>(n_tiles, l->num_sms));
   k_mlp_infer<<<grid, kThreads, static_cast<size_t>(l->smem_bytes), st>>>(l->L, params, obs_dev, n, actions, q, mode);

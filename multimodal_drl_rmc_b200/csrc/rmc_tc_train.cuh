@@ -441,7 +441,7 @@ __global__ void __launch_bounds__(256) k_tc_reduce_adam(AgentCtx C, StepScalars 
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   if (p4 < n4) {
     const float4* src = reinterpret_cast<const float4*>(T.partials) + p4;
-#pragma unroll 4
+#pragma unroll 10
     for (int c = warp; c < T.n_part; c += 8) {
       const float4 v = __ldcg(src + static_cast<size_t>(c) * n4);
       acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;

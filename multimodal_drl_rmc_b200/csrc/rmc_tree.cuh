@@ -736,19 +736,20 @@ __global__ void __launch_bounds__(kThreads) k_per_sample(ReplayDev R, long long 
 // ~log2(B) - 5 nodes (one broadcast L1 hit each) and the whole batch is in flight at once (2048 descents per SM);
 // the comparison sequence per sample is still exactly sum_tree.py:53-57.  Rows are then gathered cooperatively:
 // 8 lanes fetch one 128-byte row with float4 loads, the warp's 32 output rows are written contiguously.
-__global__ void __launch_bounds__(kThreads) k_per_sample_lane(ReplayDev R, long long B, long long Bglobal, long long shard_off,
+constexpr int kLaneThreads = 128;
+__global__ void __launch_bounds__(kLaneThreads) k_per_sample_lane(ReplayDev R, long long B, long long Bglobal, long long shard_off,
                                                               double beta, const double* __restrict__ u, unsigned long long seed,
                                                               unsigned long long counter, unsigned agent, long long* __restrict__ out_nodes,
                                                               float* __restrict__ out_w, float* __restrict__ out_rows,
                                                               double* __restrict__ out_leaf_p) {
   __shared__ double s_max_w;
   const int lane = threadIdx.x & 31;
-  const long long i = blockIdx.x * static_cast<long long>(kThreads) + threadIdx.x;
+  const long long i = blockIdx.x * static_cast<long long>(kLaneThreads) + threadIdx.x;
   const long long n_nodes = 2 * R.cap - 1;
   const double* __restrict__ tree = R.tree;
   const double total = __ldg(tree);
   const long long size = R.st->size;
-  if (out_w != nullptr && threadIdx.x == kThreads - 1)
+  if (out_w != nullptr && threadIdx.x == kLaneThreads - 1)
     s_max_w = is_weight_max(static_cast<double>(size), total, static_cast<double>(R.st->min_p), beta);
   long long leaf = R.cap - 1;
   double pv = 0.0, numer = 1.0;
