@@ -539,7 +539,8 @@ extern "C" int32_t rmc_learner_create(rmc_learner_t** out, const rmc_net_spec_t*
   RMC_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
   l->max_smem_optin = max_optin;
   if (l->smem_bytes > max_optin) return fail(RMC_ERR_UNSUPPORTED, "rmc_learner_create: parameter blob does not fit shared memory");
-  RMC_CUDA(cudaFuncSetAttribute(k_learner_step, cudaFuncAttributeMaxDynamicSharedMemorySize, l->smem_bytes));
+  RMC_CUDA(cudaFuncSetAttribute(k_learner_step<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, l->smem_bytes));
+  RMC_CUDA(cudaFuncSetAttribute(k_learner_step<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, l->smem_bytes));
   RMC_CUDA(cudaFuncSetAttribute(k_mlp_infer, cudaFuncAttributeMaxDynamicSharedMemorySize, l->smem_bytes));
   const std::vector<int> map = make_param_map(l->L);
   l->P = static_cast<long long>(map.size());
@@ -708,10 +709,11 @@ static int launch_mode() {
   }
   return mode;
 }
-static int32_t launch_step(dim3 grid, void** args, size_t smem, cudaStream_t st) {
+static int32_t launch_step(dim3 grid, void** args, size_t smem, cudaStream_t st, bool one_tile) {
   const int mode = launch_mode();
+  void* fn = one_tile ? reinterpret_cast<void*>(k_learner_step<true>) : reinterpret_cast<void*>(k_learner_step<false>);
   if (mode == 0) {
-    RMC_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_learner_step), grid, dim3(kThreads, 1, 1), args, smem, st));
+    RMC_CUDA(cudaLaunchCooperativeKernel(fn, grid, dim3(kThreads, 1, 1), args, smem, st));
   } else {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid; cfg.blockDim = dim3(kThreads, 1, 1); cfg.dynamicSmemBytes = smem; cfg.stream = st;
@@ -721,7 +723,7 @@ static int32_t launch_step(dim3 grid, void** args, size_t smem, cudaStream_t st)
     at[1].id = cudaLaunchAttributeCooperative;
     at[1].val.cooperative = 1;
     cfg.attrs = at; cfg.numAttrs = (mode == 2) ? 1 : (mode == 3) ? 2 : 0;
-    RMC_CUDA(cudaLaunchKernelExC(&cfg, reinterpret_cast<void*>(k_learner_step), args));
+    RMC_CUDA(cudaLaunchKernelExC(&cfg, fn, args));
   }
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return RMC_OK;
@@ -900,7 +902,7 @@ extern "C" int32_t rmc_learner_step(rmc_learner_t* l, rmc_replay_t* r, const rmc
   l->last_grid = G;
   const AgentCtx* many = nullptr;
   void* args[] = {&single, &many, &S};
-  if (int32_t e = launch_step(dim3(G, 1, 1), args, static_cast<size_t>(l->smem_bytes), st)) return e;
+  if (int32_t e = launch_step(dim3(G, 1, 1), args, static_cast<size_t>(l->smem_bytes), st, n_tiles <= S.n_row_ctas)) return e;
   if (rows && phase_b) l->barrier_count = S.barrier_target;
   if ((a->phases & RMC_PH_FORWARD) && phase_b) l->loss_epoch = S.epoch;
   if (a->phases & RMC_PH_ADAM) ++l->online_version;
@@ -1304,7 +1306,7 @@ extern "C" int32_t rmc_group_step(rmc_group_t* g, const rmc_step_args_t* a, rmc_
   AgentCtx single = l0->ctx;
   const AgentCtx* many = g->ctx_dev;
   void* args[] = {&single, &many, &S};
-  if (int32_t e = launch_step(dim3(G, g->n, 1), args, static_cast<size_t>(l0->smem_bytes), st)) return e;
+  if (int32_t e = launch_step(dim3(G, g->n, 1), args, static_cast<size_t>(l0->smem_bytes), st, n_tiles <= S.n_row_ctas)) return e;
   if (rows && phase_b) g->barrier_count = S.barrier_target;
   return RMC_OK;
 }

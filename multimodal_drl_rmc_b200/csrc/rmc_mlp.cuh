@@ -404,6 +404,10 @@ __device__ void wgrad_run_unit(const AgentCtx& C, const StepScalars& S, int u, b
 }
 
 // ------------------------------------------------------------------ the fused learner step
+// Two instantiations: kOneTile = true when every row CTA owns at most one 4-row tile (the default single-agent
+// batches: rows and Q_target stay in shared memory, role split), false for ensembles / large batches (several tiles per
+// CTA).  Splitting them keeps each kernel's straight-line code small: the step is sensitive to instruction-fetch stalls.
+template <bool kOneTile>
 __global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, const AgentCtx* __restrict__ many, StepScalars S) {
   extern __shared__ __align__(16) float smem[];
   // private copy of the context: field reads become register / local-memory accesses that the compiler can hoist
@@ -451,7 +455,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, c
   // Role split: when every row CTA owns one tile and enough CTAs are idle in phase A, CTA n_tiles+t computes
   // Q_target(s') of tile t concurrently (it repeats tile t's sampling -- same uniforms, same leaves -- and stages
   // only the target blob), while row CTA t stages only the online blob and picks Q_target up through a flag.
-  const bool one_tile = n_tiles <= S.n_row_ctas;   // every row CTA owns at most one tile: rows / Q_target stay in smem
+  constexpr bool one_tile = kOneTile;               // == (n_tiles <= S.n_row_ctas), chosen by the host: rows / Q_target stay in smem
   const bool split = one_tile && ((S.phases & 3) == 3) && (static_cast<long long>(G) >= 2 * n_tiles);
   const bool is_row = do_rows && cta < S.n_row_ctas && cta < n_tiles;
   const bool is_tgt = do_rows && split && cta >= n_tiles && cta < 2 * n_tiles;
@@ -475,7 +479,42 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, c
     // warps 0..kTM-1: one sample each; warp kTM meanwhile computes the max IS weight (replay_memory.py:76-77),
     // which the samplers pick up at a 5-warp named barrier after their own descent.
     const bool tree_sampling = C.rp.prioritized != 0;
-    if (S.phases & 1) {
+    if ((S.phases & 1) && !one_tile) {
+      // several tiles per CTA (ensembles, large batches without the grid-wide sampler): all 8 warps draw this CTA's
+      // samples, 8 descents in flight instead of 4; rows go straight to the L2-resident scratch
+      if (tree_sampling && tid == 0)
+        sTop[kTopNodes] = is_weight_max(static_cast<double>(size), total, static_cast<double>(min_p_f), S.beta);
+      __syncthreads();
+      const long long my_tiles = (n_tiles - tile0 + S.n_row_ctas - 1) / S.n_row_ctas;
+      for (long long s = warp; s < my_tiles * kTM; s += kWarps) {
+        const long long i = (tile0 + (s / kTM) * S.n_row_ctas) * kTM + (s % kTM);
+        if (i >= B) continue;
+        long long slot = 0, node = 0;
+        double p = 0.0, numer = 1.0;
+        if (tree_sampling) {
+          const long long gi = S.shard_off + i;
+          const double ui = (S.u != nullptr) ? S.u[agent * B + i] : philox_uniform(S.seed, S.counter, agent, static_cast<uint32_t>(gi));
+          node = per_descend_cached(sTop, n_top, C.rp.tree, n_nodes, stratum_value(total, S.Bglobal, gi, ui), &p);
+          slot = node - first_leaf;
+        } else {
+          const long long pos = (S.idx != nullptr) ? S.idx[agent * B + i]
+                                                   : static_cast<long long>(feistel_perm(S.shard_off + i, size, S.seed, S.counter, agent));
+          slot = deque_pos_to_slot(pos, size, dp, C.rp.cap);
+          node = slot;
+        }
+        const RowRegs rr = gather_row_load(C.rp, slot);            // row loads in flight during the pow
+        if (tree_sampling) numer = pow(static_cast<double>(size) * (p / total), -S.beta);
+        float* dst = C.X + i * rf;
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+          if (lane + 32 * q < rf) dst[lane + 32 * q] = rr.v[q];
+        if (lane == 0) {
+          C.nodes[i] = node;
+          C.is_w[i] = tree_sampling ? static_cast<float>(numer / sTop[kTopNodes]) : 1.f;
+          C.leaf_p[i] = p;
+        }
+      }
+    } else if (S.phases & 1) {
       bool first_iter = true;
       for (long long tile = tile0; tile < n_tiles; tile += S.n_row_ctas) {
         if (warp < kTM) {
@@ -528,7 +567,27 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, c
     if (do_fwd) {
       wait_params(bar, parity);
       RMC_STAMP(C, 2);
-      if (!split || is_tgt)
+      if (!one_tile) {
+        // several tiles per CTA: Q_target(s') of TWO tiles per pass (8 rows share one sweep over the target weights)
+        for (long long ta = tile0; ta < n_tiles; ta += 2 * S.n_row_ctas) {
+          const long long tb = ta + S.n_row_ctas;
+          for (int t = tid; t < kR * D; t += kThreads) {
+            const int r = t / D, d = t % D;
+            const long long tl = (r < kTM) ? ta : tb;
+            const long long i = tl * kTM + (r % kTM);
+            sXT[d * kR + r] = (tl < n_tiles && i < B) ? __ldcg(C.X + i * rf + D + d) : 0.f;
+          }
+          __syncthreads();
+          mlp_forward<kR>(sW, L, sXT, sH1T, sH2, sPart, sQ, nullptr);
+          if (tid < kR * kQLD) {
+            const int r = tid / kQLD;
+            const long long tl = (r < kTM) ? ta : tb;
+            const long long i = tl * kTM + (r % kTM);
+            if (tl < n_tiles && i < B) C.QT[i * kQLD + (tid % kQLD)] = sQ[tid];
+          }
+          __syncthreads();
+        }
+      } else if (!split || is_tgt)
       for (long long tile = tile0; tile < n_tiles; tile += S.n_row_ctas) {
         // x^T of the s' rows -> sXT[d][0..3]
         for (int t = tid; t < kTM * D; t += kThreads) {
