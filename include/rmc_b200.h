@@ -100,6 +100,21 @@ enum rmc_phase {
 enum rmc_precision { RMC_PREC_FP32 = 0, RMC_PREC_BF16_TC = 1 };
 #define RMC_PH_LEARN (RMC_PH_SAMPLE | RMC_PH_FORWARD | RMC_PH_PRIORITY | RMC_PH_BACKWARD | RMC_PH_ADAM)
 
+/* The repo-HEAD network (env/dqn_config.py:66-193 TwoStreamHybridNetwork + network_config): the state is
+ * [macro vector | grid flattened C,H,W]; the grid goes through n_conv Conv2d(3x3, padding 1, stride (sh, sw)) + act
+ * layers, is flattened and concatenated with the macro vector (flatten first, macro last), then n_dense
+ * Linear + act layers feed the heads (fc_val/fc_adv or fc_out, dqn/network.py:50-117).  Parameters travel in
+ * torch state_dict() order: net.cnn_stream.{0,2,..}.{weight,bias}, net.dense_stream.{0,2,..}.{weight,bias}, heads. */
+typedef struct {
+  int32_t macro_len;                 /* 14                                   */
+  int32_t grid_c, grid_h, grid_w;    /* 2, 27, 5                             */
+  int32_t n_conv;                    /* 3 (<= 4)                             */
+  int32_t conv_out[4], conv_sh[4], conv_sw[4];   /* 32,64,64 ; (1,1),(2,1),(2,2) */
+  int32_t n_dense;                   /* 2 (<= 3)                             */
+  int32_t dense_out[3];              /* 512, 256                             */
+  int32_t n_actions, dueling, double_dqn, prioritized, activation;
+} rmc_hybrid_spec_t;
+
 /* Per-step inputs of a learner step. */
 typedef struct {
   int64_t batch;            /* B                                                            */
@@ -191,6 +206,11 @@ int32_t rmc_per_update_from_td(rmc_replay_t* r, const int64_t* nodes_dev, const 
  * rmc_learner_set_params (the Python mirror initialises with torch's nn.Linear init). */
 int32_t rmc_learner_create(rmc_learner_t** out, const rmc_net_spec_t* spec, const rmc_hyper_t* hyper,
                            int64_t max_batch, int32_t device);
+/* Same handle type for the hybrid CNN + MLP network: every rmc_learner_* entry point below (set/get_params,
+ * step, output, loss, q_values, heads, act) dispatches on the network kind.  Exact fp32 path only; no
+ * tensor-core mode, ensemble launch or sharded step for this network yet. */
+int32_t rmc_learner_create_hybrid(rmc_learner_t** out, const rmc_hybrid_spec_t* spec, const rmc_hyper_t* hyper,
+                                  int64_t max_batch, int32_t device);
 int32_t rmc_learner_destroy(rmc_learner_t* l);
 int64_t rmc_learner_param_count(const rmc_learner_t* l);
 

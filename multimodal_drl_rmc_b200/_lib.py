@@ -34,6 +34,15 @@ class NetSpec(C.Structure):
                 ("activation", C.c_int32)]
 
 
+class HybridSpec(C.Structure):
+    """rmc_hybrid_spec_t: the repo-HEAD two-stream network (env/dqn_config.py:66-193)."""
+    _fields_ = [("macro_len", C.c_int32), ("grid_c", C.c_int32), ("grid_h", C.c_int32), ("grid_w", C.c_int32),
+                ("n_conv", C.c_int32), ("conv_out", C.c_int32 * 4), ("conv_sh", C.c_int32 * 4), ("conv_sw", C.c_int32 * 4),
+                ("n_dense", C.c_int32), ("dense_out", C.c_int32 * 3),
+                ("n_actions", C.c_int32), ("dueling", C.c_int32), ("double_dqn", C.c_int32), ("prioritized", C.c_int32),
+                ("activation", C.c_int32)]
+
+
 class Hyper(C.Structure):
     _fields_ = [("lr", C.c_double), ("adam_beta1", C.c_double), ("adam_beta2", C.c_double), ("adam_eps", C.c_double),
                 ("gamma", C.c_double), ("polyak_k", C.c_double), ("per_eps", C.c_double), ("per_alpha", C.c_double),
@@ -108,6 +117,7 @@ _SIGS = {
     "rmc_per_update": (_i32, [_vp, _vp, _vp, _i64, _vp]),
     "rmc_per_update_from_td": (_i32, [_vp, _vp, _vp, _i64, _f32, _f32, _f32, _vp, _vp]),
     "rmc_learner_create": (_i32, [C.POINTER(_vp), C.POINTER(NetSpec), C.POINTER(Hyper), _i64, _i32]),
+    "rmc_learner_create_hybrid": (_i32, [C.POINTER(_vp), C.POINTER(HybridSpec), C.POINTER(Hyper), _i64, _i32]),
     "rmc_learner_destroy": (_i32, [_vp]),
     "rmc_learner_param_count": (_i64, [_vp]),
     "rmc_learner_set_params": (_i32, [_vp, _i32, _vp, _i64, _i32, _vp]),

@@ -88,7 +88,7 @@ class Agent:
                            1e-4, 0.6, 1.0)
         self._lh = LearnerHandle(self.online_network._obs_dim, output_dim, self._DUELING, self._DOUBLE, self._PER,
                                  max(int(batch_size), 1), self.device.index, hyper,
-                                 activation=self.online_network._activation)
+                                 activation=self.online_network._activation, hybrid=self.online_network._hybrid)
         self.online_network._bind(self._lh, _lib.ONLINE)
         self.target_network._bind(self._lh, _lib.TARGET)
         self.update_target_network(force=True)

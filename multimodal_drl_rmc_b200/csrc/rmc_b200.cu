@@ -18,6 +18,7 @@
 #include "rmc_tc_train.cuh"
 #include "rmc_comm.cuh"
 #include "rmc_infer64.cuh"
+#include "rmc_hybrid.cuh"
 #include "rmc_tree.cuh"
 
 using namespace rmc;
@@ -101,6 +102,10 @@ struct rmc_learner {
   unsigned long long tc_bwd_version = 0;
   unsigned long long target_version = 1, tc_target_version = 0;
   TcTrainBufs tct{};
+  // hybrid CNN+MLP network (rmc_hybrid.cuh): per-row activation / delta records
+  bool hybrid = false;
+  HybNet H{};
+  float *rec_on = nullptr, *rec_tg = nullptr, *drec = nullptr;
   // act staging
   float* act_pin_obs = nullptr; long long* act_pin_out = nullptr; float* act_dev_obs = nullptr; long long* act_dev_out = nullptr;
   long long act_cap = 0;
@@ -164,7 +169,7 @@ __global__ void k_init_state(ReplayState* st) {
 // ------------------------------------------------------------------------------ replay
 extern "C" int32_t rmc_replay_create(rmc_replay_t** out, int64_t capacity, int32_t obs_dim, int32_t prioritized,
                                      int32_t device) {
-  if (!out || capacity < 1 || obs_dim < 1 || obs_dim > kMaxD) return fail(RMC_ERR_ARG, "rmc_replay_create: bad capacity/obs_dim");
+  if (!out || capacity < 1 || obs_dim < 1 || obs_dim > 4096) return fail(RMC_ERR_ARG, "rmc_replay_create: bad capacity/obs_dim");
   if (capacity > (1ll << 30)) return fail(RMC_ERR_ARG, "rmc_replay_create: capacity too large");
   if (int32_t e = use_device(device)) return e;
   auto* r = new rmc_replay();
@@ -272,7 +277,7 @@ static int32_t push_impl(rmc_replay* r, const float* obs, const int64_t* act, co
   if (!r || n < 0) return fail(RMC_ERR_ARG, "rmc_replay_push: bad args");
   if (n == 0) return RMC_OK;
   if (int32_t e = use_device(r->device)) return e;
-  if (host && n <= 8 && n <= r->cap) {
+  if (host && n <= 8 && n <= r->cap && r->rf <= kMaxRowFloats) {
     // the trainer's per-env-step push: the packed rows ride in the kernel-argument buffer of the launch (no
     // staging copy, no event) -- that launch IS the host->device transfer of these n*row_floats*4 bytes
     TinyRows tr;
@@ -867,6 +872,239 @@ static int32_t step_tc(rmc_learner* l, rmc_replay* r, const rmc_step_args_t* a, 
   return RMC_OK;
 }
 
+// ------------------------------------------------------------------------------ hybrid CNN + MLP learner
+extern "C" int32_t rmc_learner_create_hybrid(rmc_learner_t** out, const rmc_hybrid_spec_t* sp, const rmc_hyper_t* hyper, int64_t max_batch,
+                                             int32_t device) {
+  if (!out || !sp || !hyper || max_batch < 1) return fail(RMC_ERR_ARG, "rmc_learner_create_hybrid: null/bad args");
+  if (sp->n_conv < 1 || sp->n_conv > kHybMaxConv || sp->n_dense < 1 || sp->n_dense > kHybMaxDense || sp->n_actions < 1 || sp->n_actions > 15 ||
+      sp->macro_len < 0 || sp->grid_c < 1 || sp->grid_h < 1 || sp->grid_w < 1)
+    return fail(RMC_ERR_UNSUPPORTED, "rmc_learner_create_hybrid: 1..4 conv layers, 1..3 dense layers, n_actions 1..15");
+  if (sp->activation != RMC_ACT_RELU && sp->activation != RMC_ACT_ELU) return fail(RMC_ERR_UNSUPPORTED, "rmc_learner_create_hybrid: activation must be ReLU or ELU(alpha=1)");
+  if (max_batch > 4096) return fail(RMC_ERR_UNSUPPORTED, "rmc_learner_create_hybrid: max_batch above 4096");
+  if (int32_t e = use_device(device)) return e;
+  HybNet N{};
+  N.n_conv = sp->n_conv; N.n_dense = sp->n_dense;
+  N.macro_len = sp->macro_len; N.grid_len = sp->grid_c * sp->grid_h * sp->grid_w; N.D = N.macro_len + N.grid_len;
+  N.A = sp->n_actions; N.dueling = sp->dueling ? 1 : 0; N.NH = N.dueling ? N.A + 1 : N.A; N.act = (sp->activation == RMC_ACT_ELU) ? 1 : 0;
+  int po = 0, ro = 0;                       // parameter offset (torch state_dict order), record offset
+  int ic = sp->grid_c, ih = sp->grid_h, iw = sp->grid_w, prev_out = -1;
+  for (int i = 0; i < N.n_conv; ++i) {     // net.cnn_stream.{2i}.weight / .bias  (env/dqn_config.py:84-93: 3x3, padding 1)
+    HybConv& c = N.conv[i];
+    c.ic = ic; c.ih = ih; c.iw = iw; c.oc = sp->conv_out[i]; c.sh = sp->conv_sh[i]; c.sw = sp->conv_sw[i];
+    if (c.oc < 4 || (c.oc & 3) || c.sh < 1 || c.sw < 1 || (i > 0 && (c.ic & 3))) return fail(RMC_ERR_UNSUPPORTED, "rmc_learner_create_hybrid: conv channels must be multiples of 4");
+    c.oh = (ih + 2 - 3) / c.sh + 1; c.ow = (iw + 2 - 3) / c.sw + 1;
+    c.w_off = po; po += c.oc * c.ic * 9;
+    c.b_off = po; po += c.oc;
+    c.in_off = prev_out;
+    c.out_off = ro;
+    if (c.ic * c.ih * c.iw > 11000 || c.oc * c.oh * c.ow > 11000) return fail(RMC_ERR_UNSUPPORTED, "rmc_learner_create_hybrid: feature map too large for the shared-memory staging");
+    prev_out = ro;
+    ro += c.oc * c.oh * c.ow;
+    ic = c.oc; ih = c.oh; iw = c.ow;
+  }
+  N.conv_flat = ic * ih * iw;
+  N.feat_off = N.conv[N.n_conv - 1].out_off;
+  N.feat_len = N.conv_flat + N.macro_len;
+  ro = round4(N.feat_off + N.feat_len);
+  int in_len = N.feat_len, in_off = N.feat_off;
+  for (int i = 0; i < N.n_dense; ++i) {    // net.dense_stream.{2i}.weight / .bias
+    HybDense& d = N.dense[i];
+    d.in = in_len; d.out = sp->dense_out[i];
+    if (d.out < 1) return fail(RMC_ERR_ARG, "rmc_learner_create_hybrid: dense width");
+    d.w_off = po; po += d.out * d.in;
+    d.b_off = po; po += d.out;
+    d.in_off = in_off; d.out_off = ro;
+    in_off = ro; in_len = d.out;
+    ro = round4(ro + d.out);
+  }
+  N.last_off = in_off; N.last_len = in_len;
+  N.head_off = ro; ro += kQLD;
+  N.rec = round4(ro);
+  if (N.dueling) {                          // fc_val.weight, fc_val.bias, fc_adv.weight, fc_adv.bias (network.py:81-82)
+    N.hw_off[0] = po; po += N.last_len; N.hb_off[0] = po; po += 1;
+    N.hw_off[1] = po; po += N.A * N.last_len; N.hb_off[1] = po; po += N.A;
+  } else {                                  // fc_out.weight, fc_out.bias (network.py:54)
+    N.hw_off[0] = po; po += N.A * N.last_len; N.hb_off[0] = po; po += N.A;
+    N.hw_off[1] = N.hb_off[1] = -1;
+  }
+  const int P = po;
+  N.total = round4(P);
+  auto* l = new rmc_learner();
+  l->device = device; l->hybrid = true; l->H = N; l->hyper = *hyper; l->max_batch = max_batch;
+  l->spec.obs_dim = N.D; l->spec.n_actions = N.A; l->spec.dueling = N.dueling; l->spec.double_dqn = sp->double_dqn; l->spec.prioritized = sp->prioritized;
+  l->spec.activation = sp->activation; l->spec.hidden1 = 0; l->spec.hidden2 = 0;
+  l->L = NetLayout{}; l->L.D = N.D; l->L.A = N.A; l->L.NH = N.NH; l->L.dueling = N.dueling; l->L.total = N.total; l->L.act = N.act;
+  l->P = P;
+  l->rf = round4(2 * N.D + 3);
+  RMC_CUDA(cudaDeviceGetAttribute(&l->num_sms, cudaDevAttrMultiProcessorCount, device));
+  int32_t e = RMC_OK;
+  for (int k = 0; k < 5; ++k)
+    if ((e = owned_alloc(l, &l->blobs[k], static_cast<size_t>(N.total)))) return e;
+  std::vector<int> map(static_cast<size_t>(P));
+  for (int i = 0; i < P; ++i) map[i] = i;  // the device layout IS the torch order
+  if ((e = owned_alloc(l, &l->map, map.size()))) return e;
+  RMC_CUDA(cudaMemcpy(l->map, map.data(), map.size() * sizeof(int), cudaMemcpyHostToDevice));
+  if ((e = owned_alloc(l, &l->io, map.size()))) return e;
+  AgentCtx& c = l->ctx;
+  c.L = l->L;
+  c.online = l->blobs[0]; c.target = l->blobs[1]; c.adam_m = l->blobs[2]; c.adam_v = l->blobs[3]; c.grads = l->blobs[4];
+  const size_t B = static_cast<size_t>(max_batch);
+  if ((e = owned_alloc(l, &c.nodes, B))) return e;
+  if ((e = owned_alloc(l, &c.leaf_p, B))) return e;
+  float** per_sample[] = {&c.is_w, &c.q_sa, &c.y, &c.abs_td, &c.hub, &c.pri, &c.gcoef};
+  for (float** p : per_sample)
+    if ((e = owned_alloc(l, p, B))) return e;
+  if ((e = owned_alloc(l, &c.QT, B * kQLD))) return e;
+  if ((e = owned_alloc(l, &c.QN, B * kQLD))) return e;
+  if ((e = owned_alloc(l, &c.Q, B * kQLD))) return e;
+  if ((e = owned_alloc(l, &c.DH, B * kQLD))) return e;
+  if ((e = owned_alloc(l, &c.X, B * l->rf))) return e;
+  if ((e = owned_alloc(l, &c.loss_part, 1024))) return e;
+  if ((e = owned_alloc(l, &c.loss, 1))) return e;
+  if ((e = owned_alloc(l, &c.barrier, 1))) return e;
+  if ((e = owned_alloc(l, &l->rec_on, 2 * B * N.rec))) return e;
+  if ((e = owned_alloc(l, &l->rec_tg, B * N.rec))) return e;
+  if ((e = owned_alloc(l, &l->drec, B * N.rec))) return e;
+  {
+    float* hp = nullptr;
+    float* dp = nullptr;
+    if (cudaHostAlloc(reinterpret_cast<void**>(&hp), 64, cudaHostAllocMapped) == cudaSuccess &&
+        cudaHostGetDevicePointer(reinterpret_cast<void**>(&dp), hp, 0) == cudaSuccess) {
+      hp[0] = 0.f; hp[1] = 0.f;
+      l->host_loss = hp;
+      c.host_loss = dp;
+    } else {
+      cudaGetLastError();
+      c.host_loss = nullptr;
+    }
+  }
+  RMC_CUDA(cudaDeviceSynchronize());
+  *out = l;
+  return RMC_OK;
+}
+
+static int32_t hyb_gemm(const HybGemm& G, cudaStream_t st) {
+  k_hyb_gemm<<<dim3(blocks_for(G.N, 64), blocks_for(G.M, 64), 1), 256, 0, st>>>(G);
+  RMC_KERNEL_OK();
+  return RMC_OK;
+}
+
+// one forward pass of R rows through the net with parameters P into the records `rec`
+static int32_t hybrid_forward(rmc_learner* l, const float* P, const HybSrc& src, float* rec, long long R, cudaStream_t st) {
+  const HybNet& N = l->H;
+  for (int i = 0; i < N.n_conv; ++i) {
+    const HybConv& c = N.conv[i];
+    k_hyb_conv_fwd<<<static_cast<unsigned>(R), 256, static_cast<size_t>(c.ic) * c.ih * c.iw * sizeof(float), st>>>(N, i, P, src, rec);
+    RMC_KERNEL_OK();
+  }
+  for (int i = 0; i < N.n_dense; ++i) {
+    const HybDense& d = N.dense[i];
+    HybGemm G{};
+    G.A = rec + d.in_off; G.a_sm = N.rec; G.a_sk = 1;
+    G.B = P + d.w_off; G.b_sk = 1; G.b_sn = d.in;
+    G.C = rec + d.out_off; G.c_sm = N.rec;
+    G.bias = P + d.b_off; G.M = static_cast<int>(R); G.N = d.out; G.K = d.in; G.epi = 0; G.act = N.act;
+    if (int32_t e = hyb_gemm(G, st)) return e;
+  }
+  k_hyb_heads_fwd<<<blocks_for(R, 8), 256, 0, st>>>(N, P, rec, R);
+  RMC_KERNEL_OK();
+  return RMC_OK;
+}
+
+static int32_t hybrid_step(rmc_learner* l, rmc_replay* r, const rmc_step_args_t* a, StepScalars& S, cudaStream_t st) {
+  const HybNet& N = l->H;
+  AgentCtx& C = l->ctx;
+  const long long B = a->batch;
+  const int ph = a->phases;
+  if (a->precision != RMC_PREC_FP32) return fail(RMC_ERR_UNSUPPORTED, "hybrid network: the exact fp32 path is the only one built");
+  if ((ph & RMC_PH_BACKWARD) && !(ph & RMC_PH_FORWARD)) return fail(RMC_ERR_ARG, "hybrid network: BACKWARD needs FORWARD in the same step");
+  if (ph & RMC_PH_SAMPLE) {
+    if (r->prioritized) {
+      if (int32_t e = launch_per_sample(r->dev, B, S.Bglobal, S.shard_off, S.beta, S.u, S.seed, S.counter, C.nodes, C.is_w, C.X, C.leaf_p, st)) return e;
+    } else {
+      k_uniform_sample<<<blocks_for(B, kWarps), kThreads, 0, st>>>(r->dev, B, S.shard_off, S.idx, S.seed, S.counter, 0u, C.nodes, C.X);
+      RMC_KERNEL_OK();
+    }
+  }
+  const HybSrc src_on{C.X, l->rf, B, N.D, 0};            // online pass: rows [0,B) = s', rows [B,2B) = s
+  const unsigned td_blocks = blocks_for(B, 128);
+  if (ph & RMC_PH_FORWARD) {
+    const HybSrc src_tg{C.X, l->rf, B, N.D, N.D};
+    if (int32_t e = hybrid_forward(l, C.online, src_on, l->rec_on, 2 * B, st)) return e;
+    if (int32_t e = hybrid_forward(l, C.target, src_tg, l->rec_tg, B, st)) return e;
+    k_hyb_td<<<td_blocks, 128, 0, st>>>(C, S, N, l->rec_on, l->rec_tg, l->drec);
+    RMC_KERNEL_OK();
+  }
+  if (ph & RMC_PH_BACKWARD) {
+    const float* rec_s = l->rec_on + B * N.rec;           // records of the s rows
+    k_hyb_heads_dgrad<<<blocks_for(B * N.last_len, 256), 256, 0, st>>>(N, C.online, rec_s, l->drec, B);
+    RMC_KERNEL_OK();
+    k_hyb_heads_wgrad<<<blocks_for(static_cast<long long>(N.NH) * N.last_len, 256), 256, 0, st>>>(N, rec_s, l->drec, B, C.grads);
+    RMC_KERNEL_OK();
+    for (int i = N.n_dense - 1; i >= 0; --i) {
+      const HybDense& d = N.dense[i];
+      HybGemm W{};                                        // dW[n][k] = sum_r dZ[r][n] X[r][k]
+      W.A = l->drec + d.out_off; W.a_sm = 1; W.a_sk = N.rec;
+      W.B = rec_s + d.in_off; W.b_sk = N.rec; W.b_sn = 1;
+      W.C = C.grads + d.w_off; W.c_sm = d.in; W.M = d.out; W.N = d.in; W.K = static_cast<int>(B); W.epi = 2;
+      if (int32_t e = hyb_gemm(W, st)) return e;
+      k_hyb_colsum<<<blocks_for(d.out, 128), 128, 0, st>>>(l->drec + d.out_off, N.rec, static_cast<int>(B), d.out, C.grads + d.b_off);
+      RMC_KERNEL_OK();
+      HybGemm G{};                                        // dX[r][k] = (sum_n dZ[r][n] W[n][k]) * act'(X[r][k])
+      G.A = l->drec + d.out_off; G.a_sm = N.rec; G.a_sk = 1;
+      G.B = C.online + d.w_off; G.b_sk = d.in; G.b_sn = 1;
+      G.C = l->drec + d.in_off; G.c_sm = N.rec; G.H = rec_s + d.in_off; G.h_sm = N.rec;
+      G.M = static_cast<int>(B); G.N = (i == 0) ? N.conv_flat : d.in; G.K = d.out; G.epi = 1; G.act = N.act;
+      if (int32_t e = hyb_gemm(G, st)) return e;
+    }
+    for (int i = N.n_conv - 1; i >= 0; --i) {
+      const HybConv& c = N.conv[i];
+      k_hyb_conv_wgrad<<<static_cast<unsigned>(c.oc * c.ic), 64, 0, st>>>(N, i, src_on, rec_s, l->drec, B, C.grads);
+      RMC_KERNEL_OK();
+      if (i > 0) {
+        k_hyb_conv_dgrad<<<static_cast<unsigned>(B), 256, static_cast<size_t>(c.oc) * c.oh * c.ow * sizeof(float), st>>>(N, i, C.online, rec_s, l->drec);
+        RMC_KERNEL_OK();
+      }
+    }
+  }
+  if (ph & (RMC_PH_FORWARD | RMC_PH_ADAM | RMC_PH_POLYAK | RMC_PH_HARDSYNC)) {
+    l->epoch = (l->epoch >= 0x7fffffffu) ? 1u : l->epoch + 1u;
+    S.epoch = l->epoch;
+    const int write_loss = (ph & RMC_PH_FORWARD) ? 1 : 0;
+    k_hyb_adam<<<blocks_for(N.total, 256), 256, 0, st>>>(C, S, N.total, static_cast<int>(td_blocks), write_loss);
+    RMC_KERNEL_OK();
+    if (write_loss) l->loss_epoch = S.epoch;
+    if (ph & RMC_PH_ADAM) ++l->online_version;
+    if (ph & (RMC_PH_POLYAK | RMC_PH_HARDSYNC)) ++l->target_version;
+  }
+  if ((ph & RMC_PH_PRIORITY) && l->spec.prioritized) {
+    if (B <= kTreeCtaMax) {
+      k_tree_update_small<<<1, kThreads, 0, st>>>(r->dev, C.nodes, nullptr, C.abs_td, C.pri, B, S.per_eps, S.per_alpha, S.per_pmax);
+      RMC_KERNEL_OK();
+    } else {
+      k_td_to_pri<<<blocks_for(B, 256), 256, 0, st>>>(C.abs_td, C.pri, B, S.per_eps, S.per_alpha, S.per_pmax);
+      RMC_KERNEL_OK();
+      if (int32_t e = tree_update_large(r, C.nodes, C.pri, B, false, st)) return e;
+    }
+  }
+  return RMC_OK;
+}
+
+// act / Q values / raw heads of n states [n][D] through the hybrid net (chunks of at most 2 * max_batch rows)
+static int32_t hybrid_infer(rmc_learner* l, const float* params, const float* obs_dev, long long n, long long* actions, float* q, int mode, cudaStream_t st) {
+  const HybNet& N = l->H;
+  const long long cap = 2 * l->max_batch;
+  const int per_row = (mode == 1) ? N.A : N.NH;
+  for (long long off = 0; off < n; off += cap) {
+    const long long m = std::min(cap, n - off);
+    const HybSrc src{obs_dev + off * N.D, N.D, m, 0, 0};
+    if (int32_t e = hybrid_forward(l, params, src, l->rec_on, m, st)) return e;
+    k_hyb_outputs<<<blocks_for(m, 128), 128, 0, st>>>(N, l->rec_on, m, actions ? actions + off : nullptr, q ? q + off * per_row : nullptr, mode);
+    RMC_KERNEL_OK();
+  }
+  return RMC_OK;
+}
+
 extern "C" int32_t rmc_learner_step(rmc_learner_t* l, rmc_replay_t* r, const rmc_step_args_t* a, rmc_stream_t s) {
   if (int32_t e = check_step(l, r, a)) return e;
   if (int32_t e = use_device(l->device)) return e;
@@ -876,6 +1114,7 @@ extern "C" int32_t rmc_learner_step(rmc_learner_t* l, rmc_replay_t* r, const rmc
   if (int32_t e = fill_scalars(l, a, &S)) return e;
   l->ctx.rp = r->dev;
   l->last_batch = a->batch;
+  if (l->hybrid) return hybrid_step(l, r, a, S, st);
   if (a->precision == RMC_PREC_BF16_TC) return step_tc(l, r, a, S, st);
   if (a->precision != RMC_PREC_FP32) return fail(RMC_ERR_ARG, "rmc_learner_step: unknown precision");
   const int G = grid_for(l, a->batch, l->num_sms);
@@ -925,6 +1164,7 @@ static void shard_range_c(long long batch, int rank, int world, long long* lo, l
 extern "C" int32_t rmc_comm_create(rmc_comm_t** out, rmc_learner_t* l, int32_t rank, int32_t world, int64_t global_batch_max) {
   if (!out || !l || world < 1 || world > kCommMaxWorld || rank < 0 || rank >= world || global_batch_max < world)
     return fail(RMC_ERR_ARG, "rmc_comm_create: bad args (world must be 1..8)");
+  if (l->hybrid) return fail(RMC_ERR_UNSUPPORTED, "rmc_comm_create: the sharded step is built for the macro MLP only");
   if (int32_t e = use_device(l->device)) return e;
   auto* c = new rmc_comm();
   c->device = l->device; c->rank = rank; c->world = world; c->learner = l;
@@ -1134,6 +1374,7 @@ extern "C" int32_t rmc_learner_loss_sync(rmc_learner_t* l, float* out_host, rmc_
 
 static int32_t infer_launch(rmc_learner* l, const float* params, const float* obs_dev, long long n, long long* actions, float* q, int mode,
                             cudaStream_t st) {
+  if (l->hybrid) return hybrid_infer(l, params, obs_dev, n, actions, q, mode, st);
   // large batches: 64-row tiles (every weight fetched from shared memory serves 64 rows; rmc_infer64.cuh)
   const int big_bytes = big_smem_floats(l->L.total) * 4;
   if (n >= 1024 && l->L.D <= 16 && big_bytes <= l->max_smem_optin) {
@@ -1174,6 +1415,7 @@ extern "C" int32_t rmc_learner_act(rmc_learner_t* l, const float* obs_dev, int64
 
 // tensor-core (tcgen05, bf16 operands / fp32 accumulate) mode of act / heads: looser, stated bound (see rmc_tc.cuh)
 static int32_t infer_tc(rmc_learner* l, const float* obs_dev, long long n, long long* actions, float* heads, int mode, cudaStream_t st) {
+  if (l->hybrid) return fail(RMC_ERR_UNSUPPORTED, "tensor-core act mode: built for the macro MLP only");
   if (l->L.D > kTcK1) return fail(RMC_ERR_UNSUPPORTED, "tensor-core act mode: obs_dim must be <= 16");
   if (l->L.act != 0) return fail(RMC_ERR_UNSUPPORTED, "tensor-core modes are built for ReLU bodies only");
   if (l->tc_packed == nullptr) {
@@ -1240,6 +1482,7 @@ extern "C" int32_t rmc_group_create(rmc_group_t** out, rmc_learner_t* const* lea
     rmc_learner* l = learners[i];
     rmc_replay* r = replays[i];
     if (!l || !r) return fail(RMC_ERR_ARG, "rmc_group_create: null member");
+    if (l->hybrid) return fail(RMC_ERR_UNSUPPORTED, "rmc_group_create: ensemble launches are built for the macro MLP only");
     if (std::memcmp(&l->spec, &l0->spec, sizeof(rmc_net_spec_t)) != 0 || l->max_batch != l0->max_batch || l->device != l0->device)
       return fail(RMC_ERR_ARG, "rmc_group_create: members must share spec, max_batch and device");
     if (r->D != l->spec.obs_dim || (r->prioritized != 0) != (l->spec.prioritized != 0) || r->device != l->device)

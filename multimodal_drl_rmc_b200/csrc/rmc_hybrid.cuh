@@ -1,0 +1,447 @@
+// rmc_hybrid.cuh -- the repo-HEAD network of the reference behind the same learner step:
+// env/dqn_config.py:66-193 TwoStreamHybridNetwork
+//     state[284] = macro[14] | grid[2][27][5]
+//     grid -> Conv(2->32, 3x3, s(1,1), p1) -> act -> Conv(32->64, s(2,1)) -> act -> Conv(64->64, s(2,2)) -> act -> flatten[1344]
+//     cat(flatten, macro)[1358] -> Linear(512) -> act -> Linear(256) -> act -> {fc_val[1], fc_adv[A]} | fc_out[A]
+// Exact fp32 path (fp32 operands, fmaf accumulation): first correct form, one kernel per layer and direction.
+// Parameters live in ONE flat blob in torch state_dict() order (conv weights [oc][ic][3][3], linear weights
+// [out][in]), so set/get_params are plain copies and the Adam kernel walks the blob linearly.
+// Activations of a pass live in a per-row scratch record (HybNet::rec floats): conv outputs | features (last conv
+// output ++ macro) | dense outputs | heads[16]; the backward pass writes deltas into a record of the same layout.
+#pragma once
+#include "rmc_mlp.cuh"
+
+namespace rmc {
+
+constexpr int kHybMaxConv = 4, kHybMaxDense = 3;
+
+struct HybConv { int ic, ih, iw, oc, oh, ow, sh, sw; int w_off, b_off; int in_off, out_off; };   // offsets: parameters / record
+struct HybDense { int in, out; int w_off, b_off; int in_off, out_off; };
+struct HybNet {
+  int n_conv, n_dense;
+  HybConv conv[kHybMaxConv];
+  HybDense dense[kHybMaxDense];
+  int macro_len, grid_len, D;       // D = macro_len + grid_len (state length)
+  int feat_off, feat_len, conv_flat;// features = [last conv output (conv_flat) | macro]
+  int last_off, last_len;           // output of the last dense layer (input of the heads)
+  int head_off;                     // heads[16] inside the record
+  int hw_off[2], hb_off[2];         // dueling: {fc_val, fc_adv}; plain: {fc_out, -}
+  int A, NH, dueling, act;
+  int rec;                          // floats per record (multiple of 4)
+  int total;                        // parameter floats (torch order), padded to a multiple of 4
+};
+
+// which gathered row / column offset feeds pass-row r: online pass = [s' rows | s rows], target pass = s' rows,
+// inference = plain [n][D] matrix
+struct HybSrc { const float* base; long long stride; long long B; int off_first, off_second; };
+__device__ __forceinline__ const float* hyb_src_row(const HybSrc& s, long long r) {
+  return (r < s.B) ? s.base + r * s.stride + s.off_first : s.base + (r - s.B) * s.stride + s.off_second;
+}
+
+// ---------------------------------------------------------------------------------------------- convolution forward
+// one CTA per row: the layer's whole input (<= 4480 floats) is staged in shared memory; a thread owns 4 output channels
+// of one output pixel, so every input value fetched feeds 4 FMAs; weights are warp-broadcast L1 reads.
+__global__ void __launch_bounds__(256) k_hyb_conv_fwd(HybNet N, int li, const float* __restrict__ P, HybSrc src, float* __restrict__ rec_base) {
+  extern __shared__ float s_in[];
+  const HybConv c = N.conv[li];
+  const long long r = blockIdx.x;
+  float* rec = rec_base + r * N.rec;
+  const float* in = (li == 0) ? hyb_src_row(src, r) + N.macro_len : rec + c.in_off;
+  const int n_in = c.ic * c.ih * c.iw;
+  for (int t = threadIdx.x; t < n_in; t += blockDim.x) s_in[t] = in[t];
+  if (li == N.n_conv - 1)          // features = [flattened last conv output | macro]
+    for (int t = threadIdx.x; t < N.macro_len; t += blockDim.x) rec[N.feat_off + N.conv_flat + t] = hyb_src_row(src, r)[t];
+  __syncthreads();
+  const int npix = c.oh * c.ow, ng = c.oc >> 2;
+  const float* W = P + c.w_off;
+  for (int t = threadIdx.x; t < ng * npix; t += blockDim.x) {
+    const int g = t / npix, pix = t - g * npix;
+    const int oy = pix / c.ow, ox = pix - oy * c.ow;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    const int wstride = c.ic * 9;
+    const float* w0 = W + (4 * g) * wstride;
+    for (int ic = 0; ic < c.ic; ++ic) {
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int iy = oy * c.sh + ky - 1;
+        if (iy < 0 || iy >= c.ih) continue;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int ix = ox * c.sw + kx - 1;
+          if (ix < 0 || ix >= c.iw) continue;
+          const float x = s_in[(ic * c.ih + iy) * c.iw + ix];
+          const float* w = w0 + ic * 9 + ky * 3 + kx;
+          a0 = fmaf(x, __ldg(w), a0);
+          a1 = fmaf(x, __ldg(w + wstride), a1);
+          a2 = fmaf(x, __ldg(w + 2 * wstride), a2);
+          a3 = fmaf(x, __ldg(w + 3 * wstride), a3);
+        }
+      }
+    }
+    const float* b = P + c.b_off + 4 * g;
+    float* o = rec + c.out_off + (4 * g) * npix + pix;
+    o[0] = act_fwd(a0 + __ldg(b), N.act);
+    o[npix] = act_fwd(a1 + __ldg(b + 1), N.act);
+    o[2 * npix] = act_fwd(a2 + __ldg(b + 2), N.act);
+    o[3 * npix] = act_fwd(a3 + __ldg(b + 3), N.act);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- generic SGEMM
+// C[m][n] = sum_k A(m,k) * B(k,n) with arbitrary element strides (covers x.W^T, dY.W and dY^T.X), 64x64x16 tiles,
+// 256 threads, 4x4 register tiles, fixed summation order.
+//   epi 0: C = act(C + bias[n])            (forward)
+//   epi 1: C = C * act'(H[m][n])           (data gradient; H = the forward output of the layer below)
+//   epi 2: C as is                         (weight gradient, written into the gradient blob)
+struct HybGemm {
+  const float* A; long long a_sm, a_sk;
+  const float* B; long long b_sk, b_sn;
+  float* C; long long c_sm;
+  const float* bias;
+  const float* H; long long h_sm;
+  int M, N, K, epi, act;
+};
+__global__ void __launch_bounds__(256) k_hyb_gemm(HybGemm G) {
+  __shared__ float sA[16][65], sB[16][65];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  // loader mapping follows the unit-stride dimension of each operand
+  const bool a_kfast = G.a_sk == 1, b_kfast = G.b_sk == 1;
+  for (int k0 = 0; k0 < G.K; k0 += 16) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int t = tid + 256 * e;                     // 1024 elements per operand tile
+      {
+        const int kk = a_kfast ? (t & 15) : (t >> 6), mm = a_kfast ? (t >> 4) : (t & 63);
+        const int m = m0 + mm, k = k0 + kk;
+        sA[kk][mm] = (m < G.M && k < G.K) ? __ldg(G.A + m * G.a_sm + k * G.a_sk) : 0.f;
+      }
+      {
+        const int kk = b_kfast ? (t & 15) : (t >> 6), nn = b_kfast ? (t >> 4) : (t & 63);
+        const int n = n0 + nn, k = k0 + kk;
+        sB[kk][nn] = (n < G.N && k < G.K) ? __ldg(G.B + k * G.b_sk + n * G.b_sn) : 0.f;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = sA[kk][ty + 16 * i]; b[i] = sB[kk][tx + 16 * i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty + 16 * i;
+    if (m >= G.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx + 16 * j;
+      if (n >= G.N) continue;
+      float v = acc[i][j];
+      if (G.epi == 0) v = act_fwd(v + __ldg(G.bias + n), G.act);
+      else if (G.epi == 1) v = act_bwd(v, __ldg(G.H + m * G.h_sm + n), G.act);
+      G.C[m * G.c_sm + n] = v;
+    }
+  }
+}
+
+// column sums: out[n] = sum_m X[m*ld + n]   (bias gradients of the dense layers), one thread per column, fixed order
+__global__ void k_hyb_colsum(const float* __restrict__ X, long long ld, int M, int N, float* __restrict__ out) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float s = 0.f;
+  for (int m = 0; m < M; ++m) s += __ldg(X + m * ld + n);
+  out[n] = s;
+}
+
+// ---------------------------------------------------------------------------------------------- heads
+// warp per row: heads[a] = <h, W_a> + b_a  (fc_val / fc_adv or fc_out; network.py:54-63,81-96)
+__global__ void __launch_bounds__(256) k_hyb_heads_fwd(HybNet N, const float* __restrict__ P, float* __restrict__ rec_base, long long R) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long r = blockIdx.x * 8ll + warp;
+  if (r >= R) return;
+  float* rec = rec_base + r * N.rec;
+  const float* h = rec + N.last_off;
+  float out = 0.f;
+  for (int a = 0; a < N.NH; ++a) {
+    const float* w = N.dueling ? (a == 0 ? P + N.hw_off[0] : P + N.hw_off[1] + (a - 1) * N.last_len) : P + N.hw_off[0] + a * N.last_len;
+    float s = 0.f;
+    for (int k = lane; k < N.last_len; k += 32) s = fmaf(h[k], __ldg(w + k), s);
+#pragma unroll
+    for (int sh = 16; sh > 0; sh >>= 1) s += __shfl_xor_sync(0xffffffffu, s, sh);
+    const float b = N.dueling ? (a == 0 ? __ldg(P + N.hb_off[0]) : __ldg(P + N.hb_off[1] + a - 1)) : __ldg(P + N.hb_off[0] + a);
+    if (lane == a) out = s + b;
+  }
+  if (lane < kQLD) rec[N.head_off + lane] = (lane < N.NH) ? out : 0.f;
+}
+
+__device__ __forceinline__ void hyb_heads_to_q(const float* h, int A, int dueling, float (&q)[kQLD]) {
+  if (dueling) {        // Q = val + (adv - mean(adv))   (dqn/network.py:83)
+    float sum = 0.f;
+#pragma unroll
+    for (int a = 0; a < kQLD - 1; ++a) sum += (a < A) ? h[1 + a] : 0.f;
+    const float mean = sum / static_cast<float>(A);
+#pragma unroll
+    for (int a = 0; a < kQLD - 1; ++a) q[a] = h[0] + (h[1 + a] - mean);
+    q[kQLD - 1] = 0.f;
+  } else {
+#pragma unroll
+    for (int a = 0; a < kQLD; ++a) q[a] = h[a];
+  }
+}
+
+// TD target, |td|, Huber, loss partials, head deltas (dqn/agent.py:166-185 / 204-226 / 245-272)
+// online record r < B: s' row; r >= B: s row.  Head deltas go to the delta record of sample i.
+__global__ void __launch_bounds__(128) k_hyb_td(AgentCtx C, StepScalars S, HybNet N, const float* __restrict__ rec_on, const float* __restrict__ rec_tg,
+                                                float* __restrict__ drec) {
+  __shared__ float s_part[4];
+  const long long i = blockIdx.x * 128ll + threadIdx.x;
+  const bool per = S.prioritized != 0;
+  float lterm = 0.f;
+  if (i < S.B) {
+    float hn[kQLD], ht[kQLD], hs[kQLD], qn[kQLD], qt[kQLD], qs[kQLD];
+#pragma unroll
+    for (int a = 0; a < kQLD; ++a) {
+      hn[a] = rec_on[i * N.rec + N.head_off + a];
+      ht[a] = rec_tg[i * N.rec + N.head_off + a];
+      hs[a] = rec_on[(S.B + i) * N.rec + N.head_off + a];
+    }
+    hyb_heads_to_q(hn, N.A, N.dueling, qn);
+    hyb_heads_to_q(ht, N.A, N.dueling, qt);
+    hyb_heads_to_q(hs, N.A, N.dueling, qs);
+    float qsel = qt[0];
+    if (S.double_dqn) {
+      int astar = 0;
+      float bv = qn[0];
+#pragma unroll
+      for (int a = 1; a < kQLD - 1; ++a)
+        if (a < N.A && qn[a] > bv) { bv = qn[a]; astar = a; }
+#pragma unroll
+      for (int a = 1; a < kQLD - 1; ++a) qsel = (a == astar) ? qt[a] : qsel;
+    } else {
+#pragma unroll
+      for (int a = 1; a < kQLD - 1; ++a) qsel = (a < N.A) ? fmaxf(qsel, qt[a]) : qsel;
+    }
+    const int rf = C.rp.row_floats;
+    const int act = __float_as_int(__ldcg(C.X + i * rf + 2 * N.D));
+    const float rew = __ldcg(C.X + i * rf + 2 * N.D + 1), done = __ldcg(C.X + i * rf + 2 * N.D + 2);
+    const float w = per ? C.is_w[i] : 1.f;
+    const float y = rew + ((1.f - done) * S.gamma) * qsel;
+    float q_sa = qs[0];
+#pragma unroll
+    for (int a = 1; a < kQLD - 1; ++a) q_sa = (a == act) ? qs[a] : q_sa;
+    const float delta = q_sa - y;
+    const float atd = fabsf(y - q_sa);
+    const float z = fabsf(delta);
+    const float hub = (z < 1.f) ? (0.5f * z) * z : z - 0.5f;
+    const float go = per ? (1.f / static_cast<float>(S.Bglobal)) * w : 1.f / static_cast<float>(S.Bglobal);
+    const float g = fminf(fmaxf(delta, -1.f), 1.f) * go;
+    lterm = per ? w * hub : hub;
+    C.y[i] = y; C.q_sa[i] = q_sa; C.abs_td[i] = atd; C.hub[i] = hub; C.gcoef[i] = g;
+    float dh[kQLD];
+    if (N.dueling) {
+      const float mean = g / static_cast<float>(N.A);
+      dh[0] = g;
+#pragma unroll
+      for (int a = 0; a < kQLD - 1; ++a) dh[1 + a] = (a < N.A) ? ((a == act) ? g : 0.f) - mean : 0.f;
+    } else {
+#pragma unroll
+      for (int a = 0; a < kQLD; ++a) dh[a] = (a < N.A && a == act) ? g : 0.f;
+    }
+#pragma unroll
+    for (int a = 0; a < kQLD; ++a) {
+      drec[i * N.rec + N.head_off + a] = dh[a];
+      C.QT[i * kQLD + a] = qt[a]; C.QN[i * kQLD + a] = qn[a]; C.Q[i * kQLD + a] = qs[a]; C.DH[i * kQLD + a] = dh[a];
+    }
+  }
+#pragma unroll
+  for (int sh = 16; sh > 0; sh >>= 1) lterm += __shfl_down_sync(0xffffffffu, lterm, sh);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = lterm;
+  __syncthreads();
+  if (threadIdx.x == 0) C.loss_part[blockIdx.x] = (s_part[0] + s_part[1]) + (s_part[2] + s_part[3]);
+}
+
+// heads backward: d(last)[i][k] = (sum_a dh[i][a] W_a[k]) * act'(h[i][k]);  dW_a[k] = sum_i dh[i][a] h[i][k];  db_a = sum_i dh[i][a]
+__global__ void __launch_bounds__(256) k_hyb_heads_dgrad(HybNet N, const float* __restrict__ P, const float* __restrict__ rec_s, float* __restrict__ drec, long long B) {
+  const long long t = blockIdx.x * 256ll + threadIdx.x;
+  if (t >= B * N.last_len) return;
+  const long long i = t / N.last_len;
+  const int k = static_cast<int>(t - i * N.last_len);
+  const float* dh = drec + i * N.rec + N.head_off;
+  float s = 0.f;
+  for (int a = 0; a < N.NH; ++a) {
+    const float* w = N.dueling ? (a == 0 ? P + N.hw_off[0] : P + N.hw_off[1] + (a - 1) * N.last_len) : P + N.hw_off[0] + a * N.last_len;
+    s = fmaf(dh[a], __ldg(w + k), s);
+  }
+  drec[i * N.rec + N.last_off + k] = act_bwd(s, rec_s[i * N.rec + N.last_off + k], N.act);
+}
+__global__ void __launch_bounds__(256) k_hyb_heads_wgrad(HybNet N, const float* __restrict__ rec_s, const float* __restrict__ drec, long long B, float* __restrict__ grads) {
+  const int t = blockIdx.x * 256 + threadIdx.x;
+  const int a = t / N.last_len, k = t - a * N.last_len;
+  if (a >= N.NH) return;
+  float s = 0.f, sb = 0.f;
+  for (long long i = 0; i < B; ++i) {
+    const float d = drec[i * N.rec + N.head_off + a];
+    s = fmaf(d, rec_s[i * N.rec + N.last_off + k], s);
+    sb += d;
+  }
+  const int wo = N.dueling ? (a == 0 ? N.hw_off[0] : N.hw_off[1] + (a - 1) * N.last_len) : N.hw_off[0] + a * N.last_len;
+  grads[wo + k] = s;
+  if (k == 0) grads[N.dueling ? (a == 0 ? N.hb_off[0] : N.hb_off[1] + a - 1) : N.hb_off[0] + a] = sb;
+}
+
+// ---------------------------------------------------------------------------------------------- convolution backward
+// data gradient (gather form): one CTA per row, the layer's output deltas staged in shared memory; a thread owns 4 input
+// channels of one input pixel.  Result is multiplied by act'(input activation): it is the delta of the layer below.
+__global__ void __launch_bounds__(256) k_hyb_conv_dgrad(HybNet N, int li, const float* __restrict__ P, const float* __restrict__ rec_s, float* __restrict__ drec_base) {
+  extern __shared__ float s_dz[];
+  const HybConv c = N.conv[li];
+  const long long r = blockIdx.x;
+  float* drec = drec_base + r * N.rec;
+  const float* rec = rec_s + r * N.rec;
+  const int npix = c.oh * c.ow, n_out = c.oc * npix;
+  for (int t = threadIdx.x; t < n_out; t += blockDim.x) s_dz[t] = drec[c.out_off + t];
+  __syncthreads();
+  const int ipix = c.ih * c.iw, ng = c.ic >> 2;
+  const float* W = P + c.w_off;
+  for (int t = threadIdx.x; t < ng * ipix; t += blockDim.x) {
+    const int g = t / ipix, pix = t - g * ipix;
+    const int iy = pix / c.iw, ix = pix - iy * c.iw;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int ny = iy + 1 - ky;
+      if (ny < 0 || ny % c.sh != 0) continue;
+      const int oy = ny / c.sh;
+      if (oy >= c.oh) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int nx = ix + 1 - kx;
+        if (nx < 0 || nx % c.sw != 0) continue;
+        const int ox = nx / c.sw;
+        if (ox >= c.ow) continue;
+        const float* w = W + (4 * g) * 9 + ky * 3 + kx;
+        for (int oc = 0; oc < c.oc; ++oc) {
+          const float d = s_dz[oc * npix + oy * c.ow + ox];
+          const float* wo = w + oc * c.ic * 9;
+          a0 = fmaf(d, __ldg(wo), a0);
+          a1 = fmaf(d, __ldg(wo + 9), a1);
+          a2 = fmaf(d, __ldg(wo + 18), a2);
+          a3 = fmaf(d, __ldg(wo + 27), a3);
+        }
+      }
+    }
+    const int o = c.in_off + (4 * g) * ipix + pix;
+    drec[o] = act_bwd(a0, rec[o], N.act);
+    drec[o + ipix] = act_bwd(a1, rec[o + ipix], N.act);
+    drec[o + 2 * ipix] = act_bwd(a2, rec[o + 2 * ipix], N.act);
+    drec[o + 3 * ipix] = act_bwd(a3, rec[o + 3 * ipix], N.act);
+  }
+}
+
+// weight gradient: one CTA (64 threads) per (oc, ic); the threads split the (row, pixel) range, keep 9 partial sums each
+// and combine them with a fixed-order tree; the ic == 0 CTA also produces the bias gradient.
+__global__ void __launch_bounds__(64) k_hyb_conv_wgrad(HybNet N, int li, HybSrc src, const float* __restrict__ rec_s, const float* __restrict__ drec_base,
+                                                       long long B, float* __restrict__ grads) {
+  __shared__ float s_red[10][64];
+  const HybConv c = N.conv[li];
+  const int oc = blockIdx.x / c.ic, ic = blockIdx.x - oc * c.ic;
+  const int npix = c.oh * c.ow;
+  float acc[9], accb = 0.f;
+#pragma unroll
+  for (int q = 0; q < 9; ++q) acc[q] = 0.f;
+  for (long long t = threadIdx.x; t < B * npix; t += 64) {
+    const long long r = t / npix;
+    const int pix = static_cast<int>(t - r * npix);
+    const int oy = pix / c.ow, ox = pix - oy * c.ow;
+    const float d = drec_base[r * N.rec + c.out_off + oc * npix + pix];
+    const float* in = (li == 0) ? hyb_src_row(src, B + r) + N.macro_len : rec_s + r * N.rec + c.in_off;   // s rows: second half of the online pass
+    in += ic * c.ih * c.iw;
+    accb += d;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int iy = oy * c.sh + ky - 1;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int ix = ox * c.sw + kx - 1;
+        const bool ok = iy >= 0 && iy < c.ih && ix >= 0 && ix < c.iw;
+        acc[ky * 3 + kx] = fmaf(d, ok ? __ldg(in + iy * c.iw + ix) : 0.f, acc[ky * 3 + kx]);
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 9; ++q) s_red[q][threadIdx.x] = acc[q];
+  s_red[9][threadIdx.x] = accb;
+  __syncthreads();
+  for (int w = 32; w > 0; w >>= 1) {
+    if (threadIdx.x < w)
+#pragma unroll
+      for (int q = 0; q < 10; ++q) s_red[q][threadIdx.x] += s_red[q][threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x < 9) grads[c.w_off + (oc * c.ic + ic) * 9 + threadIdx.x] = s_red[threadIdx.x][0];
+  if (threadIdx.x == 9 && ic == 0) grads[c.b_off + oc] = s_red[9][0];
+}
+
+// Adam (+ Polyak / hard sync) over the flat blob, and the loss of the step
+__global__ void __launch_bounds__(256) k_hyb_adam(AgentCtx C, StepScalars S, int total, int n_loss_parts, int write_loss) {
+  const int pi = blockIdx.x * 256 + threadIdx.x;
+  if (pi < total) {
+    const float g = (S.grads_in != nullptr) ? __ldcg(S.grads_in + pi) : __ldcg(C.grads + pi);
+    adam_polyak_element(C, S, pi, g);
+  }
+  if (write_loss && blockIdx.x == 0 && threadIdx.x == 0) {
+    float s = 0.f;
+    for (int c = 0; c < n_loss_parts; ++c) s += __ldcg(C.loss_part + c);
+    const float loss = s / static_cast<float>(S.Bglobal);
+    C.loss[0] = loss;
+    if (C.host_loss != nullptr) {
+      C.host_loss[0] = loss;
+      __threadfence_system();
+      C.host_loss[1] = __uint_as_float(S.epoch);
+    }
+  }
+}
+
+// inference outputs from the head records: mode 0 greedy actions, 1 Q values [n][A], 2 raw heads [n][NH]
+__global__ void k_hyb_outputs(HybNet N, const float* __restrict__ rec_base, long long n, long long* __restrict__ actions, float* __restrict__ q_out, int mode) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  float h[kQLD], q[kQLD];
+#pragma unroll
+  for (int a = 0; a < kQLD; ++a) h[a] = rec_base[i * N.rec + N.head_off + a];
+  if (mode == 2) {
+#pragma unroll
+    for (int a = 0; a < kQLD; ++a)
+      if (a < N.NH) q_out[i * N.NH + a] = h[a];
+    return;
+  }
+  if (mode == 0) {       // dueling: argmax of RAW advantages (network.py:110-117); plain: argmax Q; first maximum wins
+    int best = 0;
+    float bv = N.dueling ? h[1] : h[0];
+#pragma unroll
+    for (int a = 1; a < kQLD - 1; ++a) {
+      const float v = N.dueling ? h[a + 1] : h[a];
+      if (a < N.A && v > bv) { bv = v; best = a; }
+    }
+    actions[i] = best;
+    return;
+  }
+  hyb_heads_to_q(h, N.A, N.dueling, q);
+#pragma unroll
+  for (int a = 0; a < kQLD; ++a)
+    if (a < N.A) q_out[i * N.A + a] = q[a];
+}
+
+}  // namespace rmc

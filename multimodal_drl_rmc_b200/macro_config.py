@@ -36,6 +36,39 @@ def network_config_elu(input_dim_space):
     return net, 128, optim.Adam, nn.SmoothL1Loss
 
 
+class TwoStreamBody(nn.Module):
+    """The repo-HEAD body (env/dqn_config.py:66-193): state = [macro | grid C,H,W]; grid -> (Conv2d 3x3 p1 + act) x n ->
+    flatten; cat([flatten, macro]) -> (Linear + act) x m.  Attribute names (``cnn_stream``, ``dense_stream``,
+    ``macro_len``, ``micro_shape``) are the ones the reference's checkpoints and ``network.match_hybrid_body`` expect.
+    The module only carries parameters and structure: compute runs in librmc_b200."""
+
+    def __init__(self, macro_len=14, micro_shape=(2, 27, 5), cnn=((32, (1, 1)), (64, (2, 1)), (64, (2, 2))), dense=(512, 256),
+                 activation=nn.ELU):
+        super().__init__()
+        act = activation()
+        self.macro_len, self.micro_shape = int(macro_len), tuple(int(v) for v in micro_shape)
+        layers, ch, h, w = [], self.micro_shape[0], self.micro_shape[1], self.micro_shape[2]
+        for out_ch, (sh, sw) in cnn:
+            layers += [nn.Conv2d(ch, out_ch, kernel_size=(3, 3), stride=(sh, sw), padding=(1, 1)), act]
+            ch, h, w = out_ch, (h + 2 - 3) // sh + 1, (w + 2 - 3) // sw + 1
+        self.cnn_stream = nn.Sequential(*layers)
+        layers, width = [], ch * h * w + self.macro_len
+        for out_f in dense:
+            layers += [nn.Linear(width, out_f), act]
+            width = out_f
+        self.dense_stream = nn.Sequential(*layers)
+        self.fc_out_dim = width
+
+
+def network_config_hybrid(input_dim_space):
+    """``network_config`` of env/dqn_config.py:148-193 (macro 14 + grid 2x27x5, CNN 32/64/64, dense 512/256, ELU)."""
+    net = TwoStreamBody()
+    return net, net.fc_out_dim, optim.Adam, nn.SmoothL1Loss
+
+
+HYBRID_OBS_DIM = 14 + 2 * 27 * 5
+
+
 def make_agent(algo, obs_dim, batch_size, buffer_size, *, save_dir, log_dir, n_actions=8, gpu="0", activation="relu",
                **overrides):
     """Construct an agent the way train.py:24-48 does, with the reference defaults."""
@@ -45,7 +78,8 @@ def make_agent(algo, obs_dim, batch_size, buffer_size, *, save_dir, log_dir, n_a
     cls = getattr(Agents, algo)
     return cls(n_env=hp["n_env"], lr=hp["lr"], gamma=hp["gamma"], epsilon_start=hp["eps_start"],
                epsilon_min=hp["eps_min"], epsilon_decay=hp["eps_dec"], epsilon_exp_decay=hp["eps_dec_exp"],
-               nn_conf_func=network_config_elu if activation == "elu" else network_config, input_dim=ObsSpace(obs_dim),
+               nn_conf_func=(network_config_hybrid if activation == "hybrid" else network_config_elu if activation == "elu" else network_config),
+               input_dim=ObsSpace(obs_dim),
                output_dim=n_actions,
                batch_size=batch_size, min_buffer_size=min(hp["min_mem"], buffer_size), buffer_size=buffer_size,
                update_target_frequency=hp["target_update_freq"], target_soft_update=hp["target_soft_update"],

@@ -29,6 +29,43 @@ def _hidden_activation(mod):
     return None
 
 
+def match_hybrid_body(net, fc_out_dim):
+    """The repo-HEAD body (env/dqn_config.py:66-143 ``TwoStreamHybridNetwork``), recognised structurally: attributes
+    ``macro_len``, ``micro_shape`` (C, H, W), ``cnn_stream`` = Sequential of (Conv2d 3x3 padding 1, act) pairs and
+    ``dense_stream`` = Sequential of (Linear, act) pairs, one activation kind throughout, parameters registered in that
+    order.  Returns a dict for ``rmc_hybrid_spec_t`` or None when ``net`` is not of this family."""
+    if not all(hasattr(net, a) for a in ("macro_len", "micro_shape", "cnn_stream", "dense_stream")):
+        return None
+    cnn, dense = net.cnn_stream, net.dense_stream
+    if not (isinstance(cnn, nn.Sequential) and isinstance(dense, nn.Sequential) and len(cnn) % 2 == 0 and len(dense) % 2 == 0
+            and 2 <= len(cnn) <= 8 and 2 <= len(dense) <= 6):
+        return None
+    acts = set()
+    convs, denses = [], []
+    for i in range(0, len(cnn), 2):
+        c, a = cnn[i], cnn[i + 1]
+        if not (isinstance(c, nn.Conv2d) and tuple(c.kernel_size) == (3, 3) and tuple(c.padding) == (1, 1) and tuple(c.dilation) == (1, 1)
+                and c.groups == 1 and c.bias is not None and c.padding_mode == "zeros" and _hidden_activation(a) is not None):
+            return None
+        acts.add(_hidden_activation(a))
+        convs.append(c)
+    for i in range(0, len(dense), 2):
+        d, a = dense[i], dense[i + 1]
+        if not (isinstance(d, nn.Linear) and d.bias is not None and _hidden_activation(a) is not None):
+            return None
+        acts.add(_hidden_activation(a))
+        denses.append(d)
+    ch, hh, ww = (int(v) for v in net.micro_shape)
+    keys = [k for k, _ in net.named_parameters()]
+    want = ["cnn_stream.%d.%s" % (2 * i, n) for i in range(len(convs)) for n in ("weight", "bias")] + \
+           ["dense_stream.%d.%s" % (2 * i, n) for i in range(len(denses)) for n in ("weight", "bias")]
+    if len(acts) != 1 or keys != want or convs[0].in_channels != ch or denses[-1].out_features != fc_out_dim:
+        return None
+    return dict(macro_len=int(net.macro_len), grid=(ch, hh, ww), conv_out=[c.out_channels for c in convs],
+                conv_stride=[tuple(int(v) for v in c.stride) for c in convs], dense_out=[d.out_features for d in denses],
+                activation=acts.pop(), obs_dim=int(net.macro_len) + ch * hh * ww)
+
+
 def match_macro_body(net, fc_out_dim, optim_func, loss_func):
     """The fused path is built for the macro-state body of the reference
     (env/custom_env/macro with lane/dqn_config.py:58-104): Sequential(Linear(D,256), act,
@@ -54,16 +91,31 @@ class LearnerHandle:
     """Owner of one ``rmc_learner_t`` (online + target + Adam state + scratch)."""
 
     def __init__(self, obs_dim, n_actions, dueling, double_dqn, prioritized, max_batch, device_index, hyper: _lib.Hyper,
-                 activation=0):
+                 activation=0, hybrid=None):
         _lib.require_cuda()
-        self.spec = _lib.NetSpec(int(obs_dim), 256, 128, int(n_actions), int(dueling), int(double_dqn),
-                                 int(prioritized), int(activation))
         self.hyper = hyper
         self.device_index = int(device_index)
         self.max_batch = int(max_batch)
+        self.hybrid = hybrid
         h = C.c_void_p()
-        check(lib().rmc_learner_create(C.byref(h), C.byref(self.spec), C.byref(self.hyper), self.max_batch,
-                                       self.device_index))
+        if hybrid is not None:       # the repo-HEAD CNN + MLP body (match_hybrid_body)
+            sp = _lib.HybridSpec()
+            sp.macro_len = hybrid["macro_len"]
+            sp.grid_c, sp.grid_h, sp.grid_w = hybrid["grid"]
+            sp.n_conv, sp.n_dense = len(hybrid["conv_out"]), len(hybrid["dense_out"])
+            for i, (o, st) in enumerate(zip(hybrid["conv_out"], hybrid["conv_stride"])):
+                sp.conv_out[i], sp.conv_sh[i], sp.conv_sw[i] = int(o), int(st[0]), int(st[1])
+            for i, o in enumerate(hybrid["dense_out"]):
+                sp.dense_out[i] = int(o)
+            sp.n_actions, sp.dueling, sp.double_dqn, sp.prioritized = int(n_actions), int(dueling), int(double_dqn), int(prioritized)
+            sp.activation = int(hybrid["activation"])
+            self.spec = sp
+            check(lib().rmc_learner_create_hybrid(C.byref(h), C.byref(sp), C.byref(self.hyper), self.max_batch, self.device_index))
+        else:
+            self.spec = _lib.NetSpec(int(obs_dim), 256, 128, int(n_actions), int(dueling), int(double_dqn),
+                                     int(prioritized), int(activation))
+            check(lib().rmc_learner_create(C.byref(h), C.byref(self.spec), C.byref(self.hyper), self.max_batch,
+                                           self.device_index))
         self.handle = h
         self.n_params = int(lib().rmc_learner_param_count(h))
         self.version = [0, 0]   # bumped whenever the blob of kind ONLINE / TARGET changes on the device
@@ -112,7 +164,13 @@ class Network(nn.Module):
     def __init__(self, device, nn_conf_func, input_dim):
         super().__init__()
         self.net, self.fc_out_dim, optim_func, loss_func = nn_conf_func(input_dim)
-        self._obs_dim, self._activation = match_macro_body(self.net, self.fc_out_dim, optim_func, loss_func)
+        self._hybrid = match_hybrid_body(self.net, self.fc_out_dim)
+        if self._hybrid is not None:
+            if optim_func is not T.optim.Adam or loss_func is not nn.SmoothL1Loss:
+                raise NotImplementedError("librmc_b200 fuses torch.optim.Adam + nn.SmoothL1Loss only")
+            self._obs_dim, self._activation = self._hybrid["obs_dim"], self._hybrid["activation"]
+        else:
+            self._obs_dim, self._activation = match_macro_body(self.net, self.fc_out_dim, optim_func, loss_func)
         self.optim_func = (lambda params, lr: optim_func(params, lr=lr))
         self.loss_func = (lambda reduction: loss_func(reduction=reduction))
         self.device = device
@@ -136,7 +194,7 @@ class Network(nn.Module):
             index = dev.index if dev.index is not None else T.cuda.current_device()
             hyper = _lib.Hyper(1e-4, 0.9, 0.999, 1e-8, 0.99, 1e-3, 1e-4, 0.6, 1.0)
             self._bind(LearnerHandle(self._obs_dim, self._n_actions, self._dueling, True, False, 1, index, hyper,
-                                     activation=self._activation), _lib.ONLINE)
+                                     activation=self._activation, hybrid=self._hybrid), _lib.ONLINE)
         return self._lh
 
     def _flat_module_params(self):

@@ -200,6 +200,38 @@ def macro_body(obs_dim: int, hidden=(256, 128), activation="relu"):
                          nn.Linear(hidden[0], hidden[1]), act())
 
 
+class OracleHybridBody(nn.Module):
+    """Restatement of the repo-HEAD body (env/dqn_config.py:66-143 ``TwoStreamHybridNetwork`` as configured by
+    ``network_config`` :148-193): state = [macro(14) | grid(2,27,5) flattened]; grid -> Conv2d(2,32,3,s(1,1),p1) -> act ->
+    Conv2d(32,64,3,s(2,1),p1) -> act -> Conv2d(64,64,3,s(2,2),p1) -> act -> flatten; cat([flatten, macro]) ->
+    Linear(1358,512) -> act -> Linear(512,256) -> act.  Attribute names follow the reference so that the state_dict keys
+    equal the ``.pack`` checkpoint keys (``net.cnn_stream.0.weight`` ... ``net.dense_stream.2.bias``)."""
+
+    def __init__(self, macro_len=14, micro_shape=(2, 27, 5), cnn=((32, (1, 1)), (64, (2, 1)), (64, (2, 2))), dense=(512, 256),
+                 activation="elu"):
+        super().__init__()
+        act = nn.ELU() if activation == "elu" else nn.ReLU()       # ONE shared module instance, as in the reference
+        self.macro_len, self.micro_shape = int(macro_len), tuple(micro_shape)
+        layers, ch = [], self.micro_shape[0]
+        for out_ch, stride in cnn:                                  # dqn_config.py:84-93
+            layers += [nn.Conv2d(ch, out_ch, kernel_size=(3, 3), stride=stride, padding=(1, 1)), act]
+            ch = out_ch
+        self.cnn_stream = nn.Sequential(*layers)
+        with torch.no_grad():                                       # dqn_config.py:98-105
+            flat = self.cnn_stream(torch.zeros(1, *self.micro_shape)).flatten(start_dim=1).shape[1]
+        layers, width = [], flat + self.macro_len
+        for out_f in dense:                                         # dqn_config.py:108-114
+            layers += [nn.Linear(width, out_f), act]
+            width = out_f
+        self.dense_stream = nn.Sequential(*layers)
+        self.fc_out_dim = width
+
+    def forward(self, x):                                           # dqn_config.py:119-143
+        macro, grid = x[:, :self.macro_len], x[:, self.macro_len:].view(-1, *self.micro_shape)
+        feat = self.cnn_stream(grid).flatten(start_dim=1)
+        return self.dense_stream(torch.cat([feat, macro], dim=1))
+
+
 class OracleQNet(nn.Module):
     """dqn/network.py:50-74 (plain head ``fc_out``) and :77-117 (dueling ``fc_val``/``fc_adv``).
 
@@ -207,10 +239,14 @@ class OracleQNet(nn.Module):
     checkpoint keys (``net.0.weight`` ... ``fc_adv.bias``).  Construction order (body, then
     val, then adv / out) matches the reference so that a seeded default init is identical."""
 
-    def __init__(self, obs_dim: int, n_actions: int, dueling: bool, hidden=(256, 128), activation="relu"):
+    def __init__(self, obs_dim: int, n_actions: int, dueling: bool, hidden=(256, 128), activation="relu", body="macro"):
         super().__init__()
         self.dueling = bool(dueling)
-        self.net = macro_body(obs_dim, hidden, activation)
+        if body == "hybrid":
+            self.net = OracleHybridBody(activation=activation)
+            hidden = (None, self.net.fc_out_dim)
+        else:
+            self.net = macro_body(obs_dim, hidden, activation)
         if self.dueling:
             self.fc_val = nn.Linear(hidden[1], 1)
             self.fc_adv = nn.Linear(hidden[1], n_actions)
@@ -254,7 +290,7 @@ class OracleLearner:
 
     def __init__(self, algo: str, obs_dim: int, n_actions: int, batch: int, capacity: int, *,
                  lr=1e-4, gamma=0.99, tau=1e-3, soft=True, target_freq=30000, eps_decay=2e6,
-                 n_env=1, activation="relu"):
+                 n_env=1, activation="relu", body="macro"):
         f = self.ALGOS[algo]
         self.algo, self.per, self.dueling, self.double = algo, f["per"], f["dueling"], f["double"]
         self.obs_dim, self.n_actions, self.batch, self.capacity = obs_dim, n_actions, batch, capacity
@@ -263,8 +299,8 @@ class OracleLearner:
         self.replay = (OraclePrioritizedReplay(capacity, batch, eps_decay) if self.per
                        else OracleUniformReplay(capacity, batch))
         # construction order online -> target, as in agent.py:282-283 etc.
-        self.online = OracleQNet(obs_dim, n_actions, self.dueling, activation=activation)
-        self.target = OracleQNet(obs_dim, n_actions, self.dueling, activation=activation)
+        self.online = OracleQNet(obs_dim, n_actions, self.dueling, activation=activation, body=body)
+        self.target = OracleQNet(obs_dim, n_actions, self.dueling, activation=activation, body=body)
         self.opt = torch.optim.Adam(self.online.parameters(), lr=lr)   # network.py:17,56
         self.huber = nn.SmoothL1Loss(reduction="none" if self.per else "mean")  # agent.py:317
         self.sync_target(force=True)                                   # agent.py:284

@@ -112,15 +112,37 @@ def macro_network_config_elu(input_dim_space):
     return body, 128, optim.Adam, nn.SmoothL1Loss
 
 
+def hybrid_network_config(input_dim_space):
+    """The reference's OWN repo-HEAD network: ``TwoStreamHybridNetwork`` is executed from the class definition in
+    ``env/dqn_config.py:66-143`` (the module itself imports the SUMO bindings and cannot be imported here, so only that
+    class is compiled, from the reference tree, at fixture-generation time) with the parameters of
+    ``network_config`` (:148-193): macro 14, grid (2,27,5), CNN (32,(3,3),(1,1)) (64,(3,3),(2,1)) (64,(3,3),(2,2)),
+    dense [512, 256], ELU, Adam, SmoothL1."""
+    import ast
+    import torch
+    import torch.nn as nn
+    import torch.optim as optim
+
+    path = os.path.join(REFERENCE_ROOT, "env", "dqn_config.py")
+    tree = ast.parse(open(path).read())
+    cls = [n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "TwoStreamHybridNetwork"][0]
+    ns = {"nn": nn, "T": torch}
+    exec(compile(ast.Module(body=[cls], type_ignores=[]), path, "exec"), ns)
+    net = ns["TwoStreamHybridNetwork"](macro_vec_len=14, micro_shape_chw=(2, 27, 5),
+                                       cnn_params=[(32, (3, 3), (1, 1)), (64, (3, 3), (2, 1)), (64, (3, 3), (2, 2))],
+                                       dense_params=[512, 256], activation_fn=nn.ELU())
+    return net, net.fc_out_dim, optim.Adam, nn.SmoothL1Loss
+
+
 def make_reference_agent(algo: str, obs_dim: int, batch: int, cap: int, tmpdir: str, *,
                          lr=1e-4, gamma=0.99, tau=1e-3, soft=True, target_freq=30000,
-                         eps_decay=2e6, n_env=1, n_actions=8, activation="relu"):
+                         eps_decay=2e6, n_env=1, n_actions=8, activation="relu", body="macro"):
     """Construct a reference agent exactly as train.py:24-48 would (macro MLP)."""
     dqn = import_reference()
     cls = getattr(dqn.Agents, algo)
     return cls(n_env=n_env, lr=lr, gamma=gamma, epsilon_start=1.0, epsilon_min=0.01,
                epsilon_decay=eps_decay, epsilon_exp_decay=True,
-               nn_conf_func=macro_network_config_elu if activation == "elu" else macro_network_config,
+               nn_conf_func=hybrid_network_config if body == "hybrid" else (macro_network_config_elu if activation == "elu" else macro_network_config),
                input_dim=ObsBox(obs_dim), output_dim=n_actions, batch_size=batch,
                min_buffer_size=batch, buffer_size=cap, update_target_frequency=target_freq,
                target_soft_update=soft, target_soft_update_tau=tau, save_frequency=10000,

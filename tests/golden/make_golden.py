@@ -38,6 +38,7 @@ CASES = {
     "double_d8_hard": dict(algo="DoubleDQNAgent", D=8, B=32, cap=256, fill=200, steps=4, soft=False,
                            target_freq=2),
     "dqn_d14": dict(algo="DQNAgent", D=14, B=16, cap=128, fill=128, steps=2, soft=True),
+    "per_hybrid": dict(algo="PerDuelingDoubleDQNAgent", D=284, B=16, cap=150, fill=150, steps=2, soft=True, activation="elu", body="hybrid"),
     "per_d14_elu": dict(algo="PerDuelingDoubleDQNAgent", D=14, B=64, cap=600, fill=600, steps=3, soft=True, activation="elu"),
 }
 WEIGHT_SEED = 0
@@ -80,7 +81,7 @@ def run_case(name: str, c: dict, tmp: str) -> dict:
     torch.manual_seed(WEIGHT_SEED)
     agent = refharness.make_reference_agent(c["algo"], c["D"], c["B"], c["cap"], tmp,
                                             soft=c["soft"], target_freq=c.get("target_freq", 30000),
-                                            activation=c.get("activation", "relu"))
+                                            activation=c.get("activation", "relu"), body=c.get("body", "macro"))
     perturb_target(agent)
     per = c["algo"].startswith("Per")
     out = {"init_online_sha": sha(flat_params(agent.online_network)),

@@ -29,16 +29,17 @@ def flat_sd(net):
     return np.concatenate([v.detach().cpu().numpy().ravel() for v in net.state_dict().values()])
 
 
-def make_pair(algo, D, B, cap, fill, seed, soft=True, target_freq=30000, tmpdir=None, activation="relu"):
+def make_pair(algo, D, B, cap, fill, seed, soft=True, target_freq=30000, tmpdir=None, activation="relu", body="macro"):
     """(oracle learner, CUDA agent) with identical weights and identical replay contents."""
     from multimodal_drl_rmc_b200 import macro_config
     torch.set_num_threads(1)
     torch.manual_seed(seed)
-    orc = OracleLearner(algo, D, 8, B, cap, soft=soft, target_freq=target_freq, activation=activation)
+    orc = OracleLearner(algo, D, 8, B, cap, soft=soft, target_freq=target_freq, activation=activation, body=body)
     perturb_target(orc.target, seed + 100)
     tmp = tmpdir or tempfile.mkdtemp(prefix="rmc_parity_")
     agent = macro_config.make_agent(algo, D, B, cap, save_dir=tmp + "/", log_dir=tmp + "/",
-                                    target_soft_update=soft, target_update_freq=target_freq, activation=activation)
+                                    target_soft_update=soft, target_update_freq=target_freq,
+                                    activation="hybrid" if body == "hybrid" else activation)
     agent.online_network.load_state_dict({k: v.clone() for k, v in orc.online.state_dict().items()})
     agent.target_network.load_state_dict({k: v.clone() for k, v in orc.target.state_dict().items()})
     obs, act, rew, done, nxt = synthetic_transitions(fill, D, 20251018 + seed)
@@ -58,9 +59,9 @@ def gpu_out(agent, name, dtype=torch.float32):
     return agent._lh.output(name, dtype).cpu().numpy()
 
 
-def run_parity_case(algo, D, B, cap, fill, steps, seed, soft=True, target_freq=30000, resync_tree=True, activation="relu"):
+def run_parity_case(algo, D, B, cap, fill, steps, seed, soft=True, target_freq=30000, resync_tree=True, activation="relu", body="macro"):
     from multimodal_drl_rmc_b200 import _lib
-    orc, agent = make_pair(algo, D, B, cap, fill, seed, soft, target_freq, activation=activation)
+    orc, agent = make_pair(algo, D, B, cap, fill, seed, soft, target_freq, activation=activation, body=body)
     per = orc.per
     sizes = tensor_sizes(orc.online)
     rng = np.random.default_rng(seed + 1)
@@ -96,6 +97,12 @@ def run_parity_case(algo, D, B, cap, fill, steps, seed, soft=True, target_freq=3
         g_gpu = agent._lh.get_params(_lib.GRADS).cpu().numpy()
         g_ref = np.concatenate([tr["grads"][k].ravel() for k, _ in orc.online.named_parameters()])
         pt = per_tensor_max_rel(g_gpu, g_ref, sizes)
+        if "fc_val.bias" in pt:
+            # a ONE-element tensor: d(fc_val.bias) = sum_i g_i, a cancelling sum of the per-sample loss coefficients -- its own
+            # magnitude says nothing about the conditioning of the sum, so it is measured against sum_i |g_i|
+            off = sum(n for k, n in sizes[:[k for k, _ in sizes].index("fc_val.bias")])
+            scale = float(np.sum(np.abs(gpu_out(agent, "gcoef").astype(np.float64))))
+            pt["fc_val.bias"] = abs(float(g_gpu[off]) - float(g_ref[off])) / max(scale, 1e-30)
         worst = max(pt, key=pt.get)
         if pt[worst] > res["max_rel_grads"]:
             res["max_rel_grads"], res["worst_grad"] = pt[worst], worst

@@ -56,7 +56,8 @@ def build_oracle_case(c: dict, meta: dict) -> OracleLearner:
     torch.set_num_threads(1)
     torch.manual_seed(meta["weight_seed"])
     lrn = OracleLearner(c["algo"], c["D"], 8, c["B"], c["cap"], soft=c["soft"],
-                        target_freq=c.get("target_freq", 30000), activation=c.get("activation", "relu"))
+                        target_freq=c.get("target_freq", 30000), activation=c.get("activation", "relu"),
+                        body=c.get("body", "macro"))
     perturb_target(lrn.target, meta["target_noise_seed"])
     obs, act, rew, done, nxt = synthetic_transitions(c["fill"], c["D"], meta["data_seed"])
     for i in range(c["fill"]):
