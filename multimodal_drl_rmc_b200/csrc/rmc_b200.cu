@@ -105,7 +105,7 @@ struct rmc_learner {
   // hybrid CNN+MLP network (rmc_hybrid.cuh): per-row activation / delta records
   bool hybrid = false;
   HybNet H{};
-  float *rec_on = nullptr, *rec_tg = nullptr, *drec = nullptr;
+  float *rec_on = nullptr, *rec_tg = nullptr, *drec = nullptr, *hyb_ws = nullptr;
   // act staging
   float* act_pin_obs = nullptr; long long* act_pin_out = nullptr; float* act_dev_obs = nullptr; long long* act_dev_out = nullptr;
   long long act_cap = 0;
@@ -873,6 +873,7 @@ static int32_t step_tc(rmc_learner* l, rmc_replay* r, const rmc_step_args_t* a, 
 }
 
 // ------------------------------------------------------------------------------ hybrid CNN + MLP learner
+static constexpr long long kHybWsFloats = 4ll << 20;      // split-K workspace (16 MB)
 extern "C" int32_t rmc_learner_create_hybrid(rmc_learner_t** out, const rmc_hybrid_spec_t* sp, const rmc_hyper_t* hyper, int64_t max_batch,
                                              int32_t device) {
   if (!out || !sp || !hyper || max_batch < 1) return fail(RMC_ERR_ARG, "rmc_learner_create_hybrid: null/bad args");
@@ -965,6 +966,7 @@ extern "C" int32_t rmc_learner_create_hybrid(rmc_learner_t** out, const rmc_hybr
   if ((e = owned_alloc(l, &l->rec_on, 2 * B * N.rec))) return e;
   if ((e = owned_alloc(l, &l->rec_tg, B * N.rec))) return e;
   if ((e = owned_alloc(l, &l->drec, B * N.rec))) return e;
+  if ((e = owned_alloc(l, &l->hyb_ws, static_cast<size_t>(kHybWsFloats)))) return e;
   {
     float* hp = nullptr;
     float* dp = nullptr;
@@ -983,19 +985,50 @@ extern "C" int32_t rmc_learner_create_hybrid(rmc_learner_t** out, const rmc_hybr
   return RMC_OK;
 }
 
-static int32_t hyb_gemm(const HybGemm& G, cudaStream_t st) {
-  k_hyb_gemm<<<dim3(blocks_for(G.N, 64), blocks_for(G.M, 64), 1), 256, 0, st>>>(G);
+template <int MODE>
+static int32_t hyb_gemm_mode(rmc_learner* l, HybGemm G, cudaStream_t st) {
+  // skinny problems (few output tiles, long K) are split along K so that the operand streams of one GEMM are spread
+  // over the SMs; the partial sums are combined in split order by a second kernel (deterministic)
+  const long long tiles = static_cast<long long>(blocks_for(G.N, 64)) * blocks_for(G.M, 64);
+  int splits = 1;
+  if (tiles < 96 && G.K >= 128) {
+    splits = static_cast<int>(std::min<long long>(16, std::min<long long>((148 + tiles - 1) / tiles, G.K / 64)));
+    while (splits > 1 && static_cast<long long>(splits) * G.M * G.N > kHybWsFloats) --splits;
+  }
+  G.splits = splits; G.ws = l->hyb_ws;
+  G.k_chunk = ((G.K + splits - 1) / splits + 15) / 16 * 16;
+  if (splits > 1) G.splits = (G.K + G.k_chunk - 1) / G.k_chunk;
+  k_hyb_gemm<MODE><<<dim3(blocks_for(G.N, 64), blocks_for(G.M, 64), static_cast<unsigned>(G.splits)), 256, 0, st>>>(G);
   RMC_KERNEL_OK();
+  if (G.splits > 1) {
+    k_hyb_splitk_reduce<MODE><<<blocks_for(static_cast<long long>(G.M) * G.N, 256), 256, 0, st>>>(G);
+    RMC_KERNEL_OK();
+  }
   return RMC_OK;
 }
+static int32_t hyb_gemm(rmc_learner* l, const HybGemm& G, cudaStream_t st) { return hyb_gemm_mode<0>(l, G, st); }
 
 // one forward pass of R rows through the net with parameters P into the records `rec`
 static int32_t hybrid_forward(rmc_learner* l, const float* P, const HybSrc& src, float* rec, long long R, cudaStream_t st) {
   const HybNet& N = l->H;
   for (int i = 0; i < N.n_conv; ++i) {
     const HybConv& c = N.conv[i];
-    k_hyb_conv_fwd<<<static_cast<unsigned>(R), 256, static_cast<size_t>(c.ic) * c.ih * c.iw * sizeof(float), st>>>(N, i, P, src, rec);
-    RMC_KERNEL_OK();
+    if (i == 0 || c.ic * 9 < 64) {          // tiny K (first layer: 2 input channels): the direct kernel
+      const unsigned slices = blocks_for(static_cast<long long>(c.oc / 4) * c.oh * c.ow, 256);
+      k_hyb_conv_fwd<<<dim3(static_cast<unsigned>(R), slices, 1), 256, static_cast<size_t>(c.ic) * c.ih * c.iw * sizeof(float), st>>>(N, i, P, src, rec);
+      RMC_KERNEL_OK();
+      continue;
+    }
+    HybGemm G{};                             // implicit GEMM: [R*pixels x ic*9] . [ic*9 x oc]
+    G.cv = c; G.img = rec + c.in_off; G.img_stride = N.rec;
+    G.B = P + c.w_off; G.b_sk = 1; G.b_sn = c.ic * 9;
+    G.C = rec + c.out_off; G.c_sm = N.rec; G.bias = P + c.b_off;
+    G.M = static_cast<int>(R) * c.oh * c.ow; G.N = c.oc; G.K = c.ic * 9; G.epi = 0; G.act = N.act;
+    if (int32_t e = hyb_gemm_mode<1>(l, G, st)) return e;
+    if (i == N.n_conv - 1) {                 // features = [flattened last conv output | macro]
+      k_hyb_copy_macro<<<blocks_for(R * N.macro_len, 128), 128, 0, st>>>(N, src, rec, R);
+      RMC_KERNEL_OK();
+    }
   }
   for (int i = 0; i < N.n_dense; ++i) {
     const HybDense& d = N.dense[i];
@@ -1004,7 +1037,7 @@ static int32_t hybrid_forward(rmc_learner* l, const float* P, const HybSrc& src,
     G.B = P + d.w_off; G.b_sk = 1; G.b_sn = d.in;
     G.C = rec + d.out_off; G.c_sm = N.rec;
     G.bias = P + d.b_off; G.M = static_cast<int>(R); G.N = d.out; G.K = d.in; G.epi = 0; G.act = N.act;
-    if (int32_t e = hyb_gemm(G, st)) return e;
+    if (int32_t e = hyb_gemm(l, G, st)) return e;
   }
   k_hyb_heads_fwd<<<blocks_for(R, 8), 256, 0, st>>>(N, P, rec, R);
   RMC_KERNEL_OK();
@@ -1047,7 +1080,7 @@ static int32_t hybrid_step(rmc_learner* l, rmc_replay* r, const rmc_step_args_t*
       W.A = l->drec + d.out_off; W.a_sm = 1; W.a_sk = N.rec;
       W.B = rec_s + d.in_off; W.b_sk = N.rec; W.b_sn = 1;
       W.C = C.grads + d.w_off; W.c_sm = d.in; W.M = d.out; W.N = d.in; W.K = static_cast<int>(B); W.epi = 2;
-      if (int32_t e = hyb_gemm(W, st)) return e;
+      if (int32_t e = hyb_gemm(l, W, st)) return e;
       k_hyb_colsum<<<blocks_for(d.out, 128), 128, 0, st>>>(l->drec + d.out_off, N.rec, static_cast<int>(B), d.out, C.grads + d.b_off);
       RMC_KERNEL_OK();
       HybGemm G{};                                        // dX[r][k] = (sum_n dZ[r][n] W[n][k]) * act'(X[r][k])
@@ -1055,15 +1088,26 @@ static int32_t hybrid_step(rmc_learner* l, rmc_replay* r, const rmc_step_args_t*
       G.B = C.online + d.w_off; G.b_sk = d.in; G.b_sn = 1;
       G.C = l->drec + d.in_off; G.c_sm = N.rec; G.H = rec_s + d.in_off; G.h_sm = N.rec;
       G.M = static_cast<int>(B); G.N = (i == 0) ? N.conv_flat : d.in; G.K = d.out; G.epi = 1; G.act = N.act;
-      if (int32_t e = hyb_gemm(G, st)) return e;
+      if (int32_t e = hyb_gemm(l, G, st)) return e;
     }
     for (int i = N.n_conv - 1; i >= 0; --i) {
       const HybConv& c = N.conv[i];
-      k_hyb_conv_wgrad<<<static_cast<unsigned>(c.oc * c.ic), 64, 0, st>>>(N, i, src_on, rec_s, l->drec, B, C.grads);
+      const int npix = c.oh * c.ow;
+      HybGemm W{};                           // dW[oc][(ic,ky,kx)] = sum_(row,pix) dZ . im2col   (split along K = rows x pixels)
+      W.cv = c; W.dz = l->drec + c.out_off; W.dz_stride = N.rec;
+      if (i == 0) { W.img = nullptr; W.src = src_on; W.src_row0 = B; W.macro_len = N.macro_len; }
+      else { W.img = rec_s + c.in_off; W.img_stride = N.rec; }
+      W.C = C.grads + c.w_off; W.c_sm = c.ic * 9; W.M = c.oc; W.N = c.ic * 9; W.K = static_cast<int>(B) * npix; W.epi = 2;
+      if (int32_t e = hyb_gemm_mode<3>(l, W, st)) return e;
+      k_hyb_conv_bias_grad<<<static_cast<unsigned>(c.oc), 256, 0, st>>>(l->drec + c.out_off, N.rec, npix, B, C.grads + c.b_off);
       RMC_KERNEL_OK();
-      if (i > 0) {
-        k_hyb_conv_dgrad<<<static_cast<unsigned>(B), 256, static_cast<size_t>(c.oc) * c.oh * c.ow * sizeof(float), st>>>(N, i, C.online, rec_s, l->drec);
-        RMC_KERNEL_OK();
+      if (i > 0) {                           // delta of the layer below: (gathered dZ . W) * act'(input activation)
+        HybGemm G{};
+        G.cv = c; G.dz = l->drec + c.out_off; G.dz_stride = N.rec;
+        G.B = C.online + c.w_off;
+        G.C = l->drec + c.in_off; G.c_sm = N.rec; G.H = rec_s + c.in_off;
+        G.M = static_cast<int>(B) * c.ih * c.iw; G.N = c.ic; G.K = c.oc * 9; G.epi = 1; G.act = N.act;
+        if (int32_t e = hyb_gemm_mode<2>(l, G, st)) return e;
       }
     }
   }

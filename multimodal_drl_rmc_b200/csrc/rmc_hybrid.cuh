@@ -39,8 +39,9 @@ __device__ __forceinline__ const float* hyb_src_row(const HybSrc& s, long long r
 }
 
 // ---------------------------------------------------------------------------------------------- convolution forward
-// one CTA per row: the layer's whole input (<= 4480 floats) is staged in shared memory; a thread owns 4 output channels
-// of one output pixel, so every input value fetched feeds 4 FMAs; weights are warp-broadcast L1 reads.
+// grid = (rows, slices): the layer's whole input (<= 4480 floats) of the row is staged in shared memory; a work item is 4
+// output channels of one output pixel (every input value fetched feeds 4 FMAs; weights are warp-broadcast L1 reads) and
+// a CTA owns a slice of 256 items, so even a 32-row batch spreads over > 148 CTAs.
 __global__ void __launch_bounds__(256) k_hyb_conv_fwd(HybNet N, int li, const float* __restrict__ P, HybSrc src, float* __restrict__ rec_base) {
   extern __shared__ float s_in[];
   const HybConv c = N.conv[li];
@@ -49,12 +50,12 @@ __global__ void __launch_bounds__(256) k_hyb_conv_fwd(HybNet N, int li, const fl
   const float* in = (li == 0) ? hyb_src_row(src, r) + N.macro_len : rec + c.in_off;
   const int n_in = c.ic * c.ih * c.iw;
   for (int t = threadIdx.x; t < n_in; t += blockDim.x) s_in[t] = in[t];
-  if (li == N.n_conv - 1)          // features = [flattened last conv output | macro]
+  if (li == N.n_conv - 1 && blockIdx.y == 0)          // features = [flattened last conv output | macro]
     for (int t = threadIdx.x; t < N.macro_len; t += blockDim.x) rec[N.feat_off + N.conv_flat + t] = hyb_src_row(src, r)[t];
   __syncthreads();
   const int npix = c.oh * c.ow, ng = c.oc >> 2;
   const float* W = P + c.w_off;
-  for (int t = threadIdx.x; t < ng * npix; t += blockDim.x) {
+  for (int t = blockIdx.y * blockDim.x + threadIdx.x; t < ng * npix; t += gridDim.y * blockDim.x) {
     const int g = t / npix, pix = t - g * npix;
     const int oy = pix / c.ow, ox = pix - oy * c.ow;
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
@@ -87,11 +88,25 @@ __global__ void __launch_bounds__(256) k_hyb_conv_fwd(HybNet N, int li, const fl
   }
 }
 
+// features = [flattened last conv output | macro]: the macro part of every pass row
+__global__ void k_hyb_copy_macro(HybNet N, HybSrc src, float* __restrict__ rec_base, long long R) {
+  const long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (t >= R * N.macro_len) return;
+  const long long r = t / N.macro_len;
+  const int d = static_cast<int>(t - r * N.macro_len);
+  rec_base[r * N.rec + N.feat_off + N.conv_flat + d] = hyb_src_row(src, r)[d];
+}
+
 // ---------------------------------------------------------------------------------------------- generic SGEMM
-// C[m][n] = sum_k A(m,k) * B(k,n) with arbitrary element strides (covers x.W^T, dY.W and dY^T.X), 64x64x16 tiles,
-// 256 threads, 4x4 register tiles, fixed summation order.
+// C[m][n] = sum_k A(m,k) * B(k,n), 64x64x16 tiles, 256 threads, 4x4 register tiles, fixed summation order.
+// MODE 0  strided operands (covers x.W^T, dY.W and dY^T.X of the dense layers)
+// MODE 1  convolution forward as an implicit GEMM: m = (row, output pixel), k = (ic, ky, kx), n = oc;
+//         A is the im2col view of the layer input (zero outside the image), B = W[oc][k]
+// MODE 2  convolution data gradient: m = (row, input pixel), k = (oc, ky, kx), n = ic; A gathers the output deltas that the
+//         input pixel feeds (stride-aware), B = W[oc][ic][ky][kx]
+// MODE 3  convolution weight gradient: m = oc, k = (row, output pixel), n = (ic, ky, kx); A = output deltas, B = im2col
 //   epi 0: C = act(C + bias[n])            (forward)
-//   epi 1: C = C * act'(H[m][n])           (data gradient; H = the forward output of the layer below)
+//   epi 1: C = C * act'(H at C's address)  (data gradient; H = the forward activation below)
 //   epi 2: C as is                         (weight gradient, written into the gradient blob)
 struct HybGemm {
   const float* A; long long a_sm, a_sk;
@@ -100,7 +115,65 @@ struct HybGemm {
   const float* bias;
   const float* H; long long h_sm;
   int M, N, K, epi, act;
+  int splits, k_chunk;              // split-K: blockIdx.z owns k in [z*k_chunk, (z+1)*k_chunk); raw partial sums go to ws[z][M][N]
+  float* ws;
+  // convolution geometry (MODE 1-3): image operand = img(row) + (c*ih + y)*iw + x, delta operand = dz + row*dz_stride + oc*npix + pix
+  HybConv cv;
+  const float* img; long long img_stride;       // layer input of row r (nullptr: take it from `src`, row src_row0 + r, after the macro part)
+  HybSrc src; long long src_row0; int macro_len;
+  const float* dz; long long dz_stride;
 };
+__device__ __forceinline__ const float* hyb_img_row(const HybGemm& G, long long r) {
+  return (G.img != nullptr) ? G.img + r * G.img_stride : hyb_src_row(G.src, G.src_row0 + r) + G.macro_len;
+}
+// im2col element: row r, output pixel pix, k9 = (ic, ky, kx)
+__device__ __forceinline__ float hyb_im2col(const HybGemm& G, int r, int pix, int k9) {
+  const HybConv& c = G.cv;
+  const int ic = k9 / 9, q = k9 - 9 * ic, ky = q / 3, kx = q - 3 * ky;
+  const int oy = pix / c.ow, ox = pix - oy * c.ow;
+  const int iy = oy * c.sh + ky - 1, ix = ox * c.sw + kx - 1;
+  if (iy < 0 || iy >= c.ih || ix < 0 || ix >= c.iw) return 0.f;
+  return __ldg(hyb_img_row(G, r) + (ic * c.ih + iy) * c.iw + ix);
+}
+template <int MODE>
+__device__ __forceinline__ float hyb_load_a(const HybGemm& G, int m, int k) {
+  if constexpr (MODE == 0) return __ldg(G.A + m * G.a_sm + k * G.a_sk);
+  const HybConv& c = G.cv;
+  const int npix = c.oh * c.ow;
+  if constexpr (MODE == 1) { const int r = m / npix; return hyb_im2col(G, r, m - r * npix, k); }
+  if constexpr (MODE == 2) {
+    const int ipix = c.ih * c.iw, r = m / ipix, p = m - r * ipix, iy = p / c.iw, ix = p - iy * c.iw;
+    const int oc = k / 9, q = k - 9 * oc, ky = q / 3, kx = q - 3 * ky;
+    const int ny = iy + 1 - ky, nx = ix + 1 - kx;
+    if (ny < 0 || nx < 0 || ny % c.sh != 0 || nx % c.sw != 0) return 0.f;
+    const int oy = ny / c.sh, ox = nx / c.sw;
+    if (oy >= c.oh || ox >= c.ow) return 0.f;
+    return __ldg(G.dz + r * G.dz_stride + oc * npix + oy * c.ow + ox);
+  }
+  const int r = k / npix;                                  // MODE 3
+  return __ldg(G.dz + r * G.dz_stride + m * npix + (k - r * npix));
+}
+template <int MODE>
+__device__ __forceinline__ float hyb_load_b(const HybGemm& G, int k, int n) {
+  if constexpr (MODE == 0 || MODE == 1) return __ldg(G.B + k * G.b_sk + n * G.b_sn);
+  const HybConv& c = G.cv;
+  if constexpr (MODE == 2) { const int oc = k / 9; return __ldg(G.B + (oc * c.ic + n) * 9 + (k - 9 * oc)); }
+  const int npix = c.oh * c.ow, r = k / npix;              // MODE 3
+  return hyb_im2col(G, r, k - r * npix, n);
+}
+// address of C[m][n] (and of the matching activation for epi 1) relative to G.C / G.H
+template <int MODE>
+__device__ __forceinline__ long long hyb_c_index(const HybGemm& G, int m, int n) {
+  if constexpr (MODE == 1) { const int npix = G.cv.oh * G.cv.ow, r = m / npix; return r * G.c_sm + n * npix + (m - r * npix); }
+  if constexpr (MODE == 2) { const int ipix = G.cv.ih * G.cv.iw, r = m / ipix; return r * G.c_sm + n * ipix + (m - r * ipix); }
+  return m * G.c_sm + n;
+}
+__device__ __forceinline__ float hyb_epilogue(const HybGemm& G, float v, int n, long long ci) {
+  if (G.epi == 0) return act_fwd(v + __ldg(G.bias + n), G.act);
+  if (G.epi == 1) return act_bwd(v, __ldg(G.H + ci), G.act);
+  return v;
+}
+template <int MODE>
 __global__ void __launch_bounds__(256) k_hyb_gemm(HybGemm G) {
   __shared__ float sA[16][65], sB[16][65];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -110,24 +183,38 @@ __global__ void __launch_bounds__(256) k_hyb_gemm(HybGemm G) {
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  // loader mapping follows the unit-stride dimension of each operand
-  const bool a_kfast = G.a_sk == 1, b_kfast = G.b_sk == 1;
-  for (int k0 = 0; k0 < G.K; k0 += 16) {
+  // loader mapping follows the unit-stride dimension of each operand; the NEXT k-tile is fetched into registers while the
+  // current one is multiplied (the global-load latency of a tile would otherwise be exposed once per 16 k)
+  const bool a_kfast = (MODE == 0) ? (G.a_sk == 1) : (MODE == 3), b_kfast = (MODE == 0 || MODE == 1) ? (G.b_sk == 1) : (MODE == 3);
+  float ra[4], rb[4];
+  auto fetch = [&](int k0, int k_end) {
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const int t = tid + 256 * e;                     // 1024 elements per operand tile
       {
         const int kk = a_kfast ? (t & 15) : (t >> 6), mm = a_kfast ? (t >> 4) : (t & 63);
         const int m = m0 + mm, k = k0 + kk;
-        sA[kk][mm] = (m < G.M && k < G.K) ? __ldg(G.A + m * G.a_sm + k * G.a_sk) : 0.f;
+        ra[e] = (m < G.M && k < k_end) ? hyb_load_a<MODE>(G, m, k) : 0.f;
       }
       {
         const int kk = b_kfast ? (t & 15) : (t >> 6), nn = b_kfast ? (t >> 4) : (t & 63);
         const int n = n0 + nn, k = k0 + kk;
-        sB[kk][nn] = (n < G.N && k < G.K) ? __ldg(G.B + k * G.b_sk + n * G.b_sn) : 0.f;
+        rb[e] = (n < G.N && k < k_end) ? hyb_load_b<MODE>(G, k, n) : 0.f;
       }
     }
+  };
+  const int k_lo = (G.splits > 1) ? blockIdx.z * G.k_chunk : 0;
+  const int k_hi = (G.splits > 1) ? min(G.K, k_lo + G.k_chunk) : G.K;
+  fetch(k_lo, k_hi);
+  for (int k0 = k_lo; k0 < k_hi; k0 += 16) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int t = tid + 256 * e;
+      sA[a_kfast ? (t & 15) : (t >> 6)][a_kfast ? (t >> 4) : (t & 63)] = ra[e];
+      sB[b_kfast ? (t & 15) : (t >> 6)][b_kfast ? (t >> 4) : (t & 63)] = rb[e];
+    }
     __syncthreads();
+    if (k0 + 16 < k_hi) fetch(k0 + 16, k_hi);
 #pragma unroll
     for (int kk = 0; kk < 16; ++kk) {
       float a[4], b[4];
@@ -148,12 +235,44 @@ __global__ void __launch_bounds__(256) k_hyb_gemm(HybGemm G) {
     for (int j = 0; j < 4; ++j) {
       const int n = n0 + tx + 16 * j;
       if (n >= G.N) continue;
-      float v = acc[i][j];
-      if (G.epi == 0) v = act_fwd(v + __ldg(G.bias + n), G.act);
-      else if (G.epi == 1) v = act_bwd(v, __ldg(G.H + m * G.h_sm + n), G.act);
-      G.C[m * G.c_sm + n] = v;
+      if (G.splits > 1) {
+        G.ws[(static_cast<long long>(blockIdx.z) * G.M + m) * G.N + n] = acc[i][j];
+      } else {
+        const long long ci = hyb_c_index<MODE>(G, m, n);
+        G.C[ci] = hyb_epilogue(G, acc[i][j], n, ci);
+      }
     }
   }
+}
+
+// split-K second pass: C = epilogue(sum_z ws[z]) in split order (deterministic)
+template <int MODE>
+__global__ void __launch_bounds__(256) k_hyb_splitk_reduce(HybGemm G) {
+  const long long t = blockIdx.x * 256ll + threadIdx.x;
+  if (t >= static_cast<long long>(G.M) * G.N) return;
+  const int m = static_cast<int>(t / G.N), n = static_cast<int>(t - static_cast<long long>(m) * G.N);
+  float v = 0.f;
+  for (int z = 0; z < G.splits; ++z) v += __ldcg(G.ws + (static_cast<long long>(z) * G.M + m) * G.N + n);
+  const long long ci = hyb_c_index<MODE>(G, m, n);
+  G.C[ci] = hyb_epilogue(G, v, n, ci);
+}
+
+// per-channel sums of the output deltas of a conv layer: db[oc] = sum_{row, pix} dz   (one CTA per channel, fixed-order tree)
+__global__ void __launch_bounds__(256) k_hyb_conv_bias_grad(const float* __restrict__ dz, long long dz_stride, int npix, long long B, float* __restrict__ out) {
+  __shared__ float s_red[256];
+  const int oc = blockIdx.x;
+  float s = 0.f;
+  for (long long t = threadIdx.x; t < B * npix; t += 256) {
+    const long long r = t / npix;
+    s += __ldg(dz + r * dz_stride + oc * npix + (t - r * npix));
+  }
+  s_red[threadIdx.x] = s;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if (threadIdx.x < w) s_red[threadIdx.x] += s_red[threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[oc] = s_red[0];
 }
 
 // column sums: out[n] = sum_m X[m*ld + n]   (bias gradients of the dense layers), one thread per column, fixed order
@@ -315,7 +434,7 @@ __global__ void __launch_bounds__(256) k_hyb_conv_dgrad(HybNet N, int li, const 
   __syncthreads();
   const int ipix = c.ih * c.iw, ng = c.ic >> 2;
   const float* W = P + c.w_off;
-  for (int t = threadIdx.x; t < ng * ipix; t += blockDim.x) {
+  for (int t = blockIdx.y * blockDim.x + threadIdx.x; t < ng * ipix; t += gridDim.y * blockDim.x) {
     const int g = t / ipix, pix = t - g * ipix;
     const int iy = pix / c.iw, ix = pix - iy * c.iw;
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
