@@ -510,6 +510,25 @@ def extra_workloads(agent):
             del ens, members
     except Exception as exc:  # pragma: no cover
         out["ensemble8"] = {"error": repr(exc)}
+    try:   # the repo-HEAD hybrid CNN + MLP network (env/dqn_config.py:66-193), HEAD defaults (B = 32, uniform replay)
+        import tempfile
+        from multimodal_drl_rmc_b200 import macro_config
+        from oracle.dqn_oracle import synthetic_transitions
+        tmp = tempfile.mkdtemp(prefix="rmc_bench_hyb_")
+        for name, algo, bsz in (("hybrid_default32", "DuelingDoubleDQNAgent", 32), ("hybrid_per256", "PerDuelingDoubleDQNAgent", 256)):
+            ah = macro_config.make_agent(algo, macro_config.HYBRID_OBS_DIM, bsz, 20000, save_dir=tmp + "/", log_dir=tmp + "/", activation="hybrid",
+                                         gpu=str(agent.device.index))
+            ah.replay_memory_buffer._ring.push_host(*synthetic_transitions(20000, macro_config.HYBRID_OBS_DIM, 20251018))
+
+            def steph():
+                ah.step += 1
+                ah.learn(fuse_target_update=True)
+            ms = _time_steps(steph, 100, 5)
+            out[name] = {"us_per_step": 1e3 * ms, "transitions_per_s": bsz / (ms * 1e-3), "params": 885481,
+                         "mode": "exact fp32 (implicit-GEMM convolutions, one kernel per layer and direction)"}
+            del ah
+    except Exception as exc:  # pragma: no cover
+        out["hybrid_default32"] = {"error": repr(exc)}
     try:   # C5 at N = 1: one learner step on a 65,536-transition minibatch
         wl = dict(WORKLOADS["per256"], B=65536)
         a5, _ = build_gpu_agent(wl, agent.device.index, seed=12)
