@@ -57,3 +57,31 @@ def test_cross_load_with_the_reference_implementation(tmp_path):
     path2 = str(tmp_path / "ref" / "y.pack")
     ref.save(path2, 123, 4, np.float64(1.5), np.float64(90.0))
     assert open(path, "rb").read() == open(path2, "rb").read()
+
+
+def test_hybrid_state_dict_layout():
+    """The hybrid body's parameter names/shapes are those of the reference's shipped hybrid checkpoints."""
+    from multimodal_drl_rmc_b200.macro_config import network_config_hybrid, HYBRID_OBS_DIM
+    net = Networks.DuelingDeepQNetwork(torch.device("cpu"), 1e-4, network_config_hybrid, ObsSpace(HYBRID_OBS_DIM), 8)
+    got = [(k, tuple(v.shape)) for k, v in net.state_dict().items()]
+    assert got == [("net.cnn_stream.0.weight", (32, 2, 3, 3)), ("net.cnn_stream.0.bias", (32,)),
+                   ("net.cnn_stream.2.weight", (64, 32, 3, 3)), ("net.cnn_stream.2.bias", (64,)),
+                   ("net.cnn_stream.4.weight", (64, 64, 3, 3)), ("net.cnn_stream.4.bias", (64,)),
+                   ("net.dense_stream.0.weight", (512, 1358)), ("net.dense_stream.0.bias", (512,)),
+                   ("net.dense_stream.2.weight", (256, 512)), ("net.dense_stream.2.bias", (256,)),
+                   ("fc_val.weight", (1, 256)), ("fc_val.bias", (1,)), ("fc_adv.weight", (8, 256)), ("fc_adv.bias", (8,))]
+    assert sum(v.numel() for v in net.state_dict().values()) == 885481 and net._hybrid is not None
+
+
+@pytest.mark.skipif(not refharness.reference_available(), reason="reference tree only exists in the build container")
+def test_shipped_hybrid_checkpoint_loads_and_resaves_byte_identically(tmp_path):
+    """save/1ramp_1x3/DuelingDoubleDQNAgent_lr0.0001_model.pack (3.5 MB, the repo-HEAD network) through our Network."""
+    from multimodal_drl_rmc_b200.macro_config import network_config_hybrid, HYBRID_OBS_DIM
+    src = os.path.join(refharness.REFERENCE_ROOT, "save", "1ramp_1x3", "DuelingDoubleDQNAgent_lr0.0001_model.pack")
+    if not os.path.exists(src):
+        pytest.skip("shipped hybrid checkpoint not present")
+    net = Networks.DuelingDeepQNetwork(torch.device("cpu"), 1e-4, network_config_hybrid, ObsSpace(HYBRID_OBS_DIM), 8)
+    meta = net.load(src)
+    out = str(tmp_path / "h.pack")
+    net.save(out, *meta)
+    assert open(out, "rb").read() == open(src, "rb").read()
