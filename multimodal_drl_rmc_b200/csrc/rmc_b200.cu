@@ -44,6 +44,32 @@ static int32_t fail(int32_t code, const std::string& msg) {
     if (_e != cudaSuccess) return fail(RMC_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(_e)); \
   } while (0)
 
+
+// Programmatic dependent launch for the multi-kernel pipelines (tensor-core step, hybrid network, grid-wide sampler / tree
+// write-back, peer exchange): every kernel of these chains begins with pdl_enter() (griddepcontrol.launch_dependents +
+// griddepcontrol.wait), so the NEXT kernel's launch latency overlaps this kernel's execution while its body still runs
+// strictly after this kernel has completed and flushed.  RMC_PDL=0 launches them as ordinary stream-ordered kernels.
+// Measured (B200): tensor-core step 173 -> 167 us; for the hybrid network's many multi-wave kernels it is neutral at
+// B = 32 and SLOWER at B = 256 (1.63 -> 2.01 ms: early-resident dependent CTAs take SM slots from the running grid), so
+// the hybrid paths switch it off with a PdlScope.
+static thread_local bool g_pdl_on = true;
+struct PdlScope {
+  bool prev;
+  explicit PdlScope(bool on) : prev(g_pdl_on) { g_pdl_on = on; }
+  ~PdlScope() { g_pdl_on = prev; }
+};
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  static const bool enabled = [] { const char* e = std::getenv("RMC_PDL"); return !(e && e[0] == '0'); }();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = (enabled && g_pdl_on) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 static inline cudaStream_t as_stream(rmc_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 static inline unsigned blocks_for(long long n, int threads) { return static_cast<unsigned>((n + threads - 1) / threads); }
 static inline int round4(int x) { return (x + 3) & ~3; }
@@ -240,7 +266,7 @@ static int32_t tree_rebuild(rmc_replay* r, cudaStream_t st) {
 }
 static int32_t minmax_rebuild(rmc_replay* r, cudaStream_t st) {
   const unsigned grid = std::max(1u, std::min(static_cast<unsigned>(kExtBlocks), blocks_for(r->cap, 1024)));
-  k_extremes_scan<<<grid, 256, 0, st>>>(r->dev, r->ext_parts, r->ext_arrive);
+  RMC_CUDA(launch_pdl(k_extremes_scan, dim3(grid), dim3(256), 0, st, r->dev, r->ext_parts, r->ext_arrive));
   RMC_KERNEL_OK();
   return RMC_OK;
 }
@@ -392,9 +418,9 @@ static int32_t launch_per_sample(const ReplayDev& R, long long B, long long Bglo
                                  unsigned long long seed, unsigned long long counter, long long* nodes, float* is_w, float* rows,
                                  double* leaf_p, cudaStream_t st) {
   if (B >= kLaneSampleMin)
-    k_per_sample_lane<<<blocks_for(B, kLaneThreads), kLaneThreads, 0, st>>>(R, B, Bglobal, shard_off, beta, u, seed, counter, 0u, nodes, is_w, rows, leaf_p);
+    RMC_CUDA(launch_pdl(k_per_sample_lane, dim3(blocks_for(B, kLaneThreads)), dim3(kLaneThreads), 0, st, R, B, Bglobal, shard_off, beta, u, seed, counter, 0u, nodes, is_w, rows, leaf_p));
   else
-    k_per_sample<<<blocks_for(B, kWarps), kThreads, 0, st>>>(R, B, Bglobal, shard_off, beta, u, seed, counter, 0u, nodes, is_w, rows, leaf_p);
+    RMC_CUDA(launch_pdl(k_per_sample, dim3(blocks_for(B, kWarps)), dim3(kThreads), 0, st, R, B, Bglobal, shard_off, beta, u, seed, counter, 0u, nodes, is_w, rows, leaf_p));
   RMC_KERNEL_OK();
   return RMC_OK;
 }
@@ -422,26 +448,26 @@ extern "C" int32_t rmc_uniform_sample(rmc_replay_t* r, int64_t batch, const int6
   if (!r || batch < 1 || !out_slots_dev) return fail(RMC_ERR_ARG, "rmc_uniform_sample: bad args");
   if (r->size < batch) return fail(RMC_ERR_STATE, "rmc_uniform_sample: sample larger than population");
   if (int32_t e = use_device(r->device)) return e;
-  k_uniform_sample<<<blocks_for(batch, kWarps), kThreads, 0, as_stream(s)>>>(r->dev, batch, 0, reinterpret_cast<const long long*>(idx_dev),
+  RMC_CUDA(launch_pdl(k_uniform_sample, dim3(blocks_for(batch, kWarps)), dim3(kThreads), 0, as_stream(s), r->dev, batch, 0, reinterpret_cast<const long long*>(idx_dev),
                                                                             seed, counter, 0u,
-                                                                            reinterpret_cast<long long*>(out_slots_dev), out_rows_dev);
+                                                                            reinterpret_cast<long long*>(out_slots_dev), out_rows_dev));
   RMC_KERNEL_OK();
   return RMC_OK;
 }
 
 static int32_t tree_update_large(rmc_replay* r, const long long* nodes, const float* pri, long long n, bool stamps_done, cudaStream_t st) {
   if (!stamps_done) {
-    k_tree_stamp<<<blocks_for(n, 256), 256, 0, st>>>(r->dev, nodes, n);
+    RMC_CUDA(launch_pdl(k_tree_stamp, dim3(blocks_for(n, 256)), dim3(256), 0, st, r->dev, nodes, n));
     RMC_KERNEL_OK();
   }
   // ancestors below the top levels by float64 reductions (few updates per node); the contended top is rebuilt by one CTA
   int L = 0;
   while (L < 11 && (2ll << L) <= r->cap) ++L;             // largest L <= 11 with 2^L <= cap
   const int F = (L >= 3 && n >= 1024) ? (1 << L) - 1 : 0; // small batches / tiny trees: plain propagation to the root
-  k_tree_apply<<<blocks_for(n, 256), 256, 0, st>>>(r->dev, nodes, pri, n, static_cast<long long>(F));
+  RMC_CUDA(launch_pdl(k_tree_apply, dim3(blocks_for(n, 256)), dim3(256), 0, st, r->dev, nodes, pri, n, static_cast<long long>(F)));
   RMC_KERNEL_OK();
   if (F > 0) {
-    k_tree_rebuild_top<<<1, 1024, 0, st>>>(r->dev, F);
+    RMC_CUDA(launch_pdl(k_tree_rebuild_top, dim3(1), dim3(1024), 0, st, r->dev, F));
     RMC_KERNEL_OK();
   }
   return minmax_rebuild(r, st);
@@ -455,12 +481,12 @@ extern "C" int32_t rmc_per_update_from_td(rmc_replay_t* r, const int64_t* nodes_
   const long long* nodes = reinterpret_cast<const long long*>(nodes_dev);
   if (batch <= kTreeCtaMax) {
     float* pri = out_pri_dev ? out_pri_dev : r->scratch_pri;
-    k_tree_update_small<<<1, kThreads, 0, st>>>(r->dev, nodes, nullptr, abs_td_dev, pri, batch, eps, alpha, pmax);
+    RMC_CUDA(launch_pdl(k_tree_update_small, dim3(1), dim3(kThreads), 0, st, r->dev, nodes, nullptr, abs_td_dev, pri, batch, eps, alpha, pmax));
     RMC_KERNEL_OK();
     return RMC_OK;
   }
   if (!out_pri_dev) return fail(RMC_ERR_ARG, "rmc_per_update_from_td: out_pri_dev required for batch > 4096");
-  k_td_to_pri<<<blocks_for(batch, 256), 256, 0, st>>>(abs_td_dev, out_pri_dev, batch, eps, alpha, pmax);
+  RMC_CUDA(launch_pdl(k_td_to_pri, dim3(blocks_for(batch, 256)), dim3(256), 0, st, abs_td_dev, out_pri_dev, batch, eps, alpha, pmax));
   RMC_KERNEL_OK();
   return tree_update_large(r, nodes, out_pri_dev, batch, false, st);
 }
@@ -471,7 +497,7 @@ extern "C" int32_t rmc_per_update(rmc_replay_t* r, const int64_t* nodes_dev, con
   cudaStream_t st = as_stream(s);
   const long long* nodes = reinterpret_cast<const long long*>(nodes_dev);
   if (batch <= kTreeCtaMax) {
-    k_tree_update_small<<<1, kThreads, 0, st>>>(r->dev, nodes, pri_dev, nullptr, nullptr, batch, 0.f, 0.f, 0.f);
+    RMC_CUDA(launch_pdl(k_tree_update_small, dim3(1), dim3(kThreads), 0, st, r->dev, nodes, pri_dev, nullptr, nullptr, batch, 0.f, 0.f, 0.f));
     RMC_KERNEL_OK();
     return RMC_OK;
   }
@@ -803,23 +829,23 @@ static int32_t step_tc(rmc_learner* l, rmc_replay* r, const rmc_step_args_t* a, 
     if (r->prioritized) {
       if (int32_t e = launch_per_sample(r->dev, B, S.Bglobal, S.shard_off, S.beta, S.u, S.seed, S.counter, C.nodes, C.is_w, C.X, C.leaf_p, st)) return e;
     } else {
-      k_uniform_sample<<<blocks_for(B, kWarps), kThreads, 0, st>>>(r->dev, B, S.shard_off, S.idx, S.seed, S.counter, 0u, C.nodes, C.X);
+      RMC_CUDA(launch_pdl(k_uniform_sample, dim3(blocks_for(B, kWarps)), dim3(kThreads), 0, st, r->dev, B, S.shard_off, S.idx, S.seed, S.counter, 0u, C.nodes, C.X));
       RMC_KERNEL_OK();
     }
   }
   // bf16 operand images of the online net (forward + backward forms) and of the target net
   if (l->tc_packed_version != l->online_version) {
-    k_tc_pack<<<blocks_for(kH2 * kH1, 256), 256, 0, st>>>(l->blobs[RMC_ONLINE], l->L, l->tc_packed);
+    RMC_CUDA(launch_pdl(k_tc_pack, dim3(blocks_for(kH2 * kH1, 256)), dim3(256), 0, st, l->blobs[RMC_ONLINE], l->L, l->tc_packed));
     RMC_KERNEL_OK();
     l->tc_packed_version = l->online_version;
   }
   if (l->tc_bwd_version != l->online_version) {
-    k_tc_pack_bwd<<<blocks_for(kH1 * kH2, 256), 256, 0, st>>>(l->blobs[RMC_ONLINE], l->L, l->tc_packed_bwd);
+    RMC_CUDA(launch_pdl(k_tc_pack_bwd, dim3(blocks_for(kH1 * kH2, 256)), dim3(256), 0, st, l->blobs[RMC_ONLINE], l->L, l->tc_packed_bwd));
     RMC_KERNEL_OK();
     l->tc_bwd_version = l->online_version;
   }
   if (l->tc_target_version != l->target_version) {
-    k_tc_pack<<<blocks_for(kH2 * kH1, 256), 256, 0, st>>>(l->blobs[RMC_TARGET], l->L, l->tc_packed_target);
+    RMC_CUDA(launch_pdl(k_tc_pack, dim3(blocks_for(kH2 * kH1, 256)), dim3(256), 0, st, l->blobs[RMC_TARGET], l->L, l->tc_packed_target));
     RMC_KERNEL_OK();
     l->tc_target_version = l->target_version;
   }
@@ -839,32 +865,32 @@ static int32_t step_tc(rmc_learner* l, rmc_replay* r, const rmc_step_args_t* a, 
   J.j[0].cta_begin = 0;      J.j[0].cta_count = c0;
   J.j[1].cta_begin = c0;     J.j[1].cta_count = c0;
   J.j[2].cta_begin = 2 * c0; J.j[2].cta_count = c2;
-  k_tc_fwd3<<<2 * c0 + c2, kTcFwdThreads, kTcSmemBytes, st>>>(J, l->L.D, l->L.A, l->L.NH, l->L.dueling, C.X, B);
+  RMC_CUDA(launch_pdl(k_tc_fwd3, dim3(2 * c0 + c2), dim3(kTcFwdThreads), kTcSmemBytes, st, J, l->L.D, l->L.A, l->L.NH, l->L.dueling, C.X, B));
   RMC_KERNEL_OK();
   l->ctx.rp = r->dev;
   const unsigned td_blocks = blocks_for(B, kTdThreads);
   if (td_blocks > 1024) return fail(RMC_ERR_UNSUPPORTED, "tensor-core learner mode: batch above 131,072");
-  k_tc_td<<<td_blocks, kTdThreads, 0, st>>>(l->ctx, S, T);
+  RMC_CUDA(launch_pdl(k_tc_td, dim3(td_blocks), dim3(kTdThreads), 0, st, l->ctx, S, T));
   RMC_KERNEL_OK();
   // backward: dgrad chain + weight gradients fused per 128-row tile
   T.n_part = static_cast<int>(grid);
-  k_tc_bwd_fused<<<grid, kThreads, kTcBwdFusedSmemBytes, st>>>(l->ctx, reinterpret_cast<const unsigned char*>(l->tc_packed_bwd), B, T);
+  RMC_CUDA(launch_pdl(k_tc_bwd_fused, dim3(grid), dim3(kThreads), kTcBwdFusedSmemBytes, st, l->ctx, reinterpret_cast<const unsigned char*>(l->tc_packed_bwd), B, T));
   RMC_KERNEL_OK();
   l->epoch = (l->epoch >= 0x7fffffffu) ? 1u : l->epoch + 1u;
   S.epoch = l->epoch;
   // the Adam kernel refreshes the bf16 operand images element by element: no pack kernels on the next step
   const TcPackOut P{l->tc_packed, l->tc_packed_bwd, l->tc_packed_target};
-  k_tc_reduce_adam<<<blocks_for(l->L.total, 128), 256, 0, st>>>(l->ctx, S, T, static_cast<int>(td_blocks), P);
+  RMC_CUDA(launch_pdl(k_tc_reduce_adam, dim3(blocks_for(l->L.total, 128)), dim3(256), 0, st, l->ctx, S, T, static_cast<int>(td_blocks), P));
   RMC_KERNEL_OK();
   l->loss_epoch = S.epoch;
   if (a->phases & RMC_PH_ADAM) l->tc_packed_version = l->tc_bwd_version = ++l->online_version;
   if (a->phases & (RMC_PH_POLYAK | RMC_PH_HARDSYNC)) l->tc_target_version = ++l->target_version;
   if ((a->phases & RMC_PH_PRIORITY) && l->spec.prioritized) {
     if (B <= kTreeCtaMax) {
-      k_tree_update_small<<<1, kThreads, 0, st>>>(r->dev, C.nodes, nullptr, C.abs_td, C.pri, B, S.per_eps, S.per_alpha, S.per_pmax);
+      RMC_CUDA(launch_pdl(k_tree_update_small, dim3(1), dim3(kThreads), 0, st, r->dev, C.nodes, nullptr, C.abs_td, C.pri, B, S.per_eps, S.per_alpha, S.per_pmax));
       RMC_KERNEL_OK();
     } else {
-      k_td_to_pri<<<blocks_for(B, 256), 256, 0, st>>>(C.abs_td, C.pri, B, S.per_eps, S.per_alpha, S.per_pmax);
+      RMC_CUDA(launch_pdl(k_td_to_pri, dim3(blocks_for(B, 256)), dim3(256), 0, st, C.abs_td, C.pri, B, S.per_eps, S.per_alpha, S.per_pmax));
       RMC_KERNEL_OK();
       if (int32_t e = tree_update_large(r, C.nodes, C.pri, B, false, st)) return e;
     }
@@ -998,10 +1024,10 @@ static int32_t hyb_gemm_mode(rmc_learner* l, HybGemm G, cudaStream_t st) {
   G.splits = splits; G.ws = l->hyb_ws;
   G.k_chunk = ((G.K + splits - 1) / splits + 15) / 16 * 16;
   if (splits > 1) G.splits = (G.K + G.k_chunk - 1) / G.k_chunk;
-  k_hyb_gemm<MODE><<<dim3(blocks_for(G.N, 64), blocks_for(G.M, 64), static_cast<unsigned>(G.splits)), 256, 0, st>>>(G);
+  RMC_CUDA(launch_pdl(k_hyb_gemm<MODE>, dim3(blocks_for(G.N, 64), blocks_for(G.M, 64), static_cast<unsigned>(G.splits)), dim3(256), 0, st, G));
   RMC_KERNEL_OK();
   if (G.splits > 1) {
-    k_hyb_splitk_reduce<MODE><<<blocks_for(static_cast<long long>(G.M) * G.N, 256), 256, 0, st>>>(G);
+    RMC_CUDA(launch_pdl(k_hyb_splitk_reduce<MODE>, dim3(blocks_for(static_cast<long long>(G.M) * G.N, 256)), dim3(256), 0, st, G));
     RMC_KERNEL_OK();
   }
   return RMC_OK;
@@ -1015,7 +1041,7 @@ static int32_t hybrid_forward(rmc_learner* l, const float* P, const HybSrc& src,
     const HybConv& c = N.conv[i];
     if (i == 0 || c.ic * 9 < 64) {          // tiny K (first layer: 2 input channels): the direct kernel
       const unsigned slices = blocks_for(static_cast<long long>(c.oc / 4) * c.oh * c.ow, 256);
-      k_hyb_conv_fwd<<<dim3(static_cast<unsigned>(R), slices, 1), 256, static_cast<size_t>(c.ic) * c.ih * c.iw * sizeof(float), st>>>(N, i, P, src, rec);
+      RMC_CUDA(launch_pdl(k_hyb_conv_fwd, dim3(static_cast<unsigned>(R), slices, 1), dim3(256), static_cast<size_t>(c.ic) * c.ih * c.iw * sizeof(float), st, N, i, P, src, rec));
       RMC_KERNEL_OK();
       continue;
     }
@@ -1026,7 +1052,7 @@ static int32_t hybrid_forward(rmc_learner* l, const float* P, const HybSrc& src,
     G.M = static_cast<int>(R) * c.oh * c.ow; G.N = c.oc; G.K = c.ic * 9; G.epi = 0; G.act = N.act;
     if (int32_t e = hyb_gemm_mode<1>(l, G, st)) return e;
     if (i == N.n_conv - 1) {                 // features = [flattened last conv output | macro]
-      k_hyb_copy_macro<<<blocks_for(R * N.macro_len, 128), 128, 0, st>>>(N, src, rec, R);
+      RMC_CUDA(launch_pdl(k_hyb_copy_macro, dim3(blocks_for(R * N.macro_len, 128)), dim3(128), 0, st, N, src, rec, R));
       RMC_KERNEL_OK();
     }
   }
@@ -1039,12 +1065,13 @@ static int32_t hybrid_forward(rmc_learner* l, const float* P, const HybSrc& src,
     G.bias = P + d.b_off; G.M = static_cast<int>(R); G.N = d.out; G.K = d.in; G.epi = 0; G.act = N.act;
     if (int32_t e = hyb_gemm(l, G, st)) return e;
   }
-  k_hyb_heads_fwd<<<blocks_for(R, 8), 256, 0, st>>>(N, P, rec, R);
+  RMC_CUDA(launch_pdl(k_hyb_heads_fwd, dim3(blocks_for(R, 8)), dim3(256), 0, st, N, P, rec, R));
   RMC_KERNEL_OK();
   return RMC_OK;
 }
 
 static int32_t hybrid_step(rmc_learner* l, rmc_replay* r, const rmc_step_args_t* a, StepScalars& S, cudaStream_t st) {
+  const PdlScope no_pdl(false);
   const HybNet& N = l->H;
   AgentCtx& C = l->ctx;
   const long long B = a->batch;
@@ -1055,7 +1082,7 @@ static int32_t hybrid_step(rmc_learner* l, rmc_replay* r, const rmc_step_args_t*
     if (r->prioritized) {
       if (int32_t e = launch_per_sample(r->dev, B, S.Bglobal, S.shard_off, S.beta, S.u, S.seed, S.counter, C.nodes, C.is_w, C.X, C.leaf_p, st)) return e;
     } else {
-      k_uniform_sample<<<blocks_for(B, kWarps), kThreads, 0, st>>>(r->dev, B, S.shard_off, S.idx, S.seed, S.counter, 0u, C.nodes, C.X);
+      RMC_CUDA(launch_pdl(k_uniform_sample, dim3(blocks_for(B, kWarps)), dim3(kThreads), 0, st, r->dev, B, S.shard_off, S.idx, S.seed, S.counter, 0u, C.nodes, C.X));
       RMC_KERNEL_OK();
     }
   }
@@ -1065,14 +1092,14 @@ static int32_t hybrid_step(rmc_learner* l, rmc_replay* r, const rmc_step_args_t*
     const HybSrc src_tg{C.X, l->rf, B, N.D, N.D};
     if (int32_t e = hybrid_forward(l, C.online, src_on, l->rec_on, 2 * B, st)) return e;
     if (int32_t e = hybrid_forward(l, C.target, src_tg, l->rec_tg, B, st)) return e;
-    k_hyb_td<<<td_blocks, 128, 0, st>>>(C, S, N, l->rec_on, l->rec_tg, l->drec);
+    RMC_CUDA(launch_pdl(k_hyb_td, dim3(td_blocks), dim3(128), 0, st, C, S, N, l->rec_on, l->rec_tg, l->drec));
     RMC_KERNEL_OK();
   }
   if (ph & RMC_PH_BACKWARD) {
     const float* rec_s = l->rec_on + B * N.rec;           // records of the s rows
-    k_hyb_heads_dgrad<<<blocks_for(B * N.last_len, 256), 256, 0, st>>>(N, C.online, rec_s, l->drec, B);
+    RMC_CUDA(launch_pdl(k_hyb_heads_dgrad, dim3(blocks_for(B * N.last_len, 256)), dim3(256), 0, st, N, C.online, rec_s, l->drec, B));
     RMC_KERNEL_OK();
-    k_hyb_heads_wgrad<<<blocks_for(static_cast<long long>(N.NH) * N.last_len, 256), 256, 0, st>>>(N, rec_s, l->drec, B, C.grads);
+    RMC_CUDA(launch_pdl(k_hyb_heads_wgrad, dim3(blocks_for(static_cast<long long>(N.NH) * N.last_len, 256)), dim3(256), 0, st, N, rec_s, l->drec, B, C.grads));
     RMC_KERNEL_OK();
     for (int i = N.n_dense - 1; i >= 0; --i) {
       const HybDense& d = N.dense[i];
@@ -1081,7 +1108,7 @@ static int32_t hybrid_step(rmc_learner* l, rmc_replay* r, const rmc_step_args_t*
       W.B = rec_s + d.in_off; W.b_sk = N.rec; W.b_sn = 1;
       W.C = C.grads + d.w_off; W.c_sm = d.in; W.M = d.out; W.N = d.in; W.K = static_cast<int>(B); W.epi = 2;
       if (int32_t e = hyb_gemm(l, W, st)) return e;
-      k_hyb_colsum<<<blocks_for(d.out, 128), 128, 0, st>>>(l->drec + d.out_off, N.rec, static_cast<int>(B), d.out, C.grads + d.b_off);
+      RMC_CUDA(launch_pdl(k_hyb_colsum, dim3(blocks_for(d.out, 128)), dim3(128), 0, st, l->drec + d.out_off, N.rec, static_cast<int>(B), d.out, C.grads + d.b_off));
       RMC_KERNEL_OK();
       HybGemm G{};                                        // dX[r][k] = (sum_n dZ[r][n] W[n][k]) * act'(X[r][k])
       G.A = l->drec + d.out_off; G.a_sm = N.rec; G.a_sk = 1;
@@ -1099,7 +1126,7 @@ static int32_t hybrid_step(rmc_learner* l, rmc_replay* r, const rmc_step_args_t*
       else { W.img = rec_s + c.in_off; W.img_stride = N.rec; }
       W.C = C.grads + c.w_off; W.c_sm = c.ic * 9; W.M = c.oc; W.N = c.ic * 9; W.K = static_cast<int>(B) * npix; W.epi = 2;
       if (int32_t e = hyb_gemm_mode<3>(l, W, st)) return e;
-      k_hyb_conv_bias_grad<<<static_cast<unsigned>(c.oc), 256, 0, st>>>(l->drec + c.out_off, N.rec, npix, B, C.grads + c.b_off);
+      RMC_CUDA(launch_pdl(k_hyb_conv_bias_grad, dim3(static_cast<unsigned>(c.oc)), dim3(256), 0, st, l->drec + c.out_off, N.rec, npix, B, C.grads + c.b_off));
       RMC_KERNEL_OK();
       if (i > 0) {                           // delta of the layer below: (gathered dZ . W) * act'(input activation)
         HybGemm G{};
@@ -1115,7 +1142,7 @@ static int32_t hybrid_step(rmc_learner* l, rmc_replay* r, const rmc_step_args_t*
     l->epoch = (l->epoch >= 0x7fffffffu) ? 1u : l->epoch + 1u;
     S.epoch = l->epoch;
     const int write_loss = (ph & RMC_PH_FORWARD) ? 1 : 0;
-    k_hyb_adam<<<blocks_for(N.total, 256), 256, 0, st>>>(C, S, N.total, static_cast<int>(td_blocks), write_loss);
+    RMC_CUDA(launch_pdl(k_hyb_adam, dim3(blocks_for(N.total, 256)), dim3(256), 0, st, C, S, N.total, static_cast<int>(td_blocks), write_loss));
     RMC_KERNEL_OK();
     if (write_loss) l->loss_epoch = S.epoch;
     if (ph & RMC_PH_ADAM) ++l->online_version;
@@ -1123,10 +1150,10 @@ static int32_t hybrid_step(rmc_learner* l, rmc_replay* r, const rmc_step_args_t*
   }
   if ((ph & RMC_PH_PRIORITY) && l->spec.prioritized) {
     if (B <= kTreeCtaMax) {
-      k_tree_update_small<<<1, kThreads, 0, st>>>(r->dev, C.nodes, nullptr, C.abs_td, C.pri, B, S.per_eps, S.per_alpha, S.per_pmax);
+      RMC_CUDA(launch_pdl(k_tree_update_small, dim3(1), dim3(kThreads), 0, st, r->dev, C.nodes, nullptr, C.abs_td, C.pri, B, S.per_eps, S.per_alpha, S.per_pmax));
       RMC_KERNEL_OK();
     } else {
-      k_td_to_pri<<<blocks_for(B, 256), 256, 0, st>>>(C.abs_td, C.pri, B, S.per_eps, S.per_alpha, S.per_pmax);
+      RMC_CUDA(launch_pdl(k_td_to_pri, dim3(blocks_for(B, 256)), dim3(256), 0, st, C.abs_td, C.pri, B, S.per_eps, S.per_alpha, S.per_pmax));
       RMC_KERNEL_OK();
       if (int32_t e = tree_update_large(r, C.nodes, C.pri, B, false, st)) return e;
     }
@@ -1136,6 +1163,7 @@ static int32_t hybrid_step(rmc_learner* l, rmc_replay* r, const rmc_step_args_t*
 
 // act / Q values / raw heads of n states [n][D] through the hybrid net (chunks of at most 2 * max_batch rows)
 static int32_t hybrid_infer(rmc_learner* l, const float* params, const float* obs_dev, long long n, long long* actions, float* q, int mode, cudaStream_t st) {
+  const PdlScope no_pdl(false);
   const HybNet& N = l->H;
   const long long cap = 2 * l->max_batch;
   const int per_row = (mode == 1) ? N.A : N.NH;
@@ -1143,7 +1171,7 @@ static int32_t hybrid_infer(rmc_learner* l, const float* params, const float* ob
     const long long m = std::min(cap, n - off);
     const HybSrc src{obs_dev + off * N.D, N.D, m, 0, 0};
     if (int32_t e = hybrid_forward(l, params, src, l->rec_on, m, st)) return e;
-    k_hyb_outputs<<<blocks_for(m, 128), 128, 0, st>>>(N, l->rec_on, m, actions ? actions + off : nullptr, q ? q + off * per_row : nullptr, mode);
+    RMC_CUDA(launch_pdl(k_hyb_outputs, dim3(blocks_for(m, 128)), dim3(128), 0, st, N, l->rec_on, m, actions ? actions + off : nullptr, q ? q + off * per_row : nullptr, mode));
     RMC_KERNEL_OK();
   }
   return RMC_OK;
@@ -1173,7 +1201,7 @@ extern "C" int32_t rmc_learner_step(rmc_learner_t* l, rmc_replay_t* r, const rmc
       if (int32_t e = launch_per_sample(r->dev, a->batch, S.Bglobal, S.shard_off, S.beta, S.u, S.seed, S.counter, l->ctx.nodes, l->ctx.is_w, l->ctx.X,
                                         l->ctx.leaf_p, st)) return e;
     } else {
-      k_uniform_sample<<<blocks_for(a->batch, kWarps), kThreads, 0, st>>>(r->dev, a->batch, S.shard_off, S.idx, S.seed, S.counter, 0u, l->ctx.nodes, l->ctx.X);
+      RMC_CUDA(launch_pdl(k_uniform_sample, dim3(blocks_for(a->batch, kWarps)), dim3(kThreads), 0, st, r->dev, a->batch, S.shard_off, S.idx, S.seed, S.counter, 0u, l->ctx.nodes, l->ctx.X));
       RMC_KERNEL_OK();
     }
     S.phases &= ~RMC_PH_SAMPLE;
@@ -1191,7 +1219,7 @@ extern "C" int32_t rmc_learner_step(rmc_learner_t* l, rmc_replay_t* r, const rmc
   if (a->phases & RMC_PH_ADAM) ++l->online_version;
   if (a->phases & (RMC_PH_POLYAK | RMC_PH_HARDSYNC)) ++l->target_version;
   if ((a->phases & RMC_PH_PRIORITY) && l->spec.prioritized && a->batch > kTreeCtaMax) {
-    k_td_to_pri<<<blocks_for(a->batch, 256), 256, 0, st>>>(l->ctx.abs_td, l->ctx.pri, a->batch, S.per_eps, S.per_alpha, S.per_pmax);
+    RMC_CUDA(launch_pdl(k_td_to_pri, dim3(blocks_for(a->batch, 256)), dim3(256), 0, st, l->ctx.abs_td, l->ctx.pri, a->batch, S.per_eps, S.per_alpha, S.per_pmax));
     RMC_KERNEL_OK();
     if (int32_t e = tree_update_large(r, l->ctx.nodes, l->ctx.pri, a->batch, false, st)) return e;
   }
@@ -1328,8 +1356,8 @@ extern "C" int32_t rmc_learner_step_sharded(rmc_learner_t* l, rmc_replay_t* r, r
   if (int32_t e = rmc_learner_step(l, r, &a1, s)) return e;
   // 2. publish: gradient blob, loss partial, (leaf, |td|) slice -> own exchange buffer, then one flag per rank
   const unsigned pub_blocks = std::max(1u, std::min(64u, blocks_for(std::max<long long>(l->L.total, n_local), 1024)));
-  k_comm_publish<<<pub_blocks, 256, 0, st>>>(V, parity, c->epoch, l->ctx.grads, l->L.total, l->ctx.loss, per ? l->ctx.nodes : nullptr, l->ctx.abs_td,
-                                            n_local, c->arrive);
+  RMC_CUDA(launch_pdl(k_comm_publish, dim3(pub_blocks), dim3(256), 0, st, V, parity, c->epoch, l->ctx.grads, l->L.total, l->ctx.loss, per ? l->ctx.nodes : nullptr, l->ctx.abs_td,
+                                            n_local, c->arrive));
   RMC_KERNEL_OK();
   }
   if (!(stages & 2)) return RMC_OK;
@@ -1345,7 +1373,7 @@ extern "C" int32_t rmc_learner_step_sharded(rmc_learner_t* l, rmc_replay_t* r, r
   const bool images = l->tct_ready && l->tc_packed_version == l->online_version && l->tc_bwd_version == l->online_version &&
                       l->tc_target_version == l->target_version;      // keep the bf16 operand images current (tensor-core mode)
   const TcPackOut P{images ? l->tc_packed : nullptr, images ? l->tc_packed_bwd : nullptr, images ? l->tc_packed_target : nullptr};
-  k_comm_reduce_adam<<<param_blocks + gather_blocks, 256, 0, st>>>(l->ctx, S, V, parity, c->epoch, param_blocks, c->g_nodes, c->g_td, per ? 1 : 0, P);
+  RMC_CUDA(launch_pdl(k_comm_reduce_adam, dim3(param_blocks + gather_blocks), dim3(256), 0, st, l->ctx, S, V, parity, c->epoch, param_blocks, c->g_nodes, c->g_td, per ? 1 : 0, P));
   RMC_KERNEL_OK();
   l->loss_epoch = S.epoch;
   ++l->online_version;
@@ -1357,12 +1385,12 @@ extern "C" int32_t rmc_learner_step_sharded(rmc_learner_t* l, rmc_replay_t* r, r
   // 4. PER: the full write-back of the GLOBAL batch on every replica, in global batch order (trees stay identical)
   if (per) {
     if (Bg <= kTreeCtaMax) {
-      k_tree_update_small<<<1, kThreads, 0, st>>>(r->dev, c->g_nodes, nullptr, c->g_td, c->g_pri, Bg, static_cast<float>(l->hyper.per_eps),
-                                                 static_cast<float>(l->hyper.per_alpha), static_cast<float>(l->hyper.per_pmax));
+      RMC_CUDA(launch_pdl(k_tree_update_small, dim3(1), dim3(kThreads), 0, st, r->dev, c->g_nodes, nullptr, c->g_td, c->g_pri, Bg, static_cast<float>(l->hyper.per_eps),
+                                                 static_cast<float>(l->hyper.per_alpha), static_cast<float>(l->hyper.per_pmax)));
       RMC_KERNEL_OK();
     } else {
-      k_td_to_pri<<<blocks_for(Bg, 256), 256, 0, st>>>(c->g_td, c->g_pri, Bg, static_cast<float>(l->hyper.per_eps), static_cast<float>(l->hyper.per_alpha),
-                                                      static_cast<float>(l->hyper.per_pmax));
+      RMC_CUDA(launch_pdl(k_td_to_pri, dim3(blocks_for(Bg, 256)), dim3(256), 0, st, c->g_td, c->g_pri, Bg, static_cast<float>(l->hyper.per_eps), static_cast<float>(l->hyper.per_alpha),
+                                                      static_cast<float>(l->hyper.per_pmax)));
       RMC_KERNEL_OK();
       if (int32_t e = tree_update_large(r, c->g_nodes, c->g_pri, Bg, false, st)) return e;
     }
@@ -1467,7 +1495,7 @@ static int32_t infer_tc(rmc_learner* l, const float* obs_dev, long long n, long 
     RMC_CUDA(cudaFuncSetAttribute(k_mlp_infer_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
   }
   if (l->tc_packed_version != l->online_version) {
-    k_tc_pack<<<blocks_for(kH2 * kH1, 256), 256, 0, st>>>(l->blobs[RMC_ONLINE], l->L, l->tc_packed);
+    RMC_CUDA(launch_pdl(k_tc_pack, dim3(blocks_for(kH2 * kH1, 256)), dim3(256), 0, st, l->blobs[RMC_ONLINE], l->L, l->tc_packed));
     RMC_KERNEL_OK();
     l->tc_packed_version = l->online_version;
   }

@@ -54,6 +54,7 @@ __device__ __forceinline__ long long ld_sys_s64(const long long* p) {
 __global__ void __launch_bounds__(256) k_comm_publish(CommView V, int parity, unsigned epoch, const float* __restrict__ grads, int total,
                                                       const float* __restrict__ loss, const long long* __restrict__ nodes,
                                                       const float* __restrict__ abs_td, long long n_local, unsigned* arrive) {
+  pdl_enter();
   __shared__ bool s_last;
   unsigned char* slot = comm_slot(V, V.rank, parity);
   float* g = reinterpret_cast<float*>(slot);
@@ -82,6 +83,7 @@ __global__ void __launch_bounds__(256) k_comm_publish(CommView V, int parity, un
 // blocks [0, param_blocks): parameters; the remaining blocks: (leaf, |td|) gather.
 __global__ void __launch_bounds__(256) k_comm_reduce_adam(AgentCtx C, StepScalars S, CommView V, int parity, unsigned epoch, int param_blocks,
                                                           long long* __restrict__ g_nodes, float* __restrict__ g_td, int want_gather, TcPackOut P) {
+  pdl_enter();
   __shared__ int s_ok;
   unsigned* my_flags = reinterpret_cast<unsigned*>(V.base[V.rank]);
   if (threadIdx.x == 0) s_ok = 1;

@@ -89,6 +89,13 @@ __device__ __forceinline__ void agent_barrier(unsigned* ctr, unsigned target) {
   __syncthreads();
 }
 
+// first statement of every kernel launched through launch_pdl(): let the next launch be scheduled early, then wait until
+// the preceding grid has completed and its writes are visible (no-ops for ordinary launches)
+__device__ __forceinline__ void pdl_enter() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 __device__ __forceinline__ unsigned long long global_timer_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));

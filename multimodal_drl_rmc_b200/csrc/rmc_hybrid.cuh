@@ -3,7 +3,8 @@
 //     state[284] = macro[14] | grid[2][27][5]
 //     grid -> Conv(2->32, 3x3, s(1,1), p1) -> act -> Conv(32->64, s(2,1)) -> act -> Conv(64->64, s(2,2)) -> act -> flatten[1344]
 //     cat(flatten, macro)[1358] -> Linear(512) -> act -> Linear(256) -> act -> {fc_val[1], fc_adv[A]} | fc_out[A]
-// Exact fp32 path (fp32 operands, fmaf accumulation): first correct form, one kernel per layer and direction.
+// Exact fp32 path (fp32 operands, fmaf accumulation), one kernel per layer and direction; the GEMM-shaped pieces
+// (dense layers and the convolutions as implicit GEMMs) share one tiled kernel template.
 // Parameters live in ONE flat blob in torch state_dict() order (conv weights [oc][ic][3][3], linear weights
 // [out][in]), so set/get_params are plain copies and the Adam kernel walks the blob linearly.
 // Activations of a pass live in a per-row scratch record (HybNet::rec floats): conv outputs | features (last conv
@@ -43,6 +44,7 @@ __device__ __forceinline__ const float* hyb_src_row(const HybSrc& s, long long r
 // output channels of one output pixel (every input value fetched feeds 4 FMAs; weights are warp-broadcast L1 reads) and
 // a CTA owns a slice of 256 items, so even a 32-row batch spreads over > 148 CTAs.
 __global__ void __launch_bounds__(256) k_hyb_conv_fwd(HybNet N, int li, const float* __restrict__ P, HybSrc src, float* __restrict__ rec_base) {
+  pdl_enter();
   extern __shared__ float s_in[];
   const HybConv c = N.conv[li];
   const long long r = blockIdx.x;
@@ -90,6 +92,7 @@ __global__ void __launch_bounds__(256) k_hyb_conv_fwd(HybNet N, int li, const fl
 
 // features = [flattened last conv output | macro]: the macro part of every pass row
 __global__ void k_hyb_copy_macro(HybNet N, HybSrc src, float* __restrict__ rec_base, long long R) {
+  pdl_enter();
   const long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (t >= R * N.macro_len) return;
   const long long r = t / N.macro_len;
@@ -175,6 +178,7 @@ __device__ __forceinline__ float hyb_epilogue(const HybGemm& G, float v, int n, 
 }
 template <int MODE>
 __global__ void __launch_bounds__(256) k_hyb_gemm(HybGemm G) {
+  pdl_enter();
   __shared__ float sA[16][65], sB[16][65];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
@@ -248,6 +252,7 @@ __global__ void __launch_bounds__(256) k_hyb_gemm(HybGemm G) {
 // split-K second pass: C = epilogue(sum_z ws[z]) in split order (deterministic)
 template <int MODE>
 __global__ void __launch_bounds__(256) k_hyb_splitk_reduce(HybGemm G) {
+  pdl_enter();
   const long long t = blockIdx.x * 256ll + threadIdx.x;
   if (t >= static_cast<long long>(G.M) * G.N) return;
   const int m = static_cast<int>(t / G.N), n = static_cast<int>(t - static_cast<long long>(m) * G.N);
@@ -259,6 +264,7 @@ __global__ void __launch_bounds__(256) k_hyb_splitk_reduce(HybGemm G) {
 
 // per-channel sums of the output deltas of a conv layer: db[oc] = sum_{row, pix} dz   (one CTA per channel, fixed-order tree)
 __global__ void __launch_bounds__(256) k_hyb_conv_bias_grad(const float* __restrict__ dz, long long dz_stride, int npix, long long B, float* __restrict__ out) {
+  pdl_enter();
   __shared__ float s_red[256];
   const int oc = blockIdx.x;
   float s = 0.f;
@@ -277,6 +283,7 @@ __global__ void __launch_bounds__(256) k_hyb_conv_bias_grad(const float* __restr
 
 // column sums: out[n] = sum_m X[m*ld + n]   (bias gradients of the dense layers), one thread per column, fixed order
 __global__ void k_hyb_colsum(const float* __restrict__ X, long long ld, int M, int N, float* __restrict__ out) {
+  pdl_enter();
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   float s = 0.f;
@@ -287,6 +294,7 @@ __global__ void k_hyb_colsum(const float* __restrict__ X, long long ld, int M, i
 // ---------------------------------------------------------------------------------------------- heads
 // warp per row: heads[a] = <h, W_a> + b_a  (fc_val / fc_adv or fc_out; network.py:54-63,81-96)
 __global__ void __launch_bounds__(256) k_hyb_heads_fwd(HybNet N, const float* __restrict__ P, float* __restrict__ rec_base, long long R) {
+  pdl_enter();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long r = blockIdx.x * 8ll + warp;
   if (r >= R) return;
@@ -324,6 +332,7 @@ __device__ __forceinline__ void hyb_heads_to_q(const float* h, int A, int duelin
 // online record r < B: s' row; r >= B: s row.  Head deltas go to the delta record of sample i.
 __global__ void __launch_bounds__(128) k_hyb_td(AgentCtx C, StepScalars S, HybNet N, const float* __restrict__ rec_on, const float* __restrict__ rec_tg,
                                                 float* __restrict__ drec) {
+  pdl_enter();
   __shared__ float s_part[4];
   const long long i = blockIdx.x * 128ll + threadIdx.x;
   const bool per = S.prioritized != 0;
@@ -393,6 +402,7 @@ __global__ void __launch_bounds__(128) k_hyb_td(AgentCtx C, StepScalars S, HybNe
 
 // heads backward: d(last)[i][k] = (sum_a dh[i][a] W_a[k]) * act'(h[i][k]);  dW_a[k] = sum_i dh[i][a] h[i][k];  db_a = sum_i dh[i][a]
 __global__ void __launch_bounds__(256) k_hyb_heads_dgrad(HybNet N, const float* __restrict__ P, const float* __restrict__ rec_s, float* __restrict__ drec, long long B) {
+  pdl_enter();
   const long long t = blockIdx.x * 256ll + threadIdx.x;
   if (t >= B * N.last_len) return;
   const long long i = t / N.last_len;
@@ -406,6 +416,7 @@ __global__ void __launch_bounds__(256) k_hyb_heads_dgrad(HybNet N, const float* 
   drec[i * N.rec + N.last_off + k] = act_bwd(s, rec_s[i * N.rec + N.last_off + k], N.act);
 }
 __global__ void __launch_bounds__(256) k_hyb_heads_wgrad(HybNet N, const float* __restrict__ rec_s, const float* __restrict__ drec, long long B, float* __restrict__ grads) {
+  pdl_enter();
   const int t = blockIdx.x * 256 + threadIdx.x;
   const int a = t / N.last_len, k = t - a * N.last_len;
   if (a >= N.NH) return;
@@ -420,101 +431,9 @@ __global__ void __launch_bounds__(256) k_hyb_heads_wgrad(HybNet N, const float* 
   if (k == 0) grads[N.dueling ? (a == 0 ? N.hb_off[0] : N.hb_off[1] + a - 1) : N.hb_off[0] + a] = sb;
 }
 
-// ---------------------------------------------------------------------------------------------- convolution backward
-// data gradient (gather form): one CTA per row, the layer's output deltas staged in shared memory; a thread owns 4 input
-// channels of one input pixel.  Result is multiplied by act'(input activation): it is the delta of the layer below.
-__global__ void __launch_bounds__(256) k_hyb_conv_dgrad(HybNet N, int li, const float* __restrict__ P, const float* __restrict__ rec_s, float* __restrict__ drec_base) {
-  extern __shared__ float s_dz[];
-  const HybConv c = N.conv[li];
-  const long long r = blockIdx.x;
-  float* drec = drec_base + r * N.rec;
-  const float* rec = rec_s + r * N.rec;
-  const int npix = c.oh * c.ow, n_out = c.oc * npix;
-  for (int t = threadIdx.x; t < n_out; t += blockDim.x) s_dz[t] = drec[c.out_off + t];
-  __syncthreads();
-  const int ipix = c.ih * c.iw, ng = c.ic >> 2;
-  const float* W = P + c.w_off;
-  for (int t = blockIdx.y * blockDim.x + threadIdx.x; t < ng * ipix; t += gridDim.y * blockDim.x) {
-    const int g = t / ipix, pix = t - g * ipix;
-    const int iy = pix / c.iw, ix = pix - iy * c.iw;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll
-    for (int ky = 0; ky < 3; ++ky) {
-      const int ny = iy + 1 - ky;
-      if (ny < 0 || ny % c.sh != 0) continue;
-      const int oy = ny / c.sh;
-      if (oy >= c.oh) continue;
-#pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        const int nx = ix + 1 - kx;
-        if (nx < 0 || nx % c.sw != 0) continue;
-        const int ox = nx / c.sw;
-        if (ox >= c.ow) continue;
-        const float* w = W + (4 * g) * 9 + ky * 3 + kx;
-        for (int oc = 0; oc < c.oc; ++oc) {
-          const float d = s_dz[oc * npix + oy * c.ow + ox];
-          const float* wo = w + oc * c.ic * 9;
-          a0 = fmaf(d, __ldg(wo), a0);
-          a1 = fmaf(d, __ldg(wo + 9), a1);
-          a2 = fmaf(d, __ldg(wo + 18), a2);
-          a3 = fmaf(d, __ldg(wo + 27), a3);
-        }
-      }
-    }
-    const int o = c.in_off + (4 * g) * ipix + pix;
-    drec[o] = act_bwd(a0, rec[o], N.act);
-    drec[o + ipix] = act_bwd(a1, rec[o + ipix], N.act);
-    drec[o + 2 * ipix] = act_bwd(a2, rec[o + 2 * ipix], N.act);
-    drec[o + 3 * ipix] = act_bwd(a3, rec[o + 3 * ipix], N.act);
-  }
-}
-
-// weight gradient: one CTA (64 threads) per (oc, ic); the threads split the (row, pixel) range, keep 9 partial sums each
-// and combine them with a fixed-order tree; the ic == 0 CTA also produces the bias gradient.
-__global__ void __launch_bounds__(64) k_hyb_conv_wgrad(HybNet N, int li, HybSrc src, const float* __restrict__ rec_s, const float* __restrict__ drec_base,
-                                                       long long B, float* __restrict__ grads) {
-  __shared__ float s_red[10][64];
-  const HybConv c = N.conv[li];
-  const int oc = blockIdx.x / c.ic, ic = blockIdx.x - oc * c.ic;
-  const int npix = c.oh * c.ow;
-  float acc[9], accb = 0.f;
-#pragma unroll
-  for (int q = 0; q < 9; ++q) acc[q] = 0.f;
-  for (long long t = threadIdx.x; t < B * npix; t += 64) {
-    const long long r = t / npix;
-    const int pix = static_cast<int>(t - r * npix);
-    const int oy = pix / c.ow, ox = pix - oy * c.ow;
-    const float d = drec_base[r * N.rec + c.out_off + oc * npix + pix];
-    const float* in = (li == 0) ? hyb_src_row(src, B + r) + N.macro_len : rec_s + r * N.rec + c.in_off;   // s rows: second half of the online pass
-    in += ic * c.ih * c.iw;
-    accb += d;
-#pragma unroll
-    for (int ky = 0; ky < 3; ++ky) {
-      const int iy = oy * c.sh + ky - 1;
-#pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        const int ix = ox * c.sw + kx - 1;
-        const bool ok = iy >= 0 && iy < c.ih && ix >= 0 && ix < c.iw;
-        acc[ky * 3 + kx] = fmaf(d, ok ? __ldg(in + iy * c.iw + ix) : 0.f, acc[ky * 3 + kx]);
-      }
-    }
-  }
-#pragma unroll
-  for (int q = 0; q < 9; ++q) s_red[q][threadIdx.x] = acc[q];
-  s_red[9][threadIdx.x] = accb;
-  __syncthreads();
-  for (int w = 32; w > 0; w >>= 1) {
-    if (threadIdx.x < w)
-#pragma unroll
-      for (int q = 0; q < 10; ++q) s_red[q][threadIdx.x] += s_red[q][threadIdx.x + w];
-    __syncthreads();
-  }
-  if (threadIdx.x < 9) grads[c.w_off + (oc * c.ic + ic) * 9 + threadIdx.x] = s_red[threadIdx.x][0];
-  if (threadIdx.x == 9 && ic == 0) grads[c.b_off + oc] = s_red[9][0];
-}
-
 // Adam (+ Polyak / hard sync) over the flat blob, and the loss of the step
 __global__ void __launch_bounds__(256) k_hyb_adam(AgentCtx C, StepScalars S, int total, int n_loss_parts, int write_loss) {
+  pdl_enter();
   const int pi = blockIdx.x * 256 + threadIdx.x;
   if (pi < total) {
     const float g = (S.grads_in != nullptr) ? __ldcg(S.grads_in + pi) : __ldcg(C.grads + pi);
@@ -535,6 +454,7 @@ __global__ void __launch_bounds__(256) k_hyb_adam(AgentCtx C, StepScalars S, int
 
 // inference outputs from the head records: mode 0 greedy actions, 1 Q values [n][A], 2 raw heads [n][NH]
 __global__ void k_hyb_outputs(HybNet N, const float* __restrict__ rec_base, long long n, long long* __restrict__ actions, float* __restrict__ q_out, int mode) {
+  pdl_enter();
   const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (i >= n) return;
   float h[kQLD], q[kQLD];

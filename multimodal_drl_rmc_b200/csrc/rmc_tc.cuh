@@ -39,6 +39,7 @@ __host__ __device__ __forceinline__ int tc_off(int r, int k, int K) {
 
 // fp32 device-layout parameter blob -> packed bf16 operands + fp32 biases
 __global__ void k_tc_pack(const float* __restrict__ blob, NetLayout L, unsigned char* __restrict__ out) {
+  pdl_enter();
   __nv_bfloat16* w = reinterpret_cast<__nv_bfloat16*>(out);
   float* bias = reinterpret_cast<float*>(out + kTcBf16Elems * 2);
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -397,6 +398,7 @@ struct TcFwdJob {
 };
 struct TcFwdJobs { TcFwdJob j[3]; };
 __global__ void __launch_bounds__(kTcFwdThreads, 1) k_tc_fwd3(TcFwdJobs J, int D, int A, int NH, int dueling, const float* __restrict__ rows, long long n) {
+  pdl_enter();
   const int b = blockIdx.x;
   const int k = (b >= J.j[2].cta_begin) ? 2 : (b >= J.j[1].cta_begin) ? 1 : 0;
   const TcFwdJob& job = J.j[k];

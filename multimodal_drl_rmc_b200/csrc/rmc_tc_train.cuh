@@ -24,6 +24,7 @@ constexpr int kTcBwdElems = kTcBwdOffW2 + kH1 * kH2;
 constexpr int kTcBwdBytes = kTcBwdElems * 2;          // 69,632 B
 
 __global__ void k_tc_pack_bwd(const float* __restrict__ blob, NetLayout L, __nv_bfloat16* __restrict__ out) {
+  pdl_enter();
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t < kH2 * kTcNH) {                                 // (j, a) -> Wh[a][j]
     const int j = t / kTcNH, a = t % kTcNH;
@@ -108,6 +109,7 @@ __device__ __forceinline__ int argmax_first16(const float (&q)[16], int A) {
 
 constexpr int kTdThreads = 128;
 __global__ void __launch_bounds__(kTdThreads) k_tc_td(AgentCtx C, StepScalars S, TcTrainBufs T) {
+  pdl_enter();
   __shared__ float s_part[kTdThreads / 32];
   const long long i = blockIdx.x * static_cast<long long>(kTdThreads) + threadIdx.x;
   const NetLayout& L = C.L;
@@ -239,6 +241,7 @@ __device__ __forceinline__ void bf_mask_epilogue(uint32_t tS, int q, int row, in
 }
 
 __global__ void __launch_bounds__(kThreads, 1) k_tc_bwd_fused(AgentCtx C, const unsigned char* __restrict__ packed_bwd, long long n, TcTrainBufs T) {
+  pdl_enter();
   extern __shared__ __align__(128) unsigned char tsm[];
   const __nv_bfloat16* sW = reinterpret_cast<const __nv_bfloat16*>(tsm);          // Wh^T | W2 (K-major, packed by k_tc_pack_bwd)
   __nv_bfloat16* sDH = reinterpret_cast<__nv_bfloat16*>(tsm + kBfOffDH);
@@ -433,6 +436,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_bwd_fused(AgentCtx C, const 
 // A block owns 128 consecutive parameters: warp w sums partials w, w+8, ... with float4 loads (512 contiguous bytes per
 // warp load), the eight warp sums are combined in warp order through shared memory.
 __global__ void __launch_bounds__(256) k_tc_reduce_adam(AgentCtx C, StepScalars S, TcTrainBufs T, int n_loss_parts, TcPackOut P) {
+  pdl_enter();
   __shared__ float4 s_sum[8][32];
   const NetLayout& L = C.L;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

@@ -441,6 +441,7 @@ __device__ void tree_update_team(const ReplayDev& R, const long long* __restrict
 __global__ void __launch_bounds__(kThreads) k_tree_update_small(ReplayDev R, const long long* nodes, const float* pri_in,
                                                                 const float* abs_td, float* pri_out, long long n,
                                                                 float eps, float alpha, float pmax) {
+  pdl_enter();
   const float* pri = pri_in;
   if (abs_td != nullptr) {
     for (long long i = threadIdx.x; i < n; i += blockDim.x) pri_out[i] = td_to_priority(abs_td[i], eps, alpha, pmax);
@@ -454,16 +455,19 @@ __global__ void __launch_bounds__(kThreads) k_tree_update_small(ReplayDev R, con
 
 // grid-wide variants for large batches
 __global__ void k_td_to_pri(const float* abs_td, float* pri, long long n, float eps, float alpha, float pmax) {
+  pdl_enter();
   const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (i < n) pri[i] = td_to_priority(abs_td[i], eps, alpha, pmax);
 }
 __global__ void k_tree_stamp(ReplayDev R, const long long* nodes, long long n) {
+  pdl_enter();
   const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (i < n) atomicMax(R.stamps + (nodes[i] - (R.cap - 1)), static_cast<int>(i + 1));
 }
 // Leaf stores + float64 reductions on the ancestors at heap index >= first_fixed only (the contended top of the
 // tree is rebuilt afterwards by k_tree_rebuild_top; sums of f32-exact values are exact in any order, SURVEY finding 6).
 __global__ void k_tree_apply(ReplayDev R, const long long* nodes, const float* pri, long long n, long long first_fixed) {
+  pdl_enter();
   const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (i < n) {
     const long long leaf = nodes[i];
@@ -477,6 +481,7 @@ __global__ void k_tree_apply(ReplayDev R, const long long* nodes, const float* p
 // ONE CTA: nodes [0, F) rebuilt bottom-up in shared memory from nodes [F, 2F+1)  (F = 2^L - 1 <= kTopLargeMax)
 constexpr int kTopLargeMax = 2047;
 __global__ void __launch_bounds__(1024) k_tree_rebuild_top(ReplayDev R, int F) {
+  pdl_enter();
   __shared__ double s_buf[2 * kTopLargeMax + 1];
   const int tid = threadIdx.x, nt = blockDim.x;
   for (int k = F + tid; k < 2 * F + 1; k += nt) s_buf[k] = __ldcg(R.tree + k);
@@ -505,6 +510,7 @@ __device__ __forceinline__ void ext_warp_merge(ExtTuple& a) {
 }
 constexpr int kExtBlocks = 592;
 __global__ void __launch_bounds__(256) k_extremes_scan(ReplayDev R, ExtTuple* parts, unsigned* arrive) {
+  pdl_enter();
   __shared__ ExtTuple s_w[8];
   __shared__ bool s_last;
   const long long size = R.st->size;
@@ -706,6 +712,7 @@ __global__ void __launch_bounds__(kThreads) k_per_sample(ReplayDev R, long long 
                                                          double beta, const double* u, unsigned long long seed,
                                                          unsigned long long counter, unsigned agent, long long* out_nodes,
                                                          float* out_w, float* out_rows, double* out_leaf_p) {
+  pdl_enter();
   __shared__ double s_max_w;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long i = blockIdx.x * static_cast<long long>(kWarps) + warp;
@@ -742,6 +749,7 @@ __global__ void __launch_bounds__(kLaneThreads) k_per_sample_lane(ReplayDev R, l
                                                               unsigned long long counter, unsigned agent, long long* __restrict__ out_nodes,
                                                               float* __restrict__ out_w, float* __restrict__ out_rows,
                                                               double* __restrict__ out_leaf_p) {
+  pdl_enter();
   __shared__ double s_max_w;
   const int lane = threadIdx.x & 31;
   const long long i = blockIdx.x * static_cast<long long>(kLaneThreads) + threadIdx.x;
@@ -807,6 +815,7 @@ __device__ __forceinline__ long long deque_pos_to_slot(long long pos, long long 
 __global__ void __launch_bounds__(kThreads) k_uniform_sample(ReplayDev R, long long B, long long shard_off, const long long* idx,
                                                              unsigned long long seed, unsigned long long counter,
                                                              unsigned agent, long long* out_slots, float* out_rows) {
+  pdl_enter();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long i = blockIdx.x * static_cast<long long>(kWarps) + warp;
   if (i >= B) return;
