@@ -131,7 +131,9 @@ struct rmc_learner {
   // hybrid CNN+MLP network (rmc_hybrid.cuh): per-row activation / delta records
   bool hybrid = false;
   HybNet H{};
-  float *rec_on = nullptr, *rec_tg = nullptr, *drec = nullptr, *hyb_ws = nullptr;
+  float *rec_on = nullptr, *rec_tg = nullptr, *drec = nullptr, *hyb_ws = nullptr, *hyb_ws2 = nullptr;
+  cudaStream_t hyb_side = nullptr;          // second stream: target-network pass and the weight-gradient kernels
+  cudaEvent_t hyb_ev[16] = {};
   // act staging
   float* act_pin_obs = nullptr; long long* act_pin_out = nullptr; float* act_dev_obs = nullptr; long long* act_dev_out = nullptr;
   long long act_cap = 0;
@@ -630,6 +632,7 @@ extern "C" int32_t rmc_learner_destroy(rmc_learner_t* l) {
   if (l->act_pin_obs) cudaFreeHost(l->act_pin_obs);
   if (l->act_pin_out) cudaFreeHost(l->act_pin_out);
   if (l->host_loss) cudaFreeHost(const_cast<float*>(l->host_loss));
+  if (l->hyb_side) { cudaStreamDestroy(l->hyb_side); for (auto& ev : l->hyb_ev) if (ev) cudaEventDestroy(ev); }
   cudaFree(l->act_dev_obs);
   cudaFree(l->act_dev_out);
   delete l;
@@ -993,6 +996,9 @@ extern "C" int32_t rmc_learner_create_hybrid(rmc_learner_t** out, const rmc_hybr
   if ((e = owned_alloc(l, &l->rec_tg, B * N.rec))) return e;
   if ((e = owned_alloc(l, &l->drec, B * N.rec))) return e;
   if ((e = owned_alloc(l, &l->hyb_ws, static_cast<size_t>(kHybWsFloats)))) return e;
+  if ((e = owned_alloc(l, &l->hyb_ws2, static_cast<size_t>(kHybWsFloats)))) return e;
+  RMC_CUDA(cudaStreamCreateWithFlags(&l->hyb_side, cudaStreamNonBlocking));
+  for (auto& ev : l->hyb_ev) RMC_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   {
     float* hp = nullptr;
     float* dp = nullptr;
@@ -1021,7 +1027,7 @@ static int32_t hyb_gemm_mode(rmc_learner* l, HybGemm G, cudaStream_t st) {
     splits = static_cast<int>(std::min<long long>(16, std::min<long long>((148 + tiles - 1) / tiles, G.K / 64)));
     while (splits > 1 && static_cast<long long>(splits) * G.M * G.N > kHybWsFloats) --splits;
   }
-  G.splits = splits; G.ws = l->hyb_ws;
+  G.splits = splits; G.ws = (st == l->hyb_side) ? l->hyb_ws2 : l->hyb_ws;        // one split-K workspace per stream
   G.k_chunk = ((G.K + splits - 1) / splits + 15) / 16 * 16;
   if (splits > 1) G.splits = (G.K + G.k_chunk - 1) / G.k_chunk;
   RMC_CUDA(launch_pdl(k_hyb_gemm<MODE>, dim3(blocks_for(G.N, 64), blocks_for(G.M, 64), static_cast<unsigned>(G.splits)), dim3(256), 0, st, G));
@@ -1088,18 +1094,36 @@ static int32_t hybrid_step(rmc_learner* l, rmc_replay* r, const rmc_step_args_t*
   }
   const HybSrc src_on{C.X, l->rf, B, N.D, 0};            // online pass: rows [0,B) = s', rows [B,2B) = s
   const unsigned td_blocks = blocks_for(B, 128);
+  // Two streams: the target-network pass runs beside the online pass, and the weight-gradient kernels of a layer beside
+  // the data-gradient chain below it (both need only that layer's deltas).  The kernels of this network are small, so the
+  // overlap roughly halves the step.  RMC_HYB_STREAMS=0 keeps everything on the caller's stream.
+  static const bool two_streams = [] { const char* e = std::getenv("RMC_HYB_STREAMS"); return !(e && e[0] == '0'); }();
+  cudaStream_t side = two_streams ? l->hyb_side : st;
+  int ev_next = 0;
+  auto hand_over = [&](cudaStream_t from, cudaStream_t to) -> int32_t {     // `to` continues after everything queued on `from`
+    if (from == to) return RMC_OK;
+    cudaEvent_t ev = l->hyb_ev[ev_next++ & 15];
+    RMC_CUDA(cudaEventRecord(ev, from));
+    RMC_CUDA(cudaStreamWaitEvent(to, ev, 0));
+    return RMC_OK;
+  };
   if (ph & RMC_PH_FORWARD) {
     const HybSrc src_tg{C.X, l->rf, B, N.D, N.D};
+    if (int32_t e = hand_over(st, side)) return e;
+    if (int32_t e = hybrid_forward(l, C.target, src_tg, l->rec_tg, B, side)) return e;
     if (int32_t e = hybrid_forward(l, C.online, src_on, l->rec_on, 2 * B, st)) return e;
-    if (int32_t e = hybrid_forward(l, C.target, src_tg, l->rec_tg, B, st)) return e;
+    if (int32_t e = hand_over(side, st)) return e;
     RMC_CUDA(launch_pdl(k_hyb_td, dim3(td_blocks), dim3(128), 0, st, C, S, N, l->rec_on, l->rec_tg, l->drec));
     RMC_KERNEL_OK();
   }
   if (ph & RMC_PH_BACKWARD) {
+    // main stream: the data-gradient chain (heads -> dense -> conv); side stream: every layer's weight / bias gradients, each
+    // released as soon as that layer's deltas exist
     const float* rec_s = l->rec_on + B * N.rec;           // records of the s rows
     RMC_CUDA(launch_pdl(k_hyb_heads_dgrad, dim3(blocks_for(B * N.last_len, 256)), dim3(256), 0, st, N, C.online, rec_s, l->drec, B));
     RMC_KERNEL_OK();
-    RMC_CUDA(launch_pdl(k_hyb_heads_wgrad, dim3(blocks_for(static_cast<long long>(N.NH) * N.last_len, 256)), dim3(256), 0, st, N, rec_s, l->drec, B, C.grads));
+    if (int32_t e = hand_over(st, side)) return e;
+    RMC_CUDA(launch_pdl(k_hyb_heads_wgrad, dim3(blocks_for(static_cast<long long>(N.NH) * N.last_len, 256)), dim3(256), 0, side, N, rec_s, l->drec, B, C.grads));
     RMC_KERNEL_OK();
     for (int i = N.n_dense - 1; i >= 0; --i) {
       const HybDense& d = N.dense[i];
@@ -1107,8 +1131,8 @@ static int32_t hybrid_step(rmc_learner* l, rmc_replay* r, const rmc_step_args_t*
       W.A = l->drec + d.out_off; W.a_sm = 1; W.a_sk = N.rec;
       W.B = rec_s + d.in_off; W.b_sk = N.rec; W.b_sn = 1;
       W.C = C.grads + d.w_off; W.c_sm = d.in; W.M = d.out; W.N = d.in; W.K = static_cast<int>(B); W.epi = 2;
-      if (int32_t e = hyb_gemm(l, W, st)) return e;
-      RMC_CUDA(launch_pdl(k_hyb_colsum, dim3(blocks_for(d.out, 128)), dim3(128), 0, st, l->drec + d.out_off, N.rec, static_cast<int>(B), d.out, C.grads + d.b_off));
+      if (int32_t e = hyb_gemm(l, W, side)) return e;
+      RMC_CUDA(launch_pdl(k_hyb_colsum, dim3(blocks_for(d.out, 128)), dim3(128), 0, side, l->drec + d.out_off, N.rec, static_cast<int>(B), d.out, C.grads + d.b_off));
       RMC_KERNEL_OK();
       HybGemm G{};                                        // dX[r][k] = (sum_n dZ[r][n] W[n][k]) * act'(X[r][k])
       G.A = l->drec + d.out_off; G.a_sm = N.rec; G.a_sk = 1;
@@ -1116,6 +1140,7 @@ static int32_t hybrid_step(rmc_learner* l, rmc_replay* r, const rmc_step_args_t*
       G.C = l->drec + d.in_off; G.c_sm = N.rec; G.H = rec_s + d.in_off; G.h_sm = N.rec;
       G.M = static_cast<int>(B); G.N = (i == 0) ? N.conv_flat : d.in; G.K = d.out; G.epi = 1; G.act = N.act;
       if (int32_t e = hyb_gemm(l, G, st)) return e;
+      if (int32_t e = hand_over(st, side)) return e;
     }
     for (int i = N.n_conv - 1; i >= 0; --i) {
       const HybConv& c = N.conv[i];
@@ -1125,8 +1150,8 @@ static int32_t hybrid_step(rmc_learner* l, rmc_replay* r, const rmc_step_args_t*
       if (i == 0) { W.img = nullptr; W.src = src_on; W.src_row0 = B; W.macro_len = N.macro_len; }
       else { W.img = rec_s + c.in_off; W.img_stride = N.rec; }
       W.C = C.grads + c.w_off; W.c_sm = c.ic * 9; W.M = c.oc; W.N = c.ic * 9; W.K = static_cast<int>(B) * npix; W.epi = 2;
-      if (int32_t e = hyb_gemm_mode<3>(l, W, st)) return e;
-      RMC_CUDA(launch_pdl(k_hyb_conv_bias_grad, dim3(static_cast<unsigned>(c.oc)), dim3(256), 0, st, l->drec + c.out_off, N.rec, npix, B, C.grads + c.b_off));
+      if (int32_t e = hyb_gemm_mode<3>(l, W, side)) return e;
+      RMC_CUDA(launch_pdl(k_hyb_conv_bias_grad, dim3(static_cast<unsigned>(c.oc)), dim3(256), 0, side, l->drec + c.out_off, N.rec, npix, B, C.grads + c.b_off));
       RMC_KERNEL_OK();
       if (i > 0) {                           // delta of the layer below: (gathered dZ . W) * act'(input activation)
         HybGemm G{};
@@ -1135,8 +1160,10 @@ static int32_t hybrid_step(rmc_learner* l, rmc_replay* r, const rmc_step_args_t*
         G.C = l->drec + c.in_off; G.c_sm = N.rec; G.H = rec_s + c.in_off;
         G.M = static_cast<int>(B) * c.ih * c.iw; G.N = c.ic; G.K = c.oc * 9; G.epi = 1; G.act = N.act;
         if (int32_t e = hyb_gemm_mode<2>(l, G, st)) return e;
+        if (int32_t e = hand_over(st, side)) return e;
       }
     }
+    if (int32_t e = hand_over(side, st)) return e;         // every gradient is in place before Adam
   }
   if (ph & (RMC_PH_FORWARD | RMC_PH_ADAM | RMC_PH_POLYAK | RMC_PH_HARDSYNC)) {
     l->epoch = (l->epoch >= 0x7fffffffu) ? 1u : l->epoch + 1u;
