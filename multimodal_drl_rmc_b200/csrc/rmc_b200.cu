@@ -1024,8 +1024,8 @@ static int32_t hyb_gemm_mode(rmc_learner* l, HybGemm G, cudaStream_t st) {
   const long long tiles = static_cast<long long>(blocks_for(G.N, 64)) * blocks_for(G.M, 64);
   int splits = 1;
   if (tiles < 96 && G.K >= 128) {
-    splits = static_cast<int>(std::min<long long>(16, std::min<long long>((148 + tiles - 1) / tiles, G.K / 64)));
-    while (splits > 1 && static_cast<long long>(splits) * G.M * G.N > kHybWsFloats) --splits;
+    splits = static_cast<int>(std::min<long long>(64, std::min<long long>((2 * 148 + tiles - 1) / tiles, G.K / 64)));
+    while (splits > 1 && static_cast<long long>(splits) * G.M * G.N > kHybWsFloats - 16 * 1024) --splits;
   }
   G.splits = splits; G.ws = (st == l->hyb_side) ? l->hyb_ws2 : l->hyb_ws;        // one split-K workspace per stream
   G.k_chunk = ((G.K + splits - 1) / splits + 15) / 16 * 16;
@@ -1151,8 +1151,13 @@ static int32_t hybrid_step(rmc_learner* l, rmc_replay* r, const rmc_step_args_t*
       else { W.img = rec_s + c.in_off; W.img_stride = N.rec; }
       W.C = C.grads + c.w_off; W.c_sm = c.ic * 9; W.M = c.oc; W.N = c.ic * 9; W.K = static_cast<int>(B) * npix; W.epi = 2;
       if (int32_t e = hyb_gemm_mode<3>(l, W, side)) return e;
-      RMC_CUDA(launch_pdl(k_hyb_conv_bias_grad, dim3(static_cast<unsigned>(c.oc)), dim3(256), 0, side, l->drec + c.out_off, N.rec, npix, B, C.grads + c.b_off));
-      RMC_KERNEL_OK();
+      {   // bias gradient in two fixed-order stages: (oc, 16 row slices) partial sums, then one thread per channel
+        float* part = ((side == l->hyb_side) ? l->hyb_ws2 : l->hyb_ws) + kHybWsFloats - 16 * 1024;     // tail of the stream's workspace
+        RMC_CUDA(launch_pdl(k_hyb_conv_bias_grad, dim3(static_cast<unsigned>(c.oc), 16, 1), dim3(256), 0, side, l->drec + c.out_off, N.rec, npix, B, part));
+        RMC_KERNEL_OK();
+        RMC_CUDA(launch_pdl(k_hyb_colsum, dim3(blocks_for(c.oc, 128)), dim3(128), 0, side, static_cast<const float*>(part), static_cast<long long>(c.oc), 16, c.oc, C.grads + c.b_off));
+        RMC_KERNEL_OK();
+      }
       if (i > 0) {                           // delta of the layer below: (gathered dZ . W) * act'(input activation)
         HybGemm G{};
         G.cv = c; G.dz = l->drec + c.out_off; G.dz_stride = N.rec;

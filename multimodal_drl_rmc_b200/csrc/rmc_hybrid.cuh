@@ -262,13 +262,15 @@ __global__ void __launch_bounds__(256) k_hyb_splitk_reduce(HybGemm G) {
   G.C[ci] = hyb_epilogue(G, v, n, ci);
 }
 
-// per-channel sums of the output deltas of a conv layer: db[oc] = sum_{row, pix} dz   (one CTA per channel, fixed-order tree)
-__global__ void __launch_bounds__(256) k_hyb_conv_bias_grad(const float* __restrict__ dz, long long dz_stride, int npix, long long B, float* __restrict__ out) {
+// per-channel sums of the output deltas of a conv layer, stage 1: CTA (oc, slice) sums its slice of the rows with a
+// fixed-order tree -> part[slice][oc]; stage 2 is k_hyb_colsum over the slices
+__global__ void __launch_bounds__(256) k_hyb_conv_bias_grad(const float* __restrict__ dz, long long dz_stride, int npix, long long B, float* __restrict__ part) {
   pdl_enter();
   __shared__ float s_red[256];
   const int oc = blockIdx.x;
+  const long long rows_per = (B + gridDim.y - 1) / gridDim.y, r_lo = blockIdx.y * rows_per, r_hi = min(B, r_lo + rows_per);
   float s = 0.f;
-  for (long long t = threadIdx.x; t < B * npix; t += 256) {
+  for (long long t = r_lo * npix + threadIdx.x; t < r_hi * npix; t += 256) {
     const long long r = t / npix;
     s += __ldg(dz + r * dz_stride + oc * npix + (t - r * npix));
   }
@@ -278,7 +280,7 @@ __global__ void __launch_bounds__(256) k_hyb_conv_bias_grad(const float* __restr
     if (threadIdx.x < w) s_red[threadIdx.x] += s_red[threadIdx.x + w];
     __syncthreads();
   }
-  if (threadIdx.x == 0) out[oc] = s_red[0];
+  if (threadIdx.x == 0) part[blockIdx.y * gridDim.x + oc] = s_red[0];
 }
 
 // column sums: out[n] = sum_m X[m*ld + n]   (bias gradients of the dense layers), one thread per column, fixed order
