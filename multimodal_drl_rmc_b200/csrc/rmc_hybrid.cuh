@@ -179,8 +179,8 @@ __device__ __forceinline__ float hyb_epilogue(const HybGemm& G, float v, int n, 
 template <int MODE>
 __global__ void __launch_bounds__(256) k_hyb_gemm(HybGemm G) {
   pdl_enter();
-  __shared__ float sA[16][65], sB[16][65];
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  __shared__ __align__(16) float sA[16][68], sB[16][68];      // rows padded to 68 floats: 16-byte aligned 4-wide fragments
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;   // thread tile: rows 4*ty.., columns 4*tx..
   const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
   float acc[4][4];
 #pragma unroll
@@ -221,9 +221,8 @@ __global__ void __launch_bounds__(256) k_hyb_gemm(HybGemm G) {
     if (k0 + 16 < k_hi) fetch(k0 + 16, k_hi);
 #pragma unroll
     for (int kk = 0; kk < 16; ++kk) {
-      float a[4], b[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) { a[i] = sA[kk][ty + 16 * i]; b[i] = sB[kk][tx + 16 * i]; }
+      const float4 av = *reinterpret_cast<const float4*>(&sA[kk][4 * ty]), bv = *reinterpret_cast<const float4*>(&sB[kk][4 * tx]);
+      const float a[4] = {av.x, av.y, av.z, av.w}, b[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -233,11 +232,11 @@ __global__ void __launch_bounds__(256) k_hyb_gemm(HybGemm G) {
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const int m = m0 + ty + 16 * i;
+    const int m = m0 + 4 * ty + i;
     if (m >= G.M) continue;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int n = n0 + tx + 16 * j;
+      const int n = n0 + 4 * tx + j;
       if (n >= G.N) continue;
       if (G.splits > 1) {
         G.ws[(static_cast<long long>(blockIdx.z) * G.M + m) * G.N + n] = acc[i][j];
