@@ -61,3 +61,39 @@ def test_hybrid_rejects_modes_not_built():
     agent.learn_precision = "bf16"
     with pytest.raises(Exception):
         agent.learn()
+
+
+def test_hybrid_sidecar_resume_diagnostics_and_epsilon_greedy(tmp_path):
+    """The learner-state side-car, the on-device diagnostics (8f-4) and choose_actions work unchanged for
+    the hybrid network; the step is deterministic (two identically seeded agents stay bit-identical)."""
+    import random
+    _, a = PU.make_pair("PerDuelingDoubleDQNAgent", D, 16, 128, 128, seed=12, activation="elu", body="hybrid")
+    _, b = PU.make_pair("PerDuelingDoubleDQNAgent", D, 16, 128, 128, seed=12, activation="elu", body="hybrid")
+    rng = np.random.default_rng(0)
+    us = [rng.random(16) for _ in range(4)]
+    for s in range(2):
+        for ag in (a, b):
+            ag.step = s
+            ag.learn(u=us[s], fuse_target_update=True)
+    np.testing.assert_array_equal(PU.flat_sd(a.online_network), PU.flat_sd(b.online_network))
+    side = str(tmp_path / "state.npz")
+    a.save_learner_state(side)
+    z = torch.zeros(b._lh.n_params)
+    for kind in (0, 1, 2, 3):
+        b._lh.set_params(kind, z)
+    b._adam_t = 0
+    b.load_learner_state(side)
+    for s in range(2, 4):
+        for ag in (a, b):
+            ag.step = s
+            ag.learn(u=us[s], fuse_target_update=True)
+    np.testing.assert_array_equal(PU.flat_sd(a.online_network), PU.flat_sd(b.online_network))
+    np.testing.assert_array_equal(PU.flat_sd(a.target_network), PU.flat_sd(b.target_network))
+    np.testing.assert_array_equal(a.replay_memory_buffer.replay_buffer.tree, b.replay_memory_buffer.replay_buffer.tree)
+    d = a.diagnostics()
+    assert np.isfinite(d["loss"]) and d["replay_size"] == 128
+    obs = np.random.default_rng(3).random((4, D), dtype=np.float32)
+    a.step = 10 ** 9                      # epsilon at its floor: mostly greedy
+    random.seed(5)
+    acts = a.choose_actions(obs)
+    assert len(acts) == 4 and all(0 <= x < 8 for x in acts)
