@@ -229,6 +229,11 @@ int32_t rmc_learner_set_hyper(rmc_learner_t* l, const rmc_hyper_t* hyper);
  * parts run (split variants for parity tests).  Outputs stay on the device; see
  * rmc_learner_read_*. */
 int32_t rmc_learner_step(rmc_learner_t* l, rmc_replay_t* r, const rmc_step_args_t* a, rmc_stream_t s);
+/* Agent.store_transitions (dqn/agent.py:80-84) of the n (<= 8) rows of this env step followed by the learner step,
+ * issued from one host call (train.py:91-101 calls them back to back): == rmc_replay_push_host + rmc_learner_step. */
+int32_t rmc_learner_step_push(rmc_learner_t* l, rmc_replay_t* r, const rmc_step_args_t* a, const float* obs_host,
+                              const int64_t* act_host, const float* rew_host, const float* done_host,
+                              const float* next_obs_host, int64_t n, rmc_stream_t s);
 
 /* Learner-step products of the last step (device pointers, valid until the next step):
  * name in {"nodes"(i64), "is_w","q_sa","y","abs_td","huber","pri","loss"(1), "q_next_tgt"(B*A),

@@ -124,6 +124,7 @@ _SIGS = {
     "rmc_learner_get_params": (_i32, [_vp, _i32, _vp, _i64, _i32, _vp]),
     "rmc_learner_set_hyper": (_i32, [_vp, C.POINTER(Hyper)]),
     "rmc_learner_step": (_i32, [_vp, _vp, C.POINTER(StepArgs), _vp]),
+    "rmc_learner_step_push": (_i32, [_vp, _vp, C.POINTER(StepArgs), _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "rmc_learner_output": (_i32, [_vp, _cp, C.POINTER(_vp), C.POINTER(_i64)]),
     "rmc_learner_loss_sync": (_i32, [_vp, C.POINTER(_f32), _vp]),
     "rmc_learner_q_values": (_i32, [_vp, _i32, _vp, _i64, _vp, _vp]),

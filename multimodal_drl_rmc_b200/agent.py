@@ -102,6 +102,8 @@ class Agent:
         self._args.batch = self._B
         self._args_ref = C.byref(self._args)
         self._step_fn = lib().rmc_learner_step
+        self._step_push_fn = lib().rmc_learner_step_push
+        self.replay_memory_buffer._ring.defer_small_pushes = True     # per-step rows ride with the next learn()
         self._learn_phases = _lib.PH_LEARN if self._PER else (_lib.PH_LEARN & ~_lib.PH_PRIORITY)
         self.sampling_seed = 0x5EED
 
@@ -193,7 +195,8 @@ class Agent:
         sampling randomness (tests).  ``fuse_target_update=True`` also performs this step's
         ``update_target_network()`` inside the same launch (call order of train.py:99-101); the
         following ``update_target_network()`` call is then skipped once."""
-        rh = self.replay_memory_buffer._ring.handle
+        ring = self.replay_memory_buffer._ring
+        rh = ring._handle
         if rh is None:
             raise RuntimeError("replay memory is empty (no transition stored yet)")
         self._learn_calls += 1
@@ -203,7 +206,11 @@ class Agent:
             phases |= self._target_phase()
             self._target_fused_for = self._learn_calls
         a, keep = self._step_args(phases, u, indices)
-        rc = self._step_fn(self._lh.handle, rh, self._args_ref, stream_ptr(self._dev_index))
+        n_new = ring.take_pending()
+        if n_new:      # this env step's rows (held back by store_transitions) and the step, one host call
+            rc = self._step_push_fn(self._lh.handle, rh, self._args_ref, *ring._small_ptrs, n_new, stream_ptr(self._dev_index))
+        else:
+            rc = self._step_fn(self._lh.handle, rh, self._args_ref, stream_ptr(self._dev_index))
         if rc:
             check(rc)
         ver = self._lh.version

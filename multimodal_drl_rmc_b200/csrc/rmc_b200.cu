@@ -1430,6 +1430,16 @@ extern "C" int32_t rmc_learner_step_sharded(rmc_learner_t* l, rmc_replay_t* r, r
   return RMC_OK;
 }
 
+// store_transitions of the trainer's per-env-step rows + the learner step, issued back to back from ONE host call
+// (train.py:91-101 calls them in this order; the step kernel then follows the push kernel by one launch latency instead
+// of a host round trip through the interpreter).
+extern "C" int32_t rmc_learner_step_push(rmc_learner_t* l, rmc_replay_t* r, const rmc_step_args_t* a, const float* obs_host, const int64_t* act_host,
+                                         const float* rew_host, const float* done_host, const float* next_obs_host, int64_t n, rmc_stream_t s) {
+  if (n > 0)
+    if (int32_t e = push_impl(r, obs_host, act_host, rew_host, done_host, next_obs_host, n, true, as_stream(s))) return e;
+  return rmc_learner_step(l, r, a, s);
+}
+
 extern "C" int32_t rmc_learner_output(rmc_learner_t* l, const char* name, void** dev_ptr, int64_t* n_elems) {
   if (!l || !name || !dev_ptr || !n_elems) return fail(RMC_ERR_ARG, "rmc_learner_output: null");
   const AgentCtx& c = l->ctx;

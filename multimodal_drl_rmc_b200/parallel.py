@@ -54,6 +54,7 @@ class AgentEnsemble:
         ``u`` / ``indices``: optional injected sampling randomness, shape [n_agents, batch]."""
         a0 = self.agents[0]
         for a in self.agents:
+            a.replay_memory_buffer._ring.flush()     # rows held back for a fused store + learn call
             a._learn_calls += 1
             a._adam_t += 1
         args = self._args

@@ -23,9 +23,35 @@ class DeviceRing:
         self.capacity = int(capacity)
         self.prioritized = bool(prioritized)
         self.device_index = device_index
-        self.handle = None
+        self._handle = None
+        self._pending = 0           # rows of the current env step held back for the fused store + learn call
+        self.defer_small_pushes = False
         self.obs_dim = None
         self.row_floats = None
+
+    # Every access to the handle from outside the fused path first delivers held-back rows, so deferral is invisible:
+    # stats, sampling, tree reads, explicit pushes ... all see the replay exactly as the reference would.
+    @property
+    def handle(self):
+        if self._pending:
+            self.flush()
+        return self._handle
+
+    @handle.setter
+    def handle(self, h):
+        self._handle = h
+
+    def flush(self):
+        n, self._pending = self._pending, 0
+        if n:
+            rc = self._push_fn(self._handle, *self._small_ptrs, n, stream_ptr(self.device_index))
+            if rc:
+                check(rc)
+
+    def take_pending(self):
+        """(n, pointers) of the held-back rows for rmc_learner_step_push; the caller delivers them."""
+        n, self._pending = self._pending, 0
+        return n
 
     def ensure(self, obs_dim: int):
         if self.handle is not None:
@@ -54,16 +80,16 @@ class DeviceRing:
 
     def __del__(self):
         try:
-            if self.handle is not None:
-                lib().rmc_replay_destroy(self.handle)
-                self.handle = None
+            if self._handle is not None:
+                lib().rmc_replay_destroy(self._handle)
+                self._handle = None
         except Exception:
             pass
 
     # -- host-buffer push (what store_transitions uses) ---------------------------------
     def push_host(self, obses, actions, rews, dones, new_obses):
         n = len(actions)
-        if n <= 8 and self.handle is not None:
+        if n <= 8 and self.handle is not None:      # (the handle access delivers rows held back earlier)
             # per-env-step push: copy into preallocated scratch arrays whose addresses are cached
             b = self._small
             b[0][:n] = obses
@@ -71,7 +97,10 @@ class DeviceRing:
             b[2][:n] = rews
             b[3][:n] = dones
             b[4][:n] = new_obses
-            rc = self._push_fn(self.handle, *self._small_ptrs, n, stream_ptr(self.device_index))
+            if self.defer_small_pushes:             # the Agent's next learn() carries them (one host call for store + learn)
+                self._pending = n
+                return
+            rc = self._push_fn(self._handle, *self._small_ptrs, n, stream_ptr(self.device_index))
             if rc:
                 check(rc)
             return
