@@ -260,6 +260,11 @@ int32_t rmc_learner_heads_tc(rmc_learner_t* l, const float* obs_dev, int64_t n, 
 /* same with host buffers (H2D + kernel + D2H, synchronises): what Agent.choose_actions calls. */
 int32_t rmc_learner_act_host_sync(rmc_learner_t* l, const float* obs_host, int64_t n, int64_t* actions_host,
                                   rmc_stream_t s);
+/* Agent.choose_actions (dqn/agent.py:92-99) in one call for vectorised envs: greedy act, then row i explores with
+ * probability epsilon (uniform action) from Philox(seed, counter, i) on the device.  Same distribution as the reference,
+ * not the same random stream (the Python mirror's default keeps the reference's host RNG stream). */
+int32_t rmc_learner_act_eps_host_sync(rmc_learner_t* l, const float* obs_host, int64_t n, int64_t* actions_host,
+                                      float epsilon, uint64_t seed, uint64_t counter, rmc_stream_t s);
 
 /* Diagnostics (not a reference interface): per-CTA phase timestamps (%globaltimer, ns) of the last
  * rmc_learner_step: out_host[cta*16 + k], k = 0 start, 1 sampled, 2 target weights landed,

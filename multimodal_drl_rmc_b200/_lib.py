@@ -133,6 +133,7 @@ _SIGS = {
     "rmc_learner_act_tc": (_i32, [_vp, _vp, _i64, _vp, _vp]),
     "rmc_learner_heads_tc": (_i32, [_vp, _vp, _i64, _vp, _vp]),
     "rmc_learner_act_host_sync": (_i32, [_vp, _vp, _i64, _vp, _vp]),
+    "rmc_learner_act_eps_host_sync": (_i32, [_vp, _vp, _i64, _vp, _f32, _u64, _u64, _vp]),
     "rmc_learner_debug_timing": (_i32, [_vp, _i32]),
     "rmc_learner_debug_gaps_sync": (_i32, [_vp, _vp, _vp]),
     "rmc_learner_debug_read_sync": (_i32, [_vp, _vp, _i32, C.POINTER(_i32), _vp]),

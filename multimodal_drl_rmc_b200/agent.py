@@ -147,6 +147,18 @@ class Agent:
         return np.interp(self.step * self.n_env, [0, self.epsilon_decay], [self.epsilon_start, self.epsilon_min])
 
     def choose_actions(self, obses):
+        """dqn/agent.py:92-99.  ``self.exploration = "host"`` (default) consumes Python's ``random`` exactly like the reference
+        (identical stream); ``"device"`` does greedy act + epsilon-greedy in ONE library call with a Philox stream keyed by
+        (sampling_seed, step) -- same distribution, for vectorised envs."""
+        if getattr(self, "exploration", "host") == "device":
+            net = self.online_network
+            net._push()
+            x = np.ascontiguousarray(np.asarray(obses, dtype=np.float32)).reshape(-1, net._obs_dim)
+            out = np.empty(x.shape[0], np.int64)
+            self._act_calls = getattr(self, "_act_calls", 0) + 1
+            check(lib().rmc_learner_act_eps_host_sync(self._lh.handle, x.ctypes.data, x.shape[0], out.ctypes.data, float(self.epsilon()),
+                                                      int(self.sampling_seed) ^ 0xAC7, self._act_calls, stream_ptr(self._dev_index)))
+            return out.tolist()
         actions = self.online_network.actions(obses)
         for i in range(len(actions)):
             if random.random() <= self.epsilon():

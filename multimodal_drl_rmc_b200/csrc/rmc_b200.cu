@@ -1561,7 +1561,16 @@ extern "C" int32_t rmc_learner_heads_tc(rmc_learner_t* l, const float* obs_dev, 
   return infer_tc(l, obs_dev, n, nullptr, heads_out_dev, 2, as_stream(s));
 }
 
+static int32_t act_host_impl(rmc_learner_t* l, const float* obs_host, int64_t n, int64_t* actions_host, float eps, uint64_t seed, uint64_t counter, rmc_stream_t s);
 extern "C" int32_t rmc_learner_act_host_sync(rmc_learner_t* l, const float* obs_host, int64_t n, int64_t* actions_host, rmc_stream_t s) {
+  return act_host_impl(l, obs_host, n, actions_host, -1.f, 0, 0, s);
+}
+extern "C" int32_t rmc_learner_act_eps_host_sync(rmc_learner_t* l, const float* obs_host, int64_t n, int64_t* actions_host, float epsilon,
+                                                 uint64_t seed, uint64_t counter, rmc_stream_t s) {
+  if (!(epsilon >= 0.f && epsilon <= 1.f)) return fail(RMC_ERR_ARG, "rmc_learner_act_eps_host_sync: epsilon outside [0, 1]");
+  return act_host_impl(l, obs_host, n, actions_host, epsilon, seed, counter, s);
+}
+static int32_t act_host_impl(rmc_learner_t* l, const float* obs_host, int64_t n, int64_t* actions_host, float eps, uint64_t seed, uint64_t counter, rmc_stream_t s) {
   if (!l || !obs_host || !actions_host || n < 1) return fail(RMC_ERR_ARG, "rmc_learner_act_host_sync: bad args");
   if (int32_t e = use_device(l->device)) return e;
   cudaStream_t st = as_stream(s);
@@ -1581,6 +1590,10 @@ extern "C" int32_t rmc_learner_act_host_sync(rmc_learner_t* l, const float* obs_
   std::memcpy(l->act_pin_obs, obs_host, static_cast<size_t>(n) * l->L.D * sizeof(float));
   RMC_CUDA(cudaMemcpyAsync(l->act_dev_obs, l->act_pin_obs, static_cast<size_t>(n) * l->L.D * sizeof(float), cudaMemcpyHostToDevice, st));
   if (int32_t e = infer_launch(l, l->blobs[RMC_ONLINE], l->act_dev_obs, n, l->act_dev_out, nullptr, 0, st)) return e;
+  if (eps >= 0.f) {
+    k_eps_greedy<<<blocks_for(n, 256), 256, 0, st>>>(l->act_dev_out, n, eps, l->spec.n_actions, seed, counter);
+    RMC_KERNEL_OK();
+  }
   RMC_CUDA(cudaMemcpyAsync(l->act_pin_out, l->act_dev_out, static_cast<size_t>(n) * sizeof(long long), cudaMemcpyDeviceToHost, st));
   RMC_CUDA(cudaStreamSynchronize(st));
   std::memcpy(actions_host, l->act_pin_out, static_cast<size_t>(n) * sizeof(long long));

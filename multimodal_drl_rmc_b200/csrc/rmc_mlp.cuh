@@ -875,6 +875,18 @@ __global__ void __launch_bounds__(kThreads, 1) k_mlp_infer(NetLayout L, const fl
   }
 }
 
+// epsilon-greedy on the device (Agent.choose_actions, dqn/agent.py:92-99): row i explores when u1 <= eps and then takes
+// floor(u2 * A); (u1, u2) = Philox4x32-10(seed, counter, i).  The reference draws from Python's Mersenne Twister, so this
+// mode reproduces its distribution, not its stream (the host-RNG mode of Agent.choose_actions reproduces the stream).
+__global__ void k_eps_greedy(long long* __restrict__ actions, long long n, float eps, int n_actions, unsigned long long seed, unsigned long long counter) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  const uint4 r = philox4x32_10(make_uint4(static_cast<uint32_t>(i), static_cast<uint32_t>(i >> 32), static_cast<uint32_t>(counter), static_cast<uint32_t>(counter >> 32)),
+                                make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32) ^ 0x9E3779B9u));
+  const float u1 = static_cast<float>(r.x >> 8) * (1.0f / 16777216.0f);
+  if (u1 <= eps) actions[i] = static_cast<long long>((static_cast<unsigned long long>(r.y) * static_cast<unsigned long long>(n_actions)) >> 32);
+}
+
 // parameter (de)interleave between torch state_dict order and the device layout
 __global__ void k_params_scatter(float* dev_blob, const float* src_torch, const int* map, long long n) {
   const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;

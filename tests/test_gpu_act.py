@@ -6,6 +6,7 @@ import pytest
 import torch
 
 from oracle import dqn_oracle as O
+from tests import parity_utils as PU
 from tests import recipes as R
 
 pytestmark = pytest.mark.gpu
@@ -105,3 +106,27 @@ def test_tensor_core_act_mode_within_stated_bound():
     top2 = np.sort(e[:, 1:], axis=1)[:, -2:]
     gap = top2[flips, 1] - top2[flips, 0]
     assert np.all(gap < 0.05 * np.abs(e[:, 1:]).max())
+
+
+def test_device_epsilon_greedy_distribution_and_reproducibility():
+    """Agent.exploration = "device": greedy act + Philox epsilon-greedy in one call."""
+    _, a = PU.make_pair("DuelingDoubleDQNAgent", 14, 32, 64, 64, seed=3)
+    obs = np.random.default_rng(0).random((20000, 14), dtype=np.float32)
+    greedy = np.asarray(a.online_network.actions(obs))
+    a.exploration = "device"
+    a.epsilon_exp_decay = False
+    a.epsilon_start, a.epsilon_min, a.epsilon_decay = 0.3, 0.3, 1.0          # epsilon() == 0.3
+    got = np.asarray(a.choose_actions(obs))
+    changed = got != greedy
+    # a row explores with probability 0.3 and then hits its own greedy action 1/8 of the time
+    assert abs(changed.mean() - 0.3 * 7 / 8) < 0.015
+    assert got.min() >= 0 and got.max() < 8
+    a.epsilon_start = a.epsilon_min = 1.0                                       # every row explores: uniform over the 8 actions
+    hist = np.bincount(np.asarray(a.choose_actions(obs)), minlength=8) / obs.shape[0]
+    assert np.all(np.abs(hist - 0.125) < 0.012)
+    a.epsilon_start = a.epsilon_min = 0.0
+    assert a.choose_actions(obs) == greedy.tolist()
+    _, b = PU.make_pair("DuelingDoubleDQNAgent", 14, 32, 64, 64, seed=3)
+    b.exploration, b.epsilon_exp_decay = "device", False
+    b.epsilon_start, b.epsilon_min, b.epsilon_decay = 0.3, 0.3, 1.0
+    np.testing.assert_array_equal(np.asarray(b.choose_actions(obs)), got)       # same seed and call count -> same draw
