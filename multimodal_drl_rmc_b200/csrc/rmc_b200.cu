@@ -128,6 +128,8 @@ struct rmc_learner {
   unsigned long long tc_bwd_version = 0;
   unsigned long long target_version = 1, tc_target_version = 0;
   TcTrainBufs tct{};
+  cudaStream_t tc_side = nullptr;           // the PER write-back runs here beside the backward / Adam kernels
+  cudaEvent_t tc_ev[2] = {};
   // hybrid CNN+MLP network (rmc_hybrid.cuh): per-row activation / delta records
   bool hybrid = false;
   HybNet H{};
@@ -632,6 +634,7 @@ extern "C" int32_t rmc_learner_destroy(rmc_learner_t* l) {
   if (l->act_pin_obs) cudaFreeHost(l->act_pin_obs);
   if (l->act_pin_out) cudaFreeHost(l->act_pin_out);
   if (l->host_loss) cudaFreeHost(const_cast<float*>(l->host_loss));
+  if (l->tc_side) { cudaStreamDestroy(l->tc_side); for (auto& ev : l->tc_ev) if (ev) cudaEventDestroy(ev); }
   if (l->hyb_side) { cudaStreamDestroy(l->hyb_side); for (auto& ev : l->hyb_ev) if (ev) cudaEventDestroy(ev); }
   cudaFree(l->act_dev_obs);
   cudaFree(l->act_dev_out);
@@ -813,6 +816,8 @@ static int32_t tc_train_setup(rmc_learner* l) {
   if ((e = owned_alloc(l, &T.partials, static_cast<size_t>(l->num_sms) * l->L.total))) return e;
   RMC_CUDA(cudaFuncSetAttribute(k_mlp_infer_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
   RMC_CUDA(cudaFuncSetAttribute(k_tc_fwd3, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
+  RMC_CUDA(cudaStreamCreateWithFlags(&l->tc_side, cudaStreamNonBlocking));
+  for (auto& ev : l->tc_ev) RMC_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   RMC_CUDA(cudaFuncSetAttribute(k_tc_bwd_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcBwdFusedSmemBytes));
   l->tct_ready = true;
   return RMC_OK;
@@ -875,6 +880,26 @@ static int32_t step_tc(rmc_learner* l, rmc_replay* r, const rmc_step_args_t* a, 
   if (td_blocks > 1024) return fail(RMC_ERR_UNSUPPORTED, "tensor-core learner mode: batch above 131,072");
   RMC_CUDA(launch_pdl(k_tc_td, dim3(td_blocks), dim3(kTdThreads), 0, st, l->ctx, S, T));
   RMC_KERNEL_OK();
+  // The priority write-back needs only |td| and the sampled leaves: it runs on a side stream beside the backward and
+  // Adam kernels (latency-bound tree kernels next to tensor-core CTAs) and joins before the step returns.
+  static const bool side_tree = [] { const char* e = std::getenv("RMC_TC_SIDE_TREE"); return !(e && e[0] == '0'); }();
+  const bool write_back = (a->phases & RMC_PH_PRIORITY) && l->spec.prioritized;
+  if (write_back) {
+    cudaStream_t ts = side_tree ? l->tc_side : st;
+    if (ts != st) {
+      RMC_CUDA(cudaEventRecord(l->tc_ev[0], st));
+      RMC_CUDA(cudaStreamWaitEvent(ts, l->tc_ev[0], 0));
+    }
+    if (B <= kTreeCtaMax) {
+      RMC_CUDA(launch_pdl(k_tree_update_small, dim3(1), dim3(kThreads), 0, ts, r->dev, C.nodes, nullptr, C.abs_td, C.pri, B, S.per_eps, S.per_alpha, S.per_pmax));
+      RMC_KERNEL_OK();
+    } else {
+      RMC_CUDA(launch_pdl(k_td_to_pri, dim3(blocks_for(B, 256)), dim3(256), 0, ts, C.abs_td, C.pri, B, S.per_eps, S.per_alpha, S.per_pmax));
+      RMC_KERNEL_OK();
+      if (int32_t e = tree_update_large(r, C.nodes, C.pri, B, false, ts)) return e;
+    }
+    if (ts != st) RMC_CUDA(cudaEventRecord(l->tc_ev[1], ts));
+  }
   // backward: dgrad chain + weight gradients fused per 128-row tile
   T.n_part = static_cast<int>(grid);
   RMC_CUDA(launch_pdl(k_tc_bwd_fused, dim3(grid), dim3(kThreads), kTcBwdFusedSmemBytes, st, l->ctx, reinterpret_cast<const unsigned char*>(l->tc_packed_bwd), B, T));
@@ -888,16 +913,7 @@ static int32_t step_tc(rmc_learner* l, rmc_replay* r, const rmc_step_args_t* a, 
   l->loss_epoch = S.epoch;
   if (a->phases & RMC_PH_ADAM) l->tc_packed_version = l->tc_bwd_version = ++l->online_version;
   if (a->phases & (RMC_PH_POLYAK | RMC_PH_HARDSYNC)) l->tc_target_version = ++l->target_version;
-  if ((a->phases & RMC_PH_PRIORITY) && l->spec.prioritized) {
-    if (B <= kTreeCtaMax) {
-      RMC_CUDA(launch_pdl(k_tree_update_small, dim3(1), dim3(kThreads), 0, st, r->dev, C.nodes, nullptr, C.abs_td, C.pri, B, S.per_eps, S.per_alpha, S.per_pmax));
-      RMC_KERNEL_OK();
-    } else {
-      RMC_CUDA(launch_pdl(k_td_to_pri, dim3(blocks_for(B, 256)), dim3(256), 0, st, C.abs_td, C.pri, B, S.per_eps, S.per_alpha, S.per_pmax));
-      RMC_KERNEL_OK();
-      if (int32_t e = tree_update_large(r, C.nodes, C.pri, B, false, st)) return e;
-    }
-  }
+  if (write_back && side_tree) RMC_CUDA(cudaStreamWaitEvent(st, l->tc_ev[1], 0));
   return RMC_OK;
 }
 
