@@ -130,6 +130,7 @@ struct rmc_learner {
   TcTrainBufs tct{};
   cudaStream_t tc_side = nullptr;           // the PER write-back runs here beside the backward / Adam kernels
   cudaEvent_t tc_ev[2] = {};
+  struct { rmc_comm* c = nullptr; CommView V{}; int parity = 0; bool issue_side = false; long long Bg = 0; } early;   // sharded step: (leaf,|td|) leave right after TD
   // hybrid CNN+MLP network (rmc_hybrid.cuh): per-row activation / delta records
   bool hybrid = false;
   HybNet H{};
@@ -153,6 +154,7 @@ struct rmc_comm {
   CommView view{};
   unsigned epoch = 0;
   unsigned* arrive = nullptr;
+  unsigned* arrive_td = nullptr;
   long long* g_nodes = nullptr;                 // gathered (leaf, |td|) of the whole batch + their priorities
   float* g_td = nullptr;
   float* g_pri = nullptr;
@@ -823,6 +825,31 @@ static int32_t tc_train_setup(rmc_learner* l) {
   return RMC_OK;
 }
 
+static int32_t tree_update_large(rmc_replay* r, const long long* nodes, const float* pri, long long n, bool stamps_done, cudaStream_t st);
+// sharded tensor-core step: gather every rank's (leaf, |td|) slice and apply the replicated write-back of the GLOBAL batch on
+// the side stream (fork from `st`; tc_ev[1] marks its end)
+static int32_t comm_side_writeback(rmc_learner* l, rmc_replay* r, cudaStream_t st) {
+  rmc_comm* c = l->early.c;
+  const long long Bg = l->early.Bg;
+  cudaStream_t ts = l->tc_side;
+  RMC_CUDA(cudaEventRecord(l->tc_ev[0], st));
+  RMC_CUDA(cudaStreamWaitEvent(ts, l->tc_ev[0], 0));
+  RMC_CUDA(launch_pdl(k_comm_gather_td, dim3(static_cast<unsigned>(std::min<long long>(128, (Bg + 255) / 256))), dim3(256), 0, ts, l->early.V, l->early.parity, c->epoch,
+                      c->g_nodes, c->g_td));
+  RMC_KERNEL_OK();
+  const float eps = static_cast<float>(l->hyper.per_eps), alpha = static_cast<float>(l->hyper.per_alpha), pmax = static_cast<float>(l->hyper.per_pmax);
+  if (Bg <= kTreeCtaMax) {
+    RMC_CUDA(launch_pdl(k_tree_update_small, dim3(1), dim3(kThreads), 0, ts, r->dev, c->g_nodes, nullptr, c->g_td, c->g_pri, Bg, eps, alpha, pmax));
+    RMC_KERNEL_OK();
+  } else {
+    RMC_CUDA(launch_pdl(k_td_to_pri, dim3(blocks_for(Bg, 256)), dim3(256), 0, ts, c->g_td, c->g_pri, Bg, eps, alpha, pmax));
+    RMC_KERNEL_OK();
+    if (int32_t e = tree_update_large(r, c->g_nodes, c->g_pri, Bg, false, ts)) return e;
+  }
+  RMC_CUDA(cudaEventRecord(l->tc_ev[1], ts));
+  return RMC_OK;
+}
+
 static int32_t step_tc(rmc_learner* l, rmc_replay* r, const rmc_step_args_t* a, StepScalars& S, cudaStream_t st) {
   if (l->L.D > kTcK1 - 1) return fail(RMC_ERR_UNSUPPORTED, "tensor-core learner mode: obs_dim must be <= 15 (column 15 of the X tile carries the bias-gradient ones)");
   if (l->L.act != 0) return fail(RMC_ERR_UNSUPPORTED, "tensor-core modes are built for ReLU bodies only");
@@ -884,6 +911,13 @@ static int32_t step_tc(rmc_learner* l, rmc_replay* r, const rmc_step_args_t* a, 
   // Adam kernels (latency-bound tree kernels next to tensor-core CTAs) and joins before the step returns.
   static const bool side_tree = [] { const char* e = std::getenv("RMC_TC_SIDE_TREE"); return !(e && e[0] == '0'); }();
   const bool write_back = (a->phases & RMC_PH_PRIORITY) && l->spec.prioritized;
+  if (l->early.c != nullptr) {      // sharded step: this rank's (leaf, |td|) slice leaves now, long before its gradients
+    RMC_CUDA(launch_pdl(k_comm_publish_td, dim3(static_cast<unsigned>(std::max<long long>(1, std::min<long long>(32, (B + 1023) / 1024)))), dim3(256), 0, st, l->early.V,
+                        l->early.parity, l->early.c->epoch, C.nodes, C.abs_td, B, l->early.c->arrive_td));
+    RMC_KERNEL_OK();
+    if (l->early.issue_side)
+      if (int32_t e = comm_side_writeback(l, r, st)) return e;
+  }
   if (write_back) {
     cudaStream_t ts = side_tree ? l->tc_side : st;
     if (ts != st) {
@@ -1303,6 +1337,7 @@ extern "C" int32_t rmc_comm_create(rmc_comm_t** out, rmc_learner_t* l, int32_t r
   RMC_CUDA(cudaMemset(c->local, 0, c->bytes));
   int32_t e = RMC_OK;
   if ((e = dev_alloc(&c->arrive, 1))) return e;
+  if ((e = dev_alloc(&c->arrive_td, 1))) return e;
   if ((e = dev_alloc(&c->g_nodes, static_cast<size_t>(global_batch_max)))) return e;
   if ((e = dev_alloc(&c->g_td, static_cast<size_t>(global_batch_max)))) return e;
   if ((e = dev_alloc(&c->g_pri, static_cast<size_t>(global_batch_max)))) return e;
@@ -1360,7 +1395,7 @@ extern "C" int32_t rmc_comm_destroy(rmc_comm_t* c) {
   cudaDeviceSynchronize();
   for (int r = 0; r < c->world; ++r)
     if (c->ipc_opened[r]) cudaIpcCloseMemHandle(c->peer[r]);
-  cudaFree(c->local); cudaFree(c->arrive); cudaFree(c->g_nodes); cudaFree(c->g_td); cudaFree(c->g_pri);
+  cudaFree(c->local); cudaFree(c->arrive); cudaFree(c->arrive_td); cudaFree(c->g_nodes); cudaFree(c->g_td); cudaFree(c->g_pri);
   delete c;
   return RMC_OK;
 }
@@ -1396,15 +1431,21 @@ extern "C" int32_t rmc_learner_step_sharded(rmc_learner_t* l, rmc_replay_t* r, r
     V.shard_lo[q] = (q < c->world) ? qlo : qhi;
   }
   const long long n_local = a->batch;
+  // tensor-core mode: |td| exists right after the TD kernel -> the (leaf, |td|) slices are exchanged early and the replicated
+  // write-back runs on a side stream beside the backward pass and the gradient exchange
+  const bool early = per && a->precision == RMC_PREC_BF16_TC && !l->hybrid;
   if (stages & 1) {
   // 1. local shard: sample (global strata), forward, TD, backward -> local gradient blob scaled by 1/B_global
   rmc_step_args_t a1 = *a;
   a1.phases = a->phases & (RMC_PH_SAMPLE | RMC_PH_FORWARD | RMC_PH_BACKWARD);
   a1.grads_in_dev = nullptr;
-  if (int32_t e = rmc_learner_step(l, r, &a1, s)) return e;
+  if (early) { l->early.c = c; l->early.V = V; l->early.parity = parity; l->early.Bg = Bg; l->early.issue_side = (stages == 3); }
+  const int32_t e1 = rmc_learner_step(l, r, &a1, s);
+  l->early.c = nullptr;
+  if (e1) return e1;
   // 2. publish: gradient blob, loss partial, (leaf, |td|) slice -> own exchange buffer, then one flag per rank
   const unsigned pub_blocks = std::max(1u, std::min(64u, blocks_for(std::max<long long>(l->L.total, n_local), 1024)));
-  RMC_CUDA(launch_pdl(k_comm_publish, dim3(pub_blocks), dim3(256), 0, st, V, parity, c->epoch, l->ctx.grads, l->L.total, l->ctx.loss, per ? l->ctx.nodes : nullptr, l->ctx.abs_td,
+  RMC_CUDA(launch_pdl(k_comm_publish, dim3(pub_blocks), dim3(256), 0, st, V, parity, c->epoch, l->ctx.grads, l->L.total, l->ctx.loss, (per && !early) ? l->ctx.nodes : nullptr, l->ctx.abs_td,
                                             n_local, c->arrive));
   RMC_KERNEL_OK();
   }
@@ -1416,12 +1457,18 @@ extern "C" int32_t rmc_learner_step_sharded(rmc_learner_t* l, rmc_replay_t* r, r
   if (int32_t e = fill_scalars(l, &a2, &S)) return e;
   l->epoch = (l->epoch >= 0x7fffffffu) ? 1u : l->epoch + 1u;
   S.epoch = l->epoch;
+  if (early && stages != 3) {      // ranks emulated on one GPU: the side-stream part is issued here instead of right after TD
+    l->early.c = c; l->early.V = V; l->early.parity = parity; l->early.Bg = Bg;
+    const int32_t e2 = comm_side_writeback(l, r, st);
+    l->early.c = nullptr;
+    if (e2) return e2;
+  }
   const int param_blocks = static_cast<int>(blocks_for(l->L.total, 256));
-  const int gather_blocks = per ? static_cast<int>(std::min<long long>(256, (Bg + 255) / 256)) : 0;
+  const int gather_blocks = (per && !early) ? static_cast<int>(std::min<long long>(256, (Bg + 255) / 256)) : 0;
   const bool images = l->tct_ready && l->tc_packed_version == l->online_version && l->tc_bwd_version == l->online_version &&
                       l->tc_target_version == l->target_version;      // keep the bf16 operand images current (tensor-core mode)
   const TcPackOut P{images ? l->tc_packed : nullptr, images ? l->tc_packed_bwd : nullptr, images ? l->tc_packed_target : nullptr};
-  RMC_CUDA(launch_pdl(k_comm_reduce_adam, dim3(param_blocks + gather_blocks), dim3(256), 0, st, l->ctx, S, V, parity, c->epoch, param_blocks, c->g_nodes, c->g_td, per ? 1 : 0, P));
+  RMC_CUDA(launch_pdl(k_comm_reduce_adam, dim3(param_blocks + gather_blocks), dim3(256), 0, st, l->ctx, S, V, parity, c->epoch, param_blocks, c->g_nodes, c->g_td, (per && !early) ? 1 : 0, P));
   RMC_KERNEL_OK();
   l->loss_epoch = S.epoch;
   ++l->online_version;
@@ -1431,7 +1478,9 @@ extern "C" int32_t rmc_learner_step_sharded(rmc_learner_t* l, rmc_replay_t* r, r
     if (a->phases & (RMC_PH_POLYAK | RMC_PH_HARDSYNC)) l->tc_target_version = l->target_version;
   }
   // 4. PER: the full write-back of the GLOBAL batch on every replica, in global batch order (trees stay identical)
-  if (per) {
+  if (early) {
+    RMC_CUDA(cudaStreamWaitEvent(st, l->tc_ev[1], 0));      // the side-stream write-back joins here
+  } else if (per) {
     if (Bg <= kTreeCtaMax) {
       RMC_CUDA(launch_pdl(k_tree_update_small, dim3(1), dim3(kThreads), 0, st, r->dev, c->g_nodes, nullptr, c->g_td, c->g_pri, Bg, static_cast<float>(l->hyper.per_eps),
                                                  static_cast<float>(l->hyper.per_alpha), static_cast<float>(l->hyper.per_pmax)));

@@ -19,7 +19,8 @@
 namespace rmc {
 
 constexpr int kCommMaxWorld = 8;
-constexpr int kCommHeaderBytes = 4096;     // flags[2][kCommMaxWorld] + error word, padded
+constexpr int kCommHeaderBytes = 4096;     // flags[2][kCommMaxWorld] + error word | (leaf,|td|) flags[2][kCommMaxWorld] at word 32, padded
+constexpr int kCommTdFlagWord = 32;
 
 struct CommView {
   unsigned char* base[kCommMaxWorld];      // exchange buffer of every rank (own rank: local memory)
@@ -78,6 +79,58 @@ __global__ void __launch_bounds__(256) k_comm_publish(CommView V, int parity, un
     st_release_sys_u32(flags + parity * kCommMaxWorld + V.rank, epoch);
   }
   if (threadIdx.x == 0) *arrive = 0u;
+}
+
+// Early exchange of the (leaf, |td|) slices (tensor-core mode: |td| exists right after the TD kernel, long before the
+// gradients): publish + flag, then a gather kernel on a side stream feeds the replicated priority write-back, which so
+// overlaps the backward pass and the gradient exchange.
+__global__ void __launch_bounds__(256) k_comm_publish_td(CommView V, int parity, unsigned epoch, const long long* __restrict__ nodes,
+                                                         const float* __restrict__ abs_td, long long n_local, unsigned* arrive) {
+  pdl_enter();
+  __shared__ bool s_last;
+  unsigned char* slot = comm_slot(V, V.rank, parity);
+  long long* dn = reinterpret_cast<long long*>(slot + V.off_nodes);
+  float* dt = reinterpret_cast<float*>(slot + V.off_td);
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long k = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; k < n_local; k += stride) { dn[k] = __ldcg(nodes + k); dt[k] = __ldcg(abs_td + k); }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(arrive, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence_system();
+  if (threadIdx.x < V.world) {
+    unsigned* flags = reinterpret_cast<unsigned*>(V.base[threadIdx.x]) + kCommTdFlagWord;
+    st_release_sys_u32(flags + parity * kCommMaxWorld + V.rank, epoch);
+  }
+  if (threadIdx.x == 0) *arrive = 0u;
+}
+__global__ void __launch_bounds__(256) k_comm_gather_td(CommView V, int parity, unsigned epoch, long long* __restrict__ g_nodes, float* __restrict__ g_td) {
+  pdl_enter();
+  __shared__ int s_ok;
+  unsigned* my_flags = reinterpret_cast<unsigned*>(V.base[V.rank]);
+  if (threadIdx.x == 0) s_ok = 1;
+  __syncthreads();
+  if (threadIdx.x < V.world) {
+    const unsigned* f = my_flags + kCommTdFlagWord + parity * kCommMaxWorld + threadIdx.x;
+    const unsigned long long t0 = global_timer_ns();
+    while (ld_acquire_sys_u32(f) != epoch) {
+      if (global_timer_ns() - t0 > 4000000000ull) { s_ok = 0; my_flags[2 * kCommMaxWorld] = epoch; break; }
+      __nanosleep(64);
+    }
+  }
+  __syncthreads();
+  if (!s_ok) return;
+  const long long stride = static_cast<long long>(gridDim.x) * 256;
+  for (int r = 0; r < V.world; ++r) {
+    const long long lo = V.shard_lo[r], n = V.shard_lo[r + 1] - lo;
+    const long long* sn = reinterpret_cast<const long long*>(comm_slot(V, r, parity) + V.off_nodes);
+    const float* st = reinterpret_cast<const float*>(comm_slot(V, r, parity) + V.off_td);
+    for (long long k = blockIdx.x * 256ll + threadIdx.x; k < n; k += stride) {
+      g_nodes[lo + k] = ld_sys_s64(sn + k);
+      g_td[lo + k] = ld_sys_f32(st + k);
+    }
+  }
 }
 
 // blocks [0, param_blocks): parameters; the remaining blocks: (leaf, |td|) gather.
