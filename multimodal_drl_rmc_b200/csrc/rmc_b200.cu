@@ -608,7 +608,7 @@ extern "C" int32_t rmc_learner_create(rmc_learner_t** out, const rmc_net_spec_t*
   if ((e = owned_alloc(l, &c.loss_part, 1024))) return e;
   if ((e = owned_alloc(l, &c.loss, 1))) return e;
   if ((e = owned_alloc(l, &c.barrier, 1))) return e;
-  if ((e = owned_alloc(l, &c.qt_flag, 1024))) return e;
+  if ((e = owned_alloc(l, &c.qt_flag, kFlagWords))) return e;
   {
     float* hp = nullptr;
     float* dp = nullptr;
@@ -766,6 +766,12 @@ static int32_t launch_step(dim3 grid, void** args, size_t smem, cudaStream_t st,
   }
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return RMC_OK;
+}
+
+// The one-tile instantiation keeps the sampled rows in shared memory between SAMPLE and FORWARD: a FORWARD-only launch
+// (rows already in X from an earlier launch) takes the general instantiation, which reads X.
+static bool one_tile_ok(const StepScalars& S, long long n_tiles) {
+  return n_tiles <= S.n_row_ctas && ((S.phases & (RMC_PH_SAMPLE | RMC_PH_FORWARD)) != RMC_PH_FORWARD);
 }
 
 static int grid_for(const rmc_learner* l, long long B, int max_ctas) {
@@ -1295,7 +1301,7 @@ extern "C" int32_t rmc_learner_step(rmc_learner_t* l, rmc_replay_t* r, const rmc
   l->last_grid = G;
   const AgentCtx* many = nullptr;
   void* args[] = {&single, &many, &S};
-  if (int32_t e = launch_step(dim3(G, 1, 1), args, static_cast<size_t>(l->smem_bytes), st, n_tiles <= S.n_row_ctas)) return e;
+  if (int32_t e = launch_step(dim3(G, 1, 1), args, static_cast<size_t>(l->smem_bytes), st, one_tile_ok(S, n_tiles))) return e;
   if (rows && phase_b) l->barrier_count = S.barrier_target;
   if ((a->phases & RMC_PH_FORWARD) && phase_b) l->loss_epoch = S.epoch;
   if (a->phases & RMC_PH_ADAM) ++l->online_version;
@@ -1688,13 +1694,13 @@ extern "C" int32_t rmc_group_create(rmc_group_t** out, rmc_learner_t* const* lea
   int32_t e = RMC_OK;
   if ((e = dev_alloc(&g->ctx_dev, static_cast<size_t>(n_agents), false))) return e;
   if ((e = dev_alloc(&g->barriers, static_cast<size_t>(n_agents)))) return e;
-  if ((e = dev_alloc(&g->qt_flags, static_cast<size_t>(n_agents) * 1024))) return e;
+  if ((e = dev_alloc(&g->qt_flags, static_cast<size_t>(n_agents) * kFlagWords))) return e;
   std::vector<AgentCtx> h(n_agents);
   for (int i = 0; i < n_agents; ++i) {
     h[i] = learners[i]->ctx;
     h[i].rp = replays[i]->dev;
     h[i].barrier = g->barriers + i;
-    h[i].qt_flag = g->qt_flags + static_cast<size_t>(i) * 1024;
+    h[i].qt_flag = g->qt_flags + static_cast<size_t>(i) * kFlagWords;
   }
   RMC_CUDA(cudaMemcpy(g->ctx_dev, h.data(), sizeof(AgentCtx) * n_agents, cudaMemcpyHostToDevice));
   *out = g;
@@ -1741,7 +1747,7 @@ extern "C" int32_t rmc_group_step(rmc_group_t* g, const rmc_step_args_t* a, rmc_
   AgentCtx single = l0->ctx;
   const AgentCtx* many = g->ctx_dev;
   void* args[] = {&single, &many, &S};
-  if (int32_t e = launch_step(dim3(G, g->n, 1), args, static_cast<size_t>(l0->smem_bytes), st, n_tiles <= S.n_row_ctas)) return e;
+  if (int32_t e = launch_step(dim3(G, g->n, 1), args, static_cast<size_t>(l0->smem_bytes), st, one_tile_ok(S, n_tiles))) return e;
   if (rows && phase_b) g->barrier_count = S.barrier_target;
   return RMC_OK;
 }

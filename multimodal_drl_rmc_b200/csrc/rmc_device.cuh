@@ -76,11 +76,13 @@ __device__ __forceinline__ uint32_t ld_acquire_u32(const unsigned* p) {
 
 // Barrier across the CTAs of one agent inside ONE cooperative launch (all CTAs co-resident).
 // `ctr` only ever grows; `target` = value it must reach (wrap-safe signed comparison).
+__device__ __forceinline__ void red_release_add_u32(unsigned* p, unsigned v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ void agent_barrier(unsigned* ctr, unsigned target) {
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(ctr, 1u);
+    red_release_add_u32(ctr, 1u);      // release: orders the CTA's writes (observed through the barrier above) before the arrival
     while (static_cast<int>(ld_acquire_u32(ctr) - target) < 0) {
       __nanosleep(32);
     }
@@ -168,6 +170,7 @@ struct ReplayState {   // lives in HBM, updated by the kernels themselves
   int pad;
 };
 
+constexpr int kFlagWords = 4096;   // u32 words of AgentCtx::qt_flag per agent (layout: rmc_mlp.cuh)
 constexpr int kTreeTeam = 8;     // CTAs that share the priority write-back of one learner step
 struct TeamPart {                // one tree-team member's contribution to the extremes
   float bmax, bmin;              // extremes of the NEW values it applied

@@ -256,6 +256,21 @@ struct GemmUnit {
   int bias_base;                           // param index of bias[n] or -1
 };
 
+template <int N>
+__device__ __forceinline__ void lds_vec(float* dst, const float* src) {
+  static_assert(N == 2 || N == 4 || N == 8, "lane tile width");
+  if constexpr (N == 2) {
+    const float2 v = *reinterpret_cast<const float2*>(src);
+    dst[0] = v.x; dst[1] = v.y;
+  } else {
+#pragma unroll
+    for (int k = 0; k < N; k += 4) {
+      const float4 v = *reinterpret_cast<const float4*>(src + k);
+      dst[k] = v.x; dst[k + 1] = v.y; dst[k + 2] = v.z; dst[k + 3] = v.w;
+    }
+  }
+}
+
 template <int TMO, int TNO>
 __device__ void wgrad_unit(const AgentCtx& C, const StepScalars& S, const GemmUnit& U, float* smem) {
   constexpr int LM = TMO / 8, LN = TNO / 4;       // lane tile (8 x 4 lanes cover the unit)
@@ -266,12 +281,13 @@ __device__ void wgrad_unit(const AgentCtx& C, const StepScalars& S, const GemmUn
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int mg = lane >> 2, ng = lane & 3;
   // this thread's output elements and their (prefetched) parameter state: independent of the gradient
-  int pi[NOUT];
+  int pi[NOUT], ps_off[NOUT];
   ParamVals pv[NOUT];
 #pragma unroll
   for (int q = 0; q < NOUT; ++q) {
     const int o = tid + q * kThreads, om = o / TNO, on = o % TNO;
     pi[q] = (om < U.m_valid && on < U.n_valid) ? U.out_base + om * U.out_sm + on * U.out_sn : -1;
+    ps_off[q] = om * TNO + ((on + om / LM) & (TNO - 1));      // partial-sum columns are rotated by the lane row (bank spread)
     if (pi[q] >= 0) pv[q] = param_load(C, S, pi[q]);
   }
   const int pb = (U.bias_base >= 0 && tid < U.n_valid && tid < TNO) ? U.bias_base + tid : -1;
@@ -321,10 +337,8 @@ __device__ void wgrad_unit(const AgentCtx& C, const StepScalars& S, const GemmUn
 #pragma unroll 4
     for (int r = warp; r < rows; r += kWarps) {
       float a[LM], b[LN];
-#pragma unroll
-      for (int i = 0; i < LM; ++i) a[i] = As[r * TMO + mg * LM + i];
-#pragma unroll
-      for (int j = 0; j < LN; ++j) b[j] = Bs[r * TNO + ng * LN + j];
+      lds_vec<LM>(a, As + r * TMO + mg * LM);       // 8- / 16-byte shared-memory loads (offsets are multiples of LM, LN)
+      lds_vec<LN>(b, Bs + r * TNO + ng * LN);
 #pragma unroll
       for (int i = 0; i < LM; ++i)
 #pragma unroll
@@ -338,7 +352,7 @@ __device__ void wgrad_unit(const AgentCtx& C, const StepScalars& S, const GemmUn
 #pragma unroll
   for (int i = 0; i < LM; ++i)
 #pragma unroll
-    for (int j = 0; j < LN; ++j) Ps[warp * (TMO * TNO) + (mg * LM + i) * TNO + ng * LN + j] = acc[i][j];
+    for (int j = 0; j < LN; ++j) Ps[warp * (TMO * TNO) + (mg * LM + i) * TNO + ((ng * LN + j + mg) & (TNO - 1))] = acc[i][j];
   if (mg == 0) {
 #pragma unroll
     for (int j = 0; j < LN; ++j) Pb[warp * TNO + ng * LN + j] = bsum[j];
@@ -349,7 +363,7 @@ __device__ void wgrad_unit(const AgentCtx& C, const StepScalars& S, const GemmUn
     if (pi[q] >= 0) {
       float g = 0.f;
 #pragma unroll
-      for (int w = 0; w < kWarps; ++w) g += Ps[w * (TMO * TNO) + tid + q * kThreads];
+      for (int w = 0; w < kWarps; ++w) g += Ps[w * (TMO * TNO) + ps_off[q]];
       C.grads[pi[q]] = g;
       param_apply(C, S, pi[q], g, pv[q]);
     }
@@ -404,6 +418,50 @@ __device__ void wgrad_run_unit(const AgentCtx& C, const StepScalars& S, int u, b
 }
 
 // ------------------------------------------------------------------ the fused learner step
+// Layout of AgentCtx::qt_flag (kFlagWords u32 per agent):
+//   [0, 512)      Q_target hand-off: epoch of the launch whose Q_target(s') of tile t is in QT
+//   [512, 1024)   per tile {epoch, loss partial}            (early write-back, 8-byte words)
+//   [1024, 4096)  per batch row {epoch, |td|}               (early write-back, 8-byte words)
+// The 8-byte words carry their payload WITH the flag (one relaxed vector store), so publishing them needs no fence on
+// the row CTA's critical path; the stores they must be ordered after (leaf indices and old leaf values from the
+// sampling phase) are covered by a fence that the publishing warp executes while warp 0 computes the TD block.
+constexpr int kLossWordBase = 512, kTdWordBase = 1024;
+constexpr int kEarlyMaxRows = (kFlagWords - kTdWordBase) / 2;
+__device__ __forceinline__ void st_relaxed_pair(unsigned* p, unsigned a, unsigned b) {
+  asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ uint2 ld_relaxed_pair(const unsigned* p) {
+  uint2 v;
+  asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+  return v;
+}
+
+// Who does what after the A->B barrier (identical on every CTA of the agent).
+struct PhaseBPlan { bool tree_here, team, coarse, early; int n_workers; };
+__device__ __forceinline__ PhaseBPlan phase_b_plan(const AgentCtx& C, const StepScalars& S, int G, bool per) {
+  PhaseBPlan p;
+  p.tree_here = per && (S.phases & 4) && C.rp.prioritized && S.B <= kTreeCtaMax;
+  p.coarse = G < 100;   // few CTAs per agent (ensembles): 32x32 gradient tiles instead of 16x16
+  // big tree + enough CTAs: a team of kTreeTeam CTAs shares the write-back; otherwise one CTA does it
+  p.team = p.tree_here && (2 * C.rp.cap - 1 >= 2 * kTopRebuild + 1) && (G >= wgrad_unit_count(C.L, false) + kTreeTeam);
+  const int n_tree = !p.tree_here ? 0 : (p.team ? kTreeTeam : 1);
+  p.n_workers = (p.tree_here && G > 1) ? G - n_tree : G;
+  p.early = p.tree_here && G > 1 && (S.phases & 2) && S.B <= kEarlyMaxRows;   // |td| is produced by this launch's row CTAs
+  return p;
+}
+
+// loss = (1/B) sum of the per-tile partials in tile order; also into mapped host memory (value, system fence, epoch)
+__device__ __forceinline__ void publish_loss(const AgentCtx& C, const StepScalars& S, const float* parts, int np) {
+  float s = 0.f;
+  for (int c = 0; c < np; ++c) s += parts[c];
+  const float loss = s / static_cast<float>(S.Bglobal);
+  C.loss[0] = loss;
+  if (C.host_loss != nullptr) {
+    C.host_loss[0] = loss;
+    __threadfence_system();
+    C.host_loss[1] = __uint_as_float(S.epoch);
+  }
+}
 // Two instantiations: kOneTile = true when every row CTA owns at most one 4-row tile (the default single-agent
 // batches: rows and Q_target stay in shared memory, role split), false for ensembles / large batches (several tiles per
 // CTA).  Splitting them keeps each kernel's straight-line code small: the step is sensitive to instruction-fetch stalls.
@@ -460,6 +518,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, c
   const bool is_row = do_rows && cta < S.n_row_ctas && cta < n_tiles;
   const bool is_tgt = do_rows && split && cta >= n_tiles && cta < 2 * n_tiles;
   const int tile0 = is_tgt ? cta - static_cast<int>(n_tiles) : cta;
+  // Early write-back: the priority write-back needs only (leaf, |td|), which exist right after the TD block -- long before
+  // the row CTAs finish dgrad and reach the agent barrier.  With one tile per row CTA every row CTA release-stores the
+  // launch's epoch into its tile's flag after TD; the tree CTAs arrive at the barrier without waiting, poll the flags and
+  // start the write-back (and publish the loss) while dgrad is still running.  All flags set => every sampler of this
+  // step (row CTAs and, through the Q_target hand-off, their target partners) has finished its descent.
+  const PhaseBPlan pb = phase_b_plan(C, S, G, per);
+  const bool early_td = one_tile && pb.early;
   if (is_row || is_tgt) {
     const long long n_nodes = 2 * C.rp.cap - 1;
     const int n_top = static_cast<int>(min(static_cast<long long>(kTopNodes), n_nodes));
@@ -644,11 +709,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, c
           if (tid < kTM * kQLD) sQT[tid] = __ldcg(C.QT + tile * kTM * kQLD + tid);
           __syncthreads();
         }
+        // early write-back: the publishing lanes order the sampling-phase stores of this CTA (nodes, leaf_p; made visible to
+        // them by the barriers since) before their flag words -- executed in the shadow of warp 0's TD block
+        if (early_td && warp == 1 && lane <= kTM) __threadfence();
         // ---- TD target, |td|, Huber, dQ coefficient (threads 0..kTM-1)
         if (tid < kTM) {
           const int r = tid;
           const long long i = tile * kTM + r;
-          float g = 0.f, lterm = 0.f;
+          float g = 0.f, lterm = 0.f, atd_pub = 0.f;
           int act = 0;
           if (i < B) {
             float qtv[kQLD];
@@ -676,6 +744,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, c
             const float go = per ? (1.f / static_cast<float>(S.Bglobal)) * w : 1.f / static_cast<float>(S.Bglobal);
             g = fminf(fmaxf(delta, -1.f), 1.f) * go;
             lterm = per ? w * hub : hub;
+            atd_pub = atd;
             C.y[i] = y; C.q_sa[i] = q_sa; C.abs_td[i] = atd; C.hub[i] = hub; C.gcoef[i] = g;
             // (|td| -> priority and the last-writer stamps are produced by the write-back itself, phase B)
           }
@@ -690,6 +759,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, c
             dh[act] = g;
           }
           sRed[r] = lterm;
+          sRed[kTM + r] = atd_pub;
         }
         // debug / parity outputs of the Q rows
         if (tid < kR * kQLD) {
@@ -700,6 +770,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, c
         __syncthreads();
         if (tid == 0) {
           for (int r = 0; r < kTM; ++r) loss_local += sRed[r];
+        }
+        if (early_td && warp == 1 && lane <= kTM) {     // release the write-back team: {epoch, |td|} per row, {epoch, loss partial}
+          if (lane < kTM) {
+            const long long i = tile * kTM + lane;
+            if (i < B) st_relaxed_pair(C.qt_flag + kTdWordBase + 2 * i, S.epoch, __float_as_uint(sRed[kTM + lane]));
+          } else {
+            float lp = 0.f;
+            for (int r = 0; r < kTM; ++r) lp += sRed[r];
+            st_relaxed_pair(C.qt_flag + kLossWordBase + 2 * tile, S.epoch, __float_as_uint(lp));
+          }
         }
         // ---- dh2 -> dz2 (thread: column j, rows r and r+2)
         {
@@ -759,47 +839,56 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, c
 
   const int phaseB = S.phases & (4 | 8 | 16 | 32 | 64);
   if (!phaseB) return;
-  if (do_rows) agent_barrier(C.barrier, S.barrier_target);
+  const bool tree_here = pb.tree_here, team = pb.team, coarse = pb.coarse;
+  const int n_workers = pb.n_workers, wid = cta;
+  const bool tree_cta = tree_here && G > 1 && cta >= n_workers;
+  if (do_rows) {
+    if (early_td && tree_cta) {
+      __shared__ float s_lp[kThreads];
+      __syncthreads();
+      if (tid == 0) red_release_add_u32(C.barrier, 1u);                  // arrive, do not wait
+      for (long long i = tid; i < B; i += kThreads)
+        while (ld_relaxed_pair(C.qt_flag + kTdWordBase + 2 * i).x != S.epoch) __nanosleep(20);
+      float lp = 0.f;
+      if (tid < n_tiles) {
+        uint2 w = ld_relaxed_pair(C.qt_flag + kLossWordBase + 2 * tid);
+        while (w.x != S.epoch) { __nanosleep(20); w = ld_relaxed_pair(C.qt_flag + kLossWordBase + 2 * tid); }
+        lp = __uint_as_float(w.y);
+      }
+      __threadfence();                                                   // acquire side of the flag words
+      s_lp[tid] = lp;
+      __syncthreads();
+      if (cta == n_workers && tid == 0) publish_loss(C, S, s_lp, static_cast<int>(n_tiles));
+    } else {
+      agent_barrier(C.barrier, S.barrier_target);
+    }
+  }
   RMC_STAMP(C, 6);
 
   // ---------------------------------------------------------------- phase B
-  const bool tree_here = per && (S.phases & 4) && C.rp.prioritized && B <= kTreeCtaMax;
-  // big tree + enough CTAs: a team of kTreeTeam CTAs shares the write-back; otherwise one CTA does it
-  const bool coarse = G < 100;   // few CTAs per agent (ensembles): 32x32 gradient tiles instead of 16x16
-  const bool team = tree_here && (2 * C.rp.cap - 1 >= 2 * kTopRebuild + 1) && (G >= wgrad_unit_count(L, false) + kTreeTeam);
-  const int n_tree = !tree_here ? 0 : (team ? kTreeTeam : 1);
-  int n_workers = G, wid = cta;
-  if (tree_here && G > 1) {
-    n_workers = G - n_tree;
-    if (cta >= n_workers) {
-      const long long tsize = C.rp.st->size;
-      unsigned long long* tdbg = C.dbg ? C.dbg + (blockIdx.y * gridDim.x + blockIdx.x) * 16 : nullptr;
-      if (team) {
-        tree_update_team(C.rp, C.nodes, C.abs_td, C.pri, B, tsize, (S.phases & 1) ? C.leaf_p : nullptr, S.per_eps, S.per_alpha,
-                         S.per_pmax, cta - n_workers, reinterpret_cast<double*>(smem), tdbg);
-      } else {
-        // |td| -> priority for the whole batch here (off the row CTAs' critical path), then the write-back
-        for (long long i = tid; i < B; i += kThreads) C.pri[i] = td_to_priority(__ldcg(C.abs_td + i), S.per_eps, S.per_alpha, S.per_pmax);
-        __syncthreads();
-        RMC_STAMP(C, 8);
-        tree_update_cta(C.rp, C.nodes, C.pri, B, tsize, tsize, false, (S.phases & 1) ? C.leaf_p : nullptr,
-                        reinterpret_cast<double*>(smem), tdbg);
-      }
-      RMC_STAMP(C, 7); if (gap != nullptr && threadIdx.x == 0) atomicMax(gap + 1, global_timer_ns());
-      return;
+  if (tree_cta) {
+    const long long tsize = C.rp.st->size;
+    // |td| per row: the published {epoch, |td|} words when the write-back started early, else the row CTAs' array
+    const float* td_src = early_td ? reinterpret_cast<const float*>(C.qt_flag + kTdWordBase) + 1 : C.abs_td;
+    const int td_stride = early_td ? 2 : 1;
+    unsigned long long* tdbg = C.dbg ? C.dbg + (blockIdx.y * gridDim.x + blockIdx.x) * 16 : nullptr;
+    if (team) {
+      tree_update_team(C.rp, C.nodes, td_src, td_stride, C.pri, B, tsize, (S.phases & 1) ? C.leaf_p : nullptr, S.per_eps, S.per_alpha,
+                       S.per_pmax, cta - n_workers, reinterpret_cast<double*>(smem), tdbg);
+    } else {
+      // |td| -> priority for the whole batch here (off the row CTAs' critical path), then the write-back
+      for (long long i = tid; i < B; i += kThreads) C.pri[i] = td_to_priority(__ldcg(td_src + i * td_stride), S.per_eps, S.per_alpha, S.per_pmax);
+      __syncthreads();
+      RMC_STAMP(C, 8);
+      tree_update_cta(C.rp, C.nodes, C.pri, B, tsize, tsize, false, (S.phases & 1) ? C.leaf_p : nullptr,
+                      reinterpret_cast<double*>(smem), tdbg);
     }
+    RMC_STAMP(C, 7); if (gap != nullptr && threadIdx.x == 0) atomicMax(gap + 1, global_timer_ns());
+    return;
   }
-  if (cta == 0 && (S.phases & 2) && tid == 0) {   // loss = (1/B) sum of the per-CTA partials, fixed order
-    float s = 0.f;
+  if (cta == 0 && (S.phases & 2) && tid == 0 && !early_td) {   // loss = (1/B) sum of the per-CTA partials, fixed order
     const int np = static_cast<int>(min(static_cast<long long>(S.n_row_ctas), n_tiles));
-    for (int c = 0; c < np; ++c) s += __ldcg(C.loss_part + c);
-    const float loss = s / static_cast<float>(S.Bglobal);
-    C.loss[0] = loss;
-    if (C.host_loss != nullptr) {     // zero-copy publication: value, system fence, then the launch's epoch
-      C.host_loss[0] = loss;
-      __threadfence_system();
-      C.host_loss[1] = __uint_as_float(S.epoch);
-    }
+    publish_loss(C, S, C.loss_part, np);
   }
   if (S.phases & 8) {                             // BACKWARD (+ fused Adam/Polyak)
     const int n_units = wgrad_unit_count(L, coarse);

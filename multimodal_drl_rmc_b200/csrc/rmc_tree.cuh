@@ -297,7 +297,7 @@ __device__ __forceinline__ int depth3_owner(long long node) {
   return static_cast<int>((n1 >> (depth - 3)) - 8ull);   // valid for depth >= 3
 }
 
-__device__ void tree_update_team(const ReplayDev& R, const long long* __restrict__ nodes, const float* __restrict__ abs_td,
+__device__ void tree_update_team(const ReplayDev& R, const long long* __restrict__ nodes, const float* __restrict__ abs_td, int td_stride,
                                  float* __restrict__ pri_out, long long n, long long size, const double* __restrict__ old_vals,
                                  float eps, float alpha, float pmax, int member, double* s_top_buf, unsigned long long* dbg) {
   __shared__ float s_f[64];
@@ -312,7 +312,7 @@ __device__ void tree_update_team(const ReplayDev& R, const long long* __restrict
   for (long long i = tid; i < n; i += nt) {
     const long long leaf = __ldcg(nodes + i);
     if (depth3_owner(leaf) == member) {
-      pri_out[i] = td_to_priority(__ldcg(abs_td + i), eps, alpha, pmax);
+      pri_out[i] = td_to_priority(__ldcg(abs_td + i * td_stride), eps, alpha, pmax);
       atomicMax(R.stamps + (leaf - first_leaf), static_cast<int>(i + 1));
     }
   }

@@ -44,3 +44,10 @@ for k, nm in enumerate(names):
 print("per-CTA rows (first 8, last 2):")
 for c in list(range(min(8, med.shape[0]))) + list(range(max(8, med.shape[0] - 2), med.shape[0])):
     print(c, " ".join("%7.0f" % x for x in med[c]))
+if med.shape[0] == 148 and wl.get("B") == 256:
+    # phase-B duration (barrier exit -> done) per kind of work: CTAs 0-7 own the W0 units (16x32), 8-135 the W2 units
+    # (16x16), 136-139 the head units (32x16), 140-147 are the priority write-back team
+    print("phase B: ns from barrier exit (team: from the |td| flags) to done, by kind of unit (median / max over CTAs)")
+    for nm, lo, hi in (("W0 16x32", 0, 8), ("W2 16x16", 8, 136), ("heads 32x16", 136, 140), ("tree team", 140, 148)):
+        d = med[lo:hi, 7] - med[lo:hi, 6]
+        print("  %-12s %7.0f %7.0f   done at %7.0f (max)" % (nm, np.median(d), d.max(), med[lo:hi, 7].max()))
