@@ -23,6 +23,8 @@ CASES = [
     ("DoubleDQNAgent", 8, 32, 256, 200, 4, False, 2),                   # hard target copy every 2 steps
     ("DQNAgent", 14, 16, 128, 128, 2, True, 30000),
     ("DuelingDoubleDQNAgent", 14, 1024, 4096, 4096, 2, True, 30000),    # several row tiles per CTA
+    ("PerDuelingDoubleDQNAgent", 14, 288, 5000, 5000, 2, True, 30000),  # role split where write-back CTAs are also target CTAs
+    ("PerDuelingDoubleDQNAgent", 14, 590, 8192, 8192, 2, True, 30000),  # every CTA owns a row tile (ragged last one), no role split
 ]
 
 
