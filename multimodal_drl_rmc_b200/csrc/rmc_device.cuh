@@ -170,7 +170,7 @@ struct ReplayState {   // lives in HBM, updated by the kernels themselves
   int pad;
 };
 
-constexpr int kFlagWords = 4096;   // u32 words of AgentCtx::qt_flag per agent (layout: rmc_mlp.cuh)
+constexpr int kFlagWords = 16384;   // u32 words of AgentCtx::qt_flag per agent (layout: rmc_mlp.cuh)
 constexpr int kTreeTeam = 8;     // CTAs that share the priority write-back of one learner step
 struct TeamPart {                // one tree-team member's contribution to the extremes
   float bmax, bmin;              // extremes of the NEW values it applied

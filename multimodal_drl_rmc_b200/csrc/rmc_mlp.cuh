@@ -236,6 +236,35 @@ __device__ __forceinline__ float2 param_apply(const AgentCtx& C, const StepScala
   }
   return make_float2(p, tnew);
 }
+// The same update for N independent elements with the arithmetic of all of them in ONE straight-line block (the
+// sqrt / division chains of the elements interleave instead of running back to back) and the stores separate.
+template <int N>
+__device__ __forceinline__ void param_math_n(const StepScalars& S, const float (&g)[N], const ParamVals (&x)[N], ParamVals (&o)[N]) {
+#pragma unroll
+  for (int k = 0; k < N; ++k) o[k] = x[k];
+  if (S.phases & 16 /*ADAM*/) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      const float m = fmaf(S.adam_w1, g[k] - x[k].m, x[k].m);
+      const float v = fmaf(S.adam_w2 * g[k], g[k], x[k].v * S.adam_b2);
+      const float denom = __fsqrt_rn(v) / S.adam_bc2_sqrt + S.adam_eps;
+      o[k].p = x[k].p + (S.adam_neg_step * m) / denom;
+      o[k].m = m;
+      o[k].v = v;
+    }
+  }
+  if (S.phases & 32 /*POLYAK*/) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) o[k].t = S.polyak_k * o[k].p + S.polyak_1mk * x[k].t;
+  } else if (S.phases & 64 /*HARDSYNC*/) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) o[k].t = o[k].p;
+  }
+}
+__device__ __forceinline__ void param_store(const AgentCtx& C, const StepScalars& S, int pi, const ParamVals& o) {
+  if (S.phases & 16) { C.online[pi] = o.p; C.adam_m[pi] = o.m; C.adam_v[pi] = o.v; }
+  if (S.phases & (32 | 64)) C.target[pi] = o.t;
+}
 __device__ __forceinline__ float2 adam_polyak_element(const AgentCtx& C, const StepScalars& S, int pi, float g) {
   return param_apply(C, S, pi, g, param_load(C, S, pi));
 }
@@ -282,7 +311,7 @@ __device__ void wgrad_unit(const AgentCtx& C, const StepScalars& S, const GemmUn
   const int mg = lane >> 2, ng = lane & 3;
   // this thread's output elements and their (prefetched) parameter state: independent of the gradient
   int pi[NOUT], ps_off[NOUT];
-  ParamVals pv[NOUT];
+  ParamVals pv[NOUT] = {};
 #pragma unroll
   for (int q = 0; q < NOUT; ++q) {
     const int o = tid + q * kThreads, om = o / TNO, on = o % TNO;
@@ -290,7 +319,10 @@ __device__ void wgrad_unit(const AgentCtx& C, const StepScalars& S, const GemmUn
     ps_off[q] = om * TNO + ((on + om / LM) & (TNO - 1));      // partial-sum columns are rotated by the lane row (bank spread)
     if (pi[q] >= 0) pv[q] = param_load(C, S, pi[q]);
   }
-  const int pb = (U.bias_base >= 0 && tid < U.n_valid && tid < TNO) ? U.bias_base + tid : -1;
+  // bias column sums: lanes of the LAST warp (for the W0 units its second output row is a masked padding row, so the
+  // bias update replaces work instead of adding a third dependent Adam chain to warp 0)
+  const int bt = tid - (kThreads - 32);
+  const int pb = (U.bias_base >= 0 && bt >= 0 && bt < U.n_valid && bt < TNO) ? U.bias_base + bt : -1;
   ParamVals pvb{};
   if (pb >= 0) pvb = param_load(C, S, pb);
   float acc[LM][LN];
@@ -302,23 +334,34 @@ __device__ void wgrad_unit(const AgentCtx& C, const StepScalars& S, const GemmUn
 #pragma unroll
   for (int j = 0; j < LN; ++j) bsum[j] = 0.f;
 
-  // 16-byte chunks per staged row; columns past the valid ones are zeroed once and never written.
+  // 16-byte chunks per staged row.  When the source rows are at least as wide as the tile (X, DH and the activation
+  // arrays all are: their padding columns hold finite values that only feed outputs masked by pi < 0) whole tiles are
+  // copied; otherwise columns past the valid ones are zeroed once and never written.
   // Two staging buffers: the cp.async copies of chunk c+1 are in flight while chunk c is multiplied.
-  const int ca = min(TMO / 4, (U.m_valid + 3) >> 2), cb = min(TNO / 4, (U.n_valid + 3) >> 2), cab = ca + cb;
+  const bool full = (U.m0 + TMO <= U.lda) && (U.n0 + TNO <= U.ldb);
+  const int ca = full ? TMO / 4 : min(TMO / 4, (U.m_valid + 3) >> 2), cb = full ? TNO / 4 : min(TNO / 4, (U.n_valid + 3) >> 2);
   constexpr int kBuf = kGChunk * (TMO + TNO);
   __syncthreads();
-  if (cab < (TMO + TNO) / 4) {
+  if (ca + cb < (TMO + TNO) / 4) {
     for (int t = tid; t < 2 * kBuf; t += kThreads) stage[t] = 0.f;
     __syncthreads();
   }
+  // division-free copy schedule: a thread keeps one 16-byte column slot of the staged row and walks down the rows
+  constexpr int CH = (TMO + TNO) / 4, SL = (CH <= 8) ? 8 : 16, RPP = kThreads / SL;
+  const int slot = tid & (SL - 1), row0 = tid / SL;
+  const bool a_slot = slot < TMO / 4;
+  const int cc = a_slot ? slot : slot - TMO / 4;
+  const bool slot_on = a_slot ? (cc < ca) : (slot < CH && cc < cb);
+  const float* src0 = a_slot ? U.A + U.m0 + 4 * cc : U.Bm + U.n0 + 4 * cc;
+  const int src_ld = a_slot ? U.lda : U.ldb;
+  const int dst_off = a_slot ? 4 * cc : kGChunk * TMO + 4 * cc, dst_ld = a_slot ? TMO : TNO;
   auto issue = [&](long long b0, float* buf) {
     const int rows = static_cast<int>(min(static_cast<long long>(kGChunk), S.B - b0));
-    float* As = buf;
-    float* Bs = buf + kGChunk * TMO;
-    for (int t = tid; t < rows * cab; t += kThreads) {      // LDGSTS: all copies of the chunk in flight at once
-      const int r = t / cab, c = t - r * cab;
-      if (c < ca) cp_async16(As + r * TMO + 4 * c, U.A + (b0 + r) * U.lda + U.m0 + 4 * c);
-      else cp_async16(Bs + r * TNO + 4 * (c - ca), U.Bm + (b0 + r) * U.ldb + U.n0 + 4 * (c - ca));
+    if (slot_on) {
+      const float* src = src0 + (b0 + row0) * src_ld;
+      float* dst = buf + dst_off + row0 * dst_ld;
+#pragma unroll 4
+      for (int r = row0; r < rows; r += RPP, src += RPP * src_ld, dst += RPP * dst_ld) cp_async16(dst, src);   // LDGSTS, all in flight
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
@@ -358,20 +401,28 @@ __device__ void wgrad_unit(const AgentCtx& C, const StepScalars& S, const GemmUn
     for (int j = 0; j < LN; ++j) Pb[warp * TNO + ng * LN + j] = bsum[j];
   }
   __syncthreads();
+  // gradients of this thread's outputs, then Adam / Polyak for all of them together (interleaved sqrt / division chains)
+  float gq[NOUT];
+  ParamVals po[NOUT];
+#pragma unroll
+  for (int q = 0; q < NOUT; ++q) {
+    float g = 0.f;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) g += Ps[w * (TMO * TNO) + ps_off[q]];
+    gq[q] = g;
+  }
+  param_math_n<NOUT>(S, gq, pv, po);
 #pragma unroll
   for (int q = 0; q < NOUT; ++q) {
     if (pi[q] >= 0) {
-      float g = 0.f;
-#pragma unroll
-      for (int w = 0; w < kWarps; ++w) g += Ps[w * (TMO * TNO) + ps_off[q]];
-      C.grads[pi[q]] = g;
-      param_apply(C, S, pi[q], g, pv[q]);
+      C.grads[pi[q]] = gq[q];
+      param_store(C, S, pi[q], po[q]);
     }
   }
   if (pb >= 0) {
     float g = 0.f;
 #pragma unroll
-    for (int w = 0; w < kWarps; ++w) g += Pb[w * TNO + tid];
+    for (int w = 0; w < kWarps; ++w) g += Pb[w * TNO + bt];
     C.grads[pb] = g;
     param_apply(C, S, pb, g, pvb);
   }
@@ -419,14 +470,16 @@ __device__ void wgrad_run_unit(const AgentCtx& C, const StepScalars& S, int u, b
 
 // ------------------------------------------------------------------ the fused learner step
 // Layout of AgentCtx::qt_flag (kFlagWords u32 per agent):
-//   [0, 512)      Q_target hand-off: epoch of the launch whose Q_target(s') of tile t is in QT
+//   [0, 512)      (unused)
 //   [512, 1024)   per tile {epoch, loss partial}            (early write-back, 8-byte words)
 //   [1024, 4096)  per batch row {epoch, |td|}               (early write-back, 8-byte words)
+//   [4096, ...)   per (tile, row, action) {epoch, Q_target(s')}   (role split: target CTA -> row CTA)
 // The 8-byte words carry their payload WITH the flag (one relaxed vector store), so publishing them needs no fence on
 // the row CTA's critical path; the stores they must be ordered after (leaf indices and old leaf values from the
 // sampling phase) are covered by a fence that the publishing warp executes while warp 0 computes the TD block.
-constexpr int kLossWordBase = 512, kTdWordBase = 1024;
-constexpr int kEarlyMaxRows = (kFlagWords - kTdWordBase) / 2;
+constexpr int kLossWordBase = 512, kTdWordBase = 1024, kQtWordBase = 4096;   // [4096, 4096 + 2*74*64): {epoch, Q_target} per (tile, row, action)
+constexpr int kEarlyMaxRows = (kQtWordBase - kTdWordBase) / 2;
+static_assert(kQtWordBase + 2 * 74 * kTM * kQLD <= kFlagWords, "flag words");
 __device__ __forceinline__ void st_relaxed_pair(unsigned* p, unsigned a, unsigned b) {
   asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(a), "r"(b) : "memory");
 }
@@ -670,11 +723,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, c
         }
         __syncthreads();
       }
-      if (is_tgt) {      // publish Q_target(s') of the tile: data, fence, flag (release) -- then on to phase B
-        __threadfence();
-        __syncthreads();
-        if (tid == 0) st_release_u32(C.qt_flag + tile0, S.epoch);
-      }
+      // publish Q_target(s') of the tile as {epoch, value} words (payload rides with the flag: no fence, one round trip
+      // on the consumer's side) -- then on to phase B
+      if (is_tgt && tid < kTM * kQLD) st_relaxed_pair(C.qt_flag + kQtWordBase + 2 * (tile0 * kTM * kQLD + tid), S.epoch, __float_as_uint(sQT[tid]));
       // -------- pass 2: online weights; [s'; s] rows
       RMC_STAMP(C, 3);
       if (!split) {
@@ -704,9 +755,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, c
         mlp_forward<kR>(sW, L, sXT, sH1T, sH2, sPart, sQ, nullptr);
         RMC_STAMP(C, 13);
         if (split) {     // Q_target(s') of this tile comes from its partner CTA
-          if (tid == 0) while (ld_acquire_u32(C.qt_flag + tile) != S.epoch) __nanosleep(20);
-          __syncthreads();
-          if (tid < kTM * kQLD) sQT[tid] = __ldcg(C.QT + tile * kTM * kQLD + tid);
+          if (tid < kTM * kQLD) {
+            const unsigned* wp = C.qt_flag + kQtWordBase + 2 * (tile * kTM * kQLD + tid);
+            uint2 w = ld_relaxed_pair(wp);
+            while (w.x != S.epoch) { __nanosleep(20); w = ld_relaxed_pair(wp); }
+            sQT[tid] = __uint_as_float(w.y);
+          }
           __syncthreads();
         }
         // early write-back: the publishing lanes order the sampling-phase stores of this CTA (nodes, leaf_p; made visible to
@@ -874,7 +928,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, c
     unsigned long long* tdbg = C.dbg ? C.dbg + (blockIdx.y * gridDim.x + blockIdx.x) * 16 : nullptr;
     if (team) {
       tree_update_team(C.rp, C.nodes, td_src, td_stride, C.pri, B, tsize, (S.phases & 1) ? C.leaf_p : nullptr, S.per_eps, S.per_alpha,
-                       S.per_pmax, cta - n_workers, reinterpret_cast<double*>(smem), tdbg);
+                       S.per_pmax, cta - n_workers, (S.phases & 1) != 0, reinterpret_cast<double*>(smem), tdbg);
     } else {
       // |td| -> priority for the whole batch here (off the row CTAs' critical path), then the write-back
       for (long long i = tid; i < B; i += kThreads) C.pri[i] = td_to_priority(__ldcg(td_src + i * td_stride), S.per_eps, S.per_alpha, S.per_pmax);

@@ -299,7 +299,7 @@ __device__ __forceinline__ int depth3_owner(long long node) {
 
 __device__ void tree_update_team(const ReplayDev& R, const long long* __restrict__ nodes, const float* __restrict__ abs_td, int td_stride,
                                  float* __restrict__ pri_out, long long n, long long size, const double* __restrict__ old_vals,
-                                 float eps, float alpha, float pmax, int member, double* s_top_buf, unsigned long long* dbg) {
+                                 float eps, float alpha, float pmax, int member, bool sorted, double* s_top_buf, unsigned long long* dbg) {
   __shared__ float s_f[64];
   __shared__ int s_i[64];
   __shared__ float s_loc[2];
@@ -308,32 +308,52 @@ __device__ void tree_update_team(const ReplayDev& R, const long long* __restrict
   const int tid = threadIdx.x, nt = blockDim.x, warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
   const long long first_leaf = R.cap - 1;
   const float M0 = R.st->max_p, m0 = R.st->min_p;      // extremes before this batch (size > 0 here)
-  // pass 0: my samples -> priority, election stamp
+  // Election of the writer of a leaf that occurs several times in the batch (the reference applies the updates in batch
+  // order, so the last one wins).  `sorted`: the leaves were drawn by THIS launch's stratified sampler -- stratum values
+  // are non-decreasing in the sample index (v_i <= seg*(i+1) <= v_{i+1}: hi - lo is exact by Sterbenz, rounding is monotone)
+  // and the descent is monotone in v, so equal leaves are adjacent and sample i is the writer iff leaf[i+1] != leaf[i].
+  // No stamps, no atomics, no extra round trip.  Otherwise (leaves from an earlier call): atomicMax stamps, two passes.
+  if (!sorted) {
+    for (long long i = tid; i < n; i += nt) {
+      const long long leaf = __ldcg(nodes + i);
+      if (depth3_owner(leaf) == member) {
+        pri_out[i] = td_to_priority(__ldcg(abs_td + i * td_stride), eps, alpha, pmax);
+        atomicMax(R.stamps + (leaf - first_leaf), static_cast<int>(i + 1));
+      }
+    }
+    __syncthreads();
+  }
+  RMC_TSTAMP(9);
+  // pass 1: elected writers apply (atomics only below the top 9 levels); local extremes of the new values.
+  // The thread's first sample stays in registers for pass 2 (the whole batch when n <= blockDim); later ones go through
+  // the L2-resident scratch.
+  float bmax = 0.f, bmin = finf();
+  float r_old = -3.f, r_p = 0.f;                       // -3: not mine, -2: mine but not the writer, else the overwritten value
   for (long long i = tid; i < n; i += nt) {
     const long long leaf = __ldcg(nodes + i);
+    float oldv = -3.f, p = 0.f;
     if (depth3_owner(leaf) == member) {
-      pri_out[i] = td_to_priority(__ldcg(abs_td + i * td_stride), eps, alpha, pmax);
-      atomicMax(R.stamps + (leaf - first_leaf), static_cast<int>(i + 1));
-    }
-  }
-  __syncthreads();
-  RMC_TSTAMP(9);
-  // pass 1: elected writers apply (atomics only below the top 9 levels); local extremes of the new values
-  float bmax = 0.f, bmin = finf();
-  for (long long i = tid; i < n; i += nt) {
-    const long long leaf = nodes[i];
-    float oldv = -2.f;
-    if (depth3_owner(leaf) == member) {
-      int* st = R.stamps + (leaf - first_leaf);
-      if (__ldcg(st) == static_cast<int>(i + 1)) {
-        *st = 0;
-        const float p = pri_out[i];
+      oldv = -2.f;
+      bool writer;
+      if (sorted) {
+        const long long next = (i + 1 < n) ? __ldcg(nodes + i + 1) : -1;
+        p = td_to_priority(__ldcg(abs_td + i * td_stride), eps, alpha, pmax);
+        pri_out[i] = p;
+        writer = next != leaf;
+      } else {
+        int* st = R.stamps + (leaf - first_leaf);
+        writer = __ldcg(st) == static_cast<int>(i + 1);
+        if (writer) *st = 0;
+        p = pri_out[i];
+      }
+      if (writer) {
         oldv = static_cast<float>(tree_set_leaf(R, leaf, p, old_vals ? old_vals + i : nullptr, kTopRebuild));
         bmax = fmaxf(bmax, p);
         bmin = fminf(bmin, p);
       }
-      R.scratch_old[i] = oldv;
+      if (i >= nt) R.scratch_old[i] = oldv;
     }
+    if (i < nt) { r_old = oldv; r_p = p; }
   }
   bmax = warp_max(bmax);
   bmin = warp_min(bmin);
@@ -348,7 +368,11 @@ __device__ void tree_update_team(const ReplayDev& R, const long long* __restrict
   RMC_TSTAMP(10);
   const float Mt = s_loc[0], mt = s_loc[1];
   int a = 0, b = 0, c = 0, d = 0;   // new==Mt, old==M0, new==mt, old==m0
-  for (long long i = tid; i < n; i += nt) {
+  if (r_old > -2.f) {
+    a += (r_p == Mt); c += (r_p == mt);
+    b += (r_old == M0); d += (r_old == m0);
+  }
+  for (long long i = tid + nt; i < n; i += nt) {
     if (depth3_owner(nodes[i]) == member) {
       const float oldv = R.scratch_old[i];
       if (oldv != -2.f) {
@@ -360,10 +384,11 @@ __device__ void tree_update_team(const ReplayDev& R, const long long* __restrict
   }
   a = warp_sum(a); b = warp_sum(b); c = warp_sum(c); d = warp_sum(d);
   if (lane == 0) { s_i[warp] = a; s_i[8 + warp] = b; s_i[16 + warp] = c; s_i[24 + warp] = d; }
-  __threadfence();          // this thread's leaf stores / reductions are performed before the team hand-off
+  __threadfence();          // this thread's leaf stores / reductions are performed before the local rebuild reads them
   __syncthreads();
   // Local part of the top rebuild: levels 8..3 under this member's depth-3 node depend only on its own level-9
-  // nodes (64 of them), which no other member touches -- done here, off the last arriver's tail.
+  // nodes (64 of them), which no other member touches -- done here, off the last arriver's tail.  Warp 1 meanwhile
+  // posts this member's share of the extremes.
   if (warp == 0) {
     const long long d3 = 7 + member;                              // heap index of the member's depth-3 node
     const long long first9 = ((d3 + 1) << 6) - 1;                 // its 64 descendants at depth 9
@@ -380,16 +405,16 @@ __device__ void tree_update_team(const ReplayDev& R, const long long* __restrict
       first = ((d3 + 1) << (lvl - 3)) - 1;
       if (lane < width) R.tree[first + lane] = sum;
     }
-    __threadfence();
-  }
-  __syncthreads();
-  if (tid == 0) {
+  } else if (tid == 32) {
     int ta = 0, tb = 0, tc = 0, td = 0;
     for (int w = 0; w < nw; ++w) { ta += s_i[w]; tb += s_i[8 + w]; tc += s_i[16 + w]; td += s_i[24 + w]; }
     TeamPart tp;
     tp.bmax = Mt; tp.bmin = mt; tp.cnt_bmax = ta; tp.cnt_bmin = tc; tp.old_eq_max = tb; tp.old_eq_min = td; tp.pad[0] = tp.pad[1] = 0;
     R.team_part[member] = tp;
-    __threadfence();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();        // the rebuilt levels and the TeamPart (ordered before this by the barrier) precede the arrival
     const unsigned prev = atomicAdd(R.team_ctr, 1u);
     s_last = (prev == kTreeTeam - 1) ? 1 : 0;
     if (s_last) { *R.team_ctr = 0u; __threadfence(); }
@@ -420,9 +445,7 @@ __device__ void tree_update_team(const ReplayDev& R, const long long* __restrict
     R.st->max_p = M1; R.st->min_p = m1; R.st->cnt_max = cM; R.st->cnt_min = cm;
     s_i[63] = (cM <= 0 || cm <= 0) ? 1 : 0;
   }
-  __syncthreads();
-  if (s_i[63]) extremes_rescan_cta(R, size, s_f, s_i);
-  if (tid == 0) {      // levels 2..0 from the eight depth-3 nodes the members have just rebuilt
+  if (tid == 32) {     // meanwhile: levels 2..0 from the eight depth-3 nodes the members have just rebuilt
     double v[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) v[k] = __ldcg(R.tree + 7 + k);
@@ -432,6 +455,8 @@ __device__ void tree_update_team(const ReplayDev& R, const long long* __restrict
     R.tree[1] = l1[0]; R.tree[2] = l1[1];
     R.tree[0] = l1[0] + l1[1];
   }
+  __syncthreads();
+  if (s_i[63]) extremes_rescan_cta(R, size, s_f, s_i);
   RMC_TSTAMP(12);
 #undef RMC_TSTAMP
 }
