@@ -311,7 +311,8 @@ __device__ void tree_update_team(const ReplayDev& R, const long long* __restrict
   // Election of the writer of a leaf that occurs several times in the batch (the reference applies the updates in batch
   // order, so the last one wins).  `sorted`: the leaves were drawn by THIS launch's stratified sampler -- stratum values
   // are non-decreasing in the sample index (v_i <= seg*(i+1) <= v_{i+1}: hi - lo is exact by Sterbenz, rounding is monotone)
-  // and the descent is monotone in v, so equal leaves are adjacent and sample i is the writer iff leaf[i+1] != leaf[i].
+  // and the descent is monotone in v (the drawn leaves move left to right through the tree; their heap INDEX need not grow
+  // when the capacity is not a power of two), so equal leaves are adjacent and sample i is the writer iff leaf[i+1] != leaf[i].
   // No stamps, no atomics, no extra round trip.  Otherwise (leaves from an earlier call): atomicMax stamps, two passes.
   if (!sorted) {
     for (long long i = tid; i < n; i += nt) {
