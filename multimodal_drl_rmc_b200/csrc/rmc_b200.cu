@@ -1568,7 +1568,7 @@ static int32_t infer_launch(rmc_learner* l, const float* params, const float* ob
       l->big_ready = true;
     }
     const long long big_tiles = (n + kBigRows - 1) / kBigRows;
-    k_mlp_infer64<<<static_cast<unsigned>(std::min<long long>(big_tiles, l->num_sms)), kThreads, static_cast<size_t>(big_bytes), st>>>(
+    k_mlp_infer64<<<static_cast<unsigned>(std::min<long long>(big_tiles, l->num_sms)), kBigThreads, static_cast<size_t>(big_bytes), st>>>(
         l->L, params, obs_dev, n, actions, q, mode);
     RMC_KERNEL_OK();
     return RMC_OK;

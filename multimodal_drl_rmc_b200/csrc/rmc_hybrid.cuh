@@ -302,6 +302,38 @@ __global__ void __launch_bounds__(256) k_hyb_heads_fwd(HybNet N, const float* __
   float* rec = rec_base + r * N.rec;
   const float* h = rec + N.last_off;
   float out = 0.f;
+  if (N.last_len <= 256) {
+    // every head's weights are requested before the first reduction (the dot products are latency-, not bandwidth-shaped);
+    // per head the same order as below: k = lane, lane + 32, ... then the xor tree
+    float hv[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) hv[j] = (lane + 32 * j < N.last_len) ? h[lane + 32 * j] : 0.f;
+#pragma unroll
+    for (int a0 = 0; a0 < kQLD; a0 += 4) {
+      float wv[4][8];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int a = a0 + u;
+        const float* w = N.dueling ? (a == 0 ? P + N.hw_off[0] : P + N.hw_off[1] + (a - 1) * N.last_len) : P + N.hw_off[0] + a * N.last_len;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) wv[u][j] = (a < N.NH && lane + 32 * j < N.last_len) ? __ldg(w + lane + 32 * j) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int a = a0 + u;
+        if (a < N.NH) {
+          float s = 0.f;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (lane + 32 * j < N.last_len) s = fmaf(hv[j], wv[u][j], s);
+#pragma unroll
+          for (int sh = 16; sh > 0; sh >>= 1) s += __shfl_xor_sync(0xffffffffu, s, sh);
+          const float b = N.dueling ? (a == 0 ? __ldg(P + N.hb_off[0]) : __ldg(P + N.hb_off[1] + a - 1)) : __ldg(P + N.hb_off[0] + a);
+          if (lane == a) out = s + b;
+        }
+      }
+    }
+  } else
   for (int a = 0; a < N.NH; ++a) {
     const float* w = N.dueling ? (a == 0 ? P + N.hw_off[0] : P + N.hw_off[1] + (a - 1) * N.last_len) : P + N.hw_off[0] + a * N.last_len;
     float s = 0.f;

@@ -49,6 +49,27 @@ def test_act_65536_states_vs_oracle():
     assert all((top2[i, 1] - top2[i, 0]) < 1e-5 for i in flips)
 
 
+@pytest.mark.parametrize("dueling,D,n", [(True, 14, 2048 + 5), (False, 8, 1024), (True, 8, 4096 + 63)])
+def test_q_values_through_the_64_row_kernel(dueling, D, n):
+    """n >= 1024 takes k_mlp_infer64 (8 x 8 register tiles, K of layer 2 split over the two halves of the CTA):
+    Q values within 1e-5 of the oracle, greedy actions equal except exact near-ties; ragged last tile."""
+    from multimodal_drl_rmc_b200 import Networks
+    from multimodal_drl_rmc_b200.macro_config import ObsSpace, network_config
+    torch.manual_seed(5)
+    cls = Networks.DuelingDeepQNetwork if dueling else Networks.DeepQNetwork
+    net = cls(torch.device("cuda:0"), 1e-4, network_config, ObsSpace(D), 8)
+    orc = O.OracleQNet(D, 8, dueling=dueling)
+    orc.load_state_dict({k: v.cpu() for k, v in net.state_dict().items()})
+    x = np.random.default_rng(2).random((n, D), dtype=np.float32)
+    with torch.no_grad():
+        qref = orc(torch.as_tensor(x)).numpy()
+    q = net(torch.as_tensor(x)).cpu().numpy()
+    assert q.shape == qref.shape
+    assert R.max_rel(q, qref) < 1e-5
+    ref, got = np.asarray(orc.greedy(x)), np.asarray(net.actions(x))
+    assert (ref != got).mean() <= 1e-3
+
+
 def test_plain_head_act_and_q():
     from multimodal_drl_rmc_b200 import Networks
     from multimodal_drl_rmc_b200.macro_config import ObsSpace, network_config
