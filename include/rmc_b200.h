@@ -257,7 +257,10 @@ int32_t rmc_learner_act(rmc_learner_t* l, const float* obs_dev, int64_t n, int64
  * greedy actions equal except near-ties (stated looser bound of the north star).  obs_dim <= 16. */
 int32_t rmc_learner_act_tc(rmc_learner_t* l, const float* obs_dev, int64_t n, int64_t* actions_dev, rmc_stream_t s);
 int32_t rmc_learner_heads_tc(rmc_learner_t* l, const float* obs_dev, int64_t n, float* heads_out_dev, rmc_stream_t s);
-/* same with host buffers (H2D + kernel + D2H, synchronises): what Agent.choose_actions calls. */
+/* same with host buffers (synchronises): what Agent.choose_actions calls once per environment step (dqn/agent.py:92-99).
+ * n <= 32 states of the macro MLP (the n_env of train.py): one launch, no copies -- the states travel in the kernel-argument
+ * buffer and the actions come back through mapped pinned host memory followed by the launch's epoch word.  Larger n:
+ * H2D + kernel + D2H + stream synchronisation. */
 int32_t rmc_learner_act_host_sync(rmc_learner_t* l, const float* obs_host, int64_t n, int64_t* actions_host,
                                   rmc_stream_t s);
 /* Agent.choose_actions (dqn/agent.py:92-99) in one call for vectorised envs: greedy act, then row i explores with

@@ -160,8 +160,9 @@ class Agent:
                                                       int(self.sampling_seed) ^ 0xAC7, self._act_calls, stream_ptr(self._dev_index)))
             return out.tolist()
         actions = self.online_network.actions(obses)
+        eps = self.epsilon()          # the reference re-evaluates it per env; `step` does not move inside the call, so once is the same value
         for i in range(len(actions)):
-            if random.random() <= self.epsilon():
+            if random.random() <= eps:
                 actions[i] = random.randint(0, self.output_dim - 1)
         return actions
 

@@ -140,6 +140,9 @@ struct rmc_learner {
   // act staging
   float* act_pin_obs = nullptr; long long* act_pin_out = nullptr; float* act_dev_obs = nullptr; long long* act_dev_out = nullptr;
   long long act_cap = 0;
+  // per-env-step act (k_act_tiny): mapped pinned host words [0..kActTinyMax) actions, [kActTinyMax] epoch; device view; arrival counter
+  volatile long long* act_map_host = nullptr; long long* act_map_dev = nullptr; unsigned* act_ctr = nullptr; unsigned act_epoch = 0;
+  int act_map_state = 0;   // 0 = not tried, 1 = ready, -1 = unavailable (falls back to the copy path)
   std::vector<void*> owned;
 };
 
@@ -636,6 +639,8 @@ extern "C" int32_t rmc_learner_destroy(rmc_learner_t* l) {
   if (l->act_pin_obs) cudaFreeHost(l->act_pin_obs);
   if (l->act_pin_out) cudaFreeHost(l->act_pin_out);
   if (l->host_loss) cudaFreeHost(const_cast<float*>(l->host_loss));
+  if (l->act_map_host) cudaFreeHost(const_cast<long long*>(l->act_map_host));
+  if (l->act_ctr) cudaFree(l->act_ctr);
   if (l->tc_side) { cudaStreamDestroy(l->tc_side); for (auto& ev : l->tc_ev) if (ev) cudaEventDestroy(ev); }
   if (l->hyb_side) { cudaStreamDestroy(l->hyb_side); for (auto& ev : l->hyb_ev) if (ev) cudaEventDestroy(ev); }
   cudaFree(l->act_dev_obs);
@@ -1645,6 +1650,44 @@ static int32_t act_host_impl(rmc_learner_t* l, const float* obs_host, int64_t n,
   if (!l || !obs_host || !actions_host || n < 1) return fail(RMC_ERR_ARG, "rmc_learner_act_host_sync: bad args");
   if (int32_t e = use_device(l->device)) return e;
   cudaStream_t st = as_stream(s);
+  if (n <= kActTinyMax && !l->hybrid && l->L.D <= 16 && l->act_map_state >= 0) {
+    if (l->act_map_state == 0) {
+      long long* hp = nullptr; long long* dp = nullptr;
+      if (cudaHostAlloc(reinterpret_cast<void**>(&hp), (kActTinyMax + 1) * sizeof(long long), cudaHostAllocMapped) == cudaSuccess &&
+          cudaHostGetDevicePointer(reinterpret_cast<void**>(&dp), hp, 0) == cudaSuccess && dev_alloc(&l->act_ctr, 1) == RMC_OK &&
+          cudaFuncSetAttribute(k_act_tiny, cudaFuncAttributeMaxDynamicSharedMemorySize, l->smem_bytes) == cudaSuccess) {
+        std::memset(hp, 0, (kActTinyMax + 1) * sizeof(long long));
+        l->act_map_host = hp; l->act_map_dev = dp; l->act_map_state = 1;
+      } else {
+        cudaGetLastError();
+        if (hp) cudaFreeHost(hp);
+        l->act_map_state = -1;
+      }
+    }
+    if (l->act_map_state == 1) {
+      ActTinyObs X;
+      std::memcpy(X.v, obs_host, static_cast<size_t>(n) * l->L.D * sizeof(float));
+      l->act_epoch = (l->act_epoch >= 0x7fffffffu) ? 1u : l->act_epoch + 1u;
+      const unsigned want = l->act_epoch;
+      volatile unsigned* host_epoch = reinterpret_cast<volatile unsigned*>(l->act_map_host + kActTinyMax);
+      k_act_tiny<<<blocks_for(n, kR), kThreads, static_cast<size_t>(l->smem_bytes), st>>>(
+          l->L, l->blobs[RMC_ONLINE], X, static_cast<int>(n), eps, seed, counter, l->act_map_dev,
+          reinterpret_cast<unsigned*>(l->act_map_dev + kActTinyMax), l->act_ctr, want);
+      RMC_KERNEL_OK();
+      bool got = false;
+      for (long long spin = 0; spin < 200000000ll && !got; ++spin) {
+        got = (*host_epoch == want);
+        if (!got && (spin & 0xfff) == 0xfff && cudaStreamQuery(st) != cudaErrorNotReady) break;   // finished or faulted
+      }
+      if (!got) {
+        RMC_CUDA(cudaStreamSynchronize(st));
+        if (*host_epoch != want) return fail(RMC_ERR_CUDA, "rmc_learner_act_host_sync: the act kernel did not publish its result");
+      }
+      std::atomic_thread_fence(std::memory_order_acquire);
+      for (int64_t i = 0; i < n; ++i) actions_host[i] = l->act_map_host[i];
+      return RMC_OK;
+    }
+  }
   if (n > l->act_cap) {
     RMC_CUDA(cudaStreamSynchronize(st));
     if (l->act_pin_obs) cudaFreeHost(l->act_pin_obs);

@@ -1018,6 +1018,62 @@ __global__ void __launch_bounds__(kThreads, 1) k_mlp_infer(NetLayout L, const fl
   }
 }
 
+// ------------------------------------------------------------------ per-env-step act (n <= kActTinyMax host states)
+// The call the trainer makes once per environment step (train.py:91-93 -> Agent.choose_actions) with n_env state vectors.
+// Both copies and the stream synchronisation of the general path are gone: the states ride in the kernel-argument buffer,
+// the actions are stored straight into mapped pinned host memory, and the launch's epoch follows them (system fence in
+// between), so the host waits on one word.  Same arithmetic as k_mlp_infer mode 0 and the same Philox epsilon-greedy draw
+// as k_eps_greedy (eps < 0: greedy only).  One CTA per 8 rows; the last CTA to finish publishes the epoch.
+constexpr int kActTinyMax = 32;
+struct ActTinyObs { float v[kActTinyMax * 16]; };     // [n][D] packed, D <= 16
+__device__ __forceinline__ long long eps_greedy_pick(long long greedy, long long i, float eps, int n_actions, unsigned long long seed,
+                                                     unsigned long long counter) {
+  const uint4 r = philox4x32_10(make_uint4(static_cast<uint32_t>(i), static_cast<uint32_t>(i >> 32), static_cast<uint32_t>(counter), static_cast<uint32_t>(counter >> 32)),
+                                make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32) ^ 0x9E3779B9u));
+  const float u1 = static_cast<float>(r.x >> 8) * (1.0f / 16777216.0f);
+  return (u1 <= eps) ? static_cast<long long>((static_cast<unsigned long long>(r.y) * static_cast<unsigned long long>(n_actions)) >> 32) : greedy;
+}
+__global__ void __launch_bounds__(kThreads, 1) k_act_tiny(NetLayout L, const float* __restrict__ params, const __grid_constant__ ActTinyObs X, int n,
+                                                          float eps, unsigned long long seed, unsigned long long counter,
+                                                          volatile long long* host_actions, volatile unsigned* host_epoch, unsigned* ctr, unsigned epoch) {
+  extern __shared__ __align__(16) float smem[];
+  const SmemPlan P = make_smem_plan(L.total);
+  float* sW = smem + P.w;
+  float* sXT = smem + P.xt;
+  float* sRaw = smem + P.dz2;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + P.bar);
+  const int tid = threadIdx.x, D = L.D;
+  uint32_t parity = 0;
+  if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+  __syncthreads();
+  stage_params(sW, params, L.total, bar, parity);
+  const int row0 = blockIdx.x * kR;
+  for (int t = tid; t < kR * D; t += kThreads) {
+    const int r = t / D, d = t - r * D;
+    sXT[d * kR + r] = (row0 + r < n) ? X.v[(row0 + r) * D + d] : 0.f;
+  }
+  wait_params(bar, parity);
+  __syncthreads();
+  mlp_forward<kR>(sW, L, sXT, smem + P.h1t, smem + P.h2, smem + P.part, smem + P.q, sRaw);
+  if (tid < kR && row0 + tid < n) {
+    const long long i = row0 + tid;
+    long long a = L.dueling ? argmax_first(sRaw + tid * kQLD + 1, L.A) : argmax_first(smem + P.q + tid * kQLD, L.A);
+    if (eps >= 0.f) a = eps_greedy_pick(a, i, eps, L.A, seed, counter);
+    host_actions[i] = a;
+    __threadfence_system();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    const unsigned prev = atomicAdd(ctr, 1u);
+    if (prev == gridDim.x - 1) {
+      *ctr = 0u;
+      __threadfence_system();
+      *host_epoch = epoch;
+    }
+  }
+}
+
 // epsilon-greedy on the device (Agent.choose_actions, dqn/agent.py:92-99): row i explores when u1 <= eps and then takes
 // floor(u2 * A); (u1, u2) = Philox4x32-10(seed, counter, i).  The reference draws from Python's Mersenne Twister, so this
 // mode reproduces its distribution, not its stream (the host-RNG mode of Agent.choose_actions reproduces the stream).

@@ -70,6 +70,27 @@ def test_q_values_through_the_64_row_kernel(dueling, D, n):
     assert (ref != got).mean() <= 1e-3
 
 
+@pytest.mark.parametrize("dueling,D", [(True, 14), (False, 8)])
+def test_per_env_step_act_path_equals_the_batched_kernels(dueling, D):
+    """n <= 32 host states take k_act_tiny (states in the kernel-argument buffer, actions through mapped host memory):
+    same greedy actions as the oracle and as the general copy path, for every n around the 8-row tile and the 32-row limit."""
+    from multimodal_drl_rmc_b200 import Networks
+    from multimodal_drl_rmc_b200.macro_config import ObsSpace, network_config
+    torch.manual_seed(7)
+    cls = Networks.DuelingDeepQNetwork if dueling else Networks.DeepQNetwork
+    net = cls(torch.device("cuda:0"), 1e-4, network_config, ObsSpace(D), 8)
+    orc = O.OracleQNet(D, 8, dueling=dueling)
+    orc.load_state_dict({k: v.cpu() for k, v in net.state_dict().items()})
+    x = np.random.default_rng(4).random((200, D), dtype=np.float32)
+    ref = orc.greedy(x)
+    assert net.actions(x) == ref                                   # n = 200: copy path, 8-row kernel
+    for n in (1, 2, 7, 8, 9, 16, 31, 32, 33):
+        for off in (0, 50):
+            assert net.actions(x[off:off + n]) == ref[off:off + n], (n, off)
+    for _ in range(300):                                           # epoch hand-shake over many back-to-back calls
+        assert net.actions(x[:3]) == ref[:3]
+
+
 def test_plain_head_act_and_q():
     from multimodal_drl_rmc_b200 import Networks
     from multimodal_drl_rmc_b200.macro_config import ObsSpace, network_config
