@@ -481,6 +481,31 @@ def extra_workloads(agent):
                                "mode": "tcgen05 bf16 operands / fp32 TMEM accumulate (Q within 1e-2 of fp32; includes the per-call weight pack kernel)"}
     except Exception as exc:  # pragma: no cover
         out["act_65536"] = {"error": repr(exc)}
+    try:   # one iteration of train.py's loop through the public API, without the SUMO step (train.py:91-101):
+        # choose_actions(host state) -> store_transitions(host row) -> learn() -> update_target_network()
+        obs, act, rew, done, nxt = synthetic(2048, 4242)
+        n_it = 1000
+
+        def iteration(j):
+            a = agent.choose_actions(obs[j:j + 1])
+            agent.store_transitions(obs[j:j + 1], a, [float(rew[j])], [bool(done[j])], nxt[j:j + 1], None)
+            agent.step += 1
+            agent.learn(fuse_target_update=True)
+            agent.update_target_network()
+
+        for j in range(20):
+            iteration(j)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for j in range(n_it):
+            iteration(20 + j)
+        torch.cuda.synchronize()
+        us = 1e6 * (time.perf_counter() - t0) / n_it
+        out["train_iteration_api"] = {"us_per_iteration": us, "iterations_per_s": 1e6 / us,
+                                      "what": "choose_actions(1 host state) + store_transitions(1 host row) + learn() + update_target_network() per iteration, "
+                                              "n_env = 1, PER B=256 learner; the environment step itself (SUMO, CPU) is not included"}
+    except Exception as exc:  # pragma: no cover
+        out["train_iteration_api"] = {"error": repr(exc)}
     try:   # C1: repo defaults (B = 32, uniform replay)
         wl = WORKLOADS["default32"]
         a1, _ = build_gpu_agent(wl, agent.device.index, seed=11)
