@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "rmc_device.cuh"
@@ -58,16 +59,93 @@ struct PdlScope {
   explicit PdlScope(bool on) : prev(g_pdl_on) { g_pdl_on = on; }
   ~PdlScope() { g_pdl_on = prev; }
 };
+// Re-trace-and-patch CUDA graphs for launch-bound multi-kernel steps (the hybrid network: ~47 small kernels on two
+// streams per step).  Every kernel of such a step goes through launch_pdl(), so one host routine serves three modes:
+//   * ordinary        launch the kernel;
+//   * capturing (1)   launch it into a capturing stream and remember the node it became, with a copy of its arguments;
+//   * patching  (2)   do not launch: compare the arguments with the node's copy and, where they differ (step counters,
+//                     Adam bias corrections, sampling seeds, injected pointers), update that node of the instantiated
+//                     graph.  The caller then replays the whole step with ONE cudaGraphLaunch.
+// A kernel / grid that does not match the recorded sequence marks the trace invalid; the caller falls back to ordinary
+// launches and captures again.
+struct TraceRec {
+  cudaGraphNode_t node = nullptr;
+  const void* func = nullptr;
+  dim3 grid, block;
+  size_t smem = 0;
+  std::vector<unsigned char> bytes;      // the kernel arguments, back to back
+};
+struct StepGraph {
+  long long batch = 0; int phases = 0;
+  cudaGraph_t graph = nullptr;           // kept alive: the node handles of `recs` belong to it
+  cudaGraphExec_t exec = nullptr;
+  std::vector<TraceRec> recs;
+  void destroy() {
+    if (exec) cudaGraphExecDestroy(exec);
+    if (graph) cudaGraphDestroy(graph);
+    exec = nullptr; graph = nullptr;
+  }
+};
+struct Trace { int mode = 0; StepGraph* g = nullptr; size_t cursor = 0; bool ok = true; int patched = 0; };
+static thread_local Trace* g_trace = nullptr;
+
 template <typename... KArgs, typename... Args>
 static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
   static const bool enabled = [] { const char* e = std::getenv("RMC_PDL"); return !(e && e[0] == '0'); }();
+  std::tuple<std::decay_t<KArgs>...> packed(static_cast<KArgs>(args)...);
+  void* ptrs[sizeof...(KArgs) + 1];
+  size_t total = 0;
+  std::apply([&](auto&... a) { size_t i = 0; ((ptrs[i++] = static_cast<void*>(&a), total += sizeof(a)), ...); }, packed);
+  auto pack_bytes = [&](std::vector<unsigned char>& out) {
+    out.resize(total);
+    size_t off = 0;
+    std::apply([&](auto&... a) { ((std::memcpy(out.data() + off, &a, sizeof(a)), off += sizeof(a)), ...); }, packed);
+  };
+  if (g_trace != nullptr && g_trace->mode == 2) {
+    Trace& T = *g_trace;
+    if (!T.ok) return cudaSuccess;
+    if (T.cursor >= T.g->recs.size()) { T.ok = false; return cudaSuccess; }
+    TraceRec& R = T.g->recs[T.cursor++];
+    if (R.func != reinterpret_cast<const void*>(kernel) || R.grid.x != grid.x || R.grid.y != grid.y || R.grid.z != grid.z || R.block.x != block.x ||
+        R.smem != smem || R.bytes.size() != total) { T.ok = false; return cudaSuccess; }
+    bool same = true;
+    {
+      size_t off = 0;
+      std::apply([&](auto&... a) { ((same = same && std::memcmp(R.bytes.data() + off, &a, sizeof(a)) == 0, off += sizeof(a)), ...); }, packed);
+    }
+    if (same) return cudaSuccess;
+    cudaKernelNodeParams np{};
+    np.func = const_cast<void*>(R.func); np.gridDim = grid; np.blockDim = block; np.sharedMemBytes = static_cast<unsigned>(smem);
+    np.kernelParams = ptrs; np.extra = nullptr;
+    const cudaError_t e = cudaGraphExecKernelNodeSetParams(T.g->exec, R.node, &np);
+    if (e != cudaSuccess) { T.ok = false; cudaGetLastError(); return cudaSuccess; }
+    pack_bytes(R.bytes);
+    ++T.patched;
+    return cudaSuccess;
+  }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at; cfg.numAttrs = (enabled && g_pdl_on) ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+  const cudaError_t err = cudaLaunchKernelExC(&cfg, reinterpret_cast<const void*>(kernel), ptrs);
+  if (err == cudaSuccess && g_trace != nullptr && g_trace->mode == 1 && g_trace->ok) {
+    cudaStreamCaptureStatus status = cudaStreamCaptureStatusNone;
+    const cudaGraphNode_t* deps = nullptr;
+    size_t n_deps = 0;
+    if (cudaStreamGetCaptureInfo_v2(st, &status, nullptr, nullptr, &deps, &n_deps) != cudaSuccess || status != cudaStreamCaptureStatusActive ||
+        n_deps != 1) {
+      g_trace->ok = false;
+      cudaGetLastError();
+    } else {
+      TraceRec R;
+      R.node = deps[0]; R.func = reinterpret_cast<const void*>(kernel); R.grid = grid; R.block = block; R.smem = smem;
+      pack_bytes(R.bytes);
+      g_trace->g->recs.push_back(std::move(R));
+    }
+  }
+  return err;
 }
 
 static inline cudaStream_t as_stream(rmc_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
@@ -136,6 +214,9 @@ struct rmc_learner {
   HybNet H{};
   float *rec_on = nullptr, *rec_tg = nullptr, *drec = nullptr, *hyb_ws = nullptr, *hyb_ws2 = nullptr;
   cudaStream_t hyb_side = nullptr;          // second stream: target-network pass and the weight-gradient kernels
+  cudaStream_t hyb_cap = nullptr;           // origin stream of the step-graph captures (the caller's stream may be the legacy default stream)
+  std::vector<StepGraph> hyb_graphs;        // instantiated step graphs, one per (batch, phases)
+  bool hyb_graph_off = false;               // a capture failed on this handle: ordinary launches from then on
   cudaEvent_t hyb_ev[16] = {};
   // act staging
   float* act_pin_obs = nullptr; long long* act_pin_out = nullptr; float* act_dev_obs = nullptr; long long* act_dev_out = nullptr;
@@ -643,6 +724,8 @@ extern "C" int32_t rmc_learner_destroy(rmc_learner_t* l) {
   if (l->act_ctr) cudaFree(l->act_ctr);
   if (l->tc_side) { cudaStreamDestroy(l->tc_side); for (auto& ev : l->tc_ev) if (ev) cudaEventDestroy(ev); }
   if (l->hyb_side) { cudaStreamDestroy(l->hyb_side); for (auto& ev : l->hyb_ev) if (ev) cudaEventDestroy(ev); }
+  for (auto& g : l->hyb_graphs) g.destroy();
+  if (l->hyb_cap) cudaStreamDestroy(l->hyb_cap);
   cudaFree(l->act_dev_obs);
   cudaFree(l->act_dev_out);
   delete l;
@@ -1059,6 +1142,7 @@ extern "C" int32_t rmc_learner_create_hybrid(rmc_learner_t** out, const rmc_hybr
   if ((e = owned_alloc(l, &l->hyb_ws, static_cast<size_t>(kHybWsFloats)))) return e;
   if ((e = owned_alloc(l, &l->hyb_ws2, static_cast<size_t>(kHybWsFloats)))) return e;
   RMC_CUDA(cudaStreamCreateWithFlags(&l->hyb_side, cudaStreamNonBlocking));
+  RMC_CUDA(cudaStreamCreateWithFlags(&l->hyb_cap, cudaStreamNonBlocking));
   for (auto& ev : l->hyb_ev) RMC_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   {
     float* hp = nullptr;
@@ -1137,7 +1221,7 @@ static int32_t hybrid_forward(rmc_learner* l, const float* P, const HybSrc& src,
   return RMC_OK;
 }
 
-static int32_t hybrid_step(rmc_learner* l, rmc_replay* r, const rmc_step_args_t* a, StepScalars& S, cudaStream_t st) {
+static int32_t hybrid_step_body(rmc_learner* l, rmc_replay* r, const rmc_step_args_t* a, StepScalars& S, cudaStream_t st) {
   const PdlScope no_pdl(false);
   const HybNet& N = l->H;
   AgentCtx& C = l->ctx;
@@ -1163,6 +1247,7 @@ static int32_t hybrid_step(rmc_learner* l, rmc_replay* r, const rmc_step_args_t*
   int ev_next = 0;
   auto hand_over = [&](cudaStream_t from, cudaStream_t to) -> int32_t {     // `to` continues after everything queued on `from`
     if (from == to) return RMC_OK;
+    if (g_trace != nullptr && g_trace->mode == 2) return RMC_OK;             // patching a graph: the edges are already in it
     cudaEvent_t ev = l->hyb_ev[ev_next++ & 15];
     RMC_CUDA(cudaEventRecord(ev, from));
     RMC_CUDA(cudaStreamWaitEvent(to, ev, 0));
@@ -1251,6 +1336,59 @@ static int32_t hybrid_step(rmc_learner* l, rmc_replay* r, const rmc_step_args_t*
       if (int32_t e = tree_update_large(r, C.nodes, C.pri, B, false, st)) return e;
     }
   }
+  return RMC_OK;
+}
+
+// The training step of the hybrid network as ONE graph launch (see launch_pdl): the first full step of a (batch, phases)
+// shape is captured on an internal stream -- both streams of the body and their event edges included -- and instantiated;
+// later steps re-trace the body in patch mode (no launches: only the nodes whose arguments changed are updated) and replay
+// the graph on the caller's stream.  RMC_HYB_GRAPH=0 keeps ordinary launches.  Any mismatch or capture error falls back to
+// ordinary launches (the body's host-side counters may then advance twice for that step, which only invalidates caches).
+static int32_t hybrid_step(rmc_learner* l, rmc_replay* r, const rmc_step_args_t* a, StepScalars& S, cudaStream_t st) {
+  static const bool graphs = [] { const char* e = std::getenv("RMC_HYB_GRAPH"); return !(e && e[0] == '0'); }();
+  const int full = RMC_PH_FORWARD | RMC_PH_BACKWARD | RMC_PH_ADAM;
+  if (!graphs || l->hyb_graph_off || (a->phases & full) != full || a->precision != RMC_PREC_FP32) return hybrid_step_body(l, r, a, S, st);
+  StepGraph* g = nullptr;
+  for (auto& c : l->hyb_graphs)
+    if (c.batch == a->batch && c.phases == a->phases) g = &c;
+  if (g != nullptr) {
+    Trace T; T.mode = 2; T.g = g;
+    g_trace = &T;
+    const int32_t e = hybrid_step_body(l, r, a, S, st);
+    g_trace = nullptr;
+    static const bool dbg = std::getenv("RMC_HYB_GRAPH_DEBUG") != nullptr;
+    if (dbg) std::fprintf(stderr, "[rmc] hybrid graph replay: %zu kernels, %d nodes patched, trace %s\n", g->recs.size(), T.patched, T.ok ? "ok" : "MISMATCH");
+    if (e == RMC_OK && T.ok && T.cursor == g->recs.size()) {
+      RMC_CUDA(cudaGraphLaunch(g->exec, st));
+      return RMC_OK;
+    }
+    g->destroy();                                                   // the step changed shape: forget the graph, launch normally
+    l->hyb_graphs.erase(l->hyb_graphs.begin() + (g - l->hyb_graphs.data()));
+    if (e != RMC_OK) return e;
+    return hybrid_step_body(l, r, a, S, st);
+  }
+  if (l->hyb_graphs.size() >= 8) return hybrid_step_body(l, r, a, S, st);
+  StepGraph fresh; fresh.batch = a->batch; fresh.phases = a->phases;
+  Trace T; T.mode = 1; T.g = &fresh;
+  if (cudaStreamBeginCapture(l->hyb_cap, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+    cudaGetLastError();
+    l->hyb_graph_off = true;
+    return hybrid_step_body(l, r, a, S, st);
+  }
+  g_trace = &T;
+  const int32_t e = hybrid_step_body(l, r, a, S, l->hyb_cap);
+  g_trace = nullptr;
+  const cudaError_t ce = cudaStreamEndCapture(l->hyb_cap, &fresh.graph);
+  bool ok = (e == RMC_OK) && T.ok && ce == cudaSuccess && fresh.graph != nullptr;
+  if (ok) ok = cudaGraphInstantiate(&fresh.exec, fresh.graph, 0) == cudaSuccess;
+  if (!ok) {
+    cudaGetLastError();
+    fresh.destroy();
+    l->hyb_graph_off = true;
+    return hybrid_step_body(l, r, a, S, st);
+  }
+  l->hyb_graphs.push_back(std::move(fresh));
+  RMC_CUDA(cudaGraphLaunch(l->hyb_graphs.back().exec, st));
   return RMC_OK;
 }
 

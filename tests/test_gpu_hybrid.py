@@ -15,9 +15,9 @@ D = 284
 
 
 @pytest.mark.parametrize("algo,B,cap,fill,steps,soft,tf", [
-    ("PerDuelingDoubleDQNAgent", 32, 300, 400, 3, True, 30000),
+    ("PerDuelingDoubleDQNAgent", 32, 300, 400, 5, True, 30000),       # steps 2.. replay the captured step graph (patched nodes)
     ("DuelingDoubleDQNAgent", 16, 128, 128, 2, True, 30000),
-    ("DQNAgent", 24, 200, 150, 2, False, 2),
+    ("DQNAgent", 24, 200, 150, 4, False, 2),                          # hard sync every 2nd step: two step shapes, two graphs
     ("PerDuelingDoubleDQNAgent", 130, 512, 512, 1, True, 30000),
 ])
 def test_hybrid_learner_step_parity(algo, B, cap, fill, steps, soft, tf):
