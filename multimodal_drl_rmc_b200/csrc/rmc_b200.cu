@@ -1344,17 +1344,17 @@ static int32_t hybrid_step_body(rmc_learner* l, rmc_replay* r, const rmc_step_ar
 // later steps re-trace the body in patch mode (no launches: only the nodes whose arguments changed are updated) and replay
 // the graph on the caller's stream.  RMC_HYB_GRAPH=0 keeps ordinary launches.  Any mismatch or capture error falls back to
 // ordinary launches (the body's host-side counters may then advance twice for that step, which only invalidates caches).
-static int32_t hybrid_step(rmc_learner* l, rmc_replay* r, const rmc_step_args_t* a, StepScalars& S, cudaStream_t st) {
+template <typename Body>
+static int32_t run_step_graph(rmc_learner* l, long long key_batch, int key_phases, cudaStream_t st, Body body) {
   static const bool graphs = [] { const char* e = std::getenv("RMC_HYB_GRAPH"); return !(e && e[0] == '0'); }();
-  const int full = RMC_PH_FORWARD | RMC_PH_BACKWARD | RMC_PH_ADAM;
-  if (!graphs || l->hyb_graph_off || (a->phases & full) != full || a->precision != RMC_PREC_FP32) return hybrid_step_body(l, r, a, S, st);
+  if (!graphs || l->hyb_graph_off) return body(st);
   StepGraph* g = nullptr;
   for (auto& c : l->hyb_graphs)
-    if (c.batch == a->batch && c.phases == a->phases) g = &c;
+    if (c.batch == key_batch && c.phases == key_phases) g = &c;
   if (g != nullptr) {
     Trace T; T.mode = 2; T.g = g;
     g_trace = &T;
-    const int32_t e = hybrid_step_body(l, r, a, S, st);
+    const int32_t e = body(st);
     g_trace = nullptr;
     static const bool dbg = std::getenv("RMC_HYB_GRAPH_DEBUG") != nullptr;
     if (dbg) std::fprintf(stderr, "[rmc] hybrid graph replay: %zu kernels, %d nodes patched, trace %s\n", g->recs.size(), T.patched, T.ok ? "ok" : "MISMATCH");
@@ -1365,18 +1365,18 @@ static int32_t hybrid_step(rmc_learner* l, rmc_replay* r, const rmc_step_args_t*
     g->destroy();                                                   // the step changed shape: forget the graph, launch normally
     l->hyb_graphs.erase(l->hyb_graphs.begin() + (g - l->hyb_graphs.data()));
     if (e != RMC_OK) return e;
-    return hybrid_step_body(l, r, a, S, st);
+    return body(st);
   }
-  if (l->hyb_graphs.size() >= 8) return hybrid_step_body(l, r, a, S, st);
-  StepGraph fresh; fresh.batch = a->batch; fresh.phases = a->phases;
+  if (l->hyb_graphs.size() >= 16) return body(st);
+  StepGraph fresh; fresh.batch = key_batch; fresh.phases = key_phases;
   Trace T; T.mode = 1; T.g = &fresh;
   if (cudaStreamBeginCapture(l->hyb_cap, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
     cudaGetLastError();
     l->hyb_graph_off = true;
-    return hybrid_step_body(l, r, a, S, st);
+    return body(st);
   }
   g_trace = &T;
-  const int32_t e = hybrid_step_body(l, r, a, S, l->hyb_cap);
+  const int32_t e = body(l->hyb_cap);
   g_trace = nullptr;
   const cudaError_t ce = cudaStreamEndCapture(l->hyb_cap, &fresh.graph);
   bool ok = (e == RMC_OK) && T.ok && ce == cudaSuccess && fresh.graph != nullptr;
@@ -1385,15 +1385,28 @@ static int32_t hybrid_step(rmc_learner* l, rmc_replay* r, const rmc_step_args_t*
     cudaGetLastError();
     fresh.destroy();
     l->hyb_graph_off = true;
-    return hybrid_step_body(l, r, a, S, st);
+    return body(st);
   }
   l->hyb_graphs.push_back(std::move(fresh));
   RMC_CUDA(cudaGraphLaunch(l->hyb_graphs.back().exec, st));
   return RMC_OK;
 }
 
+static int32_t hybrid_step(rmc_learner* l, rmc_replay* r, const rmc_step_args_t* a, StepScalars& S, cudaStream_t st) {
+  const int full = RMC_PH_FORWARD | RMC_PH_BACKWARD | RMC_PH_ADAM;
+  if ((a->phases & full) != full || a->precision != RMC_PREC_FP32) return hybrid_step_body(l, r, a, S, st);
+  return run_step_graph(l, a->batch, a->phases, st, [&](cudaStream_t s_) { return hybrid_step_body(l, r, a, S, s_); });
+}
+
 // act / Q values / raw heads of n states [n][D] through the hybrid net (chunks of at most 2 * max_batch rows)
+static int32_t hybrid_infer_body(rmc_learner* l, const float* params, const float* obs_dev, long long n, long long* actions, float* q, int mode, cudaStream_t st);
 static int32_t hybrid_infer(rmc_learner* l, const float* params, const float* obs_dev, long long n, long long* actions, float* q, int mode, cudaStream_t st) {
+  // the per-env-step act of the trainer (a handful of rows, ~11 small kernels): one graph launch per call shape
+  if (n > 64) return hybrid_infer_body(l, params, obs_dev, n, actions, q, mode, st);
+  return run_step_graph(l, n, 0x40000000 | (mode << 2) | (actions ? 1 : 0) | (q ? 2 : 0), st,
+                        [&](cudaStream_t s_) { return hybrid_infer_body(l, params, obs_dev, n, actions, q, mode, s_); });
+}
+static int32_t hybrid_infer_body(rmc_learner* l, const float* params, const float* obs_dev, long long n, long long* actions, float* q, int mode, cudaStream_t st) {
   const PdlScope no_pdl(false);
   const HybNet& N = l->H;
   const long long cap = 2 * l->max_batch;

@@ -10,9 +10,17 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import bench  # noqa: E402
 
-wl = dict(bench.WORKLOADS["per256"])
-wl["size"] = wl["cap"] = 4096
-agent, _ = bench.build_gpu_agent(wl, 0, 0)
+HYBRID = len(sys.argv) > 1 and sys.argv[1] == "hybrid"      # the repo-HEAD CNN + MLP network (state[284]) instead of the macro MLP
+if HYBRID:
+    import tempfile
+    from multimodal_drl_rmc_b200 import macro_config
+    tmp = tempfile.mkdtemp(prefix="rmc_act_")
+    bench.D = macro_config.HYBRID_OBS_DIM
+    agent = macro_config.make_agent("DuelingDoubleDQNAgent", bench.D, 32, 4096, save_dir=tmp + "/", log_dir=tmp + "/", activation="hybrid")
+else:
+    wl = dict(bench.WORKLOADS["per256"])
+    wl["size"] = wl["cap"] = 4096
+    agent, _ = bench.build_gpu_agent(wl, 0, 0)
 agent.epsilon_start = agent.epsilon_min = 0.0
 rng = np.random.default_rng(0)
 for mode in ("host", "device"):
