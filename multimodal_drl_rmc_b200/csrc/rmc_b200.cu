@@ -1014,7 +1014,8 @@ static int32_t step_tc(rmc_learner* l, rmc_replay* r, const rmc_step_args_t* a, 
   }
   if (write_back) {
     cudaStream_t ts = side_tree ? l->tc_side : st;
-    if (ts != st) {
+    const bool patching = g_trace != nullptr && g_trace->mode == 2;      // replaying a graph: the fork / join edges are in it
+    if (ts != st && !patching) {
       RMC_CUDA(cudaEventRecord(l->tc_ev[0], st));
       RMC_CUDA(cudaStreamWaitEvent(ts, l->tc_ev[0], 0));
     }
@@ -1026,7 +1027,7 @@ static int32_t step_tc(rmc_learner* l, rmc_replay* r, const rmc_step_args_t* a, 
       RMC_KERNEL_OK();
       if (int32_t e = tree_update_large(r, C.nodes, C.pri, B, false, ts)) return e;
     }
-    if (ts != st) RMC_CUDA(cudaEventRecord(l->tc_ev[1], ts));
+    if (ts != st && !patching) RMC_CUDA(cudaEventRecord(l->tc_ev[1], ts));
   }
   // backward: dgrad chain + weight gradients fused per 128-row tile
   T.n_part = static_cast<int>(grid);
@@ -1041,7 +1042,7 @@ static int32_t step_tc(rmc_learner* l, rmc_replay* r, const rmc_step_args_t* a, 
   l->loss_epoch = S.epoch;
   if (a->phases & RMC_PH_ADAM) l->tc_packed_version = l->tc_bwd_version = ++l->online_version;
   if (a->phases & (RMC_PH_POLYAK | RMC_PH_HARDSYNC)) l->tc_target_version = ++l->target_version;
-  if (write_back && side_tree) RMC_CUDA(cudaStreamWaitEvent(st, l->tc_ev[1], 0));
+  if (write_back && side_tree && !(g_trace != nullptr && g_trace->mode == 2)) RMC_CUDA(cudaStreamWaitEvent(st, l->tc_ev[1], 0));
   return RMC_OK;
 }
 
@@ -1368,6 +1369,11 @@ static int32_t run_step_graph(rmc_learner* l, long long key_batch, int key_phase
     return body(st);
   }
   if (l->hyb_graphs.size() >= 16) return body(st);
+  if (l->hyb_cap == nullptr && cudaStreamCreateWithFlags(&l->hyb_cap, cudaStreamNonBlocking) != cudaSuccess) {
+    cudaGetLastError();
+    l->hyb_graph_off = true;
+    return body(st);
+  }
   StepGraph fresh; fresh.batch = key_batch; fresh.phases = key_phases;
   Trace T; T.mode = 1; T.g = &fresh;
   if (cudaStreamBeginCapture(l->hyb_cap, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
@@ -1431,7 +1437,17 @@ extern "C" int32_t rmc_learner_step(rmc_learner_t* l, rmc_replay_t* r, const rmc
   l->ctx.rp = r->dev;
   l->last_batch = a->batch;
   if (l->hybrid) return hybrid_step(l, r, a, S, st);
-  if (a->precision == RMC_PREC_BF16_TC) return step_tc(l, r, a, S, st);
+  if (a->precision == RMC_PREC_BF16_TC) {
+    // single-GPU tensor-core step (13 launches on two streams): replayed as one graph once the operand images are current
+    // (the first step, and any step after an un-fused target update, still packs them and launches normally); the sharded
+    // step keeps ordinary launches -- its exchange kernels spin on peer flags.
+    const int full = RMC_PH_FORWARD | RMC_PH_BACKWARD | RMC_PH_ADAM;
+    const bool images_current = l->tct_ready && l->tc_packed_version == l->online_version && l->tc_bwd_version == l->online_version &&
+                                l->tc_target_version == l->target_version;
+    if (l->early.c == nullptr && images_current && (a->phases & full) == full && a->grads_in_dev == nullptr)
+      return run_step_graph(l, a->batch, 0x20000000 | a->phases, st, [&](cudaStream_t s_) { return step_tc(l, r, a, S, s_); });
+    return step_tc(l, r, a, S, st);
+  }
   if (a->precision != RMC_PREC_FP32) return fail(RMC_ERR_ARG, "rmc_learner_step: unknown precision");
   const int G = grid_for(l, a->batch, l->num_sms);
   const long long n_tiles = (a->batch + kTM - 1) / kTM;
