@@ -228,7 +228,8 @@ struct AgentCtx {
   float* loss_part;     // [n_tiles]
   float* loss;          // [1]
   unsigned* barrier;
-  unsigned* qt_flag;    // [tiles] epoch of the launch whose Q_target(s') for that tile is in QT (role split)
+  unsigned* qt_flag;    // [kFlagWords] {epoch, payload} hand-off words of the fused step: Q_target(s') per (tile, row, action),
+                        // |td| per row and the loss partial per tile (layout: rmc_mlp.cuh)
   volatile float* host_loss;      // mapped pinned host memory: [0] loss of the last step, [1] its epoch (as bits)
   unsigned long long* dbg;   // optional per-CTA phase timestamps [G][16] (nullptr = off)
 };

@@ -289,8 +289,9 @@ __device__ void tree_update_cta(const ReplayDev& R, const long long* __restrict_
 
 // ---- write-back by a TEAM of kTreeTeam CTAs (learner step, big trees) ---------------------------------
 // Spatial partition: member t owns the leaves below the t-th node of depth 3 (heap indices 7..14), so
-// elections (stamps) and all fix-up atomics below depth 3 are private to one member; the top 9 levels
-// are rebuilt, and the extremes combined, by whichever member arrives last (no spinning).
+// writer elections and all fix-up atomics below depth 3 are private to one member; every member rebuilds
+// levels 8..3 under its own depth-3 node, and whichever member arrives last (no spinning) finishes
+// levels 2..0 and combines the extremes.
 __device__ __forceinline__ int depth3_owner(long long node) {
   const unsigned long long n1 = static_cast<unsigned long long>(node) + 1ull;
   const int depth = 63 - __clzll(n1);            // root = depth 0
