@@ -214,7 +214,7 @@ def run_reference_arm(args, wl):
             "config": {"workload": wl["name"], "batch": wl["B"], "replay_capacity": wl["cap"], "replay_size": wl["size"], "obs_dim": D},
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": cb["value"], "unit": "transitions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit_json_line(line)
 
 
 # ------------------------------------------------------------------------------------ GPU arm
@@ -380,7 +380,7 @@ def run_ours(args, wl):
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
         if extra:
             line["extra"] = extra
-        print(json.dumps(line), flush=True)
+        emit_json_line(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -438,7 +438,7 @@ def run_sharded(args, wl, agent, rank, world, local):
                 "roofline": {"bound": "tensor", "kernel": "k_mlp_infer_tc/k_tc_bwd/k_tc_wgrad (tcgen05 bf16)" if tc else "k_learner_step (fp32 FFMA exact-parity mode)", "achieved": B * FLOP_PER_TRANSITION * K / (ms * 1e-3) / 1e12,
                              "peak": 1682.8, "unit": "TFLOP/s", "frac": B * FLOP_PER_TRANSITION * K / (ms * 1e-3) / 1e12 / 1682.8, "traffic": None,
                              "peak_source": "measured bf16 (MEASURED_PEAKS.json)" + ("" if tc else "; this mode runs on the FP32 pipe by design")}}
-        print(json.dumps(line), flush=True)
+        emit_json_line(line)
     dist.destroy_process_group()
 
 
@@ -576,7 +576,18 @@ def extra_workloads(agent):
     return out
 
 
+_REAL_STDOUT = sys.stdout
+
+
+def emit_json_line(line):
+    """The ONE line of the bench contract goes to the real stdout; everything else this process prints (the agents mirror the
+    reference's ``print("DEVICE", ...)`` in their constructor) is routed to stderr by main()."""
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
+
+
 def main():
+    sys.stdout = sys.stderr
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2000)
