@@ -29,11 +29,8 @@ import time
 
 import numpy as np
 
-# Launch mode of the fused step kernel for the benchmark: programmatic dependent launch (the next step's launch
-# latency overlaps this step's tail; measured 4.9 -> 2.2 us idle gap between steps, profiles/r1/launch_gaps.txt).
-# The library default stays the cooperative launch (driver-guaranteed co-residency for the in-kernel barrier); the
-# plain+PDL launch is equally co-resident whenever one stream of one process drives the GPU, which is the case here.
-os.environ.setdefault("RMC_LAUNCH", "pdl")
+# The benchmark runs the library's DEFAULT launch mode (programmatic dependent launch with co-residency established by
+# construction, see launch_step in csrc/rmc_b200.cu); RMC_LAUNCH=coop in the environment selects the cooperative launch.
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
@@ -55,7 +52,7 @@ METRIC = "learner transitions/sec (sample+TD+fwd/bwd+Adam) at 1/2/4/8 B200 vs ho
 WORKLOADS = {
     "large65536": dict(algo="PerDuelingDoubleDQNAgent", B=65536, cap=CAP, size=CAP, sharded=True,
                        name="large-batch learner (batch 65,536) minibatch-sharded across GPUs with NCCL gradient allreduce (BASELINE configs[4])"),
-    "ensemble8_per256": dict(algo="PerDuelingDoubleDQNAgent", B=256, cap=200_000, size=200_000, ensemble=8,
+    "ensemble8_per256": dict(algo="PerDuelingDoubleDQNAgent", B=256, cap=CAP, size=CAP, ensemble=8,
                              name="ensemble of independent PER+double+dueling agents, 8 per GPU, one launch per step for all 8, no communication (BASELINE configs[3])"),
     "per256": dict(algo="PerDuelingDoubleDQNAgent", B=256, cap=CAP, size=CAP,
                    name="PER+double+dueling DQN learner, batch 256, 1M-transition GPU-resident replay (BASELINE configs[1])"),
@@ -117,24 +114,30 @@ class ClockSampler(threading.Thread):
 
 
 def measured_traffic(kernel):
-    """DRAM bytes per launch from the committed ncu capture (profiles/r1/ncu_traffic.json), or None."""
-    path = os.path.join(ROOT, "profiles", "r1", "ncu_traffic.json")
-    try:
-        with open(path) as fh:
-            return json.load(fh)[kernel]["dram_bytes_per_launch"]
-    except Exception:
-        return None
+    """DRAM bytes per launch of `kernel` from the committed `ncu --set full` captures of this benchmark command
+    (profiles/r2/ncu_traffic.json; dram__bytes_read.sum + dram__bytes_write.sum): (warm, cold).  warm = captured with
+    --cache-control none (L2 keeps what the previous step left there: the state the benchmark runs in), cold = ncu's default
+    (L2 flushed before every replay: weights and scratch count as DRAM traffic).  ncu cannot run inside a timed run, so these
+    are per-build constants, re-captured whenever the kernel changes."""
+    for rnd in ("r2", "r1"):
+        path = os.path.join(ROOT, "profiles", rnd, "ncu_traffic.json")
+        try:
+            with open(path) as fh:
+                d = json.load(fh)[kernel]
+            return d.get("dram_bytes_per_launch_warm", d.get("dram_bytes_per_launch")), d.get("dram_bytes_per_launch_cold", d.get("dram_bytes_per_launch")), rnd
+        except Exception:
+            continue
+    return None, None, None
 
 
-def synthetic(n, seed):
-    from oracle.dqn_oracle import synthetic_transitions
-    return synthetic_transitions(n, D, seed)
+def synthetic(n, seed, obs_dim=D):
+    from multimodal_drl_rmc_b200.synthetic import synthetic_transitions
+    return synthetic_transitions(n, obs_dim, seed)
 
 
 def seeded_priorities(n, seed):
-    rng = np.random.default_rng(seed)
-    return np.power(np.minimum(np.abs(rng.normal(size=n)).astype(np.float32) + np.float32(1e-4), np.float32(1.0)),
-                    np.float32(0.6)).astype(np.float32)
+    from multimodal_drl_rmc_b200.synthetic import seeded_priorities as sp
+    return sp(n, seed)
 
 
 # ------------------------------------------------------------------------------------ CPU arm
@@ -211,8 +214,8 @@ def run_reference_arm(args, wl):
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "transitions/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl["name"], "batch": wl["B"], "replay_capacity": wl["cap"], "replay_size": wl["size"], "obs_dim": D},
-            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "config": bench_config(wl),
+            "cpu_baseline": dict({k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}, port_vs_reference=PORT_VS_REFERENCE),
             "e2e": {"value": cb["value"], "unit": "transitions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit_json_line(line)
 
@@ -237,6 +240,28 @@ def build_gpu_agent(wl, device_index, seed):
     return agent, (obs, act, rew, done, nxt)
 
 
+def kernel_span_us(agent, one_step, n=64):
+    """In-kernel span of the fused step: per launch, (latest CTA end) - (earliest CTA start) on %globaltimer, recorded by the
+    kernel itself (rmc_learner_debug_timing); mean and max over n launches.  Excludes the launch latency and the inter-launch
+    gap that the event-timed ms_per_step contains, so it is <= ms_per_step."""
+    import ctypes as C
+    import torch
+    from multimodal_drl_rmc_b200 import _lib
+    lib = _lib.lib()
+    lh = agent._lh
+    _lib.check(lib.rmc_learner_debug_timing(lh.handle, 1))
+    for _ in range(min(n, 64)):
+        one_step()
+    torch.cuda.synchronize()
+    buf = (C.c_uint64 * 128)()
+    _lib.check(lib.rmc_learner_debug_gaps_sync(lh.handle, buf, _lib.stream_ptr(lh.device_index)))
+    _lib.check(lib.rmc_learner_debug_timing(lh.handle, 0))
+    spans = [(buf[2 * k + 1] - buf[2 * k]) * 1e-3 for k in range(64) if buf[2 * k] != 0xFFFFFFFFFFFFFFFF and buf[2 * k + 1] > buf[2 * k]]
+    if not spans:
+        return None, None
+    return float(np.mean(spans)), float(np.max(spans))
+
+
 def run_ours(args, wl):
     import torch
     import torch.distributed as dist
@@ -252,7 +277,7 @@ def run_ours(args, wl):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     B, K, W = wl["B"], args.steps, max(args.warmup, 3)
     sharded = bool(wl.get("sharded"))
-    agent, data = build_gpu_agent(wl, local, seed=0 if sharded else rank)   # sharded: identical replicas on every rank
+    agent, data = build_gpu_agent(wl, local, seed=0 if sharded else 1000 * rank)   # sharded: identical replicas on every rank
     obs, act, rew, done, nxt = data
     lib = _lib.lib()
     if sharded:
@@ -270,14 +295,15 @@ def run_ours(args, wl):
         torch.cuda.synchronize()
 
     def one_step():
-        if ens is not None:
+        """One learner step through the drop-in API, exactly the call sequence of train.py:89,99-101."""
+        if ens is not None:       # config[3]: the ensemble wrapper steps all agents of this GPU (learn + target update) in one launch
             for m in ens.agents:
                 m.step += 1
             ens.learn()
             return
         agent.step += 1
-        agent.learn(fuse_target_update=True)
-        agent.update_target_network()        # no-op: already fused into the launch above
+        agent.learn()
+        agent.update_target_network()
 
     # ---- device-timed: inputs resident in HBM ----------------------------------------------
     for _ in range(W):
@@ -296,18 +322,6 @@ def run_ours(args, wl):
     barrier()
     launches = int(lib.rmc_launch_count() - l0)
     ms_total = t_start.elapsed_time(t_end)
-    # duration of the dominant kernel: one launch at a time, bracketed by events on the launching stream,
-    # the device idle before each (no queueing in the bracket)
-    Kd = min(K, 200)
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(Kd)]
-    for k in range(Kd):
-        torch.cuda.synchronize()
-        ev[k][0].record()
-        one_step()
-        ev[k][1].record()
-    torch.cuda.synchronize()
-    durs = sorted(a.elapsed_time(b) for a, b in ev)
-    kern_ms = durs[len(durs) // 2]
 
     # ---- end to end through the public API with host buffers --------------------------------
     n_new = min(len(obs), 4096)
@@ -332,57 +346,139 @@ def run_ours(args, wl):
     barrier()
     e2e_ms = max(e_start.elapsed_time(e_end), 1e3 * (time.perf_counter() - wall0))
     clocks = sampler.summary() if sampler else None
+    span_mean, span_max = (None, None)
+    if ens is None:
+        span_mean, span_max = kernel_span_us(agent, one_step)
 
     # ---- max over ranks -----------------------------------------------------------------------
-    t = torch.tensor([ms_total, e2e_ms, kern_ms], dtype=torch.float64, device="cuda")
+    t = torch.tensor([ms_total, e2e_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms, kern_ms = (float(x) for x in t.tolist())
+    ms_total, e2e_ms = (float(x) for x in t.tolist())
 
     extra = {}
-    if rank == 0 and world == 1 and not args.no_extra:
-        extra = extra_workloads(agent)
+    if not args.no_extra:
+        if world == 1 and rank == 0:
+            extra = extra_workloads(agent)
+        elif world > 1:
+            del ens
+            extra = extra_sharded(args, rank, world, local)      # collective: every rank takes part
 
     if rank == 0:
         peak, peak_src = measured_peaks()
         per = agent._PER
+        kern_ms = ms_total / K           # the step IS one launch of k_learner_step: average launch duration over the timed region
         bytes_per_launch = (BYTES_PER_TRANSITION_PER if per else BYTES_PER_TRANSITION_UNI) * B * n_agents
         achieved = bytes_per_launch / (kern_ms * 1e-3) / 1e9
         flops_per_launch = (FLOP_PER_TRANSITION * B + 16 * P_COUNT) * n_agents
+        warm, cold, traffic_round = measured_traffic("k_learner_step") if n_agents == 1 else (None, None, None)
         cb = None
         if world == 1 and not args.no_cpu:
             threads = os.cpu_count() or 1
             cb = cpu_baseline(wl, 200, 5, threads)
+        value = world * n_agents * B * K / (ms_total * 1e-3)
         line = {
-            "metric": METRIC, "value": world * n_agents * B * K / (ms_total * 1e-3), "unit": "transitions/s", "n_gpus": world, "steps": K, "warmup": W,
+            "metric": METRIC, "value": value, "unit": "transitions/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": wl["name"], "batch": B, "replay_capacity": wl["cap"], "replay_size": wl["size"], "obs_dim": D,
-                       "net": "MLP %d-256-128-(1+8) dueling" % D if agent._DUELING else "MLP %d-256-128-8" % D,
-                       "parallelism": ("%d independent agents per GPU, no collective" % n_agents) if n_agents > 1 else
-                                      ("1 independent agent per GPU (ensemble members), no collective" if world > 1 else "single agent"),
-                       "l2": "inputs larger than L2: 128 MB ring + 16 MB tree sampled at random each step (126 MB L2); the 0.3 MB of weights "
-                             "and the per-step scratch are L2-resident by design",
-                       "sampling": "on-device Philox uniforms", "target_sync": "Polyak fused into the step launch",
-                       "launch": os.environ.get("RMC_LAUNCH", "coop")},
+            "config": bench_config(wl),
+            "config_details": {
+                "net": "MLP %d-256-128-(1+8) dueling" % D if agent._DUELING else "MLP %d-256-128-8" % D,
+                "parallelism": ("%d independent agents per GPU stepped by one launch (AgentEnsemble), %d GPUs, no collective" % (n_agents, world)) if n_agents > 1 else
+                               ("1 independent agent per GPU, no collective" if world > 1 else "single agent"),
+                "api": "agent.step = k; agent.learn(); agent.update_target_network()  (train.py:89,99-101; learn() is lazy, the target update launches the fused step)"
+                       if n_agents == 1 else "AgentEnsemble.learn()  (learn + target update of every member in one launch)",
+                "l2": "inputs larger than L2: 128 MB ring + 16 MB tree per agent sampled at random each step (126 MB L2); the 0.3 MB of weights "
+                      "and the per-step scratch are L2-resident by design",
+                "sampling": "on-device Philox uniforms", "target_sync": "Polyak (soft update every step), fused into the step launch",
+                "launch": os.environ.get("RMC_LAUNCH", "pdl (library default)")},
+            "per_gpu_value": value / world,
             "e2e": {"value": world * n_agents * B * K / (e2e_ms * 1e-3), "unit": "transitions/s", "ms_per_step": e2e_ms / K,
                     "h2d_bytes_per_step": int(agent.replay_memory_buffer._ring.row_floats * 4) * n_agents, "d2h_bytes_per_step": 4 * n_agents,
-                    "what": "store_transitions(1 host row) + learn() + update_target_network() + loss read-back per step", "last_loss": loss},
+                    "what": "store_transitions(1 host row) + learn() + update_target_network() + loss read-back per step and agent", "last_loss": loss},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": "k_learner_step", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": measured_traffic("k_learner_step") if n_agents == 1 else None, "peak_source": peak_src,
+                         "traffic": warm, "traffic_cold_cache": cold, "traffic_source": ("profiles/%s/ncu_traffic.json" % traffic_round) if traffic_round else None,
+                         "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": bytes_per_launch,
-                         "kernel_ms": kern_ms, "fp32_tflops": flops_per_launch / (kern_ms * 1e-3) / 1e12,
-                         "note": "latency-bound step (SURVEY 8d): report us/step next to the fraction"},
+                         "kernel_ms": kern_ms, "kernel_ms_how": "CUDA events around the K timed steps / K launches (one launch per step; includes the inter-launch gap)",
+                         "in_kernel_span_us": span_mean, "in_kernel_span_us_max": span_max,
+                         "fp32_tflops": flops_per_launch / (kern_ms * 1e-3) / 1e12,
+                         "note": "latency-bound step (SURVEY 8d): the dependent chain sample -> forward -> TD -> dgrad -> barrier -> wgrad+Adam bounds it, "
+                                 "not bytes or flops; report us/step next to the fraction"},
             "clocks": clocks,
         }
         if cb is not None:
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            line["cpu_baseline"]["port_vs_reference"] = PORT_VS_REFERENCE
         if extra:
             line["extra"] = extra
         emit_json_line(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def bench_config(wl):
+    """The workload description shared verbatim by both arms (--impl ours / reference)."""
+    return {"workload": wl["name"], "batch": wl["B"], "replay_capacity": wl["cap"], "replay_size": wl["size"], "obs_dim": D,
+            "agents_per_gpu": int(wl.get("ensemble", 1))}
+
+
+# Timed in the BUILD container (where /root/reference exists; it cannot travel to the GPU box), same workload as
+# cpu_baseline (PER + double + dueling, B = 256, 1M-transition replay, 16 threads): the oracle port that bench.py times on
+# the GPU box vs the unmodified reference classes driven through oracle/refharness.py.  See DESIGN.md section 5.
+PORT_VS_REFERENCE = {"port_ms_per_step": 50.0, "reference_ms_per_step": 44.0, "where": "build container, survey probe + round-1 run",
+                     "note": "the port is ~14 % slower than the reference itself on the same cores (same python tree loops, torch-eager nets)"}
+
+
+def extra_sharded(args, rank, world, local):
+    """BASELINE configs[4] inside the N > 1 run: ONE logical agent, B = 65,536, minibatch sharded over the ranks; the gradient
+    exchange as peer-memory kernels and as NCCL collectives, exact fp32 and tensor-core mode.  ms/step = max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from multimodal_drl_rmc_b200 import _lib
+    from multimodal_drl_rmc_b200.parallel import ShardedLearner
+    out = {}
+    wl = WORKLOADS["large65536"]
+    try:
+        agent, _ = build_gpu_agent(wl, local, seed=0)
+        for exchange in ("peer", "nccl"):
+            sl = ShardedLearner(agent, exchange=exchange)
+            for precision in ("fp32", "bf16"):
+                agent.learn_precision = precision
+                steps = 20 if precision == "fp32" else 50
+
+                def one():
+                    agent.step += 1
+                    return sl.learn()
+                for _ in range(5):
+                    one()
+                dist.barrier()
+                torch.cuda.synchronize()
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record()
+                for _ in range(steps):
+                    one()
+                e.record()
+                dist.barrier()
+                torch.cuda.synchronize()
+                t = torch.tensor([s.elapsed_time(e)], dtype=torch.float64, device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                chk = agent._lh.get_params(_lib.ONLINE).double().sum().reshape(1)
+                lo, hi = chk.clone(), chk.clone()
+                dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+                dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+                ms = float(t.item()) / steps
+                out["%s_%s" % (precision, exchange)] = {"ms_per_step": ms, "transitions_per_s": wl["B"] / (ms * 1e-3),
+                                                        "replicas_identical": bool(float(lo) == float(hi)), "steps": steps}
+            if exchange == "peer":
+                out["peer_exchange_status"] = sl.exchange_status()
+            del sl
+        out["what"] = ("B = 65,536 learner step sharded over %d GPUs (strong scaling of ONE logical agent): peer = gradient reduce + Adam as kernels over "
+                       "NVLink peer memory, nccl = all_reduce / all_gather around the same kernels" % world)
+    except Exception as exc:  # pragma: no cover
+        out["error"] = repr(exc)
+    return {"large65536_sharded": out}
 
 
 def run_sharded(args, wl, agent, rank, world, local):
@@ -491,7 +587,7 @@ def extra_workloads(agent):
             a = agent.choose_actions(obs[j:j + 1])
             agent.store_transitions(obs[j:j + 1], a, [float(rew[j])], [bool(done[j])], nxt[j:j + 1], None)
             agent.step += 1
-            agent.learn(fuse_target_update=True)
+            agent.learn()
             agent.update_target_network()
 
         for j in range(20):
@@ -507,13 +603,39 @@ def extra_workloads(agent):
                                               "n_env = 1, PER B=256 learner; the environment step itself (SUMO, CPU) is not included"}
     except Exception as exc:  # pragma: no cover
         out["train_iteration_api"] = {"error": repr(exc)}
+    try:   # train.py's loop around the hot path against a synthetic vectorised env (n_env = 16, 0.5 ms per env step):
+        # strict reference order vs the learner step in flight while the environments step
+        import tempfile
+        from multimodal_drl_rmc_b200 import actor_loop, macro_config
+        from multimodal_drl_rmc_b200.synthetic import SyntheticVecEnv
+        tmp = tempfile.mkdtemp(prefix="rmc_bench_loop_")
+        n_env = 16
+        al = macro_config.make_agent("PerDuelingDoubleDQNAgent", D, 256, 200_000, save_dir=tmp + "/", log_dir=tmp + "/", gpu=str(agent.device.index), n_env=n_env)
+        al.replay_memory_buffer._ring.push_host(*synthetic(200_000, 77))
+        res = {}
+        for name, loop in (("strict", actor_loop.strict_loop), ("overlapped", actor_loop.overlapped_loop)):
+            env = SyntheticVecEnv(n_env, D, step_seconds=0.0005, seed=3)
+            loop(al, env, 50, start_step=1)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            loop(al, env, 400, start_step=100)
+            torch.cuda.synchronize()
+            res[name] = 1e6 * (time.perf_counter() - t0) / 400
+            env.close()
+        out["actor_loop_n_env16"] = {"strict_us_per_iteration": res["strict"], "overlapped_us_per_iteration": res["overlapped"], "env_step_us": 500.0,
+                                     "what": "choose_actions(16 host states) -> env.step (synthetic, 0.5 ms on a worker thread) -> store_transitions(16 rows) -> learn() -> "
+                                             "update_target_network(); overlapped = learner step launched between step_async and step_wait"}
+        del al
+    except Exception as exc:  # pragma: no cover
+        out["actor_loop_n_env16"] = {"error": repr(exc)}
     try:   # C1: repo defaults (B = 32, uniform replay)
         wl = WORKLOADS["default32"]
         a1, _ = build_gpu_agent(wl, agent.device.index, seed=11)
 
         def step1():
             a1.step += 1
-            a1.learn(fuse_target_update=True)
+            a1.learn()
+            a1.update_target_network()
         ms = _time_steps(step1, 1000)
         out["default32"] = {"us_per_step": 1e3 * ms, "transitions_per_s": wl["B"] / (ms * 1e-3)}
         del a1
@@ -522,7 +644,7 @@ def extra_workloads(agent):
     try:   # C4: 8 independent agents on this GPU, one launch per step for all of them
         from multimodal_drl_rmc_b200.parallel import AgentEnsemble
         for name, wl in (("ensemble8_default32", dict(WORKLOADS["default32"], size=100_000, cap=200_000)),
-                         ("ensemble8_per256", dict(WORKLOADS["per256"], size=200_000, cap=200_000))):
+                         ("ensemble8_per256", dict(WORKLOADS["per256"]))):
             members = [build_gpu_agent(wl, agent.device.index, seed=50 + k)[0] for k in range(8)]
             ens = AgentEnsemble(members)
 
@@ -539,7 +661,7 @@ def extra_workloads(agent):
     try:   # the repo-HEAD hybrid CNN + MLP network (env/dqn_config.py:66-193), HEAD defaults (B = 32, uniform replay)
         import tempfile
         from multimodal_drl_rmc_b200 import macro_config
-        from oracle.dqn_oracle import synthetic_transitions
+        from multimodal_drl_rmc_b200.synthetic import synthetic_transitions
         tmp = tempfile.mkdtemp(prefix="rmc_bench_hyb_")
         for name, algo, bsz in (("hybrid_default32", "DuelingDoubleDQNAgent", 32), ("hybrid_per256", "PerDuelingDoubleDQNAgent", 256)):
             ah = macro_config.make_agent(algo, macro_config.HYBRID_OBS_DIM, bsz, 20000, save_dir=tmp + "/", log_dir=tmp + "/", activation="hybrid",
@@ -548,7 +670,8 @@ def extra_workloads(agent):
 
             def steph():
                 ah.step += 1
-                ah.learn(fuse_target_update=True)
+                ah.learn()
+                ah.update_target_network()
             ms = _time_steps(steph, 100, 5)
             out[name] = {"us_per_step": 1e3 * ms, "transitions_per_s": bsz / (ms * 1e-3), "params": 885481,
                          "mode": "exact fp32 (implicit-GEMM convolutions, one kernel per layer and direction)"}
@@ -561,7 +684,8 @@ def extra_workloads(agent):
 
         def step5():
             a5.step += 1
-            a5.learn(fuse_target_update=True)
+            a5.learn()
+            a5.update_target_network()
         ms = _time_steps(step5, 10, 2)
         out["large_batch_65536"] = {"ms_per_step": ms, "transitions_per_s": 65536 / (ms * 1e-3),
                                     "fp32_tflops": 65536 * FLOP_PER_TRANSITION / (ms * 1e-3) / 1e12, "mode": "fp32 FFMA (exact parity)"}
@@ -593,12 +717,17 @@ def main():
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="per256", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
     ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"], help="large65536 only: learner arithmetic mode")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="large65536 only: gradient exchange (peer-memory kernels or NCCL)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary workloads")
     args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.workload is None:
+        # N = 1: BASELINE configs[1] (the config the metric is quoted on).  N > 1: configs[3], the ensemble of independent agents,
+        # 8 per GPU (the single small-batch learner does not shard: "replicas only").
+        args.workload = "per256" if max(world, args.gpus) <= 1 else "ensemble8_per256"
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
         run_reference_arm(args, wl)

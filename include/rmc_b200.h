@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define RMC_ABI_VERSION 2
+#define RMC_ABI_VERSION 3
 
 typedef void* rmc_stream_t;
 typedef struct rmc_replay rmc_replay_t;   /* GPU-resident ring buffer (+ sum tree when prioritized) */
@@ -83,6 +83,8 @@ typedef struct {
   double total_priority; /* sum_tree.py:63-65  tree[0]                               */
   double max_priority;   /* sum_tree.py:67-69  == max(leaves[:size])                 */
   double min_priority;   /* sum_tree.py:71-73  == min(leaves[:size])                 */
+  int64_t rejected_nodes;/* entries of caller-supplied tree-index lists outside the leaf range [cap-1, 2cap-2] that
+                            rmc_per_update* skipped so far (the reference would raise IndexError there) */
 } rmc_replay_stats_t;
 
 /* What one learner step does (bit mask).  The default Agent.learn() uses
@@ -174,6 +176,12 @@ int32_t rmc_replay_stats_sync(rmc_replay_t* r, rmc_replay_stats_t* out, rmc_stre
 int32_t rmc_replay_read_tree_sync(rmc_replay_t* r, double* out_host, int64_t first, int64_t n, rmc_stream_t s);
 int32_t rmc_replay_read_rows_sync(rmc_replay_t* r, float* out_host, int64_t first_slot, int64_t n, rmc_stream_t s);
 int32_t rmc_replay_row_floats(const rmc_replay_t* r);
+/* Exact-resume side-car (not a reference interface; the reference refills 100 k env steps on resume, train.py:63-81):
+ * restore a replay saved with the two read calls above -- rows_host [size][row_floats] in slot order, leaf_pri_host [size]
+ * = the float32-exact leaf priorities (NULL for uniform replay), and the ring cursor.  The inner nodes and the extremes are
+ * rebuilt from the leaves (exact sums), so tree, total/max/min and every later sample equal the saved run's.  Synchronises. */
+int32_t rmc_replay_load_host(rmc_replay_t* r, const float* rows_host, const float* leaf_pri_host, int64_t size,
+                             int64_t data_pointer, rmc_stream_t s);
 
 /* ReplayMemoryPrioritized.sample_transitions (replay_memory.py:69-92) + SumTree.get_leaf
  * (sum_tree.py:42-61): stratified proportional sampling.  out_nodes = tree indices (bit-exact
@@ -225,7 +233,7 @@ int32_t rmc_learner_get_params(rmc_learner_t* l, int32_t kind, float* dst, int64
 int32_t rmc_learner_set_hyper(rmc_learner_t* l, const rmc_hyper_t* hyper);
 
 /* {Simple,Double,PerDouble}Agent.learn (dqn/agent.py:166-185,204-226,245-272) and
- * Agent.update_target_network (:101-110) as ONE cooperative launch; `phases` selects which
+ * Agent.update_target_network (:101-110) as ONE launch; `phases` selects which
  * parts run (split variants for parity tests).  Outputs stay on the device; see
  * rmc_learner_read_*. */
 int32_t rmc_learner_step(rmc_learner_t* l, rmc_replay_t* r, const rmc_step_args_t* a, rmc_stream_t s);
@@ -239,8 +247,16 @@ int32_t rmc_learner_step_push(rmc_learner_t* l, rmc_replay_t* r, const rmc_step_
  * name in {"nodes"(i64), "is_w","q_sa","y","abs_td","huber","pri","loss"(1), "q_next_tgt"(B*A),
  *          "q_next_on"(B*A), "q"(B*A), "rows"(B*row_floats)} */
 int32_t rmc_learner_output(rmc_learner_t* l, const char* name, void** dev_ptr, int64_t* n_elems);
-/* loss of the last step -> host (synchronises). */
+/* loss of the last step -> host (synchronises).  RMC_ERR_STATE if a launch of this learner tripped the in-kernel
+ * watchdog (see rmc_learner_status). */
 int32_t rmc_learner_loss_sync(rmc_learner_t* l, float* out_host, rmc_stream_t s);
+/* Health of the fused step (does not synchronise): the kernel's agent barrier and hand-off words need every CTA of the
+ * launch co-resident.  The default launch (programmatic dependent launch, RMC_LAUNCH unset) establishes that by
+ * construction -- grid <= resident capacity, fused-step launches of one device serialised across streams -- and
+ * RMC_LAUNCH=coop asks the driver to guarantee it.  Should a wait inside the kernel nevertheless exceed 2 s (a second
+ * process running this kernel on the same GPU through MPS), the kernel gives up instead of hanging the GPU and this call
+ * (like rmc_learner_loss_sync) returns RMC_ERR_STATE; *failed_epoch = launch epoch of the failed step, 0 = healthy. */
+int32_t rmc_learner_status(rmc_learner_t* l, uint32_t* failed_epoch);
 
 /* Network.forward (network.py:59-63,90-96): Q values of `which` net (RMC_ONLINE/RMC_TARGET). */
 int32_t rmc_learner_q_values(rmc_learner_t* l, int32_t which, const float* obs_dev, int64_t n, float* q_out_dev,
@@ -307,7 +323,9 @@ int32_t rmc_group_step(rmc_group_t* g, const rmc_step_args_t* a, rmc_stream_t s)
  *                      whole step (one GPU per rank); 1 = local gradients + publish, 2 = reduce + Adam +
  *                      write-back -- only for ranks EMULATED on one GPU, where a rank's waiting reduce kernel
  *                      would keep the other rank's cooperative step kernel from becoming resident
- *   rmc_comm_status_sync : 0, or the epoch of an exchange that timed out (a peer never published) */
+ *   rmc_comm_status_sync : 0, or the epoch of an exchange that timed out (a peer never published within
+ *                      RMC_COMM_TIMEOUT_MS, default 10 s).  The decision is taken once per kernel for all its blocks:
+ *                      a timed-out exchange applies NOTHING (no Adam, no Polyak, no write-back) on this rank. */
 int32_t rmc_comm_create(rmc_comm_t** out, rmc_learner_t* l, int32_t rank, int32_t world, int64_t global_batch_max);
 int32_t rmc_comm_export(rmc_comm_t* c, void* handle64_out, void** local_ptr_out);
 int32_t rmc_comm_connect(rmc_comm_t* c, const void* handles64, void* const* same_process_ptrs);

@@ -51,7 +51,8 @@ class Hyper(C.Structure):
 
 class ReplayStats(C.Structure):
     _fields_ = [("capacity", C.c_int64), ("size", C.c_int64), ("data_pointer", C.c_int64),
-                ("total_priority", C.c_double), ("max_priority", C.c_double), ("min_priority", C.c_double)]
+                ("total_priority", C.c_double), ("max_priority", C.c_double), ("min_priority", C.c_double),
+                ("rejected_nodes", C.c_int64)]
 
 
 class StepArgs(C.Structure):
@@ -111,6 +112,7 @@ _SIGS = {
     "rmc_replay_read_tree_sync": (_i32, [_vp, _vp, _i64, _i64, _vp]),
     "rmc_replay_read_rows_sync": (_i32, [_vp, _vp, _i64, _i64, _vp]),
     "rmc_replay_row_floats": (_i32, [_vp]),
+    "rmc_replay_load_host": (_i32, [_vp, _vp, _vp, _i64, _i64, _vp]),
     "rmc_per_sample": (_i32, [_vp, _i64, _f64, _vp, _u64, _u64, _vp, _vp, _vp, _vp]),
     "rmc_uniform_sample": (_i32, [_vp, _i64, _vp, _u64, _u64, _vp, _vp, _vp]),
     "rmc_tree_get_leaf": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp]),
@@ -127,6 +129,7 @@ _SIGS = {
     "rmc_learner_step_push": (_i32, [_vp, _vp, C.POINTER(StepArgs), _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "rmc_learner_output": (_i32, [_vp, _cp, C.POINTER(_vp), C.POINTER(_i64)]),
     "rmc_learner_loss_sync": (_i32, [_vp, C.POINTER(_f32), _vp]),
+    "rmc_learner_status": (_i32, [_vp, C.POINTER(C.c_uint32)]),
     "rmc_learner_q_values": (_i32, [_vp, _i32, _vp, _i64, _vp, _vp]),
     "rmc_learner_heads": (_i32, [_vp, _i32, _vp, _i64, _vp, _vp]),
     "rmc_learner_act": (_i32, [_vp, _vp, _i64, _vp, _vp]),
@@ -147,7 +150,7 @@ _SIGS = {
     "rmc_comm_status_sync": (_i32, [_vp, C.POINTER(C.c_uint32), _vp]),
     "rmc_learner_step_sharded": (_i32, [_vp, _vp, _vp, C.POINTER(StepArgs), _i32, _vp]),
 }
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 def lib() -> C.CDLL:

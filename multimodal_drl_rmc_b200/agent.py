@@ -138,6 +138,11 @@ class Agent:
         self._step_fn = lib().rmc_learner_step
         self._step_push_fn = lib().rmc_learner_step_push
         self.replay_memory_buffer._ring.defer_small_pushes = True     # per-step rows ride with the next learn()
+        # learn() is lazy (see learn / update_target_network): whoever looks at the learner or the replay first makes the
+        # recorded step happen
+        self._pending_step = None
+        self._lh._flush_hook = self._flush_step
+        self.replay_memory_buffer._ring._owner_flush = self._flush_step
         self._learn_phases = _lib.PH_LEARN if self._PER else (_lib.PH_LEARN & ~_lib.PH_PRIORITY)
         self.sampling_seed = 0x5EED
 
@@ -236,33 +241,58 @@ class Agent:
         return ((mem.beta_end - mem.beta_start) / (x1 - 0.0)) * (x - 0.0) + mem.beta_start
 
     def learn(self, u=None, indices=None, fuse_target_update=False):
-        """dqn/agent.py:166-185 / 204-226 / 245-272 as one launch.  ``u`` / ``indices`` inject the
-        sampling randomness (tests).  ``fuse_target_update=True`` also performs this step's
-        ``update_target_network()`` inside the same launch (call order of train.py:99-101); the
-        following ``update_target_network()`` call is then skipped once."""
+        """dqn/agent.py:166-185 / 204-226 / 245-272.  ``u`` / ``indices`` inject the sampling randomness (tests).
+
+        The reference's trainer calls ``learn(); update_target_network()`` back to back (train.py:99-101) and the fused
+        kernel can do both in one launch (Polyak / hard sync on the post-Adam weights, same bits as two launches --
+        tests/test_gpu_learner.py::test_fused_target_update_equals_separate_call).  So ``learn()`` is LAZY: it fixes
+        everything that defines the step (batch, beta, sampling randomness, Adam step count, the env rows held back by
+        ``store_transitions``) and records it; the ``update_target_network()`` that follows launches it together with the
+        target update.  Anything else that looks at the learner or the replay first (``last_loss``, ``state_dict``,
+        ``choose_actions``, ``store_transitions``, replay statistics, another ``learn``) launches the recorded step as it
+        is, so the laziness is not observable.  ``fuse_target_update=True`` launches immediately with this step's target
+        update inside (the following ``update_target_network()`` call is then skipped once)."""
+        self._flush_step()
         ring = self.replay_memory_buffer._ring
-        rh = ring._handle
-        if rh is None:
+        if ring._handle is None:
             raise RuntimeError("replay memory is empty (no transition stored yet)")
+        if not self._PER and indices is None and self._B > ring.count:
+            # random.sample raises ValueError here in the reference (dqn/replay_memory.py:39); raised now, not when the recorded step is launched
+            raise _lib.RmcError("librmc_b200 error -3: rmc_learner_step: sample larger than population")
         self._learn_calls += 1
         self._adam_t += 1
         phases = self._learn_phases
-        if fuse_target_update:
-            phases |= self._target_phase()
-            self._target_fused_for = self._learn_calls
         a, keep = self._step_args(phases, u, indices)
-        n_new = ring.take_pending()
-        if n_new:      # this env step's rows (held back by store_transitions) and the step, one host call
-            rc = self._step_push_fn(self._lh.handle, rh, self._args_ref, *ring._small_ptrs, n_new, stream_ptr(self._dev_index))
+        self._keepalive = keep
+        if fuse_target_update:
+            self._launch_step(phases | self._target_phase())
+            self._target_fused_for = self._learn_calls
         else:
-            rc = self._step_fn(self._lh.handle, rh, self._args_ref, stream_ptr(self._dev_index))
+            self._pending_step = phases
+
+    def _launch_step(self, phases):
+        """One host call: this env step's rows (held back by store_transitions) + the learner step [+ target update]."""
+        a = self._args
+        a.phases = int(phases)
+        ring = self.replay_memory_buffer._ring
+        n_new = ring.take_pending()
+        if n_new:
+            rc = self._step_push_fn(self._lh.handle, ring._handle, self._args_ref, *ring._small_ptrs, n_new, stream_ptr(self._dev_index))
+        else:
+            rc = self._step_fn(self._lh.handle, ring._handle, self._args_ref, stream_ptr(self._dev_index))
         if rc:
             check(rc)
         ver = self._lh.version
         ver[0] += 1
-        if fuse_target_update:
+        if phases & (_lib.PH_POLYAK | _lib.PH_HARDSYNC):
             ver[1] += 1
-        self._keepalive = keep
+
+    def _flush_step(self):
+        """Launch a recorded learn() that no update_target_network() has picked up."""
+        phases = self._pending_step
+        if phases is not None:
+            self._pending_step = None
+            self._launch_step(phases)
 
     def _target_phase(self, force=False):
         if (not self.target_soft_update and self.step % (self.update_target_frequency // self.n_env) == 0) or force:
@@ -272,7 +302,14 @@ class Agent:
         return 0
 
     def update_target_network(self, force=False):
-        """dqn/agent.py:101-110."""
+        """dqn/agent.py:101-110.  Directly after ``learn()`` (train.py:99-101) this is the call that launches the step,
+        with the target update fused into it."""
+        pend = self._pending_step
+        if pend is not None and not force:
+            self._pending_step = None
+            self._launch_step(pend | self._target_phase())
+            return
+        self._flush_step()
         if not force and getattr(self, "_target_fused_for", None) == self._learn_calls:
             self._target_fused_for = None
             return
@@ -297,8 +334,9 @@ class Agent:
 
     def last_loss(self):
         """Loss of the last learn() (device -> host read; synchronises)."""
+        self._flush_step()
         out = C.c_float()
-        check(lib().rmc_learner_loss_sync(self._lh.handle, C.byref(out), stream_ptr()))
+        check(lib().rmc_learner_loss_sync(self._lh.handle, C.byref(out), stream_ptr(self._dev_index)))
         return out.value
 
     # ------------------------------------------------------------------ checkpoints / logs ---
@@ -354,19 +392,60 @@ class Agent:
             self.summary_writer.add_scalar("Learner/" + k, v, global_step=(self.step * self.n_env))
 
     # ------------------------------------------------------------------ exact-resume side-car ---
-    def save_learner_state(self, path):
-        """Side-car next to the (unchanged) ``.pack`` checkpoint: target net, Adam moments and step, learner
-        counters, and -- for small replays or on request -- nothing of the replay (the reference refills it).
-        The reference's resume drops all of this (dqn/agent.py:112-121); with it a resumed run continues
-        bit-identically."""
+    @staticmethod
+    def _sidecar_path(path):
+        path = os.fspath(path)
+        return path if path.endswith(".npz") else path + ".npz"      # np.savez appends the suffix; load must look for the same file
+
+    def save_learner_state(self, path, replay=True, host_rng=True):
+        """Side-car next to the (unchanged) ``.pack`` checkpoint.  The reference's resume keeps only the online weights
+        and four counters (dqn/agent.py:112-121, dqn/network.py:27-47): Adam restarts from zero moments, the target net
+        is re-copied and the replay is refilled with 100 k fresh env steps (train.py:63-81).  This file holds what is
+        needed to continue as if the process had never stopped:
+
+          always      online / target weights, Adam moments and step count, learner counters, sampling seed, episode statistics
+          replay      the replay ring rows, cursor and size and -- for PER -- the leaf priorities (inner tree nodes and
+                      max / min are rebuilt exactly on load); 132 MB for the 1M x D=14 default, read back in one D2H pass
+          host_rng    the states of python's ``random`` and of ``np.random`` (the host exploration / sampling streams)
+
+        A run resumed with ``load_learner_state`` produces bit-identical sampled indices, losses and weights
+        (tests/test_gpu_edges.py::test_sidecar_resume_is_bit_identical)."""
         lh = self._lh
-        np.savez(path, online=lh.get_params(_lib.ONLINE).cpu().numpy(), target=lh.get_params(_lib.TARGET).cpu().numpy(),
-                 adam_m=lh.get_params(_lib.ADAM_M).cpu().numpy(), adam_v=lh.get_params(_lib.ADAM_V).cpu().numpy(),
-                 adam_t=self._adam_t, learn_calls=self._learn_calls, step=self.step, seed=self.sampling_seed)
+        ring = self.replay_memory_buffer._ring
+        out = dict(format=np.int64(2), n_params=np.int64(lh.n_params), obs_dim=np.int64(self.online_network._obs_dim),
+                   n_actions=np.int64(self.output_dim), flavour=np.array([self._PER, self._DUELING, self._DOUBLE], np.int64),
+                   online=lh.get_params(_lib.ONLINE).cpu().numpy(), target=lh.get_params(_lib.TARGET).cpu().numpy(),
+                   adam_m=lh.get_params(_lib.ADAM_M).cpu().numpy(), adam_v=lh.get_params(_lib.ADAM_V).cpu().numpy(),
+                   adam_t=self._adam_t, learn_calls=self._learn_calls, step=self.step, seed=self.sampling_seed,
+                   episode_count=self.episode_count,
+                   ep_info=np.array([[e['r'], e['l']] for e in self.ep_info_buffer], np.float64).reshape(-1, 2))
+        if replay and ring.handle is not None:
+            st = ring.stats()
+            size = int(st.size)
+            out.update(replay_capacity=np.int64(st.capacity), replay_size=np.int64(size), replay_dp=np.int64(st.data_pointer),
+                       replay_rows=ring.read_rows(0, size) if size else np.zeros((0, ring.row_floats), np.float32))
+            if self._PER:
+                leaves = np.empty(size, np.float64)
+                if size:
+                    check(lib().rmc_replay_read_tree_sync(ring.handle, leaves.ctypes.data, int(st.capacity) - 1, size, stream_ptr(self._dev_index)))
+                pri = leaves.astype(np.float32)
+                assert np.array_equal(pri.astype(np.float64), leaves), "leaf priorities are float32-exact by construction"
+                out["replay_leaves"] = pri
+        if host_rng:
+            import pickle
+            out["host_rng"] = np.frombuffer(pickle.dumps((random.getstate(), np.random.get_state())), np.uint8)
+        np.savez(self._sidecar_path(path), **out)
 
     def load_learner_state(self, path):
-        z = np.load(path)
+        z = np.load(self._sidecar_path(path), allow_pickle=False)
         lh = self._lh
+        if "n_params" in z.files:       # format 2: validate before touching the learner
+            flavour = [int(v) for v in z["flavour"]]
+            if (int(z["n_params"]) != lh.n_params or int(z["obs_dim"]) != self.online_network._obs_dim or int(z["n_actions"]) != self.output_dim
+                    or flavour != [int(self._PER), int(self._DUELING), int(self._DOUBLE)]):
+                raise ValueError("side-car %s was written by a different agent (params %d, obs_dim %d, actions %d, PER/dueling/double %s)"
+                                 % (path, int(z["n_params"]), int(z["obs_dim"]), int(z["n_actions"]), flavour))
+        self._flush_step()
         for kind, key in ((_lib.ONLINE, "online"), (_lib.TARGET, "target"), (_lib.ADAM_M, "adam_m"), (_lib.ADAM_V, "adam_v")):
             lh.set_params(kind, T.as_tensor(z[key]))
         lh.version[_lib.ONLINE] += 1
@@ -374,6 +453,31 @@ class Agent:
         self.online_network._module_dirty = self.target_network._module_dirty = False
         self._adam_t, self._learn_calls, self.step = int(z["adam_t"]), int(z["learn_calls"]), int(z["step"])
         self.sampling_seed = int(z["seed"])
+        if "episode_count" in z.files:
+            self.episode_count = int(z["episode_count"])
+            self.ep_info_buffer.clear()
+            for r, l in z["ep_info"]:
+                self.ep_info_buffer.append({'r': float(r), 'l': float(l)})
+        if "replay_rows" in z.files:
+            ring = self.replay_memory_buffer._ring
+            if int(z["replay_capacity"]) != ring.capacity:
+                raise ValueError("side-car replay capacity %d differs from this agent's %d" % (int(z["replay_capacity"]), ring.capacity))
+            rows = np.ascontiguousarray(z["replay_rows"], np.float32)
+            if ring._handle is not None:      # start from an empty ring of the same shape
+                lib().rmc_replay_destroy(ring._handle)
+                ring._handle, ring._pending = None, 0
+            ring.ensure(self.online_network._obs_dim)
+            if rows.shape[1] != ring.row_floats:
+                raise ValueError("side-car replay rows have %d floats, this agent's have %d" % (rows.shape[1], ring.row_floats))
+            pri = np.ascontiguousarray(z["replay_leaves"], np.float32) if "replay_leaves" in z.files else None
+            check(lib().rmc_replay_load_host(ring._handle, rows.ctypes.data, None if pri is None else pri.ctypes.data, int(z["replay_size"]),
+                                             int(z["replay_dp"]), stream_ptr(self._dev_index)))
+            ring.count = int(z["replay_size"])
+        if "host_rng" in z.files:
+            import pickle
+            py_state, np_state = pickle.loads(z["host_rng"].tobytes())
+            random.setstate(py_state)
+            np.random.set_state(np_state)
 
     def info_mean(self, i):
         i_mean = np.mean([e[i] for e in self.ep_info_buffer]) if len(self.ep_info_buffer) else float('nan')

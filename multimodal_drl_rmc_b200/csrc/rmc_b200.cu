@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <mutex>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -239,6 +240,7 @@ struct rmc_comm {
   unsigned epoch = 0;
   unsigned* arrive = nullptr;
   unsigned* arrive_td = nullptr;
+  unsigned* verdict = nullptr;                  // [2] grid-uniform outcome of the waits (comm_wait_all)
   long long* g_nodes = nullptr;                 // gathered (leaf, |td|) of the whole batch + their priorities
   float* g_td = nullptr;
   float* g_pri = nullptr;
@@ -255,6 +257,11 @@ struct rmc_group {
   unsigned barrier_count = 0;
   unsigned epoch = 0;
 };
+
+static int32_t step_resident_ctas(int device, int smem_bytes, int* out);
+extern "C" int32_t rmc_replay_destroy(rmc_replay_t* r);
+extern "C" int32_t rmc_learner_destroy(rmc_learner_t* l);
+extern "C" int32_t rmc_comm_destroy(rmc_comm_t* c);
 
 // ------------------------------------------------------------------------------ library
 extern "C" int32_t rmc_abi_version(void) { return RMC_ABI_VERSION; }
@@ -279,7 +286,7 @@ __global__ void k_fill_f32(float* p, long long n, float v) {
 }
 __global__ void k_init_state(ReplayState* st) {
   st->size = 0; st->dp = 0; st->max_p = 0.f; st->min_p = __int_as_float(0x7f800000); st->cnt_max = 0; st->cnt_min = 0;
-  st->push_p = 1.f; st->pad = 0;
+  st->push_p = 1.f; st->bad_nodes = 0;
 }
 
 // ------------------------------------------------------------------------------ replay
@@ -297,29 +304,37 @@ extern "C" int32_t rmc_replay_create(rmc_replay_t** out, int64_t capacity, int32
   r->n_nodes = 2 * capacity - 1;
   ReplayDev& d = r->dev;
   d.cap = capacity; d.row_floats = r->rf; d.obs_dim = obs_dim; d.prioritized = r->prioritized;
-  int32_t e = RMC_OK;
-  if ((e = dev_alloc(&d.ring, static_cast<size_t>(capacity) * r->rf))) return e;
-  if ((e = dev_alloc(&d.st, 1))) return e;
-  k_init_state<<<1, 1>>>(d.st);
-  RMC_KERNEL_OK();
-  if (r->prioritized) {
-    if ((e = dev_alloc(&d.tree, static_cast<size_t>(r->n_nodes)))) return e;
-    if ((e = dev_alloc(&d.stamps, static_cast<size_t>(capacity)))) return e;
-    if ((e = dev_alloc(&d.scratch_old, kTreeCtaMax))) return e;
-    if ((e = dev_alloc(&d.team_part, kTreeTeam))) return e;
-    if ((e = dev_alloc(&d.team_ctr, 1))) return e;
+  auto build = [&]() -> int32_t {
+    int32_t e = RMC_OK;
+    if ((e = dev_alloc(&d.ring, static_cast<size_t>(capacity) * r->rf))) return e;
+    if ((e = dev_alloc(&d.st, 1))) return e;
+    k_init_state<<<1, 1>>>(d.st);
+    RMC_KERNEL_OK();
+    if (r->prioritized) {
+      if ((e = dev_alloc(&d.tree, static_cast<size_t>(r->n_nodes)))) return e;
+      if ((e = dev_alloc(&d.stamps, static_cast<size_t>(capacity)))) return e;
+      if ((e = dev_alloc(&d.scratch_old, kTreeCtaMax))) return e;
+      if ((e = dev_alloc(&d.team_part, kTreeTeam))) return e;
+      if ((e = dev_alloc(&d.team_ctr, 1))) return e;
+    }
+    if ((e = dev_alloc(&r->scratch_nodes, kTreeCtaMax))) return e;
+    if ((e = dev_alloc(&r->scratch_pri, kTreeCtaMax))) return e;
+    if ((e = dev_alloc(&r->ext_parts, kExtBlocks))) return e;
+    if ((e = dev_alloc(&r->ext_arrive, 1))) return e;
+    r->stage_rows = 16384;
+    for (int s = 0; s < kStageSlots; ++s) {
+      RMC_CUDA(cudaMallocHost(reinterpret_cast<void**>(&r->pin[s]), static_cast<size_t>(r->stage_rows) * r->rf * sizeof(float)));
+      if ((e = dev_alloc(&r->dstage[s], static_cast<size_t>(r->stage_rows) * r->rf, false))) return e;
+      RMC_CUDA(cudaEventCreateWithFlags(&r->ev[s], cudaEventDisableTiming));
+    }
+    RMC_CUDA(cudaDeviceSynchronize());
+    return RMC_OK;
+  };
+  if (int32_t e = build()) {          // a partially built handle is released by its own destroy function
+    const std::string msg = g_err;
+    rmc_replay_destroy(r);
+    return fail(e, msg);
   }
-  if ((e = dev_alloc(&r->scratch_nodes, kTreeCtaMax))) return e;
-  if ((e = dev_alloc(&r->scratch_pri, kTreeCtaMax))) return e;
-  if ((e = dev_alloc(&r->ext_parts, kExtBlocks))) return e;
-  if ((e = dev_alloc(&r->ext_arrive, 1))) return e;
-  r->stage_rows = 16384;
-  for (int s = 0; s < kStageSlots; ++s) {
-    RMC_CUDA(cudaMallocHost(reinterpret_cast<void**>(&r->pin[s]), static_cast<size_t>(r->stage_rows) * r->rf * sizeof(float)));
-    if ((e = dev_alloc(&r->dstage[s], static_cast<size_t>(r->stage_rows) * r->rf, false))) return e;
-    RMC_CUDA(cudaEventCreateWithFlags(&r->ev[s], cudaEventDisableTiming));
-  }
-  RMC_CUDA(cudaDeviceSynchronize());
   *out = r;
   return RMC_OK;
 }
@@ -467,6 +482,66 @@ extern "C" int32_t rmc_replay_set_priorities(rmc_replay_t* r, const float* pri_d
   return minmax_rebuild(r, st);
 }
 
+// Exact-resume side-car: put back a replay that rmc_replay_read_rows_sync / read_tree_sync saved.  Rows go to
+// slots [0, size) through the pinned staging ring, the float32-exact leaf priorities to the leaves, then the inner nodes and
+// the extremes are rebuilt (sums of float32-exact values are exact in float64, so the rebuilt tree equals the saved one bit
+// for bit) and (size, data_pointer) are set -- the next sample / push behaves as if the process had never stopped.
+__global__ void k_load_rows(ReplayDev R, const float* __restrict__ rows, long long first_slot, long long n) {
+  const long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (t < n * R.row_floats) R.ring[first_slot * R.row_floats + t] = rows[t];
+}
+__global__ void k_load_leaves(ReplayDev R, const float* __restrict__ pri, long long first_slot, long long n) {
+  const long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (t < n) R.tree[R.cap - 1 + first_slot + t] = static_cast<double>(pri[t]);
+}
+extern "C" int32_t rmc_replay_load_host(rmc_replay_t* r, const float* rows_host, const float* leaf_pri_host, int64_t size, int64_t data_pointer,
+                                        rmc_stream_t s) {
+  if (!r || size < 0 || size > r->cap || data_pointer < 0 || data_pointer >= r->cap || (size > 0 && !rows_host))
+    return fail(RMC_ERR_ARG, "rmc_replay_load_host: bad size / data_pointer");
+  if (size < r->cap && data_pointer != size % r->cap) return fail(RMC_ERR_ARG, "rmc_replay_load_host: a ring that has not wrapped has data_pointer == size");
+  if (r->prioritized && size > 0 && !leaf_pri_host) return fail(RMC_ERR_ARG, "rmc_replay_load_host: prioritized replay needs the leaf priorities");
+  if (int32_t e = use_device(r->device)) return e;
+  cudaStream_t st = as_stream(s);
+  for (long long off = 0; off < size; off += r->stage_rows) {
+    const long long m = std::min<long long>(r->stage_rows, size - off);
+    const int sl = r->slot;
+    r->slot = (r->slot + 1) % kStageSlots;
+    if (r->ev_used[sl]) RMC_CUDA(cudaEventSynchronize(r->ev[sl]));
+    std::memcpy(r->pin[sl], rows_host + off * r->rf, static_cast<size_t>(m) * r->rf * sizeof(float));
+    RMC_CUDA(cudaMemcpyAsync(r->dstage[sl], r->pin[sl], static_cast<size_t>(m) * r->rf * sizeof(float), cudaMemcpyHostToDevice, st));
+    k_load_rows<<<blocks_for(m * r->rf, 256), 256, 0, st>>>(r->dev, r->dstage[sl], off, m);
+    RMC_KERNEL_OK();
+    RMC_CUDA(cudaEventRecord(r->ev[sl], st));
+    r->ev_used[sl] = true;
+  }
+  if (r->prioritized) {
+    RMC_CUDA(cudaMemsetAsync(r->dev.tree, 0, static_cast<size_t>(r->n_nodes) * sizeof(double), st));
+    const long long per = r->stage_rows * r->rf;      // floats per staging slot
+    for (long long off = 0; off < size; off += per) {
+      const long long m = std::min<long long>(per, size - off);
+      const int sl = r->slot;
+      r->slot = (r->slot + 1) % kStageSlots;
+      if (r->ev_used[sl]) RMC_CUDA(cudaEventSynchronize(r->ev[sl]));
+      std::memcpy(r->pin[sl], leaf_pri_host + off, static_cast<size_t>(m) * sizeof(float));
+      RMC_CUDA(cudaMemcpyAsync(r->dstage[sl], r->pin[sl], static_cast<size_t>(m) * sizeof(float), cudaMemcpyHostToDevice, st));
+      k_load_leaves<<<blocks_for(m, 256), 256, 0, st>>>(r->dev, r->dstage[sl], off, m);
+      RMC_KERNEL_OK();
+      RMC_CUDA(cudaEventRecord(r->ev[sl], st));
+      r->ev_used[sl] = true;
+    }
+  }
+  k_push_end<<<1, 1, 0, st>>>(r->dev, data_pointer, size);
+  RMC_KERNEL_OK();
+  r->dp = data_pointer;
+  r->size = size;
+  if (r->prioritized) {
+    if (int32_t e = tree_rebuild(r, st)) return e;
+    if (int32_t e = minmax_rebuild(r, st)) return e;
+  }
+  RMC_CUDA(cudaStreamSynchronize(st));
+  return RMC_OK;
+}
+
 extern "C" int32_t rmc_replay_stats_sync(rmc_replay_t* r, rmc_replay_stats_t* out, rmc_stream_t s) {
   if (!r || !out) return fail(RMC_ERR_ARG, "rmc_replay_stats_sync: null");
   if (int32_t e = use_device(r->device)) return e;
@@ -482,6 +557,7 @@ extern "C" int32_t rmc_replay_stats_sync(rmc_replay_t* r, rmc_replay_stats_t* ou
   out->total_priority = total;
   out->max_priority = (hs.size > 0 && r->prioritized) ? static_cast<double>(hs.max_p) : 0.0;
   out->min_priority = (hs.size > 0 && r->prioritized) ? static_cast<double>(hs.min_p) : 0.0;
+  out->rejected_nodes = hs.bad_nodes;
   return RMC_OK;
 }
 
@@ -636,17 +712,7 @@ static int32_t owned_alloc(rmc_learner* l, T** p, size_t count) {
   return RMC_OK;
 }
 
-extern "C" int32_t rmc_learner_create(rmc_learner_t** out, const rmc_net_spec_t* spec, const rmc_hyper_t* hyper, int64_t max_batch,
-                                      int32_t device) {
-  if (!out || !spec || !hyper || max_batch < 1) return fail(RMC_ERR_ARG, "rmc_learner_create: null/bad args");
-  if (spec->hidden1 != kH1 || spec->hidden2 != kH2)
-    return fail(RMC_ERR_UNSUPPORTED, "rmc_learner_create: only the macro MLP body 256-128 is built (no fallback path)");
-  if (spec->activation != RMC_ACT_RELU && spec->activation != RMC_ACT_ELU)
-    return fail(RMC_ERR_UNSUPPORTED, "rmc_learner_create: hidden activation must be ReLU or ELU(alpha=1)");
-  if (spec->obs_dim < 1 || spec->obs_dim > kMaxD || spec->n_actions < 1 || spec->n_actions > 15)
-    return fail(RMC_ERR_UNSUPPORTED, "rmc_learner_create: obs_dim must be 1..32 and n_actions 1..15");
-  if (int32_t e = use_device(device)) return e;
-  auto* l = new rmc_learner();
+static int32_t learner_build_mlp(rmc_learner* l, const rmc_net_spec_t* spec, const rmc_hyper_t* hyper, int64_t max_batch, int32_t device) {
   l->device = device;
   l->spec = *spec;
   l->hyper = *hyper;
@@ -663,6 +729,11 @@ extern "C" int32_t rmc_learner_create(rmc_learner_t** out, const rmc_net_spec_t*
   RMC_CUDA(cudaFuncSetAttribute(k_learner_step<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, l->smem_bytes));
   RMC_CUDA(cudaFuncSetAttribute(k_learner_step<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, l->smem_bytes));
   RMC_CUDA(cudaFuncSetAttribute(k_mlp_infer, cudaFuncAttributeMaxDynamicSharedMemorySize, l->smem_bytes));
+  {
+    int resident = 0;
+    if (int32_t e2 = step_resident_ctas(device, l->smem_bytes, &resident)) return e2;
+    if (resident < l->num_sms) return fail(RMC_ERR_UNSUPPORTED, "rmc_learner_create: the fused step's grid (one CTA per SM) would not be co-resident on this device");
+  }
   const std::vector<int> map = make_param_map(l->L);
   l->P = static_cast<long long>(map.size());
   int32_t e = RMC_OK;
@@ -698,7 +769,7 @@ extern "C" int32_t rmc_learner_create(rmc_learner_t** out, const rmc_net_spec_t*
     float* dp = nullptr;
     if (cudaHostAlloc(reinterpret_cast<void**>(&hp), 64, cudaHostAllocMapped) == cudaSuccess &&
         cudaHostGetDevicePointer(reinterpret_cast<void**>(&dp), hp, 0) == cudaSuccess) {
-      hp[0] = 0.f; hp[1] = 0.f;
+      for (int k = 0; k < 16; ++k) hp[k] = 0.f;
       l->host_loss = hp;
       c.host_loss = dp;
     } else {
@@ -708,6 +779,26 @@ extern "C" int32_t rmc_learner_create(rmc_learner_t** out, const rmc_net_spec_t*
   }
   if ((e = owned_alloc(l, &l->dbg_buf, 1024 * 16 + 128))) return e;
   RMC_CUDA(cudaDeviceSynchronize());
+  return RMC_OK;
+}
+
+
+extern "C" int32_t rmc_learner_create(rmc_learner_t** out, const rmc_net_spec_t* spec, const rmc_hyper_t* hyper, int64_t max_batch,
+                                      int32_t device) {
+  if (!out || !spec || !hyper || max_batch < 1) return fail(RMC_ERR_ARG, "rmc_learner_create: null/bad args");
+  if (spec->hidden1 != kH1 || spec->hidden2 != kH2)
+    return fail(RMC_ERR_UNSUPPORTED, "rmc_learner_create: only the macro MLP body 256-128 is built (no fallback path)");
+  if (spec->activation != RMC_ACT_RELU && spec->activation != RMC_ACT_ELU)
+    return fail(RMC_ERR_UNSUPPORTED, "rmc_learner_create: hidden activation must be ReLU or ELU(alpha=1)");
+  if (spec->obs_dim < 1 || spec->obs_dim > kMaxD || spec->n_actions < 1 || spec->n_actions > 15)
+    return fail(RMC_ERR_UNSUPPORTED, "rmc_learner_create: obs_dim must be 1..32 and n_actions 1..15");
+  if (int32_t e = use_device(device)) return e;
+  auto* l = new rmc_learner();
+  if (int32_t e = learner_build_mlp(l, spec, hyper, max_batch, device)) {     // a partially built handle is released by its destroy function
+    const std::string msg = g_err;
+    rmc_learner_destroy(l);
+    return fail(e, msg);
+  }
   *out = l;
   return RMC_OK;
 }
@@ -825,23 +916,54 @@ static int32_t check_step(const rmc_learner* l, const rmc_replay* r, const rmc_s
   return RMC_OK;
 }
 
-// One launch of the fused step.  Default: cooperative launch (co-residency of the agent barrier's CTAs is
-// guaranteed by the driver).  RMC_LAUNCH=plain / pdl are diagnostics that measure the launch-gap cost of
-// that guarantee (a plain launch of <= #SM single-CTA/SM blocks is co-resident on an otherwise idle GPU).
+// One launch of the fused step.  Its in-kernel agent barrier and hand-off words need every CTA of the grid co-resident.
+//   pdl (default)  programmatic dependent launch: the next step's launch latency and prologue overlap this step's tail
+//                  (idle gap between steps 4.9 -> 2.2 us).  Co-residency is established by construction instead of by
+//                  the driver: the grid never exceeds the number of CTAs that fit the device at once (checked against the
+//                  occupancy calculator when the learner / group is created), steps of one stream are stream-ordered, and
+//                  fused-step launches of ONE device on DIFFERENT streams are serialised here with an event edge -- so two
+//                  grids of this kernel never share the device half-scheduled (the only way the barrier could wait for a
+//                  CTA that cannot start).  Kernels of other libraries on other streams finish by themselves and only
+//                  delay a step.  What remains uncovered is a second PROCESS running this kernel on the same GPU through
+//                  MPS: the in-kernel watchdog (SpinGuard) turns that into RMC_ERR_STATE instead of a hang; use
+//                  RMC_LAUNCH=coop there.
+//   coop           cooperative launch (driver-guaranteed co-residency; no overlap with the previous step's tail)
+//   plain / pdlcoop  diagnostics
 static int launch_mode() {
   static int mode = -1;
   if (mode < 0) {
     const char* e = std::getenv("RMC_LAUNCH");
-    mode = (e && std::strcmp(e, "plain") == 0) ? 1 : (e && std::strcmp(e, "pdl") == 0) ? 2 : (e && std::strcmp(e, "pdlcoop") == 0) ? 3 : 0;
+    mode = (e && std::strcmp(e, "plain") == 0) ? 1 : (e && std::strcmp(e, "coop") == 0) ? 0 : (e && std::strcmp(e, "pdlcoop") == 0) ? 3 : 2;
   }
   return mode;
 }
-static int32_t launch_step(dim3 grid, void** args, size_t smem, cudaStream_t st, bool one_tile) {
+static constexpr int kMaxDevices = 64;
+struct StepStreamGuard {            // per device: the stream the last fused-step launch went to
+  std::mutex mu;
+  bool any = false;
+  cudaStream_t last = nullptr;
+  cudaEvent_t ev = nullptr;
+};
+static StepStreamGuard g_step_guard[kMaxDevices];
+
+static int32_t launch_step(int device, dim3 grid, void** args, size_t smem, cudaStream_t st, bool one_tile) {
   const int mode = launch_mode();
   void* fn = one_tile ? reinterpret_cast<void*>(k_learner_step<true>) : reinterpret_cast<void*>(k_learner_step<false>);
   if (mode == 0) {
     RMC_CUDA(cudaLaunchCooperativeKernel(fn, grid, dim3(kThreads, 1, 1), args, smem, st));
   } else {
+    StepStreamGuard& G = g_step_guard[device >= 0 && device < kMaxDevices ? device : 0];
+    std::lock_guard<std::mutex> lock(G.mu);
+    if (G.any && G.last != st) {      // stream switch: this grid starts only after everything queued on the previous stream
+      if (G.ev == nullptr) RMC_CUDA(cudaEventCreateWithFlags(&G.ev, cudaEventDisableTiming));
+      if (cudaEventRecord(G.ev, G.last) == cudaSuccess) {
+        RMC_CUDA(cudaStreamWaitEvent(st, G.ev, 0));
+      } else {                        // the previous stream no longer exists: its work is ordered by a device-wide wait
+        cudaGetLastError();
+        RMC_CUDA(cudaDeviceSynchronize());
+      }
+    }
+    G.any = true; G.last = st;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid; cfg.blockDim = dim3(kThreads, 1, 1); cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute at[2];
@@ -853,6 +975,15 @@ static int32_t launch_step(dim3 grid, void** args, size_t smem, cudaStream_t st,
     RMC_CUDA(cudaLaunchKernelExC(&cfg, fn, args));
   }
   g_launches.fetch_add(1, std::memory_order_relaxed);
+  return RMC_OK;
+}
+// co-residency by construction: how many CTAs of the fused step fit the device at once
+static int32_t step_resident_ctas(int device, int smem_bytes, int* out) {
+  int per_sm_a = 0, per_sm_b = 0, sms = 0;
+  RMC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  RMC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_a, k_learner_step<true>, kThreads, static_cast<size_t>(smem_bytes)));
+  RMC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_b, k_learner_step<false>, kThreads, static_cast<size_t>(smem_bytes)));
+  *out = std::min(per_sm_a, per_sm_b) * sms;
   return RMC_OK;
 }
 
@@ -1105,6 +1236,7 @@ extern "C" int32_t rmc_learner_create_hybrid(rmc_learner_t** out, const rmc_hybr
   const int P = po;
   N.total = round4(P);
   auto* l = new rmc_learner();
+  auto build = [&]() -> int32_t {
   l->device = device; l->hybrid = true; l->H = N; l->hyper = *hyper; l->max_batch = max_batch;
   l->spec.obs_dim = N.D; l->spec.n_actions = N.A; l->spec.dueling = N.dueling; l->spec.double_dqn = sp->double_dqn; l->spec.prioritized = sp->prioritized;
   l->spec.activation = sp->activation; l->spec.hidden1 = 0; l->spec.hidden2 = 0;
@@ -1150,7 +1282,7 @@ extern "C" int32_t rmc_learner_create_hybrid(rmc_learner_t** out, const rmc_hybr
     float* dp = nullptr;
     if (cudaHostAlloc(reinterpret_cast<void**>(&hp), 64, cudaHostAllocMapped) == cudaSuccess &&
         cudaHostGetDevicePointer(reinterpret_cast<void**>(&dp), hp, 0) == cudaSuccess) {
-      hp[0] = 0.f; hp[1] = 0.f;
+      for (int k = 0; k < 16; ++k) hp[k] = 0.f;
       l->host_loss = hp;
       c.host_loss = dp;
     } else {
@@ -1159,6 +1291,13 @@ extern "C" int32_t rmc_learner_create_hybrid(rmc_learner_t** out, const rmc_hybr
     }
   }
   RMC_CUDA(cudaDeviceSynchronize());
+  return RMC_OK;
+  };
+  if (int32_t e = build()) {
+    const std::string msg = g_err;
+    rmc_learner_destroy(l);
+    return fail(e, msg);
+  }
   *out = l;
   return RMC_OK;
 }
@@ -1473,7 +1612,7 @@ extern "C" int32_t rmc_learner_step(rmc_learner_t* l, rmc_replay_t* r, const rmc
   l->last_grid = G;
   const AgentCtx* many = nullptr;
   void* args[] = {&single, &many, &S};
-  if (int32_t e = launch_step(dim3(G, 1, 1), args, static_cast<size_t>(l->smem_bytes), st, one_tile_ok(S, n_tiles))) return e;
+  if (int32_t e = launch_step(l->device, dim3(G, 1, 1), args, static_cast<size_t>(l->smem_bytes), st, one_tile_ok(S, n_tiles))) return e;
   if (rows && phase_b) l->barrier_count = S.barrier_target;
   if ((a->phases & RMC_PH_FORWARD) && phase_b) l->loss_epoch = S.epoch;
   if (a->phases & RMC_PH_ADAM) ++l->online_version;
@@ -1511,15 +1650,26 @@ extern "C" int32_t rmc_comm_create(rmc_comm_t** out, rmc_learner_t* l, int32_t r
   V.off_td = V.off_nodes + up(c->local_max * 8);
   V.slot_bytes = V.off_td + up(c->local_max * 4);
   c->bytes = static_cast<size_t>(kCommHeaderBytes + 2 * V.slot_bytes);
-  RMC_CUDA(cudaMalloc(reinterpret_cast<void**>(&c->local), c->bytes));
-  RMC_CUDA(cudaMemset(c->local, 0, c->bytes));
-  int32_t e = RMC_OK;
-  if ((e = dev_alloc(&c->arrive, 1))) return e;
-  if ((e = dev_alloc(&c->arrive_td, 1))) return e;
-  if ((e = dev_alloc(&c->g_nodes, static_cast<size_t>(global_batch_max)))) return e;
-  if ((e = dev_alloc(&c->g_td, static_cast<size_t>(global_batch_max)))) return e;
-  if ((e = dev_alloc(&c->g_pri, static_cast<size_t>(global_batch_max)))) return e;
-  RMC_CUDA(cudaDeviceSynchronize());
+  {
+    const char* t = std::getenv("RMC_COMM_TIMEOUT_MS");
+    const double ms = t ? std::atof(t) : 10000.0;
+    V.timeout_ns = static_cast<unsigned long long>((ms > 0 ? ms : 10000.0) * 1e6);
+  }
+  auto build = [&]() -> int32_t {
+    RMC_CUDA(cudaMalloc(reinterpret_cast<void**>(&c->local), c->bytes));
+    RMC_CUDA(cudaMemset(c->local, 0, c->bytes));
+    int32_t e = RMC_OK;
+    if ((e = dev_alloc(&c->arrive, 1))) return e;
+    if ((e = dev_alloc(&c->arrive_td, 1))) return e;
+    if ((e = dev_alloc(&c->verdict, 2))) return e;
+    if ((e = dev_alloc(&c->g_nodes, static_cast<size_t>(global_batch_max)))) return e;
+    if ((e = dev_alloc(&c->g_td, static_cast<size_t>(global_batch_max)))) return e;
+    if ((e = dev_alloc(&c->g_pri, static_cast<size_t>(global_batch_max)))) return e;
+    RMC_CUDA(cudaDeviceSynchronize());
+    return RMC_OK;
+  };
+  if (int32_t e = build()) { rmc_comm_destroy(c); return e; }      // partially built handle: released by its destroy function
+  V.verdict = c->verdict;
   *out = c;
   return RMC_OK;
 }
@@ -1573,7 +1723,7 @@ extern "C" int32_t rmc_comm_destroy(rmc_comm_t* c) {
   cudaDeviceSynchronize();
   for (int r = 0; r < c->world; ++r)
     if (c->ipc_opened[r]) cudaIpcCloseMemHandle(c->peer[r]);
-  cudaFree(c->local); cudaFree(c->arrive); cudaFree(c->arrive_td); cudaFree(c->g_nodes); cudaFree(c->g_td); cudaFree(c->g_pri);
+  cudaFree(c->local); cudaFree(c->arrive); cudaFree(c->arrive_td); cudaFree(c->verdict); cudaFree(c->g_nodes); cudaFree(c->g_td); cudaFree(c->g_pri);
   delete c;
   return RMC_OK;
 }
@@ -1703,9 +1853,28 @@ extern "C" int32_t rmc_learner_output(rmc_learner_t* l, const char* name, void**
   return fail(RMC_ERR_ARG, std::string("rmc_learner_output: unknown output ") + name);
 }
 
+// 0, or RMC_ERR_STATE when an in-kernel spin of one of this learner's launches timed out (device-side watchdog, SpinGuard)
+static int32_t step_health(const rmc_learner* l) {
+  if (l->host_loss == nullptr) return RMC_OK;
+  const float bits = l->host_loss[2];
+  unsigned bad = 0;
+  std::memcpy(&bad, &bits, sizeof(bad));
+  if (bad == 0) return RMC_OK;
+  return fail(RMC_ERR_STATE, "fused learner step: an in-kernel wait timed out (launch epoch " + std::to_string(bad & 0x7fffffffu) +
+                             "): the grid was not co-resident -- another process is sharing this GPU; set RMC_LAUNCH=coop");
+}
+extern "C" int32_t rmc_learner_status(rmc_learner_t* l, uint32_t* failed_epoch) {
+  if (!l) return fail(RMC_ERR_ARG, "rmc_learner_status: null");
+  unsigned bad = 0;
+  if (l->host_loss != nullptr) { const float bits = l->host_loss[2]; std::memcpy(&bad, &bits, sizeof(bad)); }
+  if (failed_epoch) *failed_epoch = bad;
+  return bad ? step_health(l) : RMC_OK;
+}
+
 extern "C" int32_t rmc_learner_loss_sync(rmc_learner_t* l, float* out_host, rmc_stream_t s) {
   if (!l || !out_host) return fail(RMC_ERR_ARG, "rmc_learner_loss_sync: null");
   if (int32_t e = use_device(l->device)) return e;
+  if (int32_t e = step_health(l)) return e;
   if (l->host_loss != nullptr && l->loss_epoch != 0) {
     // the step kernel stores (loss, epoch) straight into mapped host memory: wait for this launch's epoch
     unsigned want = l->loss_epoch, got = 0;
@@ -1715,7 +1884,7 @@ extern "C" int32_t rmc_learner_loss_sync(rmc_learner_t* l, float* out_host, rmc_
       if (got == want) {
         std::atomic_thread_fence(std::memory_order_acquire);
         *out_host = l->host_loss[0];
-        return RMC_OK;
+        return step_health(l);
       }
       if ((spin & 0xfff) == 0xfff && cudaStreamQuery(as_stream(s)) != cudaErrorNotReady) break;   // finished or faulted
     }
@@ -1893,6 +2062,8 @@ extern "C" int32_t rmc_group_create(rmc_group_t** out, rmc_learner_t* const* lea
     if (l->hybrid) return fail(RMC_ERR_UNSUPPORTED, "rmc_group_create: ensemble launches are built for the macro MLP only");
     if (std::memcmp(&l->spec, &l0->spec, sizeof(rmc_net_spec_t)) != 0 || l->max_batch != l0->max_batch || l->device != l0->device)
       return fail(RMC_ERR_ARG, "rmc_group_create: members must share spec, max_batch and device");
+    if (std::memcmp(&l->hyper, &l0->hyper, sizeof(rmc_hyper_t)) != 0)      // one launch carries ONE set of scalars (lr, gamma, tau, PER constants)
+      return fail(RMC_ERR_ARG, "rmc_group_create: members must share the hyper-parameters (rmc_hyper_t)");
     if (r->D != l->spec.obs_dim || (r->prioritized != 0) != (l->spec.prioritized != 0) || r->device != l->device)
       return fail(RMC_ERR_ARG, "rmc_group_create: replay/learner mismatch");
   }
@@ -1931,8 +2102,11 @@ extern "C" int32_t rmc_group_destroy(rmc_group_t* g) {
 extern "C" int32_t rmc_group_step(rmc_group_t* g, const rmc_step_args_t* a, rmc_stream_t s) {
   if (!g || !a) return fail(RMC_ERR_ARG, "rmc_group_step: null");
   rmc_learner* l0 = g->learners[0];
-  for (int i = 0; i < g->n; ++i)
+  for (int i = 0; i < g->n; ++i) {
     if (int32_t e = check_step(g->learners[i], g->replays[i], a)) return e;
+    if (std::memcmp(&g->learners[i]->hyper, &l0->hyper, sizeof(rmc_hyper_t)) != 0)
+      return fail(RMC_ERR_ARG, "rmc_group_step: a member's hyper-parameters were changed after rmc_group_create");
+  }
   if (a->batch > kTreeCtaMax && l0->spec.prioritized && (a->phases & RMC_PH_PRIORITY))
     return fail(RMC_ERR_UNSUPPORTED, "rmc_group_step: PER batches above 4096 are stepped per agent");
   if (int32_t e = use_device(l0->device)) return e;
@@ -1957,7 +2131,7 @@ extern "C" int32_t rmc_group_step(rmc_group_t* g, const rmc_step_args_t* a, rmc_
   AgentCtx single = l0->ctx;
   const AgentCtx* many = g->ctx_dev;
   void* args[] = {&single, &many, &S};
-  if (int32_t e = launch_step(dim3(G, g->n, 1), args, static_cast<size_t>(l0->smem_bytes), st, one_tile_ok(S, n_tiles))) return e;
+  if (int32_t e = launch_step(l0->device, dim3(G, g->n, 1), args, static_cast<size_t>(l0->smem_bytes), st, one_tile_ok(S, n_tiles))) return e;
   if (rows && phase_b) g->barrier_count = S.barrier_target;
   return RMC_OK;
 }

@@ -28,6 +28,8 @@ struct CommView {
   long long slot_bytes;                    // bytes of one parity slot
   long long off_loss, off_nodes, off_td;   // byte offsets inside a slot (gradients sit at 0)
   long long shard_lo[kCommMaxWorld + 1];   // global sample range of every rank
+  unsigned long long timeout_ns;           // how long a waiting kernel polls for the peers' flags (RMC_COMM_TIMEOUT_MS, default 10 s)
+  unsigned* verdict;                       // [2] local device words: {gradient exchange, (leaf,|td|) exchange}: (epoch << 1) | arrived
 };
 
 __device__ __forceinline__ unsigned char* comm_slot(const CommView& V, int r, int parity) {
@@ -50,6 +52,47 @@ __device__ __forceinline__ long long ld_sys_s64(const long long* p) {
   long long v;
   asm volatile("ld.relaxed.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
+}
+
+// Grid-uniform wait for the flags of all ranks (this rank's local flag array, one word per rank) to reach `epoch`.
+// EVERY block of the calling kernel returns the same answer, so an exchange is applied by all blocks or by none (a
+// per-block timer could let some blocks apply Adam while others give up).  Warp 0 of each block polls (lane r <-> rank r);
+// the first block to conclude -- all flags arrived, or `timeout_ns` elapsed -- publishes the verdict of this epoch in a
+// device word with a compare-and-swap from the previous epoch's value, the others adopt whatever verdict they find there.
+// On a timeout the epoch is also left in the error word of the header (rmc_comm_status_sync).
+__device__ __forceinline__ bool comm_wait_all(const CommView& V, const unsigned* flags, unsigned epoch, unsigned* verdict) {
+  __shared__ int s_ok;
+  if (threadIdx.x < 32) {
+    const unsigned lane = threadIdx.x;
+    unsigned d = __shfl_sync(0xffffffffu, ld_acquire_u32(verdict), 0);      // one view of the verdict per warp: the loop stays convergent
+    const unsigned long long t0 = global_timer_ns();
+    while ((d >> 1) != epoch) {
+      const bool here = (static_cast<int>(lane) >= V.world) || (ld_acquire_sys_u32(flags + lane) == epoch);
+      const bool all = __all_sync(0xffffffffu, here);
+      unsigned want = 0u;
+      if (all) want = (epoch << 1) | 1u;
+      else if (global_timer_ns() - t0 > V.timeout_ns) want = epoch << 1;
+      want = __shfl_sync(0xffffffffu, want, 0);          // lane 0's clock decides for the warp
+      if (want == 0u) {
+        __nanosleep(64);
+        d = __shfl_sync(0xffffffffu, ld_acquire_u32(verdict), 0);
+        continue;
+      }
+      if (lane == 0) {
+        __threadfence();                                  // the flags this warp acquired are visible to whoever adopts the verdict
+        const unsigned seen = atomicCAS(verdict, d, want);
+        d = (seen == d) ? want : seen;
+      }
+      d = __shfl_sync(0xffffffffu, d, 0);
+    }
+    if (lane == 0) {
+      s_ok = static_cast<int>(d & 1u);
+      if (!(d & 1u)) reinterpret_cast<unsigned*>(V.base[V.rank])[2 * kCommMaxWorld] = epoch;
+      __threadfence();
+    }
+  }
+  __syncthreads();
+  return s_ok != 0;
 }
 
 __global__ void __launch_bounds__(256) k_comm_publish(CommView V, int parity, unsigned epoch, const float* __restrict__ grads, int total,
@@ -107,20 +150,13 @@ __global__ void __launch_bounds__(256) k_comm_publish_td(CommView V, int parity,
 }
 __global__ void __launch_bounds__(256) k_comm_gather_td(CommView V, int parity, unsigned epoch, long long* __restrict__ g_nodes, float* __restrict__ g_td) {
   pdl_enter();
-  __shared__ int s_ok;
-  unsigned* my_flags = reinterpret_cast<unsigned*>(V.base[V.rank]);
-  if (threadIdx.x == 0) s_ok = 1;
-  __syncthreads();
-  if (threadIdx.x < V.world) {
-    const unsigned* f = my_flags + kCommTdFlagWord + parity * kCommMaxWorld + threadIdx.x;
-    const unsigned long long t0 = global_timer_ns();
-    while (ld_acquire_sys_u32(f) != epoch) {
-      if (global_timer_ns() - t0 > 4000000000ull) { s_ok = 0; my_flags[2 * kCommMaxWorld] = epoch; break; }
-      __nanosleep(64);
-    }
+  const unsigned* my_flags = reinterpret_cast<const unsigned*>(V.base[V.rank]);
+  if (!comm_wait_all(V, my_flags + kCommTdFlagWord + parity * kCommMaxWorld, epoch, V.verdict + 1)) {
+    // a peer never published its slice: hand the write-back that follows a list of out-of-range nodes (the tree kernels
+    // skip those), so that nothing of a half-arrived batch reaches the tree
+    for (long long k = blockIdx.x * 256ll + threadIdx.x; k < V.shard_lo[V.world]; k += static_cast<long long>(gridDim.x) * 256) { g_nodes[k] = -1; g_td[k] = 0.f; }
+    return;
   }
-  __syncthreads();
-  if (!s_ok) return;
   const long long stride = static_cast<long long>(gridDim.x) * 256;
   for (int r = 0; r < V.world; ++r) {
     const long long lo = V.shard_lo[r], n = V.shard_lo[r + 1] - lo;
@@ -137,24 +173,13 @@ __global__ void __launch_bounds__(256) k_comm_gather_td(CommView V, int parity, 
 __global__ void __launch_bounds__(256) k_comm_reduce_adam(AgentCtx C, StepScalars S, CommView V, int parity, unsigned epoch, int param_blocks,
                                                           long long* __restrict__ g_nodes, float* __restrict__ g_td, int want_gather, TcPackOut P) {
   pdl_enter();
-  __shared__ int s_ok;
-  unsigned* my_flags = reinterpret_cast<unsigned*>(V.base[V.rank]);
-  if (threadIdx.x == 0) s_ok = 1;
-  __syncthreads();
-  if (threadIdx.x < V.world) {
-    const unsigned* f = my_flags + parity * kCommMaxWorld + threadIdx.x;
-    const unsigned long long t0 = global_timer_ns();
-    while (ld_acquire_sys_u32(f) != epoch) {
-      if (global_timer_ns() - t0 > 4000000000ull) {      // 4 s: a peer died -- flag the error instead of hanging the GPU
-        s_ok = 0;
-        my_flags[2 * kCommMaxWorld] = epoch;
-        break;
-      }
-      __nanosleep(64);
-    }
+  const unsigned* my_flags = reinterpret_cast<const unsigned*>(V.base[V.rank]);
+  if (!comm_wait_all(V, my_flags + parity * kCommMaxWorld, epoch, V.verdict)) {
+    // all-or-nothing: no block applies Adam.  The (leaf, |td|) gather part hands the write-back out-of-range nodes.
+    if (want_gather && static_cast<int>(blockIdx.x) >= param_blocks)
+      for (long long k = (blockIdx.x - param_blocks) * 256ll + threadIdx.x; k < V.shard_lo[V.world]; k += static_cast<long long>(gridDim.x - param_blocks) * 256) { g_nodes[k] = -1; g_td[k] = 0.f; }
+    return;
   }
-  __syncthreads();
-  if (!s_ok) return;
   const NetLayout& L = C.L;
   if (static_cast<int>(blockIdx.x) < param_blocks) {
     const int pi = blockIdx.x * 256 + threadIdx.x;

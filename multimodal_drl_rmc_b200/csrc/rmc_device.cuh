@@ -74,17 +74,50 @@ __device__ __forceinline__ uint32_t ld_acquire_u32(const unsigned* p) {
   return v;
 }
 
-// Barrier across the CTAs of one agent inside ONE cooperative launch (all CTAs co-resident).
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// Watchdog of every in-kernel spin (agent barrier, hand-off words): the spins assume that all CTAs of the launch are
+// co-resident.  A cooperative launch guarantees it; the default programmatic-dependent launch relies on the host side
+// (grid <= #SM, one CTA per SM, fused-step launches of one device serialised across streams -- launch_step in
+// rmc_b200.cu).  If that assumption is ever broken (another process sharing the GPU through MPS, ...) the spin gives up
+// after kSpinTimeoutNs, records the launch's epoch in the mapped-host error word and lets the kernel terminate; the host
+// reports RMC_ERR_STATE at the next rmc_learner_loss_sync / rmc_learner_status.  The timer is read once per 1024 polls
+// (> 30 us of waiting), i.e. never in a healthy step.
+constexpr unsigned long long kSpinTimeoutNs = 2000000000ull;
+struct SpinGuard {
+  unsigned long long t0 = 0;
+  unsigned polls = 0;
+  __device__ __forceinline__ bool expired() {
+    if ((++polls & 0x3ffu) != 0u) return false;
+    const unsigned long long now = global_timer_ns();
+    if (t0 == 0) { t0 = now; return false; }
+    return now - t0 > kSpinTimeoutNs;
+  }
+};
+// err: mapped pinned host memory of the agent (AgentCtx::host_loss), word [2] = epoch of a launch whose spin timed out
+__device__ __forceinline__ void spin_report_timeout(volatile float* err, unsigned epoch) {
+  if (err != nullptr) {
+    err[2] = __uint_as_float(epoch);
+    __threadfence_system();
+  }
+}
+
+// Barrier across the CTAs of one agent inside ONE launch (all CTAs co-resident, see SpinGuard).
 // `ctr` only ever grows; `target` = value it must reach (wrap-safe signed comparison).
 __device__ __forceinline__ void red_release_add_u32(unsigned* p, unsigned v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ void agent_barrier(unsigned* ctr, unsigned target) {
+__device__ __forceinline__ void agent_barrier(unsigned* ctr, unsigned target, volatile float* err, unsigned epoch) {
   __syncthreads();
   if (threadIdx.x == 0) {
     red_release_add_u32(ctr, 1u);      // release: orders the CTA's writes (observed through the barrier above) before the arrival
+    SpinGuard guard;
     while (static_cast<int>(ld_acquire_u32(ctr) - target) < 0) {
       __nanosleep(32);
+      if (guard.expired()) { spin_report_timeout(err, epoch); break; }
     }
     __threadfence();
   }
@@ -98,11 +131,6 @@ __device__ __forceinline__ void pdl_enter() {
   asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
-__device__ __forceinline__ unsigned long long global_timer_ns() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
 #define RMC_STAMP(C, slot)                                                                 \
   do {                                                                                     \
     if ((C).dbg != nullptr && threadIdx.x == 0)                                            \
@@ -167,7 +195,7 @@ struct ReplayState {   // lives in HBM, updated by the kernels themselves
   long long cnt_max; // number of leaves equal to max_p
   long long cnt_min; // number of leaves equal to min_p
   float push_p;      // priority given to the rows of the current (chunked) push call
-  int pad;
+  int bad_nodes;     // entries of external index lists outside the leaf range that a write-back skipped (sticky count)
 };
 
 constexpr int kFlagWords = 16384;   // u32 words of AgentCtx::qt_flag per agent (layout: rmc_mlp.cuh)
@@ -230,7 +258,7 @@ struct AgentCtx {
   unsigned* barrier;
   unsigned* qt_flag;    // [kFlagWords] {epoch, payload} hand-off words of the fused step: Q_target(s') per (tile, row, action),
                         // |td| per row and the loss partial per tile (layout: rmc_mlp.cuh)
-  volatile float* host_loss;      // mapped pinned host memory: [0] loss of the last step, [1] its epoch (as bits)
+  volatile float* host_loss;      // mapped pinned host memory: [0] loss of the last step, [1] its epoch (as bits), [2] epoch of a launch whose in-kernel spin timed out (0 = healthy)
   unsigned long long* dbg;   // optional per-CTA phase timestamps [G][16] (nullptr = off)
 };
 

@@ -758,7 +758,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, c
           if (tid < kTM * kQLD) {
             const unsigned* wp = C.qt_flag + kQtWordBase + 2 * (tile * kTM * kQLD + tid);
             uint2 w = ld_relaxed_pair(wp);
-            while (w.x != S.epoch) { __nanosleep(20); w = ld_relaxed_pair(wp); }
+            SpinGuard guard;
+            while (w.x != S.epoch) {
+              __nanosleep(20);
+              w = ld_relaxed_pair(wp);
+              if (guard.expired()) { spin_report_timeout(C.host_loss, S.epoch); break; }
+            }
             sQT[tid] = __uint_as_float(w.y);
           }
           __syncthreads();
@@ -901,12 +906,21 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, c
       __shared__ float s_lp[kThreads];
       __syncthreads();
       if (tid == 0) red_release_add_u32(C.barrier, 1u);                  // arrive, do not wait
-      for (long long i = tid; i < B; i += kThreads)
-        while (ld_relaxed_pair(C.qt_flag + kTdWordBase + 2 * i).x != S.epoch) __nanosleep(20);
+      SpinGuard guard;
+      bool gave_up = false;
+      for (long long i = tid; i < B && !gave_up; i += kThreads)
+        while (ld_relaxed_pair(C.qt_flag + kTdWordBase + 2 * i).x != S.epoch) {
+          __nanosleep(20);
+          if (guard.expired()) { spin_report_timeout(C.host_loss, S.epoch); gave_up = true; break; }
+        }
       float lp = 0.f;
       if (tid < n_tiles) {
         uint2 w = ld_relaxed_pair(C.qt_flag + kLossWordBase + 2 * tid);
-        while (w.x != S.epoch) { __nanosleep(20); w = ld_relaxed_pair(C.qt_flag + kLossWordBase + 2 * tid); }
+        while (w.x != S.epoch && !gave_up) {
+          __nanosleep(20);
+          w = ld_relaxed_pair(C.qt_flag + kLossWordBase + 2 * tid);
+          if (guard.expired()) { spin_report_timeout(C.host_loss, S.epoch); gave_up = true; }
+        }
         lp = __uint_as_float(w.y);
       }
       __threadfence();                                                   // acquire side of the flag words
@@ -914,7 +928,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, c
       __syncthreads();
       if (cta == n_workers && tid == 0) publish_loss(C, S, s_lp, static_cast<int>(n_tiles));
     } else {
-      agent_barrier(C.barrier, S.barrier_target);
+      agent_barrier(C.barrier, S.barrier_target, C.host_loss, S.epoch);
     }
   }
   RMC_STAMP(C, 6);

@@ -215,8 +215,13 @@ __device__ void tree_update_cta(const ReplayDev& R, const long long* __restrict_
   // big trees: per-leaf atomics only below the top 9 levels, which are rebuilt afterwards
   const bool rebuild_top = (s_top_buf != nullptr) && (2 * R.cap - 1 >= 2 * kTopRebuild + 1);
   const long long first_fixed = rebuild_top ? kTopRebuild : 0;
+  // (index lists that come from outside the launch may hold anything: entries outside the leaf range are skipped and counted)
   if (!stamps_done)
-    for (long long i = tid; i < n; i += nt) atomicMax(R.stamps + (nodes[i] - first_leaf), static_cast<int>(i + 1));
+    for (long long i = tid; i < n; i += nt) {
+      const long long di = nodes[i] - first_leaf;
+      if (di >= 0 && di < R.cap) atomicMax(R.stamps + di, static_cast<int>(i + 1));
+      else atomicAdd(&R.st->bad_nodes, 1);
+    }
   __syncthreads();
   RMC_TSTAMP(9);
   // pass 1: elected writers apply; remember the overwritten value (-1: leaf was outside the old domain,
@@ -227,7 +232,7 @@ __device__ void tree_update_cta(const ReplayDev& R, const long long* __restrict_
     const long long di = leaf - first_leaf;
     int* st = R.stamps + di;
     float oldv = -2.f;
-    if (__ldcg(st) == static_cast<int>(i + 1)) {
+    if (di >= 0 && di < R.cap && __ldcg(st) == static_cast<int>(i + 1)) {
       *st = 0;
       const float p = pri[i];
       const double old = tree_set_leaf(R, leaf, p, old_vals ? old_vals + i : nullptr, first_fixed);
@@ -318,7 +323,7 @@ __device__ void tree_update_team(const ReplayDev& R, const long long* __restrict
   if (!sorted) {
     for (long long i = tid; i < n; i += nt) {
       const long long leaf = __ldcg(nodes + i);
-      if (depth3_owner(leaf) == member) {
+      if (leaf >= first_leaf && leaf - first_leaf < R.cap && depth3_owner(leaf) == member) {
         pri_out[i] = td_to_priority(__ldcg(abs_td + i * td_stride), eps, alpha, pmax);
         atomicMax(R.stamps + (leaf - first_leaf), static_cast<int>(i + 1));
       }
@@ -334,7 +339,7 @@ __device__ void tree_update_team(const ReplayDev& R, const long long* __restrict
   for (long long i = tid; i < n; i += nt) {
     const long long leaf = __ldcg(nodes + i);
     float oldv = -3.f, p = 0.f;
-    if (depth3_owner(leaf) == member) {
+    if (leaf >= first_leaf && leaf - first_leaf < R.cap && depth3_owner(leaf) == member) {
       oldv = -2.f;
       bool writer;
       if (sorted) {
@@ -375,7 +380,8 @@ __device__ void tree_update_team(const ReplayDev& R, const long long* __restrict
     b += (r_old == M0); d += (r_old == m0);
   }
   for (long long i = tid + nt; i < n; i += nt) {
-    if (depth3_owner(nodes[i]) == member) {
+    const long long leaf = nodes[i];
+    if (leaf >= first_leaf && leaf - first_leaf < R.cap && depth3_owner(leaf) == member) {
       const float oldv = R.scratch_old[i];
       if (oldv != -2.f) {
         const float p = pri_out[i];
@@ -489,7 +495,11 @@ __global__ void k_td_to_pri(const float* abs_td, float* pri, long long n, float 
 __global__ void k_tree_stamp(ReplayDev R, const long long* nodes, long long n) {
   pdl_enter();
   const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  if (i < n) atomicMax(R.stamps + (nodes[i] - (R.cap - 1)), static_cast<int>(i + 1));
+  if (i < n) {
+    const long long di = nodes[i] - (R.cap - 1);
+    if (di >= 0 && di < R.cap) atomicMax(R.stamps + di, static_cast<int>(i + 1));
+    else atomicAdd(&R.st->bad_nodes, 1);
+  }
 }
 // Leaf stores + float64 reductions on the ancestors at heap index >= first_fixed only (the contended top of the
 // tree is rebuilt afterwards by k_tree_rebuild_top; sums of f32-exact values are exact in any order, SURVEY finding 6).
@@ -498,8 +508,9 @@ __global__ void k_tree_apply(ReplayDev R, const long long* nodes, const float* p
   const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (i < n) {
     const long long leaf = nodes[i];
-    int* st = R.stamps + (leaf - (R.cap - 1));
-    if (__ldcg(st) == static_cast<int>(i + 1)) {
+    const long long di = leaf - (R.cap - 1);
+    int* st = R.stamps + di;
+    if (di >= 0 && di < R.cap && __ldcg(st) == static_cast<int>(i + 1)) {
       *st = 0;
       tree_set_leaf(R, leaf, pri[i], nullptr, first_fixed);
     }

@@ -119,6 +119,12 @@ class LearnerHandle:
         self.handle = h
         self.n_params = int(lib().rmc_learner_param_count(h))
         self.version = [0, 0]   # bumped whenever the blob of kind ONLINE / TARGET changes on the device
+        self._flush_hook = None  # set by the owning Agent: launches a learn() step it has recorded but not issued yet
+
+    def flush_pending(self):
+        """Agent.learn() is lazy (agent.py); every read or write of the learner's state goes through here first."""
+        if self._flush_hook is not None:
+            self._flush_hook()
 
     def __del__(self):
         try:
@@ -129,17 +135,20 @@ class LearnerHandle:
             pass
 
     def set_params(self, kind, flat):
+        self.flush_pending()
         flat = flat.contiguous()
-        check(lib().rmc_learner_set_params(self.handle, kind, ptr(flat), flat.numel(), int(not flat.is_cuda), stream_ptr()))
+        check(lib().rmc_learner_set_params(self.handle, kind, ptr(flat), flat.numel(), int(not flat.is_cuda), stream_ptr(self.device_index)))
 
     def get_params(self, kind, device=None):
+        self.flush_pending()
         dev = T.device("cuda", self.device_index) if device is None else device
         out = T.empty(self.n_params, dtype=T.float32, device=dev)
-        check(lib().rmc_learner_get_params(self.handle, kind, ptr(out), out.numel(), int(not out.is_cuda), stream_ptr()))
+        check(lib().rmc_learner_get_params(self.handle, kind, ptr(out), out.numel(), int(not out.is_cuda), stream_ptr(self.device_index)))
         return out
 
     def output(self, name, dtype=T.float32):
         """Zero-copy torch view of a per-step product (valid until the next step)."""
+        self.flush_pending()
         p, n = C.c_void_p(), C.c_int64()
         check(lib().rmc_learner_output(self.handle, name.encode(), C.byref(p), C.byref(n)))
         return _tensor_from_ptr(p.value, n.value, dtype, self.device_index)
@@ -202,6 +211,8 @@ class Network(nn.Module):
 
     def _push(self):
         """module tensors -> device blob."""
+        if self._lh is not None:
+            self._lh.flush_pending()
         if self._lh is not None and self._module_dirty:
             self._lh.set_params(self._kind, self._flat_module_params())
             self._lh.version[self._kind] += 1
@@ -210,6 +221,8 @@ class Network(nn.Module):
 
     def _pull(self):
         """device blob -> module tensors (after learner steps)."""
+        if self._lh is not None:
+            self._lh.flush_pending()
         if self._lh is not None and not self._module_dirty and self._seen_version != self._lh.version[self._kind]:
             flat = self._lh.get_params(self._kind)
             off = 0
@@ -253,7 +266,7 @@ class Network(nn.Module):
         squeeze = x.dim() == 1
         x = x.reshape(-1, self._obs_dim)
         q = T.empty(x.shape[0], self._n_actions, dtype=T.float32, device=dev)
-        check(lib().rmc_learner_q_values(lh.handle, self._kind, ptr(x), x.shape[0], ptr(q), stream_ptr()))
+        check(lib().rmc_learner_q_values(lh.handle, self._kind, ptr(x), x.shape[0], ptr(q), stream_ptr(lh.device_index)))
         return q[0] if squeeze else q
 
     def actions(self, obses, precision="fp32"):
@@ -267,18 +280,18 @@ class Network(nn.Module):
             dev = T.device("cuda", lh.device_index)
             x = T.as_tensor(obses, dtype=T.float32, device=dev).contiguous().reshape(-1, self._obs_dim)
             out = T.empty(x.shape[0], dtype=T.int64, device=dev)
-            check(lib().rmc_learner_act_tc(lh.handle, ptr(x), x.shape[0], ptr(out), stream_ptr()))
+            check(lib().rmc_learner_act_tc(lh.handle, ptr(x), x.shape[0], ptr(out), stream_ptr(lh.device_index)))
             return out.tolist()
         if precision != "fp32":
             raise ValueError("precision must be 'fp32' or 'bf16'")
         if T.is_tensor(obses) and obses.is_cuda:
             x = obses.to(T.float32).contiguous().reshape(-1, self._obs_dim)
             out = T.empty(x.shape[0], dtype=T.int64, device=x.device)
-            check(lib().rmc_learner_act(lh.handle, ptr(x), x.shape[0], ptr(out), stream_ptr()))
+            check(lib().rmc_learner_act(lh.handle, ptr(x), x.shape[0], ptr(out), stream_ptr(lh.device_index)))
             return out.tolist()
         x = np.ascontiguousarray(np.asarray(obses, dtype=np.float32)).reshape(-1, self._obs_dim)
         out = np.empty(x.shape[0], np.int64)
-        check(lib().rmc_learner_act_host_sync(lh.handle, x.ctypes.data, x.shape[0], out.ctypes.data, stream_ptr()))
+        check(lib().rmc_learner_act_host_sync(lh.handle, x.ctypes.data, x.shape[0], out.ctypes.data, stream_ptr(lh.device_index)))
         return out.tolist()
 
     # ---- checkpoints: format of network.py:27-47, byte compatible ------------------------------
@@ -332,7 +345,7 @@ class DuelingDeepQNetwork(Network):
         dev = T.device("cuda", lh.device_index)
         x = T.as_tensor(s, dtype=T.float32, device=dev).contiguous().reshape(-1, self._obs_dim)
         out = T.empty(x.shape[0], self._n_actions + 1, dtype=T.float32, device=dev)
-        check(lib().rmc_learner_heads(lh.handle, self._kind, ptr(x), x.shape[0], ptr(out), stream_ptr()))
+        check(lib().rmc_learner_heads(lh.handle, self._kind, ptr(x), x.shape[0], ptr(out), stream_ptr(lh.device_index)))
         return out
 
     def value(self, s):

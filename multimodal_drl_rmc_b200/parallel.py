@@ -32,6 +32,14 @@ class AgentEnsemble:
     def __init__(self, agents):
         self.agents = list(agents)
         n = len(self.agents)
+        a0 = self.agents[0]
+        for a in self.agents:       # the launch carries ONE set of scalars (agent 0's): members must agree on them
+            a._flush_step()
+            same = (type(a) is type(a0) and a.n_env == a0.n_env and a.batch_size == a0.batch_size and a.lr == a0.lr and a.gamma == a0.gamma
+                    and a.target_soft_update == a0.target_soft_update and a.target_soft_update_tau == a0.target_soft_update_tau
+                    and a.update_target_frequency == a0.update_target_frequency and a.epsilon_decay == a0.epsilon_decay)
+            if not same:
+                raise ValueError("AgentEnsemble members must share class, n_env, batch size, lr, gamma, target-update and epsilon-decay settings")
         lh = (C.c_void_p * n)(*[a._lh.handle for a in self.agents])
         rh = (C.c_void_p * n)(*[a.replay_memory_buffer._ring.require() for a in self.agents])
         g = C.c_void_p()
@@ -53,7 +61,10 @@ class AgentEnsemble:
         """One learner step of every member (dqn/agent.py learn() + update_target_network()).
         ``u`` / ``indices``: optional injected sampling randomness, shape [n_agents, batch]."""
         a0 = self.agents[0]
+        if any(a.step != a0.step for a in self.agents):
+            raise ValueError("AgentEnsemble.learn: members are at different steps (beta and the hard-sync schedule come from one step value)")
         for a in self.agents:
+            a._flush_step()                          # a lazily recorded single-agent learn()
             a.replay_memory_buffer._ring.flush()     # rows held back for a fused store + learn call
             a._learn_calls += 1
             a._adam_t += 1
@@ -114,6 +125,8 @@ class ShardedLearner:
         self.lo, self.hi = shard_range(self.B, self.rank, self.world)
         self._args = _lib.StepArgs()
         self._comm = None
+        self.status_every = 64      # peer exchange: poll the comm's error word every this many steps (a host-side sync)
+        self._steps = 0
         if exchange == "peer":
             h = C.c_void_p()
             check(lib().rmc_comm_create(C.byref(h), agent._lh.handle, self.rank, self.world, self.B))
@@ -155,6 +168,7 @@ class ShardedLearner:
 
     def _learn_peer(self, u, fuse_target_update, stages=3):
         ag = self.agent
+        ag._flush_step()
         if stages == 2:       # second half of a split step (emulated ranks): same arguments as the first half
             check(lib().rmc_learner_step_sharded(ag._lh.handle, ag.replay_memory_buffer._ring.require(), self._comm,
                                                  C.byref(self._args), 2, stream_ptr(ag.device.index)))
@@ -180,6 +194,12 @@ class ShardedLearner:
             ag._lh.version[_lib.TARGET] += 1
             ag._target_fused_for = ag._learn_calls
         self._keep = keep
+        self._steps += 1
+        if self.status_every and self._steps % self.status_every == 0 and stages == 3:
+            bad = self.exchange_status()
+            if bad:
+                raise RuntimeError("ShardedLearner: the peer exchange of step epoch %d timed out (a peer never published); "
+                                   "that step was skipped on this rank -- replicas may have diverged" % bad)
         return ag._lh.output("loss")
 
     def exchange_status(self):
@@ -194,6 +214,7 @@ class ShardedLearner:
         if self.exchange == "peer":
             return self._learn_peer(u, fuse_target_update, stages)
         ag, dist = self.agent, self.dist
+        ag._flush_step()
         lh = ag._lh
         rh = ag.replay_memory_buffer._ring.require()
         ag._learn_calls += 1
@@ -243,3 +264,30 @@ class ShardedLearner:
             ag._target_fused_for = ag._learn_calls
         self._keep = (keep, grads, loss)
         return loss
+
+
+def sharded_act(network, obses, group=None, gather=True, precision="fp32", rank=None, world=None):
+    """Batched greedy ``Network.actions`` (dqn/network.py:67-74, 110-117) with the rows split across the ranks (BASELINE
+    configs[2] on several GPUs): rows are independent, every rank holds a replica of the weights, rank r
+    evaluates rows ``shard_range(n, r, W)`` with the batched act kernel and -- ``gather=True`` -- the int64 actions are
+    all-gathered so every rank returns the full list in row order (the only communication: 8 bytes per state).  With
+    ``gather=False`` the rank's own slice is returned together with its row range.
+
+    ``obses``: [n, D] host array or CUDA tensor holding ALL rows (each rank reads only its slice)."""
+    if rank is None:
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+    else:
+        dist = None
+    n = len(obses)
+    lo, hi = shard_range(n, rank, world)
+    mine = network.actions(obses[lo:hi], precision=precision) if hi > lo else []
+    if not gather:
+        return mine, (lo, hi)
+    if dist is None:
+        raise ValueError("gather=True needs an initialised torch.distributed process group")
+    dev = T.device(network.device)
+    sizes = [shard_range(n, r, world) for r in range(world)]
+    parts = [T.empty(h - l, dtype=T.int64, device=dev) for l, h in sizes]
+    dist.all_gather(parts, T.as_tensor(mine, dtype=T.int64, device=dev), group=group)
+    return T.cat(parts).tolist()

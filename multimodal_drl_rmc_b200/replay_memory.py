@@ -25,6 +25,8 @@ class DeviceRing:
         self.device_index = device_index
         self._handle = None
         self._pending = 0           # rows of the current env step held back for the fused store + learn call
+        self._owner_flush = None    # set by the owning Agent: launches a recorded (lazy) learn() before the replay is touched
+        self.count = 0              # host mirror of the number of stored transitions (min(pushed, capacity))
         self.defer_small_pushes = False
         self.obs_dim = None
         self.row_floats = None
@@ -33,6 +35,8 @@ class DeviceRing:
     # stats, sampling, tree reads, explicit pushes ... all see the replay exactly as the reference would.
     @property
     def handle(self):
+        if self._owner_flush is not None:   # a recorded learn() samples the replay as it was when learn() was called
+            self._owner_flush()
         if self._pending:
             self.flush()
         return self._handle
@@ -89,7 +93,7 @@ class DeviceRing:
     # -- host-buffer push (what store_transitions uses) ---------------------------------
     def push_host(self, obses, actions, rews, dones, new_obses):
         n = len(actions)
-        if n <= 8 and self.handle is not None:      # (the handle access delivers rows held back earlier)
+        if n <= 8 and self.handle is not None:      # (the handle access launches a recorded learn() and delivers rows held back earlier)
             # per-env-step push: copy into preallocated scratch arrays whose addresses are cached
             b = self._small
             b[0][:n] = obses
@@ -97,6 +101,7 @@ class DeviceRing:
             b[2][:n] = rews
             b[3][:n] = dones
             b[4][:n] = new_obses
+            self.count = min(self.capacity, self.count + n)
             if self.defer_small_pushes:             # the Agent's next learn() carries them (one host call for store + learn)
                 self._pending = n
                 return
@@ -116,19 +121,21 @@ class DeviceRing:
         self.ensure(obs.shape[1])
         check(lib().rmc_replay_push_host(self.handle, obs.ctypes.data, act.ctypes.data, rew.ctypes.data,
                                          done.ctypes.data, nxt.ctypes.data, n, stream_ptr(self.device_index)))
+        self.count = min(self.capacity, self.count + n)
 
     def push_device(self, obs, act, rew, done, nxt):
         """torch CUDA tensors: obs/nxt float32 [n,D], act int64 [n], rew/done float32 [n]."""
         n = obs.shape[0]
         self.ensure(obs.shape[1])
-        check(lib().rmc_replay_push(self.handle, ptr(obs), ptr(act), ptr(rew), ptr(done), ptr(nxt), n, stream_ptr()))
+        check(lib().rmc_replay_push(self.handle, ptr(obs), ptr(act), ptr(rew), ptr(done), ptr(nxt), n, stream_ptr(self.device_index)))
+        self.count = min(self.capacity, self.count + n)
 
     def stats(self) -> _lib.ReplayStats:
         st = _lib.ReplayStats()
         if self.handle is None:
             st.capacity = self.capacity
             return st
-        check(lib().rmc_replay_stats_sync(self.handle, C.byref(st), stream_ptr()))
+        check(lib().rmc_replay_stats_sync(self.handle, C.byref(st), stream_ptr(self.device_index)))
         return st
 
     def rows_to_transitions(self, rows: np.ndarray):
@@ -140,7 +147,7 @@ class DeviceRing:
 
     def read_rows(self, first_slot: int, n: int) -> np.ndarray:
         out = np.empty((n, self.row_floats), np.float32)
-        check(lib().rmc_replay_read_rows_sync(self.require(), out.ctypes.data, int(first_slot), int(n), stream_ptr()))
+        check(lib().rmc_replay_read_rows_sync(self.require(), out.ctypes.data, int(first_slot), int(n), stream_ptr(self.device_index)))
         return out
 
 
@@ -205,7 +212,7 @@ class ReplayMemoryNaive(ReplayMemory):
         rows = torch.empty(B, self._ring.row_floats, dtype=torch.float32, device=dev)
         idx = None if indices is None else torch.as_tensor(np.asarray(indices, np.int64), device=dev)
         self._draws += 1
-        check(lib().rmc_uniform_sample(h, B, ptr(idx), self.seed, self._draws, ptr(slots), ptr(rows), stream_ptr()))
+        check(lib().rmc_uniform_sample(h, B, ptr(idx), self.seed, self._draws, ptr(slots), ptr(rows), stream_ptr(self._ring.device_index)))
         return self._ring.rows_to_transitions(rows.cpu().numpy())
 
 
@@ -231,7 +238,7 @@ class SumTree:
         n = 2 * self.capacity - 1
         out = np.zeros(n, np.float64)
         if self._ring.handle is not None:
-            check(lib().rmc_replay_read_tree_sync(self._ring.handle, out.ctypes.data, 0, n, stream_ptr()))
+            check(lib().rmc_replay_read_tree_sync(self._ring.handle, out.ctypes.data, 0, n, stream_ptr(self._ring.device_index)))
         return out
 
     @property
@@ -270,7 +277,7 @@ class SumTree:
         dev = torch.device("cuda", self._ring.device_index)
         nodes = torch.as_tensor([int(tree_index)], dtype=torch.int64, device=dev)
         pri = torch.as_tensor(np.asarray(priority, np.float32).reshape(1), device=dev)
-        check(lib().rmc_per_update(self._ring.require(), ptr(nodes), ptr(pri), 1, stream_ptr()))
+        check(lib().rmc_per_update(self._ring.require(), ptr(nodes), ptr(pri), 1, stream_ptr(self._ring.device_index)))
 
     def get_leaf(self, v):
         """sum_tree.py:42-61 -> (leaf_index, priority, transition)."""
@@ -279,7 +286,7 @@ class SumTree:
         vv = torch.as_tensor([float(v)], dtype=torch.float64, device=dev)
         node = torch.empty(1, dtype=torch.int64, device=dev)
         pri = torch.empty(1, dtype=torch.float64, device=dev)
-        check(lib().rmc_tree_get_leaf(self._ring.require(), ptr(vv), 1, ptr(node), ptr(pri), stream_ptr()))
+        check(lib().rmc_tree_get_leaf(self._ring.require(), ptr(vv), 1, ptr(node), ptr(pri), stream_ptr(self._ring.device_index)))
         leaf = int(node.item())
         row = self._ring.read_rows(leaf - self.capacity + 1, 1)
         return leaf, float(pri.item()), self._ring.rows_to_transitions(row)[0]
@@ -327,15 +334,19 @@ class ReplayMemoryPrioritized(ReplayMemory):
         rows = torch.empty(B, self._ring.row_floats, dtype=torch.float32, device=dev)
         self._draws += 1
         check(lib().rmc_per_sample(h, B, self.beta(step), ptr(u_t), self.seed, self._draws, ptr(nodes), ptr(w),
-                                   ptr(rows), stream_ptr()))
+                                   ptr(rows), stream_ptr(self._ring.device_index)))
         return (w.cpu().numpy().astype(np.float64).tolist(), nodes.cpu().tolist(),
                 self._ring.rows_to_transitions(rows.cpu().numpy()))
 
     def update_batch_priorities(self, tree_indices, abs_td_errors_np):
         torch = _lib.require_cuda()
         dev = torch.device("cuda", self._ring.device_index)
-        nodes = torch.as_tensor(np.asarray(tree_indices, np.int64).reshape(-1), device=dev)
+        idx = np.asarray(tree_indices, np.int64).reshape(-1)
+        cap = self._ring.capacity
+        if idx.size and (idx.min() < cap - 1 or idx.max() > 2 * cap - 2):      # the reference would raise IndexError / corrupt inner nodes
+            raise IndexError("tree_indices outside the leaf range [%d, %d]" % (cap - 1, 2 * cap - 2))
+        nodes = torch.as_tensor(idx, device=dev)
         td = torch.as_tensor(np.asarray(abs_td_errors_np, np.float32).reshape(-1), device=dev)
         pri = torch.empty_like(td)
         check(lib().rmc_per_update_from_td(self._ring.require(), ptr(nodes), ptr(td), nodes.numel(), self.epsilon,
-                                           self.alpha, self.max_priority_high, ptr(pri), stream_ptr()))
+                                           self.alpha, self.max_priority_high, ptr(pri), stream_ptr(self._ring.device_index)))

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol(built):
 
 def test_library_loads_and_reports_abi(built):
     h = _lib.lib()
-    assert h.rmc_abi_version() == 2
+    assert h.rmc_abi_version() == _lib.ABI_VERSION == 3
     assert h.rmc_launch_count() >= 0
 
 

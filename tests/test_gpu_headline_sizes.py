@@ -1,0 +1,90 @@
+"""-m gpu: parity at the sizes the headline numbers are quoted on (BASELINE.json configs[1] and configs[4]).
+
+  * cap = size = 1,000,000 (a non-power-of-two capacity: 21 tree levels, leaves on two depths), B = 256, PER + double +
+    dueling -- the workload of ``bench.py``'s ``value`` / ``e2e``; the replay is filled the way bench.py fills it.
+  * B = 65,536 on the same replay (duplicates among the sampled leaves are common): the exact fp32 step against the oracle,
+    and the tensor-core mode against the fp32 step at its benchmarked batch.
+
+Reference lines: dqn/utils/sum_tree.py:42-61 (descent), dqn/replay_memory.py:69-98 (stratified draw, IS weights, write-back),
+dqn/agent.py:245-272 (PerDoubleAgent.learn).  The oracle needs ~10 s for the 65,536-row step.
+"""
+import numpy as np
+import pytest
+import torch
+
+from tests import parity_utils as PU
+from tests import recipes as R
+from tests.test_gpu_learner import check_all_element_adam
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+CAP = 1_000_000
+
+
+def test_per256_on_full_1m_replay_matches_oracle():
+    pair = PU.make_pair_bulk("PerDuelingDoubleDQNAgent", 14, 256, CAP, seed=17)
+    orc, agent = pair
+    st = agent.replay_memory_buffer._ring.stats()
+    assert (st.size, st.data_pointer) == (CAP, 0)
+    assert st.total_priority == orc.replay.tree.total and st.max_priority == orc.replay.tree.max_leaf and st.min_priority == orc.replay.tree.min_leaf
+    res = PU.run_parity_case("PerDuelingDoubleDQNAgent", 14, 256, CAP, CAP, 3, seed=17, pair=pair)
+    print(res)
+    assert res["nodes_equal"], "sampled tree indices must be bit-exact (21-level descent, leaves on two depths)"
+    assert res["tree_equal"], "2M-node tree must be bit-exact after the write-back given equal float32 priorities"
+    assert res["max_pri_ulp"] <= 1.0 and res["max_rel_isw"] < 1e-6
+    assert res["max_rel_q"] < TOL and res["max_rel_loss"] < TOL and res["max_rel_grads"] < TOL, res["worst_grad"]
+    assert res["max_rel_weights"] < TOL and res["max_abs_weights_all"] <= 3e-4 and res["max_rel_target"] < 10 * TOL
+    check_all_element_adam(res)
+
+
+def test_device_sampler_on_full_1m_replay_stays_in_its_strata():
+    """The benchmark draws its uniforms on the device (Philox): every sampled leaf must be the leaf the oracle's descent
+    reaches for SOME value inside that sample's stratum -- checked through the prefix sums of the leaves."""
+    orc, agent = PU.make_pair_bulk("PerDuelingDoubleDQNAgent", 14, 256, CAP, seed=18)
+    agent.step = 5
+    agent.learn()
+    nodes = PU.gpu_out(agent, "nodes", torch.int64)
+    t = orc.replay.tree
+    # order of the leaves in a left-to-right walk of the heap: the deeper level first (indices >= 2^20 - 1), then the rest
+    first_leaf = CAP - 1
+    deep0 = (1 << 20) - 1
+    order = np.concatenate([np.arange(deep0, 2 * CAP - 1), np.arange(first_leaf, deep0)])
+    csum = np.cumsum(t.tree[order])
+    rank_of = np.empty(2 * CAP - 1, np.int64)
+    rank_of[order] = np.arange(order.size)
+    seg = t.total / 256
+    for i, n in enumerate(nodes):
+        k = rank_of[n]
+        lo_leaf, hi_leaf = (csum[k - 1] if k else 0.0), csum[k]
+        assert hi_leaf >= seg * i * (1 - 1e-12) and lo_leaf <= seg * (i + 1) * (1 + 1e-12), (i, n)
+
+
+def test_b65536_exact_step_matches_oracle():
+    pair = PU.make_pair_bulk("PerDuelingDoubleDQNAgent", 14, 65536, CAP, seed=19)
+    res = PU.run_parity_case("PerDuelingDoubleDQNAgent", 14, 65536, CAP, CAP, 1, seed=19, pair=pair)
+    print(res)
+    assert res["nodes_equal"] and res["tree_equal"], "65,536 stratified draws (with duplicate leaves) and their write-back must be bit-exact"
+    assert res["max_pri_ulp"] <= 1.0 and res["max_rel_isw"] < 1e-6
+    assert res["max_rel_q"] < TOL and res["max_rel_loss"] < TOL and res["max_rel_grads"] < TOL, res["worst_grad"]
+    assert res["max_rel_weights"] < TOL and res["max_rel_target"] < 10 * TOL
+    check_all_element_adam(res)
+
+
+def test_b65536_tensor_core_mode_within_stated_bound_of_fp32():
+    from tests.test_gpu_tc_train import GRAD_TOL, LOSS_TOL, Q_TOL, _grads_only
+    orc, agent = PU.make_pair_bulk("PerDuelingDoubleDQNAgent", 14, 65536, CAP, seed=20)
+    sizes = PU.tensor_sizes(orc.online)
+    agent.step = 4321
+    u = np.random.default_rng(6).random(65536)
+    ref = _grads_only(agent, u=u)
+    agent.learn_precision = "bf16"
+    agent._learn_calls -= 1
+    tc = _grads_only(agent, u=u)
+    agent.learn_precision = "fp32"
+    np.testing.assert_array_equal(ref["nodes"], tc["nodes"])
+    assert len(set(ref["nodes"].tolist())) < 65536, "this batch is expected to hold duplicate leaves"
+    assert R.max_rel(tc["q_sa"], ref["q_sa"]) < Q_TOL and R.max_rel(tc["y"], ref["y"]) < Q_TOL
+    assert abs(tc["loss"] - ref["loss"]) / abs(ref["loss"]) < LOSS_TOL
+    pt = PU.per_tensor_max_rel(tc["grads"], ref["grads"], sizes)
+    print({k: float("%.3g" % v) for k, v in pt.items()})
+    assert max(pt.values()) < GRAD_TOL, pt

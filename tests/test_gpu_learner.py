@@ -49,6 +49,20 @@ def test_learner_step_parity(algo, D, B, cap, fill, steps, soft, tf, act):
     assert res["max_rel_weights"] < TOL, res["worst_w"]
     assert res["max_abs_weights_all"] <= 1e-4 * steps, "ill-conditioned Adam elements move by at most lr per step"
     assert res["max_rel_target"] < 10 * TOL
+    check_all_element_adam(res)
+
+
+def check_all_element_adam(res):
+    """The checks that cover EVERY parameter element (the 1e-5 weight comparison above masks ill-conditioned ones)."""
+    print("well_conditioned_frac %.3f  zero_grad_frac %.3f  adam closure %.2f ulp  m %.2f ulp  v %.2f ulp  m/v vs oracle %.2e / %.2e"
+          % (res["well_conditioned_frac"], res["zero_grad_frac"], res["adam_closure_ulp"], res["adam_m_ulp"], res["adam_v_ulp"], res["max_rel_m"], res["max_rel_v"]))
+    # Adam / Polyak arithmetic on the device's own gradients: the bit-matched torch sequence, all elements
+    assert res["adam_closure_ulp"] <= 2.0 and res["adam_m_ulp"] <= 1.0 and res["adam_v_ulp"] <= 1.0
+    assert res["polyak_bitexact"], "target update must equal k*p + (1-k)*t (two products, one add) / the hard copy bit for bit"
+    # Adam moments are well conditioned everywhere: all elements against the oracle
+    assert res["max_rel_m"] < TOL and res["max_rel_v"] < TOL
+    # dead units: exact-zero gradients stay exact zeros and those weights equal the oracle's bit for bit
+    assert res["zero_grad_exact"] and res["zero_grad_weights_bitexact"]
 
 
 def test_adam_on_identical_inputs_is_ulp_exact():
@@ -85,17 +99,64 @@ def test_adam_on_identical_inputs_is_ulp_exact():
         assert R.max_rel(agent._lh.get_params(_lib.ADAM_V).cpu().numpy(), v_ref) < 1e-6
 
 
-def test_fused_target_update_equals_separate_call():
-    _, a1 = PU.make_pair("PerDuelingDoubleDQNAgent", 14, 64, 500, 500, seed=9)
-    _, a2 = PU.make_pair("PerDuelingDoubleDQNAgent", 14, 64, 500, 500, seed=9)
-    u = np.random.default_rng(1).random(64)
-    a1.step = a2.step = 5
-    a1.learn(u=u)
-    a1.update_target_network()
-    a2.learn(u=u, fuse_target_update=True)
-    a2.update_target_network()          # must be skipped (already done inside the launch)
-    np.testing.assert_array_equal(PU.flat_sd(a1.online_network), PU.flat_sd(a2.online_network))
-    np.testing.assert_array_equal(PU.flat_sd(a1.target_network), PU.flat_sd(a2.target_network))
+@pytest.mark.parametrize("soft", [True, False])
+def test_fused_target_update_equals_separate_call(soft):
+    """Three ways to run train.py:99-101 must give the same bits: (1) two launches -- the lazily recorded learn() is forced
+    out by reading the loss, then update_target_network() launches the target update alone; (2) the default: learn() records,
+    update_target_network() launches both as ONE kernel; (3) the explicit fuse_target_update=True kwarg."""
+    from multimodal_drl_rmc_b200 import _lib
+    agents = [PU.make_pair("PerDuelingDoubleDQNAgent", 14, 64, 500, 500, seed=9, soft=soft, target_freq=2)[1] for _ in range(3)]
+    rng = np.random.default_rng(1)
+    lib = _lib.lib()
+    for step in range(1, 5):
+        u = rng.random(64)
+        for a in agents:
+            a.step = step
+        a1, a2, a3 = agents
+        n0 = lib.rmc_launch_count()
+        a1.learn(u=u)
+        a1.last_loss()                      # observing the learner launches the recorded step (no target update inside)
+        a1.update_target_network()
+        n1 = lib.rmc_launch_count()
+        a2.learn(u=u)
+        assert lib.rmc_launch_count() == n1, "learn() alone must not launch (it is recorded)"
+        a2.update_target_network()
+        n2 = lib.rmc_launch_count()
+        a3.learn(u=u, fuse_target_update=True)
+        a3.update_target_network()          # must be skipped (already done inside the launch)
+        n3 = lib.rmc_launch_count()
+        assert n2 - n1 == 1 and n3 - n2 == 1, "learn() + update_target_network() is one launch"
+        assert n1 - n0 == (2 if (soft or step % 2 == 0) else 1)
+        for b in (a2, a3):
+            np.testing.assert_array_equal(PU.flat_sd(a1.online_network), PU.flat_sd(b.online_network))
+            np.testing.assert_array_equal(PU.flat_sd(a1.target_network), PU.flat_sd(b.target_network))
+            np.testing.assert_array_equal(a1.replay_memory_buffer.replay_buffer.tree, b.replay_memory_buffer.replay_buffer.tree)
+            assert a1.last_loss() == b.last_loss()
+
+
+def test_lazy_learn_is_not_observable():
+    """A recorded learn() is launched before anything that could see the difference: a store_transitions (the step must
+    sample the replay as it was), a second learn(), replay statistics, state_dict()."""
+    _, a = PU.make_pair("PerDuelingDoubleDQNAgent", 14, 32, 300, 300, seed=3)
+    _, b = PU.make_pair("PerDuelingDoubleDQNAgent", 14, 32, 300, 300, seed=3)
+    obs, act, rew, done, nxt = PU.synthetic_transitions(8, 14, 99)
+    rng = np.random.default_rng(2)
+    u1, u2 = rng.random(32), rng.random(32)
+    for ag, eager in ((a, False), (b, True)):
+        ag.step = 7
+        ag.learn(u=u1)
+        if eager:
+            ag.last_loss()
+        ag.store_transitions(obs[:3], act[:3].tolist(), rew[:3].tolist(), [False] * 3, nxt[:3], None)   # must not reach the step above
+        ag.learn(u=u2)
+        if eager:
+            ag.last_loss()
+        ag.update_target_network()
+    np.testing.assert_array_equal(PU.flat_sd(a.online_network), PU.flat_sd(b.online_network))
+    np.testing.assert_array_equal(PU.flat_sd(a.target_network), PU.flat_sd(b.target_network))
+    np.testing.assert_array_equal(a.replay_memory_buffer.replay_buffer.tree, b.replay_memory_buffer.replay_buffer.tree)
+    sa, sb = a.replay_memory_buffer._ring.stats(), b.replay_memory_buffer._ring.stats()
+    assert (sa.size, sa.data_pointer, sa.total_priority) == (sb.size, sb.data_pointer, sb.total_priority)
 
 
 def test_device_rng_sampling_is_valid_and_reproducible():

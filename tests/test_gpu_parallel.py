@@ -39,6 +39,62 @@ def test_ensemble_launch_equals_individual_steps(algo, B):
             assert (sa.max_priority, sa.min_priority, sa.total_priority) == (sb.max_priority, sb.min_priority, sb.total_priority)
 
 
+def test_ensemble_launch_matches_oracle_per_agent():
+    """The one-launch ensemble step against the ORACLE, member by member (not only against the single-agent CUDA path):
+    indices and trees bit-exact, Q / loss / gradients / weights at 1e-5 (dqn/agent.py:245-272 per agent)."""
+    from multimodal_drl_rmc_b200 import _lib
+    from multimodal_drl_rmc_b200.parallel import AgentEnsemble
+    n, B, cap = 3, 64, 1500
+    pairs = [PU.make_pair("PerDuelingDoubleDQNAgent", 14, B, cap, cap, seed=60 + k) for k in range(n)]
+    ens = AgentEnsemble([p[1] for p in pairs])
+    rng = np.random.default_rng(4)
+    for step in range(2):
+        u = rng.random((n, B))
+        traces = []
+        for k, (orc, ag) in enumerate(pairs):
+            orc.step = ag.step = 30 + step
+            tr = {}
+            orc.learn(u=u[k], trace=tr)
+            orc.sync_target()
+            traces.append(tr)
+        ens.learn(u=u)
+        for k, (orc, ag) in enumerate(pairs):
+            tr = traces[k]
+            np.testing.assert_array_equal(PU.gpu_out(ag, "nodes", torch.int64), tr["nodes"])
+            assert R.max_rel(PU.gpu_out(ag, "q_sa"), tr["q_sa"].reshape(-1)) < 1e-5
+            assert R.max_rel(PU.gpu_out(ag, "y"), tr["y"].reshape(-1)) < 1e-5
+            assert abs(ag.last_loss() - tr["loss"]) <= 1e-5 * abs(tr["loss"])
+            g_gpu = ag._lh.get_params(_lib.GRADS).cpu().numpy()
+            g_ref = np.concatenate([tr["grads"][kk].ravel() for kk, _ in orc.online.named_parameters()])
+            sizes = PU.tensor_sizes(orc.online)
+            pt = PU.per_tensor_max_rel(g_gpu, g_ref, sizes)
+            pt.pop("fc_val.bias", None)     # one-element cancelling sum: measured against sum |g_i| in run_parity_case
+            assert max(pt.values()) < 1e-5, pt
+            well = np.abs(g_ref) >= 1e-6
+            w_gpu, w_ref = PU.flat_sd(ag.online_network), PU.flat_sd(orc.online)
+            assert R.max_rel(np.where(well, w_gpu, w_ref), w_ref) < 1e-5 or step > 0
+            assert np.max(np.abs(w_gpu - w_ref)) <= 1e-4 * (step + 1)
+            assert R.max_rel(PU.flat_sd(ag.target_network), PU.flat_sd(orc.target)) < 1e-4
+            # trees: equal once the 1-ulp |td| -> p differences are removed (same procedure as run_parity_case)
+            p_ref = np.power(np.minimum(tr["abs_td"].reshape(-1) + np.float32(1e-4), np.float32(1.0)), np.float32(0.6)).astype(np.float32)
+            n_t, p_t = torch.as_tensor(tr["nodes"], device=ag.device), torch.as_tensor(p_ref, device=ag.device)
+            _lib.check(_lib.lib().rmc_per_update(ag.replay_memory_buffer._ring.handle, n_t.data_ptr(), p_t.data_ptr(), B, _lib.stream_ptr(ag.device.index)))
+            np.testing.assert_array_equal(ag.replay_memory_buffer.replay_buffer.tree, orc.replay.tree.tree)
+
+
+def test_ensemble_rejects_members_with_different_hyper_parameters():
+    from multimodal_drl_rmc_b200 import macro_config
+    from multimodal_drl_rmc_b200.parallel import AgentEnsemble
+    import tempfile
+    tmp = tempfile.mkdtemp()
+    a = PU.make_pair("DuelingDoubleDQNAgent", 14, 32, 200, 200, seed=1)[1]
+    b = macro_config.make_agent("DuelingDoubleDQNAgent", 14, 32, 200, save_dir=tmp + "/", log_dir=tmp + "/", lr=3e-4)
+    obs, act, rew, done, nxt = PU.synthetic_transitions(200, 14, 5)
+    b.store_transitions(obs, act.tolist(), rew.tolist(), done.astype(bool).tolist(), nxt, None)
+    with pytest.raises(ValueError):
+        AgentEnsemble([a, b])
+
+
 def test_sharded_step_emulated_on_one_gpu_equals_full_batch():
     """Two 'ranks' emulated one after the other on one GPU (replicas with identical state): the union of their
     shards is the full batch, the summed gradient blobs equal the full-batch gradients, and Adam from the summed
@@ -103,7 +159,7 @@ def test_peer_memory_exchange_two_ranks_on_one_gpu(B, precision, steps):
     from multimodal_drl_rmc_b200 import _lib
     from multimodal_drl_rmc_b200.parallel import ShardedLearner
     W, cap = 2, 20000
-    full = PU.make_pair("PerDuelingDoubleDQNAgent", 14, B, cap, cap, seed=41)[1]
+    orc, full = PU.make_pair("PerDuelingDoubleDQNAgent", 14, B, cap, cap, seed=41)
     reps = [PU.make_pair("PerDuelingDoubleDQNAgent", 14, B, cap, cap, seed=41)[1] for _ in range(W)]
     for ag in reps + [full]:
         ag.learn_precision = precision
@@ -137,6 +193,22 @@ def test_peer_memory_exchange_two_ranks_on_one_gpu(B, precision, steps):
         np.testing.assert_array_equal(t[0], t[1])
         if s == 0:
             assert abs(reps[0].last_loss() - full.last_loss()) / abs(full.last_loss()) < (1e-5 if precision == "fp32" else 1e-3)
+        if precision == "fp32" and s == 0 and B <= 1024:      # ... and against the ORACLE's full-batch step (dqn/agent.py:245-272)
+            tr = {}
+            orc.step = 50
+            orc.learn(u=u, trace=tr)
+            orc.sync_target()
+            np.testing.assert_array_equal(got, tr["nodes"])
+            assert abs(reps[0].last_loss() - tr["loss"]) <= 1e-5 * abs(tr["loss"])
+            g_ref = np.concatenate([tr["grads"][k].ravel() for k, _ in orc.online.named_parameters()])
+            g_rep = reps[0]._lh.get_params(_lib.GRADS).cpu().numpy()
+            pt = PU.per_tensor_max_rel(g_rep, g_ref, PU.tensor_sizes(orc.online))
+            pt.pop("fc_val.bias", None)
+            assert max(pt.values()) < 1e-5, pt
+            well_o = np.abs(g_ref) >= 1e-6
+            w_ref = PU.flat_sd(orc.online)
+            assert R.max_rel(np.where(well_o, w[0], w_ref), w_ref) < 1e-5
+            assert R.max_rel(PU.flat_sd(reps[0].target_network), PU.flat_sd(orc.target)) < 1e-4
         if precision == "fp32" and s == 0:
             w_full = PU.flat_sd(full.online_network)
             well = np.abs(g_full) >= 1e-6
@@ -144,3 +216,87 @@ def test_peer_memory_exchange_two_ranks_on_one_gpu(B, precision, steps):
             np.testing.assert_array_equal(t[0], full.replay_memory_buffer.replay_buffer.tree)
             sa, sb = reps[0].replay_memory_buffer._ring.stats(), full.replay_memory_buffer._ring.stats()
             assert (sa.max_priority, sa.min_priority, sa.total_priority) == (sb.max_priority, sb.min_priority, sb.total_priority)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Real CUDA-IPC exchange between two PROCESSES on two GPUs (skipped on a one-GPU box): ShardedLearner(exchange="peer")
+# maps the peers' exchange buffers through cudaIpcMemHandle_t all-gathered with torch.distributed (parallel.py
+# _connect_ipc); replicas must stay bit-identical and equal the NCCL form's result at 1e-5.
+_IPC_WORKER = r"""
+import os, sys, json
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["RMC_REPO"])
+from tests import parity_utils as PU
+from multimodal_drl_rmc_b200 import _lib
+from multimodal_drl_rmc_b200.parallel import ShardedLearner, sharded_act
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(rank)
+dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
+B, cap = 4096, 20000
+out = {}
+for precision in ("fp32", "bf16"):
+    res = {}
+    for exchange in ("peer", "nccl"):
+        ag = PU.make_pair("PerDuelingDoubleDQNAgent", 14, B, cap, cap, seed=41)[1]      # identical replicas on every rank
+        ag.learn_precision = precision
+        sl = ShardedLearner(ag, exchange=exchange)
+        rng = np.random.default_rng(3)
+        for s in range(3):
+            ag.step = 50 + s
+            sl.learn(u=rng.random(B))
+        torch.cuda.synchronize()
+        w = PU.flat_sd(ag.online_network)
+        t = ag.replay_memory_buffer.replay_buffer.tree
+        res[exchange] = (w, t, sl.exchange_status())
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (w.tobytes(), t.tobytes()))
+        res[exchange + "_identical"] = all(g == gathered[0] for g in gathered)
+        del sl, ag
+    out[precision] = dict(peer_identical=res["peer_identical"], nccl_identical=res["nccl_identical"], status=res["peer"][2],
+                          peer_vs_nccl=float(np.max(np.abs(res["peer"][0] - res["nccl"][0]))),
+                          trees_equal=bool(np.array_equal(res["peer"][1], res["nccl"][1])))
+# C3 row split: every rank evaluates its slice, actions all-gathered
+ag = PU.make_pair("DuelingDoubleDQNAgent", 14, 32, 200, 200, seed=2)[1]
+obs = np.random.default_rng(0).random((10001, 14), dtype=np.float32)
+split = sharded_act(ag.online_network, obs)
+out["act_split_equal"] = split == ag.online_network.actions(obs)
+if rank == 0:
+    print("IPC_RESULT " + json.dumps(out))
+dist.destroy_process_group()
+"""
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (real CUDA IPC mapping between two processes)")
+def test_peer_exchange_over_real_ipc_two_processes(tmp_path):
+    import json
+    import os
+    import subprocess
+    import sys
+    script = tmp_path / "ipc_worker.py"
+    script.write_text(_IPC_WORKER)
+    env = dict(os.environ, RMC_REPO=R.GOLDEN_DIR.rsplit("/tests/", 1)[0])
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port", "29631", str(script)]
+    res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    line = [l for l in res.stdout.splitlines() if l.startswith("IPC_RESULT ")][-1]
+    out = json.loads(line[len("IPC_RESULT "):])
+    print(out)
+    for precision in ("fp32", "bf16"):
+        o = out[precision]
+        assert o["status"] == 0 and o["peer_identical"] and o["nccl_identical"], o
+        assert o["trees_equal"] or precision == "bf16", o
+        assert o["peer_vs_nccl"] <= (3e-4 if precision == "fp32" else 1e-3), o      # at most ~lr per step on ill-conditioned Adam elements
+    assert out["act_split_equal"]
+
+
+def test_sharded_act_row_split_single_rank():
+    """BASELINE configs[2] across GPUs = rows split over the ranks; here the slicing logic with emulated
+    ranks on one GPU: the concatenated slices equal the unsplit call."""
+    from multimodal_drl_rmc_b200.parallel import sharded_act
+    ag = PU.make_pair("DuelingDoubleDQNAgent", 14, 32, 200, 200, seed=2)[1]
+    obs = np.random.default_rng(0).random((4099, 14), dtype=np.float32)
+    whole = ag.online_network.actions(obs)
+    for W in (1, 3, 8):
+        parts, ranges = zip(*[sharded_act(ag.online_network, obs, gather=False, rank=r, world=W) for r in range(W)])
+        assert [a for p in parts for a in p] == whole
+        assert ranges[0][0] == 0 and ranges[-1][1] == 4099 and all(ranges[i][1] == ranges[i + 1][0] for i in range(W - 1))
