@@ -286,8 +286,9 @@ int32_t rmc_learner_act_eps_host_sync(rmc_learner_t* l, const float* obs_host, i
                                       float epsilon, uint64_t seed, uint64_t counter, rmc_stream_t s);
 
 /* Diagnostics (not a reference interface): per-CTA phase timestamps (%globaltimer, ns) of the last
- * rmc_learner_step: out_host[cta*16 + k], k = 0 start, 1 sampled, 2 target weights landed,
- * 3 target pass done, 4 online weights landed, 5 row phase done, 6 past the barrier, 7 done. */
+ * rmc_learner_step: out_host[cta*32 + k], k = 0 start, 1 sampled, 2 target weights landed,
+ * 3 target pass done, 4 online weights landed, 5 row phase done, 6 past the barrier, 7 done, 8..19 finer stamps
+ * (profiles/tools/phase_timeline.py names them). */
 int32_t rmc_learner_debug_timing(rmc_learner_t* l, int32_t enable);
 /* [min CTA start, max CTA end] (%globaltimer ns) of the last 64 launches, slot = epoch % 64 (launch-gap diagnostic) */
 int32_t rmc_learner_debug_gaps_sync(rmc_learner_t* l, uint64_t* out128_host, rmc_stream_t s);

@@ -123,6 +123,7 @@ class Agent:
         self._lh = LearnerHandle(self.online_network._obs_dim, output_dim, self._DUELING, self._DOUBLE, self._PER,
                                  max(int(batch_size), 1), self.device.index, hyper,
                                  activation=self.online_network._activation, hybrid=self.online_network._hybrid)
+        self._pending_step = None        # a learn() that has been recorded but not launched yet (see learn())
         self.online_network._bind(self._lh, _lib.ONLINE)
         self.target_network._bind(self._lh, _lib.TARGET)
         self.update_target_network(force=True)

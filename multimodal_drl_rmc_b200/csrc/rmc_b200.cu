@@ -764,6 +764,15 @@ static int32_t learner_build_mlp(rmc_learner* l, const rmc_net_spec_t* spec, con
   if ((e = owned_alloc(l, &c.loss, 1))) return e;
   if ((e = owned_alloc(l, &c.barrier, 1))) return e;
   if ((e = owned_alloc(l, &c.qt_flag, kFlagWords))) return e;
+  {   // streamed phase B of the fused step: {epoch, value} word arrays (rmc_mlp.cuh, StreamPlan)
+    const size_t rows = std::min<size_t>(B, static_cast<size_t>(kStreamTilesMax) * kTM);
+    if ((e = owned_alloc(l, &c.x_words, 2 * rows * kMaxD))) return e;
+    if ((e = owned_alloc(l, &c.hp_words, 2 * rows * kH1))) return e;
+    if ((e = owned_alloc(l, &c.h2_words, 2 * rows * kH2))) return e;
+    if ((e = owned_alloc(l, &c.dh_words, 2 * rows * kQLD))) return e;
+    if ((e = owned_alloc(l, &c.zp_words, 2 * rows * kH2))) return e;
+    if ((e = owned_alloc(l, &c.z1_words, 2 * rows * kH1))) return e;
+  }
   {
     float* hp = nullptr;
     float* dp = nullptr;
@@ -777,7 +786,7 @@ static int32_t learner_build_mlp(rmc_learner* l, const rmc_net_spec_t* spec, con
       c.host_loss = nullptr;
     }
   }
-  if ((e = owned_alloc(l, &l->dbg_buf, 1024 * 16 + 128))) return e;
+  if ((e = owned_alloc(l, &l->dbg_buf, kDbgCtas * kDbgSlots + 128))) return e;
   RMC_CUDA(cudaDeviceSynchronize());
   return RMC_OK;
 }
@@ -1075,7 +1084,47 @@ static int32_t comm_side_writeback(rmc_learner* l, rmc_replay* r, cudaStream_t s
   return RMC_OK;
 }
 
+// RMC_TC_EVENTS=1 (diagnostic): CUDA events between the kernels of the tensor-core step on the main stream; the durations of
+// the PREVIOUS step are printed to stderr at the start of the next one (warm caches, real stream order -- unlike ncu's
+// serialised cold-cache replays).  Disables the step graph.
+struct TcEvents {
+  bool on = false, armed = false;
+  std::vector<cudaEvent_t> ev;
+  std::vector<const char*> names;
+  size_t n = 0;
+  void mark(const char* name, cudaStream_t st) {
+    if (!on) return;
+    if (n == ev.size()) { cudaEvent_t e; cudaEventCreate(&e); ev.push_back(e); names.push_back(name); }
+    names[n] = name;
+    cudaEventRecord(ev[n++], st);
+  }
+  void report() {
+    if (!on || !armed || n < 2) return;
+    cudaEventSynchronize(ev[n - 1]);
+    std::string line = "[rmc] tc step (us):";
+    for (size_t k = 1; k < n; ++k) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, ev[k - 1], ev[k]);
+      char buf[96];
+      std::snprintf(buf, sizeof buf, " %s %.1f", names[k], 1e3f * ms);
+      line += buf;
+    }
+    float tot = 0.f;
+    cudaEventElapsedTime(&tot, ev[0], ev[n - 1]);
+    std::fprintf(stderr, "%s | total %.1f\n", line.c_str(), 1e3f * tot);
+  }
+};
+static TcEvents g_tc_ev;
+static bool tc_events_on() {
+  static const bool on = [] { const char* e = std::getenv("RMC_TC_EVENTS"); return e && e[0] == '1'; }();
+  return on;
+}
+
 static int32_t step_tc(rmc_learner* l, rmc_replay* r, const rmc_step_args_t* a, StepScalars& S, cudaStream_t st) {
+  g_tc_ev.on = tc_events_on();
+  g_tc_ev.report();
+  g_tc_ev.n = 0; g_tc_ev.armed = true;
+  g_tc_ev.mark("start", st);
   if (l->L.D > kTcK1 - 1) return fail(RMC_ERR_UNSUPPORTED, "tensor-core learner mode: obs_dim must be <= 15 (column 15 of the X tile carries the bias-gradient ones)");
   if (l->L.act != 0) return fail(RMC_ERR_UNSUPPORTED, "tensor-core modes are built for ReLU bodies only");
   if ((a->phases & (RMC_PH_FORWARD | RMC_PH_BACKWARD)) != (RMC_PH_FORWARD | RMC_PH_BACKWARD))
@@ -1093,6 +1142,7 @@ static int32_t step_tc(rmc_learner* l, rmc_replay* r, const rmc_step_args_t* a, 
       RMC_KERNEL_OK();
     }
   }
+  g_tc_ev.mark("sample", st);
   // bf16 operand images of the online net (forward + backward forms) and of the target net
   if (l->tc_packed_version != l->online_version) {
     RMC_CUDA(launch_pdl(k_tc_pack, dim3(blocks_for(kH2 * kH1, 256)), dim3(256), 0, st, l->blobs[RMC_ONLINE], l->L, l->tc_packed));
@@ -1125,13 +1175,16 @@ static int32_t step_tc(rmc_learner* l, rmc_replay* r, const rmc_step_args_t* a, 
   J.j[0].cta_begin = 0;      J.j[0].cta_count = c0;
   J.j[1].cta_begin = c0;     J.j[1].cta_count = c0;
   J.j[2].cta_begin = 2 * c0; J.j[2].cta_count = c2;
+  g_tc_ev.mark("pack", st);
   RMC_CUDA(launch_pdl(k_tc_fwd3, dim3(2 * c0 + c2), dim3(kTcFwdThreads), kTcSmemBytes, st, J, l->L.D, l->L.A, l->L.NH, l->L.dueling, C.X, B));
   RMC_KERNEL_OK();
+  g_tc_ev.mark("fwd3", st);
   l->ctx.rp = r->dev;
   const unsigned td_blocks = blocks_for(B, kTdThreads);
   if (td_blocks > 1024) return fail(RMC_ERR_UNSUPPORTED, "tensor-core learner mode: batch above 131,072");
   RMC_CUDA(launch_pdl(k_tc_td, dim3(td_blocks), dim3(kTdThreads), 0, st, l->ctx, S, T));
   RMC_KERNEL_OK();
+  g_tc_ev.mark("td", st);
   // The priority write-back needs only |td| and the sampled leaves: it runs on a side stream beside the backward and
   // Adam kernels (latency-bound tree kernels next to tensor-core CTAs) and joins before the step returns.
   static const bool side_tree = [] { const char* e = std::getenv("RMC_TC_SIDE_TREE"); return !(e && e[0] == '0'); }();
@@ -1162,18 +1215,30 @@ static int32_t step_tc(rmc_learner* l, rmc_replay* r, const rmc_step_args_t* a, 
   }
   // backward: dgrad chain + weight gradients fused per 128-row tile
   T.n_part = static_cast<int>(grid);
+  g_tc_ev.mark("fork", st);
   RMC_CUDA(launch_pdl(k_tc_bwd_fused, dim3(grid), dim3(kThreads), kTcBwdFusedSmemBytes, st, l->ctx, reinterpret_cast<const unsigned char*>(l->tc_packed_bwd), B, T));
   RMC_KERNEL_OK();
+  g_tc_ev.mark("bwd", st);
   l->epoch = (l->epoch >= 0x7fffffffu) ? 1u : l->epoch + 1u;
   S.epoch = l->epoch;
   // the Adam kernel refreshes the bf16 operand images element by element: no pack kernels on the next step
   const TcPackOut P{l->tc_packed, l->tc_packed_bwd, l->tc_packed_target};
   RMC_CUDA(launch_pdl(k_tc_reduce_adam, dim3(blocks_for(l->L.total, 128)), dim3(256), 0, st, l->ctx, S, T, static_cast<int>(td_blocks), P));
   RMC_KERNEL_OK();
+  g_tc_ev.mark("reduce_adam", st);
+  if (g_tc_ev.on) {      // diagnostic: the same kernel again on warm inputs (how much of its time is the first touch of the partials?)
+    static const int rep = [] { const char* e = std::getenv("RMC_TC_REDUCE_REPEAT"); return e ? std::atoi(e) : 0; }();
+    for (int k = 0; k < rep; ++k) {
+      RMC_CUDA(launch_pdl(k_tc_reduce_adam, dim3(blocks_for(l->L.total, 128)), dim3(256), 0, st, l->ctx, S, T, static_cast<int>(td_blocks), P));
+      RMC_KERNEL_OK();
+    }
+    if (rep > 0) g_tc_ev.mark("reduce_adam_again_xN", st);
+  }
   l->loss_epoch = S.epoch;
   if (a->phases & RMC_PH_ADAM) l->tc_packed_version = l->tc_bwd_version = ++l->online_version;
   if (a->phases & (RMC_PH_POLYAK | RMC_PH_HARDSYNC)) l->tc_target_version = ++l->target_version;
   if (write_back && side_tree && !(g_trace != nullptr && g_trace->mode == 2)) RMC_CUDA(cudaStreamWaitEvent(st, l->tc_ev[1], 0));
+  g_tc_ev.mark("join_tree", st);
   return RMC_OK;
 }
 
@@ -1583,7 +1648,7 @@ extern "C" int32_t rmc_learner_step(rmc_learner_t* l, rmc_replay_t* r, const rmc
     const int full = RMC_PH_FORWARD | RMC_PH_BACKWARD | RMC_PH_ADAM;
     const bool images_current = l->tct_ready && l->tc_packed_version == l->online_version && l->tc_bwd_version == l->online_version &&
                                 l->tc_target_version == l->target_version;
-    if (l->early.c == nullptr && images_current && (a->phases & full) == full && a->grads_in_dev == nullptr)
+    if (l->early.c == nullptr && images_current && (a->phases & full) == full && a->grads_in_dev == nullptr && !tc_events_on())
       return run_step_graph(l, a->batch, 0x20000000 | a->phases, st, [&](cudaStream_t s_) { return step_tc(l, r, a, S, s_); });
     return step_tc(l, r, a, S, st);
   }
@@ -2143,14 +2208,14 @@ extern "C" int32_t rmc_learner_debug_timing(rmc_learner_t* l, int32_t enable) {
   if (enable) {   // [min start, max end] slots of the launch-gap diagnostic
     std::vector<unsigned long long> init(128);
     for (int k = 0; k < 64; ++k) { init[2 * k] = ~0ull; init[2 * k + 1] = 0ull; }
-    RMC_CUDA(cudaMemcpy(l->dbg_buf + 1024 * 16, init.data(), 128 * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+    RMC_CUDA(cudaMemcpy(l->dbg_buf + kDbgCtas * kDbgSlots, init.data(), 128 * sizeof(unsigned long long), cudaMemcpyHostToDevice));
   }
   return RMC_OK;
 }
 extern "C" int32_t rmc_learner_debug_gaps_sync(rmc_learner_t* l, uint64_t* out128_host, rmc_stream_t s) {
   if (!l || !out128_host) return fail(RMC_ERR_ARG, "rmc_learner_debug_gaps_sync: null");
   if (int32_t e = use_device(l->device)) return e;
-  RMC_CUDA(cudaMemcpyAsync(out128_host, l->dbg_buf + 1024 * 16, 128 * sizeof(uint64_t), cudaMemcpyDeviceToHost, as_stream(s)));
+  RMC_CUDA(cudaMemcpyAsync(out128_host, l->dbg_buf + kDbgCtas * kDbgSlots, 128 * sizeof(uint64_t), cudaMemcpyDeviceToHost, as_stream(s)));
   RMC_CUDA(cudaStreamSynchronize(as_stream(s)));
   return RMC_OK;
 }
@@ -2158,7 +2223,7 @@ extern "C" int32_t rmc_learner_debug_read_sync(rmc_learner_t* l, uint64_t* out_h
   if (!l || !out_host || !n_ctas) return fail(RMC_ERR_ARG, "rmc_learner_debug_read_sync: null");
   if (int32_t e = use_device(l->device)) return e;
   const int n = std::min(max_ctas, l->last_grid);
-  RMC_CUDA(cudaMemcpyAsync(out_host, l->dbg_buf, static_cast<size_t>(n) * 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost, as_stream(s)));
+  RMC_CUDA(cudaMemcpyAsync(out_host, l->dbg_buf, static_cast<size_t>(n) * kDbgSlots * sizeof(uint64_t), cudaMemcpyDeviceToHost, as_stream(s)));
   RMC_CUDA(cudaStreamSynchronize(as_stream(s)));
   *n_ctas = n;
   return RMC_OK;

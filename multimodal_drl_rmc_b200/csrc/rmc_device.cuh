@@ -131,10 +131,12 @@ __device__ __forceinline__ void pdl_enter() {
   asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
-#define RMC_STAMP(C, slot)                                                                 \
-  do {                                                                                     \
-    if ((C).dbg != nullptr && threadIdx.x == 0)                                            \
-      (C).dbg[(blockIdx.y * gridDim.x + blockIdx.x) * 16 + (slot)] = global_timer_ns();    \
+constexpr int kDbgSlots = 32;        // timestamps per CTA in AgentCtx::dbg
+constexpr int kDbgCtas = 1024;       // CTA records; the launch-gap slots follow them
+#define RMC_STAMP(C, slot)                                                                         \
+  do {                                                                                             \
+    if ((C).dbg != nullptr && threadIdx.x == 0)                                                    \
+      (C).dbg[(blockIdx.y * gridDim.x + blockIdx.x) * kDbgSlots + (slot)] = global_timer_ns();     \
   } while (0)
 
 // ----------------------------------------------------------------------------- Philox4x32-10
@@ -200,6 +202,7 @@ struct ReplayState {   // lives in HBM, updated by the kernels themselves
 
 constexpr int kFlagWords = 16384;   // u32 words of AgentCtx::qt_flag per agent (layout: rmc_mlp.cuh)
 constexpr int kTreeTeam = 8;     // CTAs that share the priority write-back of one learner step
+constexpr int kStreamTilesMax = 74;  // row tiles of a launch that runs the streamed phase B (one tile per row CTA, role split)
 struct TeamPart {                // one tree-team member's contribution to the extremes
   float bmax, bmin;              // extremes of the NEW values it applied
   int cnt_bmax, cnt_bmin;        // how many of its new values equal its own bmax / bmin
@@ -258,6 +261,14 @@ struct AgentCtx {
   unsigned* barrier;
   unsigned* qt_flag;    // [kFlagWords] {epoch, payload} hand-off words of the fused step: Q_target(s') per (tile, row, action),
                         // |td| per row and the loss partial per tile (layout: rmc_mlp.cuh)
+  // streamed phase B of the fused step (rmc_mlp.cuh): what the weight-gradient units need from the row CTAs, as
+  // {epoch, value} words that are polled -- no barrier and no fence between the row phase and the weight gradients
+  unsigned* x_words;    // [rows][kMaxD]  state columns of the s rows (zero past obs_dim)
+  unsigned* hp_words;   // [rows][kH1]    hidden-1 activations
+  unsigned* h2_words;   // [rows][kH2]    hidden-2 activations
+  unsigned* dh_words;   // [rows][kQLD]   head deltas
+  unsigned* zp_words;   // [rows][kH2]    layer-2 deltas dz2
+  unsigned* z1_words;   // [rows][kH1]    layer-1 deltas dz1
   volatile float* host_loss;      // mapped pinned host memory: [0] loss of the last step, [1] its epoch (as bits), [2] epoch of a launch whose in-kernel spin timed out (0 = healthy)
   unsigned long long* dbg;   // optional per-CTA phase timestamps [G][16] (nullptr = off)
 };

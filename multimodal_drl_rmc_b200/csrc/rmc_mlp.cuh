@@ -365,6 +365,7 @@ __device__ void wgrad_unit(const AgentCtx& C, const StepScalars& S, const GemmUn
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
+  RMC_STAMP(C, 16);
   issue(0, stage);
   int cur = 0;
   for (long long b0 = 0; b0 < S.B; b0 += kGChunk, cur ^= 1) {
@@ -374,6 +375,7 @@ __device__ void wgrad_unit(const AgentCtx& C, const StepScalars& S, const GemmUn
     if (more) asm volatile("cp.async.wait_group 1;" ::: "memory");
     else asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
+    if (b0 == 0) RMC_STAMP(C, 17);
     const float* As = stage + cur * kBuf;
     const float* Bs = As + kGChunk * TMO;
     // warp w takes rows w, w+8, ... (fixed order -> deterministic sums)
@@ -401,6 +403,7 @@ __device__ void wgrad_unit(const AgentCtx& C, const StepScalars& S, const GemmUn
     for (int j = 0; j < LN; ++j) Pb[warp * TNO + ng * LN + j] = bsum[j];
   }
   __syncthreads();
+  RMC_STAMP(C, 18);
   // gradients of this thread's outputs, then Adam / Polyak for all of them together (interleaved sqrt / division chains)
   float gq[NOUT];
   ParamVals po[NOUT];
@@ -426,6 +429,7 @@ __device__ void wgrad_unit(const AgentCtx& C, const StepScalars& S, const GemmUn
     C.grads[pb] = g;
     param_apply(C, S, pb, g, pvb);
   }
+  RMC_STAMP(C, 19);
   __syncthreads();
 }
 
@@ -468,6 +472,274 @@ __device__ void wgrad_run_unit(const AgentCtx& C, const StepScalars& S, int u, b
   }
 }
 
+// ------------------------------------------------------------------ streamed phase B units (see StreamPlan below)
+__device__ __forceinline__ uint4 ld_relaxed_quad(const unsigned* p) {
+  uint4 v;
+  asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_pair(unsigned* p, unsigned a, unsigned b);
+__device__ __forceinline__ uint2 ld_relaxed_pair(const unsigned* p);
+
+// One operand of a streamed unit: `cols` (16 or 32) columns starting at c0 of a [rows][ld_cols] array of {epoch, value}
+// words, staged as floats into dst[row][cols].
+struct WordTile { const unsigned* words; int ld_cols; int c0; };
+
+// Stage NQ x (kThreads / (COLS/2)) rows per pass.  A thread keeps one 16-byte slot (two words) of the staged row and walks
+// down the rows with all loads of the pass in flight (one L2 round trip); before asking for the pass it waits on ONE
+// probe word (the last row it stages) so that a CTA that is free early does not stream its whole operand through L2 on
+// every polling attempt; a pass that still holds a stale word is reloaded as a whole.
+template <int COLS>
+struct WordStager {
+  static constexpr int kSlots = COLS / 2, kRowsPerPass = kThreads / kSlots;
+  const unsigned* src; size_t ldw; float* dst; int row0;
+  __device__ __forceinline__ WordStager(const WordTile& t, float* dst_base) {
+    const int slot = threadIdx.x % kSlots;
+    row0 = threadIdx.x / kSlots;
+    src = t.words + 2 * (t.c0 + 2 * slot);
+    ldw = 2 * static_cast<size_t>(t.ld_cols);
+    dst = dst_base + 2 * slot;
+  }
+  template <int NQ>
+  __device__ __forceinline__ void issue(int base, int rows, uint4 (&w)[NQ]) const {
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      const int r = base + row0 + kRowsPerPass * q;
+      if (r < rows) w[q] = ld_relaxed_quad(src + static_cast<size_t>(r) * ldw);
+    }
+  }
+  template <int NQ>
+  __device__ __forceinline__ bool fresh(int base, int rows, const uint4 (&w)[NQ], unsigned epoch) const {
+    bool ok = true;
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      const int r = base + row0 + kRowsPerPass * q;
+      if (r < rows) ok = ok && (w[q].x == epoch) && (w[q].z == epoch);
+    }
+    return ok;
+  }
+  template <int NQ>
+  __device__ __forceinline__ void store(int base, int rows, const uint4 (&w)[NQ]) const {
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      const int r = base + row0 + kRowsPerPass * q;
+      if (r < rows) *reinterpret_cast<float2*>(dst + r * COLS) = make_float2(__uint_as_float(w[q].y), __uint_as_float(w[q].w));
+    }
+  }
+  // the last row of the pass starting at `base` that this thread stages (rows > base + row0 required)
+  template <int NQ>
+  __device__ __forceinline__ const unsigned* probe(int base, int rows) const {
+    int last = base + row0 + kRowsPerPass * (NQ - 1);
+    if (last >= rows) last = base + row0 + ((rows - 1 - base - row0) / kRowsPerPass) * kRowsPerPass;
+    return src + static_cast<size_t>(last) * ldw;
+  }
+};
+__device__ __forceinline__ void wait_word(const unsigned* p, unsigned epoch, SpinGuard& guard, volatile float* err) {
+  while (ld_relaxed_pair(p).x != epoch) {
+    __nanosleep(200);
+    if (guard.expired()) { spin_report_timeout(err, epoch); break; }
+  }
+}
+
+// A streamed gradient unit: out[m][n] = sum_b A[b][a0 + m] * Bm[b][b0 + n] over the batch rows (TMO x TNO outputs, one or
+// two per thread), the bias gradient as the column sums of Bm, fused Adam (+ Polyak) on the owning thread -- the same
+// arithmetic and summation order as wgrad_unit (warp w takes rows w, w+8, ...; warps combined in order), only the operands
+// arrive as polled words instead of cp.async copies behind a barrier.
+struct StreamUnit {
+  WordTile A, Bm;
+  int m_valid, n_valid;
+  int out_base, out_sm, out_sn;    // param index = out_base + m*out_sm + n*out_sn
+  int bias_base;                   // param index of bias[n] or -1
+};
+template <int TMO, int TNO>
+__device__ void stream_unit(const AgentCtx& C, const StepScalars& S, const StreamUnit& U, float* smem) {
+  constexpr int kRowsMax = kStreamTilesMax * kTM;      // <= 296 rows
+  constexpr int LM = TMO / 8, LN = TNO / 4, NOUT = TMO * TNO / kThreads;
+  float* As = smem;                                 // [rows][TMO]
+  float* Bs = smem + kRowsMax * TMO;                // [rows][TNO]
+  float* Ps = Bs + kRowsMax * TNO;                  // [kWarps][TMO*TNO]
+  float* Pb = Ps + kWarps * TMO * TNO;              // [kWarps][TNO]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int rows = static_cast<int>(S.B);
+  int pi[NOUT], ps_off[NOUT];
+  ParamVals pv[NOUT] = {};
+#pragma unroll
+  for (int q = 0; q < NOUT; ++q) {
+    const int o = tid + q * kThreads, om = o / TNO, on = o % TNO;
+    pi[q] = (om < U.m_valid && on < U.n_valid) ? U.out_base + om * U.out_sm + on * U.out_sn : -1;
+    ps_off[q] = om * TNO + ((on + om / LM) & (TNO - 1));
+    if (pi[q] >= 0) pv[q] = param_load(C, S, pi[q]);
+  }
+  const int bt = tid - (kThreads - 32);
+  const int pbi = (U.bias_base >= 0 && bt >= 0 && bt < U.n_valid && bt < TNO) ? U.bias_base + bt : -1;
+  ParamVals pvb{};
+  if (pbi >= 0) pvb = param_load(C, S, pbi);
+  __syncthreads();                                  // the staging area may still be in use by the CTA's previous phase
+  RMC_STAMP(C, 16);
+  {
+    const WordStager<TMO> sa(U.A, As);
+    const WordStager<TNO> sb(U.Bm, Bs);
+    constexpr int NQA = 256 / WordStager<TMO>::kRowsPerPass, NQB = 256 / WordStager<TNO>::kRowsPerPass;   // 256 rows per pass
+    SpinGuard guard;
+    for (int base = 0; base < rows; base += 256) {
+      const bool has_a = base + sa.row0 < rows, has_b = base + sb.row0 < rows;
+      if (has_b) wait_word(sb.template probe<NQB>(base, rows), S.epoch, guard, C.host_loss);     // B is the operand produced last
+      uint4 wa[NQA], wb[NQB];
+      bool ok;
+      do {
+        if (has_a) sa.template issue<NQA>(base, rows, wa);
+        if (has_b) sb.template issue<NQB>(base, rows, wb);
+        ok = (!has_a || sa.template fresh<NQA>(base, rows, wa, S.epoch)) && (!has_b || sb.template fresh<NQB>(base, rows, wb, S.epoch));
+        if (!ok) {
+          __nanosleep(100);
+          if (guard.expired()) { spin_report_timeout(C.host_loss, S.epoch); break; }
+        }
+      } while (!ok);
+      if (has_a) sa.template store<NQA>(base, rows, wa);
+      if (has_b) sb.template store<NQB>(base, rows, wb);
+    }
+  }
+  __syncthreads();
+  RMC_STAMP(C, 17);
+  const int mg = lane >> 2, ng = lane & 3;
+  float acc[LM][LN];
+  float bsum[LN];
+#pragma unroll
+  for (int i = 0; i < LM; ++i)
+#pragma unroll
+    for (int j = 0; j < LN; ++j) acc[i][j] = 0.f;
+#pragma unroll
+  for (int j = 0; j < LN; ++j) bsum[j] = 0.f;
+#pragma unroll 4
+  for (int r = warp; r < rows; r += kWarps) {       // warp w takes rows w, w+8, ... (fixed order -> deterministic sums)
+    float a[LM], b[LN];
+    lds_vec<LM>(a, As + r * TMO + mg * LM);
+    lds_vec<LN>(b, Bs + r * TNO + ng * LN);
+#pragma unroll
+    for (int i = 0; i < LM; ++i)
+#pragma unroll
+      for (int j = 0; j < LN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+#pragma unroll
+    for (int j = 0; j < LN; ++j) bsum[j] += b[j];
+  }
+#pragma unroll
+  for (int i = 0; i < LM; ++i)
+#pragma unroll
+    for (int j = 0; j < LN; ++j) Ps[warp * (TMO * TNO) + (mg * LM + i) * TNO + ((ng * LN + j + mg) & (TNO - 1))] = acc[i][j];
+  if (mg == 0) {
+#pragma unroll
+    for (int j = 0; j < LN; ++j) Pb[warp * TNO + ng * LN + j] = bsum[j];
+  }
+  __syncthreads();
+  RMC_STAMP(C, 18);
+  float gq[NOUT];
+  ParamVals po[NOUT];
+#pragma unroll
+  for (int q = 0; q < NOUT; ++q) {
+    float g = 0.f;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) g += Ps[w * (TMO * TNO) + ps_off[q]];
+    gq[q] = g;
+  }
+  param_math_n<NOUT>(S, gq, pv, po);
+#pragma unroll
+  for (int q = 0; q < NOUT; ++q) {
+    if (pi[q] >= 0) {
+      C.grads[pi[q]] = gq[q];
+      param_store(C, S, pi[q], po[q]);
+    }
+  }
+  if (pbi >= 0) {
+    float g = 0.f;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) g += Pb[w * TNO + bt];
+    C.grads[pbi] = g;
+    param_apply(C, S, pbi, g, pvb);
+  }
+  RMC_STAMP(C, 19);
+  __syncthreads();
+}
+
+// unit tables of the streamed phase B
+__device__ __forceinline__ void stream_run_w2(const AgentCtx& C, const StepScalars& S, int u, float* smem) {      // 16 x 16, u in [0, 128)
+  const NetLayout& L = C.L;
+  const int kt = u / (kH2 / 16), jt = u % (kH2 / 16);
+  StreamUnit U;
+  U.A = WordTile{C.hp_words, kH1, kt * 16};
+  U.Bm = WordTile{C.zp_words, kH2, jt * 16};
+  U.m_valid = 16; U.n_valid = 16;
+  U.out_base = L.off_w2t + kt * 16 * kW2LD + jt * 16; U.out_sm = kW2LD; U.out_sn = 1;
+  U.bias_base = (kt == 0) ? L.off_b2 + jt * 16 : -1;
+  stream_unit<16, 16>(C, S, U, smem);
+}
+__device__ __forceinline__ int stream_w0_count(const NetLayout& L) { return ((L.D + 15) / 16) * (kH1 / 16); }
+__device__ __forceinline__ void stream_run_w0(const AgentCtx& C, const StepScalars& S, int u, float* smem) {      // 16 (d) x 16 (k)
+  const NetLayout& L = C.L;
+  const int mt = u / (kH1 / 16), nt = u % (kH1 / 16);
+  StreamUnit U;
+  U.A = WordTile{C.x_words, kMaxD, mt * 16};
+  U.Bm = WordTile{C.z1_words, kH1, nt * 16};
+  U.m_valid = min(16, L.D - mt * 16); U.n_valid = 16;
+  U.out_base = L.off_w0t + mt * 16 * kH1 + nt * 16; U.out_sm = kH1; U.out_sn = 1;
+  U.bias_base = (mt == 0) ? L.off_b0 + nt * 16 : -1;
+  stream_unit<16, 16>(C, S, U, smem);
+}
+// One schedule for all three kinds of unit.  Units in the order their operands come into existence -- heads (after the TD
+// block), W2 (after dz2), W0 (after dz1) -- are dealt to the CTAs in the order those become free -- idle in phase A, target,
+// row: CTA k (in that order) takes unit extra + k, and when there are more units than CTAs the first `extra` CTAs (the
+// earliest free) take unit k before it.  At B = 256: 8 head + 128 W2 + 16 W0 units on 140 CTAs -> the 12 idle CTAs run a
+// head or W2 unit and then a W2 unit, and the W0 units land on the last 16 row CTAs.
+__device__ __forceinline__ void stream_run_any(const AgentCtx& C, const StepScalars& S, int id, float* smem);
+__device__ __forceinline__ void stream_run_heads(const AgentCtx& C, const StepScalars& S, int u, float* smem) {   // 16 (j) x 16 (a), u in [0, 8)
+  const NetLayout& L = C.L;
+  StreamUnit U;
+  U.A = WordTile{C.h2_words, kH2, u * 16};
+  U.Bm = WordTile{C.dh_words, kQLD, 0};
+  U.m_valid = 16; U.n_valid = L.NH;
+  U.out_base = L.off_wh + u * 16; U.out_sm = 1; U.out_sn = kH2;
+  U.bias_base = (u == 0) ? L.off_bh : -1;
+  stream_unit<16, 16>(C, S, U, smem);
+}
+
+__device__ __forceinline__ void stream_run_any(const AgentCtx& C, const StepScalars& S, int id, float* smem) {
+  constexpr int nH = kH2 / 16, nW2 = (kH1 / 16) * (kH2 / 16);
+  if (id < nH) stream_run_heads(C, S, id, smem);
+  else if (id < nH + nW2) stream_run_w2(C, S, id - nH, smem);
+  else stream_run_w0(C, S, id - nH - nW2, smem);
+}
+
+// loss of a streamed launch without a priority write-back team: the tiles' {epoch, loss partial} words, summed in tile order
+__device__ void stream_publish_loss(const AgentCtx& C, const StepScalars& S, int n_tiles, float* smem) {
+  float* s_lp = smem;
+  const int tid = threadIdx.x;
+  __syncthreads();
+  float lp = 0.f;
+  if (tid < n_tiles) {
+    SpinGuard guard;
+    uint2 w = ld_relaxed_pair(C.qt_flag + 512 + 2 * tid);      // kLossWordBase
+    while (w.x != S.epoch) {
+      __nanosleep(100);
+      w = ld_relaxed_pair(C.qt_flag + 512 + 2 * tid);
+      if (guard.expired()) { spin_report_timeout(C.host_loss, S.epoch); break; }
+    }
+    lp = __uint_as_float(w.y);
+  }
+  s_lp[tid] = lp;
+  __syncthreads();
+  if (tid == 0) {
+    float s = 0.f;
+    for (int c = 0; c < n_tiles; ++c) s += s_lp[c];
+    const float loss = s / static_cast<float>(S.Bglobal);
+    C.loss[0] = loss;
+    if (C.host_loss != nullptr) {
+      C.host_loss[0] = loss;
+      __threadfence_system();
+      C.host_loss[1] = __uint_as_float(S.epoch);
+    }
+  }
+  __syncthreads();
+}
+
 // ------------------------------------------------------------------ the fused learner step
 // Layout of AgentCtx::qt_flag (kFlagWords u32 per agent):
 //   [0, 512)      (unused)
@@ -503,10 +775,40 @@ __device__ __forceinline__ PhaseBPlan phase_b_plan(const AgentCtx& C, const Step
   return p;
 }
 
+// Streamed phase B (one tile per row CTA + role split + FORWARD and BACKWARD in one launch + at least kStreamIdleMin CTAs that
+// own neither a row tile nor a target tile nor tree work):
+//   * the row CTAs publish what the weight gradients need as {epoch, value} words the moment it exists -- x with the
+//     sampled rows, H1 / H2 right after the forward pass, the head deltas after the TD block, dz2 and dz1 as they are formed;
+//   * every gradient unit polls its operand words and starts as soon as its CTA is free: W2 units (16 x 16 outputs, the
+//     bulk of the parameters, one per row / target CTA) on target CTAs right after their Q values left -- they used to idle
+//     until the agent barrier -- and on row CTAs right after dz1; the head units and the W0 units on the CTAs that are idle
+//     in phase A (heads first: their operands exist 3 us before dz1);
+//   * nobody waits at a barrier and nobody executes a fence between the two phases.
+// Same arithmetic and summation order as the barrier path (wgrad_unit).  The agent barrier is only arrived at (the host
+// counts on G arrivals per launch).
+constexpr int kStreamIdleMin = 8;
+struct StreamPlan { bool on; int idle0, n_idle; };
+__device__ __forceinline__ StreamPlan stream_plan(const AgentCtx& C, const StepScalars& S, const PhaseBPlan& pb, int G, long long n_tiles, bool one_tile,
+                                                  bool split) {
+  StreamPlan sp;
+  sp.idle0 = 2 * static_cast<int>(n_tiles);
+  sp.n_idle = pb.n_workers - sp.idle0;
+  sp.on = one_tile && split && !pb.coarse && (S.phases & 8) && sp.n_idle >= kStreamIdleMin && n_tiles <= kStreamTilesMax && C.x_words != nullptr &&
+          (!pb.tree_here || pb.early) &&
+          (kH2 / 16 + (kH1 / 16) * (kH2 / 16) + ((C.L.D + 15) / 16) * (kH1 / 16)) - (sp.n_idle + 2 * static_cast<int>(n_tiles)) <= sp.n_idle;
+  return sp;
+}
+
 // loss = (1/B) sum of the per-tile partials in tile order; also into mapped host memory (value, system fence, epoch)
 __device__ __forceinline__ void publish_loss(const AgentCtx& C, const StepScalars& S, const float* parts, int np) {
   float s = 0.f;
-  for (int c = 0; c < np; ++c) s += parts[c];
+  for (int c0 = 0; c0 < np; c0 += 16) {      // 16 loads in flight, then the adds in tile order (a plain loop is one L2 round trip per partial)
+    float v[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) v[q] = (c0 + q < np) ? parts[c0 + q] : 0.f;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) s += (c0 + q < np) ? v[q] : 0.f;
+  }
   const float loss = s / static_cast<float>(S.Bglobal);
   C.loss[0] = loss;
   if (C.host_loss != nullptr) {
@@ -559,8 +861,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, c
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
   RMC_STAMP(C, 0);
-  // launch-gap diagnostic: per-launch [min start, max end] in dbg[1024*16 + 2*(epoch % 64) ..] (enabled with the stamps)
-  unsigned long long* gap = (C.dbg != nullptr) ? C.dbg + 1024 * 16 + 2 * (S.epoch & 63u) : nullptr;
+  // launch-gap diagnostic: per-launch [min start, max end] in dbg[kDbgCtas*kDbgSlots + 2*(epoch % 64) ..] (enabled with the stamps)
+  unsigned long long* gap = (C.dbg != nullptr) ? C.dbg + kDbgCtas * kDbgSlots + 2 * (S.epoch & 63u) : nullptr;
   if (gap != nullptr && threadIdx.x == 0) atomicMin(gap, global_timer_ns());
 
   // Role split: when every row CTA owns one tile and enough CTAs are idle in phase A, CTA n_tiles+t computes
@@ -578,6 +880,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, c
   // step (row CTAs and, through the Q_target hand-off, their target partners) has finished its descent.
   const PhaseBPlan pb = phase_b_plan(C, S, G, per);
   const bool early_td = one_tile && pb.early;
+  const StreamPlan sp = stream_plan(C, S, pb, G, n_tiles, one_tile, split);
+  const bool stream_b = kOneTile && sp.on;
   if (is_row || is_tgt) {
     const long long n_nodes = 2 * C.rp.cap - 1;
     const int n_top = static_cast<int>(min(static_cast<long long>(kTopNodes), n_nodes));
@@ -586,8 +890,27 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, c
     const long long size = __ldcg(&C.rp.st->size), dp = __ldcg(&C.rp.st->dp);
     const double total = per ? __ldcg(C.rp.tree) : 0.0;
     const float min_p_f = per ? __ldcg(&C.rp.st->min_p) : 0.f;
-    if ((S.phases & 1) && C.rp.prioritized)        // top levels of the tree: one coalesced read, then smem descents
-      for (int t = tid; t < n_top; t += kThreads) sTop[t] = __ldcg(C.rp.tree + t);
+    // top levels of the tree: one coalesced read, then smem descents.  The loads are issued first and the sample's uniform
+    // (Philox, independent of memory) is drawn while they are in flight.
+    double pre_u = 0.0;
+    {
+      double topv[(kTopNodes + kThreads - 1) / kThreads];
+      const bool want_top = (S.phases & 1) && C.rp.prioritized;
+#pragma unroll
+      for (int q = 0; q < (kTopNodes + kThreads - 1) / kThreads; ++q) {
+        const int t = tid + q * kThreads;
+        topv[q] = (want_top && t < n_top) ? __ldcg(C.rp.tree + t) : 0.0;
+      }
+      if (kOneTile && want_top && warp < kTM) {
+        const long long i = static_cast<long long>(tile0) * kTM + warp;
+        if (i < B) pre_u = (S.u != nullptr) ? S.u[agent * B + i] : philox_uniform(S.seed, S.counter, agent, static_cast<uint32_t>(S.shard_off + i));
+      }
+#pragma unroll
+      for (int q = 0; q < (kTopNodes + kThreads - 1) / kThreads; ++q) {
+        const int t = tid + q * kThreads;
+        if (want_top && t < n_top) sTop[t] = topv[q];
+      }
+    }
     __syncthreads();
     RMC_STAMP(C, 8);
     const bool do_fwd = (S.phases & 2) != 0;
@@ -597,6 +920,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, c
     // warps 0..kTM-1: one sample each; warp kTM meanwhile computes the max IS weight (replay_memory.py:76-77),
     // which the samplers pick up at a 5-warp named barrier after their own descent.
     const bool tree_sampling = C.rp.prioritized != 0;
+    // Importance weights (float64 pow, ~0.6 us): with the role split the TARGET partner evaluates them -- it has about a
+    // microsecond of slack before its Q values are needed -- and ships them in the spare 16th word of each Q_target row;
+    // the row CTA goes from the descent straight to the forward pass.
+    const bool isw_by_partner = split && (S.phases & 1) && tree_sampling;
+    const bool does_isw = isw_by_partner ? is_tgt : !is_tgt;
     if ((S.phases & 1) && !one_tile) {
       // several tiles per CTA (ensembles, large batches without the grid-wide sampler): all 8 warps draw this CTA's
       // samples, 8 descents in flight instead of 4; rows go straight to the L2-resident scratch
@@ -644,7 +972,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, c
           if (ok) {
             if (tree_sampling) {
               const long long gi = S.shard_off + i;
-              const double ui = (S.u != nullptr) ? S.u[agent * B + i] : philox_uniform(S.seed, S.counter, agent, static_cast<uint32_t>(gi));
+              const double ui = kOneTile ? pre_u
+                                         : ((S.u != nullptr) ? S.u[agent * B + i] : philox_uniform(S.seed, S.counter, agent, static_cast<uint32_t>(gi)));
               const double v = stratum_value(total, S.Bglobal, gi, ui);
               RMC_STAMP(C, 9);
               node = per_descend_cached(sTop, n_top, C.rp.tree, n_nodes, v, &p);
@@ -657,21 +986,22 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, c
               node = slot;
             }
             rr = gather_row_load(C.rp, slot);                      // row loads in flight during the pow
-            if (tree_sampling && !is_tgt) numer = pow(static_cast<double>(size) * (p / total), -S.beta);
+            if (tree_sampling && does_isw) numer = pow(static_cast<double>(size) * (p / total), -S.beta);
             RMC_STAMP(C, 11);
           }
-          if (tree_sampling && !is_tgt) asm volatile("bar.sync 1, %0;" ::"n"((kTM + 1) * 32) : "memory");
+          if (tree_sampling && does_isw) asm volatile("bar.sync 1, %0;" ::"n"((kTM + 1) * 32) : "memory");
           if (ok) {
+            const float w = (tree_sampling && does_isw) ? static_cast<float>(numer / sTop[kTopNodes]) : 1.f;
             if (is_tgt) {                                          // target role: rows stay in shared memory only
               gather_row_store_smem(C.rp, rr, sRows + warp * kMaxRowFloats);
+              if (lane == 0) sIsw[warp] = w;
             } else {
-              const float w = tree_sampling ? static_cast<float>(numer / sTop[kTopNodes]) : 1.f;
               gather_row_store(C.rp, rr, C.X + i * rf, sRows + warp * kMaxRowFloats);
-              if (lane == 0) { C.nodes[i] = node; C.is_w[i] = w; sIsw[warp] = w; C.leaf_p[i] = p; }
+              if (lane == 0) { C.nodes[i] = node; sIsw[warp] = w; C.leaf_p[i] = p; if (does_isw) C.is_w[i] = w; }
             }
             RMC_STAMP(C, 12);
           }
-        } else if (warp == kTM && tree_sampling && !is_tgt) {
+        } else if (warp == kTM && tree_sampling && does_isw) {
           if (first_iter && lane == 0)
             sTop[kTopNodes] = is_weight_max(static_cast<double>(size), total, static_cast<double>(min_p_f), S.beta);
           __syncwarp();
@@ -725,7 +1055,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, c
       }
       // publish Q_target(s') of the tile as {epoch, value} words (payload rides with the flag: no fence, one round trip
       // on the consumer's side) -- then on to phase B
-      if (is_tgt && tid < kTM * kQLD) st_relaxed_pair(C.qt_flag + kQtWordBase + 2 * (tile0 * kTM * kQLD + tid), S.epoch, __float_as_uint(sQT[tid]));
+      if (is_tgt && tid < kTM * kQLD) {
+        const float payload = (isw_by_partner && (tid % kQLD) == kQLD - 1) ? sIsw[tid / kQLD] : sQT[tid];      // A <= 15: column 15 is spare
+        st_relaxed_pair(C.qt_flag + kQtWordBase + 2 * (tile0 * kTM * kQLD + tid), S.epoch, __float_as_uint(payload));
+      }
       // -------- pass 2: online weights; [s'; s] rows
       RMC_STAMP(C, 3);
       if (!split) {
@@ -754,6 +1087,29 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, c
         __syncthreads();
         mlp_forward<kR>(sW, L, sXT, sH1T, sH2, sPart, sQ, nullptr);
         RMC_STAMP(C, 13);
+        if (stream_b) {  // x, H1 and H2 of the s rows leave now, long before the gradient units ask for them
+          const float4 hv = *reinterpret_cast<const float4*>(sH1T + tid * kR + kTM);
+          const float h[kTM] = {hv.x, hv.y, hv.z, hv.w};
+#pragma unroll
+          for (int r = 0; r < kTM; ++r) {
+            const long long i = tile * kTM + r;
+            if (i < B) st_relaxed_pair(C.hp_words + 2 * (i * kH1 + tid), S.epoch, __float_as_uint(h[r]));
+          }
+          {
+            const int j = tid & (kH2 - 1), r0 = tid >> 7;
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+              const int r = r0 + 2 * rr;
+              const long long i = tile * kTM + r;
+              if (i < B) st_relaxed_pair(C.h2_words + 2 * (i * kH2 + j), S.epoch, __float_as_uint(sH2[(kTM + r) * kH2 + j]));
+            }
+          }
+          if (tid < kTM * kMaxD) {
+            const int r = tid / kMaxD, d = tid % kMaxD;
+            const long long i = tile * kTM + r;
+            if (i < B) st_relaxed_pair(C.x_words + 2 * (i * kMaxD + d), S.epoch, __float_as_uint(d < D ? sXT[d * kR + kTM + r] : 0.f));
+          }
+        }
         if (split) {     // Q_target(s') of this tile comes from its partner CTA
           if (tid < kTM * kQLD) {
             const unsigned* wp = C.qt_flag + kQtWordBase + 2 * (tile * kTM * kQLD + tid);
@@ -765,6 +1121,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, c
               if (guard.expired()) { spin_report_timeout(C.host_loss, S.epoch); break; }
             }
             sQT[tid] = __uint_as_float(w.y);
+            if (isw_by_partner && (tid % kQLD) == kQLD - 1) {      // the partner's importance weight of row tid / kQLD
+              const int r = tid / kQLD;
+              const long long i = tile * kTM + r;
+              sMeta[r * 4 + 3] = (i < B) ? __uint_as_float(w.y) : 0.f;
+              if (i < B) C.is_w[i] = __uint_as_float(w.y);
+            }
           }
           __syncthreads();
         }
@@ -827,10 +1189,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, c
           if (i < B) ((r < kTM) ? C.QN : C.Q)[i * kQLD + (tid % kQLD)] = sQ[tid];
         }
         __syncthreads();
+        RMC_STAMP(C, 14);
         if (tid == 0) {
           for (int r = 0; r < kTM; ++r) loss_local += sRed[r];
         }
-        if (early_td && warp == 1 && lane <= kTM) {     // release the write-back team: {epoch, |td|} per row, {epoch, loss partial}
+        if ((early_td || stream_b) && warp == 1 && lane <= kTM) {     // release the write-back team: {epoch, |td|} per row, {epoch, loss partial}
           if (lane < kTM) {
             const long long i = tile * kTM + lane;
             if (i < B) st_relaxed_pair(C.qt_flag + kTdWordBase + 2 * i, S.epoch, __float_as_uint(sRed[kTM + lane]));
@@ -853,14 +1216,22 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, c
             const float dz = act_bwd(s, h2v, L.act);
             sDZ2[r * kH2 + j] = dz;
             const long long i = tile * kTM + r;
-            if (i < B) { C.DZ2[i * kH2 + j] = dz; C.H2[i * kH2 + j] = h2v; }
+            if (stream_b) {
+              if (i < B) st_relaxed_pair(C.zp_words + 2 * (i * kH2 + j), S.epoch, __float_as_uint(dz));
+            } else if (i < B) { C.DZ2[i * kH2 + j] = dz; C.H2[i * kH2 + j] = h2v; }
           }
-          if (tid < kTM * kQLD) {
+          if (stream_b) {
+            if (tid < kTM * kQLD) {
+              const long long i = tile * kTM + tid / kQLD;
+              if (i < B) st_relaxed_pair(C.dh_words + 2 * (i * kQLD + (tid % kQLD)), S.epoch, __float_as_uint(sDH[tid]));
+            }
+          } else if (tid < kTM * kQLD) {
             const long long i = tile * kTM + tid / kQLD;
             if (i < B) C.DH[i * kQLD + (tid % kQLD)] = sDH[tid];
           }
         }
         __syncthreads();
+        RMC_STAMP(C, 15);
         // ---- dz1[r][k] = (sum_j dz2[r][j] W2^T[k][j]) * [h1 > 0]   (thread k)
         {
           float acc[kTM] = {0.f, 0.f, 0.f, 0.f};
@@ -877,6 +1248,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, c
               acc[r] = fmaf(dz.w, w.w, acc[r]);
             }
           }
+          if (stream_b) {
+#pragma unroll
+            for (int r = 0; r < kTM; ++r) {
+              const long long i = tile * kTM + r;
+              if (i < B) st_relaxed_pair(C.z1_words + 2 * (i * kH1 + tid), S.epoch, __float_as_uint(act_bwd(acc[r], sH1T[tid * kR + kTM + r], L.act)));
+            }
+          } else {
 #pragma unroll
           for (int r = 0; r < kTM; ++r) {
             const long long i = tile * kTM + r;
@@ -885,6 +1263,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, c
               C.DZ1[i * kH1 + tid] = act_bwd(acc[r], h1v, L.act);
               C.H1[i * kH1 + tid] = h1v;
             }
+          }
           }
         }
         __syncthreads();
@@ -901,6 +1280,22 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, c
   const bool tree_here = pb.tree_here, team = pb.team, coarse = pb.coarse;
   const int n_workers = pb.n_workers, wid = cta;
   const bool tree_cta = tree_here && G > 1 && cta >= n_workers;
+  if (stream_b && !tree_cta) {
+    // ---------------------------------------------------------------- streamed phase B (no barrier: see StreamPlan)
+    if (tid == 0) asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(C.barrier), "r"(1u) : "memory");   // the host counts G arrivals per launch
+    RMC_STAMP(C, 6);
+    {
+      const int nt = static_cast<int>(n_tiles), s_idx = cta - sp.idle0;
+      const int k = (s_idx >= 0) ? s_idx : (cta >= nt ? sp.n_idle + (cta - nt) : sp.n_idle + nt + cta);      // order in which CTAs become free
+      const int total = kH2 / 16 + (kH1 / 16) * (kH2 / 16) + stream_w0_count(L), slots = sp.n_idle + 2 * nt;
+      const int extra = max(0, total - slots);
+      if (cta == nt && (S.phases & 2)) stream_publish_loss(C, S, nt, smem);      // first target CTA: its unit's operands are still 2 us away
+      if (k < extra) stream_run_any(C, S, k, smem);
+      if (extra + k < total) stream_run_any(C, S, extra + k, smem);
+    }
+    RMC_STAMP(C, 7); if (gap != nullptr && threadIdx.x == 0) atomicMax(gap + 1, global_timer_ns());
+    return;
+  }
   if (do_rows) {
     if (early_td && tree_cta) {
       __shared__ float s_lp[kThreads];
@@ -914,7 +1309,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, c
           if (guard.expired()) { spin_report_timeout(C.host_loss, S.epoch); gave_up = true; break; }
         }
       float lp = 0.f;
-      if (tid < n_tiles) {
+      // (streamed phase B: the first TARGET CTA publishes the loss -- it is free long before its gradient unit's operands
+      // exist, whereas here the system-scope fence of the publication would delay this member's share of the write-back)
+      const bool loss_here = !stream_b && cta == n_workers;
+      if (loss_here && tid < n_tiles) {
         uint2 w = ld_relaxed_pair(C.qt_flag + kLossWordBase + 2 * tid);
         while (w.x != S.epoch && !gave_up) {
           __nanosleep(20);
@@ -926,7 +1324,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, c
       __threadfence();                                                   // acquire side of the flag words
       s_lp[tid] = lp;
       __syncthreads();
-      if (cta == n_workers && tid == 0) publish_loss(C, S, s_lp, static_cast<int>(n_tiles));
+      if (loss_here && tid == 0) publish_loss(C, S, s_lp, static_cast<int>(n_tiles));
     } else {
       agent_barrier(C.barrier, S.barrier_target, C.host_loss, S.epoch);
     }
@@ -939,7 +1337,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, c
     // |td| per row: the published {epoch, |td|} words when the write-back started early, else the row CTAs' array
     const float* td_src = early_td ? reinterpret_cast<const float*>(C.qt_flag + kTdWordBase) + 1 : C.abs_td;
     const int td_stride = early_td ? 2 : 1;
-    unsigned long long* tdbg = C.dbg ? C.dbg + (blockIdx.y * gridDim.x + blockIdx.x) * 16 : nullptr;
+    unsigned long long* tdbg = C.dbg ? C.dbg + (blockIdx.y * gridDim.x + blockIdx.x) * kDbgSlots : nullptr;
     if (team) {
       tree_update_team(C.rp, C.nodes, td_src, td_stride, C.pri, B, tsize, (S.phases & 1) ? C.leaf_p : nullptr, S.per_eps, S.per_alpha,
                        S.per_pmax, cta - n_workers, (S.phases & 1) != 0, reinterpret_cast<double*>(smem), tdbg);

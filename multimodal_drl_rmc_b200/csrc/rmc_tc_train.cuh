@@ -404,6 +404,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_bwd_fused(AgentCtx C, const 
       for (int e = 0; e < 32; e += 4)
         *reinterpret_cast<float4*>(part + L.off_w2t + k * kW2LD + j0 + e) =
             make_float4(__uint_as_float(v[e]), __uint_as_float(v[e + 1]), __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
+      // the 4 padding columns of the row as well: every 32-byte sector of the partial blob is then written completely
+      // (a partially written sector has to be merged with DRAM contents when the reduction reads it)
+      if (j0 + 32 == kH2) *reinterpret_cast<float4*>(part + L.off_w2t + k * kW2LD + kH2) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
   {   // dW0^T[d][i] and db0[i] (column 15): half h handles i = 128*h + row
@@ -426,7 +429,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_bwd_fused(AgentCtx C, const 
     tc_ld16(tB2 + (static_cast<uint32_t>(32 * q) << 16), v);
     part[L.off_b2 + row] = __uint_as_float(v[15]);
   }
-  if (tid < L.NH) part[L.off_bh + tid] = dbh;
+  if (tid < ((L.NH + 3) & ~3)) part[L.off_bh + tid] = (tid < L.NH) ? dbh : 0.f;
   tc_fence_before();
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
@@ -444,11 +447,18 @@ __global__ void __launch_bounds__(256) k_tc_reduce_adam(AgentCtx C, StepScalars 
   const int n4 = L.total >> 2;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   if (p4 < n4) {
+    // batches of 8 predicated loads, all in flight before the first add (a plain `#pragma unroll` leaves a remainder loop of
+    // dependent load -> add iterations at full L2 latency each: 14 of this kernel's 21 us were spent there)
     const float4* src = reinterpret_cast<const float4*>(T.partials) + p4;
-#pragma unroll 10
-    for (int c = warp; c < T.n_part; c += 8) {
-      const float4 v = __ldcg(src + static_cast<size_t>(c) * n4);
-      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    for (int c0 = warp; c0 < T.n_part; c0 += 64) {
+      float4 v[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int c = c0 + 8 * q;
+        v[q] = (c < T.n_part) ? __ldcg(src + static_cast<size_t>(c) * n4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) { acc.x += v[q].x; acc.y += v[q].y; acc.z += v[q].z; acc.w += v[q].w; }
     }
   }
   s_sum[warp][lane] = acc;
@@ -465,9 +475,20 @@ __global__ void __launch_bounds__(256) k_tc_reduce_adam(AgentCtx C, StepScalars 
       tc_pack_updated(L, S, pi, pt, P);
     }
   }
-  if (blockIdx.x == 0 && threadIdx.x == 255) {
+  // loss: the per-block partials of k_tc_td (up to 1024) summed by the LAST block in a fixed order: thread t adds partials
+  // t, t+256, ... (loads in flight together), then the 256 thread sums are added in thread order.  (One thread walking the
+  // list serially took 20 of this kernel's 23 us: 512 dependent L2 round trips.)
+  if (blockIdx.x == gridDim.x - 1) {
+    __shared__ float s_loss[256];
+    float v[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { const int c = threadIdx.x + 256 * q; v[q] = (c < n_loss_parts) ? __ldcg(C.loss_part + c) : 0.f; }
+    __syncthreads();      // s_sum readers are done
+    s_loss[threadIdx.x] = ((v[0] + v[1]) + v[2]) + v[3];
+    __syncthreads();
+  if (threadIdx.x == 0) {
     float s = 0.f;
-    for (int c = 0; c < n_loss_parts; ++c) s += __ldcg(C.loss_part + c);
+    for (int c = 0; c < 256; ++c) s += s_loss[c];
     const float loss = s / static_cast<float>(S.Bglobal);
     C.loss[0] = loss;
     if (C.host_loss != nullptr) {
@@ -475,6 +496,7 @@ __global__ void __launch_bounds__(256) k_tc_reduce_adam(AgentCtx C, StepScalars 
       __threadfence_system();
       C.host_loss[1] = __uint_as_float(S.epoch);
     }
+  }
   }
 }
 

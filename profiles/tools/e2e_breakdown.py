@@ -21,7 +21,7 @@ for k in range(N + 200):
     agent.store_transitions(obs[j:j + 1], [int(act[j])], [float(rew[j])], [bool(done[j])], nxt[j:j + 1], None)
     t1 = time.perf_counter()
     agent.step += 1
-    agent.learn(fuse_target_update=True)
+    agent.learn()
     t2 = time.perf_counter()
     agent.update_target_network()
     t3 = time.perf_counter()
@@ -36,14 +36,14 @@ for k in range(N):
     j = k % 4096
     agent.store_transitions(obs[j:j + 1], [int(act[j])], [float(rew[j])], [bool(done[j])], nxt[j:j + 1], None)
     agent.step += 1
-    agent.learn(fuse_target_update=True)
+    agent.learn()
     agent.update_target_network()
 torch.cuda.synchronize()
 print("no per-step sync: %.1f us/step" % (1e6 * (time.perf_counter() - t0) / N))
 t0 = time.perf_counter()
 for k in range(N):
     agent.step += 1
-    agent.learn(fuse_target_update=True)
+    agent.learn()
     agent.update_target_network()
 torch.cuda.synchronize()
 print("learn only, no sync: %.1f us/step" % (1e6 * (time.perf_counter() - t0) / N))
@@ -54,7 +54,7 @@ for k in range(2000):
     j = k % 4096
     agent.store_transitions(obs[j:j + 1], [int(act[j])], [float(rew[j])], [bool(done[j])], nxt[j:j + 1], None)
     agent.step += 1
-    agent.learn(fuse_target_update=True)
+    agent.learn()
     agent.update_target_network()
     agent.last_loss()
 pr.disable()

@@ -34,13 +34,13 @@ for k in (0, 7):
     acc = []
     for it in range(6):
         step()
-        buf = np.zeros(1024 * 16, np.uint64)
+        buf = np.zeros(1024 * 32, np.uint64)
         torch.cuda.synchronize()
         # raw read of the whole debug buffer of member k
         n = C.c_int32()
         members[k]._lh  # keep alive
         _lib.check(lib.rmc_learner_debug_read_sync(members[k]._lh.handle, buf.ctypes.data, 1024, C.byref(n), _lib.stream_ptr()))
-        t = buf.reshape(1024, 16)[:, :14].astype(np.int64)
+        t = buf.reshape(1024, 32)[:, :14].astype(np.int64)
         rows = t[(t[:, 0] > 0)]
         acc.append(rows)
     a = acc[-1]

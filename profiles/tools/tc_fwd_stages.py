@@ -22,7 +22,7 @@ acts = torch.empty(n, dtype=torch.int64, device=agent.device)
 for _ in range(3):
     _lib.check(lib.rmc_learner_act_tc(agent._lh.handle, states.data_ptr(), n, acts.data_ptr(), _lib.stream_ptr()))
 torch.cuda.synchronize()
-buf = (C.c_uint64 * 64)()
+buf = (C.c_uint64 * 128)()          # 4 CTA records of 32 slots (kDbgSlots)
 got = C.c_int32(0)
 _lib.check(lib.rmc_learner_debug_read_sync(agent._lh.handle, buf, 4, C.byref(got), _lib.stream_ptr()))
 v = np.array(buf[:32], dtype=np.int64).reshape(4, 8)

@@ -18,7 +18,8 @@ agent.learn_precision = prec
 
 def step():
     agent.step += 1
-    agent.learn(fuse_target_update=True)
+    agent.learn()
+    agent.update_target_network()
 
 
 for _ in range(3):

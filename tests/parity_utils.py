@@ -129,7 +129,33 @@ def ulp_err(a, b, floor):
     return float(np.max(np.abs(a64 - b64) / sp))
 
 
-def run_parity_case(algo, D, B, cap, fill, steps, seed, soft=True, target_freq=30000, resync_tree=True, activation="relu", body="macro", pair=None):
+def f64_gradients(orc, online64, target64, tr):
+    """Gradients of the oracle's own minibatch (trace ``tr``) recomputed in float64 from float64 copies of the PRE-step
+    weights: the exact-arithmetic answer both fp32 implementations approximate (dqn/agent.py:245-272, same formulas)."""
+    o, n = torch.as_tensor(tr["obs"]).double(), torch.as_tensor(tr["nxt"]).double()
+    a = torch.as_tensor(tr["act"])
+    r, d = torch.as_tensor(tr["rew"]).double(), torch.as_tensor(tr["done"]).double()
+    with torch.no_grad():
+        q_next_tgt = target64(n)
+        if orc.double:
+            q_sel = torch.gather(q_next_tgt, 1, online64(n).argmax(dim=1, keepdim=True))
+        else:
+            q_sel = q_next_tgt.max(dim=1, keepdim=True)[0]
+        y = r + (1 - d) * float(np.float32(orc.gamma)) * q_sel
+    q_sa = torch.gather(online64(o), 1, a)
+    hub = torch.nn.functional.smooth_l1_loss(q_sa, y, reduction="none")
+    if orc.per:
+        w = torch.as_tensor(tr["is_w"].astype(np.float32)).double().unsqueeze(-1)
+        loss = torch.mean(w * hub)
+    else:
+        loss = torch.mean(hub)
+    online64.zero_grad()
+    loss.backward()
+    return np.concatenate([p.grad.numpy().ravel() for _, p in online64.named_parameters()])
+
+
+def run_parity_case(algo, D, B, cap, fill, steps, seed, soft=True, target_freq=30000, resync_tree=True, activation="relu", body="macro", pair=None,
+                    f64_truth=False):
     """Steps the oracle and the CUDA drop-in side by side.  Weights are checked three ways so that EVERY element is covered:
       * vs the oracle at 1e-5 on the elements whose gradient is well conditioned for Adam (|g| >= 1e-6; the fraction is
         returned as ``well_conditioned_frac``), and bounded by lr per step on the rest;
@@ -159,6 +185,9 @@ def run_parity_case(algo, D, B, cap, fill, steps, seed, soft=True, target_freq=3
         tr = {}
         lh = agent._lh
         pre = {k: lh.get_params(kind).cpu().numpy() for k, kind in (("p", _lib.ONLINE), ("t", _lib.TARGET), ("m", _lib.ADAM_M), ("v", _lib.ADAM_V))}
+        if f64_truth:
+            import copy
+            online64, target64 = copy.deepcopy(orc.online).double(), copy.deepcopy(orc.target).double()
         if per:
             u = rng.random(B)
             orc.learn(u=u, trace=tr)
@@ -191,6 +220,13 @@ def run_parity_case(algo, D, B, cap, fill, steps, seed, soft=True, target_freq=3
         worst = max(pt, key=pt.get)
         if pt[worst] > res["max_rel_grads"]:
             res["max_rel_grads"], res["worst_grad"] = pt[worst], worst
+        if f64_truth:      # both fp32 results against exact arithmetic: whose rounding is the difference above?
+            g64 = f64_gradients(orc, online64, target64, tr)
+            e_gpu, e_ref = per_tensor_max_rel(g_gpu, g64, sizes), per_tensor_max_rel(g_ref, g64, sizes)
+            e_gpu.pop("fc_val.bias", None), e_ref.pop("fc_val.bias", None)
+            res["gpu_grads_vs_f64"] = max(res.get("gpu_grads_vs_f64", 0.0), max(e_gpu.values()))
+            res["ref_grads_vs_f64"] = max(res.get("ref_grads_vs_f64", 0.0), max(e_ref.values()))
+            res["grads_vs_f64_per_tensor"] = {k: (float("%.3g" % e_gpu[k]), float("%.3g" % e_ref[k])) for k in e_gpu}
         # ---- priorities / tree
         if per:
             p_ref = np.power(np.minimum(tr["abs_td"].reshape(-1) + np.float32(1e-4), np.float32(1.0)), np.float32(0.6)).astype(np.float32)

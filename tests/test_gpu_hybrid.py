@@ -60,7 +60,8 @@ def test_hybrid_rejects_modes_not_built():
     _, agent = PU.make_pair("DuelingDoubleDQNAgent", D, 8, 64, 64, seed=3, activation="elu", body="hybrid")
     agent.learn_precision = "bf16"
     with pytest.raises(Exception):
-        agent.learn()
+        agent.learn()                       # recorded ...
+        agent.update_target_network()       # ... and refused when it is launched
 
 
 def test_hybrid_sidecar_resume_diagnostics_and_epsilon_greedy(tmp_path):

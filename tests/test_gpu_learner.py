@@ -106,6 +106,8 @@ def test_fused_target_update_equals_separate_call(soft):
     update_target_network() launches both as ONE kernel; (3) the explicit fuse_target_update=True kwarg."""
     from multimodal_drl_rmc_b200 import _lib
     agents = [PU.make_pair("PerDuelingDoubleDQNAgent", 14, 64, 500, 500, seed=9, soft=soft, target_freq=2)[1] for _ in range(3)]
+    for a in agents:
+        a.replay_memory_buffer._ring.flush()      # rows still held back by the last store_transitions would ride (as a push kernel) with the first step
     rng = np.random.default_rng(1)
     lib = _lib.lib()
     for step in range(1, 5):
