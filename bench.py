@@ -700,17 +700,21 @@ def extra_workloads(agent):
     return out
 
 
-_REAL_STDOUT = sys.stdout
+_JSON_FD = None
 
 
 def emit_json_line(line):
-    """The ONE line of the bench contract goes to the real stdout; everything else this process prints (the agents mirror the
-    reference's ``print("DEVICE", ...)`` in their constructor) is routed to stderr by main()."""
-    _REAL_STDOUT.write(json.dumps(line) + "\n")
-    _REAL_STDOUT.flush()
+    """The ONE line of the bench contract goes to the process's original stdout; everything else this process prints -- the
+    agents mirror the reference's ``print("DEVICE", ...)`` in their constructor, NCCL writes its version banner to the C
+    stdout -- is routed to stderr by main() (at the file-descriptor level, so native libraries are covered too)."""
+    os.write(_JSON_FD if _JSON_FD is not None else 1, (json.dumps(line) + "\n").encode())
 
 
 def main():
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)          # the real stdout, kept for the JSON line
+    os.dup2(2, 1)                 # fd 1 -> stderr for everything else (python prints and native libraries alike)
     sys.stdout = sys.stderr
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)

@@ -290,6 +290,12 @@ int32_t rmc_learner_act_eps_host_sync(rmc_learner_t* l, const float* obs_host, i
  * 3 target pass done, 4 online weights landed, 5 row phase done, 6 past the barrier, 7 done, 8..19 finer stamps
  * (profiles/tools/phase_timeline.py names them). */
 int32_t rmc_learner_debug_timing(rmc_learner_t* l, int32_t enable);
+/* Diagnostics: kernel-span recorder for the multi-kernel pipelines (tensor-core step, grid-wide sampler / tree write-back,
+ * peer exchange).  While enabled every such kernel notes its first CTA's start and last CTA's end (%globaltimer, ns); the
+ * read call returns {start, end} for 64 kernel slots (unused: {~0, 0}), resets them, and names the slots (comma separated).
+ * Shows the real overlap inside a graph-launched, two-stream step, which neither ncu nor CUDA events can. */
+int32_t rmc_debug_spans(int32_t device, int32_t enable);
+int32_t rmc_debug_spans_read_sync(int32_t device, uint64_t* out128_host, char* names_out, int32_t names_cap);
 /* [min CTA start, max CTA end] (%globaltimer ns) of the last 64 launches, slot = epoch % 64 (launch-gap diagnostic) */
 int32_t rmc_learner_debug_gaps_sync(rmc_learner_t* l, uint64_t* out128_host, rmc_stream_t s);
 int32_t rmc_learner_debug_read_sync(rmc_learner_t* l, uint64_t* out_host, int32_t max_ctas, int32_t* n_ctas,

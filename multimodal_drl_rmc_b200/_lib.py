@@ -138,6 +138,8 @@ _SIGS = {
     "rmc_learner_act_host_sync": (_i32, [_vp, _vp, _i64, _vp, _vp]),
     "rmc_learner_act_eps_host_sync": (_i32, [_vp, _vp, _i64, _vp, _f32, _u64, _u64, _vp]),
     "rmc_learner_debug_timing": (_i32, [_vp, _i32]),
+    "rmc_debug_spans": (_i32, [_i32, _i32]),
+    "rmc_debug_spans_read_sync": (_i32, [_i32, _vp, _vp, _i32]),
     "rmc_learner_debug_gaps_sync": (_i32, [_vp, _vp, _vp]),
     "rmc_learner_debug_read_sync": (_i32, [_vp, _vp, _i32, C.POINTER(_i32), _vp]),
     "rmc_group_create": (_i32, [C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), _i32]),

@@ -209,6 +209,7 @@ struct rmc_learner {
   TcTrainBufs tct{};
   cudaStream_t tc_side = nullptr;           // the PER write-back runs here beside the backward / Adam kernels
   cudaEvent_t tc_ev[2] = {};
+  bool no_graph = false;                    // set around the local part of a sharded step: the caller owns the graph
   struct { rmc_comm* c = nullptr; CommView V{}; int parity = 0; bool issue_side = false; long long Bg = 0; } early;   // sharded step: (leaf,|td|) leave right after TD
   // hybrid CNN+MLP network (rmc_hybrid.cuh): per-row activation / delta records
   bool hybrid = false;
@@ -1066,9 +1067,12 @@ static int32_t comm_side_writeback(rmc_learner* l, rmc_replay* r, cudaStream_t s
   rmc_comm* c = l->early.c;
   const long long Bg = l->early.Bg;
   cudaStream_t ts = l->tc_side;
-  RMC_CUDA(cudaEventRecord(l->tc_ev[0], st));
-  RMC_CUDA(cudaStreamWaitEvent(ts, l->tc_ev[0], 0));
-  RMC_CUDA(launch_pdl(k_comm_gather_td, dim3(static_cast<unsigned>(std::min<long long>(128, (Bg + 255) / 256))), dim3(256), 0, ts, l->early.V, l->early.parity, c->epoch,
+  const bool patching = g_trace != nullptr && g_trace->mode == 2;      // replaying a graph: the fork / join edges are in it
+  if (!patching) {
+    RMC_CUDA(cudaEventRecord(l->tc_ev[0], st));
+    RMC_CUDA(cudaStreamWaitEvent(ts, l->tc_ev[0], 0));
+  }
+  RMC_CUDA(launch_pdl(k_comm_gather_td, dim3(static_cast<unsigned>(std::min<long long>(256, (Bg + 255) / 256))), dim3(256), 0, ts, l->early.V, l->early.parity, c->epoch,
                       c->g_nodes, c->g_td));
   RMC_KERNEL_OK();
   const float eps = static_cast<float>(l->hyper.per_eps), alpha = static_cast<float>(l->hyper.per_alpha), pmax = static_cast<float>(l->hyper.per_pmax);
@@ -1080,7 +1084,7 @@ static int32_t comm_side_writeback(rmc_learner* l, rmc_replay* r, cudaStream_t s
     RMC_KERNEL_OK();
     if (int32_t e = tree_update_large(r, c->g_nodes, c->g_pri, Bg, false, ts)) return e;
   }
-  RMC_CUDA(cudaEventRecord(l->tc_ev[1], ts));
+  if (!patching) RMC_CUDA(cudaEventRecord(l->tc_ev[1], ts));
   return RMC_OK;
 }
 
@@ -1126,7 +1130,6 @@ static int32_t step_tc(rmc_learner* l, rmc_replay* r, const rmc_step_args_t* a, 
   g_tc_ev.n = 0; g_tc_ev.armed = true;
   g_tc_ev.mark("start", st);
   if (l->L.D > kTcK1 - 1) return fail(RMC_ERR_UNSUPPORTED, "tensor-core learner mode: obs_dim must be <= 15 (column 15 of the X tile carries the bias-gradient ones)");
-  if (l->L.act != 0) return fail(RMC_ERR_UNSUPPORTED, "tensor-core modes are built for ReLU bodies only");
   if ((a->phases & (RMC_PH_FORWARD | RMC_PH_BACKWARD)) != (RMC_PH_FORWARD | RMC_PH_BACKWARD))
     return fail(RMC_ERR_UNSUPPORTED, "tensor-core learner mode needs RMC_PH_FORWARD and RMC_PH_BACKWARD in one step");
   if (a->grads_in_dev != nullptr) return fail(RMC_ERR_ARG, "tensor-core learner mode: grads_in_dev belongs to an Adam-only step");
@@ -1167,6 +1170,7 @@ static int32_t step_tc(rmc_learner* l, rmc_replay* r, const rmc_step_args_t* a, 
   J.j[1].packed = l->tc_packed_target; J.j[1].heads_out = T.heads_t;
   J.j[2].packed = l->tc_packed;        J.j[2].heads_out = T.heads_s;
   J.j[0].X.row_stride = J.j[1].X.row_stride = J.j[2].X.row_stride = l->rf;
+  J.j[0].X.act = J.j[1].X.act = J.j[2].X.act = l->L.act;
   J.j[0].X.col_off = J.j[1].X.col_off = l->L.D;      // s' rows: next_obs sits D floats into the gathered row
   J.j[2].X.col_off = 0; J.j[2].X.Xb = T.Xb; J.j[2].X.H1b = T.H1b; J.j[2].X.H2b = T.H2b;
   int c0, c2;
@@ -1190,7 +1194,7 @@ static int32_t step_tc(rmc_learner* l, rmc_replay* r, const rmc_step_args_t* a, 
   static const bool side_tree = [] { const char* e = std::getenv("RMC_TC_SIDE_TREE"); return !(e && e[0] == '0'); }();
   const bool write_back = (a->phases & RMC_PH_PRIORITY) && l->spec.prioritized;
   if (l->early.c != nullptr) {      // sharded step: this rank's (leaf, |td|) slice leaves now, long before its gradients
-    RMC_CUDA(launch_pdl(k_comm_publish_td, dim3(static_cast<unsigned>(std::max<long long>(1, std::min<long long>(32, (B + 1023) / 1024)))), dim3(256), 0, st, l->early.V,
+    RMC_CUDA(launch_pdl(k_comm_publish_td, dim3(static_cast<unsigned>(std::max<long long>(1, std::min<long long>(148, (B + 1023) / 1024)))), dim3(256), 0, st, l->early.V,
                         l->early.parity, l->early.c->epoch, C.nodes, C.abs_td, B, l->early.c->arrive_td));
     RMC_KERNEL_OK();
     if (l->early.issue_side)
@@ -1223,13 +1227,14 @@ static int32_t step_tc(rmc_learner* l, rmc_replay* r, const rmc_step_args_t* a, 
   S.epoch = l->epoch;
   // the Adam kernel refreshes the bf16 operand images element by element: no pack kernels on the next step
   const TcPackOut P{l->tc_packed, l->tc_packed_bwd, l->tc_packed_target};
-  RMC_CUDA(launch_pdl(k_tc_reduce_adam, dim3(blocks_for(l->L.total, 128)), dim3(256), 0, st, l->ctx, S, T, static_cast<int>(td_blocks), P));
+  RMC_CUDA(launch_pdl(k_tc_reduce_adam, dim3(blocks_for(l->L.total, 128)), dim3(256), 0, st, l->ctx, S, T, static_cast<int>(td_blocks), P, 0));
   RMC_KERNEL_OK();
   g_tc_ev.mark("reduce_adam", st);
   if (g_tc_ev.on) {      // diagnostic: the same kernel again on warm inputs (how much of its time is the first touch of the partials?)
     static const int rep = [] { const char* e = std::getenv("RMC_TC_REDUCE_REPEAT"); return e ? std::atoi(e) : 0; }();
+    static const int skip = [] { const char* e = std::getenv("RMC_TC_REDUCE_SKIP"); return e ? std::atoi(e) : 0; }();
     for (int k = 0; k < rep; ++k) {
-      RMC_CUDA(launch_pdl(k_tc_reduce_adam, dim3(blocks_for(l->L.total, 128)), dim3(256), 0, st, l->ctx, S, T, static_cast<int>(td_blocks), P));
+      RMC_CUDA(launch_pdl(k_tc_reduce_adam, dim3(blocks_for(l->L.total, 128)), dim3(256), 0, st, l->ctx, S, T, static_cast<int>(td_blocks), P, skip));
       RMC_KERNEL_OK();
     }
     if (rep > 0) g_tc_ev.mark("reduce_adam_again_xN", st);
@@ -1648,7 +1653,7 @@ extern "C" int32_t rmc_learner_step(rmc_learner_t* l, rmc_replay_t* r, const rmc
     const int full = RMC_PH_FORWARD | RMC_PH_BACKWARD | RMC_PH_ADAM;
     const bool images_current = l->tct_ready && l->tc_packed_version == l->online_version && l->tc_bwd_version == l->online_version &&
                                 l->tc_target_version == l->target_version;
-    if (l->early.c == nullptr && images_current && (a->phases & full) == full && a->grads_in_dev == nullptr && !tc_events_on())
+    if (l->early.c == nullptr && !l->no_graph && images_current && (a->phases & full) == full && a->grads_in_dev == nullptr && !tc_events_on())
       return run_step_graph(l, a->batch, 0x20000000 | a->phases, st, [&](cudaStream_t s_) { return step_tc(l, r, a, S, s_); });
     return step_tc(l, r, a, S, st);
   }
@@ -1802,6 +1807,7 @@ extern "C" int32_t rmc_comm_status_sync(rmc_comm_t* c, uint32_t* timed_out_epoch
   return RMC_OK;
 }
 
+static int32_t sharded_body(rmc_learner* l, rmc_replay* r, rmc_comm* c, const rmc_step_args_t* a, int32_t stages, cudaStream_t st);
 extern "C" int32_t rmc_learner_step_sharded(rmc_learner_t* l, rmc_replay_t* r, rmc_comm_t* c, const rmc_step_args_t* a, int32_t stages, rmc_stream_t s) {
   if (!l || !r || !c || !a) return fail(RMC_ERR_ARG, "rmc_learner_step_sharded: null");
   if (!c->connected || c->learner != l) return fail(RMC_ERR_STATE, "rmc_learner_step_sharded: comm not connected to this learner");
@@ -1814,8 +1820,22 @@ extern "C" int32_t rmc_learner_step_sharded(rmc_learner_t* l, rmc_replay_t* r, r
   if ((a->phases & want) != want) return fail(RMC_ERR_ARG, "rmc_learner_step_sharded: needs FORWARD, BACKWARD and ADAM");
   if (stages < 1 || stages > 3) return fail(RMC_ERR_ARG, "rmc_learner_step_sharded: stages must be 1, 2 or 3");
   cudaStream_t st = as_stream(s);
+  if (stages & 1) c->epoch = (c->epoch >= 0x7fffffffu) ? 1u : c->epoch + 1u;      // once per step, outside the (re-traceable) body: ranks stay in lockstep
+  // The tensor-core step is ~16 short kernels on two streams: replayed as ONE graph launch per step once the operand images
+  // are current (re-trace and patch, see launch_pdl; the epoch / parity arguments of the exchange kernels are patched each step).
+  // A kernel of the graph that waits for a peer's flag simply keeps the graph's later nodes waiting, like stream order would.
+  const bool images = l->tct_ready && l->tc_packed_version == l->online_version && l->tc_bwd_version == l->online_version &&
+                      l->tc_target_version == l->target_version;
+  static const bool sharded_graph = [] { const char* e = std::getenv("RMC_SHARDED_GRAPH"); return !(e && e[0] == '0'); }();
+  if (sharded_graph && stages == 3 && a->precision == RMC_PREC_BF16_TC && !l->hybrid && images && a->grads_in_dev == nullptr && !tc_events_on())
+    return run_step_graph(l, a->batch, 0x10000000 | a->phases, st, [&](cudaStream_t s_) { return sharded_body(l, r, c, a, stages, s_); });
+  return sharded_body(l, r, c, a, stages, st);
+}
+
+static int32_t sharded_body(rmc_learner* l, rmc_replay* r, rmc_comm* c, const rmc_step_args_t* a, int32_t stages, cudaStream_t st) {
+  rmc_stream_t s = reinterpret_cast<rmc_stream_t>(st);
+  const long long Bg = a->global_batch > 0 ? a->global_batch : a->batch;
   const bool per = l->spec.prioritized != 0 && (a->phases & RMC_PH_PRIORITY);
-  if (stages & 1) c->epoch = (c->epoch >= 0x7fffffffu) ? 1u : c->epoch + 1u;
   const int parity = static_cast<int>(c->epoch & 1u);
   CommView V = c->view;
   for (int q = 0; q <= c->world; ++q) {
@@ -1833,11 +1853,13 @@ extern "C" int32_t rmc_learner_step_sharded(rmc_learner_t* l, rmc_replay_t* r, r
   a1.phases = a->phases & (RMC_PH_SAMPLE | RMC_PH_FORWARD | RMC_PH_BACKWARD);
   a1.grads_in_dev = nullptr;
   if (early) { l->early.c = c; l->early.V = V; l->early.parity = parity; l->early.Bg = Bg; l->early.issue_side = (stages == 3); }
+  l->no_graph = true;
   const int32_t e1 = rmc_learner_step(l, r, &a1, s);
+  l->no_graph = false;
   l->early.c = nullptr;
   if (e1) return e1;
   // 2. publish: gradient blob, loss partial, (leaf, |td|) slice -> own exchange buffer, then one flag per rank
-  const unsigned pub_blocks = std::max(1u, std::min(64u, blocks_for(std::max<long long>(l->L.total, n_local), 1024)));
+  const unsigned pub_blocks = std::max(1u, std::min(148u, blocks_for(std::max<long long>(l->L.total / 4, (per && !early) ? n_local : 0), 1024)));
   RMC_CUDA(launch_pdl(k_comm_publish, dim3(pub_blocks), dim3(256), 0, st, V, parity, c->epoch, l->ctx.grads, l->L.total, l->ctx.loss, (per && !early) ? l->ctx.nodes : nullptr, l->ctx.abs_td,
                                             n_local, c->arrive));
   RMC_KERNEL_OK();
@@ -1872,7 +1894,7 @@ extern "C" int32_t rmc_learner_step_sharded(rmc_learner_t* l, rmc_replay_t* r, r
   }
   // 4. PER: the full write-back of the GLOBAL batch on every replica, in global batch order (trees stay identical)
   if (early) {
-    RMC_CUDA(cudaStreamWaitEvent(st, l->tc_ev[1], 0));      // the side-stream write-back joins here
+    if (!(g_trace != nullptr && g_trace->mode == 2)) RMC_CUDA(cudaStreamWaitEvent(st, l->tc_ev[1], 0));      // the side-stream write-back joins here
   } else if (per) {
     if (Bg <= kTreeCtaMax) {
       RMC_CUDA(launch_pdl(k_tree_update_small, dim3(1), dim3(kThreads), 0, st, r->dev, c->g_nodes, nullptr, c->g_td, c->g_pri, Bg, static_cast<float>(l->hyper.per_eps),
@@ -1941,22 +1963,21 @@ extern "C" int32_t rmc_learner_loss_sync(rmc_learner_t* l, float* out_host, rmc_
   if (int32_t e = use_device(l->device)) return e;
   if (int32_t e = step_health(l)) return e;
   if (l->host_loss != nullptr && l->loss_epoch != 0) {
-    // the step kernel stores (loss, epoch) straight into mapped host memory: wait for this launch's epoch
-    unsigned want = l->loss_epoch, got = 0;
+    // the kernel stores {loss, epoch} as one 8-byte word into mapped host memory: wait for this launch's epoch
+    const unsigned want = l->loss_epoch;
+    const volatile unsigned long long* word = reinterpret_cast<const volatile unsigned long long*>(l->host_loss);
+    auto take = [&](unsigned long long w) {
+      const unsigned lo = static_cast<unsigned>(w & 0xffffffffull);
+      std::memcpy(out_host, &lo, sizeof(float));
+    };
     for (long long spin = 0; spin < 200000000ll; ++spin) {
-      const float bits = l->host_loss[1];
-      std::memcpy(&got, &bits, sizeof(got));
-      if (got == want) {
-        std::atomic_thread_fence(std::memory_order_acquire);
-        *out_host = l->host_loss[0];
-        return step_health(l);
-      }
+      const unsigned long long w = *word;
+      if (static_cast<unsigned>(w >> 32) == want) { take(w); return step_health(l); }
       if ((spin & 0xfff) == 0xfff && cudaStreamQuery(as_stream(s)) != cudaErrorNotReady) break;   // finished or faulted
     }
     RMC_CUDA(cudaStreamSynchronize(as_stream(s)));
-    const float bits = l->host_loss[1];
-    std::memcpy(&got, &bits, sizeof(got));
-    if (got == want) { *out_host = l->host_loss[0]; return RMC_OK; }
+    const unsigned long long w = *word;
+    if (static_cast<unsigned>(w >> 32) == want) { take(w); return RMC_OK; }
   }
   RMC_CUDA(cudaMemcpyAsync(out_host, l->ctx.loss, sizeof(float), cudaMemcpyDeviceToHost, as_stream(s)));
   RMC_CUDA(cudaStreamSynchronize(as_stream(s)));
@@ -2008,7 +2029,6 @@ extern "C" int32_t rmc_learner_act(rmc_learner_t* l, const float* obs_dev, int64
 static int32_t infer_tc(rmc_learner* l, const float* obs_dev, long long n, long long* actions, float* heads, int mode, cudaStream_t st) {
   if (l->hybrid) return fail(RMC_ERR_UNSUPPORTED, "tensor-core act mode: built for the macro MLP only");
   if (l->L.D > kTcK1) return fail(RMC_ERR_UNSUPPORTED, "tensor-core act mode: obs_dim must be <= 16");
-  if (l->L.act != 0) return fail(RMC_ERR_UNSUPPORTED, "tensor-core modes are built for ReLU bodies only");
   if (l->tc_packed == nullptr) {
     if (int32_t e = owned_alloc(l, &l->tc_packed, static_cast<size_t>(kTcBlobBytes))) return e;
     RMC_CUDA(cudaFuncSetAttribute(k_mlp_infer_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
@@ -2022,6 +2042,7 @@ static int32_t infer_tc(rmc_learner* l, const float* obs_dev, long long n, long 
   const unsigned grid = static_cast<unsigned>(std::min<long long>(n_tiles, l->num_sms));
   TcFwdExtra ex{};
   ex.row_stride = l->L.D;
+  ex.act = l->L.act;
   if (std::getenv("RMC_TC_FWD_DBG") != nullptr) ex.dbg = reinterpret_cast<long long*>(l->dbg_buf);   // diagnostics: stage clocks of CTA 0
   k_mlp_infer_tc<<<grid, kTcFwdThreads, kTcSmemBytes, st>>>(l->tc_packed, l->L.D, l->L.A, l->L.NH, l->L.dueling, obs_dev, n, actions, heads, mode, ex);
   RMC_KERNEL_OK();
@@ -2202,6 +2223,41 @@ extern "C" int32_t rmc_group_step(rmc_group_t* g, const rmc_step_args_t* a, rmc_
 }
 
 // ------------------------------------------------------------------------------ debug timing
+// Kernel-span recorder (see rmc_device.cuh): enable = 1 allocates / resets the table and points the kernels at it, 0
+// detaches it.  rmc_debug_spans_read_sync copies {first CTA start, last CTA end} (ns, %globaltimer) of the 64 slots and
+// resets them; names_out (optional) receives the slot names, comma separated.
+static unsigned long long* g_span_dev[kMaxDevices] = {nullptr};
+extern "C" int32_t rmc_debug_spans(int32_t device, int32_t enable) {
+  if (device < 0 || device >= kMaxDevices) return fail(RMC_ERR_ARG, "rmc_debug_spans: device");
+  if (int32_t e = use_device(device)) return e;
+  RMC_CUDA(cudaDeviceSynchronize());
+  unsigned long long* ptr = nullptr;
+  if (enable) {
+    if (g_span_dev[device] == nullptr) RMC_CUDA(cudaMalloc(reinterpret_cast<void**>(&g_span_dev[device]), 128 * sizeof(unsigned long long)));
+    std::vector<unsigned long long> init(128);
+    for (int k = 0; k < 64; ++k) { init[2 * k] = ~0ull; init[2 * k + 1] = 0ull; }
+    RMC_CUDA(cudaMemcpy(g_span_dev[device], init.data(), 128 * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+    ptr = g_span_dev[device];
+  }
+  RMC_CUDA(cudaMemcpyToSymbol(g_span_table, &ptr, sizeof(ptr)));
+  return RMC_OK;
+}
+extern "C" int32_t rmc_debug_spans_read_sync(int32_t device, uint64_t* out128_host, char* names_out, int32_t names_cap) {
+  if (device < 0 || device >= kMaxDevices || !out128_host || g_span_dev[device] == nullptr) return fail(RMC_ERR_ARG, "rmc_debug_spans_read_sync: not enabled");
+  if (int32_t e = use_device(device)) return e;
+  RMC_CUDA(cudaDeviceSynchronize());
+  RMC_CUDA(cudaMemcpy(out128_host, g_span_dev[device], 128 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  std::vector<unsigned long long> init(128);
+  for (int k = 0; k < 64; ++k) { init[2 * k] = ~0ull; init[2 * k + 1] = 0ull; }
+  RMC_CUDA(cudaMemcpy(g_span_dev[device], init.data(), 128 * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+  if (names_out && names_cap > 0) {
+    const char* names = "sample,fwd3,td,bwd,reduce_adam,td_to_pri,tree_stamp,tree_apply,tree_top,extremes,publish_td,gather_td,publish,comm_reduce,tree_small,uniform,pack";
+    std::strncpy(names_out, names, static_cast<size_t>(names_cap) - 1);
+    names_out[names_cap - 1] = 0;
+  }
+  return RMC_OK;
+}
+
 extern "C" int32_t rmc_learner_debug_timing(rmc_learner_t* l, int32_t enable) {
   if (!l) return fail(RMC_ERR_ARG, "rmc_learner_debug_timing: null");
   l->ctx.dbg = enable ? l->dbg_buf : nullptr;

@@ -95,33 +95,67 @@ __device__ __forceinline__ bool comm_wait_all(const CommView& V, const unsigned*
   return s_ok != 0;
 }
 
+// Publish protocol (both publish kernels): every block copies its part with the loads of a thread batched, then ONE thread
+// per block makes the block's stores visible at GPU scope (bar.sync + fence: cumulative over the block's threads) and arrives
+// at a counter; the last block to arrive executes the single system-scope fence of the kernel and release-stores the epoch
+// into every rank's flag array.  (The first version fenced at system scope in every thread of every block and copied with a
+// load -> store loop: 13-14 us for 152 KB, on the critical path of the sharded step.)
+__device__ __forceinline__ bool comm_block_arrive_last(unsigned* arrive) {
+  __shared__ bool s_last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_last = (atomicAdd(arrive, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  return s_last;
+}
+__device__ __forceinline__ void comm_raise_flags(const CommView& V, int flag_word0, int parity, unsigned epoch, unsigned* arrive) {
+  if (threadIdx.x == 0) {
+    *arrive = 0u;
+    __threadfence_system();
+  }
+  __syncthreads();
+  if (threadIdx.x < V.world) {     // flag of (this rank, this parity) in every rank's header, own included
+    unsigned* flags = reinterpret_cast<unsigned*>(V.base[threadIdx.x]) + flag_word0;
+    st_release_sys_u32(flags + parity * kCommMaxWorld + V.rank, epoch);
+  }
+}
+
 __global__ void __launch_bounds__(256) k_comm_publish(CommView V, int parity, unsigned epoch, const float* __restrict__ grads, int total,
                                                       const float* __restrict__ loss, const long long* __restrict__ nodes,
                                                       const float* __restrict__ abs_td, long long n_local, unsigned* arrive) {
   pdl_enter();
-  __shared__ bool s_last;
+  const SpanScope span_(SPAN_PUBLISH);
   unsigned char* slot = comm_slot(V, V.rank, parity);
-  float* g = reinterpret_cast<float*>(slot);
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   const long long t0 = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  for (long long k = t0; k < total; k += stride) g[k] = __ldcg(grads + k);
+  {   // gradient blob as float4 (total is a multiple of 4), 4 loads in flight per thread
+    const float4* src = reinterpret_cast<const float4*>(grads);
+    float4* dst = reinterpret_cast<float4*>(slot);
+    const long long n4 = total >> 2;
+    for (long long k0 = t0; k0 < n4; k0 += 4 * stride) {
+      float4 v[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) if (k0 + q * stride < n4) v[q] = __ldcg(src + k0 + q * stride);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) if (k0 + q * stride < n4) dst[k0 + q * stride] = v[q];
+    }
+  }
   if (t0 == 0) *reinterpret_cast<float*>(slot + V.off_loss) = __ldcg(loss);
   if (nodes != nullptr) {
     long long* dn = reinterpret_cast<long long*>(slot + V.off_nodes);
     float* dt = reinterpret_cast<float*>(slot + V.off_td);
-    for (long long k = t0; k < n_local; k += stride) { dn[k] = __ldcg(nodes + k); dt[k] = __ldcg(abs_td + k); }
+    for (long long k0 = t0; k0 < n_local; k0 += 4 * stride) {
+      long long a[4]; float b[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) if (k0 + q * stride < n_local) { a[q] = __ldcg(nodes + k0 + q * stride); b[q] = __ldcg(abs_td + k0 + q * stride); }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) if (k0 + q * stride < n_local) { dn[k0 + q * stride] = a[q]; dt[k0 + q * stride] = b[q]; }
+    }
   }
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) s_last = (atomicAdd(arrive, 1u) == gridDim.x - 1);
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence_system();
-  if (threadIdx.x < V.world) {     // flag of (this rank, this parity) in every rank's header, own included
-    unsigned* flags = reinterpret_cast<unsigned*>(V.base[threadIdx.x]);
-    st_release_sys_u32(flags + parity * kCommMaxWorld + V.rank, epoch);
-  }
-  if (threadIdx.x == 0) *arrive = 0u;
+  if (!comm_block_arrive_last(arrive)) return;
+  comm_raise_flags(V, 0, parity, epoch, arrive);
 }
 
 // Early exchange of the (leaf, |td|) slices (tensor-core mode: |td| exists right after the TD kernel, long before the
@@ -130,26 +164,41 @@ __global__ void __launch_bounds__(256) k_comm_publish(CommView V, int parity, un
 __global__ void __launch_bounds__(256) k_comm_publish_td(CommView V, int parity, unsigned epoch, const long long* __restrict__ nodes,
                                                          const float* __restrict__ abs_td, long long n_local, unsigned* arrive) {
   pdl_enter();
-  __shared__ bool s_last;
+  const SpanScope span_(SPAN_PUBLISH_TD);
   unsigned char* slot = comm_slot(V, V.rank, parity);
   long long* dn = reinterpret_cast<long long*>(slot + V.off_nodes);
   float* dt = reinterpret_cast<float*>(slot + V.off_td);
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-  for (long long k = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; k < n_local; k += stride) { dn[k] = __ldcg(nodes + k); dt[k] = __ldcg(abs_td + k); }
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) s_last = (atomicAdd(arrive, 1u) == gridDim.x - 1);
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence_system();
-  if (threadIdx.x < V.world) {
-    unsigned* flags = reinterpret_cast<unsigned*>(V.base[threadIdx.x]) + kCommTdFlagWord;
-    st_release_sys_u32(flags + parity * kCommMaxWorld + V.rank, epoch);
+  for (long long k0 = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; k0 < n_local; k0 += 4 * stride) {
+    long long a[4]; float b[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) if (k0 + q * stride < n_local) { a[q] = __ldcg(nodes + k0 + q * stride); b[q] = __ldcg(abs_td + k0 + q * stride); }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) if (k0 + q * stride < n_local) { dn[k0 + q * stride] = a[q]; dt[k0 + q * stride] = b[q]; }
   }
-  if (threadIdx.x == 0) *arrive = 0u;
+  if (!comm_block_arrive_last(arrive)) return;
+  comm_raise_flags(V, kCommTdFlagWord, parity, epoch, arrive);
 }
+
+// (leaf, |td|) of global sample i from the slot of the rank that owns it: one thread per sample (both loads of a sample in
+// flight together; a per-rank loop would chain one NVLink round trip per rank)
+__device__ __forceinline__ void comm_gather_rows(const CommView& V, int parity, long long* __restrict__ g_nodes, float* __restrict__ g_td, long long first,
+                                                 long long stride) {
+  const long long total = V.shard_lo[V.world];
+  for (long long i = first; i < total; i += stride) {
+    int r = 0;
+    while (r + 1 < V.world && i >= V.shard_lo[r + 1]) ++r;
+    const long long k = i - V.shard_lo[r];
+    const long long node = ld_sys_s64(reinterpret_cast<const long long*>(comm_slot(V, r, parity) + V.off_nodes) + k);
+    const float td = ld_sys_f32(reinterpret_cast<const float*>(comm_slot(V, r, parity) + V.off_td) + k);
+    g_nodes[i] = node;
+    g_td[i] = td;
+  }
+}
+
 __global__ void __launch_bounds__(256) k_comm_gather_td(CommView V, int parity, unsigned epoch, long long* __restrict__ g_nodes, float* __restrict__ g_td) {
   pdl_enter();
+  const SpanScope span_(SPAN_GATHER_TD);
   const unsigned* my_flags = reinterpret_cast<const unsigned*>(V.base[V.rank]);
   if (!comm_wait_all(V, my_flags + kCommTdFlagWord + parity * kCommMaxWorld, epoch, V.verdict + 1)) {
     // a peer never published its slice: hand the write-back that follows a list of out-of-range nodes (the tree kernels
@@ -157,22 +206,14 @@ __global__ void __launch_bounds__(256) k_comm_gather_td(CommView V, int parity, 
     for (long long k = blockIdx.x * 256ll + threadIdx.x; k < V.shard_lo[V.world]; k += static_cast<long long>(gridDim.x) * 256) { g_nodes[k] = -1; g_td[k] = 0.f; }
     return;
   }
-  const long long stride = static_cast<long long>(gridDim.x) * 256;
-  for (int r = 0; r < V.world; ++r) {
-    const long long lo = V.shard_lo[r], n = V.shard_lo[r + 1] - lo;
-    const long long* sn = reinterpret_cast<const long long*>(comm_slot(V, r, parity) + V.off_nodes);
-    const float* st = reinterpret_cast<const float*>(comm_slot(V, r, parity) + V.off_td);
-    for (long long k = blockIdx.x * 256ll + threadIdx.x; k < n; k += stride) {
-      g_nodes[lo + k] = ld_sys_s64(sn + k);
-      g_td[lo + k] = ld_sys_f32(st + k);
-    }
-  }
+  comm_gather_rows(V, parity, g_nodes, g_td, blockIdx.x * 256ll + threadIdx.x, static_cast<long long>(gridDim.x) * 256);
 }
 
 // blocks [0, param_blocks): parameters; the remaining blocks: (leaf, |td|) gather.
 __global__ void __launch_bounds__(256) k_comm_reduce_adam(AgentCtx C, StepScalars S, CommView V, int parity, unsigned epoch, int param_blocks,
                                                           long long* __restrict__ g_nodes, float* __restrict__ g_td, int want_gather, TcPackOut P) {
   pdl_enter();
+  const SpanScope span_(SPAN_COMM_REDUCE);
   const unsigned* my_flags = reinterpret_cast<const unsigned*>(V.base[V.rank]);
   if (!comm_wait_all(V, my_flags + parity * kCommMaxWorld, epoch, V.verdict)) {
     // all-or-nothing: no block applies Adam.  The (leaf, |td|) gather part hands the write-back out-of-range nodes.
@@ -184,34 +225,30 @@ __global__ void __launch_bounds__(256) k_comm_reduce_adam(AgentCtx C, StepScalar
   if (static_cast<int>(blockIdx.x) < param_blocks) {
     const int pi = blockIdx.x * 256 + threadIdx.x;
     if (pi < L.total) {
+      // all ranks' values in flight together, THEN the adds in rank order (a load-add loop is one NVLink round trip per rank:
+      // ~1.5 us each, 12 us at 8 ranks)
+      float v[kCommMaxWorld];
+#pragma unroll
+      for (int r = 0; r < kCommMaxWorld; ++r) v[r] = (r < V.world) ? ld_sys_f32(reinterpret_cast<const float*>(comm_slot(V, r, parity)) + pi) : 0.f;
       float g = 0.f;
-      for (int r = 0; r < V.world; ++r) g += ld_sys_f32(reinterpret_cast<const float*>(comm_slot(V, r, parity)) + pi);
+#pragma unroll
+      for (int r = 0; r < kCommMaxWorld; ++r) g += (r < V.world) ? v[r] : 0.f;
       C.grads[pi] = g;
       const float2 pt = adam_polyak_element(C, S, pi, g);
       tc_pack_updated(L, S, pi, pt, P);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
+      float lv[kCommMaxWorld];
+#pragma unroll
+      for (int r = 0; r < kCommMaxWorld; ++r) lv[r] = (r < V.world) ? ld_sys_f32(reinterpret_cast<const float*>(comm_slot(V, r, parity) + V.off_loss)) : 0.f;
       float loss = 0.f;
-      for (int r = 0; r < V.world; ++r) loss += ld_sys_f32(reinterpret_cast<const float*>(comm_slot(V, r, parity) + V.off_loss));
+#pragma unroll
+      for (int r = 0; r < kCommMaxWorld; ++r) loss += (r < V.world) ? lv[r] : 0.f;
       C.loss[0] = loss;
-      if (C.host_loss != nullptr) {
-        C.host_loss[0] = loss;
-        __threadfence_system();
-        C.host_loss[1] = __uint_as_float(S.epoch);
-      }
+      host_loss_store(C.host_loss, loss, S.epoch);
     }
   } else if (want_gather) {
-    const long long nb = gridDim.x - param_blocks;
-    const long long stride = nb * 256;
-    for (int r = 0; r < V.world; ++r) {
-      const long long lo = V.shard_lo[r], n = V.shard_lo[r + 1] - lo;
-      const long long* sn = reinterpret_cast<const long long*>(comm_slot(V, r, parity) + V.off_nodes);
-      const float* st = reinterpret_cast<const float*>(comm_slot(V, r, parity) + V.off_td);
-      for (long long k = (blockIdx.x - param_blocks) * 256ll + threadIdx.x; k < n; k += stride) {
-        g_nodes[lo + k] = ld_sys_s64(sn + k);
-        g_td[lo + k] = ld_sys_f32(st + k);
-      }
-    }
+    comm_gather_rows(V, parity, g_nodes, g_td, (blockIdx.x - param_blocks) * 256ll + threadIdx.x, static_cast<long long>(gridDim.x - param_blocks) * 256);
   }
 }
 

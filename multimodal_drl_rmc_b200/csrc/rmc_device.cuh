@@ -97,6 +97,13 @@ struct SpinGuard {
     return now - t0 > kSpinTimeoutNs;
   }
 };
+// The loss of a step goes straight to mapped pinned host memory as ONE 8-byte word {loss bits, launch epoch}: a single
+// aligned 8-byte store is one PCIe write, so the host sees the value and its epoch together and no system-scope fence is
+// needed between them (that fence cost 1.5-4 us at the end of the publishing CTA / kernel).
+__device__ __forceinline__ void host_loss_store(volatile float* host_loss, float loss, unsigned epoch) {
+  if (host_loss != nullptr)
+    asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(host_loss), "r"(__float_as_uint(loss)), "r"(epoch) : "memory");
+}
 // err: mapped pinned host memory of the agent (AgentCtx::host_loss), word [2] = epoch of a launch whose spin timed out
 __device__ __forceinline__ void spin_report_timeout(volatile float* err, unsigned epoch) {
   if (err != nullptr) {
@@ -123,6 +130,25 @@ __device__ __forceinline__ void agent_barrier(unsigned* ctr, unsigned target, vo
   }
   __syncthreads();
 }
+
+// Kernel-span recorder (diagnostic, RMC_SPANS=1): every kernel of the multi-kernel pipelines notes its first CTA's start and
+// last CTA's end (%globaltimer) in a device table, slot = kernel id.  Unlike ncu's serialised cold-cache replays and unlike
+// CUDA events (which break programmatic dependent launches and cannot look inside a graph launch), this shows the real
+// overlap of the kernels of a graph-launched step.  g_span_table == nullptr (default): one predictable branch per CTA.
+__device__ unsigned long long* g_span_table = nullptr;      // [64][2] = {min start, max end}
+__device__ __forceinline__ void span_begin(int slot) {
+  if (g_span_table != nullptr && threadIdx.x == 0) atomicMin(g_span_table + 2 * slot, global_timer_ns());
+}
+__device__ __forceinline__ void span_end(int slot) {
+  if (g_span_table != nullptr && threadIdx.x == 0) atomicMax(g_span_table + 2 * slot + 1, global_timer_ns());
+}
+struct SpanScope {      // span of a kernel whose CTAs return from several places
+  int slot;
+  __device__ __forceinline__ explicit SpanScope(int s) : slot(s) { span_begin(s); }
+  __device__ __forceinline__ ~SpanScope() { span_end(slot); }
+};
+enum SpanSlot { SPAN_SAMPLE = 0, SPAN_FWD3, SPAN_TD, SPAN_BWD, SPAN_REDUCE_ADAM, SPAN_TD_TO_PRI, SPAN_TREE_STAMP, SPAN_TREE_APPLY, SPAN_TREE_TOP,
+                SPAN_EXTREMES, SPAN_PUBLISH_TD, SPAN_GATHER_TD, SPAN_PUBLISH, SPAN_COMM_REDUCE, SPAN_TREE_SMALL, SPAN_UNIFORM, SPAN_PACK, SPAN_COUNT };
 
 // first statement of every kernel launched through launch_pdl(): let the next launch be scheduled early, then wait until
 // the preceding grid has completed and its writes are visible (no-ops for ordinary launches)

@@ -477,11 +477,7 @@ __global__ void __launch_bounds__(256) k_hyb_adam(AgentCtx C, StepScalars S, int
     for (int c = 0; c < n_loss_parts; ++c) s += __ldcg(C.loss_part + c);
     const float loss = s / static_cast<float>(S.Bglobal);
     C.loss[0] = loss;
-    if (C.host_loss != nullptr) {
-      C.host_loss[0] = loss;
-      __threadfence_system();
-      C.host_loss[1] = __uint_as_float(S.epoch);
-    }
+    host_loss_store(C.host_loss, loss, S.epoch);
   }
 }
 

@@ -731,11 +731,7 @@ __device__ void stream_publish_loss(const AgentCtx& C, const StepScalars& S, int
     for (int c = 0; c < n_tiles; ++c) s += s_lp[c];
     const float loss = s / static_cast<float>(S.Bglobal);
     C.loss[0] = loss;
-    if (C.host_loss != nullptr) {
-      C.host_loss[0] = loss;
-      __threadfence_system();
-      C.host_loss[1] = __uint_as_float(S.epoch);
-    }
+    host_loss_store(C.host_loss, loss, S.epoch);
   }
   __syncthreads();
 }
@@ -811,11 +807,7 @@ __device__ __forceinline__ void publish_loss(const AgentCtx& C, const StepScalar
   }
   const float loss = s / static_cast<float>(S.Bglobal);
   C.loss[0] = loss;
-  if (C.host_loss != nullptr) {
-    C.host_loss[0] = loss;
-    __threadfence_system();
-    C.host_loss[1] = __uint_as_float(S.epoch);
-  }
+  host_loss_store(C.host_loss, loss, S.epoch);
 }
 // Two instantiations: kOneTile = true when every row CTA owns at most one 4-row tile (the default single-agent
 // batches: rows and Q_target stay in shared memory, role split), false for ensembles / large batches (several tiles per

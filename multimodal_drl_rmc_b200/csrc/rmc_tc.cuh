@@ -146,38 +146,45 @@ __device__ __forceinline__ void tc_ld_wait(uint32_t (&r)[32]) {
 // The epilogue is instruction-issue bound (profiles/r1/tc_fwd_stages.txt), so it runs on packed operations: one
 // add.f32x2 per two bias adds (sm_100 packed fp32), one cvt per two elements, and ReLU as one max.bf16x2 on the rounded
 // pair -- max(round(x), 0) == round(max(x, 0)) because rounding is monotonic and keeps the sign.
-__device__ __forceinline__ uint32_t tc_bias_relu_pack(uint32_t a0, uint32_t a1, float b0, float b1) {
+// act = 1: ELU(alpha = 1), the repo-HEAD activation (env/dqn_config.py:175): z > 0 ? z : exp(z) - 1 in fp32 (ex2-based
+// __expf: its 2-ulp error is far below the bf16 rounding that follows), then rounded to bf16 like the ReLU output.
+__device__ __forceinline__ uint32_t tc_bias_relu_pack(uint32_t a0, uint32_t a1, float b0, float b1, int act) {
   const float2 s = __fadd2_rn(make_float2(__uint_as_float(a0), __uint_as_float(a1)), make_float2(b0, b1));
+  if (act != 0) {
+    const float x = (s.x > 0.f) ? s.x : __expf(s.x) - 1.f, y = (s.y > 0.f) ? s.y : __expf(s.y) - 1.f;
+    const __nv_bfloat162 r = __floats2bfloat162_rn(x, y);
+    return *reinterpret_cast<const uint32_t*>(&r);
+  }
   const __nv_bfloat162 r = __hmax2(__floats2bfloat162_rn(s.x, s.y), __floats2bfloat162_rn(0.f, 0.f));
   return *reinterpret_cast<const uint32_t*>(&r);
 }
 __device__ __forceinline__ void tc_hidden_chunk(const uint32_t (&v)[32], int row, int col, const float* __restrict__ bias,
-                                                __nv_bfloat16* __restrict__ dst, int Kdst) {
+                                                __nv_bfloat16* __restrict__ dst, int Kdst, int act) {
 #pragma unroll
   for (int c = 0; c < 4; ++c) {              // 4 cores of 8 columns
     const float4 b0 = *reinterpret_cast<const float4*>(bias + col + 8 * c), b1 = *reinterpret_cast<const float4*>(bias + col + 8 * c + 4);
     uint4 q;
-    q.x = tc_bias_relu_pack(v[8 * c + 0], v[8 * c + 1], b0.x, b0.y);
-    q.y = tc_bias_relu_pack(v[8 * c + 2], v[8 * c + 3], b0.z, b0.w);
-    q.z = tc_bias_relu_pack(v[8 * c + 4], v[8 * c + 5], b1.x, b1.y);
-    q.w = tc_bias_relu_pack(v[8 * c + 6], v[8 * c + 7], b1.z, b1.w);
+    q.x = tc_bias_relu_pack(v[8 * c + 0], v[8 * c + 1], b0.x, b0.y, act);
+    q.y = tc_bias_relu_pack(v[8 * c + 2], v[8 * c + 3], b0.z, b0.w, act);
+    q.z = tc_bias_relu_pack(v[8 * c + 4], v[8 * c + 5], b1.x, b1.y, act);
+    q.w = tc_bias_relu_pack(v[8 * c + 6], v[8 * c + 7], b1.z, b1.w, act);
     *reinterpret_cast<uint4*>(dst + tc_off(row, col + 8 * c, Kdst)) = q;
   }
 }
 // chunks [c_first, c_first + n32) of 32 columns each; the tensor-memory load of the next chunk is in flight while the
 // current one is converted (n32 is even)
 __device__ __forceinline__ void tc_hidden_epilogue(uint32_t tmem_acc, int lane_base, int row, int c_first, int n32,
-                                                   const float* __restrict__ bias, __nv_bfloat16* __restrict__ dst, int Kdst) {
+                                                   const float* __restrict__ bias, __nv_bfloat16* __restrict__ dst, int Kdst, int act) {
   const uint32_t t0 = tmem_acc + (static_cast<uint32_t>(lane_base) << 16) + 32 * c_first;
   uint32_t va[32], vb[32];
   tc_ld32_issue(t0, va);
   for (int b = 0; b < n32; b += 2) {
     tc_ld_wait(va);
     tc_ld32_issue(t0 + 32 * (b + 1), vb);
-    tc_hidden_chunk(va, row, 32 * (c_first + b), bias, dst, Kdst);
+    tc_hidden_chunk(va, row, 32 * (c_first + b), bias, dst, Kdst, act);
     tc_ld_wait(vb);
     if (b + 2 < n32) tc_ld32_issue(t0 + 32 * (b + 2), va);
-    tc_hidden_chunk(vb, row, 32 * (c_first + b + 1), bias, dst, Kdst);
+    tc_hidden_chunk(vb, row, 32 * (c_first + b + 1), bias, dst, Kdst, act);
   }
 }
 constexpr int kTcFwdThreads = 512;   // two tile pipelines x 8 warps: each TMEM lane quadrant is drained by two warps (column halves)
@@ -203,6 +210,7 @@ struct TcFwdExtra {
   __nv_bfloat16* H1b;
   __nv_bfloat16* H2b;
   long long* dbg;          // diagnostics: clock64() of CTA 0 / pipeline 0 at the stage boundaries of its first tiles ([tile][8])
+  int act;                 // hidden activation: 0 = ReLU, 1 = ELU(alpha = 1)
 };
 __device__ __forceinline__ void tc_fwd_body(const unsigned char* __restrict__ packed, int D, int A, int NH, int dueling,
                                             const float* __restrict__ obs, long long n, long long* __restrict__ actions,
@@ -292,7 +300,7 @@ __device__ __forceinline__ void tc_fwd_body(const unsigned char* __restrict__ pa
     mbar_wait(gb + 0, phase);
     tc_fence_after();
     TC_FWD_STAMP();               // 1: layer-1 MMA complete
-    tc_hidden_epilogue(tD1, 32 * q, row, 4 * half, 4, sBias, sH, kH1);
+    tc_hidden_epilogue(tD1, 32 * q, row, 4 * half, 4, sBias, sH, kH1, X.act);
     TC_FWD_STAMP();               // 2: epilogue 1 done (this thread)
     fence_proxy_async();
     tc_fence_before();
@@ -317,7 +325,7 @@ __device__ __forceinline__ void tc_fwd_body(const unsigned char* __restrict__ pa
       if (gtid == 0) bulk_wait_read();
       tc_group_sync(g);
     }
-    tc_hidden_epilogue(tD2, 32 * q, row, 2 * half, 2, sBias + kH1, sH, kH2);     // H2 overwrites H1 (layer 2 has consumed it)
+    tc_hidden_epilogue(tD2, 32 * q, row, 2 * half, 2, sBias + kH1, sH, kH2, X.act);     // H2 overwrites H1 (layer 2 has consumed it)
     TC_FWD_STAMP();               // 4: epilogue 2 done
     fence_proxy_async();
     tc_fence_before();
@@ -399,6 +407,7 @@ struct TcFwdJob {
 struct TcFwdJobs { TcFwdJob j[3]; };
 __global__ void __launch_bounds__(kTcFwdThreads, 1) k_tc_fwd3(TcFwdJobs J, int D, int A, int NH, int dueling, const float* __restrict__ rows, long long n) {
   pdl_enter();
+  const SpanScope span_(SPAN_FWD3);
   const int b = blockIdx.x;
   const int k = (b >= J.j[2].cta_begin) ? 2 : (b >= J.j[1].cta_begin) ? 1 : 0;
   const TcFwdJob& job = J.j[k];

@@ -110,6 +110,7 @@ __device__ __forceinline__ int argmax_first16(const float (&q)[16], int A) {
 constexpr int kTdThreads = 128;
 __global__ void __launch_bounds__(kTdThreads) k_tc_td(AgentCtx C, StepScalars S, TcTrainBufs T) {
   pdl_enter();
+  const SpanScope span_(SPAN_TD);
   __shared__ float s_part[kTdThreads / 32];
   const long long i = blockIdx.x * static_cast<long long>(kTdThreads) + threadIdx.x;
   const NetLayout& L = C.L;
@@ -213,10 +214,11 @@ constexpr int kBfOffH1 = kBfOffDZ2 + kTcRows * kH2 * 2;
 constexpr int kBfOffBars = kBfOffH1 + kTcRows * kH1 * 2;
 constexpr int kTcBwdFusedSmemBytes = kBfOffBars + 8 * 8 + 16;       // 208,976 B
 
-// epilogue: scratch columns [col0, col0+64) of this warp's 32 rows -> ReLU mask from `act` (forward-layout tile with act_K
-// columns, column offset act_c0) -> bf16 -> uoff tile `dst`
+// epilogue: scratch columns [col0, col0+64) of this warp's 32 rows -> activation derivative from the saved OUTPUT `act`
+// (forward-layout tile with act_K columns, column offset act_c0; ReLU: [h > 0], ELU: h > 0 ? 1 : h + 1 = exp(z)) -> bf16 ->
+// uoff tile `dst`
 __device__ __forceinline__ void bf_mask_epilogue(uint32_t tS, int q, int row, int col0, const __nv_bfloat16* __restrict__ act, int act_c0,
-                                                 int act_K, __nv_bfloat16* __restrict__ dst) {
+                                                 int act_K, __nv_bfloat16* __restrict__ dst, int kind) {
 #pragma unroll
   for (int blk = 0; blk < 2; ++blk) {
     const int col = col0 + 32 * blk;
@@ -230,8 +232,15 @@ __device__ __forceinline__ void bf_mask_epilogue(uint32_t tS, int q, int row, in
 #pragma unroll
       for (int e = 0; e < 4; ++e) {     // bf16 > 0  <=>  sign clear and magnitude bits non-zero
         const uint32_t lo = hw[e] & 0xffffu, hi = hw[e] >> 16;
-        f[2 * e] = (lo != 0u && lo < 0x8000u) ? __uint_as_float(v[8 * c + 2 * e]) : 0.f;
-        f[2 * e + 1] = (hi != 0u && hi < 0x8000u) ? __uint_as_float(v[8 * c + 2 * e + 1]) : 0.f;
+        const bool pos_lo = (lo != 0u && lo < 0x8000u), pos_hi = (hi != 0u && hi < 0x8000u);
+        const float u_lo = __uint_as_float(v[8 * c + 2 * e]), u_hi = __uint_as_float(v[8 * c + 2 * e + 1]);
+        if (kind == 0) {
+          f[2 * e] = pos_lo ? u_lo : 0.f;
+          f[2 * e + 1] = pos_hi ? u_hi : 0.f;
+        } else {                        // ELU: the bf16 bits widened to fp32 are h itself
+          f[2 * e] = pos_lo ? u_lo : u_lo * (__uint_as_float(lo << 16) + 1.f);
+          f[2 * e + 1] = pos_hi ? u_hi : u_hi * (__uint_as_float(hi << 16) + 1.f);
+        }
       }
       uint4 pk;
       pk.x = pack_bf16x2(f[0], f[1]); pk.y = pack_bf16x2(f[2], f[3]); pk.z = pack_bf16x2(f[4], f[5]); pk.w = pack_bf16x2(f[6], f[7]);
@@ -242,6 +251,7 @@ __device__ __forceinline__ void bf_mask_epilogue(uint32_t tS, int q, int row, in
 
 __global__ void __launch_bounds__(kThreads, 1) k_tc_bwd_fused(AgentCtx C, const unsigned char* __restrict__ packed_bwd, long long n, TcTrainBufs T) {
   pdl_enter();
+  const SpanScope span_(SPAN_BWD);
   extern __shared__ __align__(128) unsigned char tsm[];
   const __nv_bfloat16* sW = reinterpret_cast<const __nv_bfloat16*>(tsm);          // Wh^T | W2 (K-major, packed by k_tc_pack_bwd)
   __nv_bfloat16* sDH = reinterpret_cast<__nv_bfloat16*>(tsm + kBfOffDH);
@@ -326,7 +336,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_bwd_fused(AgentCtx C, const 
     mbar_wait(bars + 1, phase);
     tc_fence_after();
     // ---- S2: DZ2 = dh2 (.) [H2 > 0]
-    bf_mask_epilogue(tS, q, row, 64 * half, sH2, 0, kH2, sDZ2);
+    bf_mask_epilogue(tS, q, row, 64 * half, sH2, 0, kH2, sDZ2, L.act);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -350,7 +360,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_bwd_fused(AgentCtx C, const 
     mbar_wait(bars + 2, phase);        // dz1a done; the commit also covers dWh -> the H2 buffer is free
     tc_fence_after();
     // ---- S4: DZ1[:, :128] = dz1a (.) [H1[:, :128] > 0]  -> H2 buffer (uoff layout)
-    bf_mask_epilogue(tS, q, row, 64 * half, sH1, 0, kH1, sH2);
+    bf_mask_epilogue(tS, q, row, 64 * half, sH1, 0, kH1, sH2, L.act);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -368,7 +378,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_bwd_fused(AgentCtx C, const 
     mbar_wait(bars + 3, phase);        // dz1b done; covers dW2 / db2 / dz1a / dW0a -> the DZ2 and H2 buffers are free
     tc_fence_after();
     // ---- S6: DZ1[:, 128:] -> DZ2 buffer
-    bf_mask_epilogue(tS, q, row, 64 * half, sH1, 128, kH1, sDZ2);
+    bf_mask_epilogue(tS, q, row, 64 * half, sH1, 128, kH1, sDZ2, L.act);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -438,15 +448,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_bwd_fused(AgentCtx C, const 
 // fixed-order reduction of the per-CTA partials -> gradient blob -> Adam (+ Polyak) -> refreshed bf16 images; also the loss.
 // A block owns 128 consecutive parameters: warp w sums partials w, w+8, ... with float4 loads (512 contiguous bytes per
 // warp load), the eight warp sums are combined in warp order through shared memory.
-__global__ void __launch_bounds__(256) k_tc_reduce_adam(AgentCtx C, StepScalars S, TcTrainBufs T, int n_loss_parts, TcPackOut P) {
+__global__ void __launch_bounds__(256) k_tc_reduce_adam(AgentCtx C, StepScalars S, TcTrainBufs T, int n_loss_parts, TcPackOut P, int dbg_skip) {
   pdl_enter();
+  const SpanScope span_(SPAN_REDUCE_ADAM);
   __shared__ float4 s_sum[8][32];
   const NetLayout& L = C.L;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int p4 = blockIdx.x * 32 + lane;                 // float4 index
   const int n4 = L.total >> 2;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (p4 < n4) {
+  if (p4 < n4 && !(dbg_skip & 1)) {
     // batches of 8 predicated loads, all in flight before the first add (a plain `#pragma unroll` leaves a remainder loop of
     // dependent load -> add iterations at full L2 latency each: 14 of this kernel's 21 us were spent there)
     const float4* src = reinterpret_cast<const float4*>(T.partials) + p4;
@@ -463,7 +474,7 @@ __global__ void __launch_bounds__(256) k_tc_reduce_adam(AgentCtx C, StepScalars 
   }
   s_sum[warp][lane] = acc;
   __syncthreads();
-  if (threadIdx.x < 128) {
+  if (threadIdx.x < 128 && !(dbg_skip & 2)) {
     const int l4 = threadIdx.x >> 2, e = threadIdx.x & 3;
     const int pi = (blockIdx.x * 32 + l4) * 4 + e;
     if (pi < L.total) {
@@ -478,7 +489,7 @@ __global__ void __launch_bounds__(256) k_tc_reduce_adam(AgentCtx C, StepScalars 
   // loss: the per-block partials of k_tc_td (up to 1024) summed by the LAST block in a fixed order: thread t adds partials
   // t, t+256, ... (loads in flight together), then the 256 thread sums are added in thread order.  (One thread walking the
   // list serially took 20 of this kernel's 23 us: 512 dependent L2 round trips.)
-  if (blockIdx.x == gridDim.x - 1) {
+  if (blockIdx.x == gridDim.x - 1 && !(dbg_skip & 4)) {
     __shared__ float s_loss[256];
     float v[4];
 #pragma unroll
@@ -491,11 +502,7 @@ __global__ void __launch_bounds__(256) k_tc_reduce_adam(AgentCtx C, StepScalars 
     for (int c = 0; c < 256; ++c) s += s_loss[c];
     const float loss = s / static_cast<float>(S.Bglobal);
     C.loss[0] = loss;
-    if (C.host_loss != nullptr) {
-      C.host_loss[0] = loss;
-      __threadfence_system();
-      C.host_loss[1] = __uint_as_float(S.epoch);
-    }
+    host_loss_store(C.host_loss, loss, S.epoch);
   }
   }
 }

@@ -29,7 +29,7 @@ def flat_sd(net):
     return np.concatenate([v.detach().cpu().numpy().ravel() for v in net.state_dict().values()])
 
 
-def make_pair(algo, D, B, cap, fill, seed, soft=True, target_freq=30000, tmpdir=None, activation="relu", body="macro"):
+def make_pair(algo, D, B, cap, fill, seed, soft=True, target_freq=30000, tmpdir=None, activation="relu", body="macro", gpu="0"):
     """(oracle learner, CUDA agent) with identical weights and identical replay contents."""
     from multimodal_drl_rmc_b200 import macro_config
     torch.set_num_threads(1)
@@ -39,7 +39,7 @@ def make_pair(algo, D, B, cap, fill, seed, soft=True, target_freq=30000, tmpdir=
     tmp = tmpdir or tempfile.mkdtemp(prefix="rmc_parity_")
     agent = macro_config.make_agent(algo, D, B, cap, save_dir=tmp + "/", log_dir=tmp + "/",
                                     target_soft_update=soft, target_update_freq=target_freq,
-                                    activation="hybrid" if body == "hybrid" else activation)
+                                    activation="hybrid" if body == "hybrid" else activation, gpu=gpu)
     agent.online_network.load_state_dict({k: v.clone() for k, v in orc.online.state_dict().items()})
     agent.target_network.load_state_dict({k: v.clone() for k, v in orc.target.state_dict().items()})
     obs, act, rew, done, nxt = synthetic_transitions(fill, D, 20251018 + seed)

@@ -211,9 +211,8 @@ def test_unsupported_configs_raise():
                 conf(nn.ReLU(), nn.ReLU(), width=512), conf(nn.ReLU(), nn.ReLU(), opt=optim.SGD)):
         with pytest.raises(NotImplementedError):
             Networks.DuelingDeepQNetwork(torch.device("cuda:0"), 1e-4, bad, ObsSpace(14), 8)
-    # ELU(alpha=1) bodies are built; the tensor-core modes are ReLU-only and must say so
+    # ELU(alpha=1) bodies are built, in the exact path and in the tensor-core modes
     net = Networks.DuelingDeepQNetwork(torch.device("cuda:0"), 1e-4, conf(nn.ELU(), nn.ELU()), ObsSpace(14), 8)
     obs = np.random.default_rng(0).random((64, 14), dtype=np.float32)
     assert len(net.actions(obs)) == 64
-    with pytest.raises(Exception):
-        net.actions(obs, precision="bf16")
+    assert len(net.actions(obs, precision="bf16")) == 64

@@ -242,7 +242,7 @@ out = {}
 for precision in ("fp32", "bf16"):
     res = {}
     for exchange in ("peer", "nccl"):
-        ag = PU.make_pair("PerDuelingDoubleDQNAgent", 14, B, cap, cap, seed=41)[1]      # identical replicas on every rank
+        ag = PU.make_pair("PerDuelingDoubleDQNAgent", 14, B, cap, cap, seed=41, gpu=str(rank))[1]      # identical replicas on every rank
         ag.learn_precision = precision
         sl = ShardedLearner(ag, exchange=exchange)
         rng = np.random.default_rng(3)
@@ -261,7 +261,7 @@ for precision in ("fp32", "bf16"):
                           peer_vs_nccl=float(np.max(np.abs(res["peer"][0] - res["nccl"][0]))),
                           trees_equal=bool(np.array_equal(res["peer"][1], res["nccl"][1])))
 # C3 row split: every rank evaluates its slice, actions all-gathered
-ag = PU.make_pair("DuelingDoubleDQNAgent", 14, 32, 200, 200, seed=2)[1]
+ag = PU.make_pair("DuelingDoubleDQNAgent", 14, 32, 200, 200, seed=2, gpu=str(rank))[1]
 obs = np.random.default_rng(0).random((10001, 14), dtype=np.float32)
 split = sharded_act(ag.online_network, obs)
 out["act_split_equal"] = split == ag.online_network.actions(obs)
@@ -282,7 +282,7 @@ def test_peer_exchange_over_real_ipc_two_processes(tmp_path):
     env = dict(os.environ, RMC_REPO=R.GOLDEN_DIR.rsplit("/tests/", 1)[0])
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port", "29631", str(script)]
     res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
-    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert res.returncode == 0, res.stdout[-3000:] + "\n".join(l for l in res.stderr.splitlines() if not l.startswith("DEVICE"))[-4000:]
     line = [l for l in res.stdout.splitlines() if l.startswith("IPC_RESULT ")][-1]
     out = json.loads(line[len("IPC_RESULT "):])
     print(out)
