@@ -307,7 +307,9 @@ int32_t rmc_learner_debug_read_sync(rmc_learner_t* l, uint64_t* out_host, int32_
 int32_t rmc_group_create(rmc_group_t** out, rmc_learner_t* const* learners, rmc_replay_t* const* replays,
                          int32_t n_agents);
 int32_t rmc_group_destroy(rmc_group_t* g);
-/* u_dev / idx_dev (if given) hold n_agents * batch entries, agent-major. */
+/* u_dev / idx_dev (if given) hold n_agents * batch entries, agent-major.  precision = RMC_PREC_BF16_TC: the members'
+ * tensor-core steps (rmc_learner_step in that mode) run side by side on internal streams, forked from / joined into `s`;
+ * meant for ensembles of large-batch members -- at B = 256 per member the fused fp32 launch is faster. */
 int32_t rmc_group_step(rmc_group_t* g, const rmc_step_args_t* a, rmc_stream_t s);
 
 /* ---------------------------------------------------------------- sharded large batch (C5) --- */

@@ -257,6 +257,10 @@ struct rmc_group {
   unsigned* qt_flags = nullptr;
   unsigned barrier_count = 0;
   unsigned epoch = 0;
+  // tensor-core mode: the members' steps run side by side on one stream per member (fork / join around them)
+  std::vector<cudaStream_t> tc_streams;
+  std::vector<cudaEvent_t> tc_join;
+  cudaEvent_t tc_fork = nullptr;
 };
 
 static int32_t step_resident_ctas(int device, int smem_bytes, int* out);
@@ -2181,6 +2185,9 @@ extern "C" int32_t rmc_group_destroy(rmc_group_t* g) {
   cudaFree(g->ctx_dev);
   cudaFree(g->barriers);
   cudaFree(g->qt_flags);
+  for (auto& st : g->tc_streams) if (st) cudaStreamDestroy(st);
+  for (auto& ev : g->tc_join) if (ev) cudaEventDestroy(ev);
+  if (g->tc_fork) cudaEventDestroy(g->tc_fork);
   delete g;
   return RMC_OK;
 }
@@ -2193,10 +2200,37 @@ extern "C" int32_t rmc_group_step(rmc_group_t* g, const rmc_step_args_t* a, rmc_
     if (std::memcmp(&g->learners[i]->hyper, &l0->hyper, sizeof(rmc_hyper_t)) != 0)
       return fail(RMC_ERR_ARG, "rmc_group_step: a member's hyper-parameters were changed after rmc_group_create");
   }
-  if (a->batch > kTreeCtaMax && l0->spec.prioritized && (a->phases & RMC_PH_PRIORITY))
-    return fail(RMC_ERR_UNSUPPORTED, "rmc_group_step: PER batches above 4096 are stepped per agent");
   if (int32_t e = use_device(l0->device)) return e;
   cudaStream_t st = as_stream(s);
+  if (a->precision == RMC_PREC_BF16_TC) {
+    // Tensor-core mode of the ensemble (north star: "tensor cores ... for the large-batch and agent-ensemble configs"): every
+    // member runs its own tcgen05 step (step_tc: per-member bf16 operand images, one graph launch per member once they are
+    // current) and the members run SIDE BY SIDE, one internal stream each, forked from and joined back into the caller's
+    // stream.  Dense GEMMs need >= one 128-row UMMA tile per CTA: this mode pays for ensembles of large-batch members
+    // (B >= ~2048 each); at B = 256 per member the fused fp32 launch above is the faster path and stays the default.
+    if (g->tc_streams.empty()) {
+      g->tc_streams.resize(g->n); g->tc_join.resize(g->n);
+      for (int i = 0; i < g->n; ++i) {
+        RMC_CUDA(cudaStreamCreateWithFlags(&g->tc_streams[i], cudaStreamNonBlocking));
+        RMC_CUDA(cudaEventCreateWithFlags(&g->tc_join[i], cudaEventDisableTiming));
+      }
+      RMC_CUDA(cudaEventCreateWithFlags(&g->tc_fork, cudaEventDisableTiming));
+    }
+    RMC_CUDA(cudaEventRecord(g->tc_fork, st));
+    for (int i = 0; i < g->n; ++i) {
+      rmc_step_args_t ai = *a;
+      if (a->u_dev) ai.u_dev = a->u_dev + static_cast<size_t>(i) * a->batch;
+      if (a->idx_dev) ai.idx_dev = a->idx_dev + static_cast<size_t>(i) * a->batch;
+      ai.seed = a->seed + 0x9E3779B97F4A7C15ull * static_cast<unsigned long long>(i);      // independent sampling streams per member
+      RMC_CUDA(cudaStreamWaitEvent(g->tc_streams[i], g->tc_fork, 0));
+      if (int32_t e = rmc_learner_step(g->learners[i], g->replays[i], &ai, reinterpret_cast<rmc_stream_t>(g->tc_streams[i]))) return e;
+      RMC_CUDA(cudaEventRecord(g->tc_join[i], g->tc_streams[i]));
+      RMC_CUDA(cudaStreamWaitEvent(st, g->tc_join[i], 0));
+    }
+    return RMC_OK;
+  }
+  if (a->batch > kTreeCtaMax && l0->spec.prioritized && (a->phases & RMC_PH_PRIORITY))
+    return fail(RMC_ERR_UNSUPPORTED, "rmc_group_step: PER batches above 4096 are stepped per agent");
   StepScalars S;
   if (int32_t e = fill_scalars(l0, a, &S)) return e;
   const int per_agent_max = std::max(1, l0->num_sms / g->n);

@@ -75,6 +75,7 @@ class AgentEnsemble:
         args.seed = a0.sampling_seed
         if a0._PER:
             args.per_beta = a0._beta(a0.step * a0.n_env)
+        args.precision = a0._args.precision      # "bf16": the members' tensor-core steps side by side (see rmc_group_step)
         args.u_dev = args.idx_dev = None
         keep = None
         if u is not None:

@@ -87,6 +87,34 @@ def test_ensemble_launch_matches_oracle_per_agent():
             np.testing.assert_array_equal(ag.replay_memory_buffer.replay_buffer.tree, orc.replay.tree.tree)
 
 
+def test_ensemble_tensor_core_mode_equals_member_steps():
+    """Tensor-core mode of the ensemble launch: every member's tcgen05 step, side by side on internal streams; with the same
+    injected uniforms each member ends bit-identical to the same agent stepped alone in tensor-core mode."""
+    from multimodal_drl_rmc_b200.parallel import AgentEnsemble
+    n, B, cap = 3, 1024, 4000
+    solo = [PU.make_pair("PerDuelingDoubleDQNAgent", 14, B, cap, cap, seed=70 + k)[1] for k in range(n)]
+    team = [PU.make_pair("PerDuelingDoubleDQNAgent", 14, B, cap, cap, seed=70 + k)[1] for k in range(n)]
+    for a in solo + team:
+        a.learn_precision = "bf16"
+    ens = AgentEnsemble(team)
+    rng = np.random.default_rng(9)
+    for step in range(3):
+        u = rng.random((n, B))
+        for k, a in enumerate(solo):
+            a.step = step
+            a.learn(u=u[k])
+            a.update_target_network()
+        for a in team:
+            a.step = step
+        ens.learn(u=u)
+    torch.cuda.synchronize()
+    for a, b in zip(solo, team):
+        np.testing.assert_array_equal(PU.flat_sd(a.online_network), PU.flat_sd(b.online_network))
+        np.testing.assert_array_equal(PU.flat_sd(a.target_network), PU.flat_sd(b.target_network))
+        np.testing.assert_array_equal(a.replay_memory_buffer.replay_buffer.tree, b.replay_memory_buffer.replay_buffer.tree)
+        assert a.last_loss() == b.last_loss()
+
+
 def test_ensemble_rejects_members_with_different_hyper_parameters():
     from multimodal_drl_rmc_b200 import macro_config
     from multimodal_drl_rmc_b200.parallel import AgentEnsemble
