@@ -424,11 +424,13 @@ def bench_config(wl):
             "agents_per_gpu": int(wl.get("ensemble", 1))}
 
 
-# Timed in the BUILD container (where /root/reference exists; it cannot travel to the GPU box), same workload as
-# cpu_baseline (PER + double + dueling, B = 256, 1M-transition replay, 16 threads): the oracle port that bench.py times on
-# the GPU box vs the unmodified reference classes driven through oracle/refharness.py.  See DESIGN.md section 5.
-PORT_VS_REFERENCE = {"port_ms_per_step": 50.0, "reference_ms_per_step": 44.0, "where": "build container, survey probe + round-1 run",
-                     "note": "the port is ~14 % slower than the reference itself on the same cores (same python tree loops, torch-eager nets)"}
+# Timed in the BUILD container (where /root/reference exists; it cannot travel to the GPU box) with
+# `python oracle/time_port_vs_reference.py 60 8`: same workload as cpu_baseline (PER + double + dueling, B = 256, 1M-transition
+# replay), same 8 cores -- the oracle port that bench.py times on the GPU box vs the unmodified reference classes.
+PORT_VS_REFERENCE = {"port_ms_per_step": 44.20, "reference_ms_per_step": 40.48, "port_over_reference": 1.092, "threads": 8,
+                     "where": "build container, round 2, oracle/time_port_vs_reference.py",
+                     "note": "the port is ~9 % slower than the reference itself on the same cores (same python tree loops, torch-eager nets): "
+                             "ratios against the port overstate the speed-up over the real reference by about that much"}
 
 
 def extra_sharded(args, rank, world, local):

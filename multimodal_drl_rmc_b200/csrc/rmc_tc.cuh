@@ -148,9 +148,10 @@ __device__ __forceinline__ void tc_ld_wait(uint32_t (&r)[32]) {
 // pair -- max(round(x), 0) == round(max(x, 0)) because rounding is monotonic and keeps the sign.
 // act = 1: ELU(alpha = 1), the repo-HEAD activation (env/dqn_config.py:175): z > 0 ? z : exp(z) - 1 in fp32 (ex2-based
 // __expf: its 2-ulp error is far below the bf16 rounding that follows), then rounded to bf16 like the ReLU output.
-__device__ __forceinline__ uint32_t tc_bias_relu_pack(uint32_t a0, uint32_t a1, float b0, float b1, int act) {
+template <int ACT>
+__device__ __forceinline__ uint32_t tc_bias_relu_pack(uint32_t a0, uint32_t a1, float b0, float b1) {
   const float2 s = __fadd2_rn(make_float2(__uint_as_float(a0), __uint_as_float(a1)), make_float2(b0, b1));
-  if (act != 0) {
+  if (ACT != 0) {
     const float x = (s.x > 0.f) ? s.x : __expf(s.x) - 1.f, y = (s.y > 0.f) ? s.y : __expf(s.y) - 1.f;
     const __nv_bfloat162 r = __floats2bfloat162_rn(x, y);
     return *reinterpret_cast<const uint32_t*>(&r);
@@ -158,34 +159,42 @@ __device__ __forceinline__ uint32_t tc_bias_relu_pack(uint32_t a0, uint32_t a1, 
   const __nv_bfloat162 r = __hmax2(__floats2bfloat162_rn(s.x, s.y), __floats2bfloat162_rn(0.f, 0.f));
   return *reinterpret_cast<const uint32_t*>(&r);
 }
+template <int ACT>
 __device__ __forceinline__ void tc_hidden_chunk(const uint32_t (&v)[32], int row, int col, const float* __restrict__ bias,
-                                                __nv_bfloat16* __restrict__ dst, int Kdst, int act) {
+                                                __nv_bfloat16* __restrict__ dst, int Kdst) {
 #pragma unroll
   for (int c = 0; c < 4; ++c) {              // 4 cores of 8 columns
     const float4 b0 = *reinterpret_cast<const float4*>(bias + col + 8 * c), b1 = *reinterpret_cast<const float4*>(bias + col + 8 * c + 4);
     uint4 q;
-    q.x = tc_bias_relu_pack(v[8 * c + 0], v[8 * c + 1], b0.x, b0.y, act);
-    q.y = tc_bias_relu_pack(v[8 * c + 2], v[8 * c + 3], b0.z, b0.w, act);
-    q.z = tc_bias_relu_pack(v[8 * c + 4], v[8 * c + 5], b1.x, b1.y, act);
-    q.w = tc_bias_relu_pack(v[8 * c + 6], v[8 * c + 7], b1.z, b1.w, act);
+    q.x = tc_bias_relu_pack<ACT>(v[8 * c + 0], v[8 * c + 1], b0.x, b0.y);
+    q.y = tc_bias_relu_pack<ACT>(v[8 * c + 2], v[8 * c + 3], b0.z, b0.w);
+    q.z = tc_bias_relu_pack<ACT>(v[8 * c + 4], v[8 * c + 5], b1.x, b1.y);
+    q.w = tc_bias_relu_pack<ACT>(v[8 * c + 6], v[8 * c + 7], b1.z, b1.w);
     *reinterpret_cast<uint4*>(dst + tc_off(row, col + 8 * c, Kdst)) = q;
   }
 }
 // chunks [c_first, c_first + n32) of 32 columns each; the tensor-memory load of the next chunk is in flight while the
 // current one is converted (n32 is even)
-__device__ __forceinline__ void tc_hidden_epilogue(uint32_t tmem_acc, int lane_base, int row, int c_first, int n32,
-                                                   const float* __restrict__ bias, __nv_bfloat16* __restrict__ dst, int Kdst, int act) {
+template <int ACT>
+__device__ __forceinline__ void tc_hidden_epilogue_t(uint32_t tmem_acc, int lane_base, int row, int c_first, int n32,
+                                                     const float* __restrict__ bias, __nv_bfloat16* __restrict__ dst, int Kdst) {
   const uint32_t t0 = tmem_acc + (static_cast<uint32_t>(lane_base) << 16) + 32 * c_first;
   uint32_t va[32], vb[32];
   tc_ld32_issue(t0, va);
   for (int b = 0; b < n32; b += 2) {
     tc_ld_wait(va);
     tc_ld32_issue(t0 + 32 * (b + 1), vb);
-    tc_hidden_chunk(va, row, 32 * (c_first + b), bias, dst, Kdst, act);
+    tc_hidden_chunk<ACT>(va, row, 32 * (c_first + b), bias, dst, Kdst);
     tc_ld_wait(vb);
     if (b + 2 < n32) tc_ld32_issue(t0 + 32 * (b + 2), va);
-    tc_hidden_chunk(vb, row, 32 * (c_first + b + 1), bias, dst, Kdst, act);
+    tc_hidden_chunk<ACT>(vb, row, 32 * (c_first + b + 1), bias, dst, Kdst);
   }
+}
+// the activation is a compile-time parameter of the (instruction-issue bound) epilogue loop: one uniform branch per call
+__device__ __forceinline__ void tc_hidden_epilogue(uint32_t tmem_acc, int lane_base, int row, int c_first, int n32,
+                                                   const float* __restrict__ bias, __nv_bfloat16* __restrict__ dst, int Kdst, int act) {
+  if (act != 0) tc_hidden_epilogue_t<1>(tmem_acc, lane_base, row, c_first, n32, bias, dst, Kdst);
+  else tc_hidden_epilogue_t<0>(tmem_acc, lane_base, row, c_first, n32, bias, dst, Kdst);
 }
 constexpr int kTcFwdThreads = 512;   // two tile pipelines x 8 warps: each TMEM lane quadrant is drained by two warps (column halves)
 __device__ __forceinline__ void tc_group_sync(int g) {   // the 256 threads of one tile pipeline

@@ -217,8 +217,9 @@ constexpr int kTcBwdFusedSmemBytes = kBfOffBars + 8 * 8 + 16;       // 208,976 B
 // epilogue: scratch columns [col0, col0+64) of this warp's 32 rows -> activation derivative from the saved OUTPUT `act`
 // (forward-layout tile with act_K columns, column offset act_c0; ReLU: [h > 0], ELU: h > 0 ? 1 : h + 1 = exp(z)) -> bf16 ->
 // uoff tile `dst`
-__device__ __forceinline__ void bf_mask_epilogue(uint32_t tS, int q, int row, int col0, const __nv_bfloat16* __restrict__ act, int act_c0,
-                                                 int act_K, __nv_bfloat16* __restrict__ dst, int kind) {
+template <int kind>
+__device__ __forceinline__ void bf_mask_epilogue_t(uint32_t tS, int q, int row, int col0, const __nv_bfloat16* __restrict__ act, int act_c0,
+                                                   int act_K, __nv_bfloat16* __restrict__ dst) {
 #pragma unroll
   for (int blk = 0; blk < 2; ++blk) {
     const int col = col0 + 32 * blk;
@@ -247,6 +248,12 @@ __device__ __forceinline__ void bf_mask_epilogue(uint32_t tS, int q, int row, in
       *reinterpret_cast<uint4*>(dst + uoff(row, col + 8 * c)) = pk;
     }
   }
+}
+
+__device__ __forceinline__ void bf_mask_epilogue(uint32_t tS, int q, int row, int col0, const __nv_bfloat16* __restrict__ act, int act_c0,
+                                                 int act_K, __nv_bfloat16* __restrict__ dst, int kind) {
+  if (kind != 0) bf_mask_epilogue_t<1>(tS, q, row, col0, act, act_c0, act_K, dst);
+  else bf_mask_epilogue_t<0>(tS, q, row, col0, act, act_c0, act_K, dst);
 }
 
 __global__ void __launch_bounds__(kThreads, 1) k_tc_bwd_fused(AgentCtx C, const unsigned char* __restrict__ packed_bwd, long long n, TcTrainBufs T) {
