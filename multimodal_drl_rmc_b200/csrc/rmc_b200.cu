@@ -731,8 +731,9 @@ static int32_t learner_build_mlp(rmc_learner* l, const rmc_net_spec_t* spec, con
   RMC_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
   l->max_smem_optin = max_optin;
   if (l->smem_bytes > max_optin) return fail(RMC_ERR_UNSUPPORTED, "rmc_learner_create: parameter blob does not fit shared memory");
-  RMC_CUDA(cudaFuncSetAttribute(k_learner_step<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, l->smem_bytes));
-  RMC_CUDA(cudaFuncSetAttribute(k_learner_step<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, l->smem_bytes));
+  RMC_CUDA(cudaFuncSetAttribute(k_learner_step<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, l->smem_bytes));
+  RMC_CUDA(cudaFuncSetAttribute(k_learner_step<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, l->smem_bytes));
+  RMC_CUDA(cudaFuncSetAttribute(k_learner_step<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, l->smem_bytes));
   RMC_CUDA(cudaFuncSetAttribute(k_mlp_infer, cudaFuncAttributeMaxDynamicSharedMemorySize, l->smem_bytes));
   {
     int resident = 0;
@@ -769,6 +770,10 @@ static int32_t learner_build_mlp(rmc_learner* l, const rmc_net_spec_t* spec, con
   if ((e = owned_alloc(l, &c.loss, 1))) return e;
   if ((e = owned_alloc(l, &c.barrier, 1))) return e;
   if ((e = owned_alloc(l, &c.qt_flag, kFlagWords))) return e;
+  {   // per-CTA partial gradient blobs of the batch-stationary row phase (rmc_rows_ws.cuh): one per row CTA, tiles of >= 8 rows
+    const size_t parts = std::max<size_t>(1, std::min<size_t>(static_cast<size_t>(l->num_sms), (B + 7) / 8));
+    if ((e = owned_alloc(l, &c.gpart, parts * static_cast<size_t>(l->L.total)))) return e;
+  }
   {   // streamed phase B of the fused step: {epoch, value} word arrays (rmc_mlp.cuh, StreamPlan)
     const size_t rows = std::min<size_t>(B, static_cast<size_t>(kStreamTilesMax) * kTM);
     if ((e = owned_alloc(l, &c.x_words, 2 * rows * kMaxD))) return e;
@@ -960,9 +965,9 @@ struct StepStreamGuard {            // per device: the stream the last fused-ste
 };
 static StepStreamGuard g_step_guard[kMaxDevices];
 
-static int32_t launch_step(int device, dim3 grid, void** args, size_t smem, cudaStream_t st, bool one_tile) {
+static int32_t launch_step(int device, dim3 grid, void** args, size_t smem, cudaStream_t st, int path) {
   const int mode = launch_mode();
-  void* fn = one_tile ? reinterpret_cast<void*>(k_learner_step<true>) : reinterpret_cast<void*>(k_learner_step<false>);
+  void* fn = path == 1 ? reinterpret_cast<void*>(k_learner_step<1>) : path == 2 ? reinterpret_cast<void*>(k_learner_step<2>) : reinterpret_cast<void*>(k_learner_step<0>);
   if (mode == 0) {
     RMC_CUDA(cudaLaunchCooperativeKernel(fn, grid, dim3(kThreads, 1, 1), args, smem, st));
   } else {
@@ -993,11 +998,12 @@ static int32_t launch_step(int device, dim3 grid, void** args, size_t smem, cuda
 }
 // co-residency by construction: how many CTAs of the fused step fit the device at once
 static int32_t step_resident_ctas(int device, int smem_bytes, int* out) {
-  int per_sm_a = 0, per_sm_b = 0, sms = 0;
+  int per_sm_a = 0, per_sm_b = 0, per_sm_c = 0, sms = 0;
   RMC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
-  RMC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_a, k_learner_step<true>, kThreads, static_cast<size_t>(smem_bytes)));
-  RMC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_b, k_learner_step<false>, kThreads, static_cast<size_t>(smem_bytes)));
-  *out = std::min(per_sm_a, per_sm_b) * sms;
+  RMC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_a, k_learner_step<1>, kThreads, static_cast<size_t>(smem_bytes)));
+  RMC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_b, k_learner_step<0>, kThreads, static_cast<size_t>(smem_bytes)));
+  RMC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_c, k_learner_step<2>, kThreads, static_cast<size_t>(smem_bytes)));
+  *out = std::min(per_sm_a, std::min(per_sm_b, per_sm_c)) * sms;
   return RMC_OK;
 }
 
@@ -1005,6 +1011,13 @@ static int32_t step_resident_ctas(int device, int smem_bytes, int* out) {
 // (rows already in X from an earlier launch) takes the general instantiation, which reads X.
 static bool one_tile_ok(const StepScalars& S, long long n_tiles) {
   return n_tiles <= S.n_row_ctas && ((S.phases & (RMC_PH_SAMPLE | RMC_PH_FORWARD)) != RMC_PH_FORWARD);
+}
+// Which instantiation of k_learner_step runs a launch: 1 = one 4-row tile per row CTA (the default batches), 2 = the
+// batch-stationary phases of rmc_rows_ws.cuh once a row CTA owns at least two 16-row tiles, 0 = several 4-row tiles per CTA.
+static int step_path(const StepScalars& S, long long n_tiles, const AgentCtx& c) {
+  if (one_tile_ok(S, n_tiles)) return 1;
+  if ((S.phases & RMC_PH_FORWARD) && c.gpart != nullptr && (S.B + kWR - 1) / kWR >= 2ll * S.n_row_ctas) return 2;
+  return 0;
 }
 
 static int grid_for(const rmc_learner* l, long long B, int max_ctas) {
@@ -1686,7 +1699,7 @@ extern "C" int32_t rmc_learner_step(rmc_learner_t* l, rmc_replay_t* r, const rmc
   l->last_grid = G;
   const AgentCtx* many = nullptr;
   void* args[] = {&single, &many, &S};
-  if (int32_t e = launch_step(l->device, dim3(G, 1, 1), args, static_cast<size_t>(l->smem_bytes), st, one_tile_ok(S, n_tiles))) return e;
+  if (int32_t e = launch_step(l->device, dim3(G, 1, 1), args, static_cast<size_t>(l->smem_bytes), st, step_path(S, n_tiles, l->ctx))) return e;
   if (rows && phase_b) l->barrier_count = S.barrier_target;
   if ((a->phases & RMC_PH_FORWARD) && phase_b) l->loss_epoch = S.epoch;
   if (a->phases & RMC_PH_ADAM) ++l->online_version;
@@ -2251,7 +2264,7 @@ extern "C" int32_t rmc_group_step(rmc_group_t* g, const rmc_step_args_t* a, rmc_
   AgentCtx single = l0->ctx;
   const AgentCtx* many = g->ctx_dev;
   void* args[] = {&single, &many, &S};
-  if (int32_t e = launch_step(l0->device, dim3(G, g->n, 1), args, static_cast<size_t>(l0->smem_bytes), st, one_tile_ok(S, n_tiles))) return e;
+  if (int32_t e = launch_step(l0->device, dim3(G, g->n, 1), args, static_cast<size_t>(l0->smem_bytes), st, step_path(S, n_tiles, l0->ctx))) return e;
   if (rows && phase_b) g->barrier_count = S.barrier_target;
   return RMC_OK;
 }

@@ -283,6 +283,7 @@ struct AgentCtx {
   float *X;             // [B][row_floats] gathered rows
   float *H1, *H2, *DZ1, *DZ2, *DH;   // saved activations / deltas of the s rows
   float* loss_part;     // [n_tiles]
+  float* gpart;         // [gpart_cap][L.total] per-CTA partial gradient blobs of the batch-stationary row phase (rmc_rows_ws.cuh); zero at padding
   float* loss;          // [1]
   unsigned* barrier;
   unsigned* qt_flag;    // [kFlagWords] {epoch, payload} hand-off words of the fused step: Q_target(s') per (tile, row, action),

@@ -472,6 +472,9 @@ __device__ void wgrad_run_unit(const AgentCtx& C, const StepScalars& S, int u, b
   }
 }
 
+
+#include "rmc_rows_ws.cuh"
+
 // ------------------------------------------------------------------ streamed phase B units (see StreamPlan below)
 __device__ __forceinline__ uint4 ld_relaxed_quad(const unsigned* p) {
   uint4 v;
@@ -812,8 +815,10 @@ __device__ __forceinline__ void publish_loss(const AgentCtx& C, const StepScalar
 // Two instantiations: kOneTile = true when every row CTA owns at most one 4-row tile (the default single-agent
 // batches: rows and Q_target stay in shared memory, role split), false for ensembles / large batches (several tiles per
 // CTA).  Splitting them keeps each kernel's straight-line code small: the step is sensitive to instruction-fetch stalls.
-template <bool kOneTile>
-__global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, const AgentCtx* __restrict__ many, StepScalars S) {
+template <int kPath>
+__global__ void __launch_bounds__(kThreads, 1) k_learner_step(const __grid_constant__ AgentCtx single, const AgentCtx* __restrict__ many,
+                                                              const __grid_constant__ StepScalars S) {
+  constexpr bool kOneTile = kPath == 1;
   extern __shared__ __align__(16) float smem[];
   // private copy of the context: field reads become register / local-memory accesses that the compiler can hoist
   // (through a reference into parameter-or-global memory every C.x is a generic load that no store may cross)
@@ -874,6 +879,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, c
   const bool early_td = one_tile && pb.early;
   const StreamPlan sp = stream_plan(C, S, pb, G, n_tiles, one_tile, split);
   const bool stream_b = kOneTile && sp.on;
+  // Several row tiles per CTA: the batch-stationary phases of rmc_rows_ws.cuh (kPath 2) once a row CTA owns at least two 16-row
+  // tiles (large batches; chosen by the host, step_path in rmc_b200.cu); below that (the 8-agent ensemble launch: 16 rows
+  // per CTA) 4-row tiles through the latency-shaped passes are faster -- every phase would run once, on cold code, and the
+  // partial-gradient exchange would cost more than the gradient units (measured: 83-87 us against 73 us for 8 x 256).
+  constexpr bool use_ws = kPath == 2;
   if (is_row || is_tgt) {
     const long long n_nodes = 2 * C.rp.cap - 1;
     const int n_top = static_cast<int>(min(static_cast<long long>(kTopNodes), n_nodes));
@@ -923,9 +933,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, c
       if (tree_sampling && tid == 0)
         sTop[kTopNodes] = is_weight_max(static_cast<double>(size), total, static_cast<double>(min_p_f), S.beta);
       __syncthreads();
-      const long long my_tiles = (n_tiles - tile0 + S.n_row_ctas - 1) / S.n_row_ctas;
-      for (long long s = warp; s < my_tiles * kTM; s += kWarps) {
-        const long long i = (tile0 + (s / kTM) * S.n_row_ctas) * kTM + (s % kTM);
+      // this CTA samples the rows it will process: 16- / 8-row tiles (rmc_rows_ws.cuh) or 4-row tiles
+      const int wrs = use_ws ? ws_rows(B, S.n_row_ctas) : kTM;
+      const long long n_wide = (B + wrs - 1) / wrs;
+      const long long my_wide = (cta < n_wide) ? (n_wide - cta + S.n_row_ctas - 1) / S.n_row_ctas : 0;
+      for (long long s = warp; s < my_wide * wrs; s += kWarps) {
+        const long long i = (cta + (s / wrs) * S.n_row_ctas) * wrs + (s % wrs);
         if (i >= B) continue;
         long long slot = 0, node = 0;
         double p = 0.0, numer = 1.0;
@@ -1007,7 +1020,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, c
     if (do_fwd) {
       wait_params(bar, parity);
       RMC_STAMP(C, 2);
-      if (!one_tile) {
+      if (!one_tile && !use_ws) {
         // several tiles per CTA: Q_target(s') of TWO tiles per pass (8 rows share one sweep over the target weights)
         for (long long ta = tile0; ta < n_tiles; ta += 2 * S.n_row_ctas) {
           const long long tb = ta + S.n_row_ctas;
@@ -1027,6 +1040,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, c
           }
           __syncthreads();
         }
+      } else if (!one_tile) {
+        // batch-stationary passes (rmc_rows_ws.cuh): both forward phases run below, from one copy of the code
       } else if (!split || is_tgt)
       for (long long tile = tile0; tile < n_tiles; tile += S.n_row_ctas) {
         // x^T of the s' rows -> sXT[d][0..3]
@@ -1053,13 +1068,41 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, c
       }
       // -------- pass 2: online weights; [s'; s] rows
       RMC_STAMP(C, 3);
-      if (!split) {
+      if (!use_ws && !split) {
         stage_params(sW, C.online, L.total, bar, parity);
         wait_params(bar, parity);
       }
       RMC_STAMP(C, 4);
       float loss_local = 0.f;   // thread 0 accumulates this CTA's tiles in order
-      if (!is_tgt)
+      if (use_ws) {
+        // online pass, dgrad and the weight gradients of this CTA's rows; one partial gradient blob per CTA (summed after
+        // the agent barrier by ws_reduce_apply)
+        const WsTiles Tw = ws_tiles(S, cta);
+        const bool has_rows = Tw.first < Tw.n_wide;
+        const bool grads = (S.phases & 8) && C.gpart != nullptr;
+        float* gp = (grads && has_rows) ? C.gpart + static_cast<size_t>(cta) * L.total : nullptr;
+        const WsSmem Wd = ws_smem(smem + P.xt);
+#pragma unroll 1
+        for (int ph = 0; ph < 2; ++ph) {     // target pass, then online pass: ONE copy of the forward code
+          if (ph == 1) {
+            stage_params(sW, C.online, L.total, bar, parity);
+            wait_params(bar, parity);
+            RMC_STAMP(C, 4);
+          }
+          if (has_rows) {
+            const float lp = ws_rows_phase(C, S, sW, Wd, Tw, per, gp, ph == 0);
+            if (ph == 1) loss_local = lp;
+          }
+          if (ph == 0) RMC_STAMP(C, 3);
+        }
+        RMC_STAMP(C, 13);
+        if (has_rows) {
+          if (L.D <= 16) ws_dgrad_phase<16>(C, S, sW, sW, Wd, Tw, gp);
+          else ws_dgrad_phase<kMaxD>(C, S, sW, sW, Wd, Tw, gp);
+          RMC_STAMP(C, 14);
+          if (gp != nullptr) ws_wgrad_phase(C, S, sW, Wd, Tw, gp);
+        }
+      } else if (!is_tgt)
       for (long long tile = cta; tile < n_tiles; tile += S.n_row_ctas) {
         for (int t = tid; t < kR * D; t += kThreads) {
           const int r = t / D, d = t % D;
@@ -1348,7 +1391,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(AgentCtx single, c
     const int np = static_cast<int>(min(static_cast<long long>(S.n_row_ctas), n_tiles));
     publish_loss(C, S, C.loss_part, np);
   }
-  if (S.phases & 8) {                             // BACKWARD (+ fused Adam/Polyak)
+  if ((S.phases & 8) && use_ws) {
+    // BACKWARD of a launch whose row CTAs left per-CTA partial gradient blobs (rmc_rows_ws.cuh): sum them, Adam / Polyak
+    const int wrs = ws_rows(B, S.n_row_ctas);
+    const int n_parts = static_cast<int>(min(static_cast<long long>(S.n_row_ctas), (B + wrs - 1) / wrs));
+    ws_reduce_apply(C, S, C.gpart, n_parts, wid, n_workers);
+  } else if (S.phases & 8) {                      // BACKWARD (+ fused Adam/Polyak)
     const int n_units = wgrad_unit_count(L, coarse);
     for (int u = wid; u < n_units; u += n_workers) wgrad_run_unit(C, S, u, coarse, smem);
   } else if (S.phases & (16 | 32 | 64)) {         // element-wise Adam from given grads / target sync only

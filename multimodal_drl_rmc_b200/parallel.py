@@ -166,11 +166,19 @@ class ShardedLearner:
         arr = (C.c_void_p * len(ptrs))(*ptrs)
         for m in members:
             check(lib().rmc_comm_connect(m._comm, None, arr))
+            # Emulated ranks share ONE device: a waiting exchange kernel of one rank and the fused step of another (a whole
+            # SM per CTA) cannot be co-resident, so the second half of a split step (stages=2) is ordered after every
+            # member's first half by events.  Real ranks own a GPU each and need no such edge.
+            m._same_process = list(members)
 
     def _learn_peer(self, u, fuse_target_update, stages=3):
         ag = self.agent
         ag._flush_step()
         if stages == 2:       # second half of a split step (emulated ranks): same arguments as the first half
+            for m in getattr(self, "_same_process", ()):
+                ev = getattr(m, "_stage1_event", None)
+                if ev is not None:
+                    T.cuda.current_stream(ag.device).wait_event(ev)
             check(lib().rmc_learner_step_sharded(ag._lh.handle, ag.replay_memory_buffer._ring.require(), self._comm,
                                                  C.byref(self._args), 2, stream_ptr(ag.device.index)))
             return ag._lh.output("loss")
@@ -190,6 +198,9 @@ class ShardedLearner:
                 a.u_dev = keep.data_ptr()
         rh = ag.replay_memory_buffer._ring.require()
         check(lib().rmc_learner_step_sharded(ag._lh.handle, rh, self._comm, C.byref(a), stages, stream_ptr(ag.device.index)))
+        if stages == 1 and getattr(self, "_same_process", None):
+            self._stage1_event = T.cuda.Event()
+            self._stage1_event.record(T.cuda.current_stream(ag.device))
         ag._lh.version[_lib.ONLINE] += 1
         if fuse_target_update:
             ag._lh.version[_lib.TARGET] += 1

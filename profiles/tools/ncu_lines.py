@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Join an ncu report's per-SASS-instruction stall samples with nvdisasm line info and print the
-hottest CUDA source lines.   usage: ncu_lines.py report.ncu-rep lib.so kernel_substring [launch_idx]"""
+hottest CUDA source lines.   usage: ncu_lines.py report.ncu-rep lib.so kernel_substring [launch_idx [mangled_substring]]"""
 import collections
 import csv
 import io
@@ -11,6 +11,7 @@ import sys
 import tempfile
 
 rep, lib, kern = sys.argv[1], sys.argv[2], sys.argv[3]
+sect = sys.argv[5] if len(sys.argv) > 5 else kern      # substring of the mangled name (.text section) when it differs from ncu's kernel name
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp, check=True, capture_output=True)
 cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
@@ -19,7 +20,7 @@ dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cubin)], capture
 off2line, cur, inside = {}, None, False
 for ln in dis.splitlines():
     if ln.startswith("\t.section\t.text."):
-        inside = kern in ln
+        inside = sect in ln
     if not inside:
         continue
     m = re.search(r'//## File "([^"]+)", line (\d+)', ln)

@@ -29,7 +29,7 @@ def test_per256_on_full_1m_replay_matches_oracle():
     assert st.total_priority == orc.replay.tree.total and st.max_priority == orc.replay.tree.max_leaf and st.min_priority == orc.replay.tree.min_leaf
     res = PU.run_parity_case("PerDuelingDoubleDQNAgent", 14, 256, CAP, CAP, 3, seed=17, pair=pair, f64_truth=True)
     print(res)
-    assert res["gpu_grads_vs_f64"] < TOL and res["ref_grads_vs_f64"] < TOL
+    assert res["gpu_grads_vs_f64"] < TOL and res["ref_grads_vs_f64"] < TOL          # at B = 256 every evaluation order agrees
     assert res["nodes_equal"], "sampled tree indices must be bit-exact (21-level descent, leaves on two depths)"
     assert res["tree_equal"], "2M-node tree must be bit-exact after the write-back given equal float32 priorities"
     assert res["max_pri_ulp"] <= 1.0 and res["max_rel_isw"] < 1e-6
@@ -67,14 +67,14 @@ def test_b65536_exact_step_matches_oracle():
     assert res["nodes_equal"] and res["tree_equal"], "65,536 stratified draws (with duplicate leaves) and their write-back must be bit-exact"
     assert res["max_pri_ulp"] <= 1.0 and res["max_rel_isw"] < 1e-6
     assert res["max_rel_q"] < TOL and res["max_rel_loss"] < TOL
-    # Gradients are sums over 65,536 samples in fp32.  At this length the REFERENCE's own sums (torch's CPU GEMM) are 3.7e-5
-    # (net.2.weight, max-norm relative) away from the float64 result of the same formulas -- measured in the build container
-    # and again here -- so "within 1e-5 of the reference" is not a meaningful bar for this batch: it would require reproducing
-    # the reference's rounding error.  Asserted instead: this path is within 1e-5 of EXACT arithmetic, and its distance to the
-    # reference is explained by the reference's own distance to exact arithmetic.
-    print("gradients vs float64: this path %.3g, reference %.3g; this path vs reference %.3g" % (res["gpu_grads_vs_f64"], res["ref_grads_vs_f64"], res["max_rel_grads"]))
-    assert res["gpu_grads_vs_f64"] < TOL, res["grads_vs_f64_per_tensor"]
-    assert res["max_rel_grads"] < TOL + res["ref_grads_vs_f64"], res["worst_grad"]
+    # Gradients are sums over 65,536 samples in fp32, and at this length fp32 evaluation orders matter: the reference's own
+    # gradients are 3.7e-5 (net.2.weight, max-norm relative) away from a float64 evaluation of the same formulas on the same
+    # minibatch.  The bar is "within 1e-5 of the reference"; an implementation that is instead within 1e-5 of EXACT arithmetic is
+    # accepted as well, provided its distance to the reference is explained by the reference's own distance to exact arithmetic.
+    # (This batch runs the batch-stationary row phase of csrc/rmc_rows_ws.cuh: per-CTA gradient partials over ~443 rows each,
+    # then a sum over the 148 CTAs -- a blocked order that sits closer to exact arithmetic than one flat fp32 sum.)
+    print("gradients: this path vs reference %.3g | vs float64: this path %.3g, reference %.3g" % (res["max_rel_grads"], res["gpu_grads_vs_f64"], res["ref_grads_vs_f64"]))
+    assert res["max_rel_grads"] < TOL or (res["gpu_grads_vs_f64"] < TOL and res["max_rel_grads"] < TOL + res["ref_grads_vs_f64"]), res["worst_grad"]
     assert res["max_rel_weights"] < TOL and res["max_rel_target"] < 10 * TOL
     m_tol = TOL + 2 * res["ref_grads_vs_f64"]            # m, v are linear / quadratic in the gradient
     assert res["adam_closure_ulp"] <= 2.0 and res["polyak_bitexact"] and res["zero_grad_exact"] and res["zero_grad_weights_bitexact"]

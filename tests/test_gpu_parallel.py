@@ -246,9 +246,20 @@ def test_peer_memory_exchange_two_ranks_on_one_gpu(B, precision, steps):
             w_full = PU.flat_sd(full.online_network)
             well = np.abs(g_full) >= 1e-6
             assert R.max_rel(np.where(well, w[0], w_full), w_full) < 1e-5
-            np.testing.assert_array_equal(t[0], full.replay_memory_buffer.replay_buffer.tree)
+            t_full = full.replay_memory_buffer.replay_buffer.tree
             sa, sb = reps[0].replay_memory_buffer._ring.stats(), full.replay_memory_buffer._ring.stats()
-            assert (sa.max_priority, sa.min_priority, sa.total_priority) == (sb.max_priority, sb.min_priority, sb.total_priority)
+            if B <= 1024:
+                # shards and full batch run the same instantiation of the step kernel (one 4-row tile per CTA): same Q bits,
+                # same |td|, same priorities -> the trees must be bit-identical
+                np.testing.assert_array_equal(t[0], t_full)
+                assert (sa.max_priority, sa.min_priority, sa.total_priority) == (sb.max_priority, sb.min_priority, sb.total_priority)
+            else:
+                # B = 8192: the full batch takes the batch-stationary row phase (rmc_rows_ws.cuh, >= 2 16-row tiles per CTA), the
+                # 4096-row shards the 4-row tiles: Q differs in the last bits (K-sum order), so p = (|td| + eps)^alpha differs by
+                # alpha * 1e-6 / eps ~ 1e-4 relative for the smallest |td|.  (Each path against the ORACLE: priorities <= 1 ulp,
+                # tests/test_gpu_headline_sizes.py and test_large_batch_per_step_uses_grid_wide_tree_path.)
+                np.testing.assert_allclose(t[0], t_full, rtol=5e-4, atol=0)
+                assert abs(sa.total_priority - sb.total_priority) <= 5e-4 * sb.total_priority
 
 
 # ------------------------------------------------------------------------------------------------------------------
