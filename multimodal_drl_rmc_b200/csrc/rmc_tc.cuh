@@ -28,9 +28,16 @@ constexpr int kTcNH = 16;            // heads padded to the minimum N for M = 12
 constexpr int kTcOffW0 = 0;                            // [256 rows][K = 16]
 constexpr int kTcOffW2 = kTcOffW0 + kH1 * kTcK1;       // [128 rows][K = 256]
 constexpr int kTcOffWh = kTcOffW2 + kH2 * kH1;         // [ 16 rows][K = 128]
-constexpr int kTcBf16Elems = kTcOffWh + kTcNH * kH2;   // 38,912 bf16 = 77,824 B
-constexpr int kTcBiasFloats = kH1 + kH2 + kTcNH;       // 400 floats
-constexpr int kTcBlobBytes = kTcBf16Elems * 2 + kTcBiasFloats * 4;   // 79,424 B (multiple of 16)
+// Biases ride on the tensor core (the hidden epilogues are instruction-issue bound; a bias add per element plus the bias
+// loads were a third of their instructions): b0 sits in column 15 of the W0 image and the X tile carries 1.0 there
+// (obs_dim <= 15), b2 is one more K step of layer 2 -- A = a constant [128][16] tile with 1.0 in column 0, B = [128][16]
+// with b2 in column 0.  The biases enter as bf16 like every other operand of this mode (stated bound unchanged).
+constexpr int kTcOffB2T = kTcOffWh + kTcNH * kH2;      // [128 rows = j][K = 16]: (j, 0) = b2[j]
+constexpr int kTcOffOnes = kTcOffB2T + kH2 * kTcK1;    // [128 rows][K = 16]:     (r, 0) = 1
+constexpr int kTcBf16Elems = kTcOffOnes + kTcRows * kTcK1;   // 43,008 bf16 = 86,016 B
+constexpr int kTcBiasFloats = kH1 + kH2 + kTcNH;       // 400 floats (heads; hidden layers when obs_dim = 16 / fallback)
+constexpr int kTcBlobBytes = kTcBf16Elems * 2 + kTcBiasFloats * 4;   // 87,616 B (multiple of 16)
+__host__ __device__ __forceinline__ bool tc_bias_folded_l1(int D) { return D <= kTcK1 - 1; }
 
 // element offset of (row r, k) inside a canonical K-major no-swizzle operand with K columns
 __host__ __device__ __forceinline__ int tc_off(int r, int k, int K) {
@@ -45,7 +52,13 @@ __global__ void k_tc_pack(const float* __restrict__ blob, NetLayout L, unsigned 
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t < kH1 * kTcK1) {                                  // W0[i][d]
     const int i = t / kTcK1, d = t % kTcK1;
-    w[kTcOffW0 + tc_off(i, d, kTcK1)] = __float2bfloat16_rn(d < L.D ? blob[L.off_w0t + d * kH1 + i] : 0.f);
+    const float v = d < L.D ? blob[L.off_w0t + d * kH1 + i] : ((d == kTcK1 - 1 && tc_bias_folded_l1(L.D)) ? blob[L.off_b0 + i] : 0.f);
+    w[kTcOffW0 + tc_off(i, d, kTcK1)] = __float2bfloat16_rn(v);
+  }
+  if (t < kH2 * kTcK1) {                                  // bias tile of layer 2 and the constant ones tile
+    const int j = t / kTcK1, k = t % kTcK1;
+    w[kTcOffB2T + tc_off(j, k, kTcK1)] = __float2bfloat16_rn(k == 0 ? blob[L.off_b2 + j] : 0.f);
+    w[kTcOffOnes + tc_off(j, k, kTcK1)] = __float2bfloat16_rn(k == 0 ? 1.f : 0.f);
   }
   if (t < kH2 * kH1) {                                    // W2[j][k]
     const int j = t / kH1, k = t % kH1;
@@ -173,9 +186,34 @@ __device__ __forceinline__ void tc_hidden_chunk(const uint32_t (&v)[32], int row
     *reinterpret_cast<uint4*>(dst + tc_off(row, col + 8 * c, Kdst)) = q;
   }
 }
+// The same with the bias already inside the accumulator (see kTcOffB2T): ReLU is the .relu modifier of the conversion, so
+// a pair of elements costs ONE instruction.
+__device__ __forceinline__ uint32_t tc_cvt_relu_bf16x2(uint32_t lo, uint32_t hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(__uint_as_float(hi)), "f"(__uint_as_float(lo)));
+  return d;
+}
+template <int ACT>
+__device__ __forceinline__ uint32_t tc_act_pack(uint32_t a0, uint32_t a1) {
+  if (ACT == 0) return tc_cvt_relu_bf16x2(a0, a1);
+  const float z0 = __uint_as_float(a0), z1 = __uint_as_float(a1);
+  return pack_bf16x2((z0 > 0.f) ? z0 : __expf(z0) - 1.f, (z1 > 0.f) ? z1 : __expf(z1) - 1.f);
+}
+template <int ACT>
+__device__ __forceinline__ void tc_hidden_chunk_nb(const uint32_t (&v)[32], int row, int col, __nv_bfloat16* __restrict__ dst, int Kdst) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint4 q;
+    q.x = tc_act_pack<ACT>(v[8 * c + 0], v[8 * c + 1]);
+    q.y = tc_act_pack<ACT>(v[8 * c + 2], v[8 * c + 3]);
+    q.z = tc_act_pack<ACT>(v[8 * c + 4], v[8 * c + 5]);
+    q.w = tc_act_pack<ACT>(v[8 * c + 6], v[8 * c + 7]);
+    *reinterpret_cast<uint4*>(dst + tc_off(row, col + 8 * c, Kdst)) = q;
+  }
+}
 // chunks [c_first, c_first + n32) of 32 columns each; the tensor-memory load of the next chunk is in flight while the
 // current one is converted (n32 is even)
-template <int ACT>
+template <int ACT, bool BIAS>
 __device__ __forceinline__ void tc_hidden_epilogue_t(uint32_t tmem_acc, int lane_base, int row, int c_first, int n32,
                                                      const float* __restrict__ bias, __nv_bfloat16* __restrict__ dst, int Kdst) {
   const uint32_t t0 = tmem_acc + (static_cast<uint32_t>(lane_base) << 16) + 32 * c_first;
@@ -184,17 +222,25 @@ __device__ __forceinline__ void tc_hidden_epilogue_t(uint32_t tmem_acc, int lane
   for (int b = 0; b < n32; b += 2) {
     tc_ld_wait(va);
     tc_ld32_issue(t0 + 32 * (b + 1), vb);
-    tc_hidden_chunk<ACT>(va, row, 32 * (c_first + b), bias, dst, Kdst);
+    if (BIAS) tc_hidden_chunk<ACT>(va, row, 32 * (c_first + b), bias, dst, Kdst);
+    else tc_hidden_chunk_nb<ACT>(va, row, 32 * (c_first + b), dst, Kdst);
     tc_ld_wait(vb);
     if (b + 2 < n32) tc_ld32_issue(t0 + 32 * (b + 2), va);
-    tc_hidden_chunk<ACT>(vb, row, 32 * (c_first + b + 1), bias, dst, Kdst);
+    if (BIAS) tc_hidden_chunk<ACT>(vb, row, 32 * (c_first + b + 1), bias, dst, Kdst);
+    else tc_hidden_chunk_nb<ACT>(vb, row, 32 * (c_first + b + 1), dst, Kdst);
   }
 }
-// the activation is a compile-time parameter of the (instruction-issue bound) epilogue loop: one uniform branch per call
+// the activation (and whether the bias is still to be added) is a compile-time parameter of the instruction-issue bound
+// epilogue loop: one uniform branch per call.  bias = nullptr: already inside the accumulator.
 __device__ __forceinline__ void tc_hidden_epilogue(uint32_t tmem_acc, int lane_base, int row, int c_first, int n32,
                                                    const float* __restrict__ bias, __nv_bfloat16* __restrict__ dst, int Kdst, int act) {
-  if (act != 0) tc_hidden_epilogue_t<1>(tmem_acc, lane_base, row, c_first, n32, bias, dst, Kdst);
-  else tc_hidden_epilogue_t<0>(tmem_acc, lane_base, row, c_first, n32, bias, dst, Kdst);
+  if (bias == nullptr) {
+    if (act != 0) tc_hidden_epilogue_t<1, false>(tmem_acc, lane_base, row, c_first, n32, bias, dst, Kdst);
+    else tc_hidden_epilogue_t<0, false>(tmem_acc, lane_base, row, c_first, n32, bias, dst, Kdst);
+  } else {
+    if (act != 0) tc_hidden_epilogue_t<1, true>(tmem_acc, lane_base, row, c_first, n32, bias, dst, Kdst);
+    else tc_hidden_epilogue_t<0, true>(tmem_acc, lane_base, row, c_first, n32, bias, dst, Kdst);
+  }
 }
 constexpr int kTcFwdThreads = 512;   // two tile pipelines x 8 warps: each TMEM lane quadrant is drained by two warps (column halves)
 __device__ __forceinline__ void tc_group_sync(int g) {   // the 256 threads of one tile pipeline
@@ -234,10 +280,41 @@ __device__ __forceinline__ void tc_fwd_body(const unsigned char* __restrict__ pa
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long n_tiles = (n + kTcRows - 1) / kTcRows;
+  const bool dbg_k = X.dbg != nullptr && bid == 0 && tid == 0;      // diagnostics: kernel entry / weights landed / exit in slots 32..34
+  if (dbg_k) X.dbg[32] = clock64();
+  // Prologue, ordered so that its three latencies overlap: the weight image (one TMA bulk copy, issued by the thread that
+  // initialised its barrier), the first tile's input rows (global loads into registers) and the tensor-memory allocation.
   if (tid == 0) {
     for (int b = 0; b < 7; ++b) mbar_init(bars + b, 1);
     fence_mbar_init();
+    mbar_expect_tx(bars + 0, kTcBlobBytes);
+    bulk_g2s(tsm, packed, kTcBlobBytes, bars + 0);
   }
+  const int g = warp >> 3, q = warp & 3, half = (warp >> 2) & 1, gtid = tid & 255;
+  const int row = 32 * q + lane;                  // tile row = TMEM lane
+  // the NEXT tile's input row is fetched into registers while this tile runs (the global-load latency of the tiny X tile
+  // would otherwise sit at the head of every tile's dependent MMA -> epilogue chain)
+  float xr[16];
+  // 8-byte loads when rows and columns allow it: a warp's rows are 56-128 bytes apart, so every load instruction touches
+  // 15-32 cache lines and the 14 scalar loads of a row cost as many tag look-ups each
+  const bool vec2 = ((D & 1) == 0) && ((X.row_stride & 1) == 0) && ((X.col_off & 1) == 0) && ((reinterpret_cast<uintptr_t>(obs) & 7) == 0);
+  auto load_row = [&](long long t) {        // unconditional loads from a clamped (always valid) row: nothing depends on them until
+    if (half != 0) return;                  // the next iteration packs them (invalid rows / columns are zeroed there)
+    const long long i = min(t * kTcRows + gtid, n - 1);
+    const float* src = obs + i * X.row_stride + X.col_off;
+    if (vec2) {
+#pragma unroll
+      for (int d = 0; d < 16; d += 2)
+        if (d < D) asm volatile("ld.global.nc.v2.f32 {%0, %1}, [%2];" : "=f"(xr[d]), "=f"(xr[d + 1]) : "l"(src + d));
+    } else {
+#pragma unroll
+      for (int d = 0; d < 16; ++d)
+        if (d < D) asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(xr[d]) : "l"(src + d));
+    }
+  };
+#pragma unroll
+  for (int d = 0; d < 16; ++d) xr[d] = 0.f;
+  load_row(bid + static_cast<long long>(g) * nb);
   if (warp == 0) {   // tensor-memory allocation: all 512 columns, one warp, then release the permit
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -246,14 +323,9 @@ __device__ __forceinline__ void tc_fwd_body(const unsigned char* __restrict__ pa
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  if (tid == 0) {    // weights + biases: one TMA bulk copy
-    mbar_expect_tx(bars + 0, kTcBlobBytes);
-    bulk_g2s(tsm, packed, kTcBlobBytes, bars + 0);
-  }
   mbar_wait(bars + 0, 0);
+  if (dbg_k) X.dbg[33] = clock64();
 
-  const int g = warp >> 3, q = warp & 3, half = (warp >> 2) & 1, gtid = tid & 255;
-  const int row = 32 * q + lane;                  // tile row = TMEM lane
   __nv_bfloat16* sX = sXall + g * kTcRows * kTcK1;
   __nv_bfloat16* sH = sHall + g * kTcRows * kH1;
   uint64_t* gb = bars + 1 + 3 * g;
@@ -261,20 +333,13 @@ __device__ __forceinline__ void tc_fwd_body(const unsigned char* __restrict__ pa
   const uint32_t id1 = tc_idesc_bf16(kTcRows, kH1), id2 = tc_idesc_bf16(kTcRows, kH2), id3 = tc_idesc_bf16(kTcRows, kTcNH);
   uint32_t phase = 0;
   const bool save = X.H1b != nullptr;       // training pass over the s rows: keep X / H1 / H2 for the backward kernel
-  // the NEXT tile's input row is fetched into registers while this tile runs (the global-load latency of the tiny X tile
-  // would otherwise sit at the head of every tile's dependent MMA -> epilogue chain)
-  float xr[16];
-  auto load_row = [&](long long t) {        // unconditional loads from a clamped (always valid) row: nothing depends on them until
-    if (half != 0) return;                  // the next iteration packs them (invalid rows / columns are zeroed there)
-    const long long i = min(t * kTcRows + gtid, n - 1);
-    const float* src = obs + i * X.row_stride + X.col_off;
-#pragma unroll
-    for (int d = 0; d < 16; ++d)
-      if (d < D) xr[d] = __ldg(src + d);
-  };
-#pragma unroll
-  for (int d = 0; d < 16; ++d) xr[d] = 0.f;
-  load_row(bid + static_cast<long long>(g) * nb);
+  const bool fold1 = tc_bias_folded_l1(D);  // b0 rides in column 15 of the layer-1 operands
+  // Stagger: the two pipelines have identical stage lengths, so started together they stay in phase -- both in their
+  // epilogues (CUDA cores contended), then both in their MMAs (tensor core contended, the layer-2 wait doubles).  Pipeline 1
+  // starts its first tile when pipeline 0 has finished its first hidden epilogue; from then on one computes while the other
+  // converts.
+  bool first_tile = true;
+  if (g == 1 && bid + static_cast<long long>(nb) < n_tiles) asm volatile("bar.sync 3, 512;" ::: "memory");
   for (long long tile = bid + static_cast<long long>(g) * nb; tile < n_tiles; tile += 2ll * nb) {
     // ---- X tile: fp32 obs -> bf16 canonical [128][16]; thread = row
     if (half == 0) {
@@ -283,6 +348,7 @@ __device__ __forceinline__ void tc_fwd_body(const unsigned char* __restrict__ pa
 #pragma unroll
         for (int d = 0; d < 16; ++d) xr[d] = 0.f;
       }
+      if (fold1) xr[15] = 1.f;              // bias column of layer 1 (W0 image column 15 = b0)
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         uint4 v;
@@ -309,8 +375,10 @@ __device__ __forceinline__ void tc_fwd_body(const unsigned char* __restrict__ pa
     mbar_wait(gb + 0, phase);
     tc_fence_after();
     TC_FWD_STAMP();               // 1: layer-1 MMA complete
-    tc_hidden_epilogue(tD1, 32 * q, row, 4 * half, 4, sBias, sH, kH1, X.act);
+    tc_hidden_epilogue(tD1, 32 * q, row, 4 * half, 4, fold1 ? nullptr : sBias, sH, kH1, X.act);
     TC_FWD_STAMP();               // 2: epilogue 1 done (this thread)
+    if (first_tile && g == 0 && bid + static_cast<long long>(nb) < n_tiles) asm volatile("bar.arrive 3, 512;" ::: "memory");
+    first_tile = false;
     fence_proxy_async();
     tc_fence_before();
     tc_group_sync(g);
@@ -320,6 +388,8 @@ __device__ __forceinline__ void tc_fwd_body(const unsigned char* __restrict__ pa
       const uint64_t a0 = tc_smem_desc(sH, 128, (kH1 / 8) * 128), b0 = tc_smem_desc(sWts + kTcOffW2, 128, (kH1 / 8) * 128);
 #pragma unroll
       for (int k = 0; k < kH1 / 16; ++k) tc_mma_bf16(tD2, a0 + static_cast<uint64_t>(k * 16), b0 + static_cast<uint64_t>(k * 16), id2, k > 0 ? 1u : 0u);
+      // + b2: ones tile x bias tile (one more K step)
+      tc_mma_bf16(tD2, tc_smem_desc(sWts + kTcOffOnes, 128, (kTcK1 / 8) * 128), tc_smem_desc(sWts + kTcOffB2T, 128, (kTcK1 / 8) * 128), id2, 1u);
       tc_commit(gb + 1);
       if (save) {     // the operand images of X and H1 go to HBM as they are: two bulk stores, read by the TMA engine while layer 2 runs
         bulk_s2g(X.Xb + tile * (kTcRows * kTcK1), sX, kTcRows * kTcK1 * 2);
@@ -334,7 +404,7 @@ __device__ __forceinline__ void tc_fwd_body(const unsigned char* __restrict__ pa
       if (gtid == 0) bulk_wait_read();
       tc_group_sync(g);
     }
-    tc_hidden_epilogue(tD2, 32 * q, row, 2 * half, 2, sBias + kH1, sH, kH2, X.act);     // H2 overwrites H1 (layer 2 has consumed it)
+    tc_hidden_epilogue(tD2, 32 * q, row, 2 * half, 2, nullptr, sH, kH2, X.act);     // H2 overwrites H1 (layer 2 has consumed it)
     TC_FWD_STAMP();               // 4: epilogue 2 done
     fence_proxy_async();
     tc_fence_before();
@@ -396,6 +466,7 @@ __device__ __forceinline__ void tc_fwd_body(const unsigned char* __restrict__ pa
   tc_fence_before();
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  if (dbg_k) X.dbg[34] = clock64();
 }
 
 __global__ void __launch_bounds__(kTcFwdThreads, 1) k_mlp_infer_tc(const unsigned char* __restrict__ packed, int D, int A, int NH, int dueling,

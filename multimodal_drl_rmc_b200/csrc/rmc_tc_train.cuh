@@ -61,6 +61,7 @@ __device__ __forceinline__ void tc_pack_param(const NetLayout& L, int pi, float 
     if (w) w[kTcOffW0 + tc_off(i, d, kTcK1)] = hv;
   } else if ((r = pi - L.off_b0) >= 0 && r < kH1) {
     if (bias) bias[r] = val;
+    if (w && tc_bias_folded_l1(L.D)) w[kTcOffW0 + tc_off(r, kTcK1 - 1, kTcK1)] = hv;      // b0: column 15 of the W0 image
   } else if ((r = pi - L.off_w2t) >= 0 && r < kH1 * kW2LD) {
     const int k = r / kW2LD, j = r - k * kW2LD;
     if (j < kH2) {
@@ -69,6 +70,7 @@ __device__ __forceinline__ void tc_pack_param(const NetLayout& L, int pi, float 
     }
   } else if ((r = pi - L.off_b2) >= 0 && r < kH2) {
     if (bias) bias[kH1 + r] = val;
+    if (w) w[kTcOffB2T + tc_off(r, 0, kTcK1)] = hv;                                         // b2: column 0 of the bias tile
   } else if ((r = pi - L.off_wh) >= 0 && r < L.NH * kH2) {
     const int a = r / kH2, j = r - a * kH2;
     if (w) w[kTcOffWh + tc_off(a, j, kH2)] = hv;

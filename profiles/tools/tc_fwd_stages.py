@@ -22,7 +22,7 @@ acts = torch.empty(n, dtype=torch.int64, device=agent.device)
 for _ in range(3):
     _lib.check(lib.rmc_learner_act_tc(agent._lh.handle, states.data_ptr(), n, acts.data_ptr(), _lib.stream_ptr()))
 torch.cuda.synchronize()
-buf = (C.c_uint64 * 128)()          # 4 CTA records of 32 slots (kDbgSlots)
+buf = (C.c_uint64 * 128)()          # 4 CTA records of 32 slots (kDbgSlots); slots 32..34: kernel entry / weights landed / exit
 got = C.c_int32(0)
 _lib.check(lib.rmc_learner_debug_read_sync(agent._lh.handle, buf, 4, C.byref(got), _lib.stream_ptr()))
 v = np.array(buf[:32], dtype=np.int64).reshape(4, 8)
@@ -33,3 +33,6 @@ for t in range(4):
     d = np.diff(v[t])
     print("tile %d: " % t + "  ".join("%s +%d" % (names[k + 1], d[k]) for k in range(7)) + "   total %d cycles" % (v[t, 7] - v[t, 0]),
           ("| gap to next tile start %d" % (v[t + 1, 0] - v[t, 7])) if t < 3 and v[t + 1, 0] else "")
+
+k = np.array(buf[32:35], dtype=np.int64)
+print("CTA 0: entry -> weights landed %d cycles, -> first tile's X packed %d, entry -> exit %d cycles" % (k[1] - k[0], v[0, 0] - k[0], k[2] - k[0]))
