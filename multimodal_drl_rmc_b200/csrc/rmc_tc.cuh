@@ -339,6 +339,7 @@ __device__ __forceinline__ void tc_fwd_body(const unsigned char* __restrict__ pa
   // starts its first tile when pipeline 0 has finished its first hidden epilogue; from then on one computes while the other
   // converts.
   bool first_tile = true;
+  int tile_no = 0;
   if (g == 1 && bid + static_cast<long long>(nb) < n_tiles) asm volatile("bar.sync 3, 512;" ::: "memory");
   for (long long tile = bid + static_cast<long long>(g) * nb; tile < n_tiles; tile += 2ll * nb) {
     // ---- X tile: fp32 obs -> bf16 canonical [128][16]; thread = row
@@ -359,8 +360,8 @@ __device__ __forceinline__ void tc_fwd_body(const unsigned char* __restrict__ pa
     }
     load_row(tile + 2ll * nb);
     int dslot = 0;
-    const bool dbg_on = X.dbg != nullptr && bid == 0 && gtid == 0 && (tile - bid) / (2ll * nb) < 4;
-    long long* dbg_row = dbg_on ? X.dbg + ((tile - bid) / (2ll * nb)) * 8 : nullptr;
+    const bool dbg_on = X.dbg != nullptr && bid == 0 && gtid == 0 && g == 0 && tile_no < 4;      // (no 64-bit division here: it showed up as a 1,500-cycle "gap")
+    long long* dbg_row = dbg_on ? X.dbg + tile_no * 8 : nullptr;
 #define TC_FWD_STAMP() do { if (dbg_on) dbg_row[dslot++] = clock64(); } while (0)
     TC_FWD_STAMP();               // 0: X packed
     fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core's async proxy
@@ -461,6 +462,7 @@ __device__ __forceinline__ void tc_fwd_body(const unsigned char* __restrict__ pa
     tc_group_sync(g);     // this group's TMEM slot and operand buffers are free for its next tile
     TC_FWD_STAMP();               // 7: tile done
     phase ^= 1u;
+    ++tile_no;
   }
   if (save && gtid == 0) bulk_wait_all();
   tc_fence_before();
