@@ -121,6 +121,11 @@ __global__ void __launch_bounds__(kTdThreads) k_tc_td(AgentCtx C, StepScalars S,
   if (i < S.B) {
     const int rf = C.rp.row_floats;
     float hn[16], ht[16], hs[16], qn[16], qt[16], qs[16];
+    // every input of the row is requested before the first one is used (the transition fields and the IS weight used to be a
+    // second, dependent memory round trip behind the head rows)
+    const int act = __float_as_int(__ldcg(C.X + i * rf + 2 * L.D));
+    const float rew = __ldcg(C.X + i * rf + 2 * L.D + 1), done = __ldcg(C.X + i * rf + 2 * L.D + 2);
+    const float w = per ? __ldcg(C.is_w + i) : 1.f;
 #pragma unroll
     for (int k = 0; k < 16; k += 4) {
       *reinterpret_cast<float4*>(hn + k) = *reinterpret_cast<const float4*>(T.heads_n + i * 16 + k);
@@ -139,9 +144,6 @@ __global__ void __launch_bounds__(kTdThreads) k_tc_td(AgentCtx C, StepScalars S,
 #pragma unroll
       for (int a = 1; a < 15; ++a) qsel = (a < L.A) ? fmaxf(qsel, qt[a]) : qsel;
     }
-    const int act = __float_as_int(__ldcg(C.X + i * rf + 2 * L.D));
-    const float rew = __ldcg(C.X + i * rf + 2 * L.D + 1), done = __ldcg(C.X + i * rf + 2 * L.D + 2);
-    const float w = per ? C.is_w[i] : 1.f;
     const float y = rew + ((1.f - done) * S.gamma) * qsel;
     float q_sa = qs[0];
 #pragma unroll
