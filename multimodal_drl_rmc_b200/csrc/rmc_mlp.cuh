@@ -582,9 +582,10 @@ __device__ void stream_unit(const AgentCtx& C, const StepScalars& S, const Strea
   {
     const WordStager<TMO> sa(U.A, As);
     const WordStager<TNO> sb(U.Bm, Bs);
-    constexpr int NQA = 256 / WordStager<TMO>::kRowsPerPass, NQB = 256 / WordStager<TNO>::kRowsPerPass;   // 256 rows per pass
+    constexpr int kPass = (TNO > 16) ? 128 : 256;     // rows per pass (the wide unit halves it: its staging registers would double)
+    constexpr int NQA = kPass / WordStager<TMO>::kRowsPerPass, NQB = kPass / WordStager<TNO>::kRowsPerPass;
     SpinGuard guard;
-    for (int base = 0; base < rows; base += 256) {
+    for (int base = 0; base < rows; base += kPass) {
       const bool has_a = base + sa.row0 < rows, has_b = base + sb.row0 < rows;
       if (has_b) wait_word(sb.template probe<NQB>(base, rows), S.epoch, guard, C.host_loss);     // B is the operand produced last
       uint4 wa[NQA], wb[NQB];
@@ -674,6 +675,17 @@ __device__ __forceinline__ void stream_run_w2(const AgentCtx& C, const StepScala
   U.out_base = L.off_w2t + kt * 16 * kW2LD + jt * 16; U.out_sm = kW2LD; U.out_sn = 1;
   U.bias_base = (kt == 0) ? L.off_b2 + jt * 16 : -1;
   stream_unit<16, 16>(C, S, U, smem);
+}
+// two neighbouring W2 units as ONE 16 x 32 unit (two outputs per thread; same per-output summation order, hence the same bits)
+__device__ __forceinline__ void stream_run_w2_wide(const AgentCtx& C, const StepScalars& S, int kt, int jt0, float* smem) {
+  const NetLayout& L = C.L;
+  StreamUnit U;
+  U.A = WordTile{C.hp_words, kH1, kt * 16};
+  U.Bm = WordTile{C.zp_words, kH2, jt0 * 16};
+  U.m_valid = 16; U.n_valid = 32;
+  U.out_base = L.off_w2t + kt * 16 * kW2LD + jt0 * 16; U.out_sm = kW2LD; U.out_sn = 1;
+  U.bias_base = (kt == 0) ? L.off_b2 + jt0 * 16 : -1;
+  stream_unit<16, 32>(C, S, U, smem);
 }
 __device__ __forceinline__ int stream_w0_count(const NetLayout& L) { return ((L.D + 15) / 16) * (kH1 / 16); }
 __device__ __forceinline__ void stream_run_w0(const AgentCtx& C, const StepScalars& S, int u, float* smem) {      // 16 (d) x 16 (k)
@@ -1325,8 +1337,25 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(const __grid_const
       const int total = kH2 / 16 + (kH1 / 16) * (kH2 / 16) + stream_w0_count(L), slots = sp.n_idle + 2 * nt;
       const int extra = max(0, total - slots);
       if (cta == nt && (S.phases & 2)) stream_publish_loss(C, S, nt, smem);      // first target CTA: its unit's operands are still 2 us away
-      if (k < extra) stream_run_any(C, S, k, smem);
-      if (extra + k < total) stream_run_any(C, S, extra + k, smem);
+      // More units than CTAs: the CTAs that are idle in phase A (free from the start, 2 us before anybody else) take TWO
+      // neighbouring W2 units as one 16 x 32 unit (kt = idle index / 4, columns 32 * (idle index % 4)), which removes exactly
+      // 2 * n_idle units from the list; when what is left fits the other CTAs one to one nobody runs two units back to back
+      // (at B = 256: 12 idle CTAs cover kt 0..2, the other 128 units land on the 64 target and 64 row CTAs in the order
+      // heads, W2, W0).  Before, the idle CTAs ran two 16 x 16 units in sequence and ended the launch 2.3 us after the row CTAs.
+      constexpr int nH = kH2 / 16, nJT = kH2 / 16;
+      const bool wide_ok = extra > 0 && (sp.n_idle % (nJT / 2)) == 0 && 2 * sp.n_idle <= (kH1 / 16) * nJT && total - 2 * sp.n_idle <= 2 * nt;
+      if (wide_ok) {
+        if (s_idx >= 0) {
+          stream_run_w2_wide(C, S, s_idx / (nJT / 2), 2 * (s_idx % (nJT / 2)), smem);
+        } else {
+          const int j = (cta >= nt) ? cta - nt : nt + cta;          // target CTAs first (free first), then row CTAs
+          const int id = (j < nH) ? j : j + 2 * sp.n_idle;           // the list without the W2 units of the idle CTAs
+          if (id < total) stream_run_any(C, S, id, smem);
+        }
+      } else {
+        if (k < extra) stream_run_any(C, S, k, smem);
+        if (extra + k < total) stream_run_any(C, S, extra + k, smem);
+      }
     }
     RMC_STAMP(C, 7); if (gap != nullptr && threadIdx.x == 0) atomicMax(gap + 1, global_timer_ns());
     return;
