@@ -587,15 +587,22 @@ __device__ void stream_unit(const AgentCtx& C, const StepScalars& S, const Strea
     SpinGuard guard;
     for (int base = 0; base < rows; base += kPass) {
       const bool has_a = base + sa.row0 < rows, has_b = base + sb.row0 < rows;
-      if (has_b) wait_word(sb.template probe<NQB>(base, rows), S.epoch, guard, C.host_loss);     // B is the operand produced last
       uint4 wa[NQA], wb[NQB];
-      bool ok;
+      bool ok, first = true;
       do {
+        // First attempt without asking: a CTA that comes here late (a row CTA after its own dz1 -- the chain that ends the
+        // launch) finds its operands complete and saves the probe's L2 round trip.  A CTA that is early pays one wasted pass,
+        // then waits on ONE probe word (B is the operand produced last) instead of streaming the operands on every attempt.
         if (has_a) sa.template issue<NQA>(base, rows, wa);
         if (has_b) sb.template issue<NQB>(base, rows, wb);
         ok = (!has_a || sa.template fresh<NQA>(base, rows, wa, S.epoch)) && (!has_b || sb.template fresh<NQB>(base, rows, wb, S.epoch));
         if (!ok) {
-          __nanosleep(100);
+          if (first) {
+            if (has_b) wait_word(sb.template probe<NQB>(base, rows), S.epoch, guard, C.host_loss);
+          } else {
+            __nanosleep(100);
+          }
+          first = false;
           if (guard.expired()) { spin_report_timeout(C.host_loss, S.epoch); break; }
         }
       } while (!ok);
@@ -636,16 +643,29 @@ __device__ void stream_unit(const AgentCtx& C, const StepScalars& S, const Strea
   }
   __syncthreads();
   RMC_STAMP(C, 18);
-  float gq[NOUT];
-  ParamVals po[NOUT];
+  // The bias element of the last warp's lanes goes through the SAME straight-line Adam block as the thread's own outputs (its
+  // sqrt / division chain interleaves with theirs; as a second, dependent chain it made the last warp -- and with it the
+  // CTA -- finish 0.4 us late, on exactly the W0 units that end the launch).  Same arithmetic: param_math_n == param_apply.
+  float gq[NOUT + 1];
+  ParamVals pin[NOUT + 1], po[NOUT + 1];
 #pragma unroll
   for (int q = 0; q < NOUT; ++q) {
     float g = 0.f;
 #pragma unroll
     for (int w = 0; w < kWarps; ++w) g += Ps[w * (TMO * TNO) + ps_off[q]];
     gq[q] = g;
+    pin[q] = pv[q];
   }
-  param_math_n<NOUT>(S, gq, pv, po);
+  {
+    float g = 0.f;
+    if (pbi >= 0) {
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) g += Pb[w * TNO + bt];
+    }
+    gq[NOUT] = g;
+    pin[NOUT] = pvb;
+  }
+  param_math_n<NOUT + 1>(S, gq, pin, po);
 #pragma unroll
   for (int q = 0; q < NOUT; ++q) {
     if (pi[q] >= 0) {
@@ -654,11 +674,8 @@ __device__ void stream_unit(const AgentCtx& C, const StepScalars& S, const Strea
     }
   }
   if (pbi >= 0) {
-    float g = 0.f;
-#pragma unroll
-    for (int w = 0; w < kWarps; ++w) g += Pb[w * TNO + bt];
-    C.grads[pbi] = g;
-    param_apply(C, S, pbi, g, pvb);
+    C.grads[pbi] = gq[NOUT];
+    param_store(C, S, pbi, po[NOUT]);
   }
   RMC_STAMP(C, 19);
   __syncthreads();
