@@ -158,6 +158,32 @@ def test_tensor_core_act_mode_within_stated_bound(activation):
     assert np.all(gap < 0.05 * np.abs(e[:, 1:]).max())
 
 
+@pytest.mark.parametrize("D", [16, 15, 9])
+def test_tensor_core_act_bias_paths(D):
+    """The biases of the hidden layers ride on the MMAs (csrc/rmc_tc.cuh: b0 in column 15 of the W0 image when obs_dim <= 15, b2 as
+    one more K step); obs_dim = 16 has no spare column and adds b0 in the epilogue.  Randomly initialised nets (non-zero
+    biases), biases scaled up so that a dropped or doubled bias would be far outside the bound."""
+    from multimodal_drl_rmc_b200 import Networks, _lib
+    from multimodal_drl_rmc_b200.macro_config import ObsSpace, network_config
+    torch.manual_seed(5)
+    net = Networks.DuelingDeepQNetwork(torch.device("cuda:0"), 1e-4, network_config, ObsSpace(D), 8)
+    sd = net.state_dict()
+    for k in sd:
+        if k.endswith("bias"):
+            sd[k] = sd[k] * 8.0
+    net.load_state_dict(sd)
+    lh = net._standalone_handle()
+    n = 4096 + 5
+    x = torch.as_tensor(np.random.default_rng(D).random((n, D), dtype=np.float32), device="cuda:0")
+    exact = torch.empty(n, 9, device="cuda:0")
+    tc = torch.empty(n, 9, device="cuda:0")
+    _lib.check(_lib.lib().rmc_learner_heads(lh.handle, 0, x.data_ptr(), n, exact.data_ptr(), _lib.stream_ptr()))
+    _lib.check(_lib.lib().rmc_learner_heads_tc(lh.handle, x.data_ptr(), n, tc.data_ptr(), _lib.stream_ptr()))
+    err = R.max_rel(tc.cpu().numpy(), exact.cpu().numpy())
+    print("obs_dim", D, "tensor-core heads max-norm rel err", err)
+    assert err < 1e-2
+
+
 def test_device_epsilon_greedy_distribution_and_reproducibility():
     """Agent.exploration = "device": greedy act + Philox epsilon-greedy in one call."""
     _, a = PU.make_pair("DuelingDoubleDQNAgent", 14, 32, 64, 64, seed=3)
