@@ -621,7 +621,7 @@ __device__ void stream_unit(const AgentCtx& C, const StepScalars& S, const Strea
     for (int j = 0; j < LN; ++j) acc[i][j] = 0.f;
 #pragma unroll
   for (int j = 0; j < LN; ++j) bsum[j] = 0.f;
-#pragma unroll 4
+#pragma unroll 8
   for (int r = warp; r < rows; r += kWarps) {       // warp w takes rows w, w+8, ... (fixed order -> deterministic sums)
     float a[LM], b[LN];
     lds_vec<LM>(a, As + r * TMO + mg * LM);
