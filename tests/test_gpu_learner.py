@@ -25,6 +25,8 @@ CASES = [
     ("DuelingDoubleDQNAgent", 14, 1024, 4096, 4096, 2, True, 30000),    # several row tiles per CTA
     ("PerDuelingDoubleDQNAgent", 14, 288, 5000, 5000, 2, True, 30000),  # role split where write-back CTAs are also target CTAs
     ("PerDuelingDoubleDQNAgent", 14, 590, 8192, 8192, 2, True, 30000),  # every CTA owns a row tile (ragged last one), no role split
+    ("PerDuelingDoubleDQNAgent", 14, 240, 5000, 5000, 2, True, 30000),  # streamed phase B with 20 idle CTAs on 16x32 W2 units, 112 units on 120 CTAs
+    ("DuelingDoubleDQNAgent", 14, 192, 4096, 4096, 2, True, 30000),     # ... with 44 idle CTAs (88 of the 128 W2 units)
     # batch-stationary row phase (csrc/rmc_rows_ws.cuh: >= two 16-row tiles per row CTA, i.e. B >= 4,736 on 148 SMs):
     ("DQNAgent", 20, 5000, 8192, 8192, 2, False, 2),                    # plain heads, uniform replay, obs_dim > 16 (32-wide W0 accumulators), ragged last tile, hard sync
     ("PerDuelingDoubleDQNAgent", 14, 4808, 8192, 8192, 2, True, 30000), # PER above the one-CTA write-back limit, ragged last tile
