@@ -1,3 +1,5 @@
+"""tcgen05 act on 65,536 states: microseconds per call launched call by call, and GPU-bound inside a CUDA graph of 20 calls.
+usage (GPU box): python profiles/tools/act_tc_time.py"""
 import sys, os
 sys.path.insert(0, '.')
 import numpy as np, torch, ctypes as C

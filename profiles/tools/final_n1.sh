@@ -1,3 +1,6 @@
+#!/bin/bash
+# The N = 1 measurements kept under profiles/r2/ (bench line, reference arm, ncu launch list, spans / timelines of the
+# large-batch and ensemble launches).   usage (GPU box): bash profiles/tools/final_n1.sh
 set -x
 python bench.py > gpurun_out/r2f_bench_n1.json 2> gpurun_out/r2f_bench_n1.err; echo "exit $?"
 python bench.py --impl reference --steps 200 --warmup 5 > gpurun_out/r2f_bench_ref_n1.json 2> gpurun_out/r2f_bench_ref_n1.err; echo "exit $?"
