@@ -682,7 +682,7 @@ __device__ void stream_unit(const AgentCtx& C, const StepScalars& S, const Strea
 }
 
 // unit tables of the streamed phase B
-__device__ __forceinline__ void stream_run_w2(const AgentCtx& C, const StepScalars& S, int u, float* smem) {      // 16 x 16, u in [0, 128)
+__device__ __forceinline__ StreamUnit stream_unit_w2(const AgentCtx& C, int u) {      // 16 x 16, u in [0, 128)
   const NetLayout& L = C.L;
   const int kt = u / (kH2 / 16), jt = u % (kH2 / 16);
   StreamUnit U;
@@ -691,7 +691,10 @@ __device__ __forceinline__ void stream_run_w2(const AgentCtx& C, const StepScala
   U.m_valid = 16; U.n_valid = 16;
   U.out_base = L.off_w2t + kt * 16 * kW2LD + jt * 16; U.out_sm = kW2LD; U.out_sn = 1;
   U.bias_base = (kt == 0) ? L.off_b2 + jt * 16 : -1;
-  stream_unit<16, 16>(C, S, U, smem);
+  return U;
+}
+__device__ __forceinline__ void stream_run_w2(const AgentCtx& C, const StepScalars& S, int u, float* smem) {
+  stream_unit<16, 16>(C, S, stream_unit_w2(C, u), smem);
 }
 // two neighbouring W2 units as ONE 16 x 32 unit (two outputs per thread; same per-output summation order, hence the same bits)
 __device__ __forceinline__ void stream_run_w2_wide(const AgentCtx& C, const StepScalars& S, int kt, int jt0, float* smem) {
@@ -705,7 +708,7 @@ __device__ __forceinline__ void stream_run_w2_wide(const AgentCtx& C, const Step
   stream_unit<16, 32>(C, S, U, smem);
 }
 __device__ __forceinline__ int stream_w0_count(const NetLayout& L) { return ((L.D + 15) / 16) * (kH1 / 16); }
-__device__ __forceinline__ void stream_run_w0(const AgentCtx& C, const StepScalars& S, int u, float* smem) {      // 16 (d) x 16 (k)
+__device__ __forceinline__ StreamUnit stream_unit_w0(const AgentCtx& C, int u) {      // 16 (d) x 16 (k)
   const NetLayout& L = C.L;
   const int mt = u / (kH1 / 16), nt = u % (kH1 / 16);
   StreamUnit U;
@@ -714,15 +717,9 @@ __device__ __forceinline__ void stream_run_w0(const AgentCtx& C, const StepScala
   U.m_valid = min(16, L.D - mt * 16); U.n_valid = 16;
   U.out_base = L.off_w0t + mt * 16 * kH1 + nt * 16; U.out_sm = kH1; U.out_sn = 1;
   U.bias_base = (mt == 0) ? L.off_b0 + nt * 16 : -1;
-  stream_unit<16, 16>(C, S, U, smem);
+  return U;
 }
-// One schedule for all three kinds of unit.  Units in the order their operands come into existence -- heads (after the TD
-// block), W2 (after dz2), W0 (after dz1) -- are dealt to the CTAs in the order those become free -- idle in phase A, target,
-// row: CTA k (in that order) takes unit extra + k, and when there are more units than CTAs the first `extra` CTAs (the
-// earliest free) take unit k before it.  At B = 256: 8 head + 128 W2 + 16 W0 units on 140 CTAs -> the 12 idle CTAs run a
-// head or W2 unit and then a W2 unit, and the W0 units land on the last 16 row CTAs.
-__device__ __forceinline__ void stream_run_any(const AgentCtx& C, const StepScalars& S, int id, float* smem);
-__device__ __forceinline__ void stream_run_heads(const AgentCtx& C, const StepScalars& S, int u, float* smem) {   // 16 (j) x 16 (a), u in [0, 8)
+__device__ __forceinline__ StreamUnit stream_unit_heads(const AgentCtx& C, int u) {   // 16 (j) x 16 (a), u in [0, 8)
   const NetLayout& L = C.L;
   StreamUnit U;
   U.A = WordTile{C.h2_words, kH2, u * 16};
@@ -730,14 +727,16 @@ __device__ __forceinline__ void stream_run_heads(const AgentCtx& C, const StepSc
   U.m_valid = 16; U.n_valid = L.NH;
   U.out_base = L.off_wh + u * 16; U.out_sm = 1; U.out_sn = kH2;
   U.bias_base = (u == 0) ? L.off_bh : -1;
-  stream_unit<16, 16>(C, S, U, smem);
+  return U;
 }
-
+// One schedule for all three kinds of unit.  Units in the order their operands come into existence -- heads (after the TD
+// block), W2 (after dz2), W0 (after dz1) -- are dealt to the CTAs in the order those become free (see the call site).  All
+// three kinds are the same 16 x 16 code with different operand tables: ONE copy of it per call site (the kernel is a long
+// stretch of code that every CTA runs once, so its size is paid for in instruction fetch).
 __device__ __forceinline__ void stream_run_any(const AgentCtx& C, const StepScalars& S, int id, float* smem) {
   constexpr int nH = kH2 / 16, nW2 = (kH1 / 16) * (kH2 / 16);
-  if (id < nH) stream_run_heads(C, S, id, smem);
-  else if (id < nH + nW2) stream_run_w2(C, S, id - nH, smem);
-  else stream_run_w0(C, S, id - nH - nW2, smem);
+  const StreamUnit U = (id < nH) ? stream_unit_heads(C, id) : (id < nH + nW2) ? stream_unit_w2(C, id - nH) : stream_unit_w0(C, id - nH - nW2);
+  stream_unit<16, 16>(C, S, U, smem);
 }
 
 // loss of a streamed launch without a priority write-back team: the tiles' {epoch, loss partial} words, summed in tile order
