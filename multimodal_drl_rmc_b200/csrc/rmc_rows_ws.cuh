@@ -162,7 +162,7 @@ __device__ __forceinline__ void ws_forward(const float* __restrict__ sW, const N
     const int ks = lane & 15, cg = lane >> 4;
     const int col = 16 * warp + 8 * cg + ((ks >> 1) & 7);
     const float bias = sW[L.off_b2 + col];
-#pragma unroll 1
+#pragma unroll 2
     for (int r0 = 0; r0 < wr; r0 += 2) {
       float a0[8], a1[8];
 #pragma unroll
@@ -468,7 +468,7 @@ __device__ __forceinline__ void ws_dgrad_phase(const AgentCtx& C, const StepScal
     const float* sDZ = single ? W.dz2 : cur + kWR * kH1;
     const float* sX = cur + kWR * kH1 + kWR * kH2;
     const long long row0 = wt * wr;
-#pragma unroll 1
+#pragma unroll 2
     for (int r0 = 0; r0 < wr; r0 += 2) {
       float a0[8], a1[8];
 #pragma unroll
