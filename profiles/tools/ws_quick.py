@@ -1,3 +1,4 @@
+"""Exact fp32 step time at B = 8,192 and 65,536 (k_learner_step<2>).   usage (GPU box): python profiles/tools/ws_quick.py"""
 import sys
 sys.path.insert(0, '.')
 import bench
