@@ -840,9 +840,11 @@ __device__ __forceinline__ void publish_loss(const AgentCtx& C, const StepScalar
   C.loss[0] = loss;
   host_loss_store(C.host_loss, loss, S.epoch);
 }
-// Two instantiations: kOneTile = true when every row CTA owns at most one 4-row tile (the default single-agent
-// batches: rows and Q_target stay in shared memory, role split), false for ensembles / large batches (several tiles per
-// CTA).  Splitting them keeps each kernel's straight-line code small: the step is sensitive to instruction-fetch stalls.
+// Three instantiations, chosen by the host (step_path in rmc_b200.cu): kPath = 1 when every row CTA owns at most one 4-row
+// tile (the default single-agent batches: rows and Q_target stay in shared memory, role split, streamed phase B), 0 for
+// several 4-row tiles per CTA (ensembles, mid-size batches), 2 for the batch-stationary phases of rmc_rows_ws.cuh (a row
+// CTA owns at least two 16-row tiles).  Splitting them keeps each kernel's straight-line code small: the step is sensitive to
+// instruction-fetch stalls.
 template <int kPath>
 __global__ void __launch_bounds__(kThreads, 1) k_learner_step(const __grid_constant__ AgentCtx single, const AgentCtx* __restrict__ many,
                                                               const __grid_constant__ StepScalars S) {

@@ -1,8 +1,9 @@
-// rmc_rows_ws.cuh -- row phase AND weight gradients of the fused learner step for launches in which a CTA owns several
-// batch rows' worth of work: the agent-ensemble launch (grid.y agents share the device, 18 CTAs each) and batches of
-// thousands of rows (BASELINE configs[3] and [4]).  Included by rmc_mlp.cuh; used by k_learner_step<false>.
+// rmc_rows_ws.cuh -- row phase AND weight gradients of the fused learner step for launches in which a row CTA owns at
+// least two 16-row tiles: batches of thousands of rows (BASELINE configs[4], on one GPU and per rank of the sharded step).
+// Included by rmc_mlp.cuh; used by k_learner_step<2> (the host picks the instantiation: step_path in rmc_b200.cu).  The
+// 8-agent ensemble launch (16 rows per CTA) was measured on this path and stays on the 4-row tiles -- see DESIGN.md 3.1b.
 //
-// Why a second form of the row phase.  The single-tile path (k_learner_step<true>) is shaped by latency: 4 rows per CTA,
+// Why a second form of the row phase.  The single-tile path (k_learner_step<1>) is shaped by latency: 4 rows per CTA,
 // both operands of every product read from shared memory.  Per FMA that is 1.5-3 bytes of shared-memory traffic, and the
 // SM delivers 128 B/clk against 128 FMA/clk -- so once a CTA owns tens or hundreds of rows the passes run at the
 // shared-memory roofline, a quarter to a third of the FMA rate (measured: a 16-row layer-2 pass 8.6 us against a 2.2 us FMA
