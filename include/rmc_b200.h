@@ -311,6 +311,12 @@ int32_t rmc_group_destroy(rmc_group_t* g);
  * tensor-core steps (rmc_learner_step in that mode) run side by side on internal streams, forked from / joined into `s`;
  * meant for ensembles of large-batch members -- at B = 256 per member the fused fp32 launch is faster. */
 int32_t rmc_group_step(rmc_group_t* g, const rmc_step_args_t* a, rmc_stream_t s);
+/* Agent.store_transitions of EVERY member for one env step (dqn/agent.py:70-73 -> dqn/replay_memory.py:49-57): member i
+ * stores the n host rows obs_host[i], act_host[i], ... (n <= 8 each; new rows enter with the member's max priority).  One
+ * launch for the whole ensemble when the packed rows fit the kernel-argument buffer, else one small push per member. */
+int32_t rmc_group_push_host(rmc_group_t* g, const float* const* obs_host, const int64_t* const* act_host,
+                            const float* const* rew_host, const float* const* done_host,
+                            const float* const* next_obs_host, int64_t n, rmc_stream_t s);
 
 /* ---------------------------------------------------------------- sharded large batch (C5) --- */
 /* The reference has no multi-device path; this is the data-parallel form of

@@ -145,6 +145,7 @@ _SIGS = {
     "rmc_group_create": (_i32, [C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), _i32]),
     "rmc_group_destroy": (_i32, [_vp]),
     "rmc_group_step": (_i32, [_vp, C.POINTER(StepArgs), _vp]),
+    "rmc_group_push_host": (_i32, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), _i64, _vp]),
     "rmc_comm_create": (_i32, [C.POINTER(_vp), _vp, _i32, _i32, _i64]),
     "rmc_comm_export": (_i32, [_vp, _vp, C.POINTER(_vp)]),
     "rmc_comm_connect": (_i32, [_vp, _vp, C.POINTER(_vp)]),

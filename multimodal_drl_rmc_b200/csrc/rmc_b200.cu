@@ -2191,6 +2191,36 @@ extern "C" int32_t rmc_group_create(rmc_group_t** out, rmc_learner_t* const* lea
   return RMC_OK;
 }
 
+// Agent.store_transitions of every member for one env step (dqn/agent.py:70-73), n rows each: ONE launch (block = member).
+// Falls back to one small push per member when the packed rows do not fit the kernel-argument buffer.
+extern "C" int32_t rmc_group_push_host(rmc_group_t* g, const float* const* obs_host, const int64_t* const* act_host, const float* const* rew_host,
+                                       const float* const* done_host, const float* const* next_obs_host, int64_t n, rmc_stream_t s) {
+  if (!g || !obs_host || !act_host || !rew_host || !done_host || !next_obs_host || n < 0) return fail(RMC_ERR_ARG, "rmc_group_push_host: bad args");
+  if (n == 0) return RMC_OK;
+  rmc_replay* r0 = g->replays[0];
+  if (int32_t e = use_device(r0->device)) return e;
+  cudaStream_t st = as_stream(s);
+  const long long per_member = n * r0->rf;
+  bool one_launch = n <= 8 && per_member * g->n <= kGroupRowFloats;
+  for (int i = 0; i < g->n && one_launch; ++i) one_launch = g->replays[i]->rf == r0->rf && n <= g->replays[i]->cap;
+  if (!one_launch) {
+    for (int i = 0; i < g->n; ++i)
+      if (int32_t e = push_impl(g->replays[i], obs_host[i], act_host[i], rew_host[i], done_host[i], next_obs_host[i], n, true, st)) return e;
+    return RMC_OK;
+  }
+  GroupRows rows;
+  for (int i = 0; i < g->n; ++i)
+    pack_rows_host(rows.v + i * per_member, obs_host[i], act_host[i], rew_host[i], done_host[i], next_obs_host[i], n, r0->D, r0->rf);
+  k_push_tiny_group<<<g->n, 32, 0, st>>>(g->ctx_dev, rows, static_cast<int>(n), r0->rf, 1.0f);
+  RMC_KERNEL_OK();
+  for (int i = 0; i < g->n; ++i) {
+    rmc_replay* r = g->replays[i];
+    r->dp = (r->dp + n) % r->cap;
+    r->size = std::min<long long>(r->size + n, r->cap);
+  }
+  return RMC_OK;
+}
+
 extern "C" int32_t rmc_group_destroy(rmc_group_t* g) {
   if (!g) return RMC_OK;
   cudaSetDevice(g->learners[0]->device);

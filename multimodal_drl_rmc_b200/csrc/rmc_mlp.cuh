@@ -1462,6 +1462,19 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(const __grid_const
   RMC_STAMP(C, 7); if (gap != nullptr && threadIdx.x == 0) atomicMax(gap + 1, global_timer_ns());
 }
 
+// ------------------------------------------------------------------ per-env-step push of an ensemble
+// Every member of an ensemble launch stores the n rows its own environments produced (Agent.store_transitions,
+// dqn/agent.py:70-73 -> replay_memory.py:49-57): ONE launch, block b = member b, the rows in the kernel-argument buffer.
+// (One k_push_tiny per member was 8 launches and 8 serialised one-warp kernels in front of every ensemble step.)
+constexpr int kGroupRowFloats = 896;      // 3.5 KB of packed rows per launch, member-major
+struct GroupRows { float v[kGroupRowFloats]; };
+__global__ void __launch_bounds__(32) k_push_tiny_group(const AgentCtx* __restrict__ many, const __grid_constant__ GroupRows rows, int n, int rf, float pmax) {
+  __shared__ float s_f[64];
+  __shared__ int s_i[64];
+  const ReplayDev R = many[blockIdx.x].rp;
+  push_tiny_cta(R, rows.v + static_cast<size_t>(blockIdx.x) * n * rf, n, pmax, s_f, s_i);
+}
+
 // ------------------------------------------------------------------ batched act / Q values
 // mode 0: greedy actions (dueling -> argmax raw adv, plain -> argmax Q; dqn/network.py:67-74,110-117)
 // mode 1: Q values [n][A]

@@ -670,13 +670,10 @@ __global__ void __launch_bounds__(kThreads) k_push_small(ReplayDev R, const floa
 }
 
 // n <= 32 rows (the per-env-step push of the trainer), ONE warp: ring write, leaf <- max_priority with direct
-// ancestor atomics on every level, exact extremes bookkeeping.
-template <bool kArgs>
-__global__ void __launch_bounds__(32) k_push_tiny(ReplayDev R, const float* __restrict__ rows_ptr, TinyRows rows_arg, int n, float pmax) {
-  const float* rows = kArgs ? rows_arg.v : rows_ptr;   // kArgs: the rows travelled inside the launch itself
-  __shared__ float s_f[64];
-  __shared__ int s_i[64];
-  const int lane = threadIdx.x;
+// ancestor atomics on every level, exact extremes bookkeeping.  The body is a device function so that the ensemble's
+// one-launch push (k_push_tiny_group, rmc_mlp.cuh) runs exactly the same code per member.
+__device__ __forceinline__ void push_tiny_cta(const ReplayDev& R, const float* __restrict__ rows, int n, float pmax, float* s_f, int* s_i) {
+  const int lane = threadIdx.x;       // blockDim.x == 32
   const long long dp = R.st->dp, size = R.st->size;
   const long long new_size = min(size + static_cast<long long>(n), R.cap);
   const float M0 = (size > 0) ? R.st->max_p : 0.f, m0 = (size > 0) ? R.st->min_p : finf();
@@ -708,6 +705,12 @@ __global__ void __launch_bounds__(32) k_push_tiny(ReplayDev R, const float* __re
     R.st->dp = (dp + n) % R.cap;
     R.st->size = new_size;
   }
+}
+template <bool kArgs>
+__global__ void __launch_bounds__(32) k_push_tiny(ReplayDev R, const float* __restrict__ rows_ptr, TinyRows rows_arg, int n, float pmax) {
+  __shared__ float s_f[64];
+  __shared__ int s_i[64];
+  push_tiny_cta(R, kArgs ? rows_arg.v : rows_ptr, n, pmax, s_f, s_i);   // kArgs: the rows travelled inside the launch itself
 }
 
 // bulk path pieces

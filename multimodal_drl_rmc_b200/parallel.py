@@ -57,6 +57,21 @@ class AgentEnsemble:
         except Exception:
             pass
 
+    def _deliver_pending(self):
+        """The rows every member's ``store_transitions`` held back for this env step: ONE launch for the whole ensemble
+        (``rmc_group_push_host``) when all members hold the same number of rows, else one small push per member."""
+        rings = [a.replay_memory_buffer._ring for a in self.agents]
+        n = rings[0]._pending
+        if n and all(r._pending == n and r._handle is not None for r in rings):
+            k = len(rings)
+            cols = [(C.c_void_p * k)(*[r._small_ptrs[j] for r in rings]) for j in range(5)]
+            check(lib().rmc_group_push_host(self.handle, *cols, n, stream_ptr(self._dev)))
+            for r in rings:
+                r._pending = 0
+            return
+        for r in rings:
+            r.flush()
+
     def learn(self, fuse_target_update=True, u=None, indices=None):
         """One learner step of every member (dqn/agent.py learn() + update_target_network()).
         ``u`` / ``indices``: optional injected sampling randomness, shape [n_agents, batch]."""
@@ -65,7 +80,8 @@ class AgentEnsemble:
             raise ValueError("AgentEnsemble.learn: members are at different steps (beta and the hard-sync schedule come from one step value)")
         for a in self.agents:
             a._flush_step()                          # a lazily recorded single-agent learn()
-            a.replay_memory_buffer._ring.flush()     # rows held back for a fused store + learn call
+        self._deliver_pending()                      # rows held back by the members' store_transitions of this env step
+        for a in self.agents:
             a._learn_calls += 1
             a._adam_t += 1
         args = self._args

@@ -44,6 +44,41 @@ def test_ensemble_launch_equals_individual_steps(algo, B):
             assert sa.max_priority == sb.max_priority and sa.size == sb.size
 
 
+def test_ensemble_push_of_all_members_in_one_launch_equals_member_pushes():
+    """store_transitions of every member, delivered by AgentEnsemble in ONE launch (rmc_group_push_host, block = member):
+    rings, cursors, trees and extremes bit-identical to the same rows pushed member by member (dqn/agent.py:70-73,
+    dqn/replay_memory.py:49-57: new rows enter with the max priority), also across the ring's wrap-around."""
+    from multimodal_drl_rmc_b200.parallel import AgentEnsemble
+    n, B, cap = 3, 32, 600
+    solo = [PU.make_pair("PerDuelingDoubleDQNAgent", 14, B, cap, cap - 2, seed=80 + k)[1] for k in range(n)]
+    team = [PU.make_pair("PerDuelingDoubleDQNAgent", 14, B, cap, cap - 2, seed=80 + k)[1] for k in range(n)]
+    ens = AgentEnsemble(team)
+    rng = np.random.default_rng(9)
+    for it in range(5):                      # 5 env steps of 1 row each: the cursor wraps after the second
+        for k in range(n):
+            o, o2 = rng.random((1, 14), dtype=np.float32), rng.random((1, 14), dtype=np.float32)
+            a, r, d = [int(rng.integers(0, 8))], [float(rng.random())], [bool(rng.integers(0, 2))]
+            for ag in (solo[k], team[k]):
+                ag.store_transitions(o, a, r, d, o2, None)
+        for ag in solo:
+            ag.replay_memory_buffer._ring.flush()
+        ens._deliver_pending()
+        for a, b in zip(solo, team):
+            ra, rb = a.replay_memory_buffer._ring, b.replay_memory_buffer._ring
+            sa, sb = ra.stats(), rb.stats()
+            assert (sa.size, sa.data_pointer, sa.total_priority, sa.max_priority, sa.min_priority) == \
+                   (sb.size, sb.data_pointer, sb.total_priority, sb.max_priority, sb.min_priority)
+            np.testing.assert_array_equal(a.replay_memory_buffer.replay_buffer.tree, b.replay_memory_buffer.replay_buffer.tree)
+            np.testing.assert_array_equal(ra.read_rows(0, cap), rb.read_rows(0, cap))
+    # and inside the normal flow: store, then one ensemble step (the rows are delivered by learn())
+    for k in range(n):
+        team[k].store_transitions(rng.random((1, 14), dtype=np.float32), [1], [0.5], [False], rng.random((1, 14), dtype=np.float32), None)
+        team[k].step = 3
+    ens.learn()
+    assert all(t.replay_memory_buffer._ring._pending == 0 for t in team)
+    assert all(np.isfinite(t.last_loss()) for t in team)
+
+
 def test_ensemble_launch_matches_oracle_per_agent():
     """The one-launch ensemble step against the ORACLE, member by member (not only against the single-agent CUDA path):
     indices and trees bit-exact, Q / loss / gradients / weights at 1e-5 (dqn/agent.py:245-272 per agent)."""
