@@ -960,39 +960,74 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(const __grid_const
     if ((S.phases & 1) && !one_tile) {
       // several tiles per CTA (ensembles, large batches without the grid-wide sampler): all 8 warps draw this CTA's
       // samples, 8 descents in flight instead of 4; rows go straight to the L2-resident scratch
-      if (tree_sampling && tid == 0)
-        sTop[kTopNodes] = is_weight_max(static_cast<double>(size), total, static_cast<double>(min_p_f), S.beta);
-      __syncthreads();
+      // (the max importance weight -- replay_memory.py:76-77 -- is evaluated per warp by a third lane of the SAME float64 pow
+      //  call that serves the warp's two samples: no pow and no CTA barrier in front of the descents)
       // this CTA samples the rows it will process: 16- / 8-row tiles (rmc_rows_ws.cuh) or 4-row tiles
       const int wrs = use_ws ? ws_rows(B, S.n_row_ctas) : kTM;
       const long long n_wide = (B + wrs - 1) / wrs;
       const long long my_wide = (cta < n_wide) ? (n_wide - cta + S.n_row_ctas - 1) / S.n_row_ctas : 0;
-      for (long long s = warp; s < my_wide * wrs; s += kWarps) {
-        const long long i = (cta + (s / wrs) * S.n_row_ctas) * wrs + (s % wrs);
-        if (i >= B) continue;
-        long long slot = 0, node = 0;
-        double p = 0.0, numer = 1.0;
+      // a warp takes its samples two at a time: both descents share every memory round trip (per_descend_cached2), both rows
+      // are requested together and the two float64 pows of the importance weights overlap
+      for (long long s = warp; s < my_wide * wrs; s += 2 * kWarps) {
+        const long long sb = s + kWarps;
+        const long long ia = (cta + (s / wrs) * S.n_row_ctas) * wrs + (s % wrs);
+        const long long ib = (cta + (sb / wrs) * S.n_row_ctas) * wrs + (sb % wrs);
+        const bool has_a = ia < B, has_b = sb < my_wide * wrs && ib < B;
+        if (!has_a && !has_b) continue;
+        long long slot_a = 0, node_a = 0, slot_b = 0, node_b = 0;
+        double p_a = 0.0, p_b = 0.0, num_a = 1.0, num_b = 1.0;
         if (tree_sampling) {
-          const long long gi = S.shard_off + i;
-          const double ui = (S.u != nullptr) ? S.u[agent * B + i] : philox_uniform(S.seed, S.counter, agent, static_cast<uint32_t>(gi));
-          node = per_descend_cached(sTop, n_top, C.rp.tree, n_nodes, stratum_value(total, S.Bglobal, gi, ui), &p);
-          slot = node - first_leaf;
+          const long long ga = S.shard_off + ia, gb = S.shard_off + ib;
+          const double ua = !has_a ? 0.0 : (S.u != nullptr) ? S.u[agent * B + ia] : philox_uniform(S.seed, S.counter, agent, static_cast<uint32_t>(ga));
+          const double ub = !has_b ? 0.0 : (S.u != nullptr) ? S.u[agent * B + ib] : philox_uniform(S.seed, S.counter, agent, static_cast<uint32_t>(gb));
+          // (a missing first sample can only be the ragged end of the batch, where the second is missing as well)
+          per_descend_cached2(sTop, n_top, C.rp.tree, n_nodes, stratum_value(total, S.Bglobal, ga, ua), stratum_value(total, S.Bglobal, gb, ub),
+                              has_b, &node_a, &p_a, &node_b, &p_b);
+          slot_a = node_a - first_leaf;
+          slot_b = node_b - first_leaf;
         } else {
-          const long long pos = (S.idx != nullptr) ? S.idx[agent * B + i]
-                                                   : static_cast<long long>(feistel_perm(S.shard_off + i, size, S.seed, S.counter, agent));
-          slot = deque_pos_to_slot(pos, size, dp, C.rp.cap);
-          node = slot;
+          const long long pos_a = (S.idx != nullptr) ? S.idx[agent * B + ia]
+                                                     : static_cast<long long>(feistel_perm(S.shard_off + ia, size, S.seed, S.counter, agent));
+          slot_a = deque_pos_to_slot(pos_a, size, dp, C.rp.cap);
+          node_a = slot_a;
+          if (has_b) {
+            const long long pos_b = (S.idx != nullptr) ? S.idx[agent * B + ib]
+                                                       : static_cast<long long>(feistel_perm(S.shard_off + ib, size, S.seed, S.counter, agent));
+            slot_b = deque_pos_to_slot(pos_b, size, dp, C.rp.cap);
+            node_b = slot_b;
+          }
         }
-        const RowRegs rr = gather_row_load(C.rp, slot);            // row loads in flight during the pow
-        if (tree_sampling) numer = pow(static_cast<double>(size) * (p / total), -S.beta);
-        float* dst = C.X + i * rf;
+        const RowRegs ra = gather_row_load(C.rp, slot_a);          // row loads in flight during the pows
+        const RowRegs rb = gather_row_load(C.rp, has_b ? slot_b : slot_a);
+        double w_max = 1.0;
+        if (tree_sampling) {      // ONE pow call per warp: lane 0 -> sample a, lane 1 -> sample b, lane 2 -> the max weight (min priority)
+          const double pr = (lane == 0) ? p_a : (lane == 1) ? (has_b ? p_b : p_a) : static_cast<double>(min_p_f);
+          const double y = pow(static_cast<double>(size) * (pr / total), -S.beta);
+          num_a = __shfl_sync(0xffffffffu, y, 0);
+          num_b = __shfl_sync(0xffffffffu, y, 1);
+          w_max = __shfl_sync(0xffffffffu, y, 2);
+        }
+        {
+          float* dst = C.X + ia * rf;
 #pragma unroll
-        for (int q = 0; q < 3; ++q)
-          if (lane + 32 * q < rf) dst[lane + 32 * q] = rr.v[q];
-        if (lane == 0) {
-          C.nodes[i] = node;
-          C.is_w[i] = tree_sampling ? static_cast<float>(numer / sTop[kTopNodes]) : 1.f;
-          C.leaf_p[i] = p;
+          for (int q = 0; q < 3; ++q)
+            if (lane + 32 * q < rf) dst[lane + 32 * q] = ra.v[q];
+          if (lane == 0) {
+            C.nodes[ia] = node_a;
+            C.is_w[ia] = tree_sampling ? static_cast<float>(num_a / w_max) : 1.f;
+            C.leaf_p[ia] = p_a;
+          }
+        }
+        if (has_b) {
+          float* dst = C.X + ib * rf;
+#pragma unroll
+          for (int q = 0; q < 3; ++q)
+            if (lane + 32 * q < rf) dst[lane + 32 * q] = rb.v[q];
+          if (lane == 0) {
+            C.nodes[ib] = node_b;
+            C.is_w[ib] = tree_sampling ? static_cast<float>(num_b / w_max) : 1.f;
+            C.leaf_p[ib] = p_b;
+          }
         }
       }
     } else if (S.phases & 1) {

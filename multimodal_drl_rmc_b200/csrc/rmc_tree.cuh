@@ -62,6 +62,63 @@ __device__ __forceinline__ long long per_descend_from(const double* __restrict__
   *leaf_val = pv;
   return p;
 }
+// TWO descents per warp sharing every memory round trip (the multi-tile launches give a warp two samples: their descents are
+// independent, so both samples' 126-node look-ahead windows are requested together).  Per sample exactly the walk above.
+__device__ __forceinline__ void per_descend_load(const double* __restrict__ tree, long long n_nodes, long long p, double (&val)[4]) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int pos = lane + 32 * q;
+    val[q] = 0.0;
+    if (pos < 126) {
+      const int d = 31 - __clz(pos + 2);
+      const long long idx = ((p + 1) << d) - 1 + (pos + 2 - (1 << d));
+      if (idx < n_nodes) val[q] = __ldcg(tree + idx);
+    }
+  }
+}
+__device__ __forceinline__ bool per_descend_walk6(const double (&val)[4], long long n_nodes, long long& p, double& v, double& pv) {
+  long long cur = p;
+  int oc = 0;
+  bool leaf = false;
+#pragma unroll
+  for (int dd = 1; dd <= 6; ++dd) {
+    const long long left = 2 * cur + 1;
+    if (left >= n_nodes) { leaf = true; break; }
+    const int lpos = (1 << dd) - 2 + 2 * oc;
+    const double lv = lookahead_pick(val, lpos);
+    if (v <= lv) { cur = left; oc = 2 * oc; pv = lv; }
+    else { v = v - lv; cur = left + 1; oc = 2 * oc + 1; pv = lookahead_pick(val, lpos + 1); }
+  }
+  p = cur;
+  return leaf;
+}
+__device__ __forceinline__ void per_descend_cached2(const double* __restrict__ s_top, int n_top, const double* __restrict__ tree, long long n_nodes,
+                                                    double va, double vb, bool has_b, long long* node_a, double* leaf_a, long long* node_b,
+                                                    double* leaf_b) {
+  long long pa = 0, pb = 0;
+  double pva = s_top[0], pvb = s_top[0];
+  while (2 * pa + 2 < n_top) {
+    const double lv = s_top[2 * pa + 1];
+    if (va <= lv) { pa = 2 * pa + 1; pva = lv; }
+    else { va = va - lv; pa = 2 * pa + 2; pva = s_top[pa]; }
+  }
+  while (has_b && 2 * pb + 2 < n_top) {
+    const double lv = s_top[2 * pb + 1];
+    if (vb <= lv) { pb = 2 * pb + 1; pvb = lv; }
+    else { vb = vb - lv; pb = 2 * pb + 2; pvb = s_top[pb]; }
+  }
+  bool done_a = !(2 * pa + 1 < n_nodes), done_b = !has_b || !(2 * pb + 1 < n_nodes);
+  while (!(done_a && done_b)) {
+    double xa[4], xb[4];
+    if (!done_a) per_descend_load(tree, n_nodes, pa, xa);
+    if (!done_b) per_descend_load(tree, n_nodes, pb, xb);
+    if (!done_a) { const bool leaf = per_descend_walk6(xa, n_nodes, pa, va, pva); done_a = leaf || !(2 * pa + 1 < n_nodes); }
+    if (!done_b) { const bool leaf = per_descend_walk6(xb, n_nodes, pb, vb, pvb); done_b = leaf || !(2 * pb + 1 < n_nodes); }
+  }
+  *node_a = pa; *leaf_a = pva;
+  *node_b = pb; *leaf_b = pvb;
+}
 __device__ __forceinline__ long long per_descend_warp(const double* __restrict__ tree, long long n_nodes, double v,
                                                       double* leaf_val) {
   return per_descend_from(tree, n_nodes, 0, __ldcg(tree), v, leaf_val);

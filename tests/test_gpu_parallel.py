@@ -79,12 +79,15 @@ def test_ensemble_push_of_all_members_in_one_launch_equals_member_pushes():
     assert all(np.isfinite(t.last_loss()) for t in team)
 
 
-def test_ensemble_launch_matches_oracle_per_agent():
+@pytest.mark.parametrize("B,cap", [(64, 1500), (250, 3001)])
+def test_ensemble_launch_matches_oracle_per_agent(B, cap):
     """The one-launch ensemble step against the ORACLE, member by member (not only against the single-agent CUDA path):
-    indices and trees bit-exact, Q / loss / gradients / weights at 1e-5 (dqn/agent.py:245-272 per agent)."""
+    indices and trees bit-exact, Q / loss / gradients / weights at 1e-5 (dqn/agent.py:245-272 per agent).  B = 250 with three
+    members: 49 CTAs per agent own 63 four-row tiles (ragged last one) -- several tiles per CTA, the in-kernel sampler with two
+    descents per warp (per_descend_cached2) on a tree whose leaves lie on two depths."""
     from multimodal_drl_rmc_b200 import _lib
     from multimodal_drl_rmc_b200.parallel import AgentEnsemble
-    n, B, cap = 3, 64, 1500
+    n = 3
     pairs = [PU.make_pair("PerDuelingDoubleDQNAgent", 14, B, cap, cap, seed=60 + k) for k in range(n)]
     ens = AgentEnsemble([p[1] for p in pairs])
     rng = np.random.default_rng(4)
