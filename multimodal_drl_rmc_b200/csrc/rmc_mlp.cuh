@@ -1390,19 +1390,22 @@ __global__ void __launch_bounds__(kThreads, 1) k_learner_step(const __grid_const
       const int total = kH2 / 16 + (kH1 / 16) * (kH2 / 16) + stream_w0_count(L), slots = sp.n_idle + 2 * nt;
       const int extra = max(0, total - slots);
       if (cta == nt && (S.phases & 2)) stream_publish_loss(C, S, nt, smem);      // first target CTA: its unit's operands are still 2 us away
-      // More units than CTAs: the CTAs that are idle in phase A (free from the start, 2 us before anybody else) take TWO
-      // neighbouring W2 units as one 16 x 32 unit (kt = idle index / 4, columns 32 * (idle index % 4)), which removes exactly
-      // 2 * n_idle units from the list; when what is left fits the other CTAs one to one nobody runs two units back to back
-      // (at B = 256: 12 idle CTAs cover kt 0..2, the other 128 units land on the 64 target and 64 row CTAs in the order
-      // heads, W2, W0).  Before, the idle CTAs ran two 16 x 16 units in sequence and ended the launch 2.3 us after the row CTAs.
+      // More units than CTAs (152 units on 140 CTAs at every default batch): `nw` = extra rounded up to a multiple of four of
+      // the CTAs that are idle in phase A (free from the start, 2 us before anybody else) take TWO neighbouring W2 units as one
+      // 16 x 32 unit (kt = index / 4, columns 32 * (index % 4)); that removes 2 * nw units from the list, and what is left fits
+      // the other CTAs one to one in the order they become free -- remaining idle CTAs, target CTAs, row CTAs -- and the order
+      // the operands come into existence -- heads, W2, W0.  Nobody runs two units back to back (before, `extra` idle CTAs ran
+      // two 16 x 16 units in sequence and ended the launch 2.3 us after the row CTAs).
       constexpr int nH = kH2 / 16, nJT = kH2 / 16;
-      const bool wide_ok = extra > 0 && (sp.n_idle % (nJT / 2)) == 0 && 2 * sp.n_idle <= (kH1 / 16) * nJT && total - 2 * sp.n_idle <= 2 * nt;
+      const int nw = (extra + nJT / 2 - 1) / (nJT / 2) * (nJT / 2);
+      const bool wide_ok = extra > 0 && nw <= sp.n_idle && 2 * nw <= (kH1 / 16) * nJT;
       if (wide_ok) {
-        if (s_idx >= 0) {
+        if (s_idx >= 0 && s_idx < nw) {
           stream_run_w2_wide(C, S, s_idx / (nJT / 2), 2 * (s_idx % (nJT / 2)), smem);
         } else {
-          const int j = (cta >= nt) ? cta - nt : nt + cta;          // target CTAs first (free first), then row CTAs
-          const int id = (j < nH) ? j : j + 2 * sp.n_idle;           // the list without the W2 units of the idle CTAs
+          const int rest_idle = sp.n_idle - nw;
+          const int j = (s_idx >= 0) ? s_idx - nw : (cta >= nt) ? rest_idle + (cta - nt) : rest_idle + nt + cta;
+          const int id = (j < nH) ? j : j + 2 * nw;                  // the list without the W2 units of the wide CTAs
           if (id < total) stream_run_any(C, S, id, smem);
         }
       } else {
